@@ -1,0 +1,496 @@
+// Per-frame SMPL-H sub-model -> sensor frames -> residual, forward and hand-derived reverse pass.
+//
+// This is the arithmetic the reference obtains from (i) the third-party BodyModel call at
+// empose/bodymodels/smpl.py:121, (ii) VirtualMarkerHelper.get_virtual_pos_and_rot
+// (empose/data/virtual_sensors.py:85-96, empose/helpers/utils.py:126-146), (iii) the offset
+// application at empose/nn/models.py:478-479, (iv) reconstruction_loss (empose/nn/loss.py:23-41)
+// and (v) torch.autograd's backward through all of it (empose/nn/models.py:576-579), restricted to
+// the minimal sub-model prepared by submodel.py (22 joints, ~84 vertices, 12 sensors).
+//
+// The code is written as PHASES over a per-frame scratch state: each phase is a loop
+// `for (i = lane; i < n; i += lanes)` with no intra-phase dependencies, so a group of `lanes`
+// GPU threads runs a phase cooperatively and synchronises between phases, while the CPU test
+// harness (tests/host_harness.cpp) runs the very same functions with lanes = 1.  Templated on the
+// scalar type so the derivation can be checked in double on the host.
+//
+// The pose-blend contraction (189 features x vertex coordinates) is NOT done here: it is a dense
+// GEMM over frames and runs on the tensor cores (pose_blend jobs in plan.cu); this file consumes
+// its result (`vp_off`) and produces its reverse-mode input (`dvp`).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define EMPOSE_HD __host__ __device__ __forceinline__
+#else
+#define EMPOSE_HD inline
+#endif
+
+namespace empose {
+
+constexpr int kJoints = 22;           // root + 21 body joints (reference configuration.py:104)
+constexpr int kPoseDim = 66;
+constexpr int kBetas = 10;            // reference configuration.py:107
+constexpr int kSensors = 12;          // reference configuration.py:32-34
+constexpr int kPoseFeat = 189;        // 21 joints x 9 rotation entries
+constexpr int kPoseFeatPad = 192;     // K of the pose-blend GEMM (multiple of 32 floats = one 128B swizzle row)
+constexpr int kMaxVp = 384;           // padded 3*Vs, supports sub-meshes of up to 128 vertices
+constexpr int kMaxDegree = 12;
+
+// Packed sub-model constants (pointers into device or host memory).  Layouts: see submodel.py.
+struct SubModel {
+    int n_verts, vp_dim, n_faces, max_degree, n_skin;
+    const float* v_template;   // [vp_dim]
+    const float* shapedirs;    // [10][vp_dim]
+    const float* j0;           // [66]
+    const float* jdirs;        // [10][66]
+    const float* skin_weight;  // [n_verts][n_skin]
+    const int* skin_joint;     // [n_verts][n_skin]
+    const int* jt_ptr;         // [23]   joint -> range in jt_vert / jt_weight
+    const int* jt_vert;
+    const float* jt_weight;
+    const int* parents;        // [22]
+    const int* faces;          // [n_faces][3] local vertex ids
+    const int* sensor_vert;    // [12]
+    const int* helper_vert;    // [12]
+    const int* sensor_faces;   // [12][max_degree] rows of faces, -1 padded
+    const int* sensor_degree;  // [12]
+};
+
+// What the residual compares against and how it is weighted.
+struct ResidualSpec {
+    int use_pos, use_ori;      // reference flags use_marker_pos / use_marker_ori
+    int sensor_active[kSensors];  // 1 if the sensor is in marker_idxs (models.py:386)
+};
+
+template <typename T>
+struct FrameState {
+    T theta[kPoseDim];
+    T beta[kBetas];
+    T rot[kJoints][9];        // R_j = exp(theta_j)
+    T jrest[kJoints][3];      // J(beta)
+    T grot[kJoints][9];       // world rotation G_j^R  (== A_j^R)
+    T gpos[kJoints][3];       // world position G_j^t  (posed joint)
+    T atr[kJoints][3];        // A_j^t = G_j^t - G_j^R J_j
+    T vp[kMaxVp];             // v_template + S beta + pose blend
+    T x[kMaxVp];              // skinned vertices
+    T dx[kMaxVp];             // dE/dx, then reused for dE/dvp
+    T dar[kJoints][9];        // dE/dA^R
+    T dat[kJoints][3];        // dE/dA^t
+    T part_rot[3][kJoints][9];   // row-wise partial sums of dE/dR_j from the chain
+    T part_j[3][kJoints][3];     // row-wise partial sums of dE/dJ_j
+    T dgr[kJoints][9];        // dE/dG^R (scratch of the reverse chain)
+    T dgt[kJoints][3];
+    T drot[kJoints][9];       // dE/dR_j  (chain part; the pose-blend part is added by the caller)
+    T dj[kJoints][3];
+    T dbeta_part[32][kBetas];
+    T sensor_pos[kSensors][3];   // p'_m (offsets applied)
+    T sensor_ori[kSensors][9];   // R'_m row-major
+};
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+EMPOSE_HD void sincos_t(float a, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+    sincosf(a, s, c);
+#else
+    *s = sinf(a); *c = cosf(a);
+#endif
+}
+EMPOSE_HD void sincos_t(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
+EMPOSE_HD float sqrt_t(float a) { return sqrtf(a); }
+EMPOSE_HD double sqrt_t(double a) { return sqrt(a); }
+
+template <typename T> EMPOSE_HD void cross3(const T* a, const T* b, T* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+template <typename T> EMPOSE_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// y = x / |x|; returns |x|
+template <typename T> EMPOSE_HD T normalize3(const T* x, T* y) {
+    T len = sqrt_t(dot3(x, x));
+    T inv = T(1) / len;
+    y[0] = x[0] * inv; y[1] = x[1] * inv; y[2] = x[2] * inv;
+    return len;
+}
+// reverse of y = x/|x| given unit y, len = |x| and dy:  dx = (dy - y (y.dy)) / len
+template <typename T> EMPOSE_HD void normalize3_bwd(const T* y, T len, const T* dy, T* dx) {
+    T proj = dot3(y, dy);
+    T inv = T(1) / len;
+    dx[0] = (dy[0] - y[0] * proj) * inv;
+    dx[1] = (dy[1] - y[1] * proj) * inv;
+    dx[2] = (dy[2] - y[2] * proj) * inv;
+}
+
+// Rodrigues with the third-party convention angle = ||r + 1e-8|| (axis = r / angle), row-major R.
+template <typename T> EMPOSE_HD void rodrigues_fwd(const T* r, T* R) {
+    const T e = T(1e-8);
+    T r0 = r[0] + e, r1 = r[1] + e, r2 = r[2] + e;
+    T a = sqrt_t(r0 * r0 + r1 * r1 + r2 * r2);
+    T inv = T(1) / a;
+    T kx = r[0] * inv, ky = r[1] * inv, kz = r[2] * inv;
+    T s, c;
+    sincos_t(a, &s, &c);
+    T v = T(1) - c;
+    // K = [[0,-kz,ky],[kz,0,-kx],[-ky,kx,0]];  K^2 = k k^T - |k|^2 I
+    T kk = kx * kx + ky * ky + kz * kz;
+    R[0] = T(1) + v * (kx * kx - kk);  R[1] = -s * kz + v * kx * ky;       R[2] = s * ky + v * kx * kz;
+    R[3] = s * kz + v * kx * ky;       R[4] = T(1) + v * (ky * ky - kk);  R[5] = -s * kx + v * ky * kz;
+    R[6] = -s * ky + v * kx * kz;      R[7] = s * kx + v * ky * kz;       R[8] = T(1) + v * (kz * kz - kk);
+}
+
+// dr += J^T dR for the map above.
+template <typename T> EMPOSE_HD void rodrigues_bwd(const T* r, const T* dR, T* dr) {
+    const T e = T(1e-8);
+    T rp[3] = {r[0] + e, r[1] + e, r[2] + e};
+    T a = sqrt_t(dot3(rp, rp));
+    T inv = T(1) / a;
+    T k[3] = {r[0] * inv, r[1] * inv, r[2] * inv};
+    T s, c;
+    sincos_t(a, &s, &c);
+    T v = T(1) - c;
+    T K[9] = {T(0), -k[2], k[1], k[2], T(0), -k[0], -k[1], k[0], T(0)};
+    // K2 = K K
+    T K2[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) K2[i * 3 + j] = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
+    T dot_k = T(0), dot_k2 = T(0);
+    for (int i = 0; i < 9; ++i) { dot_k += dR[i] * K[i]; dot_k2 += dR[i] * K2[i]; }
+    T da = c * dot_k + s * dot_k2;
+    // dK = s dR + v (dR K^T + K^T dR)
+    T dK[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            T t1 = dR[i * 3] * K[j * 3] + dR[i * 3 + 1] * K[j * 3 + 1] + dR[i * 3 + 2] * K[j * 3 + 2];   // (dR K^T)_ij
+            T t2 = K[i] * dR[j] + K[3 + i] * dR[3 + j] + K[6 + i] * dR[6 + j];                            // (K^T dR)_ij
+            dK[i * 3 + j] = s * dR[i * 3 + j] + v * (t1 + t2);
+        }
+    T dk[3] = {dK[7] - dK[5], dK[2] - dK[6], dK[3] - dK[1]};
+    T kr = dk[0] * r[0] + dk[1] * r[1] + dk[2] * r[2];
+    T inv3 = inv * inv * inv;
+    for (int l = 0; l < 3; ++l) dr[l] += dk[l] * inv - kr * rp[l] * inv3 + da * rp[l] * inv;
+}
+
+// ----------------------------------------------------------------------------------------------
+// forward phases
+// ----------------------------------------------------------------------------------------------
+
+// F1: rotations, rest joints, blended rest vertices.  vp_off may be null (treated as zero).
+template <typename T, typename TIn>
+EMPOSE_HD void phase_setup(const SubModel& m, FrameState<T>& st, const TIn* vp_off, int lane, int lanes) {
+    for (int j = lane; j < kJoints; j += lanes) rodrigues_fwd(&st.theta[j * 3], st.rot[j]);
+    for (int i = lane; i < kPoseDim; i += lanes) {
+        T acc = T(m.j0[i]);
+        for (int k = 0; k < kBetas; ++k) acc += T(m.jdirs[k * kPoseDim + i]) * st.beta[k];
+        st.jrest[i / 3][i % 3] = acc;
+    }
+    const int nv3 = m.n_verts * 3;
+    for (int i = lane; i < nv3; i += lanes) {
+        T acc = T(m.v_template[i]);
+        for (int k = 0; k < kBetas; ++k) acc += T(m.shapedirs[k * m.vp_dim + i]) * st.beta[k];
+        if (vp_off) acc += T(vp_off[i]);
+        st.vp[i] = acc;
+    }
+}
+
+// F2: kinematic chain.  Row r of every world rotation depends only on row r of its ancestors, so
+// three lanes walk the whole tree independently (no synchronisation inside the chain).
+template <typename T>
+EMPOSE_HD void phase_chain(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+    for (int r = lane; r < 3; r += lanes) {
+        for (int c = 0; c < 3; ++c) st.grot[0][r * 3 + c] = st.rot[0][r * 3 + c];
+        st.gpos[0][r] = st.jrest[0][r];
+        for (int j = 1; j < kJoints; ++j) {
+            const int p = m.parents[j];
+            const T g0 = st.grot[p][r * 3], g1 = st.grot[p][r * 3 + 1], g2 = st.grot[p][r * 3 + 2];
+            const T* R = st.rot[j];
+            st.grot[j][r * 3 + 0] = g0 * R[0] + g1 * R[3] + g2 * R[6];
+            st.grot[j][r * 3 + 1] = g0 * R[1] + g1 * R[4] + g2 * R[7];
+            st.grot[j][r * 3 + 2] = g0 * R[2] + g1 * R[5] + g2 * R[8];
+            st.gpos[j][r] = g0 * (st.jrest[j][0] - st.jrest[p][0]) + g1 * (st.jrest[j][1] - st.jrest[p][1]) +
+                            g2 * (st.jrest[j][2] - st.jrest[p][2]) + st.gpos[p][r];
+        }
+        for (int j = 0; j < kJoints; ++j)
+            st.atr[j][r] = st.gpos[j][r] - (st.grot[j][r * 3] * st.jrest[j][0] + st.grot[j][r * 3 + 1] * st.jrest[j][1] +
+                                            st.grot[j][r * 3 + 2] * st.jrest[j][2]);
+    }
+}
+
+// F3: linear blend skinning of the sub-mesh; also clears dx for the reverse pass.
+template <typename T>
+EMPOSE_HD void phase_skin(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+    for (int v = lane; v < m.n_verts; v += lanes) {
+        const T p0 = st.vp[v * 3], p1 = st.vp[v * 3 + 1], p2 = st.vp[v * 3 + 2];
+        T x0 = T(0), x1 = T(0), x2 = T(0);
+        for (int s = 0; s < m.n_skin; ++s) {
+            const T w = T(m.skin_weight[v * m.n_skin + s]);
+            const int j = m.skin_joint[v * m.n_skin + s];
+            const T* A = st.grot[j];
+            x0 += w * (A[0] * p0 + A[1] * p1 + A[2] * p2 + st.atr[j][0]);
+            x1 += w * (A[3] * p0 + A[4] * p1 + A[5] * p2 + st.atr[j][1]);
+            x2 += w * (A[6] * p0 + A[7] * p1 + A[8] * p2 + st.atr[j][2]);
+        }
+        st.x[v * 3] = x0; st.x[v * 3 + 1] = x1; st.x[v * 3 + 2] = x2;
+        st.dx[v * 3] = T(0); st.dx[v * 3 + 1] = T(0); st.dx[v * 3 + 2] = T(0);
+    }
+}
+
+#if defined(__CUDA_ARCH__)
+template <typename T> __device__ __forceinline__ void scatter_add(T* addr, T val) { atomicAdd(addr, val); }
+#else
+template <typename T> inline void scatter_add(T* addr, T val) { *addr += val; }
+#endif
+
+// F4 (+ its reverse): one lane per sensor builds the frame [on_surface | third | normal]
+// (virtual_sensors.py:16-38), applies the offsets (models.py:478-479) and, if `want_grad`, forms the
+// residual direction (loss.py:27-28) and pushes it back to the vertices it touched (st.dx).
+//   meas_pos: [12][3] measured positions, meas_ori: [12][9] measured orientations (row-major),
+//   off_r: [12][9], off_t: [12][3].
+template <typename T, typename TIn>
+EMPOSE_HD void phase_sensors(const SubModel& m, FrameState<T>& st, const TIn* off_r, const TIn* off_t,
+                             const TIn* meas_pos, const TIn* meas_ori, const ResidualSpec& spec, bool want_grad,
+                             int lane, int lanes) {
+    for (int s = lane; s < kSensors; s += lanes) {
+        const int vs = m.sensor_vert[s], vh = m.helper_vert[s];
+        const int deg = m.sensor_degree[s];
+        const T* xs = &st.x[vs * 3];
+        // area-weighted normal: mean of un-normalised incident face normals (utils.py:134-140)
+        T n[3] = {T(0), T(0), T(0)};
+        for (int d = 0; d < deg; ++d) {
+            const int* f = &m.faces[m.sensor_faces[s * m.max_degree + d] * 3];
+            const T* a = &st.x[f[0] * 3];
+            const T* b = &st.x[f[1] * 3];
+            const T* c = &st.x[f[2] * 3];
+            T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+            T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+            T fn[3];
+            cross3(e1, e2, fn);
+            n[0] += fn[0]; n[1] += fn[1]; n[2] += fn[2];
+        }
+        const T inv_deg = T(1) / T(deg);
+        n[0] *= inv_deg; n[1] *= inv_deg; n[2] *= inv_deg;
+        T nh[3], u[3], s0[3], t[3], th[3], sv[3], sh[3];
+        const T n_len = normalize3(n, nh);
+        u[0] = st.x[vh * 3] - xs[0]; u[1] = st.x[vh * 3 + 1] - xs[1]; u[2] = st.x[vh * 3 + 2] - xs[2];
+        const T u_len = normalize3(u, s0);
+        cross3(nh, s0, t);
+        const T t_len = normalize3(t, th);
+        cross3(th, nh, sv);
+        const T s_len = normalize3(sv, sh);
+        // R = [sh | th | nh] as columns, row-major storage
+        T R[9] = {sh[0], th[0], nh[0], sh[1], th[1], nh[1], sh[2], th[2], nh[2]};
+        const TIn* Ro = off_r + s * 9;
+        const TIn* to = off_t + s * 3;
+        T Rc[9], pc[3];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j)
+                Rc[i * 3 + j] = R[i * 3] * T(Ro[j]) + R[i * 3 + 1] * T(Ro[3 + j]) + R[i * 3 + 2] * T(Ro[6 + j]);
+            pc[i] = xs[i] + R[i * 3] * T(to[0]) + R[i * 3 + 1] * T(to[1]) + R[i * 3 + 2] * T(to[2]);
+        }
+        for (int i = 0; i < 9; ++i) st.sensor_ori[s][i] = Rc[i];
+        for (int i = 0; i < 3; ++i) st.sensor_pos[s][i] = pc[i];
+        if (!want_grad || !spec.sensor_active[s]) continue;
+
+        // ---- reverse ----
+        T dpc[3] = {T(0), T(0), T(0)}, dRc[9];
+        for (int i = 0; i < 9; ++i) dRc[i] = T(0);
+        if (spec.use_pos) {
+            T d[3] = {pc[0] - T(meas_pos[s * 3]), pc[1] - T(meas_pos[s * 3 + 1]), pc[2] - T(meas_pos[s * 3 + 2])};
+            T len = sqrt_t(dot3(d, d));
+            T inv = len > T(0) ? T(1) / len : T(0);   // reference: NaN at exactly zero residual (sqrt backward); we emit 0
+            dpc[0] = d[0] * inv; dpc[1] = d[1] * inv; dpc[2] = d[2] * inv;
+        }
+        if (spec.use_ori) {
+            T d[9], sq = T(0);
+            for (int i = 0; i < 9; ++i) { d[i] = Rc[i] - T(meas_ori[s * 9 + i]); sq += d[i] * d[i]; }
+            T len = sqrt_t(sq);
+            T inv = len > T(0) ? T(1) / len : T(0);
+            for (int i = 0; i < 9; ++i) dRc[i] = d[i] * inv;
+        }
+        // offsets: Rc = R Ro, pc = xs + R to
+        T dR[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                dR[i * 3 + j] = dRc[i * 3] * T(Ro[j * 3]) + dRc[i * 3 + 1] * T(Ro[j * 3 + 1]) + dRc[i * 3 + 2] * T(Ro[j * 3 + 2]) +
+                                dpc[i] * T(to[j]);
+        T dsh[3] = {dR[0], dR[3], dR[6]}, dth[3] = {dR[1], dR[4], dR[7]}, dnh[3] = {dR[2], dR[5], dR[8]};
+        // sh = sv/|sv|, sv = th x nh
+        T dsv[3], tmp[3];
+        normalize3_bwd(sh, s_len, dsh, dsv);
+        cross3(nh, dsv, tmp); dth[0] += tmp[0]; dth[1] += tmp[1]; dth[2] += tmp[2];      // d th += nh x dsv
+        cross3(dsv, th, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];      // d nh += dsv x th
+        // th = t/|t|, t = nh x s0
+        T dt[3], ds0[3];
+        normalize3_bwd(th, t_len, dth, dt);
+        cross3(s0, dt, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];       // d nh += s0 x dt
+        cross3(dt, nh, ds0);                                                             // d s0  = dt x nh
+        // s0 = u/|u|
+        T du[3];
+        normalize3_bwd(s0, u_len, ds0, du);
+        // nh = n/|n|, n = mean of face normals
+        T dn[3];
+        normalize3_bwd(nh, n_len, dnh, dn);
+        dn[0] *= inv_deg; dn[1] *= inv_deg; dn[2] *= inv_deg;
+        for (int i = 0; i < 3; ++i) {
+            scatter_add(&st.dx[vh * 3 + i], du[i]);
+            scatter_add(&st.dx[vs * 3 + i], dpc[i] - du[i]);
+        }
+        for (int d = 0; d < deg; ++d) {
+            const int* f = &m.faces[m.sensor_faces[s * m.max_degree + d] * 3];
+            const T* a = &st.x[f[0] * 3];
+            const T* b = &st.x[f[1] * 3];
+            const T* c = &st.x[f[2] * 3];
+            T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+            T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+            T de1[3], de2[3];
+            cross3(e2, dn, de1);      // fn = e1 x e2: de1 = e2 x dfn, de2 = dfn x e1
+            cross3(dn, e1, de2);
+            for (int i = 0; i < 3; ++i) {
+                scatter_add(&st.dx[f[1] * 3 + i], de1[i]);
+                scatter_add(&st.dx[f[2] * 3 + i], de2[i]);
+                scatter_add(&st.dx[f[0] * 3 + i], -(de1[i] + de2[i]));
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// reverse phases
+// ----------------------------------------------------------------------------------------------
+
+// B1: gather dE/dA_j from the vertices each joint skins (lists grouped by joint: no atomics).
+template <typename T>
+EMPOSE_HD void phase_skin_bwd_joints(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+    for (int it = lane; it < kJoints * 12; it += lanes) {
+        const int j = it / 12, e = it % 12;
+        T acc = T(0);
+        if (e < 9) {
+            const int r = e / 3, c = e % 3;
+            for (int q = m.jt_ptr[j]; q < m.jt_ptr[j + 1]; ++q) {
+                const int v = m.jt_vert[q];
+                acc += T(m.jt_weight[q]) * st.dx[v * 3 + r] * st.vp[v * 3 + c];
+            }
+            st.dar[j][e] = acc;
+        } else {
+            const int r = e - 9;
+            for (int q = m.jt_ptr[j]; q < m.jt_ptr[j + 1]; ++q) acc += T(m.jt_weight[q]) * st.dx[m.jt_vert[q] * 3 + r];
+            st.dat[j][r] = acc;
+        }
+    }
+}
+
+// B2: dE/dvp_v = sum_j w A_j^R^T dE/dx_v, in place over st.dx.  Must run AFTER phase_skin_bwd_joints.
+template <typename T>
+EMPOSE_HD void phase_skin_bwd_verts(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+    for (int v = lane; v < m.n_verts; v += lanes) {
+        const T d0 = st.dx[v * 3], d1 = st.dx[v * 3 + 1], d2 = st.dx[v * 3 + 2];
+        T g0 = T(0), g1 = T(0), g2 = T(0);
+        for (int s = 0; s < m.n_skin; ++s) {
+            const T w = T(m.skin_weight[v * m.n_skin + s]);
+            const T* A = st.grot[m.skin_joint[v * m.n_skin + s]];
+            g0 += w * (A[0] * d0 + A[3] * d1 + A[6] * d2);
+            g1 += w * (A[1] * d0 + A[4] * d1 + A[7] * d2);
+            g2 += w * (A[2] * d0 + A[5] * d1 + A[8] * d2);
+        }
+        st.dx[v * 3] = g0; st.dx[v * 3 + 1] = g1; st.dx[v * 3 + 2] = g2;
+    }
+}
+
+// B3: per-lane partial sums of dE/dbeta through the shape blend shapes (st.dx now holds dE/dvp).
+template <typename T>
+EMPOSE_HD void phase_shape_bwd_partial(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+    T acc[kBetas];
+    for (int k = 0; k < kBetas; ++k) acc[k] = T(0);
+    const int nv3 = m.n_verts * 3;
+    for (int i = lane; i < nv3; i += lanes) {
+        const T g = st.dx[i];
+        for (int k = 0; k < kBetas; ++k) acc[k] += T(m.shapedirs[k * m.vp_dim + i]) * g;
+    }
+    for (int k = 0; k < kBetas; ++k) st.dbeta_part[lane][k] = acc[k];
+}
+
+// B4: reverse kinematic chain, row-parallel like the forward one.  Row r owns row r of every dG^R
+// and entry r of every dG^t; the contributions to dR_j and dJ_j are sums over rows and are left
+// as three partials (part_rot / part_j) for phase_chain_bwd_reduce.
+template <typename T>
+EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+    for (int r = lane; r < 3; r += lanes) {
+        for (int j = 0; j < kJoints; ++j) {
+            // A_j^t = G_j^t - G_j^R J_j
+            const T a = st.dat[j][r];
+            st.dgt[j][r] = a;
+            for (int c = 0; c < 3; ++c) {
+                st.dgr[j][r * 3 + c] = st.dar[j][r * 3 + c] - a * st.jrest[j][c];
+                st.part_j[r][j][c] = -st.grot[j][r * 3 + c] * a;
+            }
+        }
+        for (int j = kJoints - 1; j >= 1; --j) {
+            const int p = m.parents[j];
+            const T* R = st.rot[j];
+            const T d0 = st.dgr[j][r * 3], d1 = st.dgr[j][r * 3 + 1], d2 = st.dgr[j][r * 3 + 2];
+            const T g0 = st.grot[p][r * 3], g1 = st.grot[p][r * 3 + 1], g2 = st.grot[p][r * 3 + 2];
+            const T dt = st.dgt[j][r];
+            // G_j^R = G_p^R R_j :  dR_j += G_p^R^T dG_j^R (row r's share),  dG_p^R += dG_j^R R_j^T
+            T* pr = st.part_rot[r][j];
+            pr[0] = g0 * d0; pr[1] = g0 * d1; pr[2] = g0 * d2;
+            pr[3] = g1 * d0; pr[4] = g1 * d1; pr[5] = g1 * d2;
+            pr[6] = g2 * d0; pr[7] = g2 * d1; pr[8] = g2 * d2;
+            st.dgr[p][r * 3 + 0] += d0 * R[0] + d1 * R[1] + d2 * R[2];
+            st.dgr[p][r * 3 + 1] += d0 * R[3] + d1 * R[4] + d2 * R[5];
+            st.dgr[p][r * 3 + 2] += d0 * R[6] + d1 * R[7] + d2 * R[8];
+            // G_j^t = G_p^R (J_j - J_p) + G_p^t
+            for (int c = 0; c < 3; ++c) {
+                st.dgr[p][r * 3 + c] += dt * (st.jrest[j][c] - st.jrest[p][c]);
+                const T share = (c == 0 ? g0 : (c == 1 ? g1 : g2)) * dt;
+                st.part_j[r][j][c] += share;
+                st.part_j[r][p][c] -= share;
+            }
+            st.dgt[p][r] += dt;
+        }
+        // root: G_0^R = R_0, G_0^t = J_0
+        for (int c = 0; c < 3; ++c) {
+            for (int rr = 0; rr < 3; ++rr) st.part_rot[r][0][rr * 3 + c] = (rr == r) ? st.dgr[0][r * 3 + c] : T(0);
+            st.part_j[r][0][c] += (c == r) ? st.dgt[0][r] : T(0);
+        }
+    }
+}
+
+template <typename T>
+EMPOSE_HD void phase_chain_bwd_reduce(FrameState<T>& st, int lane, int lanes) {
+    for (int i = lane; i < kJoints * 9; i += lanes) {
+        const int j = i / 9, e = i % 9;
+        st.drot[j][e] = st.part_rot[0][j][e] + st.part_rot[1][j][e] + st.part_rot[2][j][e];
+    }
+    for (int i = lane; i < kJoints * 3; i += lanes) {
+        const int j = i / 3, c = i % 3;
+        st.dj[j][c] = st.part_j[0][j][c] + st.part_j[1][j][c] + st.part_j[2][j][c];
+    }
+}
+
+// B5: finish.  g_theta and the complete g_beta, both scaled by `coef`.  `dpf` (dE/d pose-feature,
+// the result of the transposed pose-blend GEMM) may be null: the map is linear in dR, so a caller
+// can add rodrigues_bwd(theta_j, dpf_j) later (that is what the split GPU kernels do)
+// (= [f < len_b] * frame_mask * F / len_b, the per-frame form of models.py:560-579).
+template <typename T, typename TOut, typename TPf>
+EMPOSE_HD void phase_finish(const SubModel& m, FrameState<T>& st, T coef, int n_partials, const TPf* dpf, TOut* g_theta,
+                            TOut* g_beta, int lane, int lanes) {
+    for (int j = lane; j < kJoints; j += lanes) {
+        T g[3] = {T(0), T(0), T(0)};
+        if (dpf && j > 0)
+            for (int e = 0; e < 9; ++e) st.drot[j][e] += T(dpf[(j - 1) * 9 + e]);
+        rodrigues_bwd(&st.theta[j * 3], st.drot[j], g);
+        g_theta[j * 3] = TOut(coef * g[0]); g_theta[j * 3 + 1] = TOut(coef * g[1]); g_theta[j * 3 + 2] = TOut(coef * g[2]);
+    }
+    for (int k = lane; k < kBetas; k += lanes) {
+        T acc = T(0);
+        for (int l = 0; l < n_partials; ++l) acc += st.dbeta_part[l][k];
+        for (int i = 0; i < kPoseDim; ++i) acc += T(m.jdirs[k * kPoseDim + i]) * st.dj[i / 3][i % 3];
+        g_beta[k] = TOut(coef * acc);
+    }
+}
+
+}  // namespace empose

@@ -1,0 +1,173 @@
+"""Host-side preparation of the SMPL-H constants the CUDA path keeps resident.
+
+The reference evaluates the full 6890-vertex mesh N+1 times per window
+(``empose/nn/models.py:474`` -> ``empose/bodymodels/smpl.py:121``) although the loop only
+consumes 12 sensor frames and 22 joints.  This module extracts, once per model and in float64,
+the minimal equivalent ("sub-model"):
+
+* ``J(beta) = J0 + Jdirs . beta`` -- the joint regressor folded through the shape blend shapes;
+* hand joints folded into the wrists (the reference always feeds a zero hand pose, ``smpl.py:99``,
+  so every hand joint's skinning transform equals its wrist ancestor's and only the first
+  21*9 pose-blend features are ever non-zero);
+* only the vertices in the 1-ring of the 12 sensor vertices (``virtual_sensors.py:61-75``).
+
+The mesh connectivity is derived exactly the way the reference derives it (``topology_from_faces``),
+and is plain data for the C-ABI so that kernel and oracle can never disagree about it.
+"""
+import numpy as np
+
+#: sensor vertex ids in network order (reference ``empose/helpers/configuration.py:32-34``)
+VERTEX_IDS = (3027, 3748, 5430, 5178, 5006, 4447, 4559, 1961, 1391, 1535, 959, 1072)
+N_BODY_JOINTS = 22
+N_POSE_FEATURES = 21 * 9
+N_BETAS = 10
+
+
+def vertex_faces_table(faces, n_vertices):
+    """
+    Incident faces of every vertex, ascending, padded with -1 -- the ``trimesh.Trimesh.vertex_faces``
+    contract the reference relies on (``smpl.py:58-67``).  If trimesh is installed it is used, so the
+    helper-vertex choice (first face listed, ``virtual_sensors.py:55-58``) is whatever the reference
+    would get on this machine.
+    """
+    faces = np.asarray(faces, dtype=np.int64)
+    try:
+        import trimesh  # noqa: F401  (optional)
+        if hasattr(trimesh, 'Trimesh') and getattr(trimesh, '__file__', None):
+            mesh = trimesh.Trimesh(np.zeros((n_vertices, 3)), faces, process=False)
+            return np.asarray(mesh.vertex_faces).astype(np.int64)
+    except ImportError:
+        pass
+    flat_v = faces.reshape(-1)
+    flat_f = np.repeat(np.arange(faces.shape[0]), 3)
+    order = np.lexsort((flat_f, flat_v))
+    flat_v, flat_f = flat_v[order], flat_f[order]
+    degree = np.bincount(flat_v, minlength=n_vertices)
+    table = np.full((n_vertices, int(degree.max())), -1, dtype=np.int64)
+    start = np.concatenate([[0], np.cumsum(degree)[:-1]])
+    slot = np.arange(flat_v.shape[0]) - start[flat_v]
+    table[flat_v, slot] = flat_f
+    return table
+
+
+def topology_from_faces(faces, vertex_ids=VERTEX_IDS):
+    """
+    Sub-mesh faces, per-sensor incident faces and helper vertices, as the reference computes them
+    (``virtual_sensors.py:47-75``).  All ids are GLOBAL vertex ids / rows into ``sub_faces``.
+    """
+    faces = np.asarray(faces, dtype=np.int64)
+    ids = [int(v) for v in vertex_ids]
+    n_vertices = int(faces.max()) + 1
+    full_vf = vertex_faces_table(faces, n_vertices)
+    touched = full_vf[ids]
+    sub_faces = faces[np.unique(touched[touched != -1])]
+    sensor_faces = vertex_faces_table(sub_faces, int(sub_faces.max()) + 1)[ids]
+    helper_ids = []
+    for v in ids:
+        first_face = faces[full_vf[v, 0]]
+        helper_ids.append(int(first_face[first_face != v][0]))
+    return {'sub_faces': sub_faces, 'sensor_faces': sensor_faces,
+            'helper_ids': np.asarray(helper_ids, dtype=np.int64), 'vertex_ids': np.asarray(ids, dtype=np.int64)}
+
+
+def _first_body_ancestor(parents, j):
+    while j >= N_BODY_JOINTS:
+        j = int(parents[j])
+    return j
+
+
+def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kintree_table, topology):
+    """
+    :param v_template: (V,3) or (1,V,3).  shapedirs: (V,3,>=10).  posedirs: (459, V*3) (the BodyModel buffer
+        layout found in released checkpoints under ``smpl.bm.posedirs``) or (V,3,459) (the npz layout).
+    :param j_regressor: (52,V).  weights: (V,52).  kintree_table: (2,52).  topology: ``topology_from_faces``.
+    :return: dict of float32 / int32 arrays keyed ``sub.*`` (see include/empose_b200.h) plus python ints.
+    """
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    v_template = f64(v_template).reshape(-1, 3)
+    n_v = v_template.shape[0]
+    shapedirs = f64(shapedirs)[:, :, :N_BETAS]
+    posedirs = f64(posedirs)
+    if posedirs.ndim == 3:                                   # npz layout (V,3,459) -> (459, V*3)
+        posedirs = posedirs.reshape(n_v * 3, -1).T
+    assert posedirs.shape[1] == n_v * 3
+    j_regressor, weights = f64(j_regressor), f64(weights)
+    parents = [int(p) for p in np.asarray(kintree_table)[0]]
+    parents[0] = -1
+    for j in range(1, N_BODY_JOINTS):
+        assert 0 <= parents[j] < j, 'body joints must be topologically ordered'
+
+    sub_faces = np.asarray(topology['sub_faces'], dtype=np.int64)
+    verts = np.unique(sub_faces)                                # sorted global ids of the sub-mesh
+    local = -np.ones(n_v, dtype=np.int64)
+    local[verts] = np.arange(verts.shape[0])
+    n_sub = int(verts.shape[0])
+    sensor_ids = np.asarray(topology['vertex_ids'], dtype=np.int64)
+    helper_ids = np.asarray(topology['helper_ids'], dtype=np.int64)
+    assert (local[sensor_ids] >= 0).all() and (local[helper_ids] >= 0).all()
+
+    # joints folded through the shape blend shapes
+    j0 = j_regressor[:N_BODY_JOINTS] @ v_template                                   # (22,3)
+    jdirs = np.einsum('jv,vck->kjc', j_regressor[:N_BODY_JOINTS], shapedirs)        # (10,22,3)
+
+    # hands folded into their first body ancestor
+    w22 = np.zeros((n_sub, N_BODY_JOINTS))
+    for j in range(weights.shape[1]):
+        w22[:, _first_body_ancestor(parents, j)] += weights[verts, j]
+    nnz = (w22 != 0.0)
+    n_skin = int(nnz.sum(axis=1).max())
+    skin_joint = np.zeros((n_sub, n_skin), dtype=np.int32)
+    skin_weight = np.zeros((n_sub, n_skin), dtype=np.float64)
+    for v in range(n_sub):
+        js = np.nonzero(nnz[v])[0]
+        skin_joint[v, :js.shape[0]] = js
+        skin_weight[v, :js.shape[0]] = w22[v, js]
+    # the same relation grouped by joint (gather lists for the reverse pass)
+    jt_ptr = np.zeros(N_BODY_JOINTS + 1, dtype=np.int32)
+    jt_vert, jt_weight = [], []
+    for j in range(N_BODY_JOINTS):
+        vs = np.nonzero(nnz[:, j])[0]
+        jt_vert += vs.tolist()
+        jt_weight += w22[vs, j].tolist()
+        jt_ptr[j + 1] = len(jt_vert)
+
+    vp_dim = ((n_sub * 3 + 15) // 16) * 16                     # padded width of the per-frame vertex vector
+    pd = posedirs.reshape(posedirs.shape[0], n_v, 3)[:N_POSE_FEATURES, verts].reshape(N_POSE_FEATURES, n_sub * 3)
+    sd = shapedirs[verts].reshape(n_sub * 3, N_BETAS).T                              # (10, Vs*3)
+    pad = lambda a: np.concatenate([a, np.zeros(a.shape[:-1] + (vp_dim - n_sub * 3,))], axis=-1)
+
+    sensor_faces = np.asarray(topology['sensor_faces'], dtype=np.int64)
+    degree = (sensor_faces > -1).sum(axis=1)
+    out = {
+        'sub.v_template': pad(v_template[verts].reshape(-1)),                         # (VP,)
+        'sub.shapedirs': pad(sd),                                                     # (10, VP)
+        'sub.posedirs': pad(pd),                                                      # (189, VP)
+        'sub.j0': j0.reshape(-1),                                                     # (66,)
+        'sub.jdirs': jdirs.reshape(N_BETAS, N_BODY_JOINTS * 3),                       # (10, 66)
+        'sub.skin_weight': skin_weight,                                               # (Vs, n_skin)
+        'sub.jt_weight': np.asarray(jt_weight, dtype=np.float64),
+    }
+    out = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+    out.update({
+        'sub.parents': np.asarray(parents[:N_BODY_JOINTS], dtype=np.int32),
+        'sub.skin_joint': skin_joint,
+        'sub.jt_ptr': jt_ptr,
+        'sub.jt_vert': np.asarray(jt_vert, dtype=np.int32),
+        'sub.faces': local[sub_faces].astype(np.int32),                               # (Fs,3) local ids
+        'sub.sensor_vert': local[sensor_ids].astype(np.int32),                        # (12,)
+        'sub.helper_vert': local[helper_ids].astype(np.int32),                        # (12,)
+        'sub.sensor_faces': sensor_faces.astype(np.int32),                            # (12,deg) rows into faces, -1 pad
+        'sub.sensor_degree': degree.astype(np.int32),
+        'sub.global_vertex_ids': verts.astype(np.int32),
+    })
+    out['dims'] = {'n_verts': n_sub, 'vp_dim': int(vp_dim), 'n_faces': int(sub_faces.shape[0]),
+                   'max_degree': int(sensor_faces.shape[1]), 'n_skin': n_skin, 'n_sensors': int(sensor_ids.shape[0])}
+    return out
+
+
+def submodel_from_npz(npz_path, vertex_ids=VERTEX_IDS):
+    """Convenience: SMPL-H ``model.npz`` (the file of ``smpl.py:26``) -> sub-model arrays."""
+    with np.load(npz_path) as z:
+        topo = topology_from_faces(z['f'], vertex_ids)
+        return extract_submodel(z['v_template'], z['shapedirs'], z['posedirs'], z['J_regressor'], z['weights'],
+                                z['kintree_table'], topo), topo

@@ -132,8 +132,12 @@ def make_synthetic_smplh(seed=0):
 
     parents = np.asarray(smplh_parents(), dtype=np.int64)
     kintree = np.stack([parents, np.arange(n_j, dtype=np.int64)], axis=0)
-    return {'v_template': verts, 'f': faces, 'shapedirs': shapedirs, 'posedirs': posedirs,
-            'J_regressor': j_reg, 'kintree_table': kintree, 'weights': weights}
+    # Every float array is made exactly float32-representable (stored as float64 like the real file):
+    # the reference casts the model to float32 on load (smpl.py:27), so this way the reference, the
+    # oracle and the CUDA path all start from bit-identical constants.
+    r32 = lambda a: a.astype(np.float32).astype(np.float64)
+    return {'v_template': r32(verts), 'f': faces, 'shapedirs': r32(shapedirs), 'posedirs': r32(posedirs),
+            'J_regressor': r32(j_reg), 'kintree_table': kintree, 'weights': r32(weights)}
 
 
 def write_synthetic_smplh(root_dir, seed=0):

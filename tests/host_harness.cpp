@@ -1,0 +1,89 @@
+// CPU harness around em-pose_b200/csrc/frame_math.h (TEST INFRASTRUCTURE, never shipped).
+// The per-frame forward / reverse arithmetic of the CUDA kernels is written host+device; this file
+// compiles it with g++ and runs it with one "lane" so that tests/test_frame_math.py can compare the
+// hand-derived reverse pass with the oracle's autograd without a GPU.
+#include <vector>
+#include <cstring>
+#include "frame_math.h"
+
+using namespace empose;
+
+struct HostSub {
+    int n_verts, vp_dim, n_faces, max_degree, n_skin;
+    const float *v_template, *shapedirs, *posedirs, *j0, *jdirs, *skin_weight, *jt_weight;
+    const int *skin_joint, *jt_ptr, *jt_vert, *parents, *faces, *sensor_vert, *helper_vert, *sensor_faces, *sensor_degree;
+};
+
+template <typename T>
+static void run(const HostSub& h, int n_frames, const float* theta, const float* beta, const float* off_r,
+                const float* off_t, const float* meas_pos, const float* meas_ori, const int* active, int use_pos,
+                int use_ori, const float* coef, int want_grad, double* sensor_pos, double* sensor_ori, double* joints,
+                double* g_theta, double* g_beta, double* verts) {
+    SubModel m;
+    m.n_verts = h.n_verts; m.vp_dim = h.vp_dim; m.n_faces = h.n_faces; m.max_degree = h.max_degree; m.n_skin = h.n_skin;
+    m.v_template = h.v_template; m.shapedirs = h.shapedirs; m.j0 = h.j0; m.jdirs = h.jdirs;
+    m.skin_weight = h.skin_weight; m.skin_joint = h.skin_joint; m.jt_ptr = h.jt_ptr; m.jt_vert = h.jt_vert;
+    m.jt_weight = h.jt_weight; m.parents = h.parents; m.faces = h.faces; m.sensor_vert = h.sensor_vert;
+    m.helper_vert = h.helper_vert; m.sensor_faces = h.sensor_faces; m.sensor_degree = h.sensor_degree;
+    ResidualSpec spec;
+    spec.use_pos = use_pos; spec.use_ori = use_ori;
+    for (int s = 0; s < kSensors; ++s) spec.sensor_active[s] = active[s];
+    std::vector<FrameState<T>> st_store(1);
+    FrameState<T>& st = st_store[0];
+    std::vector<T> vp_off(h.vp_dim), dpf(kPoseFeatPad);
+    for (int f = 0; f < n_frames; ++f) {
+        for (int i = 0; i < kPoseDim; ++i) st.theta[i] = T(theta[f * kPoseDim + i]);
+        for (int i = 0; i < kBetas; ++i) st.beta[i] = T(beta[f * kBetas + i]);
+        // pose blend (the GPU path does this as a GEMM): pf = vec(R_1..R_21 - I)
+        T pf[kPoseFeat];
+        for (int j = 1; j < kJoints; ++j) {
+            T R[9];
+            rodrigues_fwd(&st.theta[j * 3], R);
+            for (int e = 0; e < 9; ++e) pf[(j - 1) * 9 + e] = R[e] - ((e % 4 == 0) ? T(1) : T(0));
+        }
+        for (int i = 0; i < h.vp_dim; ++i) {
+            T acc = T(0);
+            for (int k = 0; k < kPoseFeat; ++k) acc += T(h.posedirs[k * h.vp_dim + i]) * pf[k];
+            vp_off[i] = acc;
+        }
+        phase_setup(m, st, vp_off.data(), 0, 1);
+        phase_chain(m, st, 0, 1);
+        phase_skin(m, st, 0, 1);
+        phase_sensors(m, st, off_r + f * 108, off_t + f * 36, meas_pos + f * 36, meas_ori + f * 108, spec,
+                      want_grad != 0, 0, 1);
+        for (int i = 0; i < 36; ++i) sensor_pos[f * 36 + i] = double(st.sensor_pos[i / 3][i % 3]);
+        for (int i = 0; i < 108; ++i) sensor_ori[f * 108 + i] = double(st.sensor_ori[i / 9][i % 9]);
+        for (int i = 0; i < 66; ++i) joints[f * 66 + i] = double(st.gpos[i / 3][i % 3]);
+        if (verts) for (int i = 0; i < h.n_verts * 3; ++i) verts[f * h.n_verts * 3 + i] = double(st.x[i]);
+        if (!want_grad) continue;
+        phase_skin_bwd_joints(m, st, 0, 1);
+        phase_skin_bwd_verts(m, st, 0, 1);
+        phase_shape_bwd_partial(m, st, 0, 1);
+        for (int k = 0; k < kPoseFeat; ++k) {
+            T acc = T(0);
+            for (int i = 0; i < h.n_verts * 3; ++i) acc += T(h.posedirs[k * h.vp_dim + i]) * st.dx[i];
+            dpf[k] = acc;
+        }
+        phase_chain_bwd(m, st, 0, 1);
+        phase_chain_bwd_reduce(st, 0, 1);
+        std::vector<T> gt(kPoseDim), gb(kBetas);
+        phase_finish(m, st, T(coef[f]), 1, dpf.data(), gt.data(), gb.data(), 0, 1);
+        for (int i = 0; i < kPoseDim; ++i) g_theta[f * kPoseDim + i] = double(gt[i]);
+        for (int i = 0; i < kBetas; ++i) g_beta[f * kBetas + i] = double(gb[i]);
+    }
+}
+
+extern "C" int host_frame_eval(const HostSub* h, int n_frames, const float* theta, const float* beta,
+                               const float* off_r, const float* off_t, const float* meas_pos, const float* meas_ori,
+                               const int* active, int use_pos, int use_ori, const float* coef, int want_grad,
+                               int use_double, double* sensor_pos, double* sensor_ori, double* joints, double* g_theta,
+                               double* g_beta, double* verts) {
+    if (h->vp_dim > kMaxVp || h->max_degree > kMaxDegree) return -1;
+    if (use_double)
+        run<double>(*h, n_frames, theta, beta, off_r, off_t, meas_pos, meas_ori, active, use_pos, use_ori, coef,
+                    want_grad, sensor_pos, sensor_ori, joints, g_theta, g_beta, verts);
+    else
+        run<float>(*h, n_frames, theta, beta, off_r, off_t, meas_pos, meas_ori, active, use_pos, use_ori, coef,
+                   want_grad, sensor_pos, sensor_ori, joints, g_theta, g_beta, verts);
+    return 0;
+}

@@ -1,0 +1,68 @@
+"""ctypes wrapper around tests/host_harness.cpp (the CUDA per-frame math compiled for the host)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+_LIB = None
+
+_F32_FIELDS = ['v_template', 'shapedirs', 'posedirs', 'j0', 'jdirs', 'skin_weight', 'jt_weight']
+_I32_FIELDS = ['skin_joint', 'jt_ptr', 'jt_vert', 'parents', 'faces', 'sensor_vert', 'helper_vert', 'sensor_faces',
+               'sensor_degree']
+
+
+class HostSub(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int) for n in ('n_verts', 'vp_dim', 'n_faces', 'max_degree', 'n_skin')] +
+                [(n, ctypes.POINTER(ctypes.c_float)) for n in _F32_FIELDS] +
+                [(n, ctypes.POINTER(ctypes.c_int)) for n in _I32_FIELDS])
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        out_dir = os.path.join(HERE, '_build')
+        os.makedirs(out_dir, exist_ok=True)
+        so = os.path.join(out_dir, 'host_harness.so')
+        src = os.path.join(HERE, 'host_harness.cpp')
+        hdr = os.path.join(ROOT, 'em-pose_b200', 'csrc', 'frame_math.h')
+        if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-I', os.path.dirname(hdr), src,
+                                   '-o', so])
+        _LIB = ctypes.CDLL(so)
+    return _LIB
+
+
+def frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef, use_pos=True, use_ori=True,
+               want_grad=True, use_double=False):
+    """Run the per-frame math on the host.  All per-frame inputs are (n, ...) float32 arrays."""
+    keep = []
+    hs = HostSub()
+    d = sub['dims']
+    hs.n_verts, hs.vp_dim, hs.n_faces, hs.max_degree, hs.n_skin = (d['n_verts'], d['vp_dim'], d['n_faces'],
+                                                                   d['max_degree'], d['n_skin'])
+    for n in _F32_FIELDS:
+        a = np.ascontiguousarray(sub['sub.' + n], dtype=np.float32)
+        keep.append(a)
+        setattr(hs, n, a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    for n in _I32_FIELDS:
+        a = np.ascontiguousarray(sub['sub.' + n], dtype=np.int32)
+        keep.append(a)
+        setattr(hs, n, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    n = theta.shape[0]
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    theta, beta, off_r, off_t, meas_pos, meas_ori, coef = map(f32, (theta, beta, off_r, off_t, meas_pos, meas_ori, coef))
+    active = np.ascontiguousarray(active, dtype=np.int32)
+    out = {'sensor_pos': np.zeros((n, 12, 3)), 'sensor_ori': np.zeros((n, 12, 3, 3)), 'joints': np.zeros((n, 22, 3)),
+           'g_theta': np.zeros((n, 66)), 'g_beta': np.zeros((n, 10)), 'verts': np.zeros((n, d['n_verts'], 3))}
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    rc = _lib().host_frame_eval(ctypes.byref(hs), n, fp(theta), fp(beta), fp(off_r), fp(off_t), fp(meas_pos),
+                                fp(meas_ori), active.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(use_pos),
+                                int(use_ori), fp(coef), int(want_grad), int(use_double), dp(out['sensor_pos']),
+                                dp(out['sensor_ori']), dp(out['joints']), dp(out['g_theta']), dp(out['g_beta']),
+                                dp(out['verts']))
+    assert rc == 0
+    return out

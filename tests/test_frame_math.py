@@ -1,0 +1,89 @@
+"""The CUDA per-frame math (compiled for the host) vs the oracle: forward values and the hand-derived
+reverse pass vs autograd.  No GPU needed; this is what de-risks the VJP before any kernel runs."""
+import numpy as np
+import pytest
+import torch
+
+from empose_b200 import submodel, synthetic
+from oracle import ief as oracle_ief
+from oracle import sensors
+
+import host_math
+
+
+@pytest.fixture(scope='module')
+def sub(smpl_npz):
+    s, _ = submodel.submodel_from_npz(smpl_npz)
+    return s
+
+
+def _case(n, seed, offsets=True):
+    p = synthetic.synth_window_params(1, n, seed=seed, offsets=offsets)
+    theta = p['poses'][0]
+    beta = np.repeat(p['shapes'], n, axis=0) + 0.1 * np.random.RandomState(seed).standard_normal((n, 10)).astype(np.float32)
+    off_r = np.repeat(p['offset_r'], n, axis=0)
+    off_t = np.repeat(p['offset_t'], n, axis=0)
+    return theta, beta, off_r, off_t
+
+
+def _oracle(oracle_smpl, topology, theta, beta, off_r, off_t):
+    t = lambda a: torch.from_numpy(np.asarray(a)).double()
+    pose = t(theta).requires_grad_(True)
+    shape = t(beta).requires_grad_(True)
+    pos, ori, joints = oracle_ief.project_sensors(oracle_smpl, topology, pose, shape, t(off_r), t(off_t))
+    return pose, shape, pos, ori, joints
+
+
+@pytest.mark.parametrize('use_double', [True, False])
+def test_forward_matches_full_mesh_oracle(sub, oracle_smpl, topology, use_double):
+    theta, beta, off_r, off_t = _case(6, seed=3)
+    _, _, pos, ori, joints = _oracle(oracle_smpl, topology, theta, beta, off_r, off_t)
+    z = np.zeros
+    out = host_math.frame_eval(sub, theta, beta, off_r, off_t, z((6, 12, 3)), z((6, 12, 9)), np.ones(12), np.ones(6),
+                               want_grad=False, use_double=use_double)
+    tol = 2e-6 if use_double else 5e-6        # sub-model constants are float32; metres
+    np.testing.assert_allclose(out['sensor_pos'], pos.detach().numpy(), atol=tol, rtol=0)
+    np.testing.assert_allclose(out['joints'], joints.detach().numpy(), atol=tol, rtol=0)
+    np.testing.assert_allclose(out['sensor_ori'], ori.detach().numpy(), atol=5e-5 if not use_double else 2e-5, rtol=0)
+
+
+@pytest.mark.parametrize('n_markers', [12, 6])
+@pytest.mark.parametrize('use_double', [True, False])
+def test_reverse_pass_matches_autograd(sub, oracle_smpl, topology, n_markers, use_double):
+    n = 8
+    theta, beta, off_r, off_t = _case(n, seed=5)
+    rng = np.random.RandomState(9)
+    pose, shape, pos, ori, _ = _oracle(oracle_smpl, topology, theta, beta, off_r, off_t)
+    meas_pos = pos.detach().numpy() + 0.01 * rng.standard_normal((n, 12, 3))
+    meas_ori = ori.detach().numpy() + 0.05 * rng.standard_normal((n, 12, 3, 3))
+    idx = list(range(12)) if n_markers == 12 else list(sensors.S_CONFIG_6)
+    active = np.zeros(12, dtype=np.int32)
+    active[idx] = 1
+    coef = rng.uniform(0.5, 2.0, size=n)
+    coef[2] = 0.0
+    # per-frame energy, weighted per frame
+    dp = pos[:, idx] - torch.from_numpy(meas_pos[:, idx])
+    dr = (ori[:, idx] - torch.from_numpy(meas_ori[:, idx])).reshape(n, len(idx), 9)
+    energy = (torch.sqrt((dp * dp).sum(-1)).sum(-1) + torch.sqrt((dr * dr).sum(-1)).sum(-1)) * torch.from_numpy(coef)
+    g_pose, g_shape = torch.autograd.grad(energy.sum(), [pose, shape])
+    out = host_math.frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori.reshape(n, 12, 9), active, coef,
+                               use_double=use_double)
+    scale = float(g_pose.abs().max())
+    # float32: the orientation residual differentiates normalised cross products of ~1 cm edges taken from
+    # ~0.5 m coordinates, so ~1e-3 relative noise is inherent to single precision (the reference has it too)
+    tol = (2e-5 if use_double else 1.5e-3) * max(scale, 1.0)
+    np.testing.assert_allclose(out['g_theta'], g_pose.numpy(), atol=tol, rtol=0)
+    np.testing.assert_allclose(out['g_beta'], g_shape.numpy(), atol=tol, rtol=0)
+    assert np.abs(out['g_theta'][2]).max() == 0.0
+
+
+def test_rest_pose_known_answer(sub, oracle_smpl):
+    """Zero pose and shape: skinned sub-mesh == template vertices, joints == regressed rest joints."""
+    z = np.zeros
+    eye = np.tile(np.eye(3, dtype=np.float32).reshape(1, 1, 9), (1, 12, 1))
+    out = host_math.frame_eval(sub, z((1, 66)), z((1, 10)), eye, z((1, 12, 3)), z((1, 12, 3)), z((1, 12, 9)),
+                               np.ones(12), np.ones(1), want_grad=False, use_double=True)
+    ids = sub['sub.global_vertex_ids']
+    np.testing.assert_allclose(out['verts'][0], oracle_smpl.v_template.numpy()[ids], atol=1e-6, rtol=0)
+    rest = (oracle_smpl.j_regressor @ oracle_smpl.v_template).numpy()[:22]
+    np.testing.assert_allclose(out['joints'][0], rest, atol=1e-6, rtol=0)
