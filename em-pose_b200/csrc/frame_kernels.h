@@ -1,0 +1,95 @@
+// Host interface of the per-frame CUDA kernels (frame_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "frame_math.h"
+
+namespace empose {
+
+// Input assembly: BaseModel.prepare_inputs (empose/nn/models.py:106-125) plus the per-frame weight
+// of the gradient feature (loss.py:31-41 folded per frame).
+struct PrepareParams {
+    const float* marker_pos;    // [R][36]
+    const float* marker_oris;   // [R][108]
+    const int32_t* seq_len;     // [B]
+    const float* masks;         // [R][12] or null
+    int R, F;
+    int slot_of_sensor[kSensors];   // position of each sensor in the network input, -1 if not fed
+    int use_pos, use_ori, n_pos;    // n_pos = number of position columns in the network input
+    int in_size, iter_in;
+    int round_out;
+    float* meas;                // [R][144] exact copy [pos | ori]
+    float* xin;                 // [R][in_size]   (may be null)
+    float* xiter;               // [R][iter_in]   columns [0, in_size) written (may be null)
+    float* coef;                // [R]
+};
+int launch_prepare(const PrepareParams& p, cudaStream_t s);
+
+// theta/beta update (models.py:529-535, 588-592) + pose features for the pose-blend GEMM.
+struct UpdateParams {
+    float* theta;               // [R][66] in/out
+    float* beta;                // [R][10] in/out
+    const float* dtheta;        // [R][66] network output
+    const float* dbeta;         // [R][10]
+    float step;
+    int first;                  // 1: theta = dtheta, beta = (mean of) dbeta  (initial estimate)
+    int average_shape;
+    int B, F;
+    int round_out;
+    float* xiter;               // [R][iter_in] or null: columns [in_size, in_size+76) receive theta | beta
+    int in_size, iter_in;
+    float* pf;                  // [R][192] pose features vec(R_1..R_21 - I)
+    float* hist_pose;           // [R][66] or null
+    float* hist_shape;          // [R][10] or null
+};
+int launch_update(const UpdateParams& p, cudaStream_t s);
+
+// pose features only (for empose_sensor_project)
+int launch_pose_features(const float* theta, float* pf, int R, int round_out, cudaStream_t s);
+
+// SMPL sub-model forward (+ reverse) per frame.
+struct MainParams {
+    SubModel sub;
+    ResidualSpec spec;
+    const float* theta;         // [R][66]
+    const float* beta;          // [R][10]
+    const float* vp_off;        // [R][vp_dim]  pose-blend result
+    const float* offset_r;      // [R / rows_per_offset][108]
+    const float* offset_t;      // [R / rows_per_offset][36]
+    int rows_per_offset;        // F for windows, 1 for per-frame offsets
+    const float* meas;          // [R][144] (grad only)
+    const float* coef;          // [R]      (grad only)
+    int R;
+    int want_grad;
+    int round_out;
+    float* sensor_pos;          // [R][36] or null
+    float* sensor_ori;          // [R][108] or null
+    float* joints;              // [R][66] or null
+    float* dvp;                 // [R][vp_dim]  (grad only)
+    float* gtheta_part;         // [R][66]      (grad only) coef * chain part of dE/dtheta
+    float* gbeta;               // [R][10]      (grad only) coef * dE/dbeta
+};
+int launch_main(const MainParams& p, cudaStream_t s);
+
+// adds the pose-blend part of dE/dtheta and writes the gradient features into the iter-MLP input
+struct PostParams {
+    const float* theta;         // [R][66]
+    const float* dpf;           // [R][192]
+    const float* gtheta_part;   // [R][66]
+    const float* gbeta;         // [R][10]
+    const float* coef;          // [R]
+    int R;
+    int round_out;
+    float* xiter;               // [R][iter_in]: columns [in_size+76, in_size+152) receive g_theta | g_beta
+    int in_size, iter_in;
+    float* g_theta_out;         // optional exact copies (tests), may be null
+    float* g_beta_out;
+};
+int launch_post(const PostParams& p, cudaStream_t s);
+
+// gather the last time step of a [B][F][H] sequence buffer into [B][H]
+int launch_gather_last(const float* seq, float* out, int B, int F, int H, cudaStream_t s);
+
+}  // namespace empose

@@ -64,7 +64,7 @@ struct ResidualSpec {
     int sensor_active[kSensors];  // 1 if the sensor is in marker_idxs (models.py:386)
 };
 
-template <typename T>
+template <typename T, int VP = kMaxVp>
 struct FrameState {
     T theta[kPoseDim];
     T beta[kBetas];
@@ -73,18 +73,16 @@ struct FrameState {
     T grot[kJoints][9];       // world rotation G_j^R  (== A_j^R)
     T gpos[kJoints][3];       // world position G_j^t  (posed joint)
     T atr[kJoints][3];        // A_j^t = G_j^t - G_j^R J_j
-    T vp[kMaxVp];             // v_template + S beta + pose blend
-    T x[kMaxVp];              // skinned vertices
-    T dx[kMaxVp];             // dE/dx, then reused for dE/dvp
+    T vp[VP];                 // v_template + S beta + pose blend
+    T x[VP];                  // skinned vertices
+    T dx[VP];                 // dE/dx, then reused for dE/dvp
     T dar[kJoints][9];        // dE/dA^R
     T dat[kJoints][3];        // dE/dA^t
-    T part_rot[3][kJoints][9];   // row-wise partial sums of dE/dR_j from the chain
-    T part_j[3][kJoints][3];     // row-wise partial sums of dE/dJ_j
-    T dgr[kJoints][9];        // dE/dG^R (scratch of the reverse chain)
-    T dgt[kJoints][3];
-    T drot[kJoints][9];       // dE/dR_j  (chain part; the pose-blend part is added by the caller)
-    T dj[kJoints][3];
-    T dbeta_part[32][kBetas];
+    T dgr[kJoints][9];        // dE/dG^R
+    T dgt[kJoints][3];        // dE/dG^t
+    T drot[kJoints][9];       // dE/dR_j  (chain part; the pose-blend part is added in phase_finish or by the caller)
+    T dj[kJoints][3];         // dE/dJ_j
+    T dbeta_part[3][kBetas];
     T sensor_pos[kSensors][3];   // p'_m (offsets applied)
     T sensor_ori[kSensors][9];   // R'_m row-major
 };
@@ -180,8 +178,8 @@ template <typename T> EMPOSE_HD void rodrigues_bwd(const T* r, const T* dR, T* d
 // ----------------------------------------------------------------------------------------------
 
 // F1: rotations, rest joints, blended rest vertices.  vp_off may be null (treated as zero).
-template <typename T, typename TIn>
-EMPOSE_HD void phase_setup(const SubModel& m, FrameState<T>& st, const TIn* vp_off, int lane, int lanes) {
+template <typename T, int VP, typename TIn>
+EMPOSE_HD void phase_setup(const SubModel& m, FrameState<T, VP>& st, const TIn* vp_off, int lane, int lanes) {
     for (int j = lane; j < kJoints; j += lanes) rodrigues_fwd(&st.theta[j * 3], st.rot[j]);
     for (int i = lane; i < kPoseDim; i += lanes) {
         T acc = T(m.j0[i]);
@@ -199,8 +197,8 @@ EMPOSE_HD void phase_setup(const SubModel& m, FrameState<T>& st, const TIn* vp_o
 
 // F2: kinematic chain.  Row r of every world rotation depends only on row r of its ancestors, so
 // three lanes walk the whole tree independently (no synchronisation inside the chain).
-template <typename T>
-EMPOSE_HD void phase_chain(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+template <typename T, int VP>
+EMPOSE_HD void phase_chain(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
     for (int r = lane; r < 3; r += lanes) {
         for (int c = 0; c < 3; ++c) st.grot[0][r * 3 + c] = st.rot[0][r * 3 + c];
         st.gpos[0][r] = st.jrest[0][r];
@@ -221,8 +219,8 @@ EMPOSE_HD void phase_chain(const SubModel& m, FrameState<T>& st, int lane, int l
 }
 
 // F3: linear blend skinning of the sub-mesh; also clears dx for the reverse pass.
-template <typename T>
-EMPOSE_HD void phase_skin(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+template <typename T, int VP>
+EMPOSE_HD void phase_skin(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
     for (int v = lane; v < m.n_verts; v += lanes) {
         const T p0 = st.vp[v * 3], p1 = st.vp[v * 3 + 1], p2 = st.vp[v * 3 + 2];
         T x0 = T(0), x1 = T(0), x2 = T(0);
@@ -250,8 +248,8 @@ template <typename T> inline void scatter_add(T* addr, T val) { *addr += val; }
 // residual direction (loss.py:27-28) and pushes it back to the vertices it touched (st.dx).
 //   meas_pos: [12][3] measured positions, meas_ori: [12][9] measured orientations (row-major),
 //   off_r: [12][9], off_t: [12][3].
-template <typename T, typename TIn>
-EMPOSE_HD void phase_sensors(const SubModel& m, FrameState<T>& st, const TIn* off_r, const TIn* off_t,
+template <typename T, int VP, typename TIn>
+EMPOSE_HD void phase_sensors(const SubModel& m, FrameState<T, VP>& st, const TIn* off_r, const TIn* off_t,
                              const TIn* meas_pos, const TIn* meas_ori, const ResidualSpec& spec, bool want_grad,
                              int lane, int lanes) {
     for (int s = lane; s < kSensors; s += lanes) {
@@ -363,8 +361,8 @@ EMPOSE_HD void phase_sensors(const SubModel& m, FrameState<T>& st, const TIn* of
 // ----------------------------------------------------------------------------------------------
 
 // B1: gather dE/dA_j from the vertices each joint skins (lists grouped by joint: no atomics).
-template <typename T>
-EMPOSE_HD void phase_skin_bwd_joints(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+template <typename T, int VP>
+EMPOSE_HD void phase_skin_bwd_joints(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
     for (int it = lane; it < kJoints * 12; it += lanes) {
         const int j = it / 12, e = it % 12;
         T acc = T(0);
@@ -384,8 +382,8 @@ EMPOSE_HD void phase_skin_bwd_joints(const SubModel& m, FrameState<T>& st, int l
 }
 
 // B2: dE/dvp_v = sum_j w A_j^R^T dE/dx_v, in place over st.dx.  Must run AFTER phase_skin_bwd_joints.
-template <typename T>
-EMPOSE_HD void phase_skin_bwd_verts(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+template <typename T, int VP>
+EMPOSE_HD void phase_skin_bwd_verts(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
     for (int v = lane; v < m.n_verts; v += lanes) {
         const T d0 = st.dx[v * 3], d1 = st.dx[v * 3 + 1], d2 = st.dx[v * 3 + 2];
         T g0 = T(0), g1 = T(0), g2 = T(0);
@@ -400,83 +398,80 @@ EMPOSE_HD void phase_skin_bwd_verts(const SubModel& m, FrameState<T>& st, int la
     }
 }
 
-// B3: per-lane partial sums of dE/dbeta through the shape blend shapes (st.dx now holds dE/dvp).
-template <typename T>
-EMPOSE_HD void phase_shape_bwd_partial(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
-    T acc[kBetas];
-    for (int k = 0; k < kBetas; ++k) acc[k] = T(0);
-    const int nv3 = m.n_verts * 3;
-    for (int i = lane; i < nv3; i += lanes) {
-        const T g = st.dx[i];
-        for (int k = 0; k < kBetas; ++k) acc[k] += T(m.shapedirs[k * m.vp_dim + i]) * g;
+// B3: partial sums of dE/dbeta through the shape blend shapes (st.dx now holds dE/dvp): 30 items,
+// item (k, p) sums the vertices v = p (mod 3).
+template <typename T, int VP>
+EMPOSE_HD void phase_shape_bwd_partial(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int it = lane; it < 3 * kBetas; it += lanes) {
+        const int k = it % kBetas, p = it / kBetas;
+        const float* S = m.shapedirs + k * m.vp_dim;
+        T acc = T(0);
+        for (int v = p; v < m.n_verts; v += 3)
+            acc += T(S[v * 3]) * st.dx[v * 3] + T(S[v * 3 + 1]) * st.dx[v * 3 + 1] + T(S[v * 3 + 2]) * st.dx[v * 3 + 2];
+        st.dbeta_part[p][k] = acc;
     }
-    for (int k = 0; k < kBetas; ++k) st.dbeta_part[lane][k] = acc[k];
 }
 
-// B4: reverse kinematic chain, row-parallel like the forward one.  Row r owns row r of every dG^R
-// and entry r of every dG^t; the contributions to dR_j and dJ_j are sums over rows and are left
-// as three partials (part_rot / part_j) for phase_chain_bwd_reduce.
-template <typename T>
-EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T>& st, int lane, int lanes) {
+// B4: reverse sweep of the kinematic chain, row-parallel like the forward one: lane r owns row r of
+// every dE/dG^R and entry r of every dE/dG^t.  After the sweep both are final for every joint.
+template <typename T, int VP>
+EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
     for (int r = lane; r < 3; r += lanes) {
         for (int j = 0; j < kJoints; ++j) {
-            // A_j^t = G_j^t - G_j^R J_j
+            // A_j^R = G_j^R,  A_j^t = G_j^t - G_j^R J_j
             const T a = st.dat[j][r];
             st.dgt[j][r] = a;
-            for (int c = 0; c < 3; ++c) {
-                st.dgr[j][r * 3 + c] = st.dar[j][r * 3 + c] - a * st.jrest[j][c];
-                st.part_j[r][j][c] = -st.grot[j][r * 3 + c] * a;
-            }
+            for (int c = 0; c < 3; ++c) st.dgr[j][r * 3 + c] = st.dar[j][r * 3 + c] - a * st.jrest[j][c];
         }
         for (int j = kJoints - 1; j >= 1; --j) {
             const int p = m.parents[j];
             const T* R = st.rot[j];
             const T d0 = st.dgr[j][r * 3], d1 = st.dgr[j][r * 3 + 1], d2 = st.dgr[j][r * 3 + 2];
-            const T g0 = st.grot[p][r * 3], g1 = st.grot[p][r * 3 + 1], g2 = st.grot[p][r * 3 + 2];
             const T dt = st.dgt[j][r];
-            // G_j^R = G_p^R R_j :  dR_j += G_p^R^T dG_j^R (row r's share),  dG_p^R += dG_j^R R_j^T
-            T* pr = st.part_rot[r][j];
-            pr[0] = g0 * d0; pr[1] = g0 * d1; pr[2] = g0 * d2;
-            pr[3] = g1 * d0; pr[4] = g1 * d1; pr[5] = g1 * d2;
-            pr[6] = g2 * d0; pr[7] = g2 * d1; pr[8] = g2 * d2;
-            st.dgr[p][r * 3 + 0] += d0 * R[0] + d1 * R[1] + d2 * R[2];
-            st.dgr[p][r * 3 + 1] += d0 * R[3] + d1 * R[4] + d2 * R[5];
-            st.dgr[p][r * 3 + 2] += d0 * R[6] + d1 * R[7] + d2 * R[8];
-            // G_j^t = G_p^R (J_j - J_p) + G_p^t
-            for (int c = 0; c < 3; ++c) {
-                st.dgr[p][r * 3 + c] += dt * (st.jrest[j][c] - st.jrest[p][c]);
-                const T share = (c == 0 ? g0 : (c == 1 ? g1 : g2)) * dt;
-                st.part_j[r][j][c] += share;
-                st.part_j[r][p][c] -= share;
-            }
+            // G_j^R = G_p^R R_j           -> dG_p^R += dG_j^R R_j^T
+            // G_j^t = G_p^R (J_j - J_p) + G_p^t -> dG_p^R += dG_j^t (J_j - J_p)^T,  dG_p^t += dG_j^t
+            st.dgr[p][r * 3 + 0] += d0 * R[0] + d1 * R[1] + d2 * R[2] + dt * (st.jrest[j][0] - st.jrest[p][0]);
+            st.dgr[p][r * 3 + 1] += d0 * R[3] + d1 * R[4] + d2 * R[5] + dt * (st.jrest[j][1] - st.jrest[p][1]);
+            st.dgr[p][r * 3 + 2] += d0 * R[6] + d1 * R[7] + d2 * R[8] + dt * (st.jrest[j][2] - st.jrest[p][2]);
             st.dgt[p][r] += dt;
         }
-        // root: G_0^R = R_0, G_0^t = J_0
-        for (int c = 0; c < 3; ++c) {
-            for (int rr = 0; rr < 3; ++rr) st.part_rot[r][0][rr * 3 + c] = (rr == r) ? st.dgr[0][r * 3 + c] : T(0);
-            st.part_j[r][0][c] += (c == r) ? st.dgt[0][r] : T(0);
+    }
+}
+
+// B5: local gradients from the final dE/dG.
+//   dE/dR_j = G_p^R^T dE/dG_j^R   (j > 0),   dE/dR_0 = dE/dG_0^R
+//   dE/dJ_j = (G_p^R - G_j^R)^T dE/dG_j^t   (j > 0),   dE/dJ_0 = (I - G_0^R)^T dE/dG_0^t
+// (the second line collects the three places J_j appears: A_j^t, its own bone and its children's bones,
+//  using dE/dG_j^t = dE/dA_j^t + sum over children of dE/dG_child^t).
+template <typename T, int VP>
+EMPOSE_HD void phase_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int i = lane; i < kJoints * 12; i += lanes) {
+        const int j = i / 12, e = i % 12;
+        const int p = m.parents[j];
+        if (e < 9) {
+            const int a = e / 3, b = e % 3;
+            T acc;
+            if (j == 0) acc = st.dgr[0][e];
+            else acc = st.grot[p][a] * st.dgr[j][b] + st.grot[p][3 + a] * st.dgr[j][3 + b] + st.grot[p][6 + a] * st.dgr[j][6 + b];
+            st.drot[j][e] = acc;
+        } else {
+            const int c = e - 9;
+            T acc = T(0);
+            for (int r = 0; r < 3; ++r) {
+                const T gp = (j == 0) ? (r == c ? T(1) : T(0)) : st.grot[p][r * 3 + c];
+                acc += (gp - st.grot[j][r * 3 + c]) * st.dgt[j][r];
+            }
+            st.dj[j][c] = acc;
         }
     }
 }
 
-template <typename T>
-EMPOSE_HD void phase_chain_bwd_reduce(FrameState<T>& st, int lane, int lanes) {
-    for (int i = lane; i < kJoints * 9; i += lanes) {
-        const int j = i / 9, e = i % 9;
-        st.drot[j][e] = st.part_rot[0][j][e] + st.part_rot[1][j][e] + st.part_rot[2][j][e];
-    }
-    for (int i = lane; i < kJoints * 3; i += lanes) {
-        const int j = i / 3, c = i % 3;
-        st.dj[j][c] = st.part_j[0][j][c] + st.part_j[1][j][c] + st.part_j[2][j][c];
-    }
-}
-
-// B5: finish.  g_theta and the complete g_beta, both scaled by `coef`.  `dpf` (dE/d pose-feature,
-// the result of the transposed pose-blend GEMM) may be null: the map is linear in dR, so a caller
-// can add rodrigues_bwd(theta_j, dpf_j) later (that is what the split GPU kernels do)
-// (= [f < len_b] * frame_mask * F / len_b, the per-frame form of models.py:560-579).
-template <typename T, typename TOut, typename TPf>
-EMPOSE_HD void phase_finish(const SubModel& m, FrameState<T>& st, T coef, int n_partials, const TPf* dpf, TOut* g_theta,
+// B6: finish.  g_theta and the complete g_beta, both scaled by `coef`
+// (= [f < len_b] * frame_mask * F / len_b, the per-frame form of models.py:560-579).  `dpf`
+// (dE/d pose-feature, the result of the transposed pose-blend GEMM) may be null: the map is linear in
+// dR, so a caller can add coef * rodrigues_bwd(theta_j, dpf_j) later (the split GPU kernels do that).
+template <typename T, int VP, typename TOut, typename TPf>
+EMPOSE_HD void phase_finish(const SubModel& m, FrameState<T, VP>& st, T coef, const TPf* dpf, TOut* g_theta,
                             TOut* g_beta, int lane, int lanes) {
     for (int j = lane; j < kJoints; j += lanes) {
         T g[3] = {T(0), T(0), T(0)};
@@ -486,8 +481,7 @@ EMPOSE_HD void phase_finish(const SubModel& m, FrameState<T>& st, T coef, int n_
         g_theta[j * 3] = TOut(coef * g[0]); g_theta[j * 3 + 1] = TOut(coef * g[1]); g_theta[j * 3 + 2] = TOut(coef * g[2]);
     }
     for (int k = lane; k < kBetas; k += lanes) {
-        T acc = T(0);
-        for (int l = 0; l < n_partials; ++l) acc += st.dbeta_part[l][k];
+        T acc = st.dbeta_part[0][k] + st.dbeta_part[1][k] + st.dbeta_part[2][k];
         for (int i = 0; i < kPoseDim; ++i) acc += T(m.jdirs[k * kPoseDim + i]) * st.dj[i / 3][i % 3];
         g_beta[k] = TOut(coef * acc);
     }

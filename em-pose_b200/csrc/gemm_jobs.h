@@ -1,0 +1,128 @@
+// GEMM job descriptors and the epilogues shared by the two job executors
+// (gemm_tc.cu: tcgen05 + TMA + TMEM, gemm_simt.cu: fp32 FFMA).
+//
+// A job is one output tile-column of one "layer":  D[M x n_count] = A[M x K] . W[n_begin.., K]^T
+// followed by an epilogue that turns the fp32 accumulators into whatever the layer produces.
+// A can be the concatenation of up to two K-segments taken from different buffers (the LSTM uses
+// [h_{t-1} | x_t]).  Jobs are row-tile agnostic: executors apply a job to a 128-row tile at row m0.
+//
+// Reference semantics implemented by the epilogues:
+//   EPI_LINEAR : nn.Linear (+ folded BatchNorm1d) + optional PReLU + optional LinearLayers skip
+//                (empose/nn/layers.py:13-77); also the plain contraction of the pose blend.
+//   EPI_LSTM   : one LSTM cell update with packed-sequence masking (empose/nn/layers.py:146-153).
+#pragma once
+
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace empose {
+
+constexpr int kTileM = 128;       // rows per tile (UMMA M)
+constexpr int kMaxTileN = 256;    // columns per job (UMMA N), multiple of 16
+constexpr int kChunkK = 32;       // floats per K chunk = one 128-byte swizzle row
+
+enum EpilogueKind : int32_t { EPI_LINEAR = 0, EPI_LSTM = 1 };
+
+struct GemmJob {
+    // ---- A operand: up to two K segments ----
+    const float* a_ptr[2];
+    int64_t a_stride[2];     // floats between consecutive rows
+    int32_t a_k[2];          // real K extent of the segment (0 = unused); padded to kChunkK in W
+    int32_t a_map[2];        // tensor-map slot (tcgen05 executor)
+    // ---- W operand: packed [n_total][w_ld], K-major, segment s starts at column w_koff[s] ----
+    const float* w_ptr;
+    int64_t w_ld;
+    int32_t w_koff[2];
+    int32_t w_map;
+    int32_t n_begin;         // first W row / output column of this job
+    int32_t n_count;         // columns computed (multiple of 16, <= kMaxTileN)
+    int32_t m_rows;          // valid rows overall; rows >= m_rows are never written
+    int32_t dep;             // chain-local index of the job that must have finished before A may be loaded (-1: none)
+    // ---- epilogue ----
+    int32_t epi;
+    int32_t round_out;       // 1: round outputs that feed later GEMMs to tf32 and use fast transcendentals
+    const float* bias;       // indexed by global column (n_begin + c); may be null
+    int32_t has_act;
+    float prelu_alpha;
+    int32_t n_valid;         // columns >= n_valid (global index) are discarded
+    float* out;              // columns [0, split)
+    int64_t out_stride;
+    int32_t out_col0;        // added to the global column index
+    int32_t split;           // columns >= split go to out2 at (col - split)
+    float* out2;
+    int64_t out2_stride;
+    const float* res;        // optional residual added after the activation (LinearLayers skip), same indexing as out
+    int64_t res_stride;
+    // row masking: rows whose frame index (row % frames_per_window) >= seq_len[row / frames_per_window]
+    // contribute only the bias (the LSTM output of a padded frame is zero, layers.py:153)
+    const int32_t* seq_len;
+    int32_t frames_per_window;
+    int32_t mask_rows;
+    // ---- LSTM ----
+    float* c_state;          // [M][H] cell state, updated in place
+    const float* h_prev;     // carry source for frozen rows (row stride h_prev_stride)
+    int64_t h_prev_stride;
+    int32_t t;               // time step of this job
+    int32_t hidden;          // H
+};
+
+// Columns of an LSTM job are packed in groups of 32 = 8 hidden units x 4 gates:
+// packed column n -> unit (n / 32) * 8 + n % 8, gate (n % 32) / 8  with gates ordered i, f, g, o.
+__host__ __device__ inline int lstm_unit_of_packed(int n) { return (n / 32) * 8 + (n % 8); }
+__host__ __device__ inline int lstm_gate_of_packed(int n) { return (n % 32) / 8; }
+
+#if defined(__CUDACC__)
+// Process 32 consecutive accumulator columns [c0, c0+32) (c0 relative to the job, multiple of 32)
+// of one row.  `v` holds the raw fp32 accumulators.
+__device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row, int c0, float (&v)[32]) {
+    if (row >= j.m_rows) return;
+    const int n0 = j.n_begin + c0;                 // global column of v[0]
+    if (j.epi == EPI_LINEAR) {
+        bool masked = false;
+        if (j.mask_rows) masked = (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int n = n0 + i;
+            if (c0 + i >= j.n_count || n >= j.n_valid) continue;
+            float y = masked ? 0.0f : v[i];
+            if (j.bias) y += j.bias[n];
+            if (j.has_act) y = y > 0.0f ? y : j.prelu_alpha * y;
+            if (j.res) y += j.res[(int64_t)row * j.res_stride + j.out_col0 + n];
+            if (j.round_out) y = round_tf32(y);
+            if (n < j.split) j.out[(int64_t)row * j.out_stride + j.out_col0 + n] = y;
+            else j.out2[(int64_t)row * j.out2_stride + (n - j.split)] = y;
+        }
+    } else {  // EPI_LSTM
+        const int unit0 = lstm_unit_of_packed(n0);
+        const bool live = j.t < j.seq_len[row];
+        float* c_ptr = j.c_state + (int64_t)row * j.hidden + unit0;
+        float* h_ptr = j.out + (int64_t)row * j.out_stride + unit0;
+        if (live) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float gi = v[u] + j.bias[n0 + u];
+                const float gf = v[8 + u] + j.bias[n0 + 8 + u];
+                const float gg = v[16 + u] + j.bias[n0 + 16 + u];
+                const float go = v[24 + u] + j.bias[n0 + 24 + u];
+                float c_new, h_new;
+                if (j.round_out) {
+                    c_new = sigmoid_f(gf) * c_ptr[u] + sigmoid_f(gi) * tanh_f(gg);
+                    h_new = round_tf32(sigmoid_f(go) * tanh_f(c_new));
+                } else {
+                    c_new = (1.0f / (1.0f + expf(-gf))) * c_ptr[u] + (1.0f / (1.0f + expf(-gi))) * tanhf(gg);
+                    h_new = (1.0f / (1.0f + expf(-go))) * tanhf(c_new);
+                }
+                c_ptr[u] = c_new;
+                h_ptr[u] = h_new;
+            }
+        } else {
+            const float* hp = j.h_prev + (int64_t)row * j.h_prev_stride + unit0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) h_ptr[u] = hp[u];
+        }
+    }
+}
+#endif
+
+}  // namespace empose

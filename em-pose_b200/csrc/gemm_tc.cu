@@ -1,0 +1,341 @@
+// tcgen05 / TMA / TMEM job executor (sm_100a).
+//
+// One persistent, warp-specialised kernel executes lists of GemmJob (gemm_jobs.h) on 128-row tiles:
+//
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of A [128 x 32] and W [n x 32] fp32 chunks
+//                           into a 4-stage shared-memory ring, completion on mbarriers
+//   warp 1   MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256, K=8),
+//                           accumulating in TMEM; tcgen05.commit releases ring slots and publishes accumulators
+//   warp 2   TMEM allocator 512 columns = two 128x256 fp32 accumulators (double buffered across jobs)
+//   warps 4-7 epilogue      tcgen05.ld 32 columns at a time -> epilogue_chunk() -> global memory
+//
+// A work item is (row tile, group of consecutive jobs).  Jobs of one item run back to back in the
+// same CTA; a job may depend on an earlier job of its item (an MLP layer reading the previous layer's
+// activations): the producer then waits for that job's epilogue, whose global stores are made visible
+// to the TMA (async proxy) with fence.proxy.async before it is counted as done.  Independent jobs in
+// between (the pose and shape MLPs are interleaved layer by layer) keep the tensor pipe busy meanwhile.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/empose_b200.h"
+#include "gemm_jobs.h"
+#include "gemm_tc.h"
+
+namespace empose {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kABytes = kTileM * kChunkK * 4;        // 16 KB
+constexpr int kWBytes = kMaxTileN * kChunkK * 4;     // 32 KB
+constexpr int kStageBytes = kABytes + kWBytes;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 256;
+constexpr int kEpiThreads = 128;
+
+struct __align__(8) Control {
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    volatile uint32_t epi_done;
+};
+
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*Control*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int crd0, int crd1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor for a K-major tile whose rows are 128 bytes (32 fp32) apart, stored
+// with the 128-byte swizzle TMA produces: 8-row groups are 1024 bytes apart (SBO), LBO is unused.
+// Field layout: cute::UMMA::SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
+// [46,48), layout_type [61,64) with SWIZZLE_128B = 2).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ int job_k_chunks(const GemmJob& j) {
+    return (j.a_k[0] + kChunkK - 1) / kChunkK + (j.a_k[1] + kChunkK - 1) / kChunkK;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __restrict__ jobs,
+                                                              const CUtensorMap* __restrict__ maps, int job_begin,
+                                                              int job_count, int jobs_per_item, int m_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Control* ctl = reinterpret_cast<Control*>(smem + kStages * kStageBytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int groups = job_count / jobs_per_item;
+    const int n_items = m_tiles * groups;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&ctl->tmem_full[b], 1);
+            mbar_init(&ctl->tmem_empty[b], 1);
+        }
+        ctl->epi_done = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, items_done = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++items_done) {
+                const int m0 = (item / groups) * kTileM;
+                const int first = job_begin + (item % groups) * jobs_per_item;
+                for (int jj = 0; jj < jobs_per_item; ++jj) {
+                    const GemmJob& job = jobs[first + jj];
+                    if (job.dep >= 0) {
+                        const uint32_t need = items_done * (uint32_t)jobs_per_item + (uint32_t)job.dep + 1u;
+                        while (ctl->epi_done < need) {
+                        }
+                        __threadfence_block();
+                    }
+                    const uint32_t w_bytes = (uint32_t)job.n_count * kChunkK * 4u;
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int chunks = (job.a_k[seg] + kChunkK - 1) / kChunkK;
+                        for (int kc = 0; kc < chunks; ++kc) {
+                            mbar_wait(&ctl->empty[stage], phase ^ 1u);
+                            uint8_t* a_dst = smem + stage * kStageBytes;
+                            uint8_t* w_dst = a_dst + kABytes;
+                            mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
+                            tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * kChunkK, m0);
+                            tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * kChunkK,
+                                        job.n_begin);
+                            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, seq = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int first = job_begin + (item % groups) * jobs_per_item;
+                for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
+                    const GemmJob& job = jobs[first + jj];
+                    const uint32_t buf = seq & 1u;
+                    mbar_wait(&ctl->tmem_empty[buf], ((seq >> 1) & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * kMaxTileN;
+                    const uint32_t idesc = make_idesc(job.n_count);
+                    const int chunks = job_k_chunks(job);
+                    for (int kc = 0; kc < chunks; ++kc) {
+                        mbar_wait(&ctl->full[stage], phase);
+                        tcgen05_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+                        const uint64_t a_desc = make_smem_desc(a_addr);
+                        const uint64_t b_desc = make_smem_desc(a_addr + kABytes);
+#pragma unroll
+                        for (int k = 0; k < kChunkK / 8; ++k) {
+                            // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
+                            umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                      (kc | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&ctl->empty[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(&ctl->tmem_full[buf]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp - 4;
+        uint32_t seq = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int m0 = (item / groups) * kTileM;
+            const int first = job_begin + (item % groups) * jobs_per_item;
+            for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
+                const GemmJob job = jobs[first + jj];       // by value: keeps the fields in registers
+                const uint32_t buf = seq & 1u;
+                mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
+                tcgen05_fence_after();
+                const int row = m0 + ew * 32 + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * kMaxTileN;
+                for (int c0 = 0; c0 < job.n_count; c0 += 32) {
+                    float v[32];
+                    tmem_load_32cols(taddr + (uint32_t)c0, v);
+                    epilogue_chunk(job, row, c0, v);
+                }
+                tcgen05_fence_before();
+                __threadfence();                                  // stores visible at L2 ...
+                asm volatile("fence.proxy.async;" ::: "memory");   // ... and ordered before later TMA reads
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                if (threadIdx.x == 4 * 32) {
+                    mbar_arrive(&ctl->tmem_empty[buf]);
+                    ctl->epi_done = seq + 1u;
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+int tc_encode_map(void* out_map, const float* base, int64_t row_stride_floats, int k_extent, int64_t rows,
+                  int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return EMPOSE_E_CUDA;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((row_stride_floats * 4) & 15) || box_rows < 1 || box_rows > 256) {
+        set_last_error("tensor map: base / stride must be 16-byte aligned and the box at most 256 rows");
+        return EMPOSE_E_ARG;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride_floats * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
+    cuuint32_t elem[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<float*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return EMPOSE_E_CUDA;
+    }
+    return EMPOSE_OK;
+}
+
+int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_count, int jobs_per_item, int m_tiles,
+              int num_sms, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        configured = true;
+    }
+    const int n_items = m_tiles * (job_count / jobs_per_item);
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(d_jobs, reinterpret_cast<const CUtensorMap*>(d_maps),
+                                                           job_begin, job_count, jobs_per_item, m_tiles);
+    EMPOSE_CUDA_TRY(cudaGetLastError());
+    return EMPOSE_OK;
+}
+
+}  // namespace empose

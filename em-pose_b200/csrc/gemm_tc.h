@@ -1,0 +1,27 @@
+// Host interface of the tcgen05 job executor (gemm_tc.cu) and the FFMA job executor (gemm_simt.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_jobs.h"
+
+namespace empose {
+
+constexpr int kTensorMapBytes = 128;   // sizeof(CUtensorMap)
+
+// Encode a 2-D fp32 tensor map {k_extent, rows} with row stride `row_stride_floats`, box {32, box_rows},
+// 128-byte swizzle, zero fill out of bounds.  `out_map` is HOST memory of kTensorMapBytes.
+int tc_encode_map(void* out_map, const float* base, int64_t row_stride_floats, int k_extent, int64_t rows,
+                  int box_rows);
+
+// Run jobs [job_begin, job_begin + job_count) of the device array `d_jobs` on `m_tiles` row tiles.
+// `jobs_per_item` consecutive jobs form one work item executed by one CTA in order.
+int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_count, int jobs_per_item, int m_tiles,
+              int num_sms, cudaStream_t stream);
+
+// Same contract on the fp32 FFMA executor (one launch per job; tensor maps unused).
+int simt_launch(const GemmJob* d_jobs, const GemmJob* h_jobs, int job_begin, int job_count, int m_tiles,
+                cudaStream_t stream, int64_t* launch_counter);
+
+}  // namespace empose

@@ -1,0 +1,915 @@
+// Model context, weight packing, execution plans and the C-ABI entry points (include/empose_b200.h).
+//
+// The pass implemented here is IterativeErrorFeedback.forward of the reference
+// (empose/nn/models.py:485-632) in inference mode:
+//
+//   prepare  -> [LSTM (F+L-1 wavefront launches) -> heads | init MLPs] -> update(first)
+//   N x { pose-blend GEMM -> frame kernel (SMPL sub-model fwd + reverse) -> transposed pose-blend GEMM
+//         -> gradient features -> pose & shape iter-MLP chain -> update }
+//   pose-blend GEMM -> frame kernel (forward only) -> outputs
+//
+// Every GEMM-shaped step is a list of GemmJob executed by the tcgen05 executor (TF32 mode) or the
+// FFMA executor (FP32 mode).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/empose_b200.h"
+#include "common.cuh"
+#include "frame_kernels.h"
+#include "gemm_jobs.h"
+#include "gemm_tc.h"
+
+namespace empose {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+#define EMPOSE_TRY(expr)            \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != EMPOSE_OK) return _rc; \
+    } while (0)
+
+float host_round_tf32(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;   // inf / nan
+    u += 0x1000u;                                       // round to nearest, ties away (cvt.rna)
+    u &= 0xFFFFE000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+
+// ---- tensor table -----------------------------------------------------------------------------
+struct TensorTable {
+    const empose_tensor* t;
+    int n;
+    const empose_tensor* find(const std::string& name) const {
+        for (int i = 0; i < n; ++i)
+            if (name == t[i].name) return &t[i];
+        return nullptr;
+    }
+    int64_t numel(const empose_tensor* e) const {
+        int64_t k = 1;
+        for (int d = 0; d < e->ndim; ++d) k *= e->shape[d];
+        return k;
+    }
+    // fetch a float tensor with an exact shape
+    int get_f32(const std::string& name, std::initializer_list<int64_t> shape, const float** out) const {
+        const empose_tensor* e = find(name);
+        if (!e) { set_last_error("missing tensor '" + name + "'"); return EMPOSE_E_MISSING; }
+        if (e->dtype != EMPOSE_F32) { set_last_error("tensor '" + name + "' must be float32"); return EMPOSE_E_SHAPE; }
+        int64_t want = 1;
+        for (int64_t s : shape) want *= s;
+        if (numel(e) != want) {
+            set_last_error("tensor '" + name + "' has " + std::to_string(numel(e)) + " elements, expected " + std::to_string(want));
+            return EMPOSE_E_SHAPE;
+        }
+        *out = static_cast<const float*>(e->data);
+        return EMPOSE_OK;
+    }
+    int get_i32(const std::string& name, int64_t count, const int32_t** out) const {
+        const empose_tensor* e = find(name);
+        if (!e) { set_last_error("missing tensor '" + name + "'"); return EMPOSE_E_MISSING; }
+        if (e->dtype != EMPOSE_I32) { set_last_error("tensor '" + name + "' must be int32"); return EMPOSE_E_SHAPE; }
+        if (count >= 0 && numel(e) != count) { set_last_error("tensor '" + name + "' has the wrong size"); return EMPOSE_E_SHAPE; }
+        *out = static_cast<const int32_t*>(e->data);
+        return EMPOSE_OK;
+    }
+};
+
+// ---- device memory ------------------------------------------------------------------------------
+struct Arena {
+    std::vector<void*> ptrs;
+    ~Arena() { for (void* p : ptrs) cudaFree(p); }
+    int alloc(size_t bytes, void** out, bool zero = false) {
+        void* p = nullptr;
+        if (bytes == 0) bytes = 16;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            set_last_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+            return EMPOSE_E_NOMEM;
+        }
+        ptrs.push_back(p);
+        if (zero) EMPOSE_CUDA_TRY(cudaMemset(p, 0, bytes));
+        *out = p;
+        return EMPOSE_OK;
+    }
+    template <typename T> int alloc_n(size_t count, T** out, bool zero = false) {
+        void* p;
+        EMPOSE_TRY(alloc(count * sizeof(T), &p, zero));
+        *out = static_cast<T*>(p);
+        return EMPOSE_OK;
+    }
+    template <typename T> int upload(const std::vector<T>& h, T** out) {
+        EMPOSE_TRY(alloc_n<T>(h.size(), out));
+        if (!h.empty()) EMPOSE_CUDA_TRY(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return EMPOSE_OK;
+    }
+};
+
+// ---- packed weights -----------------------------------------------------------------------------
+struct PackedMatrix {
+    float* w = nullptr;       // device [n_pad][ld]
+    float* bias = nullptr;    // device [n_pad] or null
+    int n = 0, n_pad = 0, tile_n = 0, n_tiles = 0;
+    int kseg[2] = {0, 0};     // real K of each segment
+    int koff[2] = {0, 0};     // column where the segment starts in w
+    int64_t ld = 0;
+    int has_act = 0;
+    float alpha = 0.0f;
+};
+
+void choose_tiles(int n, int granule, PackedMatrix* pm) {
+    const int n16 = round_up(n, granule);
+    pm->n = n;
+    pm->n_tiles = ceil_div(n16, kMaxTileN);
+    pm->tile_n = round_up(ceil_div(n16, pm->n_tiles), granule);
+    pm->n_pad = pm->tile_n * pm->n_tiles;
+}
+
+// rows: function giving source row r (0..n-1) as (pointer to K0 floats, pointer to K1 floats) plus scale/bias
+struct RowSource {
+    const float* w0; const float* w1; double scale; double bias;
+};
+
+template <typename F>
+int pack_matrix(Arena& arena, int n, int k0, int k1, int granule, bool round, bool with_bias, F row_of, PackedMatrix* pm) {
+    choose_tiles(n, granule, pm);
+    pm->kseg[0] = k0; pm->kseg[1] = k1;
+    pm->koff[0] = 0; pm->koff[1] = round_up(k0, kChunkK);
+    pm->ld = round_up(k0, kChunkK) + (k1 > 0 ? round_up(k1, kChunkK) : 0);
+    std::vector<float> hw((size_t)pm->n_pad * pm->ld, 0.0f), hb((size_t)pm->n_pad, 0.0f);
+    for (int r = 0; r < n; ++r) {
+        RowSource src = row_of(r);
+        float* dst = &hw[(size_t)r * pm->ld];
+        for (int k = 0; k < k0; ++k) dst[k] = (float)(src.scale * (double)src.w0[k]);
+        for (int k = 0; k < k1; ++k) dst[pm->koff[1] + k] = (float)(src.scale * (double)src.w1[k]);
+        if (round) for (int64_t k = 0; k < pm->ld; ++k) dst[k] = host_round_tf32(dst[k]);
+        hb[r] = (float)src.bias;
+    }
+    EMPOSE_TRY(arena.upload(hw, &pm->w));
+    if (with_bias) EMPOSE_TRY(arena.upload(hb, &pm->bias));
+    return EMPOSE_OK;
+}
+
+struct MlpPacked { std::vector<PackedMatrix> layers; };   // input, 2*blocks hidden, output
+
+// nn.Linear (+ BatchNorm1d in eval mode folded in double) (+ PReLU slope) -> PackedMatrix
+int pack_linear(Arena& arena, const TensorTable& tt, const std::string& lin, const std::string& bn,
+                const std::string& prelu, int n_out, int n_in, bool round, PackedMatrix* pm) {
+    const float *w, *b, *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
+    EMPOSE_TRY(tt.get_f32(lin + ".weight", {n_out, n_in}, &w));
+    EMPOSE_TRY(tt.get_f32(lin + ".bias", {n_out}, &b));
+    if (!bn.empty()) {
+        EMPOSE_TRY(tt.get_f32(bn + ".weight", {n_out}, &g));
+        EMPOSE_TRY(tt.get_f32(bn + ".bias", {n_out}, &be));
+        EMPOSE_TRY(tt.get_f32(bn + ".running_mean", {n_out}, &mu));
+        EMPOSE_TRY(tt.get_f32(bn + ".running_var", {n_out}, &var));
+    }
+    EMPOSE_TRY(pack_matrix(arena, n_out, n_in, 0, 16, round, true, [&](int r) {
+        RowSource s{w + (size_t)r * n_in, nullptr, 1.0, (double)b[r]};
+        if (g) {   // y = gamma (Wx + b - mean) / sqrt(var + eps) + beta   (eps = 1e-5, torch default used by layers.py:26,57)
+            const double sc = (double)g[r] / std::sqrt((double)var[r] + 1e-5);
+            s.scale = sc;
+            s.bias = ((double)b[r] - (double)mu[r]) * sc + (double)be[r];
+        }
+        return s;
+    }, pm));
+    if (!prelu.empty()) {
+        const float* a;
+        EMPOSE_TRY(tt.get_f32(prelu + ".weight", {1}, &a));
+        pm->has_act = 1;
+        pm->alpha = a[0];
+    }
+    return EMPOSE_OK;
+}
+
+// MLP of empose/nn/layers.py:46-77 with the reference's state-dict key layout
+int pack_mlp(Arena& arena, const TensorTable& tt, const std::string& prefix, int n_in, int n_out, int hidden, int blocks,
+             bool bn, bool round, MlpPacked* out) {
+    out->layers.clear();
+    out->layers.resize(2 + 2 * blocks);
+    EMPOSE_TRY(pack_linear(arena, tt, prefix + ".input_to_hidden", bn ? prefix + ".batch_norm" : "", prefix + ".activation_fn",
+                           hidden, n_in, round, &out->layers[0]));
+    const int stride = bn ? 4 : 3;
+    for (int b = 0; b < blocks; ++b)
+        for (int l = 0; l < 2; ++l) {
+            const std::string base = prefix + ".hidden_layers." + std::to_string(b) + ".layers.";
+            EMPOSE_TRY(pack_linear(arena, tt, base + std::to_string(l * stride), bn ? base + std::to_string(l * stride + 1) : "",
+                                   base + std::to_string(l * stride + (bn ? 2 : 1)), hidden, hidden, round,
+                                   &out->layers[1 + 2 * b + l]));
+        }
+    EMPOSE_TRY(pack_linear(arena, tt, prefix + ".hidden_to_output", "", "", n_out, hidden, round, &out->layers.back()));
+    return EMPOSE_OK;
+}
+
+// ---- execution plan -------------------------------------------------------------------------------
+struct JobRange { int begin = 0, count = 0, per_item = 1; };
+
+struct MapKey {
+    const void* ptr; int64_t stride; int k; int64_t rows; int box;
+    bool operator<(const MapKey& o) const {
+        return std::tie(ptr, stride, k, rows, box) < std::tie(o.ptr, o.stride, o.k, o.rows, o.box);
+    }
+};
+
+struct ASrc { const float* ptr = nullptr; int64_t stride = 0; int k = 0; int64_t rows = 0; };
+
+struct JobBook {        // jobs + tensor maps of one plan
+    bool use_tc = false;
+    std::vector<GemmJob> jobs;
+    std::vector<uint8_t> maps;     // kTensorMapBytes each
+    std::map<MapKey, int> map_index;
+    GemmJob* d_jobs = nullptr;
+    void* d_maps = nullptr;
+
+    int get_map(const float* ptr, int64_t stride, int k, int64_t rows, int box, int* out) {
+        *out = -1;
+        if (!use_tc) return EMPOSE_OK;
+        MapKey key{ptr, stride, k, rows, box};
+        auto it = map_index.find(key);
+        if (it != map_index.end()) { *out = it->second; return EMPOSE_OK; }
+        const int idx = (int)(maps.size() / kTensorMapBytes);
+        maps.resize(maps.size() + kTensorMapBytes);
+        EMPOSE_TRY(tc_encode_map(&maps[(size_t)idx * kTensorMapBytes], ptr, stride, k, rows, box));
+        map_index[key] = idx;
+        *out = idx;
+        return EMPOSE_OK;
+    }
+
+    // appends one job per N tile of `W`; `proto` carries the epilogue fields (n_begin/n_count/maps are filled here)
+    int add(const PackedMatrix& W, const ASrc& a0, const ASrc& a1, GemmJob proto, int m_rows, int dep, JobRange* range) {
+        if (range->count == 0) range->begin = (int)jobs.size();
+        for (int t = 0; t < W.n_tiles; ++t) {
+            GemmJob j = proto;
+            j.a_ptr[0] = a0.ptr; j.a_stride[0] = a0.stride; j.a_k[0] = a0.k;
+            j.a_ptr[1] = a1.ptr; j.a_stride[1] = a1.stride; j.a_k[1] = a1.k;
+            EMPOSE_TRY(get_map(a0.ptr, a0.stride, a0.k, a0.rows, kTileM, &j.a_map[0]));
+            j.a_map[1] = -1;
+            if (a1.k > 0) EMPOSE_TRY(get_map(a1.ptr, a1.stride, a1.k, a1.rows, kTileM, &j.a_map[1]));
+            j.w_ptr = W.w; j.w_ld = W.ld; j.w_koff[0] = W.koff[0]; j.w_koff[1] = W.koff[1];
+            EMPOSE_TRY(get_map(W.w, W.ld, (int)W.ld, W.n_pad, W.tile_n, &j.w_map));
+            j.n_begin = t * W.tile_n;
+            j.n_count = W.tile_n;
+            j.m_rows = m_rows;
+            j.dep = dep;
+            j.bias = W.bias;
+            jobs.push_back(j);
+            ++range->count;
+        }
+        return EMPOSE_OK;
+    }
+
+    int finalize(Arena& arena) {
+        EMPOSE_TRY(arena.upload(jobs, &d_jobs));
+        if (use_tc) {
+            void* p;
+            EMPOSE_TRY(arena.alloc(maps.size(), &p));
+            EMPOSE_CUDA_TRY(cudaMemcpy(p, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+            d_maps = p;
+        }
+        return EMPOSE_OK;
+    }
+};
+
+GemmJob linear_proto(const PackedMatrix& W, bool round, float* out, int64_t out_stride, int n_valid) {
+    GemmJob j;
+    memset(&j, 0, sizeof(j));
+    j.epi = EPI_LINEAR;
+    j.round_out = round ? 1 : 0;
+    j.has_act = W.has_act;
+    j.prelu_alpha = W.alpha;
+    j.n_valid = n_valid;
+    j.out = out;
+    j.out_stride = out_stride;
+    j.split = 1 << 30;
+    j.frames_per_window = 1;
+    return j;
+}
+
+struct Plan {
+    int B = 0, F = 0, R = 0;
+    Arena arena;
+    JobBook book;
+    // workspace
+    float *meas = nullptr, *xin = nullptr, *xiter = nullptr, *coef = nullptr;
+    float *theta = nullptr, *beta = nullptr, *dtheta = nullptr, *dbeta = nullptr;
+    float *pf = nullptr, *vpoff = nullptr, *dvp = nullptr, *dpf = nullptr, *gth_part = nullptr, *gbeta = nullptr;
+    float *joints = nullptr, *spos = nullptr, *sori = nullptr;
+    float *off_r = nullptr, *off_t = nullptr;
+    int32_t* seq_len = nullptr;
+    float* act[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pose|shape][ping-pong]
+    std::vector<float*> hseq, cstate, hinit;
+    // staging for the host-buffer entry point
+    float *in_pos = nullptr, *in_ori = nullptr, *in_masks = nullptr, *io_state = nullptr;
+    float *in_off_r = nullptr, *in_off_t = nullptr;
+    int32_t* in_len = nullptr;
+    float *o_pose = nullptr, *o_shape = nullptr, *o_joints = nullptr;
+    float* o_hist[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // job ranges
+    std::vector<JobRange> lstm_diag;
+    JobRange heads, init_chain, iter_chain, pb, pbt;
+};
+
+}  // namespace
+}  // namespace empose
+
+using namespace empose;
+
+struct empose_ief {
+    empose_ief_config cfg;
+    int num_sms = 148;
+    int in_size = 0, iter_in = 0, n_pos = 0;
+    bool round = true;         // TF32 mode
+    Arena arena;
+    SubModel sub;
+    ResidualSpec spec;
+    int slot_of_sensor[kSensors];
+    std::vector<PackedMatrix> lstm;
+    PackedMatrix heads;
+    MlpPacked pose_init, shape_init, pose_iter, shape_iter;
+    PackedMatrix pb, pbt;
+    std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+    std::map<int, std::unique_ptr<Plan>> project_plans;
+    int64_t last_launches = 0;
+};
+
+namespace empose {
+namespace {
+
+int run_jobs(empose_ief* ctx, Plan& pl, const JobRange& r, int m_tiles, cudaStream_t s) {
+    if (r.count == 0) return EMPOSE_OK;
+    if (ctx->round) {
+        ++ctx->last_launches;
+        return tc_launch(pl.book.d_jobs, pl.book.d_maps, r.begin, r.count, r.per_item, m_tiles, ctx->num_sms, s);
+    }
+    return simt_launch(pl.book.d_jobs, pl.book.jobs.data(), r.begin, r.count, m_tiles, s, &ctx->last_launches);
+}
+
+// two interleaved MLP chains (pose, shape) reading the same input X
+int build_mlp_pair(empose_ief* ctx, Plan& pl, const MlpPacked& mp, const MlpPacked& ms, const float* X, int64_t x_stride,
+                   int x_k, JobRange* range) {
+    const int R = pl.R, hidden = ctx->cfg.hidden_size;
+    const int nl = (int)mp.layers.size();
+    const MlpPacked* nets[2] = {&mp, &ms};
+    int last_job[2] = {-1, -1};          // chain-local index of the last job of the previous layer
+    float* finals[2] = {pl.dtheta, pl.dbeta};
+    const int final_n[2] = {kPoseDim, kBetas};
+    for (int l = 0; l < nl; ++l)
+        for (int c = 0; c < 2; ++c) {
+            const PackedMatrix& W = nets[c]->layers[l];
+            ASrc a0, none;
+            if (l == 0) a0 = ASrc{X, x_stride, x_k, R};
+            else a0 = ASrc{pl.act[c][(l - 1) & 1], hidden, hidden, R};
+            GemmJob proto;
+            if (l == nl - 1) {
+                proto = linear_proto(W, false, finals[c], final_n[c], final_n[c]);
+            } else {
+                proto = linear_proto(W, ctx->round, pl.act[c][l & 1], hidden, hidden);
+                if (ctx->cfg.skip_connections && l >= 2 && (l % 2) == 0) {   // end of a LinearLayers block
+                    proto.res = pl.act[c][l & 1];                            // block input lives in the buffer being overwritten
+                    proto.res_stride = hidden;
+                }
+            }
+            EMPOSE_TRY(pl.book.add(W, a0, none, proto, R, last_job[c], range));
+            last_job[c] = range->count - 1;
+        }
+    range->per_item = range->count;
+    return EMPOSE_OK;
+}
+
+int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
+    auto key = std::make_pair(B, F);
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) { *out = it->second.get(); return EMPOSE_OK; }
+    if (ctx->plans.size() >= 4) ctx->plans.clear();      // bound the workspace kept alive
+    std::unique_ptr<Plan> plp(new Plan());
+    Plan& pl = *plp;
+    const empose_ief_config& cfg = ctx->cfg;
+    pl.B = B; pl.F = F; pl.R = B * F;
+    const int R = pl.R, hidden = cfg.hidden_size, H = cfg.rnn_hidden_size, L = cfg.rnn_num_layers, vp = ctx->sub.vp_dim;
+    pl.book.use_tc = ctx->round;
+    Arena& A = pl.arena;
+    const size_t Rz = (size_t)R;
+    EMPOSE_TRY(A.alloc_n(Rz * 144, &pl.meas));
+    EMPOSE_TRY(A.alloc_n(Rz * ctx->in_size, &pl.xin));
+    EMPOSE_TRY(A.alloc_n(Rz * ctx->iter_in, &pl.xiter, true));
+    EMPOSE_TRY(A.alloc_n(Rz, &pl.coef));
+    EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.theta));
+    EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.beta));
+    EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.dtheta));
+    EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.dbeta));
+    EMPOSE_TRY(A.alloc_n(Rz * kPoseFeatPad, &pl.pf, true));
+    EMPOSE_TRY(A.alloc_n(Rz * vp, &pl.vpoff));
+    EMPOSE_TRY(A.alloc_n(Rz * vp, &pl.dvp));
+    EMPOSE_TRY(A.alloc_n(Rz * kPoseFeatPad, &pl.dpf));
+    EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.gth_part));
+    EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.gbeta));
+    EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.joints));
+    EMPOSE_TRY(A.alloc_n(Rz * 36, &pl.spos));
+    EMPOSE_TRY(A.alloc_n(Rz * 108, &pl.sori));
+    EMPOSE_TRY(A.alloc_n((size_t)B * 108, &pl.off_r));
+    EMPOSE_TRY(A.alloc_n((size_t)B * 36, &pl.off_t));
+    EMPOSE_TRY(A.alloc_n((size_t)B, &pl.seq_len));
+    for (int c = 0; c < 2; ++c)
+        for (int q = 0; q < 2; ++q) EMPOSE_TRY(A.alloc_n(Rz * hidden, &pl.act[c][q]));
+
+    const int m_rows_R = R;
+    if (cfg.rnn_init) {
+        pl.hseq.resize(L); pl.cstate.resize(L); pl.hinit.resize(L);
+        for (int l = 0; l < L; ++l) {
+            EMPOSE_TRY(A.alloc_n(Rz * H, &pl.hseq[l]));
+            EMPOSE_TRY(A.alloc_n((size_t)B * H, &pl.cstate[l], true));
+            EMPOSE_TRY(A.alloc_n((size_t)B * H, &pl.hinit[l], true));
+        }
+        pl.lstm_diag.resize(F + L - 1);
+        for (int d = 0; d < F + L - 1; ++d)
+            for (int l = 0; l < L; ++l) {
+                const int t = d - l;
+                if (t < 0 || t >= F) continue;
+                ASrc a0 = (t == 0) ? ASrc{pl.hinit[l], H, H, B} : ASrc{pl.hseq[l] + (size_t)(t - 1) * H, (int64_t)F * H, H, B};
+                ASrc a1 = (l == 0) ? ASrc{pl.xin + (size_t)t * ctx->in_size, (int64_t)F * ctx->in_size, ctx->in_size, B}
+                                   : ASrc{pl.hseq[l - 1] + (size_t)t * H, (int64_t)F * H, H, B};
+                GemmJob proto;
+                memset(&proto, 0, sizeof(proto));
+                proto.epi = EPI_LSTM;
+                proto.round_out = ctx->round ? 1 : 0;
+                proto.out = pl.hseq[l] + (size_t)t * H;
+                proto.out_stride = (int64_t)F * H;
+                proto.c_state = pl.cstate[l];
+                proto.h_prev = a0.ptr;
+                proto.h_prev_stride = a0.stride;
+                proto.t = t;
+                proto.hidden = H;
+                proto.seq_len = pl.seq_len;
+                proto.frames_per_window = 1;
+                proto.split = 1 << 30;
+                EMPOSE_TRY(pl.book.add(ctx->lstm[l], a0, a1, proto, B, -1, &pl.lstm_diag[d]));
+            }
+        // heads: theta0 | beta0 from the (masked) last-layer sequence
+        GemmJob proto = linear_proto(ctx->heads, false, pl.dtheta, kPoseDim, kPoseDim + kBetas);
+        proto.split = kPoseDim;
+        proto.out2 = pl.dbeta;
+        proto.out2_stride = kBetas;
+        proto.mask_rows = 1;
+        proto.seq_len = pl.seq_len;
+        proto.frames_per_window = F;
+        EMPOSE_TRY(pl.book.add(ctx->heads, ASrc{pl.hseq[L - 1], H, H, R}, ASrc{}, proto, m_rows_R, -1, &pl.heads));
+    } else {
+        EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_init, ctx->shape_init, pl.xin, ctx->in_size, ctx->in_size, &pl.init_chain));
+    }
+    EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_iter, ctx->shape_iter, pl.xiter, ctx->iter_in, ctx->iter_in, &pl.iter_chain));
+    {
+        GemmJob proto = linear_proto(ctx->pb, false, pl.vpoff, vp, vp);
+        EMPOSE_TRY(pl.book.add(ctx->pb, ASrc{pl.pf, kPoseFeatPad, kPoseFeatPad, R}, ASrc{}, proto, m_rows_R, -1, &pl.pb));
+        GemmJob proto_t = linear_proto(ctx->pbt, false, pl.dpf, kPoseFeatPad, kPoseFeatPad);
+        EMPOSE_TRY(pl.book.add(ctx->pbt, ASrc{pl.dvp, vp, vp, R}, ASrc{}, proto_t, m_rows_R, -1, &pl.pbt));
+    }
+    EMPOSE_TRY(pl.book.finalize(A));
+    *out = plp.get();
+    ctx->plans[key] = std::move(plp);
+    return EMPOSE_OK;
+}
+
+int project_plan(empose_ief* ctx, int R, Plan** out) {
+    auto it = ctx->project_plans.find(R);
+    if (it != ctx->project_plans.end()) { *out = it->second.get(); return EMPOSE_OK; }
+    if (ctx->project_plans.size() >= 4) ctx->project_plans.clear();
+    std::unique_ptr<Plan> plp(new Plan());
+    Plan& pl = *plp;
+    pl.R = R; pl.B = R; pl.F = 1;
+    pl.book.use_tc = ctx->round;
+    const int vp = ctx->sub.vp_dim;
+    EMPOSE_TRY(pl.arena.alloc_n((size_t)R * kPoseFeatPad, &pl.pf, true));
+    EMPOSE_TRY(pl.arena.alloc_n((size_t)R * vp, &pl.vpoff));
+    GemmJob proto = linear_proto(ctx->pb, false, pl.vpoff, vp, vp);
+    EMPOSE_TRY(pl.book.add(ctx->pb, ASrc{pl.pf, kPoseFeatPad, kPoseFeatPad, R}, ASrc{}, proto, R, -1, &pl.pb));
+    EMPOSE_TRY(pl.book.finalize(pl.arena));
+    *out = plp.get();
+    ctx->project_plans[R] = std::move(plp);
+    return EMPOSE_OK;
+}
+
+int check_config(const empose_ief_config& c) {
+    auto bad = [](const std::string& m) { set_last_error(m); return EMPOSE_E_ARG; };
+    if (c.n_markers != 6 && c.n_markers != 12) return bad("n_markers must be 6 or 12 (reference models.py:385)");
+    if (!c.use_marker_pos && !c.use_marker_ori) return bad("at least one of use_marker_pos / use_marker_ori is required");
+    if (c.num_iterations < 0 || c.num_iterations > 64) return bad("num_iterations out of range");
+    if (c.hidden_size < 16 || c.hidden_size % 16) return bad("hidden_size must be a positive multiple of 16");
+    if (c.num_layers < 0 || c.num_layers > 8) return bad("num_layers out of range");
+    if (c.rnn_init) {
+        const int g = 4 * c.rnn_hidden_size;
+        if (c.rnn_hidden_size < 8 || (g % 32) || (g > kMaxTileN && g % kMaxTileN))
+            return bad("rnn_hidden_size must make 4H a multiple of 32 and, above 256, of 256");
+        if (c.rnn_num_layers < 1 || c.rnn_num_layers > 4) return bad("rnn_num_layers must be 1..4");
+    }
+    if (c.precision != EMPOSE_PRECISION_TF32 && c.precision != EMPOSE_PRECISION_FP32) return bad("unknown precision");
+    return EMPOSE_OK;
+}
+
+int upload_submodel(empose_ief* ctx, const TensorTable& tt) {
+    const int32_t* dims;
+    EMPOSE_TRY(tt.get_i32("sub.dims", 6, &dims));   // n_verts, vp_dim, n_faces, max_degree, n_skin, n_sensors
+    SubModel& m = ctx->sub;
+    m.n_verts = dims[0]; m.vp_dim = dims[1]; m.n_faces = dims[2]; m.max_degree = dims[3]; m.n_skin = dims[4];
+    if (dims[5] != kSensors) { set_last_error("exactly 12 sensors are supported"); return EMPOSE_E_ARG; }
+    if (m.vp_dim > kMaxVp || m.vp_dim % 16 || m.n_verts * 3 > m.vp_dim || m.max_degree > kMaxDegree) {
+        set_last_error("sub-model dimensions out of range");
+        return EMPOSE_E_ARG;
+    }
+    auto up_f = [&](const char* name, std::initializer_list<int64_t> shape, const float** dst) -> int {
+        const float* h;
+        EMPOSE_TRY(tt.get_f32(name, shape, &h));
+        int64_t n = 1;
+        for (int64_t s : shape) n *= s;
+        float* d;
+        EMPOSE_TRY(ctx->arena.upload(std::vector<float>(h, h + n), &d));
+        *dst = d;
+        return EMPOSE_OK;
+    };
+    auto up_i = [&](const char* name, int64_t count, const int** dst, int lo, int hi) -> int {
+        const int32_t* h;
+        EMPOSE_TRY(tt.get_i32(name, count, &h));
+        const empose_tensor* e = tt.find(name);
+        const int64_t n = tt.numel(e);
+        for (int64_t i = 0; i < n; ++i)
+            if (h[i] < lo || h[i] >= hi) { set_last_error(std::string("index out of range in '") + name + "'"); return EMPOSE_E_ARG; }
+        int* d;
+        EMPOSE_TRY(ctx->arena.upload(std::vector<int>(h, h + n), &d));
+        *dst = d;
+        return EMPOSE_OK;
+    };
+    EMPOSE_TRY(up_f("sub.v_template", {m.vp_dim}, &m.v_template));
+    EMPOSE_TRY(up_f("sub.shapedirs", {kBetas, m.vp_dim}, &m.shapedirs));
+    EMPOSE_TRY(up_f("sub.j0", {kPoseDim}, &m.j0));
+    EMPOSE_TRY(up_f("sub.jdirs", {kBetas, kPoseDim}, &m.jdirs));
+    EMPOSE_TRY(up_f("sub.skin_weight", {m.n_verts, m.n_skin}, &m.skin_weight));
+    EMPOSE_TRY(up_i("sub.skin_joint", (int64_t)m.n_verts * m.n_skin, &m.skin_joint, 0, kJoints));
+    const int32_t* jt_ptr;
+    EMPOSE_TRY(tt.get_i32("sub.jt_ptr", kJoints + 1, &jt_ptr));
+    const int n_jt = jt_ptr[kJoints];
+    EMPOSE_TRY(up_i("sub.jt_ptr", kJoints + 1, &m.jt_ptr, 0, n_jt + 1));
+    EMPOSE_TRY(up_i("sub.jt_vert", n_jt, &m.jt_vert, 0, m.n_verts));
+    EMPOSE_TRY(up_f("sub.jt_weight", {n_jt}, &m.jt_weight));
+    EMPOSE_TRY(up_i("sub.parents", kJoints, &m.parents, -1, kJoints));
+    EMPOSE_TRY(up_i("sub.faces", (int64_t)m.n_faces * 3, &m.faces, 0, m.n_verts));
+    EMPOSE_TRY(up_i("sub.sensor_vert", kSensors, &m.sensor_vert, 0, m.n_verts));
+    EMPOSE_TRY(up_i("sub.helper_vert", kSensors, &m.helper_vert, 0, m.n_verts));
+    EMPOSE_TRY(up_i("sub.sensor_faces", (int64_t)kSensors * m.max_degree, &m.sensor_faces, -1, m.n_faces));
+    EMPOSE_TRY(up_i("sub.sensor_degree", kSensors, &m.sensor_degree, 1, m.max_degree + 1));
+
+    // pose-blend matrices: forward W[i][k] = P[k][i] (N = vp_dim, K = 189 -> 192), transposed W[k][i] = P[k][i]
+    const float* P;
+    EMPOSE_TRY(tt.get_f32("sub.posedirs", {kPoseFeat, m.vp_dim}, &P));
+    std::vector<float> col(kPoseFeat);
+    const int vp = m.vp_dim;
+    std::vector<float> pt((size_t)vp * kPoseFeat);
+    for (int i = 0; i < vp; ++i)
+        for (int k = 0; k < kPoseFeat; ++k) pt[(size_t)i * kPoseFeat + k] = P[(size_t)k * vp + i];
+    EMPOSE_TRY(pack_matrix(ctx->arena, vp, kPoseFeat, 0, 16, ctx->round, false,
+                           [&](int r) { return RowSource{&pt[(size_t)r * kPoseFeat], nullptr, 1.0, 0.0}; }, &ctx->pb));
+    EMPOSE_TRY(pack_matrix(ctx->arena, kPoseFeat, vp, 0, 16, ctx->round, false,
+                           [&](int r) { return RowSource{P + (size_t)r * vp, nullptr, 1.0, 0.0}; }, &ctx->pbt));
+    return EMPOSE_OK;
+}
+
+int pack_lstm(empose_ief* ctx, const TensorTable& tt) {
+    const int H = ctx->cfg.rnn_hidden_size, L = ctx->cfg.rnn_num_layers;
+    ctx->lstm.resize(L);
+    for (int l = 0; l < L; ++l) {
+        const int n_in = l == 0 ? ctx->in_size : H;
+        const std::string sfx = "_l" + std::to_string(l);
+        const float *wih, *whh, *bih, *bhh;
+        EMPOSE_TRY(tt.get_f32("rnn.lstm.weight_ih" + sfx, {4 * H, n_in}, &wih));
+        EMPOSE_TRY(tt.get_f32("rnn.lstm.weight_hh" + sfx, {4 * H, H}, &whh));
+        EMPOSE_TRY(tt.get_f32("rnn.lstm.bias_ih" + sfx, {4 * H}, &bih));
+        EMPOSE_TRY(tt.get_f32("rnn.lstm.bias_hh" + sfx, {4 * H}, &bhh));
+        // packed row n <- torch row gate*H + unit (gate order i,f,g,o; layers.py:114 / torch.nn.LSTM layout)
+        EMPOSE_TRY(pack_matrix(ctx->arena, 4 * H, H, n_in, 32, ctx->round, true, [&](int n) {
+            const int src = lstm_gate_of_packed(n) * H + lstm_unit_of_packed(n);
+            return RowSource{whh + (size_t)src * H, wih + (size_t)src * n_in, 1.0, (double)bih[src] + (double)bhh[src]};
+        }, &ctx->lstm[l]));
+    }
+    // heads (models.py:429-430): rows 0..65 pose_net_init, 66..75 shape_net_init
+    const float *wp, *bp, *ws, *bs;
+    EMPOSE_TRY(tt.get_f32("pose_net_init.weight", {kPoseDim, H}, &wp));
+    EMPOSE_TRY(tt.get_f32("pose_net_init.bias", {kPoseDim}, &bp));
+    EMPOSE_TRY(tt.get_f32("shape_net_init.weight", {kBetas, H}, &ws));
+    EMPOSE_TRY(tt.get_f32("shape_net_init.bias", {kBetas}, &bs));
+    EMPOSE_TRY(pack_matrix(ctx->arena, kPoseDim + kBetas, H, 0, 16, ctx->round, true, [&](int r) {
+        if (r < kPoseDim) return RowSource{wp + (size_t)r * H, nullptr, 1.0, (double)bp[r]};
+        return RowSource{ws + (size_t)(r - kPoseDim) * H, nullptr, 1.0, (double)bs[r - kPoseDim]};
+    }, &ctx->heads));
+    return EMPOSE_OK;
+}
+
+int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const float* marker_oris, const float* offset_r,
+                   const float* offset_t, const int32_t* seq_lengths, const float* marker_masks, float* lstm_state,
+                   int is_new_sequence, float* pose_hat, float* shape_hat, float* joints_hat,
+                   const empose_ief_history* hist, cudaStream_t s) {
+    const empose_ief_config& cfg = ctx->cfg;
+    const int B = pl.B, F = pl.F, R = pl.R, H = cfg.rnn_hidden_size, L = cfg.rnn_num_layers, N = cfg.num_iterations;
+    const int mt_R = ceil_div(R, kTileM), mt_B = ceil_div(B, kTileM);
+    const int rnd = ctx->round ? 1 : 0;
+    ctx->last_launches = 0;
+    auto count = [&](int rc) { ++ctx->last_launches; return rc; };
+
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.seq_len, seq_lengths, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.off_r, offset_r, (size_t)B * 108 * 4, cudaMemcpyDeviceToDevice, s));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.off_t, offset_t, (size_t)B * 36 * 4, cudaMemcpyDeviceToDevice, s));
+
+    PrepareParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.marker_pos = marker_pos; pp.marker_oris = marker_oris; pp.seq_len = pl.seq_len; pp.masks = marker_masks;
+    pp.R = R; pp.F = F;
+    for (int i = 0; i < kSensors; ++i) pp.slot_of_sensor[i] = ctx->slot_of_sensor[i];
+    pp.use_pos = cfg.use_marker_pos; pp.use_ori = cfg.use_marker_ori; pp.n_pos = ctx->n_pos;
+    pp.in_size = ctx->in_size; pp.iter_in = ctx->iter_in; pp.round_out = rnd;
+    pp.meas = pl.meas; pp.xin = pl.xin; pp.xiter = pl.xiter; pp.coef = pl.coef;
+    EMPOSE_TRY(count(launch_prepare(pp, s)));
+
+    if (cfg.rnn_init) {
+        const size_t st_bytes = (size_t)B * H * 4;
+        for (int l = 0; l < L; ++l) {
+            if (lstm_state && !is_new_sequence) {
+                EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.hinit[l], lstm_state + (size_t)l * B * H, st_bytes, cudaMemcpyDeviceToDevice, s));
+                EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.cstate[l], lstm_state + (size_t)(L + l) * B * H, st_bytes, cudaMemcpyDeviceToDevice, s));
+            } else {
+                EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.hinit[l], 0, st_bytes, s));
+                EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.cstate[l], 0, st_bytes, s));
+            }
+        }
+        for (const JobRange& d : pl.lstm_diag) EMPOSE_TRY(run_jobs(ctx, pl, d, mt_B, s));
+        EMPOSE_TRY(run_jobs(ctx, pl, pl.heads, mt_R, s));
+        if (lstm_state)
+            for (int l = 0; l < L; ++l) {
+                EMPOSE_TRY(count(launch_gather_last(pl.hseq[l], lstm_state + (size_t)l * B * H, B, F, H, s)));
+                EMPOSE_CUDA_TRY(cudaMemcpyAsync(lstm_state + (size_t)(L + l) * B * H, pl.cstate[l], st_bytes, cudaMemcpyDeviceToDevice, s));
+            }
+    } else {
+        EMPOSE_TRY(run_jobs(ctx, pl, pl.init_chain, mt_R, s));
+    }
+
+    for (int it = 0; it <= N; ++it) {
+        UpdateParams up;
+        memset(&up, 0, sizeof(up));
+        up.theta = pl.theta; up.beta = pl.beta; up.dtheta = pl.dtheta; up.dbeta = pl.dbeta;
+        up.step = cfg.step_size; up.first = (it == 0); up.average_shape = cfg.average_shape;
+        up.B = B; up.F = F; up.round_out = rnd;
+        up.xiter = pl.xiter; up.in_size = ctx->in_size; up.iter_in = ctx->iter_in; up.pf = pl.pf;
+        if (hist && hist->pose) up.hist_pose = hist->pose + (size_t)it * R * kPoseDim;
+        if (hist && hist->shape) up.hist_shape = hist->shape + (size_t)it * R * kBetas;
+        EMPOSE_TRY(count(launch_update(up, s)));
+        EMPOSE_TRY(run_jobs(ctx, pl, pl.pb, mt_R, s));
+
+        const bool grad = (it < N) && cfg.use_gradient;
+        MainParams mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.sub = ctx->sub; mp.spec = ctx->spec;
+        mp.theta = pl.theta; mp.beta = pl.beta; mp.vp_off = pl.vpoff;
+        mp.offset_r = pl.off_r; mp.offset_t = pl.off_t; mp.rows_per_offset = F;
+        mp.meas = pl.meas; mp.coef = pl.coef; mp.R = R; mp.want_grad = grad; mp.round_out = rnd;
+        mp.sensor_pos = (hist && hist->markers) ? hist->markers + (size_t)it * R * 36 : nullptr;
+        mp.sensor_ori = (hist && hist->markers_ori) ? hist->markers_ori + (size_t)it * R * 108 : nullptr;
+        mp.joints = (hist && hist->joints) ? hist->joints + (size_t)it * R * kPoseDim : nullptr;
+        if (it == N && !mp.joints) mp.joints = pl.joints;
+        mp.dvp = pl.dvp; mp.gtheta_part = pl.gth_part; mp.gbeta = pl.gbeta;
+        EMPOSE_TRY(count(launch_main(mp, s)));
+        if (it == N) {
+            if (joints_hat)
+                EMPOSE_CUDA_TRY(cudaMemcpyAsync(joints_hat, mp.joints, (size_t)R * kPoseDim * 4, cudaMemcpyDeviceToDevice, s));
+            break;
+        }
+        if (grad) {
+            EMPOSE_TRY(run_jobs(ctx, pl, pl.pbt, mt_R, s));
+            PostParams po;
+            memset(&po, 0, sizeof(po));
+            po.theta = pl.theta; po.dpf = pl.dpf; po.gtheta_part = pl.gth_part; po.gbeta = pl.gbeta; po.coef = pl.coef;
+            po.R = R; po.round_out = rnd; po.xiter = pl.xiter; po.in_size = ctx->in_size; po.iter_in = ctx->iter_in;
+            EMPOSE_TRY(count(launch_post(po, s)));
+        }
+        EMPOSE_TRY(run_jobs(ctx, pl, pl.iter_chain, mt_R, s));
+    }
+    if (pose_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pose_hat, pl.theta, (size_t)R * kPoseDim * 4, cudaMemcpyDeviceToDevice, s));
+    if (shape_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(shape_hat, pl.beta, (size_t)R * kBetas * 4, cudaMemcpyDeviceToDevice, s));
+    return EMPOSE_OK;
+}
+
+int check_call(empose_ief* ctx, int B, int F) {
+    if (!ctx) { set_last_error("null context"); return EMPOSE_E_ARG; }
+    if (B < 1 || F < 1 || (int64_t)B * F > (int64_t)1 << 26) { set_last_error("B and F must be positive (and B*F <= 2^26)"); return EMPOSE_E_ARG; }
+    EMPOSE_CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return EMPOSE_OK;
+}
+
+}  // namespace
+}  // namespace empose
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+#pragma GCC visibility push(default)
+
+int empose_abi_version(void) { return EMPOSE_ABI_VERSION; }
+const char* empose_last_error(void) { return g_last_error.c_str(); }
+
+int empose_ief_create(const empose_ief_config* cfg, const empose_tensor* tensors, int32_t n_tensors, empose_ief** out) {
+    if (!cfg || !tensors || !out) { set_last_error("null argument"); return EMPOSE_E_ARG; }
+    *out = nullptr;
+    EMPOSE_TRY(check_config(*cfg));
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device available: empose_b200 has no CPU fallback");
+        return EMPOSE_E_CUDA;
+    }
+    EMPOSE_CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    EMPOSE_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        set_last_error("empose_b200 is built for sm_100a (B200) only; found compute capability " + std::to_string(prop.major) +
+                       "." + std::to_string(prop.minor));
+        return EMPOSE_E_CUDA;
+    }
+    std::unique_ptr<empose_ief> ctx(new empose_ief());
+    ctx->cfg = *cfg;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->round = cfg->precision == EMPOSE_PRECISION_TF32;
+    ctx->n_pos = cfg->use_marker_pos ? 3 * cfg->n_markers : 0;
+    ctx->in_size = ctx->n_pos + (cfg->use_marker_ori ? 9 * cfg->n_markers : 0);
+    ctx->iter_in = ctx->in_size + kPoseDim + kBetas + (cfg->use_gradient ? kPoseDim + kBetas : 0);
+    static const int kConfig6[6] = {0, 1, 2, 6, 7, 11};                     // reference configuration.py:89
+    for (int i = 0; i < kSensors; ++i) { ctx->slot_of_sensor[i] = cfg->n_markers == 12 ? i : -1; }
+    if (cfg->n_markers == 6) for (int i = 0; i < 6; ++i) ctx->slot_of_sensor[kConfig6[i]] = i;
+    ctx->spec.use_pos = cfg->use_marker_pos; ctx->spec.use_ori = cfg->use_marker_ori;
+    for (int i = 0; i < kSensors; ++i) ctx->spec.sensor_active[i] = ctx->slot_of_sensor[i] >= 0;
+
+    TensorTable tt{tensors, n_tensors};
+    EMPOSE_TRY(upload_submodel(ctx.get(), tt));
+    const bool bn = cfg->batch_norm != 0;
+    if (cfg->rnn_init) {
+        EMPOSE_TRY(pack_lstm(ctx.get(), tt));
+    } else {
+        EMPOSE_TRY(pack_mlp(ctx->arena, tt, "pose_net_init", ctx->in_size, kPoseDim, cfg->hidden_size, cfg->num_layers, bn, ctx->round, &ctx->pose_init));
+        EMPOSE_TRY(pack_mlp(ctx->arena, tt, "shape_net_init", ctx->in_size, kBetas, cfg->hidden_size, cfg->num_layers, bn, ctx->round, &ctx->shape_init));
+    }
+    EMPOSE_TRY(pack_mlp(ctx->arena, tt, "pose_net_iter", ctx->iter_in, kPoseDim, cfg->hidden_size, cfg->num_layers, bn, ctx->round, &ctx->pose_iter));
+    EMPOSE_TRY(pack_mlp(ctx->arena, tt, "shape_net_iter", ctx->iter_in, kBetas, cfg->hidden_size, cfg->num_layers, bn, ctx->round, &ctx->shape_iter));
+    *out = ctx.release();
+    return EMPOSE_OK;
+}
+
+void empose_ief_destroy(empose_ief* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    delete ctx;
+}
+
+int64_t empose_ief_last_launch_count(const empose_ief* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int empose_ief_forward(empose_ief* ctx, const float* marker_pos, const float* marker_oris, const float* offset_r,
+                       const float* offset_t, const int32_t* seq_lengths, const float* marker_masks, float* lstm_state,
+                       int32_t is_new_sequence, int32_t B, int32_t F, float* pose_hat, float* shape_hat, float* joints_hat,
+                       const empose_ief_history* history, void* stream) {
+    EMPOSE_TRY(check_call(ctx, B, F));
+    if (!marker_pos || !marker_oris || !offset_r || !offset_t || !seq_lengths) { set_last_error("null input"); return EMPOSE_E_ARG; }
+    Plan* pl;
+    EMPOSE_TRY(build_plan(ctx, B, F, &pl));
+    return forward_device(ctx, *pl, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks, lstm_state,
+                          is_new_sequence, pose_hat, shape_hat, joints_hat, history, static_cast<cudaStream_t>(stream));
+}
+
+int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const float* marker_oris, const float* offset_r,
+                            const float* offset_t, const int32_t* seq_lengths, const float* marker_masks, float* lstm_state,
+                            int32_t is_new_sequence, int32_t B, int32_t F, float* pose_hat, float* shape_hat,
+                            float* joints_hat, const empose_ief_history* history, void* stream) {
+    EMPOSE_TRY(check_call(ctx, B, F));
+    if (!marker_pos || !marker_oris || !offset_r || !offset_t || !seq_lengths) { set_last_error("null input"); return EMPOSE_E_ARG; }
+    Plan* plp;
+    EMPOSE_TRY(build_plan(ctx, B, F, &plp));
+    Plan& pl = *plp;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t R = (size_t)pl.R;
+    const int L = ctx->cfg.rnn_num_layers, H = ctx->cfg.rnn_hidden_size, N = ctx->cfg.num_iterations;
+    const size_t state_n = ctx->cfg.rnn_init ? (size_t)2 * L * B * H : 0;
+    if (!pl.in_pos) {
+        EMPOSE_TRY(pl.arena.alloc_n(R * 36, &pl.in_pos));
+        EMPOSE_TRY(pl.arena.alloc_n(R * 108, &pl.in_ori));
+        EMPOSE_TRY(pl.arena.alloc_n(R * 12, &pl.in_masks));
+        EMPOSE_TRY(pl.arena.alloc_n(state_n, &pl.io_state));
+        EMPOSE_TRY(pl.arena.alloc_n(R * kPoseDim, &pl.o_pose));
+        EMPOSE_TRY(pl.arena.alloc_n(R * kBetas, &pl.o_shape));
+        EMPOSE_TRY(pl.arena.alloc_n(R * kPoseDim, &pl.o_joints));
+        EMPOSE_TRY(pl.arena.alloc_n((size_t)B * 108, &pl.in_off_r));
+        EMPOSE_TRY(pl.arena.alloc_n((size_t)B * 36, &pl.in_off_t));
+        EMPOSE_TRY(pl.arena.alloc_n((size_t)B, &pl.in_len));
+    }
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_pos, marker_pos, R * 36 * 4, cudaMemcpyHostToDevice, s));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_ori, marker_oris, R * 108 * 4, cudaMemcpyHostToDevice, s));
+    if (marker_masks) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_masks, marker_masks, R * 12 * 4, cudaMemcpyHostToDevice, s));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_off_r, offset_r, (size_t)B * 108 * 4, cudaMemcpyHostToDevice, s));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_off_t, offset_t, (size_t)B * 36 * 4, cudaMemcpyHostToDevice, s));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_len, seq_lengths, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    if (lstm_state && state_n && !is_new_sequence)
+        EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.io_state, lstm_state, state_n * 4, cudaMemcpyHostToDevice, s));
+    empose_ief_history dh = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const size_t hist_dof[5] = {kPoseDim, kBetas, kPoseDim, 36, 108};
+    if (history) {
+        float* hp[5] = {history->pose, history->shape, history->joints, history->markers, history->markers_ori};
+        float** dp[5] = {&dh.pose, &dh.shape, &dh.joints, &dh.markers, &dh.markers_ori};
+        for (int i = 0; i < 5; ++i)
+            if (hp[i]) {
+                if (!pl.o_hist[i]) EMPOSE_TRY(pl.arena.alloc_n((size_t)(N + 1) * R * hist_dof[i], &pl.o_hist[i]));
+                *dp[i] = pl.o_hist[i];
+            }
+    }
+    int rc = forward_device(ctx, pl, pl.in_pos, pl.in_ori, pl.in_off_r, pl.in_off_t, pl.in_len, marker_masks ? pl.in_masks : nullptr,
+                            (lstm_state && state_n) ? pl.io_state : nullptr, is_new_sequence, pl.o_pose, pl.o_shape,
+                            pl.o_joints, history ? &dh : nullptr, s);
+    if (rc != EMPOSE_OK) return rc;
+    if (pose_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pose_hat, pl.o_pose, R * kPoseDim * 4, cudaMemcpyDeviceToHost, s));
+    if (shape_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(shape_hat, pl.o_shape, R * kBetas * 4, cudaMemcpyDeviceToHost, s));
+    if (joints_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(joints_hat, pl.o_joints, R * kPoseDim * 4, cudaMemcpyDeviceToHost, s));
+    if (lstm_state && state_n) EMPOSE_CUDA_TRY(cudaMemcpyAsync(lstm_state, pl.io_state, state_n * 4, cudaMemcpyDeviceToHost, s));
+    if (history) {
+        float* hp[5] = {history->pose, history->shape, history->joints, history->markers, history->markers_ori};
+        for (int i = 0; i < 5; ++i)
+            if (hp[i]) EMPOSE_CUDA_TRY(cudaMemcpyAsync(hp[i], pl.o_hist[i], (size_t)(N + 1) * R * hist_dof[i] * 4, cudaMemcpyDeviceToHost, s));
+    }
+    EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));
+    return EMPOSE_OK;
+}
+
+int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shapes, const float* offset_r,
+                          const float* offset_t, int32_t R, float* sensor_pos, float* sensor_ori, float* joints, void* stream) {
+    EMPOSE_TRY(check_call(ctx, R, 1));
+    if (!poses || !shapes || !offset_r || !offset_t) { set_last_error("null input"); return EMPOSE_E_ARG; }
+    Plan* pl;
+    EMPOSE_TRY(project_plan(ctx, R, &pl));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int rnd = ctx->round ? 1 : 0;
+    ctx->last_launches = 1;
+    EMPOSE_TRY(launch_pose_features(poses, pl->pf, R, rnd, s));
+    EMPOSE_TRY(run_jobs(ctx, *pl, pl->pb, ceil_div(R, kTileM), s));
+    MainParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.sub = ctx->sub; mp.spec = ctx->spec; mp.theta = poses; mp.beta = shapes; mp.vp_off = pl->vpoff;
+    mp.offset_r = offset_r; mp.offset_t = offset_t; mp.rows_per_offset = 1; mp.R = R; mp.want_grad = 0; mp.round_out = rnd;
+    mp.sensor_pos = sensor_pos; mp.sensor_ori = sensor_ori; mp.joints = joints;
+    ++ctx->last_launches;
+    return launch_main(mp, s);
+}
+
+int empose_gemm_selftest(int32_t precision, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                         float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream) {
+    if (!A || !W || !C || M < 1 || N < 1 || K < 1) { set_last_error("bad argument"); return EMPOSE_E_ARG; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    EMPOSE_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    EMPOSE_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    PackedMatrix pm;
+    choose_tiles(N, 16, &pm);
+    pm.w = const_cast<float*>(W); pm.bias = const_cast<float*>(bias);
+    pm.kseg[0] = K; pm.ld = ldw;
+    Arena arena;
+    JobBook book;
+    book.use_tc = precision == EMPOSE_PRECISION_TF32;
+    JobRange range;
+    GemmJob proto = linear_proto(pm, false, C, ldc, N);
+    // the W tensor map describes the caller's matrix directly: K extent K (zero fill beyond), N rows
+    for (int t = 0; t < pm.n_tiles; ++t) {
+        GemmJob j = proto;
+        j.a_ptr[0] = A; j.a_stride[0] = lda; j.a_k[0] = K;
+        EMPOSE_TRY(book.get_map(A, lda, K, M, kTileM, &j.a_map[0]));
+        j.a_map[1] = -1;
+        j.w_ptr = W; j.w_ld = ldw;
+        EMPOSE_TRY(book.get_map(W, ldw, K, N, pm.tile_n, &j.w_map));
+        j.n_begin = t * pm.tile_n; j.n_count = pm.tile_n; j.m_rows = M; j.dep = -1; j.bias = bias;
+        if (range.count == 0) range.begin = (int)book.jobs.size();
+        book.jobs.push_back(j);
+        ++range.count;
+    }
+    EMPOSE_TRY(book.finalize(arena));
+    int rc;
+    if (book.use_tc) rc = tc_launch(book.d_jobs, book.d_maps, range.begin, range.count, 1, ceil_div(M, kTileM), prop.multiProcessorCount, s);
+    else rc = simt_launch(book.d_jobs, book.jobs.data(), range.begin, range.count, ceil_div(M, kTileM), s, nullptr);
+    if (rc != EMPOSE_OK) return rc;
+    EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));     // the job array is freed when `arena` goes out of scope
+    return EMPOSE_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,248 @@
+"""ctypes binding of the C ABI declared in ``include/empose_b200.h``.
+
+This is the only place Python touches the native library.  PyTorch is used for device memory and
+streams only: tensors are handed over as raw device pointers (``tensor.data_ptr()``) together with
+the current CUDA stream.  There is no fallback of any kind: if ``libempose_b200.so`` is missing or
+no CUDA device is present, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libempose_b200.so')
+
+PRECISION_TF32 = 0
+PRECISION_FP32 = 1
+_DTYPES = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2}
+
+#: every symbol include/empose_b200.h declares (checked by tests/test_cabi.py)
+EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_create', 'empose_ief_destroy',
+                    'empose_ief_forward', 'empose_ief_forward_host', 'empose_sensor_project',
+                    'empose_ief_last_launch_count', 'empose_gemm_selftest')
+
+
+class EmposeError(RuntimeError):
+    pass
+
+
+class Tensor(ctypes.Structure):
+    _fields_ = [('name', ctypes.c_char_p), ('data', ctypes.c_void_p), ('dtype', ctypes.c_int32),
+                ('ndim', ctypes.c_int32), ('shape', ctypes.c_int64 * 4)]
+
+
+class IefConfig(ctypes.Structure):
+    _fields_ = [('n_markers', ctypes.c_int32), ('num_iterations', ctypes.c_int32), ('step_size', ctypes.c_float),
+                ('rnn_init', ctypes.c_int32), ('average_shape', ctypes.c_int32), ('use_gradient', ctypes.c_int32),
+                ('use_marker_pos', ctypes.c_int32), ('use_marker_ori', ctypes.c_int32), ('hidden_size', ctypes.c_int32),
+                ('num_layers', ctypes.c_int32), ('rnn_hidden_size', ctypes.c_int32), ('rnn_num_layers', ctypes.c_int32),
+                ('skip_connections', ctypes.c_int32), ('batch_norm', ctypes.c_int32), ('precision', ctypes.c_int32),
+                ('device', ctypes.c_int32)]
+
+
+class History(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('pose', 'shape', 'joints', 'markers', 'markers_ori')]
+
+
+_lib = None
+
+
+def load():
+    """Load the native library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EmposeError('native library %s not found: build it with `python em-pose_b200/build.py` '
+                          '(or __graft_entry__.build()); there is no Python/CPU fallback' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp = ctypes.c_void_p
+    i32 = ctypes.c_int32
+    lib.empose_abi_version.restype = ctypes.c_int
+    lib.empose_last_error.restype = ctypes.c_char_p
+    lib.empose_ief_create.restype = ctypes.c_int
+    lib.empose_ief_create.argtypes = [ctypes.POINTER(IefConfig), ctypes.POINTER(Tensor), i32, ctypes.POINTER(vp)]
+    lib.empose_ief_destroy.restype = None
+    lib.empose_ief_destroy.argtypes = [vp]
+    fwd_args = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, ctypes.POINTER(History), vp]
+    lib.empose_ief_forward.restype = ctypes.c_int
+    lib.empose_ief_forward.argtypes = fwd_args
+    lib.empose_ief_forward_host.restype = ctypes.c_int
+    lib.empose_ief_forward_host.argtypes = fwd_args
+    lib.empose_sensor_project.restype = ctypes.c_int
+    lib.empose_sensor_project.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.empose_ief_last_launch_count.restype = ctypes.c_int64
+    lib.empose_ief_last_launch_count.argtypes = [vp]
+    lib.empose_gemm_selftest.restype = ctypes.c_int
+    lib.empose_gemm_selftest.argtypes = [i32, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, i32, i32,
+                                         i32, vp]
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise EmposeError('empose_b200 error %d: %s' % (rc, load().empose_last_error().decode()))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_tensor_table(arrays):
+    """{name: numpy array} -> (ctypes array of Tensor, keep-alive list)."""
+    keep = []
+    table = (Tensor * len(arrays))()
+    for i, (name, arr) in enumerate(arrays.items()):
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype not in _DTYPES:
+            raise EmposeError('tensor %s has unsupported dtype %s' % (name, arr.dtype))
+        if arr.ndim > 4:
+            arr = arr.reshape(arr.shape[0], -1)
+        bname = name.encode()
+        keep += [arr, bname]
+        table[i].name = bname
+        table[i].data = arr.ctypes.data
+        table[i].dtype = _DTYPES[arr.dtype]
+        table[i].ndim = arr.ndim
+        for d in range(arr.ndim):
+            table[i].shape[d] = arr.shape[d]
+    return table, keep
+
+
+class IefContext(object):
+    """Owns one ``empose_ief*``: packed weights, sub-model and cached plans on one device."""
+
+    def __init__(self, config, arrays):
+        """
+        :param config: dict with the fields of ``empose_ief_config``.
+        :param arrays: {name: numpy array}: the reference's state-dict keys plus the ``sub.*`` arrays.
+        """
+        lib = load()
+        cfg = IefConfig()
+        for name, _ in IefConfig._fields_:
+            setattr(cfg, name, config[name])
+        self.config = dict(config)
+        table, keep = make_tensor_table(arrays)
+        handle = ctypes.c_void_p()
+        _check(lib.empose_ief_create(ctypes.byref(cfg), table, len(arrays), ctypes.byref(handle)))
+        del keep
+        self._handle = handle
+        self.n_iter = int(config['num_iterations'])
+        self.rnn_layers = int(config['rnn_num_layers']) if config['rnn_init'] else 0
+        self.rnn_hidden = int(config['rnn_hidden_size'])
+        self.device_index = int(config['device'])
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            load().empose_ief_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def last_launch_count(self):
+        return int(load().empose_ief_last_launch_count(self._handle))
+
+    def forward(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None, lstm_state=None,
+                is_new_sequence=True, want_history=True):
+        """
+        Device tensors in, device tensors out (all float32 / int32, contiguous, on this context's device).
+        :return: dict pose (B,F,66), shape (B,F,10), joints (B,F,66), history (dict of (N+1,B,F,dof)) or None,
+                 lstm_state (2,L,B,H) or None.
+        """
+        import torch
+        dev = marker_pos.device
+        if dev.type != 'cuda':
+            raise EmposeError('inputs must be CUDA tensors (no CPU path)')
+        b, f = int(marker_pos.shape[0]), int(marker_pos.shape[1])
+        f32 = lambda t: t.to(dtype=torch.float32).contiguous()
+        marker_pos, marker_oris = f32(marker_pos).reshape(b, f, 36), f32(marker_oris).reshape(b, f, 108)
+        offset_r, offset_t = f32(offset_r).reshape(b, 12, 9), f32(offset_t).reshape(b, 12, 3)
+        seq_lengths = seq_lengths.to(device=dev, dtype=torch.int32).contiguous()
+        if marker_masks is not None:
+            marker_masks = f32(marker_masks).reshape(b, f, 12)
+        opts = dict(dtype=torch.float32, device=dev)
+        pose = torch.empty((b, f, 66), **opts)
+        shape = torch.empty((b, f, 10), **opts)
+        joints = torch.empty((b, f, 66), **opts)
+        hist, hist_struct = None, None
+        if want_history:
+            n1 = self.n_iter + 1
+            hist = {'pose': torch.empty((n1, b, f, 66), **opts), 'shape': torch.empty((n1, b, f, 10), **opts),
+                    'joints': torch.empty((n1, b, f, 66), **opts), 'markers': torch.empty((n1, b, f, 36), **opts),
+                    'markers_ori': torch.empty((n1, b, f, 108), **opts)}
+            hist_struct = History(*[hist[k].data_ptr() for k in ('pose', 'shape', 'joints', 'markers', 'markers_ori')])
+        state = None
+        if self.rnn_layers:
+            if lstm_state is not None and not is_new_sequence:
+                state = f32(lstm_state).reshape(2, self.rnn_layers, b, self.rnn_hidden).clone()
+            else:
+                state = torch.zeros((2, self.rnn_layers, b, self.rnn_hidden), **opts)
+        _check(load().empose_ief_forward(
+            self._handle, _ptr(marker_pos), _ptr(marker_oris), _ptr(offset_r), _ptr(offset_t), _ptr(seq_lengths),
+            _ptr(marker_masks), _ptr(state), int(bool(is_new_sequence)), b, f, _ptr(pose), _ptr(shape), _ptr(joints),
+            ctypes.byref(hist_struct) if hist_struct is not None else None, _stream()))
+        return {'pose': pose, 'shape': shape, 'joints': joints, 'history': hist, 'lstm_state': state}
+
+    def forward_host(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None,
+                     lstm_state=None, is_new_sequence=True):
+        """Host (CPU, ideally pinned) tensors in and out through ``empose_ief_forward_host``; synchronises."""
+        import torch
+        b, f = int(marker_pos.shape[0]), int(marker_pos.shape[1])
+        f32 = lambda t: t.to(dtype=torch.float32).contiguous()
+        marker_pos, marker_oris = f32(marker_pos), f32(marker_oris)
+        offset_r, offset_t = f32(offset_r), f32(offset_t)
+        seq_lengths = seq_lengths.to(dtype=torch.int32).contiguous()
+        if marker_masks is not None:
+            marker_masks = f32(marker_masks)
+        pose = torch.empty((b, f, 66), dtype=torch.float32).pin_memory()
+        shape = torch.empty((b, f, 10), dtype=torch.float32).pin_memory()
+        joints = torch.empty((b, f, 66), dtype=torch.float32).pin_memory()
+        state = None
+        if self.rnn_layers:
+            state = torch.zeros((2, self.rnn_layers, b, self.rnn_hidden), dtype=torch.float32)
+            if lstm_state is not None and not is_new_sequence:
+                state.copy_(lstm_state.reshape(state.shape))
+        with torch.cuda.device(self.device_index):
+            _check(load().empose_ief_forward_host(
+                self._handle, _ptr(marker_pos), _ptr(marker_oris), _ptr(offset_r), _ptr(offset_t), _ptr(seq_lengths),
+                _ptr(marker_masks), _ptr(state), int(bool(is_new_sequence)), b, f, _ptr(pose), _ptr(shape),
+                _ptr(joints), None, _stream()))
+        return {'pose': pose, 'shape': shape, 'joints': joints, 'lstm_state': state}
+
+    def sensor_project(self, poses, shapes, offset_r, offset_t):
+        """(R,66), (R,10), (R,12,3,3), (R,12,3) device tensors -> sensor_pos (R,12,3), sensor_ori (R,12,3,3), joints (R,22,3)."""
+        import torch
+        r = int(poses.shape[0])
+        f32 = lambda t: t.to(dtype=torch.float32).contiguous()
+        poses, shapes, offset_r, offset_t = f32(poses), f32(shapes), f32(offset_r), f32(offset_t)
+        opts = dict(dtype=torch.float32, device=poses.device)
+        pos = torch.empty((r, 12, 3), **opts)
+        ori = torch.empty((r, 12, 3, 3), **opts)
+        joints = torch.empty((r, 22, 3), **opts)
+        _check(load().empose_sensor_project(self._handle, _ptr(poses), _ptr(shapes), _ptr(offset_r), _ptr(offset_t), r,
+                                            _ptr(pos), _ptr(ori), _ptr(joints), _stream()))
+        return pos, ori, joints
+
+
+def gemm_selftest(a, w, bias, precision=PRECISION_TF32):
+    """C = A . W^T + bias on the job executor; a (M,K), w (N,K), bias (N,) CUDA float32 tensors."""
+    import torch
+    a, w = a.contiguous(), w.contiguous()
+    m, k = a.shape
+    n = w.shape[0]
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    _check(load().empose_gemm_selftest(precision, _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(c),
+                                       c.stride(0), m, n, k, _stream()))
+    return c

@@ -1,0 +1,274 @@
+"""The LGD / IEF model with the reference's class surface, executed by libempose_b200.
+
+Mirrors ``empose/nn/models.py``: ``create_model`` (``:23-33``), ``BaseModel`` bookkeeping (``:41-96``)
+and ``IterativeErrorFeedback`` (``:369-688``).  Same constructor arguments, same ``forward`` /
+``backward`` signatures and outputs, same ``*_history`` attributes, same state-dict keys -- but
+``forward`` marshals the batch through the C ABI (``empose_b200.lib``) into hand-written sm_100a CUDA
+instead of running PyTorch ops.  Inference only for now: calling ``forward`` in training mode raises.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from empose_b200 import lib as _lib
+from empose_b200.helpers.configuration import CONSTANTS as C
+from empose_b200.nn.layers import MLP
+from empose_b200.nn.layers import RNNLayer
+
+
+def create_model(config, *args):
+    """``models.py:23-33``.  Only the LGD family is implemented by this package."""
+    m_type = config.m_type
+    if m_type in ('ief', 'lgd'):
+        return IterativeErrorFeedback(config, *args)
+    if m_type in ('rnn', 'resnet'):
+        raise NotImplementedError("model type '%s' is outside the LGD hot path built by empose_b200" % m_type)
+    raise ValueError("Model type '{}' unknown.".format(m_type))
+
+
+def _frame_mask(seq_lengths, n_frames):
+    t = torch.arange(n_frames, device=seq_lengths.device).unsqueeze(0)
+    return t < seq_lengths.reshape(-1, 1)
+
+
+class IterativeErrorFeedback(nn.Module):
+    """The LGD(-RNN) model (``models.py:369-688``)."""
+
+    def __init__(self, config, smpl_model, precision=_lib.PRECISION_TF32):
+        super(IterativeErrorFeedback, self).__init__()
+        self.config = config
+        self.n_markers = config.n_markers if getattr(config, 'n_markers', -1) > -1 else C.N_TRACKERS_WO_ROOT
+        assert self.n_markers in [6, 12]                                    # models.py:385
+        self.n_frames = config.window_size
+        self.smpl = smpl_model
+        self.N = config.m_num_iterations
+        self.step_size = config.m_step_size
+        self.shape_avg = config.m_average_shape
+        self.r_weight = config.m_reprojection_loss_weight
+        self.use_gradient = config.m_use_gradient
+        self.skip_connections = config.m_skip_connections
+        self.rnn_init = config.m_rnn_init
+        self.estimate_shape = config.m_estimate_shape
+        self.fk_loss_weight = config.m_fk_loss
+        self.do_fk = self.fk_loss_weight > 0.0
+        if self.do_fk:
+            assert self.smpl is not None
+        self.shape_weight = getattr(config, 'm_shape_loss_weight', 1.0)
+        self.pose_weight = getattr(config, 'm_pose_loss_weight', 1.0)
+        self.precision = precision
+        if getattr(config, 'use_marker_nor', False):
+            raise ValueError('Normals currently not supported.')             # models.py:122-123
+        if getattr(config, 'm_rnn_bidirectional', False) and self.rnn_init:
+            raise NotImplementedError('bidirectional init RNN is not part of the released LGD models')
+
+        # sizes (models.py:397-421); the constructor mutates the config like the reference does
+        self.pos_d_start, self.pos_d_end, self.ori_d_start, self.ori_d_end = 0, 0, 0, 0
+        input_size = 0
+        if config.use_marker_pos:
+            input_size += self.n_markers * 3
+            self.pos_d_end = self.n_markers * 3
+            self.ori_d_start = self.pos_d_end
+        if config.use_marker_ori:
+            input_size += self.n_markers * 9
+            self.ori_d_end = self.ori_d_start + self.n_markers * 9
+        self.input_size = input_size
+        self.pose_size = (C.N_JOINTS + 1) * 3
+        self.shape_size = C.N_SHAPE_PARAMS
+        self.input_iter_size = input_size + self.pose_size + self.shape_size
+        if self.use_gradient:
+            self.input_iter_size += self.pose_size + self.shape_size
+        for k in ('input_size', 'pose_size', 'shape_size', 'input_iter_size'):
+            setattr(config, k, getattr(self, k))
+
+        # parameter containers with the reference's names (models.py:424-454)
+        bn = not config.m_no_batch_norm
+        mlp = lambda n_in, n_out: MLP(n_in, n_out, config.m_hidden_size, config.m_num_layers, config.m_dropout_hidden,
+                                      self.skip_connections, bn)
+        if self.rnn_init:
+            self.rnn = RNNLayer(self.input_size, config.m_rnn_hidden_size, config.m_rnn_num_layers,
+                                dropout=config.m_dropout, bidirectional=False)
+            self.pose_net_init = nn.Linear(config.m_rnn_hidden_size, self.pose_size)
+            self.shape_net_init = nn.Linear(config.m_rnn_hidden_size, self.shape_size)
+        else:
+            self.pose_net_init = mlp(self.input_size, self.pose_size)
+            self.shape_net_init = mlp(self.input_size, self.shape_size)
+        self.pose_net_iter = mlp(self.input_iter_size, self.pose_size)
+        self.shape_net_iter = mlp(self.input_iter_size, self.shape_size)
+        self.smpl_loss = nn.L1Loss(reduction='none')
+
+        self.vertex_ids = C.VERTEX_IDS
+        self.marker_idxs = list(range(12)) if self.n_markers == 12 else C.S_CONFIG_6
+        self.markers_hat_history = None
+        self.markers_ori_hat_history = None
+        self.pose_hat_history = None
+        self.shape_hat_history = None
+        self.joints_hat_history = None
+        self._ctx = None
+        self._ctx_key = None
+
+    # ------------------------------------------------------------------------------------------------
+    def model_name(self):
+        """``models.py:459-469``."""
+        c = self.config
+        name = "IEF-{}x{}-N{}".format(c.m_num_layers, c.m_hidden_size, c.m_num_iterations)
+        if self.rnn_init:
+            name += '-{}RNN-{}x{}'.format('', c.m_rnn_num_layers, c.m_rnn_hidden_size)
+        name += '-r{}-ws{}-lr{}'.format(self.r_weight, c.window_size, c.lr)
+        name += '-grad' if self.use_gradient else ''
+        name += '-skip' if self.skip_connections else ''
+        name += '-n{}'.format(self.n_markers)
+        return name
+
+    # ------------------------------------------------------------------------------------------------
+    def _native_config(self, device_index):
+        c = self.config
+        return dict(n_markers=self.n_markers, num_iterations=self.N, step_size=float(self.step_size),
+                    rnn_init=int(self.rnn_init), average_shape=int(self.shape_avg), use_gradient=int(self.use_gradient),
+                    use_marker_pos=int(c.use_marker_pos), use_marker_ori=int(c.use_marker_ori),
+                    hidden_size=int(c.m_hidden_size), num_layers=int(c.m_num_layers),
+                    rnn_hidden_size=int(c.m_rnn_hidden_size), rnn_num_layers=int(c.m_rnn_num_layers),
+                    skip_connections=int(self.skip_connections), batch_norm=int(not c.m_no_batch_norm),
+                    precision=int(self.precision), device=int(device_index))
+
+    def _weights_key(self, device_index):
+        tensors = [t for k, t in self.state_dict(keep_vars=True).items()]
+        return (device_index, self.precision) + tuple((t.data_ptr(), t._version) for t in tensors)
+
+    def native_context(self, device):
+        """Build (or reuse) the native context for the current weights on ``device``."""
+        if device.type != 'cuda':
+            raise _lib.EmposeError('empose_b200 runs on CUDA devices only (no CPU fallback); got %s' % device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = self._weights_key(index)
+        if self._ctx is None or key != self._ctx_key:
+            if self._ctx is not None:
+                self._ctx.close()
+            arrays = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()
+                      if not k.startswith('smpl.') and v.is_floating_point()}
+            arrays = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in arrays.items()}
+            arrays.update(self.smpl.submodel_arrays())
+            self._ctx = _lib.IefContext(self._native_config(index), arrays)
+            self._ctx_key = key
+        return self._ctx
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, batch, window_size=None, is_new_sequence=True):
+        """``models.py:485-632``.  ``batch`` is an ``ABatch`` (anything with ``get_inputs``, ``seq_lengths``,
+        ``batch_size`` and ``seq_length``).  Works inside ``torch.no_grad()`` like the reference."""
+        if self.training:
+            raise NotImplementedError('empose_b200 implements the inference path of the LGD loop; call net.eval() '
+                                      '(training: batch-statistics BatchNorm + backward are not built yet)')
+        if self.rnn_init:
+            if is_new_sequence:
+                self.rnn.final_state = None
+            self.rnn.init_state = self.rnn.final_state
+
+        seq_len = batch.seq_length
+        if window_size is None:
+            spans = [(None, None)]
+        else:                                                                # models.py:146-159
+            n_windows = seq_len // window_size + int(seq_len % window_size > 0)
+            spans = [(i * window_size, min((i + 1) * window_size, seq_len)) for i in range(n_windows)]
+
+        outs, hists = [], []
+        for sf, ef in spans:
+            inputs = batch.get_inputs(sf=sf, ef=ef) if sf is not None else batch.get_inputs()
+            marker_pos = inputs['marker_pos']
+            if sf is None:
+                lengths = batch.seq_lengths
+            else:
+                lengths = torch.full((marker_pos.shape[0],), ef - sf, dtype=torch.int32, device=marker_pos.device)
+            ctx = self.native_context(marker_pos.device)
+            state = None
+            if self.rnn_init and self.rnn.final_state is not None:
+                state = torch.stack([self.rnn.final_state[0], self.rnn.final_state[1]])
+            res = ctx.forward(marker_pos, inputs['marker_oris'], inputs['offset_r'], inputs['offset_t'], lengths,
+                              marker_masks=inputs.get('marker_masks'), lstm_state=state,
+                              is_new_sequence=state is None, want_history=True)
+            if self.rnn_init:
+                self.rnn.init_state = self.rnn.final_state
+                self.rnn.final_state = (res['lstm_state'][0], res['lstm_state'][1])
+            outs.append(res)
+            hists.append(res['history'])
+
+        cat = lambda key: torch.cat([o[key] for o in outs], dim=1)
+        n1 = self.N + 1
+        hist_cat = {k: [torch.cat([h[k][i] for h in hists], dim=1) for i in range(n1)] for k in hists[0]}
+        self.pose_hat_history = hist_cat['pose']
+        self.shape_hat_history = hist_cat['shape']
+        self.joints_hat_history = hist_cat['joints']
+        self.markers_hat_history = hist_cat['markers']
+        self.markers_ori_hat_history = hist_cat['markers_ori']
+        pose = cat('pose')
+        return {'pose_hat': pose[:, :, 3:], 'root_ori_hat': pose[:, :, :3], 'shape_hat': cat('shape'),
+                'joints_hat': cat('joints')}
+
+    # ------------------------------------------------------------------------------------------------
+    def prepare_inputs(self, batch_inputs):
+        """``models.py:106-125`` (host-side view used by ``backward``; the kernels do their own gather)."""
+        n, f = batch_inputs['marker_pos'].shape[0], batch_inputs['marker_pos'].shape[1]
+        m_pos = batch_inputs['marker_pos'].reshape((n, f, -1, 3))
+        m_ori = batch_inputs['marker_oris'].reshape((n, f, -1, 3, 3))
+        if self.n_markers == 6:
+            m_pos, m_ori = m_pos[:, :, C.S_CONFIG_6], m_ori[:, :, C.S_CONFIG_6]
+        parts = []
+        if self.config.use_marker_pos:
+            parts.append(m_pos.reshape((n, f, -1)))
+        if self.config.use_marker_ori:
+            parts.append(m_ori.reshape((n, f, -1)))
+        return torch.cat(parts, dim=-1)
+
+    @staticmethod
+    def _masked_mean(per_frame, seq_lengths):
+        mask = _frame_mask(seq_lengths, per_frame.shape[1]).to(per_frame.dtype)
+        return ((per_frame * mask).sum(-1) / seq_lengths.to(per_frame.dtype)).mean()
+
+    def _recon(self, gt, hat, seq_lengths, marker_masks):
+        """``loss.py:23-41``."""
+        diff = hat - gt
+        per_frame = torch.sqrt((diff * diff).sum(dim=-1)).sum(dim=-1)
+        if marker_masks is not None:
+            per_frame = per_frame * marker_masks.logical_not().any(dim=-1).logical_not()
+        return self._masked_mean(per_frame, seq_lengths)
+
+    def backward(self, batch, model_out, writer=None, global_step=None):
+        """
+        ``models.py:634-688``: the training loss over all N+1 iterates, evaluated from the histories of the
+        last ``forward``.  Returns ``(total_loss, loss_vals)``.  The loss value is what
+        ``empose/eval/helpers.py:86`` logs during validation; ``total_loss.backward()`` (training) is not built.
+        """
+        if self.training:
+            raise NotImplementedError('the training backward pass is not built yet in empose_b200')
+        bsz, n_frames = batch.batch_size, batch.seq_length
+        inputs_ = self.prepare_inputs(batch.get_inputs())
+        markers_in = inputs_[:, :, self.pos_d_start:self.pos_d_end].reshape((bsz, n_frames, -1, 3))
+        markers_ori_in = inputs_[:, :, self.ori_d_start:self.ori_d_end].reshape((bsz, n_frames, -1, 9))
+        lengths = batch.seq_lengths
+        dev = inputs_.device
+        zero = lambda: torch.zeros(1, device=dev)
+        recon_t, shape_t, pose_t, fk_t = zero(), zero(), zero(), zero()
+        n_hist = len(self.pose_hat_history)
+        pose_gt = torch.cat([batch.poses_root, batch.poses_body], dim=-1)
+        shape_gt = batch.shapes.unsqueeze(1).repeat((1, n_frames, 1))
+        for i in range(n_hist):
+            pose_t += self._masked_mean((pose_gt - self.pose_hat_history[i]).abs().mean(-1), lengths)
+            shape_t += self._masked_mean((shape_gt - self.shape_hat_history[i]).abs().mean(-1), lengths)
+            if self.do_fk:
+                fk_t += self._recon(batch.joints_gt.reshape(bsz, n_frames, -1, 3),
+                                    model_out['joints_hat'].reshape(bsz, n_frames, -1, 3), lengths, batch.marker_masks)
+            if self.config.use_marker_pos:
+                hat = self.markers_hat_history[i].reshape((bsz, n_frames, -1, 3))[:, :, self.marker_idxs]
+                recon_t += self._recon(markers_in, hat, lengths, batch.marker_masks)
+            if self.config.use_marker_ori:
+                hat = self.markers_ori_hat_history[i].reshape((bsz, n_frames, -1, 9))[:, :, self.marker_idxs]
+                recon_t += self._recon(markers_ori_in, hat, lengths, batch.marker_masks)
+        total = (self.pose_weight * pose_t + self.fk_loss_weight * fk_t + self.shape_weight * shape_t +
+                 self.r_weight * recon_t) / n_hist
+        loss_vals = {'pose': pose_t.cpu().item() / n_hist, 'shape': shape_t.cpu().item() / n_hist,
+                     'reconstruction': recon_t.cpu().item() / n_hist, 'fk': fk_t.cpu().item() / n_hist,
+                     'total_loss': total.cpu().item()}
+        if writer is not None:
+            prefix = 'train' if self.training else 'valid'
+            for k in loss_vals:
+                writer.add_scalar('{}/{}'.format(k, prefix), loss_vals[k], global_step)
+        return total, loss_vals

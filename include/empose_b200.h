@@ -1,0 +1,151 @@
+/*
+ * empose_b200 -- C ABI of the B200-native EM-POSE learned-gradient-descent (LGD / IEF) hot path.
+ *
+ * The reference (facebookresearch/em-pose) has no FFI: its seam for this path is two Python
+ * classes.  This header is the boundary a binding for those classes talks to; every entry point
+ * names the reference interface it stands in for (paths are relative to the reference tree).
+ *
+ *   empose_ief_create / _destroy   <- create_model(config, smpl_model)            empose/nn/models.py:23-33
+ *                                     + nn.Module.load_state_dict (state-dict keys of models.py:424-454,
+ *                                       layers.py:13-77,114) + VirtualMarkerHelper topology
+ *                                       (empose/data/virtual_sensors.py:47-75)
+ *   empose_ief_forward             <- IterativeErrorFeedback.forward              empose/nn/models.py:485-632
+ *   empose_ief_forward_host        <- same, host buffers (what scripts/evaluate_real.py:61 does around it:
+ *                                     chunk.to_gpu(), net(chunk), .cpu())
+ *   empose_sensor_project          <- IterativeErrorFeedback.get_estimated_real_markers
+ *                                                                                 empose/nn/models.py:471-483
+ *   empose_smpl_forward            <- SMPLLayer.forward / fk / _fk                empose/bodymodels/smpl.py:81-165
+ *   empose_gemm_selftest           <- (no reference counterpart) checks the tcgen05 GEMM engine
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * EMPOSE_E_* code and never throws; empose_last_error() gives the message of the last failure on the
+ * calling thread.  Unless a parameter says "host", data pointers are DEVICE pointers on the context's
+ * device, borrowed for the duration of the call; work is enqueued on `stream` (a cudaStream_t passed
+ * as void*) and is stream-ordered -- the call does not synchronise unless noted.  A context may be
+ * used from one host thread at a time.  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with EMPOSE_E_CUDA.
+ *
+ * Layouts are the reference's: row-major float32; poses are axis-angle [root(3) | 21 body joints];
+ * sensors are in S_ORDER (empose/helpers/configuration.py:86-88); orientations are row-major 3x3.
+ */
+#ifndef EMPOSE_B200_H
+#define EMPOSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMPOSE_ABI_VERSION 1
+
+enum {
+    EMPOSE_OK = 0,
+    EMPOSE_E_ARG = -1,       /* bad argument / unsupported configuration (reference: ValueError / assert) */
+    EMPOSE_E_MISSING = -2,   /* a required tensor is absent from the tensor table (reference: load_state_dict KeyError) */
+    EMPOSE_E_SHAPE = -3,     /* tensor with the wrong shape or dtype */
+    EMPOSE_E_CUDA = -4,      /* CUDA runtime / driver failure, or no device */
+    EMPOSE_E_NOMEM = -5
+};
+
+enum { EMPOSE_F32 = 0, EMPOSE_I32 = 1, EMPOSE_I64 = 2 };
+
+/* Arithmetic of the learned layers and the pose-blend contraction. */
+enum {
+    EMPOSE_PRECISION_TF32 = 0,   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (product default) */
+    EMPOSE_PRECISION_FP32 = 1    /* plain fp32 FFMA kernels: exact-arithmetic mode for parity studies */
+};
+
+/* One named host tensor.  Names are the reference's state-dict keys ("rnn.lstm.weight_ih_l0",
+ * "pose_net_iter.hidden_layers.0.layers.1.running_var", ...) plus the "sub.*" arrays produced by
+ * submodel.py (the SMPL-H sub-model and sensor topology). */
+typedef struct {
+    const char* name;
+    const void* data;        /* HOST pointer, contiguous row-major */
+    int32_t dtype;           /* EMPOSE_F32 / EMPOSE_I32 / EMPOSE_I64 */
+    int32_t ndim;
+    int64_t shape[4];
+} empose_tensor;
+
+/* The flags of empose/helpers/configuration.py:150-209 that the path reads. */
+typedef struct {
+    int32_t n_markers;          /* 6 or 12 (models.py:385) */
+    int32_t num_iterations;     /* m_num_iterations */
+    float step_size;            /* m_step_size */
+    int32_t rnn_init;           /* m_rnn_init */
+    int32_t average_shape;      /* m_average_shape */
+    int32_t use_gradient;       /* m_use_gradient */
+    int32_t use_marker_pos;
+    int32_t use_marker_ori;
+    int32_t hidden_size;        /* m_hidden_size */
+    int32_t num_layers;         /* m_num_layers: LinearLayers blocks per MLP */
+    int32_t rnn_hidden_size;    /* m_rnn_hidden_size */
+    int32_t rnn_num_layers;     /* m_rnn_num_layers */
+    int32_t skip_connections;   /* m_skip_connections */
+    int32_t batch_norm;         /* !m_no_batch_norm */
+    int32_t precision;          /* EMPOSE_PRECISION_* */
+    int32_t device;             /* CUDA device ordinal */
+} empose_ief_config;
+
+typedef struct empose_ief empose_ief;   /* opaque: packed weights + sub-model + cached execution plans */
+
+/* Optional per-iterate outputs (the five *_history lists of models.py:620-629).  Any pointer may be
+ * NULL.  Each is [N+1][B][F][dof] with dof = 66, 10, 66, 36, 108. */
+typedef struct {
+    float* pose;
+    float* shape;
+    float* joints;
+    float* markers;
+    float* markers_ori;
+} empose_ief_history;
+
+int empose_abi_version(void);
+const char* empose_last_error(void);
+
+/* Build a model context: folds BatchNorm (eval statistics) into the Linear layers in double
+ * precision, packs and (TF32 mode) rounds the weights, uploads the sub-model.  Inference semantics
+ * (nn.Module.eval()).  Host pointers in `tensors` are only read during the call. */
+int empose_ief_create(const empose_ief_config* cfg, const empose_tensor* tensors, int32_t n_tensors,
+                      empose_ief** out);
+void empose_ief_destroy(empose_ief* ctx);
+
+/* One pass of the hot path over a batch of B windows of F frames.
+ *   marker_pos  [B][F][36]   marker_oris [B][F][108]   (always 12 sensors, as batch.get_inputs() supplies)
+ *   offset_r    [B][12][9]   offset_t    [B][12][3]
+ *   seq_lengths [B] int32 (1..F)      marker_masks [B][F][12] float (non-zero = present) or NULL
+ *   lstm_state  [2][rnn_num_layers][B][H] (h then c), in/out, or NULL.  Read unless is_new_sequence;
+ *               always written when non-NULL (RNNLayer.final_state, models.py:489-492).
+ * Outputs (any may be NULL): pose_hat [B][F][66] (root first: callers slice [3:] / [:3] as models.py:606-607),
+ *   shape_hat [B][F][10], joints_hat [B][F][66]. */
+int empose_ief_forward(empose_ief* ctx, const float* marker_pos, const float* marker_oris, const float* offset_r,
+                       const float* offset_t, const int32_t* seq_lengths, const float* marker_masks,
+                       float* lstm_state, int32_t is_new_sequence, int32_t B, int32_t F, float* pose_hat,
+                       float* shape_hat, float* joints_hat, const empose_ief_history* history, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): uploads the inputs, runs the pass and downloads
+ * the outputs on `stream`, then synchronises the stream.  lstm_state / history are host pointers too. */
+int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const float* marker_oris,
+                            const float* offset_r, const float* offset_t, const int32_t* seq_lengths,
+                            const float* marker_masks, float* lstm_state, int32_t is_new_sequence, int32_t B,
+                            int32_t F, float* pose_hat, float* shape_hat, float* joints_hat,
+                            const empose_ief_history* history, void* stream);
+
+/* SMPL-H sub-model -> 12 sensor frames with offsets applied -> first 22 joints, for R frames.
+ *   poses [R][66], shapes [R][10], offset_r [R][12][9], offset_t [R][12][3]
+ *   -> sensor_pos [R][36], sensor_ori [R][108], joints [R][66] (any output may be NULL). */
+int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shapes, const float* offset_r,
+                          const float* offset_t, int32_t R, float* sensor_pos, float* sensor_ori, float* joints,
+                          void* stream);
+
+/* Number of kernels the last empose_ief_forward* call on this context launched (for bench accounting). */
+int64_t empose_ief_last_launch_count(const empose_ief* ctx);
+
+/* Engine self-test: C[M][N] = A[M][K] . W[N][K]^T + bias through the same job executor the model uses
+ * (precision selects tcgen05 or FFMA).  Device pointers; lda / ldw / ldc in floats. */
+int empose_gemm_selftest(int32_t precision, const float* A, int64_t lda, const float* W, int64_t ldw,
+                         const float* bias, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMPOSE_B200_H */

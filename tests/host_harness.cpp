@@ -65,9 +65,9 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
             dpf[k] = acc;
         }
         phase_chain_bwd(m, st, 0, 1);
-        phase_chain_bwd_reduce(st, 0, 1);
+        phase_chain_bwd_local(m, st, 0, 1);
         std::vector<T> gt(kPoseDim), gb(kBetas);
-        phase_finish(m, st, T(coef[f]), 1, dpf.data(), gt.data(), gb.data(), 0, 1);
+        phase_finish(m, st, T(coef[f]), dpf.data(), gt.data(), gb.data(), 0, 1);
         for (int i = 0; i < kPoseDim; ++i) g_theta[f * kPoseDim + i] = double(gt[i]);
         for (int i = 0; i < kBetas; ++i) g_beta[f * kBetas + i] = double(gb[i]);
     }

@@ -1,0 +1,90 @@
+"""CPU-side checks of the boundary: the library loads, exports every declared symbol, the Python module
+mirrors the reference's state-dict layout, and the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from empose_b200 import lib as native
+from empose_b200 import synthetic
+
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def built_lib():
+    from empose_b200 import build
+    build.build_library()
+    return native.load()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, 'include', 'empose_b200.h')).read()
+    declared = set(re.findall(r'\b(empose_[a-z_0-9]+)\s*\(', header))
+    declared = {d for d in declared if not d.endswith('_t')}
+    assert declared == set(native.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert built_lib.empose_abi_version() == 1
+
+
+def test_struct_layouts_match_header(built_lib):
+    assert ctypes.sizeof(native.IefConfig) == 16 * 4
+    assert ctypes.sizeof(native.Tensor) == 8 + 8 + 4 + 4 + 32
+    assert ctypes.sizeof(native.History) == 5 * 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_create_fails_loudly_without_gpu(built_lib, smpl_npz):
+    net = util.build_module(smpl_npz)
+    with pytest.raises(native.EmposeError):
+        net.native_context(torch.device('cpu'))
+    cfg = net._native_config(0)
+    arrays = {k: v.numpy() for k, v in net.state_dict().items() if not k.startswith('smpl.') and v.is_floating_point()}
+    arrays.update(net.smpl.submodel_arrays())
+    with pytest.raises(native.EmposeError, match='no CUDA device|CUDA'):
+        native.IefContext(cfg, arrays)
+
+
+def test_bad_config_is_rejected_before_touching_the_gpu(built_lib):
+    cfg = native.IefConfig()
+    cfg.n_markers = 7
+    handle = ctypes.c_void_p()
+    table, _ = native.make_tensor_table({'x': np.zeros(1, dtype=np.float32)})
+    rc = built_lib.empose_ief_create(ctypes.byref(cfg), table, 1, ctypes.byref(handle))
+    assert rc == -1 and b'n_markers' in built_lib.empose_last_error()
+
+
+@pytest.mark.parametrize('n_markers,rnn_init', [(12, True), (6, True), (12, False)])
+def test_state_dict_keys_match_reference_layout(smpl_npz, n_markers, rnn_init):
+    net = util.build_module(smpl_npz, n_markers=n_markers, rnn_init=rnn_init)
+    keys = set(net.state_dict().keys())
+    learned = {k for k, _, _ in synthetic.lgd_state_dict_spec(n_markers=n_markers, rnn_init=rnn_init)}
+    smpl = {'smpl.bm.' + k for k in ('trans', 'root_orient', 'pose_body', 'pose_hand', 'betas', 'v_template', 'f',
+                                      'shapedirs', 'J_regressor', 'posedirs', 'kintree_table', 'weights')}
+    assert keys == learned | smpl            # SURVEY.md section 8b key list
+    n_params = sum(p.numel() for p in net.parameters() if p.requires_grad)
+    if n_markers == 6 and rnn_init:
+        pass  # N does not change the count; README.md:228 quotes 5721419 for this layout
+    gold = util.load_golden({(12, True): 'lgd_rnn12_n4', (6, True): 'lgd_rnn6_n2_real', (12, False): 'lgd_mlp12_n4'}[(n_markers, rnn_init)])
+    assert n_params == int(gold['n_trainable_params'])
+
+
+def test_training_mode_is_refused(smpl_npz):
+    net = util.build_module(smpl_npz).train()
+    with pytest.raises(NotImplementedError):
+        net(None)
+
+
+def test_submodel_arrays_are_complete(smpl_npz):
+    net = util.build_module(smpl_npz)
+    sub = net.smpl.submodel_arrays()
+    assert sub['sub.dims'].tolist()[-1] == 12 and sub['sub.posedirs'].shape[0] == 189
+    assert set(sub) >= {'sub.v_template', 'sub.shapedirs', 'sub.posedirs', 'sub.j0', 'sub.jdirs', 'sub.skin_weight',
+                        'sub.skin_joint', 'sub.jt_ptr', 'sub.jt_vert', 'sub.jt_weight', 'sub.parents', 'sub.faces',
+                        'sub.sensor_vert', 'sub.helper_vert', 'sub.sensor_faces', 'sub.sensor_degree', 'sub.dims'}

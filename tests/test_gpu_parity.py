@@ -1,0 +1,180 @@
+"""Parity of the CUDA path against the oracle and the golden vectors (run on the B200 box: -m gpu).
+
+Everything here calls through the C ABI (``empose_b200.lib`` -> ``libempose_b200.so``).  Tolerances:
+the task's bar is <= 1e-4 rad per-joint rotation and <= 0.1 mm joint position against the reference
+path on identical inputs; the FP32 executor is held to a much tighter bound.
+"""
+import numpy as np
+import pytest
+import torch
+
+from empose_b200 import lib as native
+from empose_b200 import synthetic
+from oracle import ief as oracle_ief
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+PARITY_RAD = 1e-4      # north_star tolerance, per-joint axis-angle
+PARITY_MM = 0.1        # north_star tolerance, joint position
+PRECISIONS = [native.PRECISION_FP32, native.PRECISION_TF32]
+PNAME = {native.PRECISION_FP32: 'fp32', native.PRECISION_TF32: 'tf32'}
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'these tests need the B200'
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device('cuda:0')
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the GEMM engine
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', PRECISIONS, ids=PNAME.get)
+@pytest.mark.parametrize('m,n,k', [(128, 256, 32), (128, 16, 8), (300, 512, 296), (257, 80, 512), (1000, 192, 256),
+                                   (4096, 2048, 656), (19, 66, 144)])
+def test_gemm_engine(dev, precision, m, n, k):
+    g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
+    a = torch.randn(m, k, generator=g).to(dev)
+    w = (torch.randn(n, k, generator=g) / np.sqrt(k)).to(dev)
+    bias = torch.randn(n, generator=g).to(dev)
+    got = native.gemm_selftest(a, w, bias, precision)
+    want = (a.double() @ w.double().T + bias.double()).float()
+    err = (got - want).abs().max().item()
+    # tf32 inputs carry 2^-11 relative rounding (truncation in the worst case 2^-10): |a||w| ~ 1 per term, sqrt(k) growth
+    tol = 2e-5 if precision == native.PRECISION_FP32 else 4e-3
+    assert err < tol, 'max abs err %g' % err
+    if precision == native.PRECISION_TF32:          # same operands pre-rounded: only accumulation order differs
+        r = lambda t: (t.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)
+        want_r = (r(a).double() @ r(w).double().T + bias.double()).float()
+        assert (native.gemm_selftest(r(a), r(w), bias, precision) - want_r).abs().max().item() < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SMPL sub-model -> sensors (empose_sensor_project)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', PRECISIONS, ids=PNAME.get)
+def test_sensor_projection_matches_oracle(dev, smpl_npz, oracle_smpl, topology, precision):
+    net = util.build_module(smpl_npz, precision=precision, device=dev)
+    ctx = net.native_context(dev)
+    p = synthetic.synth_window_params(5, 7, seed=4, offsets=True)
+    r = 35
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    poses = t(p['poses']).reshape(r, 66)
+    shapes = t(p['shapes']).unsqueeze(1).repeat(1, 7, 1).reshape(r, 10)
+    off_r = t(p['offset_r']).unsqueeze(1).repeat(1, 7, 1, 1, 1).reshape(r, 12, 3, 3)
+    off_t = t(p['offset_t']).unsqueeze(1).repeat(1, 7, 1, 1).reshape(r, 12, 3)
+    pos, ori, joints = ctx.sensor_project(poses.to(dev), shapes.to(dev), off_r.to(dev), off_t.to(dev))
+    with torch.no_grad():
+        o_pos, o_ori, o_j = oracle_ief.project_sensors(oracle_smpl, topology, poses.double(), shapes.double(),
+                                                       off_r.double(), off_t.double())
+    assert util.max_joint_pos_err_mm(joints.cpu().numpy(), o_j.numpy()) < 0.005
+    assert util.max_joint_pos_err_mm(pos.cpu().numpy(), o_pos.numpy()) < 0.01
+    np.testing.assert_allclose(ori.cpu().numpy(), o_ori.numpy(), atol=2e-4, rtol=0)
+
+    # golden vectors from the reference's own SMPLLayer + VirtualMarkerHelper
+    gold = util.load_golden('smpl_sensors')
+    gp = t(gold['poses']).reshape(-1, 66)
+    f = gp.shape[0]
+    pos, ori, _ = ctx.sensor_project(gp.to(dev), t(gold['shapes']).repeat(f, 1).to(dev),
+                                     t(gold['offset_r']).repeat(f, 1, 1, 1).to(dev), t(gold['offset_t']).repeat(f, 1, 1).to(dev))
+    assert util.max_joint_pos_err_mm(pos.cpu().numpy(), gold['sensor_pos'].reshape(f, 12, 3)) < 0.01
+    np.testing.assert_allclose(ori.cpu().numpy(), gold['sensor_ori'].reshape(f, 12, 3, 3), atol=2e-4, rtol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole loop vs golden outputs of the unmodified reference
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', PRECISIONS, ids=PNAME.get)
+@pytest.mark.parametrize('name', sorted(util.GOLDEN_CASES))
+def test_ief_matches_reference_golden(dev, smpl_npz, name, precision):
+    flags = util.GOLDEN_CASES[name]
+    gold = util.load_golden(name)
+    net = util.build_module(smpl_npz, precision=precision, device=dev, **flags)
+    rad_tol, mm_tol = (2e-5, 0.02) if precision == native.PRECISION_FP32 else (PARITY_RAD, PARITY_MM)
+    c = 0
+    while ('c%d_pose_hat' % c) in gold:
+        inp = util.chunk_inputs(gold, c)
+        batch = util.DuckBatch(**inp).to(dev)
+        with torch.no_grad():
+            out = net(batch, is_new_sequence=(c == 0))
+        tag = 'c%d_' % c
+        live = util.valid_frame_mask(gold[tag + 'seq_lengths'], inp['marker_pos'].shape[1])
+        got = {k: v.cpu().numpy() for k, v in out.items()}
+        assert util.max_joint_angle_err(got['pose_hat'][live], gold[tag + 'pose_hat'][live]) <= rad_tol
+        assert util.max_joint_angle_err(got['root_ori_hat'][live], gold[tag + 'root_ori_hat'][live]) <= rad_tol
+        assert util.max_joint_pos_err_mm(got['joints_hat'][live], gold[tag + 'joints_hat'][live]) <= mm_tol
+        np.testing.assert_allclose(got['shape_hat'][live], gold[tag + 'shape_hat'][live], atol=rad_tol * 5, rtol=0)
+        # all N+1 iterates (what IterativeErrorFeedback.backward consumes)
+        hist = {'pose_hat_history': net.pose_hat_history, 'shape_hat_history': net.shape_hat_history,
+                'joints_hat_history': net.joints_hat_history, 'markers_hat_history': net.markers_hat_history,
+                'markers_ori_hat_history': net.markers_ori_hat_history}
+        for k, lst in hist.items():
+            g = np.stack([h.cpu().numpy() for h in lst])
+            assert g.shape == gold[tag + k].shape, k
+            tol = 5e-4 if 'ori' in k else rad_tol * 5
+            np.testing.assert_allclose(g[:, live], gold[tag + k][:, live], atol=tol, rtol=0, err_msg=k)
+        if flags['rnn_init']:
+            np.testing.assert_allclose(net.rnn.final_state[0].cpu().numpy(), gold[tag + 'final_h'], atol=2e-3 if precision else 5e-6, rtol=0)
+        c += 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# vs the oracle on fresh seeded inputs: ragged lengths, dropped sensors, offsets, both sensor counts
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', PRECISIONS, ids=PNAME.get)
+@pytest.mark.parametrize('n_markers,rnn_init,n_iter', [(12, True, 4), (6, True, 2), (12, False, 4)])
+def test_ief_matches_oracle(dev, smpl_npz, oracle_smpl, topology, precision, n_markers, rnn_init, n_iter):
+    b, f = 6, 32
+    params = synthetic.synth_window_params(b, f, seed=31 + n_markers, ragged=True, offsets=True, drop_rate=0.05)
+    inp = util.oracle_inputs_from_params(oracle_smpl, topology, params, seed=5)
+    cfg = oracle_ief.IefConfig(n_markers=n_markers, num_iterations=n_iter, rnn_init=rnn_init)
+    sd = util.torch_state_dict(synthetic.synth_state_dict(seed=0, n_markers=n_markers, rnn_init=rnn_init))
+    want = oracle_ief.ief_forward(cfg, sd, oracle_smpl, topology, **inp)
+    net = util.build_module(smpl_npz, n_markers=n_markers, num_iterations=n_iter, rnn_init=rnn_init,
+                            precision=precision, device=dev)
+    with torch.no_grad():
+        out = net(util.DuckBatch(**inp).to(dev))
+    live = util.valid_frame_mask(params['seq_lengths'], f)
+    rad_tol, mm_tol = (2e-5, 0.02) if precision == native.PRECISION_FP32 else (PARITY_RAD, PARITY_MM)
+    pose = torch.cat([out['root_ori_hat'], out['pose_hat']], dim=-1).cpu().numpy()
+    want_pose = torch.cat([want['root_ori_hat'], want['pose_hat']], dim=-1).numpy()
+    assert util.max_joint_angle_err(pose[live], want_pose[live]) <= rad_tol
+    assert util.max_joint_pos_err_mm(out['joints_hat'].cpu().numpy()[live], want['joints_hat'].numpy()[live]) <= mm_tol
+
+
+def test_window_shape_is_shared_and_batch_shards_are_independent(dev, smpl_npz):
+    """Size-independent properties at a larger size: one shape per window (models.py:529-535) and
+    window independence (what lets inference shard over GPUs without a collective)."""
+    net = util.build_module(smpl_npz, precision=native.PRECISION_TF32, device=dev)
+    ctx = net.native_context(dev)
+    b, f = 512, 32
+    p = synthetic.synth_window_params(b, f, seed=77, offsets=True)
+    t = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    poses = t(p['poses']).reshape(b * f, 66)
+    shapes = t(p['shapes']).unsqueeze(1).repeat(1, f, 1).reshape(b * f, 10)
+    off_r = t(p['offset_r']).unsqueeze(1).repeat(1, f, 1, 1, 1).reshape(b * f, 12, 3, 3)
+    off_t = t(p['offset_t']).unsqueeze(1).repeat(1, f, 1, 1).reshape(b * f, 12, 3)
+    pos, ori, _ = ctx.sensor_project(poses, shapes, off_r, off_t)
+    mpos = (pos + 0.01 * torch.randn(pos.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3))).reshape(b, f, 36)
+    mori = ori.reshape(b, f, 108)
+    lengths = t(p['seq_lengths'])
+    full = ctx.forward(mpos, mori, t(p['offset_r']), t(p['offset_t']), lengths, want_history=False)
+    assert torch.isfinite(full['pose']).all() and torch.isfinite(full['joints']).all()
+    assert (full['shape'] - full['shape'][:, :1]).abs().max().item() == 0.0
+    half = ctx.forward(mpos[256:], mori[256:], t(p['offset_r'])[256:], t(p['offset_t'])[256:], lengths[256:], want_history=False)
+    assert torch.equal(half['pose'], full['pose'][256:]) and torch.equal(half['joints'], full['joints'][256:])
+
+
+def test_host_buffer_entry_point_matches_device_entry_point(dev, smpl_npz, oracle_smpl, topology):
+    net = util.build_module(smpl_npz, precision=native.PRECISION_TF32, device=dev)
+    ctx = net.native_context(dev)
+    params = synthetic.synth_window_params(4, 16, seed=9, ragged=True, offsets=True)
+    inp = util.oracle_inputs_from_params(oracle_smpl, topology, params, seed=2)
+    d = {k: (v.to(dev) if v is not None else None) for k, v in inp.items()}
+    a = ctx.forward(d['marker_pos'], d['marker_oris'], d['offset_r'], d['offset_t'], d['seq_lengths'], want_history=False)
+    h = ctx.forward_host(inp['marker_pos'], inp['marker_oris'], inp['offset_r'], inp['offset_t'], inp['seq_lengths'])
+    assert torch.equal(a['pose'].cpu(), h['pose']) and torch.equal(a['joints'].cpu(), h['joints'])
+    assert torch.equal(a['lstm_state'].cpu(), h['lstm_state'])

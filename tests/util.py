@@ -52,3 +52,74 @@ def max_joint_pos_err_mm(j_a, j_b):
     d = (np.asarray(j_a, dtype=np.float64) - np.asarray(j_b, dtype=np.float64))
     d = d.reshape(d.shape[:-1] + (-1, 3))
     return float(np.sqrt((d * d).sum(-1)).max() * 1000.0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# product-side helpers
+# ----------------------------------------------------------------------------------------------------------------------
+class DuckBatch(object):
+    """The slice of the reference's ``ABatch`` interface the model reads (data.py:304-309, 433-459)."""
+
+    def __init__(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None):
+        self.marker_pos, self.marker_oris = marker_pos, marker_oris
+        self.offset_r, self.offset_t = offset_r, offset_t
+        self.seq_lengths = seq_lengths
+        self.marker_masks = marker_masks
+
+    @property
+    def batch_size(self):
+        return self.marker_pos.shape[0]
+
+    @property
+    def seq_length(self):
+        return self.marker_pos.shape[1]
+
+    def get_inputs(self, sf=None, ef=None, **kwargs):
+        return {'marker_pos': self.marker_pos[:, sf:ef], 'marker_oris': self.marker_oris[:, sf:ef],
+                'offset_r': self.offset_r, 'offset_t': self.offset_t,
+                'marker_masks': None if self.marker_masks is None else self.marker_masks[:, sf:ef]}
+
+    def to(self, device):
+        mv = lambda t: None if t is None else t.to(device)
+        return DuckBatch(mv(self.marker_pos), mv(self.marker_oris), mv(self.offset_r), mv(self.offset_t),
+                         mv(self.seq_lengths), mv(self.marker_masks))
+
+
+def build_module(smpl_npz, n_markers=12, num_iterations=4, rnn_init=True, precision=0, device='cpu', hidden_size=512,
+                 **config_overrides):
+    """An ``empose_b200`` IterativeErrorFeedback in eval mode carrying the deterministic synthetic weights."""
+    from empose_b200 import synthetic
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from empose_b200.helpers.configuration import lgd_config
+    from empose_b200.nn.models import IterativeErrorFeedback
+    cfg = lgd_config(n_markers=n_markers, num_iterations=num_iterations, rnn_init=rnn_init, hidden_size=hidden_size,
+                     **config_overrides)
+    smpl = SMPLLayer(smpl_npz).to(dtype=torch.float32)
+    net = IterativeErrorFeedback(cfg, smpl, precision=precision)
+    sd = net.state_dict()
+    synth = synthetic.synth_state_dict(seed=0, n_markers=n_markers, rnn_init=rnn_init, hidden_size=hidden_size,
+                                       rnn_hidden_size=cfg.m_rnn_hidden_size, num_layers=cfg.m_num_layers,
+                                       batch_norm=not cfg.m_no_batch_norm)
+    for k, v in synth.items():
+        sd[k] = torch.from_numpy(np.asarray(v))
+    net.load_state_dict(sd, strict=True)
+    return net.to(device).eval()
+
+
+def oracle_inputs_from_params(oracle_smpl, topology, params, seed):
+    """Synthetic measured sensors for ``synth_window_params`` output via the oracle projection (CPU, float64)."""
+    from empose_b200 import synthetic
+    from oracle import ief as oracle_ief
+    b, f = params['poses'].shape[:2]
+    t = lambda a: torch.from_numpy(np.asarray(a)).double()
+    poses = t(params['poses']).reshape(b * f, 66)
+    shapes = t(params['shapes']).unsqueeze(1).repeat(1, f, 1).reshape(b * f, 10)
+    off_r = t(params['offset_r']).unsqueeze(1).repeat(1, f, 1, 1, 1).reshape(b * f, 12, 3, 3)
+    off_t = t(params['offset_t']).unsqueeze(1).repeat(1, f, 1, 1).reshape(b * f, 12, 3)
+    with torch.no_grad():
+        pos, ori, _ = oracle_ief.project_sensors(oracle_smpl, topology, poses, shapes, off_r, off_t)
+    mpos, mori = synthetic.synth_measurements(pos.reshape(b, f, 12, 3).numpy(), ori.reshape(b, f, 12, 3, 3).numpy(), seed=seed)
+    masks = None if params['marker_masks'] is None else torch.from_numpy(params['marker_masks'])
+    return dict(marker_pos=torch.from_numpy(mpos), marker_oris=torch.from_numpy(mori),
+                offset_r=torch.from_numpy(params['offset_r']), offset_t=torch.from_numpy(params['offset_t']),
+                seq_lengths=torch.from_numpy(params['seq_lengths']), marker_masks=masks)
