@@ -12,6 +12,23 @@ namespace {
 
 __device__ __forceinline__ float maybe_round(float x, int round_out) { return round_out ? round_tf32(x) : x; }
 
+// pose features of one joint: vec(R - I), optionally split into a tf32 value and its tf32 residual
+__device__ __forceinline__ void write_pose_features(const float* r, float* dst, int split) {
+    float R[9];
+    rodrigues_fwd(r, R);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+        const float v = R[e] - ((e % 4 == 0) ? 1.0f : 0.0f);
+        if (split) {
+            const float hi = round_tf32(v);
+            dst[e] = hi;
+            dst[kPoseFeatPad + e] = round_tf32(v - hi);
+        } else {
+            dst[e] = v;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prepare_kernel(PrepareParams p) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,26 +103,18 @@ __global__ void __launch_bounds__(128) update_kernel(UpdateParams p) {
         const int f = i / (kJoints - 1), j = 1 + i % (kJoints - 1);
         const int64_t row = row0 + f;
         float r[3] = {p.theta[row * kPoseDim + j * 3], p.theta[row * kPoseDim + j * 3 + 1], p.theta[row * kPoseDim + j * 3 + 2]};
-        float R[9];
-        rodrigues_fwd(r, R);
-        float* dst = p.pf + row * kPoseFeatPad + (j - 1) * 9;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) dst[e] = maybe_round(R[e] - ((e % 4 == 0) ? 1.0f : 0.0f), p.round_out);
+        write_pose_features(r, p.pf + row * p.pf_stride + (j - 1) * 9, p.pf_split);
     }
 }
 
-__global__ void __launch_bounds__(256) pose_feature_kernel(const float* __restrict__ theta, float* __restrict__ pf, int R,
-                                                           int round_out) {
+__global__ void __launch_bounds__(256) pose_feature_kernel(const float* __restrict__ theta, float* __restrict__ pf,
+                                                           int pf_stride, int pf_split, int R) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)R * (kJoints - 1)) return;
     const int64_t row = i / (kJoints - 1);
     const int j = 1 + (int)(i % (kJoints - 1));
     float r[3] = {theta[row * kPoseDim + j * 3], theta[row * kPoseDim + j * 3 + 1], theta[row * kPoseDim + j * 3 + 2]};
-    float Rm[9];
-    rodrigues_fwd(r, Rm);
-    float* dst = pf + row * kPoseFeatPad + (j - 1) * 9;
-#pragma unroll
-    for (int e = 0; e < 9; ++e) dst[e] = maybe_round(Rm[e] - ((e % 4 == 0) ? 1.0f : 0.0f), round_out);
+    write_pose_features(r, pf + row * pf_stride + (j - 1) * 9, pf_split);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -217,8 +226,8 @@ int launch_update(const UpdateParams& p, cudaStream_t s) {
     return EMPOSE_OK;
 }
 
-int launch_pose_features(const float* theta, float* pf, int R, int round_out, cudaStream_t s) {
-    pose_feature_kernel<<<blocks_for((int64_t)R * (kJoints - 1), 256), 256, 0, s>>>(theta, pf, R, round_out);
+int launch_pose_features(const float* theta, float* pf, int pf_stride, int pf_split, int R, cudaStream_t s) {
+    pose_feature_kernel<<<blocks_for((int64_t)R * (kJoints - 1), 256), 256, 0, s>>>(theta, pf, pf_stride, pf_split, R);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

@@ -40,14 +40,16 @@ struct UpdateParams {
     int round_out;
     float* xiter;               // [R][iter_in] or null: columns [in_size, in_size+76) receive theta | beta
     int in_size, iter_in;
-    float* pf;                  // [R][192] pose features vec(R_1..R_21 - I)
+    float* pf;                  // [R][pf_stride] pose features vec(R_1..R_21 - I); split: [hi(192) | lo(192)]
+    int pf_stride;              // 192, or 384 when split
+    int pf_split;               // 1: write tf32 hi part and tf32 residual (error-compensated pose-blend GEMM)
     float* hist_pose;           // [R][66] or null
     float* hist_shape;          // [R][10] or null
 };
 int launch_update(const UpdateParams& p, cudaStream_t s);
 
 // pose features only (for empose_sensor_project)
-int launch_pose_features(const float* theta, float* pf, int R, int round_out, cudaStream_t s);
+int launch_pose_features(const float* theta, float* pf, int pf_stride, int pf_split, int R, cudaStream_t s);
 
 // SMPL sub-model forward (+ reverse) per frame.
 struct MainParams {

@@ -73,54 +73,84 @@ __host__ __device__ inline int lstm_unit_of_packed(int n) { return (n / 32) * 8 
 __host__ __device__ inline int lstm_gate_of_packed(int n) { return (n % 32) / 8; }
 
 #if defined(__CUDACC__)
-// Process 32 consecutive accumulator columns [c0, c0+32) (c0 relative to the job, multiple of 32)
-// of one row.  `v` holds the raw fp32 accumulators.
-__device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row, int c0, float (&v)[32]) {
-    if (row >= j.m_rows) return;
+constexpr int kStageLd = 33;                       // padded row pitch of the per-warp staging tile
+constexpr int kStageFloats = 32 * kStageLd;        // one warp-private [32][33] fp32 tile
+
+// Epilogue of 32 consecutive accumulator columns [c0, c0+32) (c0 relative to the job, multiple of 32)
+// for the 32 rows [row0, row0+32) owned by one warp: lane l holds row row0+l in `v` (the TMEM lane
+// layout).  Results go through a warp-private shared-memory tile so that every global store (and the
+// LSTM cell-state read-modify-write) is a fully coalesced row segment instead of 32 scattered words.
+// Must be called by all 32 lanes of the warp.
+__device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int lane, int c0, float (&v)[32], float* stage) {
     const int n0 = j.n_begin + c0;                 // global column of v[0]
+    const int row = row0 + lane;
     if (j.epi == EPI_LINEAR) {
         bool masked = false;
-        if (j.mask_rows) masked = (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window];
+        if (j.mask_rows && row < j.m_rows) masked = (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            const int n = n0 + i;
-            if (c0 + i >= j.n_count || n >= j.n_valid) continue;
             float y = masked ? 0.0f : v[i];
-            if (j.bias) y += j.bias[n];
+            const int n = n0 + i;
+            if (j.bias && n < j.n_valid) y += j.bias[n];
             if (j.has_act) y = y > 0.0f ? y : j.prelu_alpha * y;
-            if (j.res) y += j.res[(int64_t)row * j.res_stride + j.out_col0 + n];
+            if (j.res && row < j.m_rows && n < j.n_valid) y += j.res[(int64_t)row * j.res_stride + j.out_col0 + n];
             if (j.round_out) y = round_tf32(y);
-            if (n < j.split) j.out[(int64_t)row * j.out_stride + j.out_col0 + n] = y;
-            else j.out2[(int64_t)row * j.out2_stride + (n - j.split)] = y;
+            stage[lane * kStageLd + i] = y;
         }
-    } else {  // EPI_LSTM
+        __syncwarp();
+        const int n = n0 + lane;
+        const bool col_ok = (c0 + lane < j.n_count) && (n < j.n_valid);
+        float* dst;
+        int64_t stride;
+        if (n < j.split) { dst = j.out + j.out_col0 + n; stride = j.out_stride; }
+        else { dst = j.out2 + (n - j.split); stride = j.out2_stride; }
+        const int rows = min(32, j.m_rows - row0);
+        if (col_ok)
+            for (int r = 0; r < rows; ++r) dst[(int64_t)(row0 + r) * stride] = stage[r * kStageLd + lane];
+        __syncwarp();
+    } else {  // EPI_LSTM: 8 hidden units x 4 gates per chunk
         const int unit0 = lstm_unit_of_packed(n0);
-        const bool live = j.t < j.seq_len[row];
-        float* c_ptr = j.c_state + (int64_t)row * j.hidden + unit0;
-        float* h_ptr = j.out + (int64_t)row * j.out_stride + unit0;
-        if (live) {
+        float* sc = stage;                 // [32][9] cell state
+        float* sh = stage + 32 * 9;        // [32][9] carried / new hidden state
+        const int sub = lane >> 3, u = lane & 7;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float gi = v[u] + j.bias[n0 + u];
-                const float gf = v[8 + u] + j.bias[n0 + 8 + u];
-                const float gg = v[16 + u] + j.bias[n0 + 16 + u];
-                const float go = v[24 + u] + j.bias[n0 + 24 + u];
+        for (int q = 0; q < 8; ++q) {      // coalesced: 4 rows x 8 units per instruction
+            const int r = q * 4 + sub;
+            if (row0 + r < j.m_rows) {
+                sc[r * 9 + u] = j.c_state[(int64_t)(row0 + r) * j.hidden + unit0 + u];
+                sh[r * 9 + u] = j.h_prev[(int64_t)(row0 + r) * j.h_prev_stride + unit0 + u];
+            }
+        }
+        __syncwarp();
+        if (row < j.m_rows && j.t < j.seq_len[row]) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gi = v[k] + j.bias[n0 + k];
+                const float gf = v[8 + k] + j.bias[n0 + 8 + k];
+                const float gg = v[16 + k] + j.bias[n0 + 16 + k];
+                const float go = v[24 + k] + j.bias[n0 + 24 + k];
                 float c_new, h_new;
                 if (j.round_out) {
-                    c_new = sigmoid_f(gf) * c_ptr[u] + sigmoid_f(gi) * tanh_f(gg);
+                    c_new = sigmoid_f(gf) * sc[lane * 9 + k] + sigmoid_f(gi) * tanh_f(gg);
                     h_new = round_tf32(sigmoid_f(go) * tanh_f(c_new));
                 } else {
-                    c_new = (1.0f / (1.0f + expf(-gf))) * c_ptr[u] + (1.0f / (1.0f + expf(-gi))) * tanhf(gg);
+                    c_new = (1.0f / (1.0f + expf(-gf))) * sc[lane * 9 + k] + (1.0f / (1.0f + expf(-gi))) * tanhf(gg);
                     h_new = (1.0f / (1.0f + expf(-go))) * tanhf(c_new);
                 }
-                c_ptr[u] = c_new;
-                h_ptr[u] = h_new;
+                sc[lane * 9 + k] = c_new;
+                sh[lane * 9 + k] = h_new;
             }
-        } else {
-            const float* hp = j.h_prev + (int64_t)row * j.h_prev_stride + unit0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) h_ptr[u] = hp[u];
         }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = q * 4 + sub;
+            if (row0 + r < j.m_rows) {
+                j.c_state[(int64_t)(row0 + r) * j.hidden + unit0 + u] = sc[r * 9 + u];
+                j.out[(int64_t)(row0 + r) * j.out_stride + unit0 + u] = sh[r * 9 + u];
+            }
+        }
+        __syncwarp();
     }
 }
 #endif

@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(kTileM) gemm_simt_kernel(const GemmJob* __rest
     const GemmJob j = jobs[job_index];
     __shared__ float a_s[kChunkK][kTileM + 1];
     __shared__ float w_s[kChunkK][33];
+    __shared__ float epi_stage[(kTileM / 32) * kStageFloats];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * kTileM;
     const int c0 = blockIdx.y * 32;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kTileM) gemm_simt_kernel(const GemmJob* __rest
             __syncthreads();
         }
     }
-    epilogue_chunk(j, m0 + tid, c0, acc);
+    epilogue_chunk(j, m0 + (tid & ~31), tid & 31, c0, acc, epi_stage + (tid >> 5) * kStageFloats);
 }
 
 }  // namespace

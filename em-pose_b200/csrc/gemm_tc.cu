@@ -42,7 +42,8 @@ struct __align__(8) Control {
     volatile uint32_t epi_done;
 };
 
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*Control*/;
+constexpr int kEpiStageBytes = 4 * kStageFloats * 4;     // one [32][33] fp32 transpose tile per epilogue warp
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*alignment slack*/ + 256 /*Control*/;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                                               int job_count, int jobs_per_item, int m_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    Control* ctl = reinterpret_cast<Control*>(smem + kStages * kStageBytes);
+    float* epi_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+    Control* ctl = reinterpret_cast<Control*>(smem + kStages * kStageBytes + kEpiStageBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,12 +253,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 const uint32_t buf = seq & 1u;
                 mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 tcgen05_fence_after();
-                const int row = m0 + ew * 32 + lane;
+                const int row0 = m0 + ew * 32;
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * kMaxTileN;
                 for (int c0 = 0; c0 < job.n_count; c0 += 32) {
                     float v[32];
                     tmem_load_32cols(taddr + (uint32_t)c0, v);
-                    epilogue_chunk(job, row, c0, v);
+                    epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats);
                 }
                 tcgen05_fence_before();
                 __threadfence();                                  // stores visible at L2 ...

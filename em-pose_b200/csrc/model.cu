@@ -332,6 +332,7 @@ struct empose_ief {
     int num_sms = 148;
     int in_size = 0, iter_in = 0, n_pos = 0;
     bool round = true;         // TF32 mode
+    int pf_stride = kPoseFeatPad;   // floats per row of the pose-feature buffer (2x when split hi|lo)
     Arena arena;
     SubModel sub;
     ResidualSpec spec;
@@ -343,16 +344,43 @@ struct empose_ief {
     std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
     std::map<int, std::unique_ptr<Plan>> project_plans;
     int64_t last_launches = 0;
+    // optional per-launch timing of the GEMM executor (empose_ief_set_profiling)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    ~empose_ief() {
+        for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    }
 };
 
 namespace empose {
 namespace {
 
+// A operand of the pose-blend GEMM: [pf_hi | pf_lo] then pf_hi again in TF32 mode, plain pf in FP32 mode
+ASrc pose_blend_a0(const empose_ief* ctx, const float* pf, int rows) {
+    return ASrc{pf, ctx->pf_stride, ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad, rows};
+}
+ASrc pose_blend_a1(const empose_ief* ctx, const float* pf, int rows) {
+    return ctx->round ? ASrc{pf, ctx->pf_stride, kPoseFeatPad, rows} : ASrc{};
+}
+
 int run_jobs(empose_ief* ctx, Plan& pl, const JobRange& r, int m_tiles, cudaStream_t s) {
     if (r.count == 0) return EMPOSE_OK;
     if (ctx->round) {
         ++ctx->last_launches;
-        return tc_launch(pl.book.d_jobs, pl.book.d_maps, r.begin, r.count, r.per_item, m_tiles, ctx->num_sms, s);
+        if (!ctx->profiling)
+            return tc_launch(pl.book.d_jobs, pl.book.d_maps, r.begin, r.count, r.per_item, m_tiles, ctx->num_sms, s);
+        if (ctx->prof_used == ctx->prof_events.size()) {
+            cudaEvent_t a, b;
+            EMPOSE_CUDA_TRY(cudaEventCreate(&a));
+            EMPOSE_CUDA_TRY(cudaEventCreate(&b));
+            ctx->prof_events.emplace_back(a, b);
+        }
+        auto& ev = ctx->prof_events[ctx->prof_used++];
+        EMPOSE_CUDA_TRY(cudaEventRecord(ev.first, s));
+        const int rc = tc_launch(pl.book.d_jobs, pl.book.d_maps, r.begin, r.count, r.per_item, m_tiles, ctx->num_sms, s);
+        EMPOSE_CUDA_TRY(cudaEventRecord(ev.second, s));
+        return rc;
     }
     return simt_launch(pl.book.d_jobs, pl.book.jobs.data(), r.begin, r.count, m_tiles, s, &ctx->last_launches);
 }
@@ -410,7 +438,7 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
     EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.beta));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.dtheta));
     EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.dbeta));
-    EMPOSE_TRY(A.alloc_n(Rz * kPoseFeatPad, &pl.pf, true));
+    EMPOSE_TRY(A.alloc_n(Rz * ctx->pf_stride, &pl.pf, true));
     EMPOSE_TRY(A.alloc_n(Rz * vp, &pl.vpoff));
     EMPOSE_TRY(A.alloc_n(Rz * vp, &pl.dvp));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseFeatPad, &pl.dpf));
@@ -472,7 +500,7 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
     EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_iter, ctx->shape_iter, pl.xiter, ctx->iter_in, ctx->iter_in, &pl.iter_chain));
     {
         GemmJob proto = linear_proto(ctx->pb, false, pl.vpoff, vp, vp);
-        EMPOSE_TRY(pl.book.add(ctx->pb, ASrc{pl.pf, kPoseFeatPad, kPoseFeatPad, R}, ASrc{}, proto, m_rows_R, -1, &pl.pb));
+        EMPOSE_TRY(pl.book.add(ctx->pb, pose_blend_a0(ctx, pl.pf, R), pose_blend_a1(ctx, pl.pf, R), proto, m_rows_R, -1, &pl.pb));
         GemmJob proto_t = linear_proto(ctx->pbt, false, pl.dpf, kPoseFeatPad, kPoseFeatPad);
         EMPOSE_TRY(pl.book.add(ctx->pbt, ASrc{pl.dvp, vp, vp, R}, ASrc{}, proto_t, m_rows_R, -1, &pl.pbt));
     }
@@ -491,10 +519,10 @@ int project_plan(empose_ief* ctx, int R, Plan** out) {
     pl.R = R; pl.B = R; pl.F = 1;
     pl.book.use_tc = ctx->round;
     const int vp = ctx->sub.vp_dim;
-    EMPOSE_TRY(pl.arena.alloc_n((size_t)R * kPoseFeatPad, &pl.pf, true));
+    EMPOSE_TRY(pl.arena.alloc_n((size_t)R * ctx->pf_stride, &pl.pf, true));
     EMPOSE_TRY(pl.arena.alloc_n((size_t)R * vp, &pl.vpoff));
     GemmJob proto = linear_proto(ctx->pb, false, pl.vpoff, vp, vp);
-    EMPOSE_TRY(pl.book.add(ctx->pb, ASrc{pl.pf, kPoseFeatPad, kPoseFeatPad, R}, ASrc{}, proto, R, -1, &pl.pb));
+    EMPOSE_TRY(pl.book.add(ctx->pb, pose_blend_a0(ctx, pl.pf, R), pose_blend_a1(ctx, pl.pf, R), proto, R, -1, &pl.pb));
     EMPOSE_TRY(pl.book.finalize(pl.arena));
     *out = plp.get();
     ctx->project_plans[R] = std::move(plp);
@@ -577,8 +605,27 @@ int upload_submodel(empose_ief* ctx, const TensorTable& tt) {
     std::vector<float> pt((size_t)vp * kPoseFeat);
     for (int i = 0; i < vp; ++i)
         for (int k = 0; k < kPoseFeat; ++k) pt[(size_t)i * kPoseFeat + k] = P[(size_t)k * vp + i];
-    EMPOSE_TRY(pack_matrix(ctx->arena, vp, kPoseFeat, 0, 16, ctx->round, false,
-                           [&](int r) { return RowSource{&pt[(size_t)r * kPoseFeat], nullptr, 1.0, 0.0}; }, &ctx->pb));
+    if (ctx->round) {
+        // Error-compensated (3xTF32) pose blend by K-concatenation: with x = x_hi + x_lo (both tf32),
+        //   [pf_hi | pf_lo | pf_hi] . [P_hi | P_hi | P_lo]^T = pf_hi P_hi + pf_lo P_hi + pf_hi P_lo.
+        // The vertex offsets feed cross products of ~1 cm mesh edges, which amplify plain TF32 rounding
+        // into ~1e-3 rad of sensor-orientation noise; the split brings it back to fp32 level.
+        std::vector<float> w0((size_t)vp * 2 * kPoseFeatPad, 0.0f), w1((size_t)vp * kPoseFeat, 0.0f);
+        for (int i = 0; i < vp; ++i)
+            for (int k = 0; k < kPoseFeat; ++k) {
+                const float v = pt[(size_t)i * kPoseFeat + k];
+                const float hi = host_round_tf32(v);
+                w0[(size_t)i * 2 * kPoseFeatPad + k] = hi;
+                w0[(size_t)i * 2 * kPoseFeatPad + kPoseFeatPad + k] = hi;
+                w1[(size_t)i * kPoseFeat + k] = host_round_tf32(v - hi);
+            }
+        EMPOSE_TRY(pack_matrix(ctx->arena, vp, 2 * kPoseFeatPad, kPoseFeat, 16, true, false, [&](int r) {
+            return RowSource{&w0[(size_t)r * 2 * kPoseFeatPad], &w1[(size_t)r * kPoseFeat], 1.0, 0.0};
+        }, &ctx->pb));
+    } else {
+        EMPOSE_TRY(pack_matrix(ctx->arena, vp, kPoseFeat, 0, 16, false, false,
+                               [&](int r) { return RowSource{&pt[(size_t)r * kPoseFeat], nullptr, 1.0, 0.0}; }, &ctx->pb));
+    }
     EMPOSE_TRY(pack_matrix(ctx->arena, kPoseFeat, vp, 0, 16, ctx->round, false,
                            [&](int r) { return RowSource{P + (size_t)r * vp, nullptr, 1.0, 0.0}; }, &ctx->pbt));
     return EMPOSE_OK;
@@ -668,6 +715,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         up.step = cfg.step_size; up.first = (it == 0); up.average_shape = cfg.average_shape;
         up.B = B; up.F = F; up.round_out = rnd;
         up.xiter = pl.xiter; up.in_size = ctx->in_size; up.iter_in = ctx->iter_in; up.pf = pl.pf;
+        up.pf_stride = ctx->pf_stride; up.pf_split = rnd;
         if (hist && hist->pose) up.hist_pose = hist->pose + (size_t)it * R * kPoseDim;
         if (hist && hist->shape) up.hist_shape = hist->shape + (size_t)it * R * kBetas;
         EMPOSE_TRY(count(launch_update(up, s)));
@@ -747,6 +795,7 @@ int empose_ief_create(const empose_ief_config* cfg, const empose_tensor* tensors
     ctx->cfg = *cfg;
     ctx->num_sms = prop.multiProcessorCount;
     ctx->round = cfg->precision == EMPOSE_PRECISION_TF32;
+    ctx->pf_stride = ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad;
     ctx->n_pos = cfg->use_marker_pos ? 3 * cfg->n_markers : 0;
     ctx->in_size = ctx->n_pos + (cfg->use_marker_ori ? 9 * cfg->n_markers : 0);
     ctx->iter_in = ctx->in_size + kPoseDim + kBetas + (cfg->use_gradient ? kPoseDim + kBetas : 0);
@@ -778,6 +827,29 @@ void empose_ief_destroy(empose_ief* ctx) {
 }
 
 int64_t empose_ief_last_launch_count(const empose_ief* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int empose_ief_set_profiling(empose_ief* ctx, int32_t enable) {
+    if (!ctx) { set_last_error("null context"); return EMPOSE_E_ARG; }
+    ctx->profiling = enable != 0;
+    ctx->prof_used = 0;
+    return EMPOSE_OK;
+}
+
+int empose_ief_profile_read(empose_ief* ctx, double* gemm_ms, int64_t* gemm_launches) {
+    if (!ctx || !gemm_ms || !gemm_launches) { set_last_error("null argument"); return EMPOSE_E_ARG; }
+    EMPOSE_CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    double total = 0.0;
+    for (size_t i = 0; i < ctx->prof_used; ++i) {
+        EMPOSE_CUDA_TRY(cudaEventSynchronize(ctx->prof_events[i].second));
+        float ms = 0.0f;
+        EMPOSE_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second));
+        total += ms;
+    }
+    *gemm_ms = total;
+    *gemm_launches = (int64_t)ctx->prof_used;
+    ctx->prof_used = 0;
+    return EMPOSE_OK;
+}
 
 int empose_ief_forward(empose_ief* ctx, const float* marker_pos, const float* marker_oris, const float* offset_r,
                        const float* offset_t, const int32_t* seq_lengths, const float* marker_masks, float* lstm_state,
@@ -861,7 +933,7 @@ int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shap
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int rnd = ctx->round ? 1 : 0;
     ctx->last_launches = 1;
-    EMPOSE_TRY(launch_pose_features(poses, pl->pf, R, rnd, s));
+    EMPOSE_TRY(launch_pose_features(poses, pl->pf, ctx->pf_stride, rnd, R, s));
     EMPOSE_TRY(run_jobs(ctx, *pl, pl->pb, ceil_div(R, kTileM), s));
     MainParams mp;
     memset(&mp, 0, sizeof(mp));

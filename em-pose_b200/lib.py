@@ -20,7 +20,8 @@ _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2
 #: every symbol include/empose_b200.h declares (checked by tests/test_cabi.py)
 EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_create', 'empose_ief_destroy',
                     'empose_ief_forward', 'empose_ief_forward_host', 'empose_sensor_project',
-                    'empose_ief_last_launch_count', 'empose_gemm_selftest')
+                    'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read',
+                    'empose_gemm_selftest')
 
 
 class EmposeError(RuntimeError):
@@ -74,6 +75,10 @@ def load():
     lib.empose_sensor_project.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.empose_ief_last_launch_count.restype = ctypes.c_int64
     lib.empose_ief_last_launch_count.argtypes = [vp]
+    lib.empose_ief_set_profiling.restype = ctypes.c_int
+    lib.empose_ief_set_profiling.argtypes = [vp, i32]
+    lib.empose_ief_profile_read.restype = ctypes.c_int
+    lib.empose_ief_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     lib.empose_gemm_selftest.restype = ctypes.c_int
     lib.empose_gemm_selftest.argtypes = [i32, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, i32, i32,
                                          i32, vp]
@@ -153,6 +158,15 @@ class IefContext(object):
     @property
     def last_launch_count(self):
         return int(load().empose_ief_last_launch_count(self._handle))
+
+    def set_profiling(self, enable):
+        _check(load().empose_ief_set_profiling(self._handle, int(bool(enable))))
+
+    def profile_read(self):
+        """(summed device ms of the GEMM executor launches, number of launches) since the last read."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        _check(load().empose_ief_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     def forward(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None, lstm_state=None,
                 is_new_sequence=True, want_history=True):

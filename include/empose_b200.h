@@ -14,7 +14,6 @@
  *                                     chunk.to_gpu(), net(chunk), .cpu())
  *   empose_sensor_project          <- IterativeErrorFeedback.get_estimated_real_markers
  *                                                                                 empose/nn/models.py:471-483
- *   empose_smpl_forward            <- SMPLLayer.forward / fk / _fk                empose/bodymodels/smpl.py:81-165
  *   empose_gemm_selftest           <- (no reference counterpart) checks the tcgen05 GEMM engine
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
@@ -139,6 +138,12 @@ int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shap
 
 /* Number of kernels the last empose_ief_forward* call on this context launched (for bench accounting). */
 int64_t empose_ief_last_launch_count(const empose_ief* ctx);
+
+/* Optional timing of the tensor-core GEMM executor: while enabled, every executor launch is bracketed by
+ * CUDA events on its stream (TF32 mode only).  empose_ief_profile_read waits for them, returns the summed
+ * device time and the number of launches since the last read / enable, and resets the counters. */
+int empose_ief_set_profiling(empose_ief* ctx, int32_t enable);
+int empose_ief_profile_read(empose_ief* ctx, double* gemm_ms, int64_t* gemm_launches);
 
 /* Engine self-test: C[M][N] = A[M][K] . W[N][K]^T + bias through the same job executor the model uses
  * (precision selects tcgen05 or FFMA).  Device pointers; lda / ldw / ldc in floats. */

@@ -44,7 +44,7 @@ def test_gemm_engine(dev, precision, m, n, k):
     want = (a.double() @ w.double().T + bias.double()).float()
     err = (got - want).abs().max().item()
     # tf32 inputs carry 2^-11 relative rounding (truncation in the worst case 2^-10): |a||w| ~ 1 per term, sqrt(k) growth
-    tol = 2e-5 if precision == native.PRECISION_FP32 else 4e-3
+    tol = 2e-5 if precision == native.PRECISION_FP32 else 1e-2
     assert err < tol, 'max abs err %g' % err
     if precision == native.PRECISION_TF32:          # same operands pre-rounded: only accumulation order differs
         r = lambda t: (t.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)
@@ -70,6 +70,9 @@ def test_sensor_projection_matches_oracle(dev, smpl_npz, oracle_smpl, topology, 
     with torch.no_grad():
         o_pos, o_ori, o_j = oracle_ief.project_sensors(oracle_smpl, topology, poses.double(), shapes.double(),
                                                        off_r.double(), off_t.double())
+    util.report('sensor_project', precision=PNAME[precision], joints_mm=util.max_joint_pos_err_mm(joints.cpu().numpy(), o_j.numpy()),
+                pos_mm=util.max_joint_pos_err_mm(pos.cpu().numpy(), o_pos.numpy()),
+                ori=float(np.abs(ori.cpu().numpy() - o_ori.numpy()).max()))
     assert util.max_joint_pos_err_mm(joints.cpu().numpy(), o_j.numpy()) < 0.005
     assert util.max_joint_pos_err_mm(pos.cpu().numpy(), o_pos.numpy()) < 0.01
     np.testing.assert_allclose(ori.cpu().numpy(), o_ori.numpy(), atol=2e-4, rtol=0)
@@ -103,6 +106,10 @@ def test_ief_matches_reference_golden(dev, smpl_npz, name, precision):
         tag = 'c%d_' % c
         live = util.valid_frame_mask(gold[tag + 'seq_lengths'], inp['marker_pos'].shape[1])
         got = {k: v.cpu().numpy() for k, v in out.items()}
+        util.report('golden', case=name, chunk=c, precision=PNAME[precision],
+                    rad=max(util.max_joint_angle_err(got['pose_hat'][live], gold[tag + 'pose_hat'][live]),
+                            util.max_joint_angle_err(got['root_ori_hat'][live], gold[tag + 'root_ori_hat'][live])),
+                    mm=util.max_joint_pos_err_mm(got['joints_hat'][live], gold[tag + 'joints_hat'][live]))
         assert util.max_joint_angle_err(got['pose_hat'][live], gold[tag + 'pose_hat'][live]) <= rad_tol
         assert util.max_joint_angle_err(got['root_ori_hat'][live], gold[tag + 'root_ori_hat'][live]) <= rad_tol
         assert util.max_joint_pos_err_mm(got['joints_hat'][live], gold[tag + 'joints_hat'][live]) <= mm_tol
@@ -117,7 +124,7 @@ def test_ief_matches_reference_golden(dev, smpl_npz, name, precision):
             tol = 5e-4 if 'ori' in k else rad_tol * 5
             np.testing.assert_allclose(g[:, live], gold[tag + k][:, live], atol=tol, rtol=0, err_msg=k)
         if flags['rnn_init']:
-            np.testing.assert_allclose(net.rnn.final_state[0].cpu().numpy(), gold[tag + 'final_h'], atol=2e-3 if precision else 5e-6, rtol=0)
+            np.testing.assert_allclose(net.rnn.final_state[0].cpu().numpy(), gold[tag + 'final_h'], atol=5e-6 if precision == native.PRECISION_FP32 else 2e-3, rtol=0)
         c += 1
 
 
@@ -141,8 +148,11 @@ def test_ief_matches_oracle(dev, smpl_npz, oracle_smpl, topology, precision, n_m
     rad_tol, mm_tol = (2e-5, 0.02) if precision == native.PRECISION_FP32 else (PARITY_RAD, PARITY_MM)
     pose = torch.cat([out['root_ori_hat'], out['pose_hat']], dim=-1).cpu().numpy()
     want_pose = torch.cat([want['root_ori_hat'], want['pose_hat']], dim=-1).numpy()
-    assert util.max_joint_angle_err(pose[live], want_pose[live]) <= rad_tol
-    assert util.max_joint_pos_err_mm(out['joints_hat'].cpu().numpy()[live], want['joints_hat'].numpy()[live]) <= mm_tol
+    rad = util.max_joint_angle_err(pose[live], want_pose[live])
+    mm = util.max_joint_pos_err_mm(out['joints_hat'].cpu().numpy()[live], want['joints_hat'].numpy()[live])
+    util.report('oracle', n_markers=n_markers, rnn_init=rnn_init, n_iter=n_iter, precision=PNAME[precision], rad=rad, mm=mm)
+    assert rad <= rad_tol
+    assert mm <= mm_tol
 
 
 def test_window_shape_is_shared_and_batch_shards_are_independent(dev, smpl_npz):

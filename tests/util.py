@@ -123,3 +123,15 @@ def oracle_inputs_from_params(oracle_smpl, topology, params, seed):
     return dict(marker_pos=torch.from_numpy(mpos), marker_oris=torch.from_numpy(mori),
                 offset_r=torch.from_numpy(params['offset_r']), offset_t=torch.from_numpy(params['offset_t']),
                 seq_lengths=torch.from_numpy(params['seq_lengths']), marker_masks=masks)
+
+
+def report(kind, **vals):
+    """Append one JSON line with achieved errors to gpurun_out/parity_report.jsonl (kept under profiles/)."""
+    import json
+    out_dir = os.path.join(os.path.dirname(GOLDEN_DIR.rstrip('/')).rsplit('/tests', 1)[0], 'gpurun_out')
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, 'parity_report.jsonl'), 'a') as f:
+            f.write(json.dumps(dict(kind=kind, **{k: (float(v) if isinstance(v, (float, np.floating)) else v) for k, v in vals.items()})) + '\n')
+    except OSError:
+        pass
