@@ -80,74 +80,128 @@ constexpr int kStageFloats = 32 * kStageLd;        // one warp-private [32][33] 
 // for the 32 rows [row0, row0+32) owned by one warp: lane l holds row row0+l in `v` (the TMEM lane
 // layout).  Results go through a warp-private shared-memory tile so that every global store (and the
 // LSTM cell-state read-modify-write) is a fully coalesced row segment instead of 32 scattered words.
+// Loads are batched into registers before any store so that pointer aliasing cannot serialise them.
+// Bias arrays are padded by 32 floats, so the vector loads below never leave the allocation.
 // Must be called by all 32 lanes of the warp.
-__device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int lane, int c0, float (&v)[32], float* stage) {
+__device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int lane, int c0, float (&v)[32],
+                                               float* __restrict__ stage) {
     const int n0 = j.n_begin + c0;                 // global column of v[0]
     const int row = row0 + lane;
+    float bias[32];
+    if (j.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(j.bias + n0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldg(bp + q);
+            bias[4 * q] = t.x; bias[4 * q + 1] = t.y; bias[4 * q + 2] = t.z; bias[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias[i] = 0.0f;
+    }
     if (j.epi == EPI_LINEAR) {
-        bool masked = false;
-        if (j.mask_rows && row < j.m_rows) masked = (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window];
+        if (j.mask_rows && row < j.m_rows && (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window]) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+        }
+        const float alpha = j.has_act ? j.prelu_alpha : 1.0f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            float y = masked ? 0.0f : v[i];
-            const int n = n0 + i;
-            if (j.bias && n < j.n_valid) y += j.bias[n];
-            if (j.has_act) y = y > 0.0f ? y : j.prelu_alpha * y;
-            if (j.res && row < j.m_rows && n < j.n_valid) y += j.res[(int64_t)row * j.res_stride + j.out_col0 + n];
-            if (j.round_out) y = round_tf32(y);
-            stage[lane * kStageLd + i] = y;
+            float y = v[i] + bias[i];
+            y = y > 0.0f ? y : alpha * y;
+            v[i] = y;
         }
+        if (j.res && row < j.m_rows) {
+            const float* rp = j.res + (int64_t)row * j.res_stride + j.out_col0 + n0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < j.n_valid) v[i] += rp[i];
+        }
+        if (j.round_out) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stage[lane * kStageLd + i] = v[i];
         __syncwarp();
+        float o[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) o[r] = stage[r * kStageLd + lane];
         const int n = n0 + lane;
         const bool col_ok = (c0 + lane < j.n_count) && (n < j.n_valid);
         float* dst;
         int64_t stride;
         if (n < j.split) { dst = j.out + j.out_col0 + n; stride = j.out_stride; }
         else { dst = j.out2 + (n - j.split); stride = j.out2_stride; }
-        const int rows = min(32, j.m_rows - row0);
-        if (col_ok)
-            for (int r = 0; r < rows; ++r) dst[(int64_t)(row0 + r) * stride] = stage[r * kStageLd + lane];
+        dst += (int64_t)row0 * stride;
+        const int rows = j.m_rows - row0;
+        if (col_ok) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+                if (r < rows) dst[(int64_t)r * stride] = o[r];
+        }
         __syncwarp();
     } else {  // EPI_LSTM: 8 hidden units x 4 gates per chunk
         const int unit0 = lstm_unit_of_packed(n0);
         float* sc = stage;                 // [32][9] cell state
         float* sh = stage + 32 * 9;        // [32][9] carried / new hidden state
         const int sub = lane >> 3, u = lane & 7;
+        const int rows = j.m_rows - row0;
+        float* cg = j.c_state + (int64_t)row0 * j.hidden + unit0 + u;
+        const float* hg = j.h_prev + (int64_t)row0 * j.h_prev_stride + unit0 + u;
+        float cl[8], hl[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {      // coalesced: 4 rows x 8 units per instruction
             const int r = q * 4 + sub;
-            if (row0 + r < j.m_rows) {
-                sc[r * 9 + u] = j.c_state[(int64_t)(row0 + r) * j.hidden + unit0 + u];
-                sh[r * 9 + u] = j.h_prev[(int64_t)(row0 + r) * j.h_prev_stride + unit0 + u];
-            }
+            cl[q] = r < rows ? cg[(int64_t)r * j.hidden] : 0.0f;
+            hl[q] = r < rows ? hg[(int64_t)r * j.h_prev_stride] : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            sc[(q * 4 + sub) * 9 + u] = cl[q];
+            sh[(q * 4 + sub) * 9 + u] = hl[q];
         }
         __syncwarp();
         if (row < j.m_rows && j.t < j.seq_len[row]) {
+            float c_old[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c_old[k] = sc[lane * 9 + k];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float gi = v[k] + j.bias[n0 + k];
-                const float gf = v[8 + k] + j.bias[n0 + 8 + k];
-                const float gg = v[16 + k] + j.bias[n0 + 16 + k];
-                const float go = v[24 + k] + j.bias[n0 + 24 + k];
+                const float gi = v[k] + bias[k];
+                const float gf = v[8 + k] + bias[8 + k];
+                const float gg = v[16 + k] + bias[16 + k];
+                const float go = v[24 + k] + bias[24 + k];
                 float c_new, h_new;
                 if (j.round_out) {
-                    c_new = sigmoid_f(gf) * sc[lane * 9 + k] + sigmoid_f(gi) * tanh_f(gg);
+                    c_new = sigmoid_f(gf) * c_old[k] + sigmoid_f(gi) * tanh_f(gg);
                     h_new = round_tf32(sigmoid_f(go) * tanh_f(c_new));
                 } else {
-                    c_new = (1.0f / (1.0f + expf(-gf))) * sc[lane * 9 + k] + (1.0f / (1.0f + expf(-gi))) * tanhf(gg);
+                    c_new = (1.0f / (1.0f + expf(-gf))) * c_old[k] + (1.0f / (1.0f + expf(-gi))) * tanhf(gg);
                     h_new = (1.0f / (1.0f + expf(-go))) * tanhf(c_new);
                 }
-                sc[lane * 9 + k] = c_new;
-                sh[lane * 9 + k] = h_new;
+                v[k] = c_new;
+                v[8 + k] = h_new;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sc[lane * 9 + k] = v[k];
+                sh[lane * 9 + k] = v[8 + k];
             }
         }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+            cl[q] = sc[(q * 4 + sub) * 9 + u];
+            hl[q] = sh[(q * 4 + sub) * 9 + u];
+        }
+        float* og = j.out + (int64_t)row0 * j.out_stride + unit0 + u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
             const int r = q * 4 + sub;
-            if (row0 + r < j.m_rows) {
-                j.c_state[(int64_t)(row0 + r) * j.hidden + unit0 + u] = sc[r * 9 + u];
-                j.out[(int64_t)(row0 + r) * j.out_stride + unit0 + u] = sh[r * 9 + u];
+            if (r < rows) {
+                cg[(int64_t)r * j.hidden] = cl[q];
+                og[(int64_t)r * j.out_stride] = hl[q];
             }
         }
         __syncwarp();

@@ -7,7 +7,8 @@
 //   warp 1   MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256, K=8),
 //                           accumulating in TMEM; tcgen05.commit releases ring slots and publishes accumulators
 //   warp 2   TMEM allocator 512 columns = two 128x256 fp32 accumulators (double buffered across jobs)
-//   warps 4-7 epilogue      tcgen05.ld 32 columns at a time -> epilogue_chunk() -> global memory
+//   warps 4-11 epilogue     tcgen05.ld 32 columns at a time -> epilogue_chunk() -> global memory
+//                           (two warps per TMEM lane quadrant, each taking 128 of the 256 columns)
 //
 // A work item is (row tile, group of consecutive jobs).  Jobs of one item run back to back in the
 // same CTA; a job may depend on an earlier job of its item (an MLP layer reading the previous layer's
@@ -16,6 +17,7 @@
 // between (the pose and shape MLPs are interleaved layer by layer) keep the tensor pipe busy meanwhile.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/empose_b200.h"
 #include "gemm_jobs.h"
@@ -30,8 +32,9 @@ constexpr int kABytes = kTileM * kChunkK * 4;        // 16 KB
 constexpr int kWBytes = kMaxTileN * kChunkK * 4;     // 32 KB
 constexpr int kStageBytes = kABytes + kWBytes;
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each taking half of the columns
+constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int kEpiThreads = kEpiWarps * 32;
 
 struct __align__(8) Control {
     uint64_t full[kStages];
@@ -42,7 +45,7 @@ struct __align__(8) Control {
     volatile uint32_t epi_done;
 };
 
-constexpr int kEpiStageBytes = 4 * kStageFloats * 4;     // one [32][33] fp32 transpose tile per epilogue warp
+constexpr int kEpiStageBytes = kEpiWarps * kStageFloats * 4;     // one [32][33] fp32 transpose tile per epilogue warp
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*alignment slack*/ + 256 /*Control*/;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -142,7 +145,8 @@ __device__ __forceinline__ int job_k_chunks(const GemmJob& j) {
 // ---- the kernel -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __restrict__ jobs,
                                                               const CUtensorMap* __restrict__ maps, int job_begin,
-                                                              int job_count, int jobs_per_item, int m_tiles) {
+                                                              int job_count, int jobs_per_item, int m_tiles,
+                                                              int debug_mode) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes);
@@ -198,10 +202,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                             mbar_wait(&ctl->empty[stage], phase ^ 1u);
                             uint8_t* a_dst = smem + stage * kStageBytes;
                             uint8_t* w_dst = a_dst + kABytes;
-                            mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
-                            tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * kChunkK, m0);
-                            tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * kChunkK,
-                                        job.n_begin);
+                            if (debug_mode == 2) {            // measurement only: no loads, MMAs run on stale data
+                                mbar_arrive(&ctl->full[stage]);
+                            } else {
+                                mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
+                                tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * kChunkK, m0);
+                                tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * kChunkK,
+                                            job.n_begin);
+                            }
                             if (++stage == kStages) { stage = 0; phase ^= 1u; }
                         }
                     }
@@ -228,13 +236,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
                         const uint64_t a_desc = make_smem_desc(a_addr);
                         const uint64_t b_desc = make_smem_desc(a_addr + kABytes);
+                        if (debug_mode == 1) {                // measurement only: loads without MMAs
+                            mbar_arrive(&ctl->empty[stage]);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < kChunkK / 8; ++k) {
-                            // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
-                            umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                                      (kc | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < kChunkK / 8; ++k) {
+                                // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
+                                umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                          (kc | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit(&ctl->empty[stage]);
                         }
-                        umma_commit(&ctl->empty[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
                     umma_commit(&ctl->tmem_full[buf]);
@@ -244,6 +256,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     } else if (warp >= 4) {
         // ================= epilogue =================
         const int ew = warp - 4;
+        const int quad = ew & 3;                  // TMEM lanes 32*quad .. 32*quad+31 (a warp may only touch its own quadrant)
+        const int half = ew >> 2;                 // columns [half*128, half*128 + 128) of the accumulator
         uint32_t seq = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int m0 = (item / groups) * kTileM;
@@ -253,9 +267,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 const uint32_t buf = seq & 1u;
                 mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 tcgen05_fence_after();
-                const int row0 = m0 + ew * 32;
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * kMaxTileN;
-                for (int c0 = 0; c0 < job.n_count; c0 += 32) {
+                const int row0 = m0 + quad * 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kMaxTileN;
+                const int c_end = min(job.n_count, (half + 1) * (kMaxTileN / 2));
+                for (int c0 = half * (kMaxTileN / 2); c0 < c_end; c0 += 32) {
                     float v[32];
                     tmem_load_32cols(taddr + (uint32_t)c0, v);
                     epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats);
@@ -334,8 +349,13 @@ int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_
     }
     const int n_items = m_tiles * (job_count / jobs_per_item);
     const int grid = n_items < num_sms ? n_items : num_sms;
+    static int debug_mode = -1;       // EMPOSE_TC_DEBUG=1: TMA only, =2: MMA only (throughput experiments; results are garbage)
+    if (debug_mode < 0) {
+        const char* e = getenv("EMPOSE_TC_DEBUG");
+        debug_mode = e ? atoi(e) : 0;
+    }
     gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(d_jobs, reinterpret_cast<const CUtensorMap*>(d_maps),
-                                                           job_begin, job_count, jobs_per_item, m_tiles);
+                                                           job_begin, job_count, jobs_per_item, m_tiles, debug_mode);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

@@ -149,7 +149,7 @@ int pack_matrix(Arena& arena, int n, int k0, int k1, int granule, bool round, bo
     pm->kseg[0] = k0; pm->kseg[1] = k1;
     pm->koff[0] = 0; pm->koff[1] = round_up(k0, kChunkK);
     pm->ld = round_up(k0, kChunkK) + (k1 > 0 ? round_up(k1, kChunkK) : 0);
-    std::vector<float> hw((size_t)pm->n_pad * pm->ld, 0.0f), hb((size_t)pm->n_pad, 0.0f);
+    std::vector<float> hw((size_t)pm->n_pad * pm->ld, 0.0f), hb((size_t)pm->n_pad + 32, 0.0f);   // bias padded for vector loads
     for (int r = 0; r < n; ++r) {
         RowSource src = row_of(r);
         float* dst = &hw[(size_t)r * pm->ld];
@@ -944,22 +944,25 @@ int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shap
     return launch_main(mp, s);
 }
 
-int empose_gemm_selftest(int32_t precision, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
-                         float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream) {
-    if (!A || !W || !C || M < 1 || N < 1 || K < 1) { set_last_error("bad argument"); return EMPOSE_E_ARG; }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+static int gemm_engine_run(int32_t precision, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                           float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t reps, float* ms_out,
+                           cudaStream_t s) {
+    if (!A || !W || !C || M < 1 || N < 1 || K < 1 || reps < 1) { set_last_error("bad argument"); return EMPOSE_E_ARG; }
     int dev = 0;
     EMPOSE_CUDA_TRY(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     EMPOSE_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     PackedMatrix pm;
     choose_tiles(N, 16, &pm);
-    pm.w = const_cast<float*>(W); pm.bias = const_cast<float*>(bias);
-    pm.kseg[0] = K; pm.ld = ldw;
     Arena arena;
     JobBook book;
     book.use_tc = precision == EMPOSE_PRECISION_TF32;
     JobRange range;
+    float* bias_padded = nullptr;                      // the epilogue reads bias in aligned groups of 32
+    if (bias) {
+        EMPOSE_TRY(arena.alloc_n((size_t)pm.n_pad + 32, &bias_padded, true));
+        EMPOSE_CUDA_TRY(cudaMemcpyAsync(bias_padded, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, s));
+    }
     GemmJob proto = linear_proto(pm, false, C, ldc, N);
     // the W tensor map describes the caller's matrix directly: K extent K (zero fill beyond), N rows
     for (int t = 0; t < pm.n_tiles; ++t) {
@@ -969,18 +972,44 @@ int empose_gemm_selftest(int32_t precision, const float* A, int64_t lda, const f
         j.a_map[1] = -1;
         j.w_ptr = W; j.w_ld = ldw;
         EMPOSE_TRY(book.get_map(W, ldw, K, N, pm.tile_n, &j.w_map));
-        j.n_begin = t * pm.tile_n; j.n_count = pm.tile_n; j.m_rows = M; j.dep = -1; j.bias = bias;
+        j.n_begin = t * pm.tile_n; j.n_count = pm.tile_n; j.m_rows = M; j.dep = -1; j.bias = bias_padded;
         if (range.count == 0) range.begin = (int)book.jobs.size();
         book.jobs.push_back(j);
         ++range.count;
     }
     EMPOSE_TRY(book.finalize(arena));
-    int rc;
-    if (book.use_tc) rc = tc_launch(book.d_jobs, book.d_maps, range.begin, range.count, 1, ceil_div(M, kTileM), prop.multiProcessorCount, s);
-    else rc = simt_launch(book.d_jobs, book.jobs.data(), range.begin, range.count, ceil_div(M, kTileM), s, nullptr);
-    if (rc != EMPOSE_OK) return rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms_out) {
+        EMPOSE_CUDA_TRY(cudaEventCreate(&e0));
+        EMPOSE_CUDA_TRY(cudaEventCreate(&e1));
+    }
+    int rc = EMPOSE_OK;
+    for (int r = 0; r < reps + (ms_out ? 1 : 0) && rc == EMPOSE_OK; ++r) {
+        if (ms_out && r == 1) cudaEventRecord(e0, s);           // launch 0 is the warm-up
+        if (book.use_tc) rc = tc_launch(book.d_jobs, book.d_maps, range.begin, range.count, 1, ceil_div(M, kTileM), prop.multiProcessorCount, s);
+        else rc = simt_launch(book.d_jobs, book.jobs.data(), range.begin, range.count, ceil_div(M, kTileM), s, nullptr);
+    }
+    if (ms_out) cudaEventRecord(e1, s);
     EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));     // the job array is freed when `arena` goes out of scope
-    return EMPOSE_OK;
+    if (ms_out) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out = ms / (float)reps;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return rc;
+}
+
+int empose_gemm_selftest(int32_t precision, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                         float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream) {
+    return gemm_engine_run(precision, A, lda, W, ldw, bias, C, ldc, M, N, K, 1, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int empose_gemm_bench(int32_t precision, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                      float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t reps, float* ms_per_launch, void* stream) {
+    if (!ms_per_launch) { set_last_error("null output"); return EMPOSE_E_ARG; }
+    return gemm_engine_run(precision, A, lda, W, ldw, bias, C, ldc, M, N, K, reps, ms_per_launch, static_cast<cudaStream_t>(stream));
 }
 
 #pragma GCC visibility pop

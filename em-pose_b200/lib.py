@@ -21,7 +21,7 @@ _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2
 EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_create', 'empose_ief_destroy',
                     'empose_ief_forward', 'empose_ief_forward_host', 'empose_sensor_project',
                     'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read',
-                    'empose_gemm_selftest')
+                    'empose_gemm_selftest', 'empose_gemm_bench')
 
 
 class EmposeError(RuntimeError):
@@ -82,6 +82,9 @@ def load():
     lib.empose_gemm_selftest.restype = ctypes.c_int
     lib.empose_gemm_selftest.argtypes = [i32, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, i32, i32,
                                          i32, vp]
+    lib.empose_gemm_bench.restype = ctypes.c_int
+    lib.empose_gemm_bench.argtypes = [i32, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, i32, i32, i32,
+                                      i32, ctypes.POINTER(ctypes.c_float), vp]
     _lib = lib
     return lib
 
@@ -260,3 +263,16 @@ def gemm_selftest(a, w, bias, precision=PRECISION_TF32):
     _check(load().empose_gemm_selftest(precision, _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(c),
                                        c.stride(0), m, n, k, _stream()))
     return c
+
+
+def gemm_bench(a, w, bias, precision=PRECISION_TF32, reps=10):
+    """Mean device milliseconds per launch of C = A . W^T + bias on the job executor."""
+    import torch
+    a, w = a.contiguous(), w.contiguous()
+    m, k = a.shape
+    n = w.shape[0]
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    ms = ctypes.c_float()
+    _check(load().empose_gemm_bench(precision, _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(c),
+                                    c.stride(0), m, n, k, reps, ctypes.byref(ms), _stream()))
+    return ms.value

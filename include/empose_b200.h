@@ -150,6 +150,11 @@ int empose_ief_profile_read(empose_ief* ctx, double* gemm_ms, int64_t* gemm_laun
 int empose_gemm_selftest(int32_t precision, const float* A, int64_t lda, const float* W, int64_t ldw,
                          const float* bias, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream);
 
+/* Same engine, event-timed: one warm-up launch, then `reps` launches; *ms_per_launch receives the mean device time. */
+int empose_gemm_bench(int32_t precision, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                      float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t reps, float* ms_per_launch,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
