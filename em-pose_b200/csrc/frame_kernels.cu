@@ -1,6 +1,6 @@
 // Per-frame CUDA kernels of the LGD loop: input assembly, estimate update + pose features, the SMPL
-// sub-model forward / reverse pass (one warp per frame, per-frame state in shared memory, arithmetic
-// in frame_math.h) and the gradient-feature finish.  Reference call sites are cited in
+// sub-model forward / reverse pass (8 frames per CTA, per-frame state in shared memory, every phase of
+// frame_math.h flattened over (frame, item) across the CTA) and the gradient-feature finish.  Reference call sites are cited in
 // frame_kernels.h and frame_math.h.
 #include "../../include/empose_b200.h"
 #include "common.cuh"
@@ -118,56 +118,68 @@ __global__ void __launch_bounds__(256) pose_feature_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kFramesPerCta = 4;   // one warp per frame
+// CTA-cooperative mapping: a CTA owns kFramesPerCta frames whose scratch state lives in shared memory, and every
+// phase of frame_math.h is flattened over (frame, item) across all threads of the CTA.  Narrow phases (the
+// 3-row kinematic chain, the 12 sensors) then occupy one or two warps for ALL frames of the CTA instead of a
+// few lanes in every warp, which is what the one-warp-per-frame mapping wasted most of its issue slots on.
+constexpr int kFramesPerCta = 8;
+constexpr int kMainThreads = 256;
+constexpr int kOneItem = 1 << 30;
+
+#define EMPOSE_FOR_ITEMS(n_items, f, i)                                                          \
+    for (int _idx = threadIdx.x, _n = (n_items), f = _idx / _n, i = _idx - f * _n; _idx < nf * _n; \
+         _idx += kMainThreads, f = _idx / _n, i = _idx - f * _n)
 
 template <int VP>
-__global__ void __launch_bounds__(kFramesPerCta * 32) main_kernel(MainParams p) {
+__global__ void __launch_bounds__(kMainThreads) main_kernel(MainParams p) {
     extern __shared__ __align__(16) uint8_t smem_main[];
-    FrameState<float, VP>* states = reinterpret_cast<FrameState<float, VP>*>(smem_main);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * kFramesPerCta + warp;
-    if (row >= p.R) return;                     // warps are independent: only __syncwarp below
-    FrameState<float, VP>& st = states[warp];
+    FrameState<float, VP>* st = reinterpret_cast<FrameState<float, VP>*>(smem_main);
     const SubModel& m = p.sub;
+    const int64_t row0 = (int64_t)blockIdx.x * kFramesPerCta;
+    const int nf = (int)min((int64_t)kFramesPerCta, (int64_t)p.R - row0);
+    const int nv3 = m.n_verts * 3;
 
-    for (int i = lane; i < kPoseDim; i += 32) st.theta[i] = p.theta[row * kPoseDim + i];
-    if (lane < kBetas) st.beta[lane] = p.beta[row * kBetas + lane];
-    __syncwarp();
-    phase_setup(m, st, p.vp_off + row * m.vp_dim, lane, 32);
-    __syncwarp();
-    phase_chain(m, st, lane, 32);
-    __syncwarp();
-    phase_skin(m, st, lane, 32);
-    __syncwarp();
-    const int64_t orow = row / p.rows_per_offset;
-    const float* meas = p.meas ? p.meas + row * 144 : nullptr;
-    phase_sensors(m, st, p.offset_r + orow * 108, p.offset_t + orow * 36, meas, meas ? meas + 36 : nullptr, p.spec,
-                  p.want_grad != 0, lane, 32);
-    __syncwarp();
-    if (p.sensor_pos)
-        for (int i = lane; i < 36; i += 32) p.sensor_pos[row * 36 + i] = st.sensor_pos[i / 3][i % 3];
-    if (p.sensor_ori)
-        for (int i = lane; i < 108; i += 32) p.sensor_ori[row * 108 + i] = st.sensor_ori[i / 9][i % 9];
-    if (p.joints)
-        for (int i = lane; i < kPoseDim; i += 32) p.joints[row * kPoseDim + i] = st.gpos[i / 3][i % 3];
+    EMPOSE_FOR_ITEMS(kPoseDim + kBetas, f, i) {
+        if (i < kPoseDim) st[f].theta[i] = p.theta[(row0 + f) * kPoseDim + i];
+        else st[f].beta[i - kPoseDim] = p.beta[(row0 + f) * kBetas + (i - kPoseDim)];
+    }
+    __syncthreads();
+    EMPOSE_FOR_ITEMS(kJoints, f, i) phase_rodrigues(st[f], i, kOneItem);
+    EMPOSE_FOR_ITEMS(kPoseDim, f, i) phase_rest_joints(m, st[f], i, kOneItem);
+    EMPOSE_FOR_ITEMS(nv3, f, i) phase_blend_verts(m, st[f], p.vp_off + (row0 + f) * m.vp_dim, i, kOneItem);
+    __syncthreads();
+    EMPOSE_FOR_ITEMS(3, f, i) phase_chain(m, st[f], i, kOneItem);
+    __syncthreads();
+    EMPOSE_FOR_ITEMS(m.n_verts, f, i) phase_skin(m, st[f], i, kOneItem);
+    __syncthreads();
+    EMPOSE_FOR_ITEMS(kSensors, f, i) {
+        const int64_t row = row0 + f;
+        const int64_t orow = row / p.rows_per_offset;
+        const float* meas = p.meas ? p.meas + row * 144 : nullptr;
+        phase_sensors(m, st[f], p.offset_r + orow * 108, p.offset_t + orow * 36, meas, meas ? meas + 36 : nullptr, p.spec,
+                      p.want_grad != 0, i, kOneItem);
+    }
+    __syncthreads();
+    if (p.sensor_pos) EMPOSE_FOR_ITEMS(36, f, i) p.sensor_pos[(row0 + f) * 36 + i] = st[f].sensor_pos[i / 3][i % 3];
+    if (p.sensor_ori) EMPOSE_FOR_ITEMS(108, f, i) p.sensor_ori[(row0 + f) * 108 + i] = st[f].sensor_ori[i / 9][i % 9];
+    if (p.joints) EMPOSE_FOR_ITEMS(kPoseDim, f, i) p.joints[(row0 + f) * kPoseDim + i] = st[f].gpos[i / 3][i % 3];
     if (!p.want_grad) return;
 
-    phase_skin_bwd_joints(m, st, lane, 32);
-    __syncwarp();
-    phase_skin_bwd_verts(m, st, lane, 32);
-    __syncwarp();
-    {
-        const int nv3 = m.n_verts * 3;
-        float* dst = p.dvp + row * m.vp_dim;
-        for (int i = lane; i < m.vp_dim; i += 32) dst[i] = i < nv3 ? maybe_round(st.dx[i], p.round_out) : 0.0f;
-    }
-    phase_shape_bwd_partial(m, st, lane, 32);
-    phase_chain_bwd(m, st, lane, 32);
-    __syncwarp();
-    phase_chain_bwd_local(m, st, lane, 32);
-    __syncwarp();
-    phase_finish(m, st, p.coef[row], (const float*)nullptr, p.gtheta_part + row * kPoseDim, p.gbeta + row * kBetas, lane,
-                 32);
+    EMPOSE_FOR_ITEMS(m.n_vj, f, i) phase_skin_bwd_chunks(m, st[f], i, kOneItem);
+    __syncthreads();
+    EMPOSE_FOR_ITEMS(kJoints * 12, f, i) phase_skin_bwd_reduce(m, st[f], i, kOneItem);
+    EMPOSE_FOR_ITEMS(m.n_verts, f, i) phase_skin_bwd_verts(m, st[f], i, kOneItem);
+    __syncthreads();
+    EMPOSE_FOR_ITEMS(m.vp_dim, f, i)
+        p.dvp[(row0 + f) * m.vp_dim + i] = i < nv3 ? maybe_round(st[f].dx[i], p.round_out) : 0.0f;
+    EMPOSE_FOR_ITEMS(3 * kBetas, f, i) phase_shape_bwd_partial(m, st[f], i, kOneItem);
+    EMPOSE_FOR_ITEMS(3, f, i) phase_chain_bwd(m, st[f], i, kOneItem);
+    __syncthreads();
+    EMPOSE_FOR_ITEMS(kJoints * 12, f, i) phase_chain_bwd_local(m, st[f], i, kOneItem);
+    __syncthreads();
+    EMPOSE_FOR_ITEMS(kJoints, f, i)
+        phase_finish_theta(st[f], p.coef[row0 + f], (const float*)nullptr, p.gtheta_part + (row0 + f) * kPoseDim, i, kOneItem);
+    EMPOSE_FOR_ITEMS(kBetas, f, i) phase_finish_beta(m, st[f], p.coef[row0 + f], p.gbeta + (row0 + f) * kBetas, i, kOneItem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,17 +246,18 @@ int launch_pose_features(const float* theta, float* pf, int pf_stride, int pf_sp
 
 int launch_main(const MainParams& p, cudaStream_t s) {
     const unsigned grid = blocks_for(p.R, kFramesPerCta);
+    static bool configured = false;
+    if (!configured) {
+        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(main_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(FrameState<float, 256>) * kFramesPerCta)));
+        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(main_kernel<kMaxVp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(FrameState<float, kMaxVp>) * kFramesPerCta)));
+        configured = true;
+    }
     if (p.sub.vp_dim <= 256) {
-        const size_t smem = sizeof(FrameState<float, 256>) * kFramesPerCta;
-        main_kernel<256><<<grid, kFramesPerCta * 32, smem, s>>>(p);
+        main_kernel<256><<<grid, kMainThreads, sizeof(FrameState<float, 256>) * kFramesPerCta, s>>>(p);
     } else if (p.sub.vp_dim <= kMaxVp) {
-        const size_t smem = sizeof(FrameState<float, kMaxVp>) * kFramesPerCta;
-        static bool configured = false;
-        if (!configured) {
-            EMPOSE_CUDA_TRY(cudaFuncSetAttribute(main_kernel<kMaxVp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-        main_kernel<kMaxVp><<<grid, kFramesPerCta * 32, smem, s>>>(p);
+        main_kernel<kMaxVp><<<grid, kMainThreads, sizeof(FrameState<float, kMaxVp>) * kFramesPerCta, s>>>(p);
     } else {
         set_last_error("sensor sub-mesh too large (more than 128 vertices)");
         return EMPOSE_E_ARG;

@@ -37,6 +37,7 @@ constexpr int kPoseFeat = 189;        // 21 joints x 9 rotation entries
 constexpr int kPoseFeatPad = 192;     // K of the pose-blend GEMM (multiple of 32 floats = one 128B swizzle row)
 constexpr int kMaxVp = 384;           // padded 3*Vs, supports sub-meshes of up to 128 vertices
 constexpr int kMaxDegree = 12;
+constexpr int kMaxVj = 44;            // chunks of the joint->vertex lists (their partial sums alias dgr..dj below)
 
 // Packed sub-model constants (pointers into device or host memory).  Layouts: see submodel.py.
 struct SubModel {
@@ -50,6 +51,9 @@ struct SubModel {
     const int* jt_ptr;         // [23]   joint -> range in jt_vert / jt_weight
     const int* jt_vert;
     const float* jt_weight;
+    int n_vj;                  // "virtual joints": the per-joint lists cut into chunks of bounded length
+    const int* vj_ptr;         // [n_vj+1] chunk -> range in jt_vert / jt_weight
+    const int* jvj_ptr;        // [23]     joint -> range of chunks
     const int* parents;        // [22]
     const int* faces;          // [n_faces][3] local vertex ids
     const int* sensor_vert;    // [12]
@@ -78,10 +82,15 @@ struct FrameState {
     T dx[VP];                 // dE/dx, then reused for dE/dvp
     T dar[kJoints][9];        // dE/dA^R
     T dat[kJoints][3];        // dE/dA^t
-    T dgr[kJoints][9];        // dE/dG^R
-    T dgt[kJoints][3];        // dE/dG^t
-    T drot[kJoints][9];       // dE/dR_j  (chain part; the pose-blend part is added in phase_finish or by the caller)
-    T dj[kJoints][3];         // dE/dJ_j
+    union {
+        struct {
+            T dgr[kJoints][9];    // dE/dG^R
+            T dgt[kJoints][3];    // dE/dG^t
+            T drot[kJoints][9];   // dE/dR_j  (chain part; the pose-blend part is added in phase_finish or by the caller)
+            T dj[kJoints][3];     // dE/dJ_j
+        };
+        T dav[kMaxVj][12];        // per-chunk partial sums of dE/dA (dead before dgr.. are first written)
+    };
     T dbeta_part[3][kBetas];
     T sensor_pos[kSensors][3];   // p'_m (offsets applied)
     T sensor_ori[kSensors][9];   // R'_m row-major
@@ -177,15 +186,26 @@ template <typename T> EMPOSE_HD void rodrigues_bwd(const T* r, const T* dR, T* d
 // forward phases
 // ----------------------------------------------------------------------------------------------
 
-// F1: rotations, rest joints, blended rest vertices.  vp_off may be null (treated as zero).
-template <typename T, int VP, typename TIn>
-EMPOSE_HD void phase_setup(const SubModel& m, FrameState<T, VP>& st, const TIn* vp_off, int lane, int lanes) {
+// Every phase below is ONE loop `for (i = lane; i < n_items; i += lanes)` over independent items, so a caller
+// may also run a single item i with (lane = i, lanes = huge); the item counts are given by the *_items helpers.
+
+// F1a: joint rotations (22 items).
+template <typename T, int VP>
+EMPOSE_HD void phase_rodrigues(FrameState<T, VP>& st, int lane, int lanes) {
     for (int j = lane; j < kJoints; j += lanes) rodrigues_fwd(&st.theta[j * 3], st.rot[j]);
+}
+// F1b: rest joints J(beta) (66 items).
+template <typename T, int VP>
+EMPOSE_HD void phase_rest_joints(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
     for (int i = lane; i < kPoseDim; i += lanes) {
         T acc = T(m.j0[i]);
         for (int k = 0; k < kBetas; ++k) acc += T(m.jdirs[k * kPoseDim + i]) * st.beta[k];
         st.jrest[i / 3][i % 3] = acc;
     }
+}
+// F1c: blended rest vertices (3 * n_verts items).  vp_off may be null (treated as zero).
+template <typename T, int VP, typename TIn>
+EMPOSE_HD void phase_blend_verts(const SubModel& m, FrameState<T, VP>& st, const TIn* vp_off, int lane, int lanes) {
     const int nv3 = m.n_verts * 3;
     for (int i = lane; i < nv3; i += lanes) {
         T acc = T(m.v_template[i]);
@@ -360,28 +380,39 @@ EMPOSE_HD void phase_sensors(const SubModel& m, FrameState<T, VP>& st, const TIn
 // reverse phases
 // ----------------------------------------------------------------------------------------------
 
-// B1: gather dE/dA_j from the vertices each joint skins (lists grouped by joint: no atomics).
+// B1a: dE/dA summed over one chunk ("virtual joint") of a joint's vertex list (n_vj items).  Each chunk walks
+// its (bounded) list once and accumulates all 12 entries in registers, so lanes stay balanced.
 template <typename T, int VP>
-EMPOSE_HD void phase_skin_bwd_joints(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+EMPOSE_HD void phase_skin_bwd_chunks(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int c = lane; c < m.n_vj; c += lanes) {
+        T acc[12];
+        for (int e = 0; e < 12; ++e) acc[e] = T(0);
+        for (int q = m.vj_ptr[c]; q < m.vj_ptr[c + 1]; ++q) {
+            const int v = m.jt_vert[q];
+            const T w = T(m.jt_weight[q]);
+            const T d0 = w * st.dx[v * 3], d1 = w * st.dx[v * 3 + 1], d2 = w * st.dx[v * 3 + 2];
+            const T p0 = st.vp[v * 3], p1 = st.vp[v * 3 + 1], p2 = st.vp[v * 3 + 2];
+            acc[0] += d0 * p0; acc[1] += d0 * p1; acc[2] += d0 * p2;
+            acc[3] += d1 * p0; acc[4] += d1 * p1; acc[5] += d1 * p2;
+            acc[6] += d2 * p0; acc[7] += d2 * p1; acc[8] += d2 * p2;
+            acc[9] += d0; acc[10] += d1; acc[11] += d2;
+        }
+        for (int e = 0; e < 12; ++e) st.dav[c][e] = acc[e];
+    }
+}
+// B1b: dE/dA_j = sum of its chunks (22 * 12 items).
+template <typename T, int VP>
+EMPOSE_HD void phase_skin_bwd_reduce(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
     for (int it = lane; it < kJoints * 12; it += lanes) {
         const int j = it / 12, e = it % 12;
         T acc = T(0);
-        if (e < 9) {
-            const int r = e / 3, c = e % 3;
-            for (int q = m.jt_ptr[j]; q < m.jt_ptr[j + 1]; ++q) {
-                const int v = m.jt_vert[q];
-                acc += T(m.jt_weight[q]) * st.dx[v * 3 + r] * st.vp[v * 3 + c];
-            }
-            st.dar[j][e] = acc;
-        } else {
-            const int r = e - 9;
-            for (int q = m.jt_ptr[j]; q < m.jt_ptr[j + 1]; ++q) acc += T(m.jt_weight[q]) * st.dx[m.jt_vert[q] * 3 + r];
-            st.dat[j][r] = acc;
-        }
+        for (int c = m.jvj_ptr[j]; c < m.jvj_ptr[j + 1]; ++c) acc += st.dav[c][e];
+        if (e < 9) st.dar[j][e] = acc;
+        else st.dat[j][e - 9] = acc;
     }
 }
 
-// B2: dE/dvp_v = sum_j w A_j^R^T dE/dx_v, in place over st.dx.  Must run AFTER phase_skin_bwd_joints.
+// B2: dE/dvp_v = sum_j w A_j^R^T dE/dx_v, in place over st.dx.  Must run AFTER phase_skin_bwd_chunks.
 template <typename T, int VP>
 EMPOSE_HD void phase_skin_bwd_verts(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
     for (int v = lane; v < m.n_verts; v += lanes) {
@@ -471,8 +502,7 @@ EMPOSE_HD void phase_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, i
 // (dE/d pose-feature, the result of the transposed pose-blend GEMM) may be null: the map is linear in
 // dR, so a caller can add coef * rodrigues_bwd(theta_j, dpf_j) later (the split GPU kernels do that).
 template <typename T, int VP, typename TOut, typename TPf>
-EMPOSE_HD void phase_finish(const SubModel& m, FrameState<T, VP>& st, T coef, const TPf* dpf, TOut* g_theta,
-                            TOut* g_beta, int lane, int lanes) {
+EMPOSE_HD void phase_finish_theta(FrameState<T, VP>& st, T coef, const TPf* dpf, TOut* g_theta, int lane, int lanes) {
     for (int j = lane; j < kJoints; j += lanes) {
         T g[3] = {T(0), T(0), T(0)};
         if (dpf && j > 0)
@@ -480,6 +510,9 @@ EMPOSE_HD void phase_finish(const SubModel& m, FrameState<T, VP>& st, T coef, co
         rodrigues_bwd(&st.theta[j * 3], st.drot[j], g);
         g_theta[j * 3] = TOut(coef * g[0]); g_theta[j * 3 + 1] = TOut(coef * g[1]); g_theta[j * 3 + 2] = TOut(coef * g[2]);
     }
+}
+template <typename T, int VP, typename TOut>
+EMPOSE_HD void phase_finish_beta(const SubModel& m, FrameState<T, VP>& st, T coef, TOut* g_beta, int lane, int lanes) {
     for (int k = lane; k < kBetas; k += lanes) {
         T acc = st.dbeta_part[0][k] + st.dbeta_part[1][k] + st.dbeta_part[2][k];
         for (int i = 0; i < kPoseDim; ++i) acc += T(m.jdirs[k * kPoseDim + i]) * st.dj[i / 3][i % 3];

@@ -590,6 +590,12 @@ int upload_submodel(empose_ief* ctx, const TensorTable& tt) {
     EMPOSE_TRY(up_i("sub.jt_ptr", kJoints + 1, &m.jt_ptr, 0, n_jt + 1));
     EMPOSE_TRY(up_i("sub.jt_vert", n_jt, &m.jt_vert, 0, m.n_verts));
     EMPOSE_TRY(up_f("sub.jt_weight", {n_jt}, &m.jt_weight));
+    const empose_tensor* vj = tt.find("sub.vj_ptr");
+    if (!vj) { set_last_error("missing tensor 'sub.vj_ptr'"); return EMPOSE_E_MISSING; }
+    m.n_vj = (int)tt.numel(vj) - 1;
+    if (m.n_vj < 1 || m.n_vj > kMaxVj) { set_last_error("sub.vj_ptr: number of chunks out of range"); return EMPOSE_E_ARG; }
+    EMPOSE_TRY(up_i("sub.vj_ptr", m.n_vj + 1, &m.vj_ptr, 0, n_jt + 1));
+    EMPOSE_TRY(up_i("sub.jvj_ptr", kJoints + 1, &m.jvj_ptr, 0, m.n_vj + 1));
     EMPOSE_TRY(up_i("sub.parents", kJoints, &m.parents, -1, kJoints));
     EMPOSE_TRY(up_i("sub.faces", (int64_t)m.n_faces * 3, &m.faces, 0, m.n_verts));
     EMPOSE_TRY(up_i("sub.sensor_vert", kSensors, &m.sensor_vert, 0, m.n_verts));

@@ -131,6 +131,21 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
         jt_weight += w22[vs, j].tolist()
         jt_ptr[j + 1] = len(jt_vert)
 
+    # the same lists cut into chunks of bounded length ("virtual joints") so GPU lanes stay balanced; at most
+    # MAX_CHUNKS chunks because their partial sums share storage with other per-joint scratch (frame_math.h kMaxVj)
+    MAX_CHUNKS = 44
+    chunk_len = 8
+    while True:
+        vj_ptr, jvj_ptr = [0], [0]
+        for j in range(N_BODY_JOINTS):
+            lo, hi = int(jt_ptr[j]), int(jt_ptr[j + 1])
+            for start in range(lo, hi, chunk_len):
+                vj_ptr.append(min(start + chunk_len, hi))
+            jvj_ptr.append(len(vj_ptr) - 1)
+        if len(vj_ptr) - 1 <= MAX_CHUNKS:
+            break
+        chunk_len += 2
+
     vp_dim = ((n_sub * 3 + 15) // 16) * 16                     # padded width of the per-frame vertex vector
     pd = posedirs.reshape(posedirs.shape[0], n_v, 3)[:N_POSE_FEATURES, verts].reshape(N_POSE_FEATURES, n_sub * 3)
     sd = shapedirs[verts].reshape(n_sub * 3, N_BETAS).T                              # (10, Vs*3)
@@ -153,6 +168,8 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
         'sub.skin_joint': skin_joint,
         'sub.jt_ptr': jt_ptr,
         'sub.jt_vert': np.asarray(jt_vert, dtype=np.int32),
+        'sub.vj_ptr': np.asarray(vj_ptr, dtype=np.int32),
+        'sub.jvj_ptr': np.asarray(jvj_ptr, dtype=np.int32),
         'sub.faces': local[sub_faces].astype(np.int32),                               # (Fs,3) local ids
         'sub.sensor_vert': local[sensor_ids].astype(np.int32),                        # (12,)
         'sub.helper_vert': local[helper_ids].astype(np.int32),                        # (12,)

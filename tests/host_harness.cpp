@@ -12,6 +12,8 @@ struct HostSub {
     int n_verts, vp_dim, n_faces, max_degree, n_skin;
     const float *v_template, *shapedirs, *posedirs, *j0, *jdirs, *skin_weight, *jt_weight;
     const int *skin_joint, *jt_ptr, *jt_vert, *parents, *faces, *sensor_vert, *helper_vert, *sensor_faces, *sensor_degree;
+    const int *vj_ptr, *jvj_ptr;
+    int n_vj;
 };
 
 template <typename T>
@@ -25,6 +27,7 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
     m.skin_weight = h.skin_weight; m.skin_joint = h.skin_joint; m.jt_ptr = h.jt_ptr; m.jt_vert = h.jt_vert;
     m.jt_weight = h.jt_weight; m.parents = h.parents; m.faces = h.faces; m.sensor_vert = h.sensor_vert;
     m.helper_vert = h.helper_vert; m.sensor_faces = h.sensor_faces; m.sensor_degree = h.sensor_degree;
+    m.n_vj = h.n_vj; m.vj_ptr = h.vj_ptr; m.jvj_ptr = h.jvj_ptr;
     ResidualSpec spec;
     spec.use_pos = use_pos; spec.use_ori = use_ori;
     for (int s = 0; s < kSensors; ++s) spec.sensor_active[s] = active[s];
@@ -46,7 +49,9 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
             for (int k = 0; k < kPoseFeat; ++k) acc += T(h.posedirs[k * h.vp_dim + i]) * pf[k];
             vp_off[i] = acc;
         }
-        phase_setup(m, st, vp_off.data(), 0, 1);
+        phase_rodrigues(st, 0, 1);
+        phase_rest_joints(m, st, 0, 1);
+        phase_blend_verts(m, st, vp_off.data(), 0, 1);
         phase_chain(m, st, 0, 1);
         phase_skin(m, st, 0, 1);
         phase_sensors(m, st, off_r + f * 108, off_t + f * 36, meas_pos + f * 36, meas_ori + f * 108, spec,
@@ -56,7 +61,8 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
         for (int i = 0; i < 66; ++i) joints[f * 66 + i] = double(st.gpos[i / 3][i % 3]);
         if (verts) for (int i = 0; i < h.n_verts * 3; ++i) verts[f * h.n_verts * 3 + i] = double(st.x[i]);
         if (!want_grad) continue;
-        phase_skin_bwd_joints(m, st, 0, 1);
+        phase_skin_bwd_chunks(m, st, 0, 1);
+        phase_skin_bwd_reduce(m, st, 0, 1);
         phase_skin_bwd_verts(m, st, 0, 1);
         phase_shape_bwd_partial(m, st, 0, 1);
         for (int k = 0; k < kPoseFeat; ++k) {
@@ -67,7 +73,8 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
         phase_chain_bwd(m, st, 0, 1);
         phase_chain_bwd_local(m, st, 0, 1);
         std::vector<T> gt(kPoseDim), gb(kBetas);
-        phase_finish(m, st, T(coef[f]), dpf.data(), gt.data(), gb.data(), 0, 1);
+        phase_finish_theta(st, T(coef[f]), dpf.data(), gt.data(), 0, 1);
+        phase_finish_beta(m, st, T(coef[f]), gb.data(), 0, 1);
         for (int i = 0; i < kPoseDim; ++i) g_theta[f * kPoseDim + i] = double(gt[i]);
         for (int i = 0; i < kBetas; ++i) g_beta[f * kBetas + i] = double(gb[i]);
     }
@@ -78,7 +85,7 @@ extern "C" int host_frame_eval(const HostSub* h, int n_frames, const float* thet
                                const int* active, int use_pos, int use_ori, const float* coef, int want_grad,
                                int use_double, double* sensor_pos, double* sensor_ori, double* joints, double* g_theta,
                                double* g_beta, double* verts) {
-    if (h->vp_dim > kMaxVp || h->max_degree > kMaxDegree) return -1;
+    if (h->vp_dim > kMaxVp || h->max_degree > kMaxDegree || h->n_vj > kMaxVj) return -1;
     if (use_double)
         run<double>(*h, n_frames, theta, beta, off_r, off_t, meas_pos, meas_ori, active, use_pos, use_ori, coef,
                     want_grad, sensor_pos, sensor_ori, joints, g_theta, g_beta, verts);

@@ -11,13 +11,13 @@ _LIB = None
 
 _F32_FIELDS = ['v_template', 'shapedirs', 'posedirs', 'j0', 'jdirs', 'skin_weight', 'jt_weight']
 _I32_FIELDS = ['skin_joint', 'jt_ptr', 'jt_vert', 'parents', 'faces', 'sensor_vert', 'helper_vert', 'sensor_faces',
-               'sensor_degree']
+               'sensor_degree', 'vj_ptr', 'jvj_ptr']
 
 
 class HostSub(ctypes.Structure):
     _fields_ = ([(n, ctypes.c_int) for n in ('n_verts', 'vp_dim', 'n_faces', 'max_degree', 'n_skin')] +
                 [(n, ctypes.POINTER(ctypes.c_float)) for n in _F32_FIELDS] +
-                [(n, ctypes.POINTER(ctypes.c_int)) for n in _I32_FIELDS])
+                [(n, ctypes.POINTER(ctypes.c_int)) for n in _I32_FIELDS] + [('n_vj', ctypes.c_int)])
 
 
 def _lib():
@@ -51,6 +51,7 @@ def frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef,
         a = np.ascontiguousarray(sub['sub.' + n], dtype=np.int32)
         keep.append(a)
         setattr(hs, n, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    hs.n_vj = int(sub['sub.vj_ptr'].shape[0]) - 1
     n = theta.shape[0]
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     theta, beta, off_r, off_t, meas_pos, meas_ori, coef = map(f32, (theta, beta, off_r, off_t, meas_pos, meas_ori, coef))
