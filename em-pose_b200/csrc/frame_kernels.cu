@@ -126,9 +126,13 @@ constexpr int kFramesPerCta = 8;
 constexpr int kMainThreads = 256;
 constexpr int kOneItem = 1 << 30;
 
-#define EMPOSE_FOR_ITEMS(n_items, f, i)                                                          \
-    for (int _idx = threadIdx.x, _n = (n_items), f = _idx / _n, i = _idx - f * _n; _idx < nf * _n; \
-         _idx += kMainThreads, f = _idx / _n, i = _idx - f * _n)
+// flattened (frame, item) loop over threads [t0, t0 + nt) of the CTA
+#define EMPOSE_FOR_ITEMS_ON(t0, nt, n_items, f, i)                                                       \
+    for (int _idx = (int)threadIdx.x - (t0), _n = (n_items), f = _idx / _n, i = _idx - f * _n;            \
+         _idx >= 0 && _idx < nf * _n; _idx += (nt), f = _idx / _n, i = _idx - f * _n)
+#define EMPOSE_FOR_ITEMS(n_items, f, i) EMPOSE_FOR_ITEMS_ON(0, kMainThreads, n_items, f, i)
+// items of the serial kinematic chains, on the last warp of the CTA
+#define EMPOSE_FOR_ITEMS_CHAIN(n_items, f, i) EMPOSE_FOR_ITEMS_ON(kMainThreads - 32, 32, n_items, f, i)
 
 template <int VP>
 __global__ void __launch_bounds__(kMainThreads) main_kernel(MainParams p) {
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(kMainThreads) main_kernel(MainParams p) {
     const int64_t row0 = (int64_t)blockIdx.x * kFramesPerCta;
     const int nf = (int)min((int64_t)kFramesPerCta, (int64_t)p.R - row0);
     const int nv3 = m.n_verts * 3;
+    const bool static_tree = p.static_tree != 0;
 
     EMPOSE_FOR_ITEMS(kPoseDim + kBetas, f, i) {
         if (i < kPoseDim) st[f].theta[i] = p.theta[(row0 + f) * kPoseDim + i];
@@ -146,9 +151,14 @@ __global__ void __launch_bounds__(kMainThreads) main_kernel(MainParams p) {
     __syncthreads();
     EMPOSE_FOR_ITEMS(kJoints, f, i) phase_rodrigues(st[f], i, kOneItem);
     EMPOSE_FOR_ITEMS(kPoseDim, f, i) phase_rest_joints(m, st[f], i, kOneItem);
-    EMPOSE_FOR_ITEMS(nv3, f, i) phase_blend_verts(m, st[f], p.vp_off + (row0 + f) * m.vp_dim, i, kOneItem);
     __syncthreads();
-    EMPOSE_FOR_ITEMS(3, f, i) phase_chain(m, st[f], i, kOneItem);
+    // The serial kinematic chain runs on the last warp first; all threads (that warp joining late) then do the
+    // wide, independent vertex blend, so the chain's latency hides behind it.
+    if (threadIdx.x >= kMainThreads - 32) {
+        if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) phase_chain_static(st[f], i, kOneItem); }
+        else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) phase_chain(m, st[f], i, kOneItem); }
+    }
+    EMPOSE_FOR_ITEMS(nv3, f, i) phase_blend_verts(m, st[f], p.vp_off + (row0 + f) * m.vp_dim, i, kOneItem);
     __syncthreads();
     EMPOSE_FOR_ITEMS(m.n_verts, f, i) phase_skin(m, st[f], i, kOneItem);
     __syncthreads();
@@ -164,16 +174,20 @@ __global__ void __launch_bounds__(kMainThreads) main_kernel(MainParams p) {
     if (p.sensor_ori) EMPOSE_FOR_ITEMS(108, f, i) p.sensor_ori[(row0 + f) * 108 + i] = st[f].sensor_ori[i / 9][i % 9];
     if (p.joints) EMPOSE_FOR_ITEMS(kPoseDim, f, i) p.joints[(row0 + f) * kPoseDim + i] = st[f].gpos[i / 3][i % 3];
     if (!p.want_grad) return;
+    __syncthreads();                      // the forward scratch (gpos, atr, x, sensor outputs) is dead from here on
 
     EMPOSE_FOR_ITEMS(m.n_vj, f, i) phase_skin_bwd_chunks(m, st[f], i, kOneItem);
     __syncthreads();
     EMPOSE_FOR_ITEMS(kJoints * 12, f, i) phase_skin_bwd_reduce(m, st[f], i, kOneItem);
     EMPOSE_FOR_ITEMS(m.n_verts, f, i) phase_skin_bwd_verts(m, st[f], i, kOneItem);
     __syncthreads();
+    if (threadIdx.x >= kMainThreads - 32) {
+        if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) phase_chain_bwd_static(st[f], i, kOneItem); }
+        else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) phase_chain_bwd(m, st[f], i, kOneItem); }
+    }
     EMPOSE_FOR_ITEMS(m.vp_dim, f, i)
         p.dvp[(row0 + f) * m.vp_dim + i] = i < nv3 ? maybe_round(st[f].dx[i], p.round_out) : 0.0f;
     EMPOSE_FOR_ITEMS(3 * kBetas, f, i) phase_shape_bwd_partial(m, st[f], i, kOneItem);
-    EMPOSE_FOR_ITEMS(3, f, i) phase_chain_bwd(m, st[f], i, kOneItem);
     __syncthreads();
     EMPOSE_FOR_ITEMS(kJoints * 12, f, i) phase_chain_bwd_local(m, st[f], i, kOneItem);
     __syncthreads();

@@ -37,7 +37,7 @@ constexpr int kPoseFeat = 189;        // 21 joints x 9 rotation entries
 constexpr int kPoseFeatPad = 192;     // K of the pose-blend GEMM (multiple of 32 floats = one 128B swizzle row)
 constexpr int kMaxVp = 384;           // padded 3*Vs, supports sub-meshes of up to 128 vertices
 constexpr int kMaxDegree = 12;
-constexpr int kMaxVj = 44;            // chunks of the joint->vertex lists (their partial sums alias dgr..dj below)
+constexpr int kMaxVj = 44;            // chunks of the joint->vertex lists (their partial sums alias dgr .. dj below)
 
 // Packed sub-model constants (pointers into device or host memory).  Layouts: see submodel.py.
 struct SubModel {
@@ -75,25 +75,31 @@ struct FrameState {
     T rot[kJoints][9];        // R_j = exp(theta_j)
     T jrest[kJoints][3];      // J(beta)
     T grot[kJoints][9];       // world rotation G_j^R  (== A_j^R)
-    T gpos[kJoints][3];       // world position G_j^t  (posed joint)
-    T atr[kJoints][3];        // A_j^t = G_j^t - G_j^R J_j
     T vp[VP];                 // v_template + S beta + pose blend
-    T x[VP];                  // skinned vertices
     T dx[VP];                 // dE/dx, then reused for dE/dvp
     T dar[kJoints][9];        // dE/dA^R
     T dat[kJoints][3];        // dE/dA^t
+    T dbeta_part[3][kBetas];
+    // Forward-only scratch and reverse-only scratch share storage: everything in `fwd` is dead once the sensor
+    // outputs and joints have been written out, which is before the first member of `bwd` is written.
     union {
         struct {
-            T dgr[kJoints][9];    // dE/dG^R
-            T dgt[kJoints][3];    // dE/dG^t
-            T drot[kJoints][9];   // dE/dR_j  (chain part; the pose-blend part is added in phase_finish or by the caller)
-            T dj[kJoints][3];     // dE/dJ_j
+            T gpos[kJoints][3];          // world position G_j^t  (posed joint)
+            T atr[kJoints][3];           // A_j^t = G_j^t - G_j^R J_j
+            T x[VP];                     // skinned vertices
+            T sensor_pos[kSensors][3];   // p'_m (offsets applied)
+            T sensor_ori[kSensors][9];   // R'_m row-major
         };
-        T dav[kMaxVj][12];        // per-chunk partial sums of dE/dA (dead before dgr.. are first written)
+        union {
+            struct {
+                T dgr[kJoints][9];        // dE/dG^R
+                T dgt[kJoints][3];        // dE/dG^t
+                T drot[kJoints][9];       // dE/dR_j (chain part; the pose-blend part is added in phase_finish_theta or by the caller)
+                T dj[kJoints][3];         // dE/dJ_j
+            };
+            T dav[kMaxVj][12];            // per-chunk partial sums of dE/dA (dead before dgr .. dj are written)
+        };
     };
-    T dbeta_part[3][kBetas];
-    T sensor_pos[kSensors][3];   // p'_m (offsets applied)
-    T sensor_ori[kSensors][9];   // R'_m row-major
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -235,6 +241,42 @@ EMPOSE_HD void phase_chain(const SubModel& m, FrameState<T, VP>& st, int lane, i
         for (int j = 0; j < kJoints; ++j)
             st.atr[j][r] = st.gpos[j][r] - (st.grot[j][r * 3] * st.jrest[j][0] + st.grot[j][r * 3 + 1] * st.jrest[j][1] +
                                             st.grot[j][r * 3 + 2] * st.jrest[j][2]);
+    }
+}
+
+// The SMPL body tree (reference configuration.py:118) as a compile-time function, so the chain can be fully
+// unrolled with every world transform held in registers (no shared-memory round trip between joints).
+EMPOSE_HD constexpr int smpl_parent(int j) {
+    return j == 0 ? -1 : j <= 3 ? 0 : j <= 11 ? j - 3 : j <= 14 ? 9 : j <= 17 ? j - 3 : j - 2;
+}
+
+// F2': phase_chain specialised for the standard SMPL tree (same arithmetic, same order of operations).
+template <typename T, int VP>
+EMPOSE_HD void phase_chain_static(FrameState<T, VP>& st, int lane, int lanes) {
+    for (int r = lane; r < 3; r += lanes) {
+        T g[kJoints][3], t[kJoints];
+        g[0][0] = st.rot[0][r * 3]; g[0][1] = st.rot[0][r * 3 + 1]; g[0][2] = st.rot[0][r * 3 + 2];
+        t[0] = st.jrest[0][r];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 1; j < kJoints; ++j) {
+            const int p = smpl_parent(j);
+            const T* R = st.rot[j];
+            g[j][0] = g[p][0] * R[0] + g[p][1] * R[3] + g[p][2] * R[6];
+            g[j][1] = g[p][0] * R[1] + g[p][1] * R[4] + g[p][2] * R[7];
+            g[j][2] = g[p][0] * R[2] + g[p][1] * R[5] + g[p][2] * R[8];
+            t[j] = g[p][0] * (st.jrest[j][0] - st.jrest[p][0]) + g[p][1] * (st.jrest[j][1] - st.jrest[p][1]) +
+                   g[p][2] * (st.jrest[j][2] - st.jrest[p][2]) + t[p];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < kJoints; ++j) {
+            st.grot[j][r * 3] = g[j][0]; st.grot[j][r * 3 + 1] = g[j][1]; st.grot[j][r * 3 + 2] = g[j][2];
+            st.gpos[j][r] = t[j];
+            st.atr[j][r] = t[j] - (g[j][0] * st.jrest[j][0] + g[j][1] * st.jrest[j][1] + g[j][2] * st.jrest[j][2]);
+        }
     }
 }
 
@@ -465,6 +507,42 @@ EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int lan
             st.dgr[p][r * 3 + 1] += d0 * R[3] + d1 * R[4] + d2 * R[5] + dt * (st.jrest[j][1] - st.jrest[p][1]);
             st.dgr[p][r * 3 + 2] += d0 * R[6] + d1 * R[7] + d2 * R[8] + dt * (st.jrest[j][2] - st.jrest[p][2]);
             st.dgt[p][r] += dt;
+        }
+    }
+}
+
+// B4': phase_chain_bwd specialised for the standard SMPL tree, dE/dG rows held in registers.
+template <typename T, int VP>
+EMPOSE_HD void phase_chain_bwd_static(FrameState<T, VP>& st, int lane, int lanes) {
+    for (int r = lane; r < 3; r += lanes) {
+        T d[kJoints][3], dt[kJoints];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < kJoints; ++j) {
+            const T a = st.dat[j][r];
+            dt[j] = a;
+            d[j][0] = st.dar[j][r * 3] - a * st.jrest[j][0];
+            d[j][1] = st.dar[j][r * 3 + 1] - a * st.jrest[j][1];
+            d[j][2] = st.dar[j][r * 3 + 2] - a * st.jrest[j][2];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = kJoints - 1; j >= 1; --j) {
+            const int p = smpl_parent(j);
+            const T* R = st.rot[j];
+            d[p][0] += d[j][0] * R[0] + d[j][1] * R[1] + d[j][2] * R[2] + dt[j] * (st.jrest[j][0] - st.jrest[p][0]);
+            d[p][1] += d[j][0] * R[3] + d[j][1] * R[4] + d[j][2] * R[5] + dt[j] * (st.jrest[j][1] - st.jrest[p][1]);
+            d[p][2] += d[j][0] * R[6] + d[j][1] * R[7] + d[j][2] * R[8] + dt[j] * (st.jrest[j][2] - st.jrest[p][2]);
+            dt[p] += dt[j];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < kJoints; ++j) {
+            st.dgr[j][r * 3] = d[j][0]; st.dgr[j][r * 3 + 1] = d[j][1]; st.dgr[j][r * 3 + 2] = d[j][2];
+            st.dgt[j][r] = dt[j];
         }
     }
 }

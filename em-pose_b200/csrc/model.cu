@@ -337,6 +337,7 @@ struct empose_ief {
     SubModel sub;
     ResidualSpec spec;
     int slot_of_sensor[kSensors];
+    int static_tree = 0;       // sub.parents equals the standard SMPL body tree
     std::vector<PackedMatrix> lstm;
     PackedMatrix heads;
     MlpPacked pose_init, shape_init, pose_iter, shape_iter;
@@ -597,6 +598,13 @@ int upload_submodel(empose_ief* ctx, const TensorTable& tt) {
     EMPOSE_TRY(up_i("sub.vj_ptr", m.n_vj + 1, &m.vj_ptr, 0, n_jt + 1));
     EMPOSE_TRY(up_i("sub.jvj_ptr", kJoints + 1, &m.jvj_ptr, 0, m.n_vj + 1));
     EMPOSE_TRY(up_i("sub.parents", kJoints, &m.parents, -1, kJoints));
+    {
+        const int32_t* hp;
+        EMPOSE_TRY(tt.get_i32("sub.parents", kJoints, &hp));
+        ctx->static_tree = 1;
+        for (int j = 0; j < kJoints; ++j)
+            if (hp[j] != smpl_parent(j)) ctx->static_tree = 0;
+    }
     EMPOSE_TRY(up_i("sub.faces", (int64_t)m.n_faces * 3, &m.faces, 0, m.n_verts));
     EMPOSE_TRY(up_i("sub.sensor_vert", kSensors, &m.sensor_vert, 0, m.n_verts));
     EMPOSE_TRY(up_i("sub.helper_vert", kSensors, &m.helper_vert, 0, m.n_verts));
@@ -734,6 +742,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         mp.theta = pl.theta; mp.beta = pl.beta; mp.vp_off = pl.vpoff;
         mp.offset_r = pl.off_r; mp.offset_t = pl.off_t; mp.rows_per_offset = F;
         mp.meas = pl.meas; mp.coef = pl.coef; mp.R = R; mp.want_grad = grad; mp.round_out = rnd;
+        mp.static_tree = ctx->static_tree;
         mp.sensor_pos = (hist && hist->markers) ? hist->markers + (size_t)it * R * 36 : nullptr;
         mp.sensor_ori = (hist && hist->markers_ori) ? hist->markers_ori + (size_t)it * R * 108 : nullptr;
         mp.joints = (hist && hist->joints) ? hist->joints + (size_t)it * R * kPoseDim : nullptr;
@@ -945,6 +954,7 @@ int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shap
     memset(&mp, 0, sizeof(mp));
     mp.sub = ctx->sub; mp.spec = ctx->spec; mp.theta = poses; mp.beta = shapes; mp.vp_off = pl->vpoff;
     mp.offset_r = offset_r; mp.offset_t = offset_t; mp.rows_per_offset = 1; mp.R = R; mp.want_grad = 0; mp.round_out = rnd;
+    mp.static_tree = ctx->static_tree;
     mp.sensor_pos = sensor_pos; mp.sensor_ori = sensor_ori; mp.joints = joints;
     ++ctx->last_launches;
     return launch_main(mp, s);

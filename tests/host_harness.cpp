@@ -14,6 +14,7 @@ struct HostSub {
     const int *skin_joint, *jt_ptr, *jt_vert, *parents, *faces, *sensor_vert, *helper_vert, *sensor_faces, *sensor_degree;
     const int *vj_ptr, *jvj_ptr;
     int n_vj;
+    int use_static_tree;
 };
 
 template <typename T>
@@ -31,6 +32,8 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
     ResidualSpec spec;
     spec.use_pos = use_pos; spec.use_ori = use_ori;
     for (int s = 0; s < kSensors; ++s) spec.sensor_active[s] = active[s];
+    bool use_static = h.use_static_tree != 0;
+    for (int j = 0; j < kJoints; ++j) use_static = use_static && (h.parents[j] == smpl_parent(j));
     std::vector<FrameState<T>> st_store(1);
     FrameState<T>& st = st_store[0];
     std::vector<T> vp_off(h.vp_dim), dpf(kPoseFeatPad);
@@ -52,7 +55,7 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
         phase_rodrigues(st, 0, 1);
         phase_rest_joints(m, st, 0, 1);
         phase_blend_verts(m, st, vp_off.data(), 0, 1);
-        phase_chain(m, st, 0, 1);
+        if (use_static) phase_chain_static(st, 0, 1); else phase_chain(m, st, 0, 1);
         phase_skin(m, st, 0, 1);
         phase_sensors(m, st, off_r + f * 108, off_t + f * 36, meas_pos + f * 36, meas_ori + f * 108, spec,
                       want_grad != 0, 0, 1);
@@ -70,7 +73,7 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
             for (int i = 0; i < h.n_verts * 3; ++i) acc += T(h.posedirs[k * h.vp_dim + i]) * st.dx[i];
             dpf[k] = acc;
         }
-        phase_chain_bwd(m, st, 0, 1);
+        if (use_static) phase_chain_bwd_static(st, 0, 1); else phase_chain_bwd(m, st, 0, 1);
         phase_chain_bwd_local(m, st, 0, 1);
         std::vector<T> gt(kPoseDim), gb(kBetas);
         phase_finish_theta(st, T(coef[f]), dpf.data(), gt.data(), 0, 1);

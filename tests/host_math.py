@@ -17,7 +17,7 @@ _I32_FIELDS = ['skin_joint', 'jt_ptr', 'jt_vert', 'parents', 'faces', 'sensor_ve
 class HostSub(ctypes.Structure):
     _fields_ = ([(n, ctypes.c_int) for n in ('n_verts', 'vp_dim', 'n_faces', 'max_degree', 'n_skin')] +
                 [(n, ctypes.POINTER(ctypes.c_float)) for n in _F32_FIELDS] +
-                [(n, ctypes.POINTER(ctypes.c_int)) for n in _I32_FIELDS] + [('n_vj', ctypes.c_int)])
+                [(n, ctypes.POINTER(ctypes.c_int)) for n in _I32_FIELDS] + [('n_vj', ctypes.c_int), ('use_static_tree', ctypes.c_int)])
 
 
 def _lib():
@@ -36,7 +36,7 @@ def _lib():
 
 
 def frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef, use_pos=True, use_ori=True,
-               want_grad=True, use_double=False):
+               want_grad=True, use_double=False, static_tree=True):
     """Run the per-frame math on the host.  All per-frame inputs are (n, ...) float32 arrays."""
     keep = []
     hs = HostSub()
@@ -52,6 +52,7 @@ def frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef,
         keep.append(a)
         setattr(hs, n, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
     hs.n_vj = int(sub['sub.vj_ptr'].shape[0]) - 1
+    hs.use_static_tree = int(static_tree)
     n = theta.shape[0]
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     theta, beta, off_r, off_t, meas_pos, meas_ori, coef = map(f32, (theta, beta, off_r, off_t, meas_pos, meas_ori, coef))

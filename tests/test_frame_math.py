@@ -47,9 +47,10 @@ def test_forward_matches_full_mesh_oracle(sub, oracle_smpl, topology, use_double
     np.testing.assert_allclose(out['sensor_ori'], ori.detach().numpy(), atol=5e-5 if not use_double else 2e-5, rtol=0)
 
 
+@pytest.mark.parametrize('static_tree', [True, False])
 @pytest.mark.parametrize('n_markers', [12, 6])
 @pytest.mark.parametrize('use_double', [True, False])
-def test_reverse_pass_matches_autograd(sub, oracle_smpl, topology, n_markers, use_double):
+def test_reverse_pass_matches_autograd(sub, oracle_smpl, topology, n_markers, use_double, static_tree):
     n = 8
     theta, beta, off_r, off_t = _case(n, seed=5)
     rng = np.random.RandomState(9)
@@ -67,7 +68,7 @@ def test_reverse_pass_matches_autograd(sub, oracle_smpl, topology, n_markers, us
     energy = (torch.sqrt((dp * dp).sum(-1)).sum(-1) + torch.sqrt((dr * dr).sum(-1)).sum(-1)) * torch.from_numpy(coef)
     g_pose, g_shape = torch.autograd.grad(energy.sum(), [pose, shape])
     out = host_math.frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori.reshape(n, 12, 9), active, coef,
-                               use_double=use_double)
+                               use_double=use_double, static_tree=static_tree)
     scale = float(g_pose.abs().max())
     # float32: the orientation residual differentiates normalised cross products of ~1 cm edges taken from
     # ~0.5 m coordinates, so ~1e-3 relative noise is inherent to single precision (the reference has it too)
