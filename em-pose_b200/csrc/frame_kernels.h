@@ -67,6 +67,7 @@ struct MainParams {
     int want_grad;
     int round_out;
     int static_tree;            // 1: sub.parents is the standard SMPL body tree -> register-resident chain phases
+    long long* ticks;           // development aid: per-phase clock64() samples of one CTA, or null
     float* sensor_pos;          // [R][36] or null
     float* sensor_ori;          // [R][108] or null
     float* joints;              // [R][66] or null

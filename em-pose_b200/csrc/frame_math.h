@@ -37,6 +37,7 @@ constexpr int kPoseFeat = 189;        // 21 joints x 9 rotation entries
 constexpr int kPoseFeatPad = 192;     // K of the pose-blend GEMM (multiple of 32 floats = one 128B swizzle row)
 constexpr int kMaxVp = 384;           // padded 3*Vs, supports sub-meshes of up to 128 vertices
 constexpr int kMaxDegree = 12;
+constexpr int kSplitDegree = 7;        // sensor valence up to which the sensor phase is split over (sensor, face) items
 constexpr int kMaxVj = 44;            // chunks of the joint->vertex lists (their partial sums alias dgr .. dj below)
 
 // Packed sub-model constants (pointers into device or host memory).  Layouts: see submodel.py.
@@ -54,6 +55,9 @@ struct SubModel {
     int n_vj;                  // "virtual joints": the per-joint lists cut into chunks of bounded length
     const int* vj_ptr;         // [n_vj+1] chunk -> range in jt_vert / jt_weight
     const int* jvj_ptr;        // [23]     joint -> range of chunks
+    const int* vinc_ptr;       // [n_verts+1] vertex -> its (item, code) incidences in the sensor phase
+    const int* vinc_item;      // sensor * max_degree + face slot
+    const int* vinc_code;      // 0/1/2: corner of that face, 3: the sensor vertex, 4: the helper vertex
     const int* parents;        // [22]
     const int* faces;          // [n_faces][3] local vertex ids
     const int* sensor_vert;    // [12]
@@ -77,8 +81,13 @@ struct FrameState {
     T grot[kJoints][9];       // world rotation G_j^R  (== A_j^R)
     T vp[VP];                 // v_template + S beta + pose blend
     T dx[VP];                 // dE/dx, then reused for dE/dvp
-    T dar[kJoints][9];        // dE/dA^R
-    T dat[kJoints][3];        // dE/dA^t
+    union {
+        struct {
+            T dar[kJoints][9];    // dE/dA^R
+            T dat[kJoints][3];    // dE/dA^t
+        };
+        T fn[kSensors][kSplitDegree][3];   // split sensor phases: un-normalised face normals, then (slot 0) dE/dn
+    };
     T dbeta_part[3][kBetas];
     // Forward-only scratch and reverse-only scratch share storage: everything in `fwd` is dead once the sensor
     // outputs and joints have been written out, which is before the first member of `bwd` is written.
@@ -250,29 +259,28 @@ EMPOSE_HD constexpr int smpl_parent(int j) {
     return j == 0 ? -1 : j <= 3 ? 0 : j <= 11 ? j - 3 : j <= 14 ? 9 : j <= 17 ? j - 3 : j - 2;
 }
 
-// F2': phase_chain specialised for the standard SMPL tree (same arithmetic, same order of operations).
+// F2': phase_chain specialised for the standard SMPL tree (same arithmetic, same order of operations).  Results
+// are stored as soon as they exist so that only the transforms of pending parents stay live in registers.
 template <typename T, int VP>
 EMPOSE_HD void phase_chain_static(FrameState<T, VP>& st, int lane, int lanes) {
     for (int r = lane; r < 3; r += lanes) {
         T g[kJoints][3], t[kJoints];
-        g[0][0] = st.rot[0][r * 3]; g[0][1] = st.rot[0][r * 3 + 1]; g[0][2] = st.rot[0][r * 3 + 2];
-        t[0] = st.jrest[0][r];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 1; j < kJoints; ++j) {
-            const int p = smpl_parent(j);
-            const T* R = st.rot[j];
-            g[j][0] = g[p][0] * R[0] + g[p][1] * R[3] + g[p][2] * R[6];
-            g[j][1] = g[p][0] * R[1] + g[p][1] * R[4] + g[p][2] * R[7];
-            g[j][2] = g[p][0] * R[2] + g[p][1] * R[5] + g[p][2] * R[8];
-            t[j] = g[p][0] * (st.jrest[j][0] - st.jrest[p][0]) + g[p][1] * (st.jrest[j][1] - st.jrest[p][1]) +
-                   g[p][2] * (st.jrest[j][2] - st.jrest[p][2]) + t[p];
-        }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int j = 0; j < kJoints; ++j) {
+            if (j == 0) {
+                g[0][0] = st.rot[0][r * 3]; g[0][1] = st.rot[0][r * 3 + 1]; g[0][2] = st.rot[0][r * 3 + 2];
+                t[0] = st.jrest[0][r];
+            } else {
+                const int p = smpl_parent(j);
+                const T* R = st.rot[j];
+                g[j][0] = g[p][0] * R[0] + g[p][1] * R[3] + g[p][2] * R[6];
+                g[j][1] = g[p][0] * R[1] + g[p][1] * R[4] + g[p][2] * R[7];
+                g[j][2] = g[p][0] * R[2] + g[p][1] * R[5] + g[p][2] * R[8];
+                t[j] = g[p][0] * (st.jrest[j][0] - st.jrest[p][0]) + g[p][1] * (st.jrest[j][1] - st.jrest[p][1]) +
+                       g[p][2] * (st.jrest[j][2] - st.jrest[p][2]) + t[p];
+            }
             st.grot[j][r * 3] = g[j][0]; st.grot[j][r * 3 + 1] = g[j][1]; st.grot[j][r * 3 + 2] = g[j][2];
             st.gpos[j][r] = t[j];
             st.atr[j][r] = t[j] - (g[j][0] * st.jrest[j][0] + g[j][1] * st.jrest[j][1] + g[j][2] * st.jrest[j][2]);
@@ -418,6 +426,136 @@ EMPOSE_HD void phase_sensors(const SubModel& m, FrameState<T, VP>& st, const TIn
     }
 }
 
+// F4 split in three so that the face work runs over (sensor, face) items instead of inside 12 long serial lanes
+// (used when max_degree <= kSplitDegree; same arithmetic as phase_sensors).
+// F4a: un-normalised face normals (12 * max_degree items).
+template <typename T, int VP>
+EMPOSE_HD void phase_sensor_faces(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int it = lane; it < kSensors * m.max_degree; it += lanes) {
+        const int s = it / m.max_degree, d = it % m.max_degree;
+        if (d >= m.sensor_degree[s]) continue;
+        const int* f = &m.faces[m.sensor_faces[s * m.max_degree + d] * 3];
+        const T* a = &st.x[f[0] * 3];
+        const T* b = &st.x[f[1] * 3];
+        const T* c = &st.x[f[2] * 3];
+        T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+        T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+        cross3(e1, e2, st.fn[s][d]);
+    }
+}
+
+// F4b: sensor frame, offsets, residual and its reverse up to dE/dn (12 items).  Leaves in st.fn[s][0..2]: dE/dn
+// (already divided by the degree), the helper-vertex term and the sensor-vertex term (zero for unused sensors).
+template <typename T, int VP, typename TIn>
+EMPOSE_HD void phase_sensor_frames(const SubModel& m, FrameState<T, VP>& st, const TIn* off_r, const TIn* off_t,
+                                   const TIn* meas_pos, const TIn* meas_ori, const ResidualSpec& spec, bool want_grad,
+                                   int lane, int lanes) {
+    for (int s = lane; s < kSensors; s += lanes) {
+        const int vs = m.sensor_vert[s], vh = m.helper_vert[s];
+        const int deg = m.sensor_degree[s];
+        const T* xs = &st.x[vs * 3];
+        T n[3] = {T(0), T(0), T(0)};
+        for (int d = 0; d < deg; ++d) { n[0] += st.fn[s][d][0]; n[1] += st.fn[s][d][1]; n[2] += st.fn[s][d][2]; }
+        const T inv_deg = T(1) / T(deg);
+        n[0] *= inv_deg; n[1] *= inv_deg; n[2] *= inv_deg;
+        T nh[3], u[3], s0[3], t[3], th[3], sv[3], sh[3];
+        const T n_len = normalize3(n, nh);
+        u[0] = st.x[vh * 3] - xs[0]; u[1] = st.x[vh * 3 + 1] - xs[1]; u[2] = st.x[vh * 3 + 2] - xs[2];
+        const T u_len = normalize3(u, s0);
+        cross3(nh, s0, t);
+        const T t_len = normalize3(t, th);
+        cross3(th, nh, sv);
+        const T s_len = normalize3(sv, sh);
+        T R[9] = {sh[0], th[0], nh[0], sh[1], th[1], nh[1], sh[2], th[2], nh[2]};
+        const TIn* Ro = off_r + s * 9;
+        const TIn* to = off_t + s * 3;
+        T Rc[9], pc[3];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j)
+                Rc[i * 3 + j] = R[i * 3] * T(Ro[j]) + R[i * 3 + 1] * T(Ro[3 + j]) + R[i * 3 + 2] * T(Ro[6 + j]);
+            pc[i] = xs[i] + R[i * 3] * T(to[0]) + R[i * 3 + 1] * T(to[1]) + R[i * 3 + 2] * T(to[2]);
+        }
+        for (int i = 0; i < 9; ++i) st.sensor_ori[s][i] = Rc[i];
+        for (int i = 0; i < 3; ++i) st.sensor_pos[s][i] = pc[i];
+        if (!want_grad) continue;
+        if (!spec.sensor_active[s]) {
+            for (int q = 0; q < 3; ++q) { st.fn[s][q][0] = T(0); st.fn[s][q][1] = T(0); st.fn[s][q][2] = T(0); }
+            continue;
+        }
+        T dpc[3] = {T(0), T(0), T(0)}, dRc[9];
+        for (int i = 0; i < 9; ++i) dRc[i] = T(0);
+        if (spec.use_pos) {
+            T d[3] = {pc[0] - T(meas_pos[s * 3]), pc[1] - T(meas_pos[s * 3 + 1]), pc[2] - T(meas_pos[s * 3 + 2])};
+            T len = sqrt_t(dot3(d, d));
+            T inv = len > T(0) ? T(1) / len : T(0);
+            dpc[0] = d[0] * inv; dpc[1] = d[1] * inv; dpc[2] = d[2] * inv;
+        }
+        if (spec.use_ori) {
+            T d[9], sq = T(0);
+            for (int i = 0; i < 9; ++i) { d[i] = Rc[i] - T(meas_ori[s * 9 + i]); sq += d[i] * d[i]; }
+            T len = sqrt_t(sq);
+            T inv = len > T(0) ? T(1) / len : T(0);
+            for (int i = 0; i < 9; ++i) dRc[i] = d[i] * inv;
+        }
+        T dR[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                dR[i * 3 + j] = dRc[i * 3] * T(Ro[j * 3]) + dRc[i * 3 + 1] * T(Ro[j * 3 + 1]) + dRc[i * 3 + 2] * T(Ro[j * 3 + 2]) +
+                                dpc[i] * T(to[j]);
+        T dsh[3] = {dR[0], dR[3], dR[6]}, dth[3] = {dR[1], dR[4], dR[7]}, dnh[3] = {dR[2], dR[5], dR[8]};
+        T dsv[3], tmp[3];
+        normalize3_bwd(sh, s_len, dsh, dsv);
+        cross3(nh, dsv, tmp); dth[0] += tmp[0]; dth[1] += tmp[1]; dth[2] += tmp[2];
+        cross3(dsv, th, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];
+        T dt[3], ds0[3];
+        normalize3_bwd(th, t_len, dth, dt);
+        cross3(s0, dt, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];
+        cross3(dt, nh, ds0);
+        T du[3];
+        normalize3_bwd(s0, u_len, ds0, du);
+        T dn[3];
+        normalize3_bwd(nh, n_len, dnh, dn);
+        for (int i = 0; i < 3; ++i) {
+            st.fn[s][0][i] = dn[i] * inv_deg;
+            st.fn[s][1][i] = du[i];                // goes to the helper vertex
+            st.fn[s][2][i] = dpc[i] - du[i];       // goes to the sensor vertex
+        }
+    }
+}
+
+// F4c: dE/dx by GATHER (n_verts items): every vertex sums, in a fixed order, the contributions of the faces it
+// is a corner of (recomputed from dE/dn of their sensor) and of the sensors it serves as sensor / helper vertex.
+// No atomics: the result is bit-reproducible, which window-sharded inference relies on.
+template <typename T, int VP>
+EMPOSE_HD void phase_sensor_gather(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int v = lane; v < m.n_verts; v += lanes) {
+        T g[3] = {T(0), T(0), T(0)};
+        for (int q = m.vinc_ptr[v]; q < m.vinc_ptr[v + 1]; ++q) {
+            const int item = m.vinc_item[q], code = m.vinc_code[q];
+            const int s = item / m.max_degree;
+            if (code >= 3) {
+                const T* t = st.fn[s][code == 3 ? 2 : 1];
+                g[0] += t[0]; g[1] += t[1]; g[2] += t[2];
+                continue;
+            }
+            const T* dn = st.fn[s][0];
+            const int* f = &m.faces[m.sensor_faces[item] * 3];
+            const T* a = &st.x[f[0] * 3];
+            const T* b = &st.x[f[1] * 3];
+            const T* c = &st.x[f[2] * 3];
+            T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+            T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+            T de1[3], de2[3];
+            cross3(e2, dn, de1);      // fn = e1 x e2: d e1 = e2 x dfn, d e2 = dfn x e1
+            cross3(dn, e1, de2);
+            if (code == 1) { g[0] += de1[0]; g[1] += de1[1]; g[2] += de1[2]; }
+            else if (code == 2) { g[0] += de2[0]; g[1] += de2[1]; g[2] += de2[2]; }
+            else { g[0] -= de1[0] + de2[0]; g[1] -= de1[1] + de2[1]; g[2] -= de1[2] + de2[2]; }
+        }
+        st.dx[v * 3] = g[0]; st.dx[v * 3 + 1] = g[1]; st.dx[v * 3 + 2] = g[2];
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // reverse phases
 // ----------------------------------------------------------------------------------------------
@@ -511,38 +649,36 @@ EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int lan
     }
 }
 
-// B4': phase_chain_bwd specialised for the standard SMPL tree, dE/dG rows held in registers.
+// B4': phase_chain_bwd specialised for the standard SMPL tree.  Children contributions are accumulated in
+// registers (`acc`, zero until first touched) and each joint is finalised and stored when the sweep reaches it,
+// so only the partial sums of pending parents are live.
 template <typename T, int VP>
 EMPOSE_HD void phase_chain_bwd_static(FrameState<T, VP>& st, int lane, int lanes) {
     for (int r = lane; r < 3; r += lanes) {
-        T d[kJoints][3], dt[kJoints];
+        T acc[kJoints][3], acct[kJoints];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < kJoints; ++j) {
+        for (int j = 0; j < kJoints; ++j) { acc[j][0] = T(0); acc[j][1] = T(0); acc[j][2] = T(0); acct[j] = T(0); }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = kJoints - 1; j >= 0; --j) {
             const T a = st.dat[j][r];
-            dt[j] = a;
-            d[j][0] = st.dar[j][r * 3] - a * st.jrest[j][0];
-            d[j][1] = st.dar[j][r * 3 + 1] - a * st.jrest[j][1];
-            d[j][2] = st.dar[j][r * 3 + 2] - a * st.jrest[j][2];
-        }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = kJoints - 1; j >= 1; --j) {
-            const int p = smpl_parent(j);
-            const T* R = st.rot[j];
-            d[p][0] += d[j][0] * R[0] + d[j][1] * R[1] + d[j][2] * R[2] + dt[j] * (st.jrest[j][0] - st.jrest[p][0]);
-            d[p][1] += d[j][0] * R[3] + d[j][1] * R[4] + d[j][2] * R[5] + dt[j] * (st.jrest[j][1] - st.jrest[p][1]);
-            d[p][2] += d[j][0] * R[6] + d[j][1] * R[7] + d[j][2] * R[8] + dt[j] * (st.jrest[j][2] - st.jrest[p][2]);
-            dt[p] += dt[j];
-        }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < kJoints; ++j) {
-            st.dgr[j][r * 3] = d[j][0]; st.dgr[j][r * 3 + 1] = d[j][1]; st.dgr[j][r * 3 + 2] = d[j][2];
-            st.dgt[j][r] = dt[j];
+            const T dt = a + acct[j];
+            const T d0 = st.dar[j][r * 3] - a * st.jrest[j][0] + acc[j][0];
+            const T d1 = st.dar[j][r * 3 + 1] - a * st.jrest[j][1] + acc[j][1];
+            const T d2 = st.dar[j][r * 3 + 2] - a * st.jrest[j][2] + acc[j][2];
+            st.dgr[j][r * 3] = d0; st.dgr[j][r * 3 + 1] = d1; st.dgr[j][r * 3 + 2] = d2;
+            st.dgt[j][r] = dt;
+            if (j > 0) {
+                const int p = smpl_parent(j);
+                const T* R = st.rot[j];
+                acc[p][0] += d0 * R[0] + d1 * R[1] + d2 * R[2] + dt * (st.jrest[j][0] - st.jrest[p][0]);
+                acc[p][1] += d0 * R[3] + d1 * R[4] + d2 * R[5] + dt * (st.jrest[j][1] - st.jrest[p][1]);
+                acc[p][2] += d0 * R[6] + d1 * R[7] + d2 * R[8] + dt * (st.jrest[j][2] - st.jrest[p][2]);
+                acct[p] += dt;
+            }
         }
     }
 }

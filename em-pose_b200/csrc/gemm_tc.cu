@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                             mbar_wait(&ctl->empty[stage], phase ^ 1u);
                             uint8_t* a_dst = smem + stage * kStageBytes;
                             uint8_t* w_dst = a_dst + kABytes;
-                            if (debug_mode == 2) {            // measurement only: no loads, MMAs run on stale data
+                            if (debug_mode & 2) {            // measurement only: no loads, MMAs run on stale data
                                 mbar_arrive(&ctl->full[stage]);
                             } else {
                                 mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
                         const uint64_t a_desc = make_smem_desc(a_addr);
                         const uint64_t b_desc = make_smem_desc(a_addr + kABytes);
-                        if (debug_mode == 1) {                // measurement only: loads without MMAs
+                        if (debug_mode & 1) {                // measurement only: loads without MMAs
                             mbar_arrive(&ctl->empty[stage]);
                         } else {
 #pragma unroll
@@ -273,11 +273,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 for (int c0 = half * (kMaxTileN / 2); c0 < c_end; c0 += 32) {
                     float v[32];
                     tmem_load_32cols(taddr + (uint32_t)c0, v);
-                    epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats);
+                    if (!(debug_mode & 4)) epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats);
                 }
                 tcgen05_fence_before();
-                __threadfence();                                  // stores visible at L2 ...
-                asm volatile("fence.proxy.async;" ::: "memory");   // ... and ordered before later TMA reads
+                if (!(debug_mode & 8)) {
+                    __threadfence();                                  // stores visible at L2 ...
+                    asm volatile("fence.proxy.async;" ::: "memory");   // ... and ordered before later TMA reads
+                }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 if (threadIdx.x == 4 * 32) {
                     mbar_arrive(&ctl->tmem_empty[buf]);

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -597,6 +598,12 @@ int upload_submodel(empose_ief* ctx, const TensorTable& tt) {
     if (m.n_vj < 1 || m.n_vj > kMaxVj) { set_last_error("sub.vj_ptr: number of chunks out of range"); return EMPOSE_E_ARG; }
     EMPOSE_TRY(up_i("sub.vj_ptr", m.n_vj + 1, &m.vj_ptr, 0, n_jt + 1));
     EMPOSE_TRY(up_i("sub.jvj_ptr", kJoints + 1, &m.jvj_ptr, 0, m.n_vj + 1));
+    const int32_t* vinc_ptr;
+    EMPOSE_TRY(tt.get_i32("sub.vinc_ptr", m.n_verts + 1, &vinc_ptr));
+    const int n_inc = vinc_ptr[m.n_verts];
+    EMPOSE_TRY(up_i("sub.vinc_ptr", m.n_verts + 1, &m.vinc_ptr, 0, n_inc + 1));
+    EMPOSE_TRY(up_i("sub.vinc_item", n_inc, &m.vinc_item, 0, kSensors * m.max_degree));
+    EMPOSE_TRY(up_i("sub.vinc_code", n_inc, &m.vinc_code, 0, 5));
     EMPOSE_TRY(up_i("sub.parents", kJoints, &m.parents, -1, kJoints));
     {
         const int32_t* hp;
@@ -748,7 +755,20 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         mp.joints = (hist && hist->joints) ? hist->joints + (size_t)it * R * kPoseDim : nullptr;
         if (it == N && !mp.joints) mp.joints = pl.joints;
         mp.dvp = pl.dvp; mp.gtheta_part = pl.gth_part; mp.gbeta = pl.gbeta;
+        static long long* tick_buf = nullptr;          // EMPOSE_MAIN_TICKS=1: dump phase timing of the first gradient launch
+        static const bool want_ticks = getenv("EMPOSE_MAIN_TICKS") != nullptr;
+        if (want_ticks && it == 0) {
+            if (!tick_buf) cudaMalloc(&tick_buf, 32 * sizeof(long long));
+            mp.ticks = tick_buf;
+        }
         EMPOSE_TRY(count(launch_main(mp, s)));
+        if (want_ticks && it == 0) {
+            long long h[32];
+            cudaMemcpy(h, tick_buf, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "main_kernel ticks:");
+            for (int q = 1; q < 16; ++q) fprintf(stderr, " %lld", h[q] - h[q - 1]);
+            fprintf(stderr, "\n");
+        }
         if (it == N) {
             if (joints_hat)
                 EMPOSE_CUDA_TRY(cudaMemcpyAsync(joints_hat, mp.joints, (size_t)R * kPoseDim * 4, cudaMemcpyDeviceToDevice, s));

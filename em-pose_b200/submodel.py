@@ -146,6 +146,30 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
             break
         chunk_len += 2
 
+    # per-vertex incidence lists for the atomic-free reverse of the sensor phase: entry (item, code) with
+    # item = sensor * max_degree + slot and code 0/1/2 = corner of that face, 3 = the sensor vertex itself,
+    # 4 = the sensor's helper vertex
+    sensor_faces_arr = np.asarray(topology['sensor_faces'], dtype=np.int64)
+    max_deg = int(sensor_faces_arr.shape[1])
+    local_faces = local[sub_faces]
+    inc = [[] for _ in range(n_sub)]
+    for s_idx in range(sensor_ids.shape[0]):
+        for d in range(max_deg):
+            fid = int(sensor_faces_arr[s_idx, d])
+            if fid < 0:
+                continue
+            for corner in range(3):
+                inc[int(local_faces[fid, corner])].append((s_idx * max_deg + d, corner))
+        inc[int(local[sensor_ids[s_idx]])].append((s_idx * max_deg, 3))
+        inc[int(local[helper_ids[s_idx]])].append((s_idx * max_deg, 4))
+    vinc_ptr = np.zeros(n_sub + 1, dtype=np.int32)
+    vinc_item, vinc_code = [], []
+    for v in range(n_sub):
+        for item, code in inc[v]:
+            vinc_item.append(item)
+            vinc_code.append(code)
+        vinc_ptr[v + 1] = len(vinc_item)
+
     vp_dim = ((n_sub * 3 + 15) // 16) * 16                     # padded width of the per-frame vertex vector
     pd = posedirs.reshape(posedirs.shape[0], n_v, 3)[:N_POSE_FEATURES, verts].reshape(N_POSE_FEATURES, n_sub * 3)
     sd = shapedirs[verts].reshape(n_sub * 3, N_BETAS).T                              # (10, Vs*3)
@@ -168,6 +192,9 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
         'sub.skin_joint': skin_joint,
         'sub.jt_ptr': jt_ptr,
         'sub.jt_vert': np.asarray(jt_vert, dtype=np.int32),
+        'sub.vinc_ptr': vinc_ptr,
+        'sub.vinc_item': np.asarray(vinc_item, dtype=np.int32),
+        'sub.vinc_code': np.asarray(vinc_code, dtype=np.int32),
         'sub.vj_ptr': np.asarray(vj_ptr, dtype=np.int32),
         'sub.jvj_ptr': np.asarray(jvj_ptr, dtype=np.int32),
         'sub.faces': local[sub_faces].astype(np.int32),                               # (Fs,3) local ids

@@ -7,7 +7,10 @@ from empose_b200 import lib
 
 dev = torch.device('cuda:0')
 res = {}
-for (m, n, k) in [(131072, 512, 512), (131072, 256, 576), (4096, 2048, 672), (131072, 512, 2048), (131072, 256, 512), (131072, 128, 512)]:
+shapes = [(131072, 512, 512), (131072, 256, 576), (4096, 2048, 672), (131072, 512, 2048), (131072, 256, 512), (131072, 128, 512)]
+if len(sys.argv) > 1:
+    shapes = [tuple(int(x) for x in a.split('x')) for a in sys.argv[1:]]
+for (m, n, k) in shapes:
     a = torch.randn(m, k, device=dev)
     w = torch.randn(n, k, device=dev)
     b = torch.zeros(n, device=dev)

@@ -12,7 +12,7 @@ struct HostSub {
     int n_verts, vp_dim, n_faces, max_degree, n_skin;
     const float *v_template, *shapedirs, *posedirs, *j0, *jdirs, *skin_weight, *jt_weight;
     const int *skin_joint, *jt_ptr, *jt_vert, *parents, *faces, *sensor_vert, *helper_vert, *sensor_faces, *sensor_degree;
-    const int *vj_ptr, *jvj_ptr;
+    const int *vj_ptr, *jvj_ptr, *vinc_ptr, *vinc_item, *vinc_code;
     int n_vj;
     int use_static_tree;
 };
@@ -29,6 +29,7 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
     m.jt_weight = h.jt_weight; m.parents = h.parents; m.faces = h.faces; m.sensor_vert = h.sensor_vert;
     m.helper_vert = h.helper_vert; m.sensor_faces = h.sensor_faces; m.sensor_degree = h.sensor_degree;
     m.n_vj = h.n_vj; m.vj_ptr = h.vj_ptr; m.jvj_ptr = h.jvj_ptr;
+    m.vinc_ptr = h.vinc_ptr; m.vinc_item = h.vinc_item; m.vinc_code = h.vinc_code;
     ResidualSpec spec;
     spec.use_pos = use_pos; spec.use_ori = use_ori;
     for (int s = 0; s < kSensors; ++s) spec.sensor_active[s] = active[s];
@@ -57,8 +58,15 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
         phase_blend_verts(m, st, vp_off.data(), 0, 1);
         if (use_static) phase_chain_static(st, 0, 1); else phase_chain(m, st, 0, 1);
         phase_skin(m, st, 0, 1);
-        phase_sensors(m, st, off_r + f * 108, off_t + f * 36, meas_pos + f * 36, meas_ori + f * 108, spec,
-                      want_grad != 0, 0, 1);
+        if (h.use_static_tree && m.max_degree <= kSplitDegree) {       // the split form the GPU kernel uses
+            phase_sensor_faces(m, st, 0, 1);
+            phase_sensor_frames(m, st, off_r + f * 108, off_t + f * 36, meas_pos + f * 36, meas_ori + f * 108, spec,
+                                want_grad != 0, 0, 1);
+            if (want_grad) phase_sensor_gather(m, st, 0, 1);
+        } else {
+            phase_sensors(m, st, off_r + f * 108, off_t + f * 36, meas_pos + f * 36, meas_ori + f * 108, spec,
+                          want_grad != 0, 0, 1);
+        }
         for (int i = 0; i < 36; ++i) sensor_pos[f * 36 + i] = double(st.sensor_pos[i / 3][i % 3]);
         for (int i = 0; i < 108; ++i) sensor_ori[f * 108 + i] = double(st.sensor_ori[i / 9][i % 9]);
         for (int i = 0; i < 66; ++i) joints[f * 66 + i] = double(st.gpos[i / 3][i % 3]);

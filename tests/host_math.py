@@ -11,7 +11,7 @@ _LIB = None
 
 _F32_FIELDS = ['v_template', 'shapedirs', 'posedirs', 'j0', 'jdirs', 'skin_weight', 'jt_weight']
 _I32_FIELDS = ['skin_joint', 'jt_ptr', 'jt_vert', 'parents', 'faces', 'sensor_vert', 'helper_vert', 'sensor_faces',
-               'sensor_degree', 'vj_ptr', 'jvj_ptr']
+               'sensor_degree', 'vj_ptr', 'jvj_ptr', 'vinc_ptr', 'vinc_item', 'vinc_code']
 
 
 class HostSub(ctypes.Structure):

@@ -86,5 +86,5 @@ def test_submodel_arrays_are_complete(smpl_npz):
     sub = net.smpl.submodel_arrays()
     assert sub['sub.dims'].tolist()[-1] == 12 and sub['sub.posedirs'].shape[0] == 189
     assert set(sub) >= {'sub.v_template', 'sub.shapedirs', 'sub.posedirs', 'sub.j0', 'sub.jdirs', 'sub.skin_weight',
-                        'sub.skin_joint', 'sub.jt_ptr', 'sub.jt_vert', 'sub.jt_weight', 'sub.vj_ptr', 'sub.jvj_ptr', 'sub.parents', 'sub.faces',
+                        'sub.skin_joint', 'sub.jt_ptr', 'sub.jt_vert', 'sub.jt_weight', 'sub.vj_ptr', 'sub.jvj_ptr', 'sub.vinc_ptr', 'sub.vinc_item', 'sub.vinc_code', 'sub.parents', 'sub.faces',
                         'sub.sensor_vert', 'sub.helper_vert', 'sub.sensor_faces', 'sub.sensor_degree', 'sub.dims'}
