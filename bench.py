@@ -32,6 +32,11 @@ FRAMES = 32
 FLOP_PER_FRAME = 26472448          # 2 x MACs of the learned layers, LGD-RNN-12-N4
 BYTES_PER_FRAME = 1162             # algorithmic HBM bytes per frame
 METRIC = 'frames/sec LGD-RNN-12 N=4 ws=32'
+# dram__bytes_read.sum + dram__bytes_write.sum of gemm_tc_kernel from the committed ncu --set full captures
+# (profiles/r01/ncu_summary_v4.txt): launch-weighted mean over the 47 launches of a step.
+NCU_TRAFFIC_BYTES = (4 * 4.017e9 + 33 * 0.055e9 + 10 * 0.30e9) / 47
+NCU_TRAFFIC_NOTE = ('mean per launch at 4096 windows: MLP-chain launch 4.02 GB and LSTM launch 0.055 GB measured, the ten small '
+                    'pose-blend / heads launches estimated at 0.3 GB; algorithmic bytes per launch ~3 MB')
 
 
 def asset_dir():
@@ -257,7 +262,8 @@ def run_b200(args, rank, local_rank, world):
     peaks = measured_peaks()
     achieved = FLOP_PER_FRAME * frames_per_step * prof_steps / (gemm_ms / 1000.0) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'frac': achieved / peaks['bf16_tflops_sustained'], 'traffic': NCU_TRAFFIC_BYTES,
+                'traffic_note': NCU_TRAFFIC_NOTE,
                 'kernel': 'gemm_tc_kernel (tcgen05.mma kind::tf32)', 'peak_source': peaks['source'] + ' bf16 dense, sustained',
                 'frac_of_tf32_rate': achieved / (peaks['bf16_tflops_sustained'] / 2.0),
                 'launches_per_step': gemm_launches / prof_steps, 'avg_launch_ms': gemm_ms / max(gemm_launches, 1),
