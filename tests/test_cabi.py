@@ -88,3 +88,22 @@ def test_submodel_arrays_are_complete(smpl_npz):
     assert set(sub) >= {'sub.v_template', 'sub.shapedirs', 'sub.posedirs', 'sub.j0', 'sub.jdirs', 'sub.skin_weight',
                         'sub.skin_joint', 'sub.jt_ptr', 'sub.jt_vert', 'sub.jt_weight', 'sub.vj_ptr', 'sub.jvj_ptr', 'sub.vinc_ptr', 'sub.vinc_item', 'sub.vinc_code', 'sub.parents', 'sub.faces',
                         'sub.sensor_vert', 'sub.helper_vert', 'sub.sensor_faces', 'sub.sensor_degree', 'sub.dims'}
+
+
+def test_dropin_rebinds_the_reference_factories(smpl_npz, asset_dir):
+    """With the reference tree present, dropin.install() makes the reference's own factory build our class."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip('reference tree not present on this machine')
+    ref_shims.install(asset_dir, seed=0)
+    import empose_b200.dropin
+    from empose_b200.nn.models import IterativeErrorFeedback
+    ref_models, ref_smpl = empose_b200.dropin.install()
+    flags = ['--m_type', 'lgd', '--m_num_iterations', '2', '--m_hidden_size', '512', '--m_rnn_init', '--m_average_shape',
+             '--m_use_gradient', '--use_marker_pos', '--use_marker_ori', '--n_markers', '6', '--window_size', '32']
+    cfg = ref_shims.make_config(flags)                      # the reference's own Configuration object
+    smpl = ref_smpl.SMPLLayer(smpl_npz)
+    net = ref_models.create_model(cfg, smpl)
+    assert isinstance(net, IterativeErrorFeedback) and isinstance(net, ref_models.IterativeErrorFeedback)
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == 5721419     # README.md:228
+    assert net.model_name().startswith('IEF-2x512-N2-RNN-2x512')
