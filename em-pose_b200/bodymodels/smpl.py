@@ -2,8 +2,9 @@
 
 ``SMPLLayer`` keeps the third-party ``BodyModel``'s buffers and parameters under ``.bm`` so that the
 ``smpl.bm.*`` keys of released checkpoints load unchanged, and exposes ``faces`` / ``vertex_faces`` as
-the reference does.  The LGD loop does not evaluate the full mesh: it uses the sub-model of
-``empose_b200.submodel`` inside the CUDA library.
+the reference does.  ``forward`` / ``fk`` evaluate the full 6890-vertex mesh in the CUDA library
+(``empose_smpl_forward``); the LGD loop itself never needs the full mesh and uses the sub-model of
+``empose_b200.submodel``.
 """
 import os
 
@@ -53,6 +54,9 @@ class SMPLLayer(nn.Module):
         self._vertex_faces = None
         self._faces = None
         self._topology = None
+        self._ctx = None
+        self._ctx_key = None
+        self.precision = 0            # lib.PRECISION_TF32; set to lib.PRECISION_FP32 for the exact-arithmetic mode
 
     @property
     def faces(self):
@@ -86,9 +90,42 @@ class SMPLLayer(nn.Module):
         sub.pop('sub.global_vertex_ids')
         return sub
 
+    def fullmodel_arrays(self):
+        """The ``smpl.*`` arrays of the full mesh for ``empose_smpl_create`` (float64 extraction, see submodel.py)."""
+        bm = self.bm
+        f64 = lambda t: t.detach().cpu().double().numpy()
+        return _submodel.extract_fullmodel(f64(bm.v_template), f64(bm.shapedirs), f64(bm.posedirs), f64(bm.J_regressor),
+                                           f64(bm.weights), bm.kintree_table.cpu().numpy())
+
+    def _native(self, device):
+        from empose_b200 import lib as _lib
+        if device.type != 'cuda':
+            raise _lib.EmposeError('empose_b200 runs on CUDA devices only (no CPU fallback); got %s' % device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (index, self.precision) + tuple((t.data_ptr(), t._version) for t in self.bm.buffers())
+        if self._ctx is None or key != self._ctx_key:
+            if self._ctx is not None:
+                self._ctx.close()
+            self._ctx = _lib.SmplContext(self.fullmodel_arrays(), self.precision, index)
+            self._ctx_key = key
+        return self._ctx
+
+    def _fk(self, poses_body, betas, poses_root=None, trans=None, normalize_root=False):
+        """``smpl.py:81-122``: zero hand pose, root / trans default to zero, betas broadcast and cut to 10."""
+        assert poses_body.shape[1] >= C.N_JOINTS * 3                        # smpl.py:93
+        if normalize_root:
+            raise NotImplementedError('normalize_root is a data-normalisation option outside the LGD hot path')
+        n = poses_body.shape[0]
+        if len(betas.shape) == 1 or betas.shape[0] == 1:
+            betas = betas.reshape(1, -1).repeat(n, 1)
+        betas = betas[:, :self.num_betas]
+        return self._native(poses_body.device).forward(poses_body[:, :C.N_JOINTS * 3], betas, poses_root, trans)
+
     def fk(self, poses_body, betas, poses_root=None, trans=None, normalize_root=False, window_size=None):
-        raise NotImplementedError('full-mesh SMPLLayer.forward is not built yet in empose_b200 (the LGD loop uses the '
-                                  'sensor sub-model); see DESIGN.md "next"')
+        """``smpl.py:124-147``.  ``window_size`` is accepted for compatibility: the library evaluates in slabs anyway."""
+        if window_size is not None and normalize_root:
+            raise ValueError("Are you sure you want to use root normalization with windowed evaluation?")
+        return self._fk(poses_body, betas, poses_root, trans, normalize_root)
 
     def forward(self, *args, **kwargs):
         return self.fk(*args, **kwargs)

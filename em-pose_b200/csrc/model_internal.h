@@ -1,0 +1,289 @@
+// Host-side helpers shared by model.cu (the LGD model context) and smpl_full.cu (the full-mesh SMPL layer):
+// tensor-table lookup, device arena, packed weight matrices, GEMM job book-keeping.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/empose_b200.h"
+#include "common.cuh"
+#include "gemm_jobs.h"
+#include "gemm_tc.h"
+
+namespace empose {
+
+#define EMPOSE_TRY(expr)            \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != EMPOSE_OK) return _rc; \
+    } while (0)
+
+inline float host_round_tf32(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;   // inf / nan
+    u += 0x1000u;                                       // round to nearest, ties away (cvt.rna)
+    u &= 0xFFFFE000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+
+// ---- tensor table -----------------------------------------------------------------------------
+struct TensorTable {
+    const empose_tensor* t;
+    int n;
+    const empose_tensor* find(const std::string& name) const {
+        for (int i = 0; i < n; ++i)
+            if (name == t[i].name) return &t[i];
+        return nullptr;
+    }
+    int64_t numel(const empose_tensor* e) const {
+        int64_t k = 1;
+        for (int d = 0; d < e->ndim; ++d) k *= e->shape[d];
+        return k;
+    }
+    // fetch a float tensor with an exact shape
+    int get_f32(const std::string& name, std::initializer_list<int64_t> shape, const float** out) const {
+        const empose_tensor* e = find(name);
+        if (!e) { set_last_error("missing tensor '" + name + "'"); return EMPOSE_E_MISSING; }
+        if (e->dtype != EMPOSE_F32) { set_last_error("tensor '" + name + "' must be float32"); return EMPOSE_E_SHAPE; }
+        int64_t want = 1;
+        for (int64_t s : shape) want *= s;
+        if (numel(e) != want) {
+            set_last_error("tensor '" + name + "' has " + std::to_string(numel(e)) + " elements, expected " + std::to_string(want));
+            return EMPOSE_E_SHAPE;
+        }
+        *out = static_cast<const float*>(e->data);
+        return EMPOSE_OK;
+    }
+    int get_i32(const std::string& name, int64_t count, const int32_t** out) const {
+        const empose_tensor* e = find(name);
+        if (!e) { set_last_error("missing tensor '" + name + "'"); return EMPOSE_E_MISSING; }
+        if (e->dtype != EMPOSE_I32) { set_last_error("tensor '" + name + "' must be int32"); return EMPOSE_E_SHAPE; }
+        if (count >= 0 && numel(e) != count) { set_last_error("tensor '" + name + "' has the wrong size"); return EMPOSE_E_SHAPE; }
+        *out = static_cast<const int32_t*>(e->data);
+        return EMPOSE_OK;
+    }
+};
+
+// ---- device memory ------------------------------------------------------------------------------
+struct Arena {
+    std::vector<void*> ptrs;
+    ~Arena() { for (void* p : ptrs) cudaFree(p); }
+    int alloc(size_t bytes, void** out, bool zero = false) {
+        void* p = nullptr;
+        if (bytes == 0) bytes = 16;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            set_last_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+            return EMPOSE_E_NOMEM;
+        }
+        ptrs.push_back(p);
+        if (zero) EMPOSE_CUDA_TRY(cudaMemset(p, 0, bytes));
+        *out = p;
+        return EMPOSE_OK;
+    }
+    template <typename T> int alloc_n(size_t count, T** out, bool zero = false) {
+        void* p;
+        EMPOSE_TRY(alloc(count * sizeof(T), &p, zero));
+        *out = static_cast<T*>(p);
+        return EMPOSE_OK;
+    }
+    template <typename T> int upload(const std::vector<T>& h, T** out) {
+        EMPOSE_TRY(alloc_n<T>(h.size(), out));
+        if (!h.empty()) EMPOSE_CUDA_TRY(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return EMPOSE_OK;
+    }
+};
+
+// ---- packed weights -----------------------------------------------------------------------------
+struct PackedMatrix {
+    float* w = nullptr;       // device [n_pad][ld]
+    float* bias = nullptr;    // device [n_pad] or null
+    int n = 0, n_pad = 0, tile_n = 0, n_tiles = 0;
+    int kseg[2] = {0, 0};     // real K of each segment
+    int koff[2] = {0, 0};     // column where the segment starts in w
+    int64_t ld = 0;
+    int has_act = 0;
+    float alpha = 0.0f;
+};
+
+inline void choose_tiles(int n, int granule, PackedMatrix* pm) {
+    const int n16 = round_up(n, granule);
+    pm->n = n;
+    pm->n_tiles = ceil_div(n16, kMaxTileN);
+    pm->tile_n = round_up(ceil_div(n16, pm->n_tiles), granule);
+    pm->n_pad = pm->tile_n * pm->n_tiles;
+}
+
+// rows: function giving source row r (0..n-1) as (pointer to K0 floats, pointer to K1 floats) plus scale/bias
+struct RowSource {
+    const float* w0; const float* w1; double scale; double bias;
+};
+
+template <typename F>
+int pack_matrix(Arena& arena, int n, int k0, int k1, int granule, bool round, bool with_bias, F row_of, PackedMatrix* pm) {
+    choose_tiles(n, granule, pm);
+    pm->kseg[0] = k0; pm->kseg[1] = k1;
+    pm->koff[0] = 0; pm->koff[1] = round_up(k0, kChunkK);
+    pm->ld = round_up(k0, kChunkK) + (k1 > 0 ? round_up(k1, kChunkK) : 0);
+    std::vector<float> hw((size_t)pm->n_pad * pm->ld, 0.0f), hb((size_t)pm->n_pad + 32, 0.0f);   // bias padded for vector loads
+    for (int r = 0; r < n; ++r) {
+        RowSource src = row_of(r);
+        float* dst = &hw[(size_t)r * pm->ld];
+        for (int k = 0; k < k0; ++k) dst[k] = (float)(src.scale * (double)src.w0[k]);
+        for (int k = 0; k < k1; ++k) dst[pm->koff[1] + k] = (float)(src.scale * (double)src.w1[k]);
+        if (round) for (int64_t k = 0; k < pm->ld; ++k) dst[k] = host_round_tf32(dst[k]);
+        hb[r] = (float)src.bias;
+    }
+    EMPOSE_TRY(arena.upload(hw, &pm->w));
+    if (with_bias) EMPOSE_TRY(arena.upload(hb, &pm->bias));
+    return EMPOSE_OK;
+}
+
+struct MlpPacked { std::vector<PackedMatrix> layers; };   // input, 2*blocks hidden, output
+
+// nn.Linear (+ BatchNorm1d in eval mode folded in double) (+ PReLU slope) -> PackedMatrix
+inline int pack_linear(Arena& arena, const TensorTable& tt, const std::string& lin, const std::string& bn,
+                const std::string& prelu, int n_out, int n_in, bool round, PackedMatrix* pm) {
+    const float *w, *b, *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
+    EMPOSE_TRY(tt.get_f32(lin + ".weight", {n_out, n_in}, &w));
+    EMPOSE_TRY(tt.get_f32(lin + ".bias", {n_out}, &b));
+    if (!bn.empty()) {
+        EMPOSE_TRY(tt.get_f32(bn + ".weight", {n_out}, &g));
+        EMPOSE_TRY(tt.get_f32(bn + ".bias", {n_out}, &be));
+        EMPOSE_TRY(tt.get_f32(bn + ".running_mean", {n_out}, &mu));
+        EMPOSE_TRY(tt.get_f32(bn + ".running_var", {n_out}, &var));
+    }
+    EMPOSE_TRY(pack_matrix(arena, n_out, n_in, 0, 16, round, true, [&](int r) {
+        RowSource s{w + (size_t)r * n_in, nullptr, 1.0, (double)b[r]};
+        if (g) {   // y = gamma (Wx + b - mean) / sqrt(var + eps) + beta   (eps = 1e-5, torch default used by layers.py:26,57)
+            const double sc = (double)g[r] / std::sqrt((double)var[r] + 1e-5);
+            s.scale = sc;
+            s.bias = ((double)b[r] - (double)mu[r]) * sc + (double)be[r];
+        }
+        return s;
+    }, pm));
+    if (!prelu.empty()) {
+        const float* a;
+        EMPOSE_TRY(tt.get_f32(prelu + ".weight", {1}, &a));
+        pm->has_act = 1;
+        pm->alpha = a[0];
+    }
+    return EMPOSE_OK;
+}
+
+// MLP of empose/nn/layers.py:46-77 with the reference's state-dict key layout
+inline int pack_mlp(Arena& arena, const TensorTable& tt, const std::string& prefix, int n_in, int n_out, int hidden, int blocks,
+             bool bn, bool round, MlpPacked* out) {
+    out->layers.clear();
+    out->layers.resize(2 + 2 * blocks);
+    EMPOSE_TRY(pack_linear(arena, tt, prefix + ".input_to_hidden", bn ? prefix + ".batch_norm" : "", prefix + ".activation_fn",
+                           hidden, n_in, round, &out->layers[0]));
+    const int stride = bn ? 4 : 3;
+    for (int b = 0; b < blocks; ++b)
+        for (int l = 0; l < 2; ++l) {
+            const std::string base = prefix + ".hidden_layers." + std::to_string(b) + ".layers.";
+            EMPOSE_TRY(pack_linear(arena, tt, base + std::to_string(l * stride), bn ? base + std::to_string(l * stride + 1) : "",
+                                   base + std::to_string(l * stride + (bn ? 2 : 1)), hidden, hidden, round,
+                                   &out->layers[1 + 2 * b + l]));
+        }
+    EMPOSE_TRY(pack_linear(arena, tt, prefix + ".hidden_to_output", "", "", n_out, hidden, round, &out->layers.back()));
+    return EMPOSE_OK;
+}
+
+// ---- execution plan -------------------------------------------------------------------------------
+struct JobRange { int begin = 0, count = 0, per_item = 1; };
+
+struct MapKey {
+    const void* ptr; int64_t stride; int k; int64_t rows; int box;
+    bool operator<(const MapKey& o) const {
+        return std::tie(ptr, stride, k, rows, box) < std::tie(o.ptr, o.stride, o.k, o.rows, o.box);
+    }
+};
+
+struct ASrc { const float* ptr = nullptr; int64_t stride = 0; int k = 0; int64_t rows = 0; };
+
+struct JobBook {        // jobs + tensor maps of one plan
+    bool use_tc = false;
+    std::vector<GemmJob> jobs;
+    std::vector<uint8_t> maps;     // kTensorMapBytes each
+    std::map<MapKey, int> map_index;
+    GemmJob* d_jobs = nullptr;
+    void* d_maps = nullptr;
+
+    int get_map(const float* ptr, int64_t stride, int k, int64_t rows, int box, int* out) {
+        *out = -1;
+        if (!use_tc) return EMPOSE_OK;
+        MapKey key{ptr, stride, k, rows, box};
+        auto it = map_index.find(key);
+        if (it != map_index.end()) { *out = it->second; return EMPOSE_OK; }
+        const int idx = (int)(maps.size() / kTensorMapBytes);
+        maps.resize(maps.size() + kTensorMapBytes);
+        EMPOSE_TRY(tc_encode_map(&maps[(size_t)idx * kTensorMapBytes], ptr, stride, k, rows, box));
+        map_index[key] = idx;
+        *out = idx;
+        return EMPOSE_OK;
+    }
+
+    // appends one job per N tile of `W`; `proto` carries the epilogue fields (n_begin/n_count/maps are filled here)
+    int add(const PackedMatrix& W, const ASrc& a0, const ASrc& a1, GemmJob proto, int m_rows, int dep, JobRange* range) {
+        if (range->count == 0) range->begin = (int)jobs.size();
+        for (int t = 0; t < W.n_tiles; ++t) {
+            GemmJob j = proto;
+            j.a_ptr[0] = a0.ptr; j.a_stride[0] = a0.stride; j.a_k[0] = a0.k;
+            j.a_ptr[1] = a1.ptr; j.a_stride[1] = a1.stride; j.a_k[1] = a1.k;
+            EMPOSE_TRY(get_map(a0.ptr, a0.stride, a0.k, a0.rows, kTileM, &j.a_map[0]));
+            j.a_map[1] = -1;
+            if (a1.k > 0) EMPOSE_TRY(get_map(a1.ptr, a1.stride, a1.k, a1.rows, kTileM, &j.a_map[1]));
+            j.w_ptr = W.w; j.w_ld = W.ld; j.w_koff[0] = W.koff[0]; j.w_koff[1] = W.koff[1];
+            EMPOSE_TRY(get_map(W.w, W.ld, (int)W.ld, W.n_pad, W.tile_n, &j.w_map));
+            j.n_begin = t * W.tile_n;
+            j.n_count = W.tile_n;
+            j.m_rows = m_rows;
+            j.dep = dep;
+            j.bias = W.bias;
+            jobs.push_back(j);
+            ++range->count;
+        }
+        return EMPOSE_OK;
+    }
+
+    int finalize(Arena& arena) {
+        EMPOSE_TRY(arena.upload(jobs, &d_jobs));
+        if (use_tc) {
+            void* p;
+            EMPOSE_TRY(arena.alloc(maps.size(), &p));
+            EMPOSE_CUDA_TRY(cudaMemcpy(p, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+            d_maps = p;
+        }
+        return EMPOSE_OK;
+    }
+};
+
+inline GemmJob linear_proto(const PackedMatrix& W, bool round, float* out, int64_t out_stride, int n_valid) {
+    GemmJob j;
+    memset(&j, 0, sizeof(j));
+    j.epi = EPI_LINEAR;
+    j.round_out = round ? 1 : 0;
+    j.has_act = W.has_act;
+    j.prelu_alpha = W.alpha;
+    j.n_valid = n_valid;
+    j.out = out;
+    j.out_stride = out_stride;
+    j.split = 1 << 30;
+    j.frames_per_window = 1;
+    return j;
+}
+
+
+}  // namespace empose

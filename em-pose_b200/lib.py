@@ -21,7 +21,8 @@ _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2
 EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_create', 'empose_ief_destroy',
                     'empose_ief_forward', 'empose_ief_forward_host', 'empose_sensor_project',
                     'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read',
-                    'empose_gemm_selftest', 'empose_gemm_bench')
+                    'empose_gemm_selftest', 'empose_gemm_bench', 'empose_smpl_create', 'empose_smpl_destroy',
+                    'empose_smpl_forward')
 
 
 class EmposeError(RuntimeError):
@@ -82,6 +83,12 @@ def load():
     lib.empose_gemm_selftest.restype = ctypes.c_int
     lib.empose_gemm_selftest.argtypes = [i32, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, i32, i32,
                                          i32, vp]
+    lib.empose_smpl_create.restype = ctypes.c_int
+    lib.empose_smpl_create.argtypes = [ctypes.POINTER(Tensor), i32, i32, i32, ctypes.POINTER(vp)]
+    lib.empose_smpl_destroy.restype = None
+    lib.empose_smpl_destroy.argtypes = [vp]
+    lib.empose_smpl_forward.restype = ctypes.c_int
+    lib.empose_smpl_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.empose_gemm_bench.restype = ctypes.c_int
     lib.empose_gemm_bench.argtypes = [i32, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, i32, i32, i32,
                                       i32, ctypes.POINTER(ctypes.c_float), vp]
@@ -251,6 +258,45 @@ class IefContext(object):
         _check(load().empose_sensor_project(self._handle, _ptr(poses), _ptr(shapes), _ptr(offset_r), _ptr(offset_t), r,
                                             _ptr(pos), _ptr(ori), _ptr(joints), _stream()))
         return pos, ori, joints
+
+
+class SmplContext(object):
+    """Owns one ``empose_smpl*``: the full-mesh SMPL-H constants on one device."""
+
+    def __init__(self, arrays, precision, device_index):
+        table, keep = make_tensor_table(arrays)
+        handle = ctypes.c_void_p()
+        _check(load().empose_smpl_create(table, len(arrays), int(precision), int(device_index), ctypes.byref(handle)))
+        del keep
+        self._handle = handle
+        self.n_verts = int(arrays['smpl.dims'][0])
+        self.device_index = int(device_index)
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            load().empose_smpl_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, poses_body, betas, poses_root=None, trans=None):
+        """(N,63), (N,10), optional (N,3), (N,3) CUDA tensors -> verts (N,V,3), joints (N,52,3)."""
+        import torch
+        if poses_body.device.type != 'cuda':
+            raise EmposeError('inputs must be CUDA tensors (no CPU path)')
+        n = int(poses_body.shape[0])
+        f32 = lambda t: None if t is None else t.to(dtype=torch.float32).contiguous()
+        poses_body, betas, poses_root, trans = f32(poses_body), f32(betas), f32(poses_root), f32(trans)
+        opts = dict(dtype=torch.float32, device=poses_body.device)
+        verts = torch.empty((n, self.n_verts, 3), **opts)
+        joints = torch.empty((n, 52, 3), **opts)
+        _check(load().empose_smpl_forward(self._handle, _ptr(poses_root), _ptr(poses_body), _ptr(betas), _ptr(trans), n,
+                                          _ptr(verts), _ptr(joints), _stream()))
+        return verts, joints
 
 
 def gemm_selftest(a, w, bias, precision=PRECISION_TF32):

@@ -215,3 +215,46 @@ def submodel_from_npz(npz_path, vertex_ids=VERTEX_IDS):
         topo = topology_from_faces(z['f'], vertex_ids)
         return extract_submodel(z['v_template'], z['shapedirs'], z['posedirs'], z['J_regressor'], z['weights'],
                                 z['kintree_table'], topo), topo
+
+
+def extract_fullmodel(v_template, shapedirs, posedirs, j_regressor, weights, kintree_table):
+    """
+    Constants of the FULL 6890-vertex mesh for ``SMPLLayer.forward`` (reference ``smpl.py:81-122``): the same folds as
+    the sub-model (joints through the shape blend shapes, zero-pose hands into their body ancestor) but for every
+    vertex and all 52 joints.  Returns float32 / int32 arrays keyed ``smpl.*``.
+    """
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    v_template = f64(v_template).reshape(-1, 3)
+    n_v = v_template.shape[0]
+    shapedirs = f64(shapedirs)[:, :, :N_BETAS]
+    posedirs = f64(posedirs)
+    if posedirs.ndim == 3:
+        posedirs = posedirs.reshape(n_v * 3, -1).T
+    j_regressor, weights = f64(j_regressor), f64(weights)
+    parents = [int(p) for p in np.asarray(kintree_table)[0]]
+    parents[0] = -1
+    n_j = j_regressor.shape[0]
+    j0 = j_regressor @ v_template                                           # (52,3)
+    jdirs = np.einsum('jv,vck->kjc', j_regressor, shapedirs)                # (10,52,3)
+    ancestor = np.asarray([_first_body_ancestor(parents, j) for j in range(n_j)], dtype=np.int32)
+    w22 = np.zeros((n_v, N_BODY_JOINTS))
+    for j in range(n_j):
+        w22[:, ancestor[j]] += weights[:, j]
+    nnz = w22 != 0.0
+    n_skin = int(nnz.sum(axis=1).max())
+    order = np.argsort(~nnz, axis=1, kind='stable')[:, :n_skin]             # non-zero joints first, ascending
+    skin_joint = order.astype(np.int32)
+    skin_weight = np.take_along_axis(w22, order, axis=1)
+    skin_joint[skin_weight == 0.0] = 0
+    return {
+        'smpl.v_template': v_template.reshape(-1).astype(np.float32),                                   # (V*3,)
+        'smpl.shapedirs': np.ascontiguousarray(shapedirs.reshape(n_v * 3, N_BETAS).T, dtype=np.float32),  # (10, V*3)
+        'smpl.posedirs': np.ascontiguousarray(posedirs[:N_POSE_FEATURES], dtype=np.float32),            # (189, V*3)
+        'smpl.j0': j0.reshape(-1).astype(np.float32),                                                   # (156,)
+        'smpl.jdirs': jdirs.reshape(N_BETAS, n_j * 3).astype(np.float32),                               # (10, 156)
+        'smpl.parents': np.asarray(parents[:N_BODY_JOINTS], dtype=np.int32),
+        'smpl.ancestor': ancestor,                                                                      # (52,)
+        'smpl.skin_joint': skin_joint,
+        'smpl.skin_weight': skin_weight.astype(np.float32),
+        'smpl.dims': np.asarray([n_v, n_j, n_skin], dtype=np.int32),
+    }

@@ -14,6 +14,8 @@
  *                                     chunk.to_gpu(), net(chunk), .cpu())
  *   empose_sensor_project          <- IterativeErrorFeedback.get_estimated_real_markers
  *                                                                                 empose/nn/models.py:471-483
+ *   empose_smpl_create / _forward  <- SMPLLayer.__init__ / forward / fk / _fk     empose/bodymodels/smpl.py:31-165
+ *                                     (the third-party BodyModel call at smpl.py:121)
  *   empose_gemm_selftest           <- (no reference counterpart) checks the tcgen05 GEMM engine
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
@@ -138,6 +140,20 @@ int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shap
 
 /* Number of kernels the last empose_ief_forward* call on this context launched (for bench accounting). */
 int64_t empose_ief_last_launch_count(const empose_ief* ctx);
+
+/* ---- full-mesh SMPL-H layer -------------------------------------------------------------------------------- */
+typedef struct empose_smpl empose_smpl;   /* opaque: full-mesh constants (all vertices, 52 joints) on one device */
+
+/* `tensors`: the "smpl.*" arrays of submodel.extract_fullmodel (host pointers, read during the call only). */
+int empose_smpl_create(const empose_tensor* tensors, int32_t n_tensors, int32_t precision, int32_t device,
+                       empose_smpl** out);
+void empose_smpl_destroy(empose_smpl* ctx);
+
+/* SMPLLayer._fk (smpl.py:81-122) with a zero hand pose: poses_body [N][63], betas [N][10], poses_root [N][3] or NULL
+ * (zeros), trans [N][3] or NULL (zeros) -> verts [N][V][3], joints [N][52][3] (either output may be NULL).
+ * Device pointers; evaluated in slabs internally, so N is unbounded. */
+int empose_smpl_forward(empose_smpl* ctx, const float* poses_root, const float* poses_body, const float* betas,
+                        const float* trans, int32_t N, float* verts, float* joints, void* stream);
 
 /* Optional timing of the tensor-core GEMM executor: while enabled, every executor launch is bracketed by
  * CUDA events on its stream (TF32 mode only).  empose_ief_profile_read waits for them, returns the summed

@@ -88,6 +88,41 @@ def test_sensor_projection_matches_oracle(dev, smpl_npz, oracle_smpl, topology, 
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# full-mesh SMPLLayer.forward (BASELINE config 1)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', PRECISIONS, ids=PNAME.get)
+def test_smpl_layer_full_mesh(dev, smpl_npz, oracle_smpl, precision):
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from oracle import smplh_lbs
+    layer = SMPLLayer(smpl_npz).to(device=dev, dtype=torch.float32)
+    layer.precision = precision
+    # known answer: zero pose and shape -> template mesh and regressed rest joints
+    v0, j0 = layer(torch.zeros(1, 63, device=dev), torch.zeros(10, device=dev))
+    np.testing.assert_allclose(v0[0].cpu().numpy(), oracle_smpl.v_template.numpy(), atol=2e-6, rtol=0)
+    np.testing.assert_allclose(j0[0].cpu().numpy(), (oracle_smpl.j_regressor @ oracle_smpl.v_template).numpy(), atol=2e-6, rtol=0)
+    # golden vectors from the reference's own SMPLLayer (tests/golden/smpl_sensors.npz)
+    gold = util.load_golden('smpl_sensors')
+    poses = torch.from_numpy(gold['poses']).reshape(-1, 66).to(dev)
+    verts, joints = layer(poses_body=poses[:, 3:], betas=torch.from_numpy(gold['shapes']).to(dev), poses_root=poses[:, :3])
+    assert verts.shape == (2, 6890, 3) and joints.shape == (2, 52, 3)
+    assert util.max_joint_pos_err_mm(verts.cpu().numpy(), gold['verts']) < 0.01
+    assert util.max_joint_pos_err_mm(joints.cpu().numpy(), gold['joints']) < 0.005
+    # random poses with translation, more frames than one slab
+    n = 2500
+    g = torch.Generator().manual_seed(5)
+    pb, pr = 0.2 * torch.randn(n, 63, generator=g), 0.2 * torch.randn(n, 3, generator=g)
+    be, tr = torch.randn(n, 10, generator=g), torch.randn(n, 3, generator=g)
+    verts, joints = layer(pb.to(dev), be.to(dev), poses_root=pr.to(dev), trans=tr.to(dev), window_size=1000)
+    sel = [0, 1, 2047, 2048, 2499]
+    hands = torch.zeros(len(sel), 90, dtype=torch.float64)
+    ov, oj = smplh_lbs.lbs(oracle_smpl, torch.cat([pr[sel].double(), pb[sel].double(), hands], dim=1), be[sel].double(), tr[sel].double())
+    util.report('smpl_full', precision=PNAME[precision], verts_mm=util.max_joint_pos_err_mm(verts[sel].cpu().numpy(), ov.numpy()),
+                joints_mm=util.max_joint_pos_err_mm(joints[sel].cpu().numpy(), oj.numpy()))
+    assert util.max_joint_pos_err_mm(verts[sel].cpu().numpy(), ov.numpy()) < 0.01
+    assert util.max_joint_pos_err_mm(joints[sel].cpu().numpy(), oj.numpy()) < 0.005
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # the whole loop vs golden outputs of the unmodified reference
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('precision', PRECISIONS, ids=PNAME.get)
