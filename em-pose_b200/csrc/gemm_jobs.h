@@ -30,6 +30,8 @@ struct GemmJob {
     int64_t a_stride[2];     // floats between consecutive rows
     int32_t a_k[2];          // real K extent of the segment (0 = unused); padded to kChunkK in W
     int32_t a_map[2];        // tensor-map slot (tcgen05 executor)
+    int32_t a_scratch[2];    // 1: the segment is CTA-local scratch: rows are indexed by 128 * blockIdx.x, not by the tile
+    int32_t out_scratch;     // 1: the output is CTA-local scratch (tcgen05 executor only)
     // ---- W operand: packed [n_total][w_ld], K-major, segment s starts at column w_koff[s] ----
     const float* w_ptr;
     int64_t w_ld;
@@ -124,21 +126,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
 #pragma unroll
         for (int i = 0; i < 32; ++i) stage[lane * kStageLd + i] = v[i];
         __syncwarp();
-        float o[32];
-#pragma unroll
-        for (int r = 0; r < 32; ++r) o[r] = stage[r * kStageLd + lane];
         const int n = n0 + lane;
         const bool col_ok = (c0 + lane < j.n_count) && (n < j.n_valid);
         float* dst;
-        int64_t stride;
-        if (n < j.split) { dst = j.out + j.out_col0 + n; stride = j.out_stride; }
-        else { dst = j.out2 + (n - j.split); stride = j.out2_stride; }
+        int stride;
+        if (n < j.split) { dst = j.out + j.out_col0 + n; stride = (int)j.out_stride; }
+        else { dst = j.out2 + (n - j.split); stride = (int)j.out2_stride; }
         dst += (int64_t)row0 * stride;
-        const int rows = j.m_rows - row0;
-        if (col_ok) {
+        const int rows = col_ok ? min(32, j.m_rows - row0) : 0;
 #pragma unroll
-            for (int r = 0; r < 32; ++r)
-                if (r < rows) dst[(int64_t)r * stride] = o[r];
+        for (int r0 = 0; r0 < 32; r0 += 8) {          // batches of 8: loads first, then stores, few live registers
+            float o[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] = stage[(r0 + r) * kStageLd + lane];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r0 + r < rows) dst[(r0 + r) * stride] = o[r];
         }
         __syncwarp();
     } else {  // EPI_LSTM: 8 hidden units x 4 gates per chunk

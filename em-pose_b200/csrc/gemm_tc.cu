@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                 mbar_arrive(&ctl->full[stage]);
                             } else {
                                 mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
-                                tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * kChunkK, m0);
+                                tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * kChunkK,
+                                            job.a_scratch[seg] ? (int)blockIdx.x * kTileM : m0);
                                 tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * kChunkK,
                                             job.n_begin);
                             }
@@ -263,11 +264,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
             const int m0 = (item / groups) * kTileM;
             const int first = job_begin + (item % groups) * jobs_per_item;
             for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
-                const GemmJob job = jobs[first + jj];       // by value: keeps the fields in registers
+                const GemmJob& job = jobs[first + jj];      // read-only global data: fields are fetched on demand
                 const uint32_t buf = seq & 1u;
                 mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 tcgen05_fence_after();
-                const int row0 = m0 + quad * 32;
+                // activations chained inside this CTA live in CTA-local scratch rows: they are re-read from L2 by the next
+                // layer and overwritten by the next tile before they would be written back to HBM
+                const int row0 = (job.out_scratch ? (int)blockIdx.x * kTileM : m0) + quad * 32;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kMaxTileN;
                 const int c_end = min(job.n_count, (half + 1) * (kMaxTileN / 2));
                 for (int c0 = half * (kMaxTileN / 2); c0 < c_end; c0 += 32) {

@@ -47,6 +47,7 @@ struct Plan {
     float *off_r = nullptr, *off_t = nullptr;
     int32_t* seq_len = nullptr;
     float* act[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pose|shape][ping-pong]
+    int64_t act_rows = 0;
     std::vector<float*> hseq, cstate, hinit;
     // staging for the host-buffer entry point
     float *in_pos = nullptr, *in_ori = nullptr, *in_masks = nullptr, *io_state = nullptr;
@@ -136,9 +137,11 @@ int build_mlp_pair(empose_ief* ctx, Plan& pl, const MlpPacked& mp, const MlpPack
         for (int c = 0; c < 2; ++c) {
             const PackedMatrix& W = nets[c]->layers[l];
             ASrc a0, none;
+            const bool scratch = ctx->round;
             if (l == 0) a0 = ASrc{X, x_stride, x_k, R};
-            else a0 = ASrc{pl.act[c][(l - 1) & 1], hidden, hidden, R};
+            else a0 = ASrc{pl.act[c][(l - 1) & 1], hidden, hidden, pl.act_rows};
             GemmJob proto;
+            int m_rows = R;
             if (l == nl - 1) {
                 proto = linear_proto(W, false, finals[c], final_n[c], final_n[c]);
             } else {
@@ -147,8 +150,10 @@ int build_mlp_pair(empose_ief* ctx, Plan& pl, const MlpPacked& mp, const MlpPack
                     proto.res = pl.act[c][l & 1];                            // block input lives in the buffer being overwritten
                     proto.res_stride = hidden;
                 }
+                if (scratch) { proto.out_scratch = 1; m_rows = (int)pl.act_rows; }
             }
-            EMPOSE_TRY(pl.book.add(W, a0, none, proto, R, last_job[c], range));
+            if (scratch && l > 0) proto.a_scratch[0] = 1;
+            EMPOSE_TRY(pl.book.add(W, a0, none, proto, m_rows, last_job[c], range));
             last_job[c] = range->count - 1;
         }
     range->per_item = range->count;
@@ -188,8 +193,11 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
     EMPOSE_TRY(A.alloc_n((size_t)B * 108, &pl.off_r));
     EMPOSE_TRY(A.alloc_n((size_t)B * 36, &pl.off_t));
     EMPOSE_TRY(A.alloc_n((size_t)B, &pl.seq_len));
+    // Hidden activations of the MLP chains: in TF32 mode a CTA chains all layers of a 128-row tile, so the buffers
+    // are CTA-local scratch (num_sms tiles, L2-resident); the FFMA executor runs layer by layer over all rows.
+    pl.act_rows = ctx->round ? (int64_t)ctx->num_sms * kTileM : (int64_t)R;
     for (int c = 0; c < 2; ++c)
-        for (int q = 0; q < 2; ++q) EMPOSE_TRY(A.alloc_n(Rz * hidden, &pl.act[c][q]));
+        for (int q = 0; q < 2; ++q) EMPOSE_TRY(A.alloc_n((size_t)pl.act_rows * hidden, &pl.act[c][q], true));
 
     const int m_rows_R = R;
     if (cfg.rnn_init) {
