@@ -125,13 +125,17 @@ __global__ void __launch_bounds__(256) pose_feature_kernel(const float* __restri
 constexpr int kFramesPerCta = 4;
 constexpr int kMainThreads = 256;
 constexpr int kMainCtasPerSm = 4;
-constexpr int kOneItem = 1 << 30;
+constexpr int kGroup = kMainThreads / kFramesPerCta;     // threads per frame in the frame-grouped mapping
 
 // flattened (frame, item) loop over threads [t0, t0 + nt) of the CTA
 #define EMPOSE_FOR_ITEMS_ON(t0, nt, n_items, f, i)                                                       \
     for (int _idx = (int)threadIdx.x - (t0), _n = (n_items), f = _idx / _n, i = _idx - f * _n;            \
          _idx >= 0 && _idx < nf * _n; _idx += (nt), f = _idx / _n, i = _idx - f * _n)
 #define EMPOSE_FOR_ITEMS(n_items, f, i) EMPOSE_FOR_ITEMS_ON(0, kMainThreads, n_items, f, i)
+// frame-grouped mapping for wide phases whose item count is a runtime value: kMainThreads / kFramesPerCta threads
+// per frame, no integer division per item
+#define EMPOSE_FOR_FRAME_ITEMS(n_items, f, i)                                                   \
+    for (int f = threadIdx.x / kGroup, i = threadIdx.x % kGroup, _n = (n_items); f < nf && i < _n; i += kGroup)
 // items of the serial kinematic chains, on the last warp of the CTA
 #define EMPOSE_FOR_ITEMS_CHAIN(n_items, f, i) EMPOSE_FOR_ITEMS_ON(kMainThreads - 32, 32, n_items, f, i)
 
@@ -149,82 +153,82 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     const bool static_tree = p.static_tree != 0;
     EMPOSE_TICK(0);
 
-    EMPOSE_FOR_ITEMS(kPoseDim + kBetas, f, i) {
+    EMPOSE_FOR_FRAME_ITEMS(kPoseDim + kBetas, f, i) {
         if (i < kPoseDim) st[f].theta[i] = p.theta[(row0 + f) * kPoseDim + i];
         else st[f].beta[i - kPoseDim] = p.beta[(row0 + f) * kBetas + (i - kPoseDim)];
     }
     __syncthreads();
     EMPOSE_TICK(1);
-    EMPOSE_FOR_ITEMS(kJoints, f, i) phase_rodrigues(st[f], i, kOneItem);
-    EMPOSE_FOR_ITEMS(kPoseDim, f, i) phase_rest_joints(m, st[f], i, kOneItem);
+    EMPOSE_FOR_ITEMS(kJoints, f, i) item_rodrigues(st[f], i);
+    EMPOSE_FOR_FRAME_ITEMS(kPoseDim, f, i) item_rest_joints(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(2);
     // The serial kinematic chain runs on the last warp first; all threads (that warp joining late) then do the
     // wide, independent vertex blend, so the chain's latency hides behind it.
     if (threadIdx.x >= kMainThreads - 32) {
-        if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) phase_chain_static(st[f], i, kOneItem); }
-        else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) phase_chain(m, st[f], i, kOneItem); }
+        if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_static(st[f], i); }
+        else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain(m, st[f], i); }
     }
-    EMPOSE_FOR_ITEMS(nv3, f, i) phase_blend_verts(m, st[f], p.vp_off + (row0 + f) * m.vp_dim, i, kOneItem);
+    EMPOSE_FOR_FRAME_ITEMS(nv3, f, i) item_blend_verts(m, st[f], p.vp_off + (row0 + f) * m.vp_dim, i);
     __syncthreads();
     EMPOSE_TICK(3);
-    EMPOSE_FOR_ITEMS(m.n_verts, f, i) phase_skin(m, st[f], i, kOneItem);
+    EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_skin(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(4);
     if (m.max_degree <= kSplitDegree) {
-        EMPOSE_FOR_ITEMS(kSensors * m.max_degree, f, i) phase_sensor_faces(m, st[f], i, kOneItem);
+        EMPOSE_FOR_FRAME_ITEMS(kSensors * m.max_degree, f, i) item_sensor_faces(m, st[f], i);
         __syncthreads();
     EMPOSE_TICK(5);
         EMPOSE_FOR_ITEMS(kSensors, f, i) {
             const int64_t row = row0 + f;
             const int64_t orow = row / p.rows_per_offset;
             const float* meas = p.meas ? p.meas + row * 144 : nullptr;
-            phase_sensor_frames(m, st[f], p.offset_r + orow * 108, p.offset_t + orow * 36, meas, meas ? meas + 36 : nullptr,
-                                p.spec, p.want_grad != 0, i, kOneItem);
+            item_sensor_frames(m, st[f], p.offset_r + orow * 108, p.offset_t + orow * 36, meas, meas ? meas + 36 : nullptr,
+                                p.spec, p.want_grad != 0, i);
         }
         __syncthreads();
     EMPOSE_TICK(6);
-        if (p.want_grad) EMPOSE_FOR_ITEMS(m.n_verts, f, i) phase_sensor_gather(m, st[f], i, kOneItem);
+        if (p.want_grad) EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_sensor_gather(m, st[f], i);
     } else {
         EMPOSE_FOR_ITEMS(kSensors, f, i) {
             const int64_t row = row0 + f;
             const int64_t orow = row / p.rows_per_offset;
             const float* meas = p.meas ? p.meas + row * 144 : nullptr;
-            phase_sensors(m, st[f], p.offset_r + orow * 108, p.offset_t + orow * 36, meas, meas ? meas + 36 : nullptr, p.spec,
-                          p.want_grad != 0, i, kOneItem);
+            item_sensors(m, st[f], p.offset_r + orow * 108, p.offset_t + orow * 36, meas, meas ? meas + 36 : nullptr, p.spec,
+                          p.want_grad != 0, i);
         }
     }
     __syncthreads();
     EMPOSE_TICK(7);
     if (p.sensor_pos) EMPOSE_FOR_ITEMS(36, f, i) p.sensor_pos[(row0 + f) * 36 + i] = st[f].sensor_pos[i / 3][i % 3];
-    if (p.sensor_ori) EMPOSE_FOR_ITEMS(108, f, i) p.sensor_ori[(row0 + f) * 108 + i] = st[f].sensor_ori[i / 9][i % 9];
-    if (p.joints) EMPOSE_FOR_ITEMS(kPoseDim, f, i) p.joints[(row0 + f) * kPoseDim + i] = st[f].gpos[i / 3][i % 3];
+    if (p.sensor_ori) EMPOSE_FOR_FRAME_ITEMS(108, f, i) p.sensor_ori[(row0 + f) * 108 + i] = st[f].sensor_ori[i / 9][i % 9];
+    if (p.joints) EMPOSE_FOR_FRAME_ITEMS(kPoseDim, f, i) p.joints[(row0 + f) * kPoseDim + i] = st[f].gpos[i / 3][i % 3];
     if (!p.want_grad) return;
     __syncthreads();
     EMPOSE_TICK(8);
 
-    EMPOSE_FOR_ITEMS(m.n_vj, f, i) phase_skin_bwd_chunks(m, st[f], i, kOneItem);
+    EMPOSE_FOR_FRAME_ITEMS(m.n_vj, f, i) item_skin_bwd_chunks(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(9);
-    EMPOSE_FOR_ITEMS(kJoints * 12, f, i) phase_skin_bwd_reduce(m, st[f], i, kOneItem);
-    EMPOSE_FOR_ITEMS(m.n_verts, f, i) phase_skin_bwd_verts(m, st[f], i, kOneItem);
+    EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_skin_bwd_reduce(m, st[f], i);
+    EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_skin_bwd_verts(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(10);
     if (threadIdx.x >= kMainThreads - 32) {
-        if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) phase_chain_bwd_static(st[f], i, kOneItem); }
-        else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) phase_chain_bwd(m, st[f], i, kOneItem); }
+        if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd_static(st[f], i); }
+        else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd(m, st[f], i); }
     }
-    EMPOSE_FOR_ITEMS(m.vp_dim, f, i)
+    EMPOSE_FOR_FRAME_ITEMS(m.vp_dim, f, i)
         p.dvp[(row0 + f) * m.vp_dim + i] = i < nv3 ? maybe_round(st[f].dx[i], p.round_out) : 0.0f;
-    EMPOSE_FOR_ITEMS(3 * kBetas, f, i) phase_shape_bwd_partial(m, st[f], i, kOneItem);
+    EMPOSE_FOR_ITEMS(3 * kBetas, f, i) item_shape_bwd_partial(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(11);
-    EMPOSE_FOR_ITEMS(kJoints * 12, f, i) phase_chain_bwd_local(m, st[f], i, kOneItem);
+    EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_chain_bwd_local(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(12);
     EMPOSE_FOR_ITEMS(kJoints, f, i)
-        phase_finish_theta(st[f], p.coef[row0 + f], (const float*)nullptr, p.gtheta_part + (row0 + f) * kPoseDim, i, kOneItem);
-    EMPOSE_FOR_ITEMS(kBetas, f, i) phase_finish_beta(m, st[f], p.coef[row0 + f], p.gbeta + (row0 + f) * kBetas, i, kOneItem);
+        item_finish_theta(st[f], p.coef[row0 + f], (const float*)nullptr, p.gtheta_part + (row0 + f) * kPoseDim, i);
+    EMPOSE_FOR_ITEMS(kBetas, f, i) item_finish_beta(m, st[f], p.coef[row0 + f], p.gbeta + (row0 + f) * kBetas, i);
     EMPOSE_TICK(13);
 }
 

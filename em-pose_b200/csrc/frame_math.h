@@ -206,51 +206,60 @@ template <typename T> EMPOSE_HD void rodrigues_bwd(const T* r, const T* dR, T* d
 
 // F1a: joint rotations (22 items).
 template <typename T, int VP>
+EMPOSE_HD void item_rodrigues(FrameState<T, VP>& st, int j) {
+    rodrigues_fwd(&st.theta[j * 3], st.rot[j]);
+}
+template <typename T, int VP>
 EMPOSE_HD void phase_rodrigues(FrameState<T, VP>& st, int lane, int lanes) {
-    for (int j = lane; j < kJoints; j += lanes) rodrigues_fwd(&st.theta[j * 3], st.rot[j]);
+    for (int j = lane; j < kJoints; j += lanes) item_rodrigues(st, j);
 }
 // F1b: rest joints J(beta) (66 items).
 template <typename T, int VP>
+EMPOSE_HD void item_rest_joints(const SubModel& m, FrameState<T, VP>& st, int i) {
+    T acc = T(m.j0[i]);
+    for (int k = 0; k < kBetas; ++k) acc += T(m.jdirs[k * kPoseDim + i]) * st.beta[k];
+    st.jrest[i / 3][i % 3] = acc;
+}
+template <typename T, int VP>
 EMPOSE_HD void phase_rest_joints(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int i = lane; i < kPoseDim; i += lanes) {
-        T acc = T(m.j0[i]);
-        for (int k = 0; k < kBetas; ++k) acc += T(m.jdirs[k * kPoseDim + i]) * st.beta[k];
-        st.jrest[i / 3][i % 3] = acc;
-    }
+    for (int i = lane; i < kPoseDim; i += lanes) item_rest_joints(m, st, i);
 }
 // F1c: blended rest vertices (3 * n_verts items).  vp_off may be null (treated as zero).
 template <typename T, int VP, typename TIn>
+EMPOSE_HD void item_blend_verts(const SubModel& m, FrameState<T, VP>& st, const TIn* vp_off, int i) {
+    T acc = T(m.v_template[i]);
+    for (int k = 0; k < kBetas; ++k) acc += T(m.shapedirs[k * m.vp_dim + i]) * st.beta[k];
+    if (vp_off) acc += T(vp_off[i]);
+    st.vp[i] = acc;
+}
+template <typename T, int VP, typename TIn>
 EMPOSE_HD void phase_blend_verts(const SubModel& m, FrameState<T, VP>& st, const TIn* vp_off, int lane, int lanes) {
-    const int nv3 = m.n_verts * 3;
-    for (int i = lane; i < nv3; i += lanes) {
-        T acc = T(m.v_template[i]);
-        for (int k = 0; k < kBetas; ++k) acc += T(m.shapedirs[k * m.vp_dim + i]) * st.beta[k];
-        if (vp_off) acc += T(vp_off[i]);
-        st.vp[i] = acc;
-    }
+    for (int i = lane; i < m.n_verts * 3; i += lanes) item_blend_verts(m, st, vp_off, i);
 }
 
 // F2: kinematic chain.  Row r of every world rotation depends only on row r of its ancestors, so
 // three lanes walk the whole tree independently (no synchronisation inside the chain).
 template <typename T, int VP>
-EMPOSE_HD void phase_chain(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int r = lane; r < 3; r += lanes) {
-        for (int c = 0; c < 3; ++c) st.grot[0][r * 3 + c] = st.rot[0][r * 3 + c];
-        st.gpos[0][r] = st.jrest[0][r];
-        for (int j = 1; j < kJoints; ++j) {
-            const int p = m.parents[j];
-            const T g0 = st.grot[p][r * 3], g1 = st.grot[p][r * 3 + 1], g2 = st.grot[p][r * 3 + 2];
-            const T* R = st.rot[j];
-            st.grot[j][r * 3 + 0] = g0 * R[0] + g1 * R[3] + g2 * R[6];
-            st.grot[j][r * 3 + 1] = g0 * R[1] + g1 * R[4] + g2 * R[7];
-            st.grot[j][r * 3 + 2] = g0 * R[2] + g1 * R[5] + g2 * R[8];
-            st.gpos[j][r] = g0 * (st.jrest[j][0] - st.jrest[p][0]) + g1 * (st.jrest[j][1] - st.jrest[p][1]) +
-                            g2 * (st.jrest[j][2] - st.jrest[p][2]) + st.gpos[p][r];
-        }
-        for (int j = 0; j < kJoints; ++j)
-            st.atr[j][r] = st.gpos[j][r] - (st.grot[j][r * 3] * st.jrest[j][0] + st.grot[j][r * 3 + 1] * st.jrest[j][1] +
-                                            st.grot[j][r * 3 + 2] * st.jrest[j][2]);
+EMPOSE_HD void item_chain(const SubModel& m, FrameState<T, VP>& st, int r) {
+    for (int c = 0; c < 3; ++c) st.grot[0][r * 3 + c] = st.rot[0][r * 3 + c];
+    st.gpos[0][r] = st.jrest[0][r];
+    for (int j = 1; j < kJoints; ++j) {
+        const int p = m.parents[j];
+        const T g0 = st.grot[p][r * 3], g1 = st.grot[p][r * 3 + 1], g2 = st.grot[p][r * 3 + 2];
+        const T* R = st.rot[j];
+        st.grot[j][r * 3 + 0] = g0 * R[0] + g1 * R[3] + g2 * R[6];
+        st.grot[j][r * 3 + 1] = g0 * R[1] + g1 * R[4] + g2 * R[7];
+        st.grot[j][r * 3 + 2] = g0 * R[2] + g1 * R[5] + g2 * R[8];
+        st.gpos[j][r] = g0 * (st.jrest[j][0] - st.jrest[p][0]) + g1 * (st.jrest[j][1] - st.jrest[p][1]) +
+                        g2 * (st.jrest[j][2] - st.jrest[p][2]) + st.gpos[p][r];
     }
+    for (int j = 0; j < kJoints; ++j)
+        st.atr[j][r] = st.gpos[j][r] - (st.grot[j][r * 3] * st.jrest[j][0] + st.grot[j][r * 3 + 1] * st.jrest[j][1] +
+                                        st.grot[j][r * 3 + 2] * st.jrest[j][2]);
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_chain(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int r = lane; r < 3; r += lanes) item_chain(m, st, r);
 }
 
 // The SMPL body tree (reference configuration.py:118) as a compile-time function, so the chain can be fully
@@ -262,49 +271,53 @@ EMPOSE_HD constexpr int smpl_parent(int j) {
 // F2': phase_chain specialised for the standard SMPL tree (same arithmetic, same order of operations).  Results
 // are stored as soon as they exist so that only the transforms of pending parents stay live in registers.
 template <typename T, int VP>
-EMPOSE_HD void phase_chain_static(FrameState<T, VP>& st, int lane, int lanes) {
-    for (int r = lane; r < 3; r += lanes) {
-        T g[kJoints][3], t[kJoints];
+EMPOSE_HD void item_chain_static(FrameState<T, VP>& st, int r) {
+    T g[kJoints][3], t[kJoints];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < kJoints; ++j) {
-            if (j == 0) {
-                g[0][0] = st.rot[0][r * 3]; g[0][1] = st.rot[0][r * 3 + 1]; g[0][2] = st.rot[0][r * 3 + 2];
-                t[0] = st.jrest[0][r];
-            } else {
-                const int p = smpl_parent(j);
-                const T* R = st.rot[j];
-                g[j][0] = g[p][0] * R[0] + g[p][1] * R[3] + g[p][2] * R[6];
-                g[j][1] = g[p][0] * R[1] + g[p][1] * R[4] + g[p][2] * R[7];
-                g[j][2] = g[p][0] * R[2] + g[p][1] * R[5] + g[p][2] * R[8];
-                t[j] = g[p][0] * (st.jrest[j][0] - st.jrest[p][0]) + g[p][1] * (st.jrest[j][1] - st.jrest[p][1]) +
-                       g[p][2] * (st.jrest[j][2] - st.jrest[p][2]) + t[p];
-            }
-            st.grot[j][r * 3] = g[j][0]; st.grot[j][r * 3 + 1] = g[j][1]; st.grot[j][r * 3 + 2] = g[j][2];
-            st.gpos[j][r] = t[j];
-            st.atr[j][r] = t[j] - (g[j][0] * st.jrest[j][0] + g[j][1] * st.jrest[j][1] + g[j][2] * st.jrest[j][2]);
+    for (int j = 0; j < kJoints; ++j) {
+        if (j == 0) {
+            g[0][0] = st.rot[0][r * 3]; g[0][1] = st.rot[0][r * 3 + 1]; g[0][2] = st.rot[0][r * 3 + 2];
+            t[0] = st.jrest[0][r];
+        } else {
+            const int p = smpl_parent(j);
+            const T* R = st.rot[j];
+            g[j][0] = g[p][0] * R[0] + g[p][1] * R[3] + g[p][2] * R[6];
+            g[j][1] = g[p][0] * R[1] + g[p][1] * R[4] + g[p][2] * R[7];
+            g[j][2] = g[p][0] * R[2] + g[p][1] * R[5] + g[p][2] * R[8];
+            t[j] = g[p][0] * (st.jrest[j][0] - st.jrest[p][0]) + g[p][1] * (st.jrest[j][1] - st.jrest[p][1]) +
+                   g[p][2] * (st.jrest[j][2] - st.jrest[p][2]) + t[p];
         }
+        st.grot[j][r * 3] = g[j][0]; st.grot[j][r * 3 + 1] = g[j][1]; st.grot[j][r * 3 + 2] = g[j][2];
+        st.gpos[j][r] = t[j];
+        st.atr[j][r] = t[j] - (g[j][0] * st.jrest[j][0] + g[j][1] * st.jrest[j][1] + g[j][2] * st.jrest[j][2]);
     }
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_chain_static(FrameState<T, VP>& st, int lane, int lanes) {
+    for (int r = lane; r < 3; r += lanes) item_chain_static(st, r);
 }
 
 // F3: linear blend skinning of the sub-mesh; also clears dx for the reverse pass.
 template <typename T, int VP>
-EMPOSE_HD void phase_skin(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int v = lane; v < m.n_verts; v += lanes) {
-        const T p0 = st.vp[v * 3], p1 = st.vp[v * 3 + 1], p2 = st.vp[v * 3 + 2];
-        T x0 = T(0), x1 = T(0), x2 = T(0);
-        for (int s = 0; s < m.n_skin; ++s) {
-            const T w = T(m.skin_weight[v * m.n_skin + s]);
-            const int j = m.skin_joint[v * m.n_skin + s];
-            const T* A = st.grot[j];
-            x0 += w * (A[0] * p0 + A[1] * p1 + A[2] * p2 + st.atr[j][0]);
-            x1 += w * (A[3] * p0 + A[4] * p1 + A[5] * p2 + st.atr[j][1]);
-            x2 += w * (A[6] * p0 + A[7] * p1 + A[8] * p2 + st.atr[j][2]);
-        }
-        st.x[v * 3] = x0; st.x[v * 3 + 1] = x1; st.x[v * 3 + 2] = x2;
-        st.dx[v * 3] = T(0); st.dx[v * 3 + 1] = T(0); st.dx[v * 3 + 2] = T(0);
+EMPOSE_HD void item_skin(const SubModel& m, FrameState<T, VP>& st, int v) {
+    const T p0 = st.vp[v * 3], p1 = st.vp[v * 3 + 1], p2 = st.vp[v * 3 + 2];
+    T x0 = T(0), x1 = T(0), x2 = T(0);
+    for (int s = 0; s < m.n_skin; ++s) {
+        const T w = T(m.skin_weight[v * m.n_skin + s]);
+        const int j = m.skin_joint[v * m.n_skin + s];
+        const T* A = st.grot[j];
+        x0 += w * (A[0] * p0 + A[1] * p1 + A[2] * p2 + st.atr[j][0]);
+        x1 += w * (A[3] * p0 + A[4] * p1 + A[5] * p2 + st.atr[j][1]);
+        x2 += w * (A[6] * p0 + A[7] * p1 + A[8] * p2 + st.atr[j][2]);
     }
+    st.x[v * 3] = x0; st.x[v * 3 + 1] = x1; st.x[v * 3 + 2] = x2;
+    st.dx[v * 3] = T(0); st.dx[v * 3 + 1] = T(0); st.dx[v * 3 + 2] = T(0);
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_skin(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int v = lane; v < m.n_verts; v += lanes) item_skin(m, st, v);
 }
 
 #if defined(__CUDA_ARCH__)
@@ -319,241 +332,253 @@ template <typename T> inline void scatter_add(T* addr, T val) { *addr += val; }
 //   meas_pos: [12][3] measured positions, meas_ori: [12][9] measured orientations (row-major),
 //   off_r: [12][9], off_t: [12][3].
 template <typename T, int VP, typename TIn>
-EMPOSE_HD void phase_sensors(const SubModel& m, FrameState<T, VP>& st, const TIn* off_r, const TIn* off_t,
+EMPOSE_HD void item_sensors(const SubModel& m, FrameState<T, VP>& st, const TIn* off_r, const TIn* off_t,
                              const TIn* meas_pos, const TIn* meas_ori, const ResidualSpec& spec, bool want_grad,
-                             int lane, int lanes) {
-    for (int s = lane; s < kSensors; s += lanes) {
-        const int vs = m.sensor_vert[s], vh = m.helper_vert[s];
-        const int deg = m.sensor_degree[s];
-        const T* xs = &st.x[vs * 3];
-        // area-weighted normal: mean of un-normalised incident face normals (utils.py:134-140)
-        T n[3] = {T(0), T(0), T(0)};
-        for (int d = 0; d < deg; ++d) {
-            const int* f = &m.faces[m.sensor_faces[s * m.max_degree + d] * 3];
-            const T* a = &st.x[f[0] * 3];
-            const T* b = &st.x[f[1] * 3];
-            const T* c = &st.x[f[2] * 3];
-            T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-            T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
-            T fn[3];
-            cross3(e1, e2, fn);
-            n[0] += fn[0]; n[1] += fn[1]; n[2] += fn[2];
-        }
-        const T inv_deg = T(1) / T(deg);
-        n[0] *= inv_deg; n[1] *= inv_deg; n[2] *= inv_deg;
-        T nh[3], u[3], s0[3], t[3], th[3], sv[3], sh[3];
-        const T n_len = normalize3(n, nh);
-        u[0] = st.x[vh * 3] - xs[0]; u[1] = st.x[vh * 3 + 1] - xs[1]; u[2] = st.x[vh * 3 + 2] - xs[2];
-        const T u_len = normalize3(u, s0);
-        cross3(nh, s0, t);
-        const T t_len = normalize3(t, th);
-        cross3(th, nh, sv);
-        const T s_len = normalize3(sv, sh);
-        // R = [sh | th | nh] as columns, row-major storage
-        T R[9] = {sh[0], th[0], nh[0], sh[1], th[1], nh[1], sh[2], th[2], nh[2]};
-        const TIn* Ro = off_r + s * 9;
-        const TIn* to = off_t + s * 3;
-        T Rc[9], pc[3];
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j)
-                Rc[i * 3 + j] = R[i * 3] * T(Ro[j]) + R[i * 3 + 1] * T(Ro[3 + j]) + R[i * 3 + 2] * T(Ro[6 + j]);
-            pc[i] = xs[i] + R[i * 3] * T(to[0]) + R[i * 3 + 1] * T(to[1]) + R[i * 3 + 2] * T(to[2]);
-        }
-        for (int i = 0; i < 9; ++i) st.sensor_ori[s][i] = Rc[i];
-        for (int i = 0; i < 3; ++i) st.sensor_pos[s][i] = pc[i];
-        if (!want_grad || !spec.sensor_active[s]) continue;
-
-        // ---- reverse ----
-        T dpc[3] = {T(0), T(0), T(0)}, dRc[9];
-        for (int i = 0; i < 9; ++i) dRc[i] = T(0);
-        if (spec.use_pos) {
-            T d[3] = {pc[0] - T(meas_pos[s * 3]), pc[1] - T(meas_pos[s * 3 + 1]), pc[2] - T(meas_pos[s * 3 + 2])};
-            T len = sqrt_t(dot3(d, d));
-            T inv = len > T(0) ? T(1) / len : T(0);   // reference: NaN at exactly zero residual (sqrt backward); we emit 0
-            dpc[0] = d[0] * inv; dpc[1] = d[1] * inv; dpc[2] = d[2] * inv;
-        }
-        if (spec.use_ori) {
-            T d[9], sq = T(0);
-            for (int i = 0; i < 9; ++i) { d[i] = Rc[i] - T(meas_ori[s * 9 + i]); sq += d[i] * d[i]; }
-            T len = sqrt_t(sq);
-            T inv = len > T(0) ? T(1) / len : T(0);
-            for (int i = 0; i < 9; ++i) dRc[i] = d[i] * inv;
-        }
-        // offsets: Rc = R Ro, pc = xs + R to
-        T dR[9];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j)
-                dR[i * 3 + j] = dRc[i * 3] * T(Ro[j * 3]) + dRc[i * 3 + 1] * T(Ro[j * 3 + 1]) + dRc[i * 3 + 2] * T(Ro[j * 3 + 2]) +
-                                dpc[i] * T(to[j]);
-        T dsh[3] = {dR[0], dR[3], dR[6]}, dth[3] = {dR[1], dR[4], dR[7]}, dnh[3] = {dR[2], dR[5], dR[8]};
-        // sh = sv/|sv|, sv = th x nh
-        T dsv[3], tmp[3];
-        normalize3_bwd(sh, s_len, dsh, dsv);
-        cross3(nh, dsv, tmp); dth[0] += tmp[0]; dth[1] += tmp[1]; dth[2] += tmp[2];      // d th += nh x dsv
-        cross3(dsv, th, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];      // d nh += dsv x th
-        // th = t/|t|, t = nh x s0
-        T dt[3], ds0[3];
-        normalize3_bwd(th, t_len, dth, dt);
-        cross3(s0, dt, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];       // d nh += s0 x dt
-        cross3(dt, nh, ds0);                                                             // d s0  = dt x nh
-        // s0 = u/|u|
-        T du[3];
-        normalize3_bwd(s0, u_len, ds0, du);
-        // nh = n/|n|, n = mean of face normals
-        T dn[3];
-        normalize3_bwd(nh, n_len, dnh, dn);
-        dn[0] *= inv_deg; dn[1] *= inv_deg; dn[2] *= inv_deg;
-        for (int i = 0; i < 3; ++i) {
-            scatter_add(&st.dx[vh * 3 + i], du[i]);
-            scatter_add(&st.dx[vs * 3 + i], dpc[i] - du[i]);
-        }
-        for (int d = 0; d < deg; ++d) {
-            const int* f = &m.faces[m.sensor_faces[s * m.max_degree + d] * 3];
-            const T* a = &st.x[f[0] * 3];
-            const T* b = &st.x[f[1] * 3];
-            const T* c = &st.x[f[2] * 3];
-            T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-            T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
-            T de1[3], de2[3];
-            cross3(e2, dn, de1);      // fn = e1 x e2: de1 = e2 x dfn, de2 = dfn x e1
-            cross3(dn, e1, de2);
-            for (int i = 0; i < 3; ++i) {
-                scatter_add(&st.dx[f[1] * 3 + i], de1[i]);
-                scatter_add(&st.dx[f[2] * 3 + i], de2[i]);
-                scatter_add(&st.dx[f[0] * 3 + i], -(de1[i] + de2[i]));
-            }
-        }
-    }
-}
-
-// F4 split in three so that the face work runs over (sensor, face) items instead of inside 12 long serial lanes
-// (used when max_degree <= kSplitDegree; same arithmetic as phase_sensors).
-// F4a: un-normalised face normals (12 * max_degree items).
-template <typename T, int VP>
-EMPOSE_HD void phase_sensor_faces(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int it = lane; it < kSensors * m.max_degree; it += lanes) {
-        const int s = it / m.max_degree, d = it % m.max_degree;
-        if (d >= m.sensor_degree[s]) continue;
+                             int s) {
+    const int vs = m.sensor_vert[s], vh = m.helper_vert[s];
+    const int deg = m.sensor_degree[s];
+    const T* xs = &st.x[vs * 3];
+    // area-weighted normal: mean of un-normalised incident face normals (utils.py:134-140)
+    T n[3] = {T(0), T(0), T(0)};
+    for (int d = 0; d < deg; ++d) {
         const int* f = &m.faces[m.sensor_faces[s * m.max_degree + d] * 3];
         const T* a = &st.x[f[0] * 3];
         const T* b = &st.x[f[1] * 3];
         const T* c = &st.x[f[2] * 3];
         T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
         T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
-        cross3(e1, e2, st.fn[s][d]);
+        T fn[3];
+        cross3(e1, e2, fn);
+        n[0] += fn[0]; n[1] += fn[1]; n[2] += fn[2];
     }
+    const T inv_deg = T(1) / T(deg);
+    n[0] *= inv_deg; n[1] *= inv_deg; n[2] *= inv_deg;
+    T nh[3], u[3], s0[3], t[3], th[3], sv[3], sh[3];
+    const T n_len = normalize3(n, nh);
+    u[0] = st.x[vh * 3] - xs[0]; u[1] = st.x[vh * 3 + 1] - xs[1]; u[2] = st.x[vh * 3 + 2] - xs[2];
+    const T u_len = normalize3(u, s0);
+    cross3(nh, s0, t);
+    const T t_len = normalize3(t, th);
+    cross3(th, nh, sv);
+    const T s_len = normalize3(sv, sh);
+    // R = [sh | th | nh] as columns, row-major storage
+    T R[9] = {sh[0], th[0], nh[0], sh[1], th[1], nh[1], sh[2], th[2], nh[2]};
+    const TIn* Ro = off_r + s * 9;
+    const TIn* to = off_t + s * 3;
+    T Rc[9], pc[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            Rc[i * 3 + j] = R[i * 3] * T(Ro[j]) + R[i * 3 + 1] * T(Ro[3 + j]) + R[i * 3 + 2] * T(Ro[6 + j]);
+        pc[i] = xs[i] + R[i * 3] * T(to[0]) + R[i * 3 + 1] * T(to[1]) + R[i * 3 + 2] * T(to[2]);
+    }
+    for (int i = 0; i < 9; ++i) st.sensor_ori[s][i] = Rc[i];
+    for (int i = 0; i < 3; ++i) st.sensor_pos[s][i] = pc[i];
+    if (!want_grad || !spec.sensor_active[s]) return;
+
+    // ---- reverse ----
+    T dpc[3] = {T(0), T(0), T(0)}, dRc[9];
+    for (int i = 0; i < 9; ++i) dRc[i] = T(0);
+    if (spec.use_pos) {
+        T d[3] = {pc[0] - T(meas_pos[s * 3]), pc[1] - T(meas_pos[s * 3 + 1]), pc[2] - T(meas_pos[s * 3 + 2])};
+        T len = sqrt_t(dot3(d, d));
+        T inv = len > T(0) ? T(1) / len : T(0);   // reference: NaN at exactly zero residual (sqrt backward); we emit 0
+        dpc[0] = d[0] * inv; dpc[1] = d[1] * inv; dpc[2] = d[2] * inv;
+    }
+    if (spec.use_ori) {
+        T d[9], sq = T(0);
+        for (int i = 0; i < 9; ++i) { d[i] = Rc[i] - T(meas_ori[s * 9 + i]); sq += d[i] * d[i]; }
+        T len = sqrt_t(sq);
+        T inv = len > T(0) ? T(1) / len : T(0);
+        for (int i = 0; i < 9; ++i) dRc[i] = d[i] * inv;
+    }
+    // offsets: Rc = R Ro, pc = xs + R to
+    T dR[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            dR[i * 3 + j] = dRc[i * 3] * T(Ro[j * 3]) + dRc[i * 3 + 1] * T(Ro[j * 3 + 1]) + dRc[i * 3 + 2] * T(Ro[j * 3 + 2]) +
+                            dpc[i] * T(to[j]);
+    T dsh[3] = {dR[0], dR[3], dR[6]}, dth[3] = {dR[1], dR[4], dR[7]}, dnh[3] = {dR[2], dR[5], dR[8]};
+    // sh = sv/|sv|, sv = th x nh
+    T dsv[3], tmp[3];
+    normalize3_bwd(sh, s_len, dsh, dsv);
+    cross3(nh, dsv, tmp); dth[0] += tmp[0]; dth[1] += tmp[1]; dth[2] += tmp[2];      // d th += nh x dsv
+    cross3(dsv, th, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];      // d nh += dsv x th
+    // th = t/|t|, t = nh x s0
+    T dt[3], ds0[3];
+    normalize3_bwd(th, t_len, dth, dt);
+    cross3(s0, dt, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];       // d nh += s0 x dt
+    cross3(dt, nh, ds0);                                                             // d s0  = dt x nh
+    // s0 = u/|u|
+    T du[3];
+    normalize3_bwd(s0, u_len, ds0, du);
+    // nh = n/|n|, n = mean of face normals
+    T dn[3];
+    normalize3_bwd(nh, n_len, dnh, dn);
+    dn[0] *= inv_deg; dn[1] *= inv_deg; dn[2] *= inv_deg;
+    for (int i = 0; i < 3; ++i) {
+        scatter_add(&st.dx[vh * 3 + i], du[i]);
+        scatter_add(&st.dx[vs * 3 + i], dpc[i] - du[i]);
+    }
+    for (int d = 0; d < deg; ++d) {
+        const int* f = &m.faces[m.sensor_faces[s * m.max_degree + d] * 3];
+        const T* a = &st.x[f[0] * 3];
+        const T* b = &st.x[f[1] * 3];
+        const T* c = &st.x[f[2] * 3];
+        T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+        T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+        T de1[3], de2[3];
+        cross3(e2, dn, de1);      // fn = e1 x e2: de1 = e2 x dfn, de2 = dfn x e1
+        cross3(dn, e1, de2);
+        for (int i = 0; i < 3; ++i) {
+            scatter_add(&st.dx[f[1] * 3 + i], de1[i]);
+            scatter_add(&st.dx[f[2] * 3 + i], de2[i]);
+            scatter_add(&st.dx[f[0] * 3 + i], -(de1[i] + de2[i]));
+        }
+    }
+}
+template <typename T, int VP, typename TIn>
+EMPOSE_HD void phase_sensors(const SubModel& m, FrameState<T, VP>& st, const TIn* off_r, const TIn* off_t,
+                             const TIn* meas_pos, const TIn* meas_ori, const ResidualSpec& spec, bool want_grad,
+                             int lane, int lanes) {
+    for (int s = lane; s < kSensors; s += lanes) item_sensors(m, st, off_r, off_t, meas_pos, meas_ori, spec, want_grad, s);
+}
+
+// F4 split in three so that the face work runs over (sensor, face) items instead of inside 12 long serial lanes
+// (used when max_degree <= kSplitDegree; same arithmetic as phase_sensors).
+// F4a: un-normalised face normals (12 * max_degree items).
+template <typename T, int VP>
+EMPOSE_HD void item_sensor_faces(const SubModel& m, FrameState<T, VP>& st, int it) {
+    const int s = it / m.max_degree, d = it % m.max_degree;
+    if (d >= m.sensor_degree[s]) return;
+    const int* f = &m.faces[m.sensor_faces[s * m.max_degree + d] * 3];
+    const T* a = &st.x[f[0] * 3];
+    const T* b = &st.x[f[1] * 3];
+    const T* c = &st.x[f[2] * 3];
+    T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    cross3(e1, e2, st.fn[s][d]);
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_sensor_faces(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int it = lane; it < kSensors * m.max_degree; it += lanes) item_sensor_faces(m, st, it);
 }
 
 // F4b: sensor frame, offsets, residual and its reverse up to dE/dn (12 items).  Leaves in st.fn[s][0..2]: dE/dn
 // (already divided by the degree), the helper-vertex term and the sensor-vertex term (zero for unused sensors).
 template <typename T, int VP, typename TIn>
+EMPOSE_HD void item_sensor_frames(const SubModel& m, FrameState<T, VP>& st, const TIn* off_r, const TIn* off_t,
+                                   const TIn* meas_pos, const TIn* meas_ori, const ResidualSpec& spec, bool want_grad,
+                                   int s) {
+    const int vs = m.sensor_vert[s], vh = m.helper_vert[s];
+    const int deg = m.sensor_degree[s];
+    const T* xs = &st.x[vs * 3];
+    T n[3] = {T(0), T(0), T(0)};
+    for (int d = 0; d < deg; ++d) { n[0] += st.fn[s][d][0]; n[1] += st.fn[s][d][1]; n[2] += st.fn[s][d][2]; }
+    const T inv_deg = T(1) / T(deg);
+    n[0] *= inv_deg; n[1] *= inv_deg; n[2] *= inv_deg;
+    T nh[3], u[3], s0[3], t[3], th[3], sv[3], sh[3];
+    const T n_len = normalize3(n, nh);
+    u[0] = st.x[vh * 3] - xs[0]; u[1] = st.x[vh * 3 + 1] - xs[1]; u[2] = st.x[vh * 3 + 2] - xs[2];
+    const T u_len = normalize3(u, s0);
+    cross3(nh, s0, t);
+    const T t_len = normalize3(t, th);
+    cross3(th, nh, sv);
+    const T s_len = normalize3(sv, sh);
+    T R[9] = {sh[0], th[0], nh[0], sh[1], th[1], nh[1], sh[2], th[2], nh[2]};
+    const TIn* Ro = off_r + s * 9;
+    const TIn* to = off_t + s * 3;
+    T Rc[9], pc[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            Rc[i * 3 + j] = R[i * 3] * T(Ro[j]) + R[i * 3 + 1] * T(Ro[3 + j]) + R[i * 3 + 2] * T(Ro[6 + j]);
+        pc[i] = xs[i] + R[i * 3] * T(to[0]) + R[i * 3 + 1] * T(to[1]) + R[i * 3 + 2] * T(to[2]);
+    }
+    for (int i = 0; i < 9; ++i) st.sensor_ori[s][i] = Rc[i];
+    for (int i = 0; i < 3; ++i) st.sensor_pos[s][i] = pc[i];
+    if (!want_grad) return;
+    if (!spec.sensor_active[s]) {
+        for (int q = 0; q < 3; ++q) { st.fn[s][q][0] = T(0); st.fn[s][q][1] = T(0); st.fn[s][q][2] = T(0); }
+        return;
+    }
+    T dpc[3] = {T(0), T(0), T(0)}, dRc[9];
+    for (int i = 0; i < 9; ++i) dRc[i] = T(0);
+    if (spec.use_pos) {
+        T d[3] = {pc[0] - T(meas_pos[s * 3]), pc[1] - T(meas_pos[s * 3 + 1]), pc[2] - T(meas_pos[s * 3 + 2])};
+        T len = sqrt_t(dot3(d, d));
+        T inv = len > T(0) ? T(1) / len : T(0);
+        dpc[0] = d[0] * inv; dpc[1] = d[1] * inv; dpc[2] = d[2] * inv;
+    }
+    if (spec.use_ori) {
+        T d[9], sq = T(0);
+        for (int i = 0; i < 9; ++i) { d[i] = Rc[i] - T(meas_ori[s * 9 + i]); sq += d[i] * d[i]; }
+        T len = sqrt_t(sq);
+        T inv = len > T(0) ? T(1) / len : T(0);
+        for (int i = 0; i < 9; ++i) dRc[i] = d[i] * inv;
+    }
+    T dR[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            dR[i * 3 + j] = dRc[i * 3] * T(Ro[j * 3]) + dRc[i * 3 + 1] * T(Ro[j * 3 + 1]) + dRc[i * 3 + 2] * T(Ro[j * 3 + 2]) +
+                            dpc[i] * T(to[j]);
+    T dsh[3] = {dR[0], dR[3], dR[6]}, dth[3] = {dR[1], dR[4], dR[7]}, dnh[3] = {dR[2], dR[5], dR[8]};
+    T dsv[3], tmp[3];
+    normalize3_bwd(sh, s_len, dsh, dsv);
+    cross3(nh, dsv, tmp); dth[0] += tmp[0]; dth[1] += tmp[1]; dth[2] += tmp[2];
+    cross3(dsv, th, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];
+    T dt[3], ds0[3];
+    normalize3_bwd(th, t_len, dth, dt);
+    cross3(s0, dt, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];
+    cross3(dt, nh, ds0);
+    T du[3];
+    normalize3_bwd(s0, u_len, ds0, du);
+    T dn[3];
+    normalize3_bwd(nh, n_len, dnh, dn);
+    for (int i = 0; i < 3; ++i) {
+        st.fn[s][0][i] = dn[i] * inv_deg;
+        st.fn[s][1][i] = du[i];                // goes to the helper vertex
+        st.fn[s][2][i] = dpc[i] - du[i];       // goes to the sensor vertex
+    }
+}
+template <typename T, int VP, typename TIn>
 EMPOSE_HD void phase_sensor_frames(const SubModel& m, FrameState<T, VP>& st, const TIn* off_r, const TIn* off_t,
                                    const TIn* meas_pos, const TIn* meas_ori, const ResidualSpec& spec, bool want_grad,
                                    int lane, int lanes) {
-    for (int s = lane; s < kSensors; s += lanes) {
-        const int vs = m.sensor_vert[s], vh = m.helper_vert[s];
-        const int deg = m.sensor_degree[s];
-        const T* xs = &st.x[vs * 3];
-        T n[3] = {T(0), T(0), T(0)};
-        for (int d = 0; d < deg; ++d) { n[0] += st.fn[s][d][0]; n[1] += st.fn[s][d][1]; n[2] += st.fn[s][d][2]; }
-        const T inv_deg = T(1) / T(deg);
-        n[0] *= inv_deg; n[1] *= inv_deg; n[2] *= inv_deg;
-        T nh[3], u[3], s0[3], t[3], th[3], sv[3], sh[3];
-        const T n_len = normalize3(n, nh);
-        u[0] = st.x[vh * 3] - xs[0]; u[1] = st.x[vh * 3 + 1] - xs[1]; u[2] = st.x[vh * 3 + 2] - xs[2];
-        const T u_len = normalize3(u, s0);
-        cross3(nh, s0, t);
-        const T t_len = normalize3(t, th);
-        cross3(th, nh, sv);
-        const T s_len = normalize3(sv, sh);
-        T R[9] = {sh[0], th[0], nh[0], sh[1], th[1], nh[1], sh[2], th[2], nh[2]};
-        const TIn* Ro = off_r + s * 9;
-        const TIn* to = off_t + s * 3;
-        T Rc[9], pc[3];
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j)
-                Rc[i * 3 + j] = R[i * 3] * T(Ro[j]) + R[i * 3 + 1] * T(Ro[3 + j]) + R[i * 3 + 2] * T(Ro[6 + j]);
-            pc[i] = xs[i] + R[i * 3] * T(to[0]) + R[i * 3 + 1] * T(to[1]) + R[i * 3 + 2] * T(to[2]);
-        }
-        for (int i = 0; i < 9; ++i) st.sensor_ori[s][i] = Rc[i];
-        for (int i = 0; i < 3; ++i) st.sensor_pos[s][i] = pc[i];
-        if (!want_grad) continue;
-        if (!spec.sensor_active[s]) {
-            for (int q = 0; q < 3; ++q) { st.fn[s][q][0] = T(0); st.fn[s][q][1] = T(0); st.fn[s][q][2] = T(0); }
-            continue;
-        }
-        T dpc[3] = {T(0), T(0), T(0)}, dRc[9];
-        for (int i = 0; i < 9; ++i) dRc[i] = T(0);
-        if (spec.use_pos) {
-            T d[3] = {pc[0] - T(meas_pos[s * 3]), pc[1] - T(meas_pos[s * 3 + 1]), pc[2] - T(meas_pos[s * 3 + 2])};
-            T len = sqrt_t(dot3(d, d));
-            T inv = len > T(0) ? T(1) / len : T(0);
-            dpc[0] = d[0] * inv; dpc[1] = d[1] * inv; dpc[2] = d[2] * inv;
-        }
-        if (spec.use_ori) {
-            T d[9], sq = T(0);
-            for (int i = 0; i < 9; ++i) { d[i] = Rc[i] - T(meas_ori[s * 9 + i]); sq += d[i] * d[i]; }
-            T len = sqrt_t(sq);
-            T inv = len > T(0) ? T(1) / len : T(0);
-            for (int i = 0; i < 9; ++i) dRc[i] = d[i] * inv;
-        }
-        T dR[9];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j)
-                dR[i * 3 + j] = dRc[i * 3] * T(Ro[j * 3]) + dRc[i * 3 + 1] * T(Ro[j * 3 + 1]) + dRc[i * 3 + 2] * T(Ro[j * 3 + 2]) +
-                                dpc[i] * T(to[j]);
-        T dsh[3] = {dR[0], dR[3], dR[6]}, dth[3] = {dR[1], dR[4], dR[7]}, dnh[3] = {dR[2], dR[5], dR[8]};
-        T dsv[3], tmp[3];
-        normalize3_bwd(sh, s_len, dsh, dsv);
-        cross3(nh, dsv, tmp); dth[0] += tmp[0]; dth[1] += tmp[1]; dth[2] += tmp[2];
-        cross3(dsv, th, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];
-        T dt[3], ds0[3];
-        normalize3_bwd(th, t_len, dth, dt);
-        cross3(s0, dt, tmp); dnh[0] += tmp[0]; dnh[1] += tmp[1]; dnh[2] += tmp[2];
-        cross3(dt, nh, ds0);
-        T du[3];
-        normalize3_bwd(s0, u_len, ds0, du);
-        T dn[3];
-        normalize3_bwd(nh, n_len, dnh, dn);
-        for (int i = 0; i < 3; ++i) {
-            st.fn[s][0][i] = dn[i] * inv_deg;
-            st.fn[s][1][i] = du[i];                // goes to the helper vertex
-            st.fn[s][2][i] = dpc[i] - du[i];       // goes to the sensor vertex
-        }
-    }
+    for (int s = lane; s < kSensors; s += lanes) item_sensor_frames(m, st, off_r, off_t, meas_pos, meas_ori, spec, want_grad, s);
 }
 
 // F4c: dE/dx by GATHER (n_verts items): every vertex sums, in a fixed order, the contributions of the faces it
 // is a corner of (recomputed from dE/dn of their sensor) and of the sensors it serves as sensor / helper vertex.
 // No atomics: the result is bit-reproducible, which window-sharded inference relies on.
 template <typename T, int VP>
-EMPOSE_HD void phase_sensor_gather(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int v = lane; v < m.n_verts; v += lanes) {
-        T g[3] = {T(0), T(0), T(0)};
-        for (int q = m.vinc_ptr[v]; q < m.vinc_ptr[v + 1]; ++q) {
-            const int item = m.vinc_item[q], code = m.vinc_code[q];
-            const int s = item / m.max_degree;
-            if (code >= 3) {
-                const T* t = st.fn[s][code == 3 ? 2 : 1];
-                g[0] += t[0]; g[1] += t[1]; g[2] += t[2];
-                continue;
-            }
-            const T* dn = st.fn[s][0];
-            const int* f = &m.faces[m.sensor_faces[item] * 3];
-            const T* a = &st.x[f[0] * 3];
-            const T* b = &st.x[f[1] * 3];
-            const T* c = &st.x[f[2] * 3];
-            T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-            T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
-            T de1[3], de2[3];
-            cross3(e2, dn, de1);      // fn = e1 x e2: d e1 = e2 x dfn, d e2 = dfn x e1
-            cross3(dn, e1, de2);
-            if (code == 1) { g[0] += de1[0]; g[1] += de1[1]; g[2] += de1[2]; }
-            else if (code == 2) { g[0] += de2[0]; g[1] += de2[1]; g[2] += de2[2]; }
-            else { g[0] -= de1[0] + de2[0]; g[1] -= de1[1] + de2[1]; g[2] -= de1[2] + de2[2]; }
+EMPOSE_HD void item_sensor_gather(const SubModel& m, FrameState<T, VP>& st, int v) {
+    T g[3] = {T(0), T(0), T(0)};
+    for (int q = m.vinc_ptr[v]; q < m.vinc_ptr[v + 1]; ++q) {
+        const int item = m.vinc_item[q], code = m.vinc_code[q];
+        const int s = item / m.max_degree;
+        if (code >= 3) {
+            const T* t = st.fn[s][code == 3 ? 2 : 1];
+            g[0] += t[0]; g[1] += t[1]; g[2] += t[2];
+            continue;
         }
-        st.dx[v * 3] = g[0]; st.dx[v * 3 + 1] = g[1]; st.dx[v * 3 + 2] = g[2];
+        const T* dn = st.fn[s][0];
+        const int* f = &m.faces[m.sensor_faces[item] * 3];
+        const T* a = &st.x[f[0] * 3];
+        const T* b = &st.x[f[1] * 3];
+        const T* c = &st.x[f[2] * 3];
+        T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+        T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+        T de1[3], de2[3];
+        cross3(e2, dn, de1);      // fn = e1 x e2: d e1 = e2 x dfn, d e2 = dfn x e1
+        cross3(dn, e1, de2);
+        if (code == 1) { g[0] += de1[0]; g[1] += de1[1]; g[2] += de1[2]; }
+        else if (code == 2) { g[0] += de2[0]; g[1] += de2[1]; g[2] += de2[2]; }
+        else { g[0] -= de1[0] + de2[0]; g[1] -= de1[1] + de2[1]; g[2] -= de1[2] + de2[2]; }
     }
+    st.dx[v * 3] = g[0]; st.dx[v * 3 + 1] = g[1]; st.dx[v * 3 + 2] = g[2];
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_sensor_gather(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int v = lane; v < m.n_verts; v += lanes) item_sensor_gather(m, st, v);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -563,124 +588,136 @@ EMPOSE_HD void phase_sensor_gather(const SubModel& m, FrameState<T, VP>& st, int
 // B1a: dE/dA summed over one chunk ("virtual joint") of a joint's vertex list (n_vj items).  Each chunk walks
 // its (bounded) list once and accumulates all 12 entries in registers, so lanes stay balanced.
 template <typename T, int VP>
-EMPOSE_HD void phase_skin_bwd_chunks(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int c = lane; c < m.n_vj; c += lanes) {
-        T acc[12];
-        for (int e = 0; e < 12; ++e) acc[e] = T(0);
-        for (int q = m.vj_ptr[c]; q < m.vj_ptr[c + 1]; ++q) {
-            const int v = m.jt_vert[q];
-            const T w = T(m.jt_weight[q]);
-            const T d0 = w * st.dx[v * 3], d1 = w * st.dx[v * 3 + 1], d2 = w * st.dx[v * 3 + 2];
-            const T p0 = st.vp[v * 3], p1 = st.vp[v * 3 + 1], p2 = st.vp[v * 3 + 2];
-            acc[0] += d0 * p0; acc[1] += d0 * p1; acc[2] += d0 * p2;
-            acc[3] += d1 * p0; acc[4] += d1 * p1; acc[5] += d1 * p2;
-            acc[6] += d2 * p0; acc[7] += d2 * p1; acc[8] += d2 * p2;
-            acc[9] += d0; acc[10] += d1; acc[11] += d2;
-        }
-        for (int e = 0; e < 12; ++e) st.dav[c][e] = acc[e];
+EMPOSE_HD void item_skin_bwd_chunks(const SubModel& m, FrameState<T, VP>& st, int c) {
+    T acc[12];
+    for (int e = 0; e < 12; ++e) acc[e] = T(0);
+    for (int q = m.vj_ptr[c]; q < m.vj_ptr[c + 1]; ++q) {
+        const int v = m.jt_vert[q];
+        const T w = T(m.jt_weight[q]);
+        const T d0 = w * st.dx[v * 3], d1 = w * st.dx[v * 3 + 1], d2 = w * st.dx[v * 3 + 2];
+        const T p0 = st.vp[v * 3], p1 = st.vp[v * 3 + 1], p2 = st.vp[v * 3 + 2];
+        acc[0] += d0 * p0; acc[1] += d0 * p1; acc[2] += d0 * p2;
+        acc[3] += d1 * p0; acc[4] += d1 * p1; acc[5] += d1 * p2;
+        acc[6] += d2 * p0; acc[7] += d2 * p1; acc[8] += d2 * p2;
+        acc[9] += d0; acc[10] += d1; acc[11] += d2;
     }
+    for (int e = 0; e < 12; ++e) st.dav[c][e] = acc[e];
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_skin_bwd_chunks(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int c = lane; c < m.n_vj; c += lanes) item_skin_bwd_chunks(m, st, c);
 }
 // B1b: dE/dA_j = sum of its chunks (22 * 12 items).
 template <typename T, int VP>
+EMPOSE_HD void item_skin_bwd_reduce(const SubModel& m, FrameState<T, VP>& st, int it) {
+    const int j = it / 12, e = it % 12;
+    T acc = T(0);
+    for (int c = m.jvj_ptr[j]; c < m.jvj_ptr[j + 1]; ++c) acc += st.dav[c][e];
+    if (e < 9) st.dar[j][e] = acc;
+    else st.dat[j][e - 9] = acc;
+}
+template <typename T, int VP>
 EMPOSE_HD void phase_skin_bwd_reduce(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int it = lane; it < kJoints * 12; it += lanes) {
-        const int j = it / 12, e = it % 12;
-        T acc = T(0);
-        for (int c = m.jvj_ptr[j]; c < m.jvj_ptr[j + 1]; ++c) acc += st.dav[c][e];
-        if (e < 9) st.dar[j][e] = acc;
-        else st.dat[j][e - 9] = acc;
-    }
+    for (int it = lane; it < kJoints * 12; it += lanes) item_skin_bwd_reduce(m, st, it);
 }
 
 // B2: dE/dvp_v = sum_j w A_j^R^T dE/dx_v, in place over st.dx.  Must run AFTER phase_skin_bwd_chunks.
 template <typename T, int VP>
-EMPOSE_HD void phase_skin_bwd_verts(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int v = lane; v < m.n_verts; v += lanes) {
-        const T d0 = st.dx[v * 3], d1 = st.dx[v * 3 + 1], d2 = st.dx[v * 3 + 2];
-        T g0 = T(0), g1 = T(0), g2 = T(0);
-        for (int s = 0; s < m.n_skin; ++s) {
-            const T w = T(m.skin_weight[v * m.n_skin + s]);
-            const T* A = st.grot[m.skin_joint[v * m.n_skin + s]];
-            g0 += w * (A[0] * d0 + A[3] * d1 + A[6] * d2);
-            g1 += w * (A[1] * d0 + A[4] * d1 + A[7] * d2);
-            g2 += w * (A[2] * d0 + A[5] * d1 + A[8] * d2);
-        }
-        st.dx[v * 3] = g0; st.dx[v * 3 + 1] = g1; st.dx[v * 3 + 2] = g2;
+EMPOSE_HD void item_skin_bwd_verts(const SubModel& m, FrameState<T, VP>& st, int v) {
+    const T d0 = st.dx[v * 3], d1 = st.dx[v * 3 + 1], d2 = st.dx[v * 3 + 2];
+    T g0 = T(0), g1 = T(0), g2 = T(0);
+    for (int s = 0; s < m.n_skin; ++s) {
+        const T w = T(m.skin_weight[v * m.n_skin + s]);
+        const T* A = st.grot[m.skin_joint[v * m.n_skin + s]];
+        g0 += w * (A[0] * d0 + A[3] * d1 + A[6] * d2);
+        g1 += w * (A[1] * d0 + A[4] * d1 + A[7] * d2);
+        g2 += w * (A[2] * d0 + A[5] * d1 + A[8] * d2);
     }
+    st.dx[v * 3] = g0; st.dx[v * 3 + 1] = g1; st.dx[v * 3 + 2] = g2;
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_skin_bwd_verts(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int v = lane; v < m.n_verts; v += lanes) item_skin_bwd_verts(m, st, v);
 }
 
 // B3: partial sums of dE/dbeta through the shape blend shapes (st.dx now holds dE/dvp): 30 items,
 // item (k, p) sums the vertices v = p (mod 3).
 template <typename T, int VP>
+EMPOSE_HD void item_shape_bwd_partial(const SubModel& m, FrameState<T, VP>& st, int it) {
+    const int k = it % kBetas, p = it / kBetas;
+    const float* S = m.shapedirs + k * m.vp_dim;
+    T acc = T(0);
+    for (int v = p; v < m.n_verts; v += 3)
+        acc += T(S[v * 3]) * st.dx[v * 3] + T(S[v * 3 + 1]) * st.dx[v * 3 + 1] + T(S[v * 3 + 2]) * st.dx[v * 3 + 2];
+    st.dbeta_part[p][k] = acc;
+}
+template <typename T, int VP>
 EMPOSE_HD void phase_shape_bwd_partial(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int it = lane; it < 3 * kBetas; it += lanes) {
-        const int k = it % kBetas, p = it / kBetas;
-        const float* S = m.shapedirs + k * m.vp_dim;
-        T acc = T(0);
-        for (int v = p; v < m.n_verts; v += 3)
-            acc += T(S[v * 3]) * st.dx[v * 3] + T(S[v * 3 + 1]) * st.dx[v * 3 + 1] + T(S[v * 3 + 2]) * st.dx[v * 3 + 2];
-        st.dbeta_part[p][k] = acc;
-    }
+    for (int it = lane; it < 3 * kBetas; it += lanes) item_shape_bwd_partial(m, st, it);
 }
 
 // B4: reverse sweep of the kinematic chain, row-parallel like the forward one: lane r owns row r of
 // every dE/dG^R and entry r of every dE/dG^t.  After the sweep both are final for every joint.
 template <typename T, int VP>
-EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int r = lane; r < 3; r += lanes) {
-        for (int j = 0; j < kJoints; ++j) {
-            // A_j^R = G_j^R,  A_j^t = G_j^t - G_j^R J_j
-            const T a = st.dat[j][r];
-            st.dgt[j][r] = a;
-            for (int c = 0; c < 3; ++c) st.dgr[j][r * 3 + c] = st.dar[j][r * 3 + c] - a * st.jrest[j][c];
-        }
-        for (int j = kJoints - 1; j >= 1; --j) {
-            const int p = m.parents[j];
-            const T* R = st.rot[j];
-            const T d0 = st.dgr[j][r * 3], d1 = st.dgr[j][r * 3 + 1], d2 = st.dgr[j][r * 3 + 2];
-            const T dt = st.dgt[j][r];
-            // G_j^R = G_p^R R_j           -> dG_p^R += dG_j^R R_j^T
-            // G_j^t = G_p^R (J_j - J_p) + G_p^t -> dG_p^R += dG_j^t (J_j - J_p)^T,  dG_p^t += dG_j^t
-            st.dgr[p][r * 3 + 0] += d0 * R[0] + d1 * R[1] + d2 * R[2] + dt * (st.jrest[j][0] - st.jrest[p][0]);
-            st.dgr[p][r * 3 + 1] += d0 * R[3] + d1 * R[4] + d2 * R[5] + dt * (st.jrest[j][1] - st.jrest[p][1]);
-            st.dgr[p][r * 3 + 2] += d0 * R[6] + d1 * R[7] + d2 * R[8] + dt * (st.jrest[j][2] - st.jrest[p][2]);
-            st.dgt[p][r] += dt;
-        }
+EMPOSE_HD void item_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int r) {
+    for (int j = 0; j < kJoints; ++j) {
+        // A_j^R = G_j^R,  A_j^t = G_j^t - G_j^R J_j
+        const T a = st.dat[j][r];
+        st.dgt[j][r] = a;
+        for (int c = 0; c < 3; ++c) st.dgr[j][r * 3 + c] = st.dar[j][r * 3 + c] - a * st.jrest[j][c];
     }
+    for (int j = kJoints - 1; j >= 1; --j) {
+        const int p = m.parents[j];
+        const T* R = st.rot[j];
+        const T d0 = st.dgr[j][r * 3], d1 = st.dgr[j][r * 3 + 1], d2 = st.dgr[j][r * 3 + 2];
+        const T dt = st.dgt[j][r];
+        // G_j^R = G_p^R R_j           -> dG_p^R += dG_j^R R_j^T
+        // G_j^t = G_p^R (J_j - J_p) + G_p^t -> dG_p^R += dG_j^t (J_j - J_p)^T,  dG_p^t += dG_j^t
+        st.dgr[p][r * 3 + 0] += d0 * R[0] + d1 * R[1] + d2 * R[2] + dt * (st.jrest[j][0] - st.jrest[p][0]);
+        st.dgr[p][r * 3 + 1] += d0 * R[3] + d1 * R[4] + d2 * R[5] + dt * (st.jrest[j][1] - st.jrest[p][1]);
+        st.dgr[p][r * 3 + 2] += d0 * R[6] + d1 * R[7] + d2 * R[8] + dt * (st.jrest[j][2] - st.jrest[p][2]);
+        st.dgt[p][r] += dt;
+    }
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int r = lane; r < 3; r += lanes) item_chain_bwd(m, st, r);
 }
 
 // B4': phase_chain_bwd specialised for the standard SMPL tree.  Children contributions are accumulated in
 // registers (`acc`, zero until first touched) and each joint is finalised and stored when the sweep reaches it,
 // so only the partial sums of pending parents are live.
 template <typename T, int VP>
-EMPOSE_HD void phase_chain_bwd_static(FrameState<T, VP>& st, int lane, int lanes) {
-    for (int r = lane; r < 3; r += lanes) {
-        T acc[kJoints][3], acct[kJoints];
+EMPOSE_HD void item_chain_bwd_static(FrameState<T, VP>& st, int r) {
+    T acc[kJoints][3], acct[kJoints];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < kJoints; ++j) { acc[j][0] = T(0); acc[j][1] = T(0); acc[j][2] = T(0); acct[j] = T(0); }
+    for (int j = 0; j < kJoints; ++j) { acc[j][0] = T(0); acc[j][1] = T(0); acc[j][2] = T(0); acct[j] = T(0); }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = kJoints - 1; j >= 0; --j) {
-            const T a = st.dat[j][r];
-            const T dt = a + acct[j];
-            const T d0 = st.dar[j][r * 3] - a * st.jrest[j][0] + acc[j][0];
-            const T d1 = st.dar[j][r * 3 + 1] - a * st.jrest[j][1] + acc[j][1];
-            const T d2 = st.dar[j][r * 3 + 2] - a * st.jrest[j][2] + acc[j][2];
-            st.dgr[j][r * 3] = d0; st.dgr[j][r * 3 + 1] = d1; st.dgr[j][r * 3 + 2] = d2;
-            st.dgt[j][r] = dt;
-            if (j > 0) {
-                const int p = smpl_parent(j);
-                const T* R = st.rot[j];
-                acc[p][0] += d0 * R[0] + d1 * R[1] + d2 * R[2] + dt * (st.jrest[j][0] - st.jrest[p][0]);
-                acc[p][1] += d0 * R[3] + d1 * R[4] + d2 * R[5] + dt * (st.jrest[j][1] - st.jrest[p][1]);
-                acc[p][2] += d0 * R[6] + d1 * R[7] + d2 * R[8] + dt * (st.jrest[j][2] - st.jrest[p][2]);
-                acct[p] += dt;
-            }
+    for (int j = kJoints - 1; j >= 0; --j) {
+        const T a = st.dat[j][r];
+        const T dt = a + acct[j];
+        const T d0 = st.dar[j][r * 3] - a * st.jrest[j][0] + acc[j][0];
+        const T d1 = st.dar[j][r * 3 + 1] - a * st.jrest[j][1] + acc[j][1];
+        const T d2 = st.dar[j][r * 3 + 2] - a * st.jrest[j][2] + acc[j][2];
+        st.dgr[j][r * 3] = d0; st.dgr[j][r * 3 + 1] = d1; st.dgr[j][r * 3 + 2] = d2;
+        st.dgt[j][r] = dt;
+        if (j > 0) {
+            const int p = smpl_parent(j);
+            const T* R = st.rot[j];
+            acc[p][0] += d0 * R[0] + d1 * R[1] + d2 * R[2] + dt * (st.jrest[j][0] - st.jrest[p][0]);
+            acc[p][1] += d0 * R[3] + d1 * R[4] + d2 * R[5] + dt * (st.jrest[j][1] - st.jrest[p][1]);
+            acc[p][2] += d0 * R[6] + d1 * R[7] + d2 * R[8] + dt * (st.jrest[j][2] - st.jrest[p][2]);
+            acct[p] += dt;
         }
     }
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_chain_bwd_static(FrameState<T, VP>& st, int lane, int lanes) {
+    for (int r = lane; r < 3; r += lanes) item_chain_bwd_static(st, r);
 }
 
 // B5: local gradients from the final dE/dG.
@@ -689,26 +726,28 @@ EMPOSE_HD void phase_chain_bwd_static(FrameState<T, VP>& st, int lane, int lanes
 // (the second line collects the three places J_j appears: A_j^t, its own bone and its children's bones,
 //  using dE/dG_j^t = dE/dA_j^t + sum over children of dE/dG_child^t).
 template <typename T, int VP>
-EMPOSE_HD void phase_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int i = lane; i < kJoints * 12; i += lanes) {
-        const int j = i / 12, e = i % 12;
-        const int p = m.parents[j];
-        if (e < 9) {
-            const int a = e / 3, b = e % 3;
-            T acc;
-            if (j == 0) acc = st.dgr[0][e];
-            else acc = st.grot[p][a] * st.dgr[j][b] + st.grot[p][3 + a] * st.dgr[j][3 + b] + st.grot[p][6 + a] * st.dgr[j][6 + b];
-            st.drot[j][e] = acc;
-        } else {
-            const int c = e - 9;
-            T acc = T(0);
-            for (int r = 0; r < 3; ++r) {
-                const T gp = (j == 0) ? (r == c ? T(1) : T(0)) : st.grot[p][r * 3 + c];
-                acc += (gp - st.grot[j][r * 3 + c]) * st.dgt[j][r];
-            }
-            st.dj[j][c] = acc;
+EMPOSE_HD void item_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, int i) {
+    const int j = i / 12, e = i % 12;
+    const int p = m.parents[j];
+    if (e < 9) {
+        const int a = e / 3, b = e % 3;
+        T acc;
+        if (j == 0) acc = st.dgr[0][e];
+        else acc = st.grot[p][a] * st.dgr[j][b] + st.grot[p][3 + a] * st.dgr[j][3 + b] + st.grot[p][6 + a] * st.dgr[j][6 + b];
+        st.drot[j][e] = acc;
+    } else {
+        const int c = e - 9;
+        T acc = T(0);
+        for (int r = 0; r < 3; ++r) {
+            const T gp = (j == 0) ? (r == c ? T(1) : T(0)) : st.grot[p][r * 3 + c];
+            acc += (gp - st.grot[j][r * 3 + c]) * st.dgt[j][r];
         }
+        st.dj[j][c] = acc;
     }
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int i = lane; i < kJoints * 12; i += lanes) item_chain_bwd_local(m, st, i);
 }
 
 // B6: finish.  g_theta and the complete g_beta, both scaled by `coef`
@@ -716,22 +755,26 @@ EMPOSE_HD void phase_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, i
 // (dE/d pose-feature, the result of the transposed pose-blend GEMM) may be null: the map is linear in
 // dR, so a caller can add coef * rodrigues_bwd(theta_j, dpf_j) later (the split GPU kernels do that).
 template <typename T, int VP, typename TOut, typename TPf>
+EMPOSE_HD void item_finish_theta(FrameState<T, VP>& st, T coef, const TPf* dpf, TOut* g_theta, int j) {
+    T g[3] = {T(0), T(0), T(0)};
+    if (dpf && j > 0)
+        for (int e = 0; e < 9; ++e) st.drot[j][e] += T(dpf[(j - 1) * 9 + e]);
+    rodrigues_bwd(&st.theta[j * 3], st.drot[j], g);
+    g_theta[j * 3] = TOut(coef * g[0]); g_theta[j * 3 + 1] = TOut(coef * g[1]); g_theta[j * 3 + 2] = TOut(coef * g[2]);
+}
+template <typename T, int VP, typename TOut, typename TPf>
 EMPOSE_HD void phase_finish_theta(FrameState<T, VP>& st, T coef, const TPf* dpf, TOut* g_theta, int lane, int lanes) {
-    for (int j = lane; j < kJoints; j += lanes) {
-        T g[3] = {T(0), T(0), T(0)};
-        if (dpf && j > 0)
-            for (int e = 0; e < 9; ++e) st.drot[j][e] += T(dpf[(j - 1) * 9 + e]);
-        rodrigues_bwd(&st.theta[j * 3], st.drot[j], g);
-        g_theta[j * 3] = TOut(coef * g[0]); g_theta[j * 3 + 1] = TOut(coef * g[1]); g_theta[j * 3 + 2] = TOut(coef * g[2]);
-    }
+    for (int j = lane; j < kJoints; j += lanes) item_finish_theta(st, coef, dpf, g_theta, j);
+}
+template <typename T, int VP, typename TOut>
+EMPOSE_HD void item_finish_beta(const SubModel& m, FrameState<T, VP>& st, T coef, TOut* g_beta, int k) {
+    T acc = st.dbeta_part[0][k] + st.dbeta_part[1][k] + st.dbeta_part[2][k];
+    for (int i = 0; i < kPoseDim; ++i) acc += T(m.jdirs[k * kPoseDim + i]) * st.dj[i / 3][i % 3];
+    g_beta[k] = TOut(coef * acc);
 }
 template <typename T, int VP, typename TOut>
 EMPOSE_HD void phase_finish_beta(const SubModel& m, FrameState<T, VP>& st, T coef, TOut* g_beta, int lane, int lanes) {
-    for (int k = lane; k < kBetas; k += lanes) {
-        T acc = st.dbeta_part[0][k] + st.dbeta_part[1][k] + st.dbeta_part[2][k];
-        for (int i = 0; i < kPoseDim; ++i) acc += T(m.jdirs[k * kPoseDim + i]) * st.dj[i / 3][i % 3];
-        g_beta[k] = TOut(coef * acc);
-    }
+    for (int k = lane; k < kBetas; k += lanes) item_finish_beta(m, st, coef, g_beta, k);
 }
 
 }  // namespace empose

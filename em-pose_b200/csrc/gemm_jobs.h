@@ -152,20 +152,28 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
         const int rows = j.m_rows - row0;
         float* cg = j.c_state + (int64_t)row0 * j.hidden + unit0 + u;
         const float* hg = j.h_prev + (int64_t)row0 * j.h_prev_stride + unit0 + u;
+        const bool live = row < j.m_rows && j.t < j.seq_len[row];
+        // the carried hidden state is only needed for rows whose sequence has ended (packed-sequence semantics)
+        const bool any_frozen = __any_sync(0xffffffffu, row < j.m_rows && !live);
         float cl[8], hl[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {      // coalesced: 4 rows x 8 units per instruction
             const int r = q * 4 + sub;
             cl[q] = r < rows ? cg[(int64_t)r * j.hidden] : 0.0f;
-            hl[q] = r < rows ? hg[(int64_t)r * j.h_prev_stride] : 0.0f;
+        }
+        if (any_frozen) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = q * 4 + sub;
+                hl[q] = r < rows ? hg[(int64_t)r * j.h_prev_stride] : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sh[(q * 4 + sub) * 9 + u] = hl[q];
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            sc[(q * 4 + sub) * 9 + u] = cl[q];
-            sh[(q * 4 + sub) * 9 + u] = hl[q];
-        }
+        for (int q = 0; q < 8; ++q) sc[(q * 4 + sub) * 9 + u] = cl[q];
         __syncwarp();
-        if (row < j.m_rows && j.t < j.seq_len[row]) {
+        if (live) {
             float c_old[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) c_old[k] = sc[lane * 9 + k];
