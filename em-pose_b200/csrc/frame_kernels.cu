@@ -188,7 +188,11 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
         }
         __syncthreads();
     EMPOSE_TICK(6);
-        if (p.want_grad) EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_sensor_gather(m, st[f], i);
+        if (p.want_grad) {
+            EMPOSE_FOR_FRAME_ITEMS(kSensors * m.max_degree, f, i) item_sensor_face_grads(m, st[f], i);
+            __syncthreads();
+            EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_sensor_gather(m, st[f], i);
+        }
     } else {
         EMPOSE_FOR_ITEMS(kSensors, f, i) {
             const int64_t row = row0 + f;

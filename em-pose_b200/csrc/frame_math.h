@@ -89,6 +89,7 @@ struct FrameState {
         T fn[kSensors][kSplitDegree][3];   // split sensor phases: un-normalised face normals, then (slot 0) dE/dn
     };
     T dbeta_part[3][kBetas];
+    T fg[kSensors * kSplitDegree][6];   // split sensor phases: dE/d(edge1), dE/d(edge2) of every (sensor, face) item
     // Forward-only scratch and reverse-only scratch share storage: everything in `fwd` is dead once the sensor
     // outputs and joints have been written out, which is before the first member of `bwd` is written.
     union {
@@ -546,33 +547,44 @@ EMPOSE_HD void phase_sensor_frames(const SubModel& m, FrameState<T, VP>& st, con
     for (int s = lane; s < kSensors; s += lanes) item_sensor_frames(m, st, off_r, off_t, meas_pos, meas_ori, spec, want_grad, s);
 }
 
-// F4c: dE/dx by GATHER (n_verts items): every vertex sums, in a fixed order, the contributions of the faces it
-// is a corner of (recomputed from dE/dn of their sensor) and of the sensors it serves as sensor / helper vertex.
-// No atomics: the result is bit-reproducible, which window-sharded inference relies on.
+// F4c: reverse of the face normals, once per (sensor, face) item (12 * max_degree items): with fn = e1 x e2,
+// dE/de1 = e2 x dE/dfn and dE/de2 = dE/dfn x e1, where dE/dfn is the sensor's dE/dn.
+template <typename T, int VP>
+EMPOSE_HD void item_sensor_face_grads(const SubModel& m, FrameState<T, VP>& st, int it) {
+    const int s = it / m.max_degree, d = it % m.max_degree;
+    if (d >= m.sensor_degree[s]) return;
+    const T* dn = st.fn[s][0];
+    const int* f = &m.faces[m.sensor_faces[it] * 3];
+    const T* a = &st.x[f[0] * 3];
+    const T* b = &st.x[f[1] * 3];
+    const T* c = &st.x[f[2] * 3];
+    T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    cross3(e2, dn, &st.fg[it][0]);
+    cross3(dn, e1, &st.fg[it][3]);
+}
+template <typename T, int VP>
+EMPOSE_HD void phase_sensor_face_grads(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
+    for (int it = lane; it < kSensors * m.max_degree; it += lanes) item_sensor_face_grads(m, st, it);
+}
+
+// F4d: dE/dx by GATHER (n_verts items): every vertex sums, in a fixed order, the contributions of the faces it
+// is a corner of and of the sensors it serves as sensor / helper vertex.  No atomics: the result is
+// bit-reproducible, which window-sharded inference relies on.
 template <typename T, int VP>
 EMPOSE_HD void item_sensor_gather(const SubModel& m, FrameState<T, VP>& st, int v) {
     T g[3] = {T(0), T(0), T(0)};
     for (int q = m.vinc_ptr[v]; q < m.vinc_ptr[v + 1]; ++q) {
         const int item = m.vinc_item[q], code = m.vinc_code[q];
-        const int s = item / m.max_degree;
         if (code >= 3) {
-            const T* t = st.fn[s][code == 3 ? 2 : 1];
+            const T* t = st.fn[item / m.max_degree][code == 3 ? 2 : 1];
             g[0] += t[0]; g[1] += t[1]; g[2] += t[2];
-            continue;
+        } else {
+            const T* e = st.fg[item];
+            if (code == 1) { g[0] += e[0]; g[1] += e[1]; g[2] += e[2]; }
+            else if (code == 2) { g[0] += e[3]; g[1] += e[4]; g[2] += e[5]; }
+            else { g[0] -= e[0] + e[3]; g[1] -= e[1] + e[4]; g[2] -= e[2] + e[5]; }
         }
-        const T* dn = st.fn[s][0];
-        const int* f = &m.faces[m.sensor_faces[item] * 3];
-        const T* a = &st.x[f[0] * 3];
-        const T* b = &st.x[f[1] * 3];
-        const T* c = &st.x[f[2] * 3];
-        T e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-        T e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
-        T de1[3], de2[3];
-        cross3(e2, dn, de1);      // fn = e1 x e2: d e1 = e2 x dfn, d e2 = dfn x e1
-        cross3(dn, e1, de2);
-        if (code == 1) { g[0] += de1[0]; g[1] += de1[1]; g[2] += de1[2]; }
-        else if (code == 2) { g[0] += de2[0]; g[1] += de2[1]; g[2] += de2[2]; }
-        else { g[0] -= de1[0] + de2[0]; g[1] -= de1[1] + de2[1]; g[2] -= de1[2] + de2[2]; }
     }
     st.dx[v * 3] = g[0]; st.dx[v * 3 + 1] = g[1]; st.dx[v * 3 + 2] = g[2];
 }

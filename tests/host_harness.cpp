@@ -62,7 +62,7 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
             phase_sensor_faces(m, st, 0, 1);
             phase_sensor_frames(m, st, off_r + f * 108, off_t + f * 36, meas_pos + f * 36, meas_ori + f * 108, spec,
                                 want_grad != 0, 0, 1);
-            if (want_grad) phase_sensor_gather(m, st, 0, 1);
+            if (want_grad) { phase_sensor_face_grads(m, st, 0, 1); phase_sensor_gather(m, st, 0, 1); }
         } else {
             phase_sensors(m, st, off_r + f * 108, off_t + f * 36, meas_pos + f * 36, meas_ori + f * 108, spec,
                           want_grad != 0, 0, 1);
