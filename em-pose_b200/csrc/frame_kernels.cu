@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(PrepareParams p) {
     p.meas[idx] = v;
     if (dst >= 0) {
         const float r = maybe_round(v, p.round_out);
-        if (p.xin) p.xin[(int64_t)row * p.in_size + dst] = r;
-        if (p.xiter) p.xiter[(int64_t)row * p.iter_in + dst] = r;
+        if (p.xin) p.xin[(int64_t)row * p.in_stride + dst] = r;
+        if (p.xiter) p.xiter[(int64_t)row * p.iter_stride + dst] = r;
     }
     if (c == 0) {
         const int b = row / p.F, f = row % p.F;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) update_kernel(UpdateParams p) {
             p.beta[row * kBetas + k] = v;
             if (p.hist_shape) p.hist_shape[row * kBetas + k] = v;
         }
-        if (p.xiter) p.xiter[row * p.iter_in + p.in_size + c] = maybe_round(v, p.round_out);
+        if (p.xiter) p.xiter[row * p.iter_stride + p.in_size + c] = maybe_round(v, p.round_out);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.F * (kJoints - 1); i += blockDim.x) {
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p) {
     if (i >= (int64_t)p.R * 32) return;
     const int64_t row = i >> 5;
     const int j = (int)(i & 31);
-    float* xg = p.xiter ? p.xiter + row * p.iter_in + p.in_size + 76 : nullptr;
+    float* xg = p.xiter ? p.xiter + row * p.iter_stride + p.in_size + 76 : nullptr;
     if (j < kJoints) {
         float g[3] = {p.gtheta_part[row * kPoseDim + j * 3], p.gtheta_part[row * kPoseDim + j * 3 + 1],
                       p.gtheta_part[row * kPoseDim + j * 3 + 2]};

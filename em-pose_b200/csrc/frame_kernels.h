@@ -18,11 +18,12 @@ struct PrepareParams {
     int R, F;
     int slot_of_sensor[kSensors];   // position of each sensor in the network input, -1 if not fed
     int use_pos, use_ori, n_pos;    // n_pos = number of position columns in the network input
-    int in_size, iter_in;
+    int in_size;
+    int in_stride, iter_stride; // row pitches of xin / xiter in floats (multiples of 4: TMA needs 16-byte aligned rows)
     int round_out;
     float* meas;                // [R][144] exact copy [pos | ori]
-    float* xin;                 // [R][in_size]   (may be null)
-    float* xiter;               // [R][iter_in]   columns [0, in_size) written (may be null)
+    float* xin;                 // [R][in_stride]   (may be null)
+    float* xiter;               // [R][iter_stride] columns [0, in_size) written (may be null)
     float* coef;                // [R]
 };
 int launch_prepare(const PrepareParams& p, cudaStream_t s);
@@ -38,8 +39,8 @@ struct UpdateParams {
     int average_shape;
     int B, F;
     int round_out;
-    float* xiter;               // [R][iter_in] or null: columns [in_size, in_size+76) receive theta | beta
-    int in_size, iter_in;
+    float* xiter;               // [R][iter_stride] or null: columns [in_size, in_size+76) receive theta | beta
+    int in_size, iter_stride;
     float* pf;                  // [R][pf_stride] pose features vec(R_1..R_21 - I); split: [hi(192) | lo(192)]
     int pf_stride;              // 192, or 384 when split
     int pf_split;               // 1: write tf32 hi part and tf32 residual (error-compensated pose-blend GEMM)
@@ -86,8 +87,8 @@ struct PostParams {
     const float* coef;          // [R]
     int R;
     int round_out;
-    float* xiter;               // [R][iter_in]: columns [in_size+76, in_size+152) receive g_theta | g_beta
-    int in_size, iter_in;
+    float* xiter;               // [R][iter_stride]: columns [in_size+76, in_size+152) receive g_theta | g_beta
+    int in_size, iter_stride;
     float* g_theta_out;         // optional exact copies (tests), may be null
     float* g_beta_out;
 };

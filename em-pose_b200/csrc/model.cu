@@ -69,6 +69,7 @@ struct empose_ief {
     empose_ief_config cfg;
     int num_sms = 148;
     int in_size = 0, iter_in = 0, n_pos = 0;
+    int in_stride = 0, iter_stride = 0;   // row pitches of the network-input buffers (multiples of 4 floats for TMA)
     bool round = true;         // TF32 mode
     int pf_stride = kPoseFeatPad;   // floats per row of the pose-feature buffer (2x when split hi|lo)
     Arena arena;
@@ -174,8 +175,8 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
     Arena& A = pl.arena;
     const size_t Rz = (size_t)R;
     EMPOSE_TRY(A.alloc_n(Rz * 144, &pl.meas));
-    EMPOSE_TRY(A.alloc_n(Rz * ctx->in_size, &pl.xin));
-    EMPOSE_TRY(A.alloc_n(Rz * ctx->iter_in, &pl.xiter, true));
+    EMPOSE_TRY(A.alloc_n(Rz * ctx->in_stride, &pl.xin, true));
+    EMPOSE_TRY(A.alloc_n(Rz * ctx->iter_stride, &pl.xiter, true));
     EMPOSE_TRY(A.alloc_n(Rz, &pl.coef));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.theta));
     EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.beta));
@@ -213,7 +214,7 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
                 const int t = d - l;
                 if (t < 0 || t >= F) continue;
                 ASrc a0 = (t == 0) ? ASrc{pl.hinit[l], H, H, B} : ASrc{pl.hseq[l] + (size_t)(t - 1) * H, (int64_t)F * H, H, B};
-                ASrc a1 = (l == 0) ? ASrc{pl.xin + (size_t)t * ctx->in_size, (int64_t)F * ctx->in_size, ctx->in_size, B}
+                ASrc a1 = (l == 0) ? ASrc{pl.xin + (size_t)t * ctx->in_stride, (int64_t)F * ctx->in_stride, ctx->in_size, B}
                                    : ASrc{pl.hseq[l - 1] + (size_t)t * H, (int64_t)F * H, H, B};
                 GemmJob proto;
                 memset(&proto, 0, sizeof(proto));
@@ -241,9 +242,9 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
         proto.frames_per_window = F;
         EMPOSE_TRY(pl.book.add(ctx->heads, ASrc{pl.hseq[L - 1], H, H, R}, ASrc{}, proto, m_rows_R, -1, &pl.heads));
     } else {
-        EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_init, ctx->shape_init, pl.xin, ctx->in_size, ctx->in_size, &pl.init_chain));
+        EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_init, ctx->shape_init, pl.xin, ctx->in_stride, ctx->in_size, &pl.init_chain));
     }
-    EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_iter, ctx->shape_iter, pl.xiter, ctx->iter_in, ctx->iter_in, &pl.iter_chain));
+    EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_iter, ctx->shape_iter, pl.xiter, ctx->iter_stride, ctx->iter_in, &pl.iter_chain));
     {
         GemmJob proto = linear_proto(ctx->pb, false, pl.vpoff, vp, vp);
         EMPOSE_TRY(pl.book.add(ctx->pb, pose_blend_a0(ctx, pl.pf, R), pose_blend_a1(ctx, pl.pf, R), proto, m_rows_R, -1, &pl.pb));
@@ -447,7 +448,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
     pp.R = R; pp.F = F;
     for (int i = 0; i < kSensors; ++i) pp.slot_of_sensor[i] = ctx->slot_of_sensor[i];
     pp.use_pos = cfg.use_marker_pos; pp.use_ori = cfg.use_marker_ori; pp.n_pos = ctx->n_pos;
-    pp.in_size = ctx->in_size; pp.iter_in = ctx->iter_in; pp.round_out = rnd;
+    pp.in_size = ctx->in_size; pp.in_stride = ctx->in_stride; pp.iter_stride = ctx->iter_stride; pp.round_out = rnd;
     pp.meas = pl.meas; pp.xin = pl.xin; pp.xiter = pl.xiter; pp.coef = pl.coef;
     EMPOSE_TRY(count(launch_prepare(pp, s)));
 
@@ -479,7 +480,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         up.theta = pl.theta; up.beta = pl.beta; up.dtheta = pl.dtheta; up.dbeta = pl.dbeta;
         up.step = cfg.step_size; up.first = (it == 0); up.average_shape = cfg.average_shape;
         up.B = B; up.F = F; up.round_out = rnd;
-        up.xiter = pl.xiter; up.in_size = ctx->in_size; up.iter_in = ctx->iter_in; up.pf = pl.pf;
+        up.xiter = pl.xiter; up.in_size = ctx->in_size; up.iter_stride = ctx->iter_stride; up.pf = pl.pf;
         up.pf_stride = ctx->pf_stride; up.pf_split = rnd;
         if (hist && hist->pose) up.hist_pose = hist->pose + (size_t)it * R * kPoseDim;
         if (hist && hist->shape) up.hist_shape = hist->shape + (size_t)it * R * kBetas;
@@ -523,7 +524,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
             PostParams po;
             memset(&po, 0, sizeof(po));
             po.theta = pl.theta; po.dpf = pl.dpf; po.gtheta_part = pl.gth_part; po.gbeta = pl.gbeta; po.coef = pl.coef;
-            po.R = R; po.round_out = rnd; po.xiter = pl.xiter; po.in_size = ctx->in_size; po.iter_in = ctx->iter_in;
+            po.R = R; po.round_out = rnd; po.xiter = pl.xiter; po.in_size = ctx->in_size; po.iter_stride = ctx->iter_stride;
             EMPOSE_TRY(count(launch_post(po, s)));
         }
         EMPOSE_TRY(run_jobs(ctx, pl, pl.iter_chain, mt_R, s));
@@ -578,6 +579,8 @@ int empose_ief_create(const empose_ief_config* cfg, const empose_tensor* tensors
     ctx->n_pos = cfg->use_marker_pos ? 3 * cfg->n_markers : 0;
     ctx->in_size = ctx->n_pos + (cfg->use_marker_ori ? 9 * cfg->n_markers : 0);
     ctx->iter_in = ctx->in_size + kPoseDim + kBetas + (cfg->use_gradient ? kPoseDim + kBetas : 0);
+    ctx->in_stride = round_up(ctx->in_size, 4);
+    ctx->iter_stride = round_up(ctx->iter_in, 4);
     static const int kConfig6[6] = {0, 1, 2, 6, 7, 11};                     // reference configuration.py:89
     for (int i = 0; i < kSensors; ++i) { ctx->slot_of_sensor[i] = cfg->n_markers == 12 ? i : -1; }
     if (cfg->n_markers == 6) for (int i = 0; i < 6; ++i) ctx->slot_of_sensor[kConfig6[i]] = i;

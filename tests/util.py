@@ -99,7 +99,8 @@ def build_module(smpl_npz, n_markers=12, num_iterations=4, rnn_init=True, precis
     sd = net.state_dict()
     synth = synthetic.synth_state_dict(seed=0, n_markers=n_markers, rnn_init=rnn_init, hidden_size=hidden_size,
                                        rnn_hidden_size=cfg.m_rnn_hidden_size, num_layers=cfg.m_num_layers,
-                                       batch_norm=not cfg.m_no_batch_norm)
+                                       batch_norm=not cfg.m_no_batch_norm, use_gradient=cfg.m_use_gradient,
+                                       use_marker_pos=cfg.use_marker_pos, use_marker_ori=cfg.use_marker_ori)
     for k, v in synth.items():
         sd[k] = torch.from_numpy(np.asarray(v))
     net.load_state_dict(sd, strict=True)
