@@ -14,6 +14,22 @@ GOLDEN_CASES = {
 }
 
 
+#: flags of the training golden cases, mirrored from tests/golden/make_golden_train.py
+TRAIN_CASES = {
+    'train_lgd_rnn12_n4': dict(n_markers=12, num_iterations=4, rnn_init=True, pose_weight=10.0, fk_weight=0.1),
+    'train_lgd_mlp12_n2': dict(n_markers=12, num_iterations=2, rnn_init=False, pose_weight=1.0, fk_weight=0.0),
+    'train_lgd_rnn6_n2_real': dict(n_markers=6, num_iterations=2, rnn_init=True, pose_weight=10.0, fk_weight=0.1),
+}
+
+
+def train_inputs(gold, dtype=torch.float32):
+    get = lambda k: torch.from_numpy(gold[k]).to(dtype)
+    masks = torch.from_numpy(gold['marker_masks']) if 'marker_masks' in gold else None
+    return dict(marker_pos=get('marker_pos'), marker_oris=get('marker_oris'), offset_r=get('offset_r'),
+                offset_t=get('offset_t'), seq_lengths=torch.from_numpy(gold['seq_lengths']), marker_masks=masks,
+                poses_gt=get('poses'), shapes_gt=get('shapes'), joints_gt=get('joints_gt'))
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN_DIR, name + '.npz')) as z:
         return {k: z[k] for k in z.files}
