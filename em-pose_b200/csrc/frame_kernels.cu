@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     if (p.sensor_ori) EMPOSE_FOR_FRAME_ITEMS(108, f, i) p.sensor_ori[(row0 + f) * 108 + i] = st[f].sensor_ori[i / 9][i % 9];
     if (p.joints) EMPOSE_FOR_FRAME_ITEMS(kPoseDim, f, i) p.joints[(row0 + f) * kPoseDim + i] = st[f].gpos[i / 3][i % 3];
     if (!p.want_grad) return;
+    const bool joint_up = p.joints_gt != nullptr;
+    if (joint_up) EMPOSE_FOR_ITEMS(kJoints, f, i) item_joint_residual(st[f], p.joints_gt + (row0 + f) * kPoseDim, p.joint_weight, i);
     __syncthreads();
     EMPOSE_TICK(8);
 
@@ -219,15 +221,15 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     __syncthreads();
     EMPOSE_TICK(10);
     if (threadIdx.x >= kMainThreads - 32) {
-        if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd_static(st[f], i); }
-        else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd(m, st[f], i); }
+        if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd_static(st[f], i, joint_up); }
+        else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd(m, st[f], i, joint_up); }
     }
     EMPOSE_FOR_FRAME_ITEMS(m.vp_dim, f, i)
         p.dvp[(row0 + f) * m.vp_dim + i] = i < nv3 ? maybe_round(st[f].dx[i], p.round_out) : 0.0f;
     EMPOSE_FOR_ITEMS(3 * kBetas, f, i) item_shape_bwd_partial(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(11);
-    EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_chain_bwd_local(m, st[f], i);
+    EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_chain_bwd_local(m, st[f], i, joint_up);
     __syncthreads();
     EMPOSE_TICK(12);
     EMPOSE_FOR_ITEMS(kJoints, f, i)

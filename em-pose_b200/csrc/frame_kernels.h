@@ -75,6 +75,8 @@ struct MainParams {
     float* dvp;                 // [R][vp_dim]  (grad only)
     float* gtheta_part;         // [R][66]      (grad only) coef * chain part of dE/dtheta
     float* gbeta;               // [R][10]      (grad only) coef * dE/dbeta
+    const float* joints_gt;     // [R][66] or null (training): adds joint_weight * d/d(theta,beta) sum_j ||J_j - Jgt_j||
+    float joint_weight;
 };
 int launch_main(const MainParams& p, cudaStream_t s);
 

@@ -70,6 +70,8 @@ struct SubModel {
 struct ResidualSpec {
     int use_pos, use_ori;      // reference flags use_marker_pos / use_marker_ori
     int sensor_active[kSensors];  // 1 if the sensor is in marker_idxs (models.py:386)
+    float weight;              // scale of the sensor residual's gradient (1 for the LGD feature; training uses
+                               // r_weight / (N+1) on the final iterate, models.py:672-674)
 };
 
 template <typename T, int VP = kMaxVp>
@@ -89,6 +91,7 @@ struct FrameState {
         T fn[kSensors][kSplitDegree][3];   // split sensor phases: un-normalised face normals, then (slot 0) dE/dn
     };
     T dbeta_part[3][kBetas];
+    T jup[kJoints][3];        // upstream dE/d(posed joint) of the FK loss (training, models.py:657-660); else unused
     T fg[kSensors * kSplitDegree][6];   // split sensor phases: dE/d(edge1), dE/d(edge2) of every (sensor, face) item
     // Forward-only scratch and reverse-only scratch share storage: everything in `fwd` is dead once the sensor
     // outputs and joints have been written out, which is before the first member of `bwd` is written.
@@ -382,14 +385,14 @@ EMPOSE_HD void item_sensors(const SubModel& m, FrameState<T, VP>& st, const TIn*
     if (spec.use_pos) {
         T d[3] = {pc[0] - T(meas_pos[s * 3]), pc[1] - T(meas_pos[s * 3 + 1]), pc[2] - T(meas_pos[s * 3 + 2])};
         T len = sqrt_t(dot3(d, d));
-        T inv = len > T(0) ? T(1) / len : T(0);   // reference: NaN at exactly zero residual (sqrt backward); we emit 0
+        T inv = len > T(0) ? T(spec.weight) / len : T(0);   // reference: NaN at exactly zero residual (sqrt backward); we emit 0
         dpc[0] = d[0] * inv; dpc[1] = d[1] * inv; dpc[2] = d[2] * inv;
     }
     if (spec.use_ori) {
         T d[9], sq = T(0);
         for (int i = 0; i < 9; ++i) { d[i] = Rc[i] - T(meas_ori[s * 9 + i]); sq += d[i] * d[i]; }
         T len = sqrt_t(sq);
-        T inv = len > T(0) ? T(1) / len : T(0);
+        T inv = len > T(0) ? T(spec.weight) / len : T(0);
         for (int i = 0; i < 9; ++i) dRc[i] = d[i] * inv;
     }
     // offsets: Rc = R Ro, pc = xs + R to
@@ -506,14 +509,14 @@ EMPOSE_HD void item_sensor_frames(const SubModel& m, FrameState<T, VP>& st, cons
     if (spec.use_pos) {
         T d[3] = {pc[0] - T(meas_pos[s * 3]), pc[1] - T(meas_pos[s * 3 + 1]), pc[2] - T(meas_pos[s * 3 + 2])};
         T len = sqrt_t(dot3(d, d));
-        T inv = len > T(0) ? T(1) / len : T(0);
+        T inv = len > T(0) ? T(spec.weight) / len : T(0);
         dpc[0] = d[0] * inv; dpc[1] = d[1] * inv; dpc[2] = d[2] * inv;
     }
     if (spec.use_ori) {
         T d[9], sq = T(0);
         for (int i = 0; i < 9; ++i) { d[i] = Rc[i] - T(meas_ori[s * 9 + i]); sq += d[i] * d[i]; }
         T len = sqrt_t(sq);
-        T inv = len > T(0) ? T(1) / len : T(0);
+        T inv = len > T(0) ? T(spec.weight) / len : T(0);
         for (int i = 0; i < 9; ++i) dRc[i] = d[i] * inv;
     }
     T dR[9];
@@ -597,6 +600,20 @@ EMPOSE_HD void phase_sensor_gather(const SubModel& m, FrameState<T, VP>& st, int
 // reverse phases
 // ----------------------------------------------------------------------------------------------
 
+// B0 (training only): upstream gradient of the FK loss sum_j ||J_j - Jgt_j|| (loss.py:27-28 applied to joints,
+// models.py:657-660) times `weight`, kept in st.jup (22 items).  Must run while st.gpos is still alive.
+template <typename T, int VP, typename TIn>
+EMPOSE_HD void item_joint_residual(FrameState<T, VP>& st, const TIn* joints_gt, T weight, int j) {
+    T d[3] = {st.gpos[j][0] - T(joints_gt[j * 3]), st.gpos[j][1] - T(joints_gt[j * 3 + 1]), st.gpos[j][2] - T(joints_gt[j * 3 + 2])};
+    T len = sqrt_t(dot3(d, d));
+    T inv = len > T(0) ? weight / len : T(0);
+    st.jup[j][0] = d[0] * inv; st.jup[j][1] = d[1] * inv; st.jup[j][2] = d[2] * inv;
+}
+template <typename T, int VP, typename TIn>
+EMPOSE_HD void phase_joint_residual(FrameState<T, VP>& st, const TIn* joints_gt, T weight, int lane, int lanes) {
+    for (int j = lane; j < kJoints; j += lanes) item_joint_residual(st, joints_gt, weight, j);
+}
+
 // B1a: dE/dA summed over one chunk ("virtual joint") of a joint's vertex list (n_vj items).  Each chunk walks
 // its (bounded) list once and accumulates all 12 entries in registers, so lanes stay balanced.
 template <typename T, int VP>
@@ -671,11 +688,11 @@ EMPOSE_HD void phase_shape_bwd_partial(const SubModel& m, FrameState<T, VP>& st,
 // B4: reverse sweep of the kinematic chain, row-parallel like the forward one: lane r owns row r of
 // every dE/dG^R and entry r of every dE/dG^t.  After the sweep both are final for every joint.
 template <typename T, int VP>
-EMPOSE_HD void item_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int r) {
+EMPOSE_HD void item_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int r, bool joint_up = false) {
     for (int j = 0; j < kJoints; ++j) {
-        // A_j^R = G_j^R,  A_j^t = G_j^t - G_j^R J_j
+        // A_j^R = G_j^R,  A_j^t = G_j^t - G_j^R J_j;  the posed joint itself is G_j^t (FK loss upstream)
         const T a = st.dat[j][r];
-        st.dgt[j][r] = a;
+        st.dgt[j][r] = joint_up ? a + st.jup[j][r] : a;
         for (int c = 0; c < 3; ++c) st.dgr[j][r * 3 + c] = st.dar[j][r * 3 + c] - a * st.jrest[j][c];
     }
     for (int j = kJoints - 1; j >= 1; --j) {
@@ -692,15 +709,15 @@ EMPOSE_HD void item_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int r) {
     }
 }
 template <typename T, int VP>
-EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int r = lane; r < 3; r += lanes) item_chain_bwd(m, st, r);
+EMPOSE_HD void phase_chain_bwd(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes, bool joint_up = false) {
+    for (int r = lane; r < 3; r += lanes) item_chain_bwd(m, st, r, joint_up);
 }
 
 // B4': phase_chain_bwd specialised for the standard SMPL tree.  Children contributions are accumulated in
 // registers (`acc`, zero until first touched) and each joint is finalised and stored when the sweep reaches it,
 // so only the partial sums of pending parents are live.
 template <typename T, int VP>
-EMPOSE_HD void item_chain_bwd_static(FrameState<T, VP>& st, int r) {
+EMPOSE_HD void item_chain_bwd_static(FrameState<T, VP>& st, int r, bool joint_up = false) {
     T acc[kJoints][3], acct[kJoints];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -711,7 +728,7 @@ EMPOSE_HD void item_chain_bwd_static(FrameState<T, VP>& st, int r) {
 #endif
     for (int j = kJoints - 1; j >= 0; --j) {
         const T a = st.dat[j][r];
-        const T dt = a + acct[j];
+        const T dt = joint_up ? a + st.jup[j][r] + acct[j] : a + acct[j];
         const T d0 = st.dar[j][r * 3] - a * st.jrest[j][0] + acc[j][0];
         const T d1 = st.dar[j][r * 3 + 1] - a * st.jrest[j][1] + acc[j][1];
         const T d2 = st.dar[j][r * 3 + 2] - a * st.jrest[j][2] + acc[j][2];
@@ -728,8 +745,8 @@ EMPOSE_HD void item_chain_bwd_static(FrameState<T, VP>& st, int r) {
     }
 }
 template <typename T, int VP>
-EMPOSE_HD void phase_chain_bwd_static(FrameState<T, VP>& st, int lane, int lanes) {
-    for (int r = lane; r < 3; r += lanes) item_chain_bwd_static(st, r);
+EMPOSE_HD void phase_chain_bwd_static(FrameState<T, VP>& st, int lane, int lanes, bool joint_up = false) {
+    for (int r = lane; r < 3; r += lanes) item_chain_bwd_static(st, r, joint_up);
 }
 
 // B5: local gradients from the final dE/dG.
@@ -737,8 +754,10 @@ EMPOSE_HD void phase_chain_bwd_static(FrameState<T, VP>& st, int lane, int lanes
 //   dE/dJ_j = (G_p^R - G_j^R)^T dE/dG_j^t   (j > 0),   dE/dJ_0 = (I - G_0^R)^T dE/dG_0^t
 // (the second line collects the three places J_j appears: A_j^t, its own bone and its children's bones,
 //  using dE/dG_j^t = dE/dA_j^t + sum over children of dE/dG_child^t).
+// With an upstream gradient u_j on the posed joint itself (FK loss), dE/dG_j^t also contains u_j, which does not
+// belong to the A_j^t / children terms: dE/dJ_j += G_j^R^T u_j.
 template <typename T, int VP>
-EMPOSE_HD void item_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, int i) {
+EMPOSE_HD void item_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, int i, bool joint_up = false) {
     const int j = i / 12, e = i % 12;
     const int p = m.parents[j];
     if (e < 9) {
@@ -753,13 +772,14 @@ EMPOSE_HD void item_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, in
         for (int r = 0; r < 3; ++r) {
             const T gp = (j == 0) ? (r == c ? T(1) : T(0)) : st.grot[p][r * 3 + c];
             acc += (gp - st.grot[j][r * 3 + c]) * st.dgt[j][r];
+            if (joint_up) acc += st.grot[j][r * 3 + c] * st.jup[j][r];
         }
         st.dj[j][c] = acc;
     }
 }
 template <typename T, int VP>
-EMPOSE_HD void phase_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes) {
-    for (int i = lane; i < kJoints * 12; i += lanes) item_chain_bwd_local(m, st, i);
+EMPOSE_HD void phase_chain_bwd_local(const SubModel& m, FrameState<T, VP>& st, int lane, int lanes, bool joint_up = false) {
+    for (int i = lane; i < kJoints * 12; i += lanes) item_chain_bwd_local(m, st, i, joint_up);
 }
 
 // B6: finish.  g_theta and the complete g_beta, both scaled by `coef`

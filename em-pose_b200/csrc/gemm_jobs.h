@@ -67,6 +67,11 @@ struct GemmJob {
     int64_t h_prev_stride;
     int32_t t;               // time step of this job
     int32_t hidden;          // H
+    // training only (may be null): activated gates [row][4H] in torch order i|f|g|o and the cell state after the step [row][H]
+    float* gates_out;
+    int64_t gates_stride;
+    float* c_seq_out;
+    int64_t c_seq_stride;
 };
 
 // Columns of an LSTM job are packed in groups of 32 = 8 hidden units x 4 gates:
@@ -183,13 +188,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
                 const float gf = v[8 + k] + bias[8 + k];
                 const float gg = v[16 + k] + bias[16 + k];
                 const float go = v[24 + k] + bias[24 + k];
-                float c_new, h_new;
+                float c_new, h_new, si, sf, tg, so;
                 if (j.round_out) {
-                    c_new = sigmoid_f(gf) * c_old[k] + sigmoid_f(gi) * tanh_f(gg);
-                    h_new = round_tf32(sigmoid_f(go) * tanh_f(c_new));
+                    si = sigmoid_f(gi); sf = sigmoid_f(gf); tg = tanh_f(gg); so = sigmoid_f(go);
+                    c_new = sf * c_old[k] + si * tg;
+                    h_new = round_tf32(so * tanh_f(c_new));
                 } else {
-                    c_new = (1.0f / (1.0f + expf(-gf))) * c_old[k] + (1.0f / (1.0f + expf(-gi))) * tanhf(gg);
-                    h_new = (1.0f / (1.0f + expf(-go))) * tanhf(c_new);
+                    si = 1.0f / (1.0f + expf(-gi)); sf = 1.0f / (1.0f + expf(-gf)); tg = tanhf(gg); so = 1.0f / (1.0f + expf(-go));
+                    c_new = sf * c_old[k] + si * tg;
+                    h_new = so * tanhf(c_new);
+                }
+                if (j.gates_out) {                 // training: keep the activated gates for the backward pass
+                    float* gp = j.gates_out + (int64_t)row * j.gates_stride + unit0 + k;
+                    gp[0] = si; gp[j.hidden] = sf; gp[2 * j.hidden] = tg; gp[3 * j.hidden] = so;
                 }
                 v[k] = c_new;
                 v[8 + k] = h_new;
@@ -213,6 +224,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
             if (r < rows) {
                 cg[(int64_t)r * j.hidden] = cl[q];
                 og[(int64_t)r * j.out_stride] = hl[q];
+                if (j.c_seq_out) j.c_seq_out[(int64_t)(row0 + r) * j.c_seq_stride + unit0 + u] = cl[q];
             }
         }
         __syncwarp();

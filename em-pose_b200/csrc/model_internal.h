@@ -16,6 +16,7 @@
 #include "../../include/empose_b200.h"
 #include "common.cuh"
 #include "gemm_jobs.h"
+#include "frame_kernels.h"
 #include "gemm_tc.h"
 
 namespace empose {
@@ -285,5 +286,70 @@ inline GemmJob linear_proto(const PackedMatrix& W, bool round, float* out, int64
     return j;
 }
 
+// ---- the inference plan and the model context (model.cu) ------------------------------------------
+struct Plan {
+    int B = 0, F = 0, R = 0;
+    Arena arena;
+    JobBook book;
+    // workspace
+    float *meas = nullptr, *xin = nullptr, *xiter = nullptr, *coef = nullptr;
+    float *theta = nullptr, *beta = nullptr, *dtheta = nullptr, *dbeta = nullptr;
+    float *pf = nullptr, *vpoff = nullptr, *dvp = nullptr, *dpf = nullptr, *gth_part = nullptr, *gbeta = nullptr;
+    float *joints = nullptr, *spos = nullptr, *sori = nullptr;
+    float *off_r = nullptr, *off_t = nullptr;
+    int32_t* seq_len = nullptr;
+    float* act[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pose|shape][ping-pong]
+    int64_t act_rows = 0;
+    std::vector<float*> hseq, cstate, hinit;
+    // staging for the host-buffer entry point
+    float *in_pos = nullptr, *in_ori = nullptr, *in_masks = nullptr, *io_state = nullptr;
+    float *in_off_r = nullptr, *in_off_t = nullptr;
+    int32_t* in_len = nullptr;
+    float *o_pose = nullptr, *o_shape = nullptr, *o_joints = nullptr;
+    float* o_hist[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // job ranges
+    std::vector<JobRange> lstm_diag;
+    JobRange heads, init_chain, iter_chain, pb, pbt;
+};
 
+
+struct IefData {            // everything behind the opaque `empose_ief` handle
+    empose_ief_config cfg;
+    int num_sms = 148;
+    int in_size = 0, iter_in = 0, n_pos = 0;
+    int in_stride = 0, iter_stride = 0;   // row pitches of the network-input buffers (multiples of 4 floats for TMA)
+    bool round = true;         // TF32 mode
+    int pf_stride = kPoseFeatPad;   // floats per row of the pose-feature buffer (2x when split hi|lo)
+    Arena arena;
+    SubModel sub;
+    ResidualSpec spec;
+    int slot_of_sensor[kSensors];
+    int static_tree = 0;       // sub.parents equals the standard SMPL body tree
+    std::vector<PackedMatrix> lstm;
+    PackedMatrix heads;
+    MlpPacked pose_init, shape_init, pose_iter, shape_iter;
+    PackedMatrix pb, pbt;
+    std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+    std::map<int, std::unique_ptr<Plan>> project_plans;
+    int64_t last_launches = 0;
+    // optional per-launch timing of the GEMM executor (empose_ief_set_profiling)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    ~IefData() {
+        for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    }
+};
+}  // namespace empose
+
+struct empose_ief : empose::IefData {};
+
+namespace empose {
+// A operand of the pose-blend GEMM: [pf_hi | pf_lo] then pf_hi again in TF32 mode, plain pf in FP32 mode
+inline ASrc pose_blend_a0(const empose_ief* ctx, const float* pf, int rows) {
+    return ASrc{pf, ctx->pf_stride, ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad, rows};
+}
+inline ASrc pose_blend_a1(const empose_ief* ctx, const float* pf, int rows) {
+    return ctx->round ? ASrc{pf, ctx->pf_stride, kPoseFeatPad, rows} : ASrc{};
+}
 }  // namespace empose

@@ -22,7 +22,9 @@ EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_creat
                     'empose_ief_forward', 'empose_ief_forward_host', 'empose_sensor_project',
                     'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read',
                     'empose_gemm_selftest', 'empose_gemm_bench', 'empose_smpl_create', 'empose_smpl_destroy',
-                    'empose_smpl_forward')
+                    'empose_smpl_forward', 'empose_train_layout', 'empose_train_sizes', 'empose_train_create',
+                    'empose_train_destroy', 'empose_train_forward', 'empose_train_backward',
+                    'empose_train_last_launch_count')
 
 
 class EmposeError(RuntimeError):
@@ -41,6 +43,10 @@ class IefConfig(ctypes.Structure):
                 ('num_layers', ctypes.c_int32), ('rnn_hidden_size', ctypes.c_int32), ('rnn_num_layers', ctypes.c_int32),
                 ('skip_connections', ctypes.c_int32), ('batch_norm', ctypes.c_int32), ('precision', ctypes.c_int32),
                 ('device', ctypes.c_int32)]
+
+
+class LossWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ('pose_weight', 'shape_weight', 'reprojection_weight', 'fk_weight')]
 
 
 class History(ctypes.Structure):
@@ -92,6 +98,21 @@ def load():
     lib.empose_gemm_bench.restype = ctypes.c_int
     lib.empose_gemm_bench.argtypes = [i32, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, i32, i32, i32,
                                       i32, ctypes.POINTER(ctypes.c_float), vp]
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    lib.empose_train_layout.restype = ctypes.c_int
+    lib.empose_train_layout.argtypes = [ctypes.POINTER(IefConfig), i32, ctypes.c_char_p, i32, ctypes.POINTER(i32), i64p, i64p]
+    lib.empose_train_sizes.restype = ctypes.c_int
+    lib.empose_train_sizes.argtypes = [ctypes.POINTER(IefConfig), i64p, i64p]
+    lib.empose_train_create.restype = ctypes.c_int
+    lib.empose_train_create.argtypes = [ctypes.POINTER(IefConfig), ctypes.POINTER(Tensor), i32, vp, vp, vp, ctypes.POINTER(vp)]
+    lib.empose_train_destroy.restype = None
+    lib.empose_train_destroy.argtypes = [vp]
+    lib.empose_train_forward.restype = ctypes.c_int
+    lib.empose_train_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, ctypes.POINTER(History), vp]
+    lib.empose_train_backward.restype = ctypes.c_int
+    lib.empose_train_backward.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LossWeights), ctypes.POINTER(ctypes.c_float), vp]
+    lib.empose_train_last_launch_count.restype = ctypes.c_int64
+    lib.empose_train_last_launch_count.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -140,9 +161,7 @@ class IefContext(object):
         :param arrays: {name: numpy array}: the reference's state-dict keys plus the ``sub.*`` arrays.
         """
         lib = load()
-        cfg = IefConfig()
-        for name, _ in IefConfig._fields_:
-            setattr(cfg, name, config[name])
+        cfg = _config_struct(config)
         self.config = dict(config)
         table, keep = make_tensor_table(arrays)
         handle = ctypes.c_void_p()
@@ -258,6 +277,119 @@ class IefContext(object):
         _check(load().empose_sensor_project(self._handle, _ptr(poses), _ptr(shapes), _ptr(offset_r), _ptr(offset_t), r,
                                             _ptr(pos), _ptr(ori), _ptr(joints), _stream()))
         return pos, ori, joints
+
+
+def _config_struct(config):
+    cfg = IefConfig()
+    for name, _ in IefConfig._fields_:
+        setattr(cfg, name, config[name])
+    return cfg
+
+
+def train_layout(config):
+    """The flat parameter / running-statistics layout of a configuration (``empose_train_layout``).
+    :return: (entries, n_params, n_buffers); entries = [(state-dict key, kind, offset, numel)], kind 0 = parameter
+             (params / grads vectors), 1 = BatchNorm running statistic (bn_buffers vector); sizes in floats."""
+    lib = load()
+    cfg = _config_struct(config)
+    entries = []
+    name = ctypes.create_string_buffer(256)
+    kind, off, numel = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
+    i = 0
+    while True:
+        rc = lib.empose_train_layout(ctypes.byref(cfg), i, name, 256, ctypes.byref(kind), ctypes.byref(off), ctypes.byref(numel))
+        if rc == -2:
+            break
+        _check(rc)
+        entries.append((name.value.decode(), int(kind.value), int(off.value), int(numel.value)))
+        i += 1
+    n_p, n_b = ctypes.c_int64(), ctypes.c_int64()
+    _check(lib.empose_train_sizes(ctypes.byref(cfg), ctypes.byref(n_p), ctypes.byref(n_b)))
+    return entries, int(n_p.value), int(n_b.value)
+
+
+class TrainContext(object):
+    """Owns one ``empose_train*``: the training step over caller-owned flat parameter / gradient vectors."""
+
+    def __init__(self, config, arrays, params, grads, bn_buffers):
+        """
+        :param arrays: {name: numpy array}: state dict + ``sub.*`` arrays (as for ``IefContext``).
+        :param params, grads, bn_buffers: flat float32 CUDA tensors laid out as ``train_layout(config)`` says; they
+                                          must outlive this object (bn_buffers may be None without BatchNorm).
+        """
+        lib = load()
+        cfg = _config_struct(config)
+        self.config = dict(config)
+        table, keep = make_tensor_table(arrays)
+        handle = ctypes.c_void_p()
+        self._keep_alive = (params, grads, bn_buffers)
+        _check(lib.empose_train_create(ctypes.byref(cfg), table, len(arrays), _ptr(params), _ptr(grads), _ptr(bn_buffers),
+                                       ctypes.byref(handle)))
+        del keep
+        self._handle = handle
+        self.n_iter = int(config['num_iterations'])
+        self.device_index = int(config['device'])
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            load().empose_train_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def last_launch_count(self):
+        return int(load().empose_train_last_launch_count(self._handle))
+
+    def forward(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None, want_history=True):
+        """Train-mode forward pass; same tensors in / out as ``IefContext.forward`` (no LSTM state carry)."""
+        import torch
+        dev = marker_pos.device
+        if dev.type != 'cuda':
+            raise EmposeError('inputs must be CUDA tensors (no CPU path)')
+        b, f = int(marker_pos.shape[0]), int(marker_pos.shape[1])
+        f32 = lambda t: t.to(dtype=torch.float32).contiguous()
+        marker_pos, marker_oris = f32(marker_pos).reshape(b, f, 36), f32(marker_oris).reshape(b, f, 108)
+        offset_r, offset_t = f32(offset_r).reshape(b, 12, 9), f32(offset_t).reshape(b, 12, 3)
+        seq_lengths = seq_lengths.to(device=dev, dtype=torch.int32).contiguous()
+        if marker_masks is not None:
+            marker_masks = f32(marker_masks).reshape(b, f, 12)
+        opts = dict(dtype=torch.float32, device=dev)
+        pose = torch.empty((b, f, 66), **opts)
+        shape = torch.empty((b, f, 10), **opts)
+        joints = torch.empty((b, f, 66), **opts)
+        hist, hist_struct = None, None
+        if want_history:
+            n1 = self.n_iter + 1
+            hist = {'pose': torch.empty((n1, b, f, 66), **opts), 'shape': torch.empty((n1, b, f, 10), **opts),
+                    'joints': torch.empty((n1, b, f, 66), **opts), 'markers': torch.empty((n1, b, f, 36), **opts),
+                    'markers_ori': torch.empty((n1, b, f, 108), **opts)}
+            hist_struct = History(*[hist[k].data_ptr() for k in ('pose', 'shape', 'joints', 'markers', 'markers_ori')])
+        _check(load().empose_train_forward(
+            self._handle, _ptr(marker_pos), _ptr(marker_oris), _ptr(offset_r), _ptr(offset_t), _ptr(seq_lengths),
+            _ptr(marker_masks), b, f, _ptr(pose), _ptr(shape), _ptr(joints),
+            ctypes.byref(hist_struct) if hist_struct is not None else None, _stream()))
+        self._shape = (b, f)
+        return {'pose': pose, 'shape': shape, 'joints': joints, 'history': hist}
+
+    def backward(self, poses_gt, shapes_gt, joints_gt, pose_weight, shape_weight, reprojection_weight, fk_weight):
+        """Adds the step's gradients to the flat ``grads`` vector; returns the five loss values of
+        ``models.py:676-680`` as a dict.  Synchronises."""
+        import torch
+        b, f = self._shape
+        f32 = lambda t: None if t is None else t.to(dtype=torch.float32).contiguous()
+        poses_gt = f32(poses_gt).reshape(b, f, 66)
+        shapes_gt = f32(shapes_gt).reshape(b, 10)
+        joints_gt = None if joints_gt is None else f32(joints_gt).reshape(b, f, 66)
+        w = LossWeights(float(pose_weight), float(shape_weight), float(reprojection_weight), float(fk_weight))
+        vals = (ctypes.c_float * 5)()
+        _check(load().empose_train_backward(self._handle, _ptr(poses_gt), _ptr(shapes_gt), _ptr(joints_gt), ctypes.byref(w),
+                                            vals, _stream()))
+        return dict(zip(('pose', 'shape', 'reconstruction', 'fk', 'total_loss'), [float(v) for v in vals]))
 
 
 class SmplContext(object):

@@ -4,7 +4,14 @@ Mirrors ``empose/nn/models.py``: ``create_model`` (``:23-33``), ``BaseModel`` bo
 and ``IterativeErrorFeedback`` (``:369-688``).  Same constructor arguments, same ``forward`` /
 ``backward`` signatures and outputs, same ``*_history`` attributes, same state-dict keys -- but
 ``forward`` marshals the batch through the C ABI (``empose_b200.lib``) into hand-written sm_100a CUDA
-instead of running PyTorch ops.  Inference only for now: calling ``forward`` in training mode raises.
+instead of running PyTorch ops.
+
+Training (``net.train()``): the parameters are re-homed as views of ONE flat CUDA vector (their ``.grad`` as views
+of a second one), ``forward`` runs the train-mode pass (BatchNorm on batch statistics) and ``backward`` adds to
+``.grad`` exactly what the reference leaves there after ``net(batch)`` + ``net.backward(batch, out)`` -- including
+the gradients its forward pass accumulates as a side effect (``models.py:576``).  Any ``torch.optim`` optimiser
+built on ``net.parameters()`` then steps in place, and data-parallel training all-reduces the single flat
+gradient vector (``allreduce_gradients``).
 """
 import numpy as np
 import torch
@@ -105,6 +112,10 @@ class IterativeErrorFeedback(nn.Module):
         self.joints_hat_history = None
         self._ctx = None
         self._ctx_key = None
+        self._trainer = None
+        self._trainer_device = None
+        self._flat = None                    # dict(params=, grads=, bn=, entries=) once training has started
+        self._train_batch_shape = None
 
     # ------------------------------------------------------------------------------------------------
     def model_name(self):
@@ -152,12 +163,122 @@ class IterativeErrorFeedback(nn.Module):
         return self._ctx
 
     # ------------------------------------------------------------------------------------------------
+    # training
+    # ------------------------------------------------------------------------------------------------
+    def _trainable_items(self):
+        sd = dict(self.named_parameters())
+        sd.update(dict(self.named_buffers()))
+        return sd
+
+    def trainer(self, device):
+        """Build (or reuse) the native training context on ``device``; re-homes parameters into flat vectors."""
+        if device.type != 'cuda':
+            raise _lib.EmposeError('empose_b200 trains on CUDA devices only (no CPU fallback); got %s' % device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        if self._trainer is not None and self._trainer_device == index:
+            return self._trainer
+        if getattr(self.config, 'm_dropout_hidden', 0.0) > 0.0 or getattr(self.config, 'm_dropout', 0.0) > 0.0:
+            raise NotImplementedError('training with dropout > 0 is not implemented (the released models use 0)')
+        if self._trainer is not None:
+            self._trainer.close()
+            self._trainer = None
+        cfg = self._native_config(index)
+        entries, n_params, n_buffers = _lib.train_layout(cfg)
+        dev = torch.device('cuda', index)
+        params = torch.zeros(max(n_params, 4), dtype=torch.float32, device=dev)
+        grads = torch.zeros_like(params)
+        bn = torch.zeros(max(n_buffers, 4), dtype=torch.float32, device=dev)
+        items = self._trainable_items()
+        for name, kind, off, numel in entries:
+            t = items[name]
+            flat = params if kind == 0 else bn
+            view = flat[off:off + numel].view(t.shape)
+            view.copy_(t.detach().to(device=dev, dtype=torch.float32))
+            t.data = view                                   # the Parameter / buffer object stays, its storage moves
+            if kind == 0:
+                t.grad = grads[off:off + numel].view(t.shape)
+        self._flat = dict(params=params, grads=grads, bn=bn, entries=entries)
+        arrays = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()
+                  if not k.startswith('smpl.') and v.is_floating_point()}
+        arrays = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in arrays.items()}
+        arrays.update(self.smpl.submodel_arrays())
+        self._trainer = _lib.TrainContext(cfg, arrays, params, grads, bn if n_buffers > 0 else None)
+        self._trainer_device = index
+        return self._trainer
+
+    def flat_gradients(self):
+        """The single flat gradient vector (None before the first training step)."""
+        return None if self._flat is None else self._flat['grads']
+
+    def flat_parameters(self):
+        return None if self._flat is None else self._flat['params']
+
+    def allreduce_gradients(self, average=True):
+        """Data-parallel training: ONE all-reduce over the flat gradient vector."""
+        import torch.distributed as dist
+        g = self._flat['grads']
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        if average:
+            g.div_(dist.get_world_size())
+
+    def _attach_gradients(self):
+        """``optimizer.zero_grad()`` sets ``.grad`` to None by default: re-attach (zeroed) views of the flat vector."""
+        items = dict(self.named_parameters())
+        grads = self._flat['grads']
+        for name, kind, off, numel in self._flat['entries']:
+            if kind != 0:
+                continue
+            p = items[name]
+            view = grads[off:off + numel].view(p.shape)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                view.zero_()
+                p.grad = view
+
+    def _forward_train(self, batch, window_size):
+        if window_size is not None and window_size < batch.seq_length:
+            raise NotImplementedError('windowed evaluation is an inference feature; train on whole windows')
+        inputs = batch.get_inputs()
+        marker_pos = inputs['marker_pos']
+        tr = self.trainer(marker_pos.device)
+        self._attach_gradients()
+        res = tr.forward(marker_pos, inputs['marker_oris'], inputs['offset_r'], inputs['offset_t'], batch.seq_lengths,
+                         marker_masks=inputs.get('marker_masks'), want_history=True)
+        for mod, times in ((self.pose_net_iter, self.N), (self.shape_net_iter, self.N),
+                           (None if self.rnn_init else self.pose_net_init, 1),
+                           (None if self.rnn_init else self.shape_net_init, 1)):
+            if mod is None:
+                continue
+            for m in mod.modules():
+                if isinstance(m, nn.BatchNorm1d):
+                    m.num_batches_tracked += times
+        n1 = self.N + 1
+        h = res['history']
+        self.pose_hat_history = [h['pose'][i] for i in range(n1)]
+        self.shape_hat_history = [h['shape'][i] for i in range(n1)]
+        self.joints_hat_history = [h['joints'][i] for i in range(n1)]
+        self.markers_hat_history = [h['markers'][i] for i in range(n1)]
+        self.markers_ori_hat_history = [h['markers_ori'][i] for i in range(n1)]
+        pose = res['pose']
+        return {'pose_hat': pose[:, :, 3:], 'root_ori_hat': pose[:, :, :3], 'shape_hat': res['shape'],
+                'joints_hat': res['joints']}
+
+    def _backward_train(self, batch, writer, global_step):
+        pose_gt = torch.cat([batch.poses_root, batch.poses_body], dim=-1)
+        joints_gt = batch.joints_gt if self.do_fk else None
+        vals = self._trainer.backward(pose_gt, batch.shapes, joints_gt, self.pose_weight, self.shape_weight, self.r_weight,
+                                      self.fk_loss_weight if self.do_fk else 0.0)
+        if writer is not None:
+            for k in vals:
+                writer.add_scalar('{}/{}'.format(k, 'train'), vals[k], global_step)
+        total = torch.tensor([vals['total_loss']], dtype=torch.float32, device=pose_gt.device)
+        return total, vals
+
+    # ------------------------------------------------------------------------------------------------
     def forward(self, batch, window_size=None, is_new_sequence=True):
         """``models.py:485-632``.  ``batch`` is an ``ABatch`` (anything with ``get_inputs``, ``seq_lengths``,
         ``batch_size`` and ``seq_length``).  Works inside ``torch.no_grad()`` like the reference."""
         if self.training:
-            raise NotImplementedError('empose_b200 implements the inference path of the LGD loop; call net.eval() '
-                                      '(training: batch-statistics BatchNorm + backward are not built yet)')
+            return self._forward_train(batch, window_size)
         if self.rnn_init:
             if is_new_sequence:
                 self.rnn.final_state = None
@@ -235,10 +356,11 @@ class IterativeErrorFeedback(nn.Module):
         """
         ``models.py:634-688``: the training loss over all N+1 iterates, evaluated from the histories of the
         last ``forward``.  Returns ``(total_loss, loss_vals)``.  The loss value is what
-        ``empose/eval/helpers.py:86`` logs during validation; ``total_loss.backward()`` (training) is not built.
+        ``empose/eval/helpers.py:86`` logs during validation.  In training mode the native backward pass runs
+        instead and the gradients land in ``.grad`` (the reference calls ``total_loss.backward()`` here).
         """
         if self.training:
-            raise NotImplementedError('the training backward pass is not built yet in empose_b200')
+            return self._backward_train(batch, writer, global_step)
         bsz, n_frames = batch.batch_size, batch.seq_length
         inputs_ = self.prepare_inputs(batch.get_inputs())
         markers_in = inputs_[:, :, self.pos_d_start:self.pos_d_end].reshape((bsz, n_frames, -1, 3))

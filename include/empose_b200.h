@@ -16,6 +16,11 @@
  *                                                                                 empose/nn/models.py:471-483
  *   empose_smpl_create / _forward  <- SMPLLayer.__init__ / forward / fk / _fk     empose/bodymodels/smpl.py:31-165
  *                                     (the third-party BodyModel call at smpl.py:121)
+ *   empose_train_create / _layout  <- create_model + net.parameters() as ONE flat vector (scripts/train.py:125)
+ *   empose_train_forward           <- IterativeErrorFeedback.forward with net.train()  empose/nn/models.py:485-632
+ *                                     (BatchNorm1d on batch statistics, layers.py:26,57; the gradient side effect
+ *                                     of models.py:576)
+ *   empose_train_backward          <- IterativeErrorFeedback.backward                  empose/nn/models.py:634-688
  *   empose_gemm_selftest           <- (no reference counterpart) checks the tcgen05 GEMM engine
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
@@ -154,6 +159,50 @@ void empose_smpl_destroy(empose_smpl* ctx);
  * Device pointers; evaluated in slabs internally, so N is unbounded. */
 int empose_smpl_forward(empose_smpl* ctx, const float* poses_root, const float* poses_body, const float* betas,
                         const float* trans, int32_t N, float* verts, float* joints, void* stream);
+
+/* ---- training step ------------------------------------------------------------------------------------------
+ * Parameters live in ONE flat float32 device vector, their gradients in a second one of the same layout and the
+ * BatchNorm running statistics in a third; the caller owns all three (PyTorch tensors whose views are the module's
+ * nn.Parameters), so an optimiser updates the weights in place and data-parallel training needs a single
+ * all-reduce over `grads`.  The layout is fixed by the configuration alone. */
+typedef struct empose_train empose_train;
+
+typedef struct {
+    float pose_weight;            /* m_pose_loss_weight         (models.py:58)  */
+    float shape_weight;           /* m_shape_loss_weight        (models.py:57)  */
+    float reprojection_weight;    /* m_reprojection_loss_weight (models.py:376) */
+    float fk_weight;              /* m_fk_loss                  (models.py:51)  */
+} empose_loss_weights;
+
+/* Entry `index` of the layout: state-dict key, kind (0 = parameter -> params/grads, 1 = running statistic ->
+ * bn_buffers), offset and size in floats.  Returns EMPOSE_E_MISSING one past the last entry. */
+int empose_train_layout(const empose_ief_config* cfg, int32_t index, char* name_out, int32_t name_cap, int32_t* kind,
+                        int64_t* offset, int64_t* numel);
+int empose_train_sizes(const empose_ief_config* cfg, int64_t* n_params, int64_t* n_buffers);
+
+/* `tensors`: as for empose_ief_create (state dict + "sub.*").  params / grads / bn_buffers are DEVICE pointers that
+ * stay valid for the lifetime of the context (bn_buffers may be NULL when batch_norm = 0).  Dropout is not
+ * applied (the released configurations train with p = 0, configuration.py:168,176). */
+int empose_train_create(const empose_ief_config* cfg, const empose_tensor* tensors, int32_t n_tensors, float* params,
+                        float* grads, float* bn_buffers, empose_train** out);
+void empose_train_destroy(empose_train* ctx);
+
+/* Train-mode forward pass from a zero LSTM state (scripts/train.py:146): same inputs / outputs as
+ * empose_ief_forward; BatchNorm uses batch statistics and updates bn_buffers; everything the backward pass
+ * needs is kept inside the context. */
+int empose_train_forward(empose_train* ctx, const float* marker_pos, const float* marker_oris, const float* offset_r,
+                         const float* offset_t, const int32_t* seq_lengths, const float* marker_masks, int32_t B, int32_t F,
+                         float* pose_hat, float* shape_hat, float* joints_hat, const empose_ief_history* history,
+                         void* stream);
+
+/* Losses and parameter gradients of the preceding forward pass.  poses_gt [B][F][66] (root first), shapes_gt [B][10],
+ * joints_gt [B][F][66] or NULL (required when fk_weight > 0).  ADDS to `grads` what the reference leaves in .grad
+ * after forward + backward: d(total_loss) plus, when use_gradient is set, the N reconstruction-energy gradients of
+ * the forward pass (models.py:576).  loss_vals: HOST float[5] = pose, shape, reconstruction, fk, total_loss
+ * (models.py:676-680).  Synchronises the stream (the reference does, too). */
+int empose_train_backward(empose_train* ctx, const float* poses_gt, const float* shapes_gt, const float* joints_gt,
+                          const empose_loss_weights* weights, float* loss_vals, void* stream);
+int64_t empose_train_last_launch_count(const empose_train* ctx);
 
 /* Optional timing of the tensor-core GEMM executor: while enabled, every executor launch is bracketed by
  * CUDA events on its stream (TF32 mode only).  empose_ief_profile_read waits for them, returns the summed

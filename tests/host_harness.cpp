@@ -20,8 +20,8 @@ struct HostSub {
 template <typename T>
 static void run(const HostSub& h, int n_frames, const float* theta, const float* beta, const float* off_r,
                 const float* off_t, const float* meas_pos, const float* meas_ori, const int* active, int use_pos,
-                int use_ori, const float* coef, int want_grad, double* sensor_pos, double* sensor_ori, double* joints,
-                double* g_theta, double* g_beta, double* verts) {
+                int use_ori, const float* coef, int want_grad, float sensor_weight, const float* joints_gt, float joint_weight,
+                double* sensor_pos, double* sensor_ori, double* joints, double* g_theta, double* g_beta, double* verts) {
     SubModel m;
     m.n_verts = h.n_verts; m.vp_dim = h.vp_dim; m.n_faces = h.n_faces; m.max_degree = h.max_degree; m.n_skin = h.n_skin;
     m.v_template = h.v_template; m.shapedirs = h.shapedirs; m.j0 = h.j0; m.jdirs = h.jdirs;
@@ -31,7 +31,7 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
     m.n_vj = h.n_vj; m.vj_ptr = h.vj_ptr; m.jvj_ptr = h.jvj_ptr;
     m.vinc_ptr = h.vinc_ptr; m.vinc_item = h.vinc_item; m.vinc_code = h.vinc_code;
     ResidualSpec spec;
-    spec.use_pos = use_pos; spec.use_ori = use_ori;
+    spec.use_pos = use_pos; spec.use_ori = use_ori; spec.weight = sensor_weight;
     for (int s = 0; s < kSensors; ++s) spec.sensor_active[s] = active[s];
     bool use_static = h.use_static_tree != 0;
     for (int j = 0; j < kJoints; ++j) use_static = use_static && (h.parents[j] == smpl_parent(j));
@@ -72,6 +72,7 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
         for (int i = 0; i < 66; ++i) joints[f * 66 + i] = double(st.gpos[i / 3][i % 3]);
         if (verts) for (int i = 0; i < h.n_verts * 3; ++i) verts[f * h.n_verts * 3 + i] = double(st.x[i]);
         if (!want_grad) continue;
+        if (joints_gt) phase_joint_residual(st, joints_gt + f * kPoseDim, T(joint_weight), 0, 1);
         phase_skin_bwd_chunks(m, st, 0, 1);
         phase_skin_bwd_reduce(m, st, 0, 1);
         phase_skin_bwd_verts(m, st, 0, 1);
@@ -81,8 +82,8 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
             for (int i = 0; i < h.n_verts * 3; ++i) acc += T(h.posedirs[k * h.vp_dim + i]) * st.dx[i];
             dpf[k] = acc;
         }
-        if (use_static) phase_chain_bwd_static(st, 0, 1); else phase_chain_bwd(m, st, 0, 1);
-        phase_chain_bwd_local(m, st, 0, 1);
+        if (use_static) phase_chain_bwd_static(st, 0, 1, joints_gt != nullptr); else phase_chain_bwd(m, st, 0, 1, joints_gt != nullptr);
+        phase_chain_bwd_local(m, st, 0, 1, joints_gt != nullptr);
         std::vector<T> gt(kPoseDim), gb(kBetas);
         phase_finish_theta(st, T(coef[f]), dpf.data(), gt.data(), 0, 1);
         phase_finish_beta(m, st, T(coef[f]), gb.data(), 0, 1);
@@ -94,14 +95,15 @@ static void run(const HostSub& h, int n_frames, const float* theta, const float*
 extern "C" int host_frame_eval(const HostSub* h, int n_frames, const float* theta, const float* beta,
                                const float* off_r, const float* off_t, const float* meas_pos, const float* meas_ori,
                                const int* active, int use_pos, int use_ori, const float* coef, int want_grad,
-                               int use_double, double* sensor_pos, double* sensor_ori, double* joints, double* g_theta,
+                               int use_double, float sensor_weight, const float* joints_gt, float joint_weight,
+                               double* sensor_pos, double* sensor_ori, double* joints, double* g_theta,
                                double* g_beta, double* verts) {
     if (h->vp_dim > kMaxVp || h->max_degree > kMaxDegree || h->n_vj > kMaxVj) return -1;
     if (use_double)
         run<double>(*h, n_frames, theta, beta, off_r, off_t, meas_pos, meas_ori, active, use_pos, use_ori, coef,
-                    want_grad, sensor_pos, sensor_ori, joints, g_theta, g_beta, verts);
+                    want_grad, sensor_weight, joints_gt, joint_weight, sensor_pos, sensor_ori, joints, g_theta, g_beta, verts);
     else
         run<float>(*h, n_frames, theta, beta, off_r, off_t, meas_pos, meas_ori, active, use_pos, use_ori, coef,
-                   want_grad, sensor_pos, sensor_ori, joints, g_theta, g_beta, verts);
+                   want_grad, sensor_weight, joints_gt, joint_weight, sensor_pos, sensor_ori, joints, g_theta, g_beta, verts);
     return 0;
 }

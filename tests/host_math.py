@@ -36,7 +36,8 @@ def _lib():
 
 
 def frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef, use_pos=True, use_ori=True,
-               want_grad=True, use_double=False, static_tree=True):
+               want_grad=True, use_double=False, static_tree=True, sensor_weight=1.0, joints_gt=None,
+               joint_weight=0.0):
     """Run the per-frame math on the host.  All per-frame inputs are (n, ...) float32 arrays."""
     keep = []
     hs = HostSub()
@@ -61,9 +62,11 @@ def frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef,
            'g_theta': np.zeros((n, 66)), 'g_beta': np.zeros((n, 10)), 'verts': np.zeros((n, d['n_verts'], 3))}
     fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    jgt = None if joints_gt is None else f32(joints_gt)
     rc = _lib().host_frame_eval(ctypes.byref(hs), n, fp(theta), fp(beta), fp(off_r), fp(off_t), fp(meas_pos),
                                 fp(meas_ori), active.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(use_pos),
-                                int(use_ori), fp(coef), int(want_grad), int(use_double), dp(out['sensor_pos']),
+                                int(use_ori), fp(coef), int(want_grad), int(use_double), ctypes.c_float(sensor_weight),
+                                None if jgt is None else fp(jgt), ctypes.c_float(joint_weight), dp(out['sensor_pos']),
                                 dp(out['sensor_ori']), dp(out['joints']), dp(out['g_theta']), dp(out['g_beta']),
                                 dp(out['verts']))
     assert rc == 0

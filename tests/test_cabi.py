@@ -75,10 +75,32 @@ def test_state_dict_keys_match_reference_layout(smpl_npz, n_markers, rnn_init):
     assert n_params == int(gold['n_trainable_params'])
 
 
-def test_training_mode_is_refused(smpl_npz):
+def test_training_refuses_cpu_tensors(smpl_npz):
+    """No CPU fallback in training either: the train-mode forward needs CUDA tensors."""
     net = util.build_module(smpl_npz).train()
-    with pytest.raises(NotImplementedError):
-        net(None)
+    p = synthetic.synth_window_params(2, 4, seed=3)
+    z = torch.zeros
+    batch = util.DuckBatch(z(2, 4, 36), z(2, 4, 108), torch.from_numpy(p['offset_r']), torch.from_numpy(p['offset_t']),
+                           torch.from_numpy(p['seq_lengths']))
+    with pytest.raises(native.EmposeError):
+        net(batch)
+
+
+def test_training_layout_covers_every_trainable_tensor(smpl_npz):
+    """empose_train_layout: one flat vector holds exactly the reference's trainable tensors (README.md:228 count)."""
+    for n_markers, rnn_init in ((6, True), (12, True), (12, False)):
+        net = util.build_module(smpl_npz, n_markers=n_markers, num_iterations=2, rnn_init=rnn_init)
+        entries, n_params, n_buffers = native.train_layout(net._native_config(0))
+        params = {k: v for k, v in net.named_parameters() if not k.startswith('smpl.')}
+        got = {name: numel for name, kind, off, numel in entries if kind == 0}
+        assert got == {k: v.numel() for k, v in params.items()}
+        bufs = {k: v.numel() for k, v in net.named_buffers() if 'running_' in k}
+        assert {name: numel for name, kind, off, numel in entries if kind == 1} == bufs
+        spans = sorted((off, off + numel) for name, kind, off, numel in entries if kind == 0)
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= n_params
+        assert all(off % 4 == 0 for off, _ in spans)
+        if n_markers == 6 and rnn_init:
+            assert sum(got.values()) + 169 == 5721419
 
 
 def test_submodel_arrays_are_complete(smpl_npz):

@@ -88,3 +88,29 @@ def test_rest_pose_known_answer(sub, oracle_smpl):
     np.testing.assert_allclose(out['verts'][0], oracle_smpl.v_template.numpy()[ids], atol=1e-6, rtol=0)
     rest = (oracle_smpl.j_regressor @ oracle_smpl.v_template).numpy()[:22]
     np.testing.assert_allclose(out['joints'][0], rest, atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize('static_tree', [True, False])
+def test_weighted_reverse_pass_with_joint_term_matches_autograd(sub, oracle_smpl, topology, static_tree):
+    """Training form of the reverse pass: w_s * sensor residual + w_j * sum_j ||J_j - Jgt_j|| (models.py:657-674)."""
+    n = 5
+    theta, beta, off_r, off_t = _case(n, seed=7)
+    rng = np.random.RandomState(10)
+    pose, shape, pos, ori, joints = _oracle(oracle_smpl, topology, theta, beta, off_r, off_t)
+    meas_pos = pos.detach().numpy() + 0.01 * rng.standard_normal((n, 12, 3))
+    meas_ori = ori.detach().numpy() + 0.05 * rng.standard_normal((n, 12, 3, 3))
+    joints_gt = (joints.detach().numpy() + 0.02 * rng.standard_normal((n, 22, 3))).astype(np.float32)
+    coef = rng.uniform(0.5, 2.0, size=n)
+    w_s, w_j = 0.002, 0.1
+    dp = pos - torch.from_numpy(meas_pos)
+    dr = (ori - torch.from_numpy(meas_ori)).reshape(n, 12, 9)
+    dj = joints - torch.from_numpy(joints_gt).double()
+    energy = (w_s * (torch.sqrt((dp * dp).sum(-1)).sum(-1) + torch.sqrt((dr * dr).sum(-1)).sum(-1)) +
+              w_j * torch.sqrt((dj * dj).sum(-1)).sum(-1)) * torch.from_numpy(coef)
+    g_pose, g_shape = torch.autograd.grad(energy.sum(), [pose, shape])
+    out = host_math.frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori.reshape(n, 12, 9), np.ones(12), coef,
+                               use_double=True, static_tree=static_tree, sensor_weight=w_s,
+                               joints_gt=joints_gt.reshape(n, 66), joint_weight=w_j)
+    tol = 2e-5 * max(float(g_pose.abs().max()), 1.0)
+    np.testing.assert_allclose(out['g_theta'], g_pose.numpy(), atol=tol, rtol=0)
+    np.testing.assert_allclose(out['g_beta'], g_shape.numpy(), atol=tol, rtol=0)
