@@ -239,6 +239,10 @@ struct JobBook {        // jobs + tensor maps of one plan
     // appends one job per N tile of `W`; `proto` carries the epilogue fields (n_begin/n_count/maps are filled here)
     int add(const PackedMatrix& W, const ASrc& a0, const ASrc& a1, GemmJob proto, int m_rows, int dep, JobRange* range) {
         if (range->count == 0) range->begin = (int)jobs.size();
+        if (range->begin + range->count != (int)jobs.size()) {      // a launch runs jobs [begin, begin + count)
+            set_last_error("internal error: the jobs of a range must be added contiguously");
+            return EMPOSE_E_ARG;
+        }
         for (int t = 0; t < W.n_tiles; ++t) {
             GemmJob j = proto;
             j.a_ptr[0] = a0.ptr; j.a_stride[0] = a0.stride; j.a_k[0] = a0.k;

@@ -151,8 +151,13 @@ struct MlpRun {
     std::vector<JobRange> bwd_dx;                                  // [layer] (layer >= 1): da = dz_l W_l
 };
 
+// a weight-gradient GEMM, recorded while the plan is built and turned into jobs at the end (the jobs of one launch
+// must be contiguous in the job array)
+struct DwSpec { float* aT; int64_t ldT; int m_rows; float* wT; int n_in; int k; float* grad; int group; };
+
 struct TrainPlan {
     int B = 0, F = 0, R = 0;
+    std::vector<DwSpec> dw_specs;
     Arena arena;
     JobBook book;
     int64_t ldT = 0, ldT_iter = 0;           // row pitch of transposed [*][R] / [*][N*R] operands
@@ -302,13 +307,23 @@ GemmJob plain_proto(float* out, int64_t out_stride, int n_valid, bool round) {
     return linear_proto(dummy, round, out, out_stride, n_valid);
 }
 
-// jobs accumulating dW[out][in] += A^T-operand . W-operand over K rows
-int add_dw(TrainPlan& pl, float* aT, int64_t ldT, int m_rows, float* wT, int n_in, int k, float* grad, JobRange* range) {
-    PackedMatrix W = operand_view(wT, n_in, ldT, k);
-    GemmJob proto = plain_proto(grad, n_in, n_in, false);
-    proto.res = grad;
-    proto.res_stride = n_in;
-    return pl.book.add(W, ASrc{aT, ldT, k, m_rows}, ASrc{}, proto, m_rows, -1, range);
+// jobs accumulating dW[out][in] += A^T-operand . W-operand over K rows; group 0: 512-row outputs (hidden layers),
+// 1: outputs of at most 128 rows (output layers, heads), 2: LSTM (4H rows)
+void add_dw(TrainPlan& pl, float* aT, int64_t ldT, int m_rows, float* wT, int n_in, int k, float* grad, int group) {
+    pl.dw_specs.push_back(DwSpec{aT, ldT, m_rows, wT, n_in, k, grad, group});
+}
+int emit_dw_jobs(TrainPlan& pl) {
+    JobRange* ranges[3] = {&pl.dw512, &pl.dw_small, &pl.dw_lstm};
+    for (int g = 0; g < 3; ++g)
+        for (const DwSpec& d : pl.dw_specs) {
+            if (d.group != g) continue;
+            PackedMatrix W = operand_view(d.wT, d.n_in, d.ldT, d.k);
+            GemmJob proto = plain_proto(d.grad, d.n_in, d.n_in, false);
+            proto.res = d.grad;
+            proto.res_stride = d.n_in;
+            EMPOSE_TRY(pl.book.add(W, ASrc{d.aT, d.ldT, d.k, d.m_rows}, ASrc{}, proto, d.m_rows, -1, ranges[g]));
+        }
+    return EMPOSE_OK;
 }
 
 int build_mlp_run(empose_train* t, TrainPlan& pl, const TrainMlp& net, int S, const float* X, int64_t x_ld, int x_k,
@@ -352,8 +367,8 @@ int build_mlp_run(empose_train* t, TrainPlan& pl, const TrainMlp& net, int S, co
     for (int l = 0; l < nl; ++l) {
         const LinearSite& s = net.lay->layers[l];
         float* wT = l == 0 ? const_cast<float*>(XT) : r.aT[l - 1];
-        if (l == nl - 1) EMPOSE_TRY(add_dw(pl, r.DT, ldT, n_out, wT, s.n_in, (int)M, t->grads + s.w, &pl.dw_small));
-        else EMPOSE_TRY(add_dw(pl, r.dzT[l], ldT, H, wT, s.n_in, (int)M, t->grads + s.w, &pl.dw512));
+        if (l == nl - 1) add_dw(pl, r.DT, ldT, n_out, wT, s.n_in, (int)M, t->grads + s.w, 1);
+        else add_dw(pl, r.dzT[l], ldT, H, wT, s.n_in, (int)M, t->grads + s.w, 0);
     }
     (void)rnd;
     return EMPOSE_OK;
@@ -455,7 +470,13 @@ int build_plan(empose_train* t, int B, int F, TrainPlan** out) {
                 proto.c_seq_out = pl.cseq[l] + (size_t)tt * H;
                 proto.c_seq_stride = (int64_t)F * H;
                 EMPOSE_TRY(pl.book.add(t->lstm_fw[l], a0, a1, proto, B, -1, &pl.lstm_diag[d]));
-                // backward step of the same cell: [dh_rec | dx] = dgates_t . [W_hh | W_ih]
+            }
+        // backward step of every cell: [dh_rec | dx] = dgates_t . [W_hh | W_ih]  (a separate loop: the jobs of one
+        // launch must be contiguous in the job array)
+        for (int d = 0; d < F + L - 1; ++d)
+            for (int l = 0; l < L; ++l) {
+                const int tt = d - l;
+                if (tt < 0 || tt >= F) continue;
                 if (tt == 0 && l == 0) continue;
                 GemmJob bp = plain_proto(pl.dh_rec[l], H, l == 0 ? H : 2 * H, false);
                 if (l > 0) { bp.split = H; bp.out2 = pl.dx[l - 1] + (size_t)tt * H; bp.out2_stride = (int64_t)F * H; }
@@ -470,12 +491,12 @@ int build_plan(empose_train* t, int B, int F, TrainPlan** out) {
         EMPOSE_TRY(pl.book.add(t->heads_bw, ASrc{pl.d_init_masked, kInitLd, kInitBetaCol + kBetas, R}, ASrc{}, hd, R, -1, &pl.heads_dx));
         // dW of the heads and of the LSTM
         const Layout& LY = t->layout;
-        EMPOSE_TRY(add_dw(pl, pl.d_initT, pl.ldT, kPoseDim, pl.hT[L - 1], H, R, t->grads + LY.head_wp, &pl.dw_small));
-        EMPOSE_TRY(add_dw(pl, pl.d_initT + (size_t)kInitBetaCol * pl.ldT, pl.ldT, kBetas, pl.hT[L - 1], H, R, t->grads + LY.head_ws, &pl.dw_small));
+        add_dw(pl, pl.d_initT, pl.ldT, kPoseDim, pl.hT[L - 1], H, R, t->grads + LY.head_wp, 1);
+        add_dw(pl, pl.d_initT + (size_t)kInitBetaCol * pl.ldT, pl.ldT, kBetas, pl.hT[L - 1], H, R, t->grads + LY.head_ws, 1);
         for (int l = 0; l < L; ++l) {
-            EMPOSE_TRY(add_dw(pl, pl.dgT[l], pl.ldT, 4 * H, pl.hprevT[l], H, R, t->grads + LY.lstm.whh[l], &pl.dw_lstm));
-            if (l == 0) EMPOSE_TRY(add_dw(pl, pl.dgT[l], pl.ldT, 4 * H, pl.xinT, ctx->in_size, R, t->grads + LY.lstm.wih[l], &pl.dw_lstm));
-            else EMPOSE_TRY(add_dw(pl, pl.dgT[l], pl.ldT, 4 * H, pl.hT[l - 1], H, R, t->grads + LY.lstm.wih[l], &pl.dw_lstm));
+            add_dw(pl, pl.dgT[l], pl.ldT, 4 * H, pl.hprevT[l], H, R, t->grads + LY.lstm.whh[l], 2);
+            if (l == 0) add_dw(pl, pl.dgT[l], pl.ldT, 4 * H, pl.xinT, ctx->in_size, R, t->grads + LY.lstm.wih[l], 2);
+            else add_dw(pl, pl.dgT[l], pl.ldT, 4 * H, pl.hT[l - 1], H, R, t->grads + LY.lstm.wih[l], 2);
         }
     } else {
         EMPOSE_TRY(A.alloc_n((size_t)operand_rows(ctx->in_size) * pl.ldT, &pl.xinT, true));
@@ -497,6 +518,7 @@ int build_plan(empose_train* t, int B, int F, TrainPlan** out) {
         GemmJob proto_t = plain_proto(pl.dpf, kPoseFeatPad, kPoseFeatPad, false);
         EMPOSE_TRY(pl.book.add(ctx->pbt, ASrc{pl.dvp, vp, vp, R}, ASrc{}, proto_t, R, -1, &pl.pbt));
     }
+    EMPOSE_TRY(emit_dw_jobs(pl));
     EMPOSE_TRY(pl.book.finalize(A));
     *out = plp.get();
     t->plan = std::move(plp);
@@ -557,7 +579,9 @@ int mlp_backward(empose_train* t, TrainPlan& pl, MlpRun& r, bool transpose_x, cu
         EMPOSE_TRY(launch_bn_bwd_reduce(r.da, H, r.z[l], H, R, S, H, r.mean[l], r.invstd[l], gamma, beta, alpha, pl.stat_sums, s));
         EMPOSE_TRY(launch_bn_param_grads(pl.stat_sums, S, H, bn ? G + site.gamma : nullptr, bn ? G + site.beta : nullptr, G + site.alpha, s));
         EMPOSE_TRY(launch_bn_bwd_apply(r.da, H, r.z[l], H, R, S, H, r.mean[l], r.invstd[l], gamma, beta, alpha, pl.stat_sums, rnd, r.dz, H, s));
-        EMPOSE_TRY(launch_col_sum(r.dz, H, M, H, pl.col_scratch, G + site.b, nullptr, s));
+        // A bias in front of a BatchNorm has an analytically zero gradient (the batch mean removes it; the reference holds
+        // ~1e-8 of rounding noise there): nothing is added.  Without BatchNorm it is the column sum of dz.
+        if (!bn) EMPOSE_TRY(launch_col_sum(r.dz, H, M, H, pl.col_scratch, G + site.b, nullptr, s));
         EMPOSE_TRY(launch_transpose(r.dz, H, M, H, 0, 1, 0, r.dzT[l], ldT, s));
         EMPOSE_TRY(launch_transpose(r.a[l], H, M, H, 0, 1, 0, r.aT[l], ldT, s));     // operand of dW_{l+1}
         t->launches += 7;

@@ -91,7 +91,8 @@ def test_training_step_matches_oracle_and_reference(dev, smpl_npz, oracle_smpl, 
         w = g_want.reshape(-1).numpy()
         norm = float(np.sqrt((w * w).sum()))
         err = float(np.sqrt(((g - w) ** 2).sum()))
-        rel = err / (norm + 1e-6 * np.sqrt(w.size))
+        # floor: tensors whose gradient is analytically zero (biases in front of a BatchNorm) hold ~1e-8 noise in the oracle
+        rel = err / (norm + 1e-5 * np.sqrt(w.size))
         pos = sample_positions(key, w.size)
         ref_err = float(np.abs(g[pos] - gold['g/' + key + '/samples']).max() / (np.abs(gold['g/' + key + '/samples']).max() + 1e-6))
         rows.append((key, rel, ref_err, norm))
