@@ -1,6 +1,6 @@
 """Benchmark of the LGD hot path: frames/s, LGD-RNN, 12 sensors, N=4, 32-frame windows (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--windows B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--windows B] [--workload infer|train]
 
 * default arm: the B200 path.  A "step" is one pass of ``IterativeErrorFeedback.forward`` over one batch
   of synthetic windows per GPU (BASELINE config 3: 4096 windows x 32 frames).  ``value`` is whole-job
@@ -10,6 +10,8 @@
 * ``--impl reference``: the reference's own CPU implementation on the host cores.  In the build
   container that is the UNMODIFIED reference (``/root/reference`` through ``oracle.ref_shims``); on the
   GPU box, where the reference tree does not exist, it is the oracle restatement (``oracle/``).
+* ``--workload train`` (BASELINE config 5, not the headline): one training step = zero_grad, train-mode forward,
+  backward, ONE NCCL all-reduce of the flat gradient vector (N > 1), Adam step; 512 windows per GPU by default.
 Under torchrun every rank drives its own GPU over its own shard of windows (no data-path collective:
 windows are independent); NCCL is used for the barrier and the max-over-ranks time.
 """
@@ -300,25 +302,168 @@ def run_b200(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+class _TrainBatch(object):
+    """The slice of the reference's AMASSBatch that forward / backward read (data.py:304-309, 433-459)."""
+
+    def __init__(self, inp, poses, shapes, joints):
+        self.inp = inp
+        self.seq_lengths = inp['seq_lengths']
+        self.poses_root, self.poses_body = poses[:, :, :3].contiguous(), poses[:, :, 3:].contiguous()
+        self.shapes, self.joints_gt, self.marker_masks = shapes, joints, None
+        self.batch_size, self.seq_length = poses.shape[0], poses.shape[1]
+
+    def get_inputs(self, sf=None, ef=None, **kwargs):
+        i = self.inp
+        return {'marker_pos': i['marker_pos'], 'marker_oris': i['marker_oris'], 'offset_r': i['offset_r'],
+                'offset_t': i['offset_t'], 'marker_masks': None}
+
+
+TRAIN_FLAGS = dict(m_fk_loss=0.1, m_pose_loss_weight=10.0, m_reprojection_loss_weight=0.01, lr=5e-4)   # README.md:221
+TRAIN_METRIC = 'frames/sec LGD-RNN-12 N=4 ws=32 training step (fwd + bwd + grad all-reduce + Adam)'
+
+
+def cpu_train_pass(n_windows, seed=123):
+    """One CPU training step (oracle restatement: forward, both backward passes; no optimiser) on n_windows windows."""
+    from empose_b200 import synthetic
+    from oracle import ief as oracle_ief
+    from oracle import sensors, smplh_lbs
+    from oracle import train as oracle_train
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import util
+    npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0)
+    smpl = smplh_lbs.SmplhModel(npz, num_betas=10, dtype=torch.float32)
+    smpl64 = smplh_lbs.SmplhModel(npz, num_betas=10, dtype=torch.float64)
+    topo = sensors.sensor_topology(smpl.faces.numpy())
+    params = synthetic.synth_window_params(n_windows, FRAMES, seed=seed)
+    inp = util.oracle_inputs_from_params(smpl64, topo, params, seed=seed)
+    poses, shapes = torch.from_numpy(params['poses']), torch.from_numpy(params['shapes'])
+    with torch.no_grad():
+        r = n_windows * FRAMES
+        _, _, joints = oracle_ief.project_sensors(smpl, topo, poses.reshape(r, 66), shapes.unsqueeze(1).repeat(1, FRAMES, 1).reshape(r, 10),
+                                                  torch.eye(3).repeat(r, 12, 1, 1), torch.zeros(r, 12, 3))
+    cfg = oracle_ief.IefConfig(n_markers=12, num_iterations=4, rnn_init=True)
+    sd = util.torch_state_dict(synthetic.synth_state_dict(seed=0, n_markers=12, rnn_init=True))
+    return lambda: oracle_train.ief_train_step(cfg, sd, smpl, topo, poses_gt=poses, shapes_gt=shapes,
+                                               joints_gt=joints.reshape(n_windows, FRAMES, 66), pose_weight=10.0, shape_weight=1.0,
+                                               r_weight=0.01, fk_weight=0.1, **inp)
+
+
+def run_b200_train(args, rank, local_rank, world):
+    """BASELINE config 5: LGD-RNN-12 training step, windows sharded over the GPUs, one gradient all-reduce."""
+    from empose_b200 import lib, synthetic
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from empose_b200.helpers.configuration import lgd_config
+    from empose_b200.nn.models import IterativeErrorFeedback
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0)
+    cfg = lgd_config(n_markers=12, num_iterations=4, rnn_init=True, hidden_size=512, window_size=FRAMES, **TRAIN_FLAGS)
+    net = IterativeErrorFeedback(cfg, SMPLLayer(npz).to(dtype=torch.float32), precision=lib.PRECISION_TF32)
+    sd = net.state_dict()
+    for k, v in synthetic.synth_state_dict(seed=0, n_markers=12, rnn_init=True).items():
+        sd[k] = torch.from_numpy(np.asarray(v))
+    net.load_state_dict(sd, strict=True)
+    net = net.to(device)
+    b = args.windows
+    net.eval()
+    ctx = net.native_context(device)
+    inp = synth_device_inputs(ctx, b, device, seed=2000 + rank)
+    p = synthetic.synth_window_params(b, FRAMES, seed=2000 + rank)
+    poses = torch.from_numpy(p['poses']).to(device)
+    shapes = torch.from_numpy(p['shapes']).to(device)
+    r = b * FRAMES
+    eye = torch.eye(3, device=device).repeat(r, 12, 1, 1)
+    _, _, joints = ctx.sensor_project(poses.reshape(r, 66), shapes.unsqueeze(1).repeat(1, FRAMES, 1).reshape(r, 10), eye,
+                                      torch.zeros(r, 12, 3, device=device))
+    batch = _TrainBatch(inp, poses, shapes, joints.reshape(b, FRAMES, 66))
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=cfg.lr)
+    losses = []
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        out = net(batch)
+        _, vals = net.backward(batch, out)
+        if dist is not None:
+            net.allreduce_gradients(average=True)
+        opt.step()
+        losses.append(vals['total_loss'])
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(step, args.steps, barrier)
+    if dist is not None:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.stop_flag.set()
+    sampler.join()
+    launches = net._trainer.last_launch_count
+    value = world * b * FRAMES * args.steps / (ms / 1000.0)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fn = cpu_train_pass(args.ref_windows)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        cpu = {'value': args.ref_windows * FRAMES / dt, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': '%d windows x %d frames, one training step (forward + gradients) after 1 warm-up' % (args.ref_windows, FRAMES)}
+    if rank == 0:
+        n_grad = int(net.flat_gradients().numel())
+        print(json.dumps({
+            'metric': TRAIN_METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
+            'config': {'workload': 'LGD-RNN-12 N=4 ws=32 TRAINING step, %d windows per GPU (BASELINE config 5)' % b,
+                       'windows_per_gpu': b, 'frames_per_window': FRAMES, 'global_batch_windows': world * b,
+                       'parallelism': 'data parallel: windows sharded, one NCCL all-reduce of the %d-float flat gradient' % n_grad,
+                       'optimizer': 'torch.optim.Adam on views of the flat parameter vector', 'loss_weights': TRAIN_FLAGS,
+                       'l2': 'activations kept for the backward pass (~%.1f GB) exceed the 126 MB L2' % (r * 4 * 512 * 4 * 44 / 1e9)},
+            'clocks': sampler.summary(), 'gpu_launches': int(launches * args.steps),
+            'loss_first_last': [losses[0], losses[-1]], 'cpu_baseline': cpu}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--windows', type=int, default=4096, help='windows per GPU (BASELINE config 3: 4096)')
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train'])
+    ap.add_argument('--windows', type=int, default=None, help='windows per GPU (inference: 4096 = BASELINE config 3; training: 512)')
     ap.add_argument('--ref-windows', type=int, default=16, help='windows per step of the CPU reference arm / baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.windows is None:
+        args.windows = 4096 if args.workload == 'infer' else 512
     if args.impl == 'reference':
         run_reference(args, rank)
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)')
-    run_b200(args, rank, local_rank, world)
+    if args.workload == 'train':
+        run_b200_train(args, rank, local_rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
 
 
 if __name__ == '__main__':

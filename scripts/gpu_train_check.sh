@@ -13,3 +13,7 @@ if [ "$1" = "all" ]; then
   timeout -s KILL 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "rc=$?" >> gpurun_out/bench.log
   tail -n 3 gpurun_out/bench.log
 fi
+if [ "$1" = "bench" ] || [ "$2" = "bench" ]; then
+  timeout -s KILL 600 python bench.py --workload train --steps 10 --warmup 3 > gpurun_out/bench_train.log 2>&1; echo "rc=$?" >> gpurun_out/bench_train.log
+  tail -n 3 gpurun_out/bench_train.log
+fi
