@@ -216,10 +216,11 @@ class IterativeErrorFeedback(nn.Module):
     def allreduce_gradients(self, average=True):
         """Data-parallel training: ONE all-reduce over the flat gradient vector."""
         import torch.distributed as dist
-        g = self._flat['grads']
-        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        from empose_b200 import sharding
         if average:
-            g.div_(dist.get_world_size())
+            sharding.allreduce_mean_(self._flat['grads'], dist)
+        else:
+            dist.all_reduce(self._flat['grads'], op=dist.ReduceOp.SUM)
 
     def _attach_gradients(self):
         """``optimizer.zero_grad()`` sets ``.grad`` to None by default: re-attach (zeroed) views of the flat vector."""

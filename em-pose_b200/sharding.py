@@ -3,7 +3,20 @@
 Inference needs no data-path collective: in eval mode nothing couples two windows (BatchNorm uses running statistics,
 the shape mean is intra-window -- reference ``models.py:529-535`` -- and the LSTM state is per window), so a batch is
 cut into contiguous shards, every rank runs its shard, and results are concatenated in rank order.
+
+Training is data parallel over windows: every rank computes the gradients of its shard into ONE flat vector and a
+single all-reduce (sum, then divide by the world size) gives every rank the same averaged gradient -- DDP semantics.
+Without BatchNorm that equals the whole-batch gradient for equal shard sizes (all losses are batch means,
+``models.py:646-674``); with BatchNorm in train mode the batch statistics are per shard (no SyncBN), as with
+``torch.nn.parallel.DistributedDataParallel`` around the reference model.
 """
+
+
+def allreduce_mean_(flat, dist_module, group=None):
+    """In-place average of a flat gradient vector over all ranks: exactly one collective."""
+    dist_module.all_reduce(flat, op=dist_module.ReduceOp.SUM, group=group)
+    flat.div_(dist_module.get_world_size(group))
+    return flat
 
 
 def shard_range(n_windows, rank, world_size):

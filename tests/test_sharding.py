@@ -50,6 +50,54 @@ def _worker(rank, world, port, npz, out_dir):
     dist.destroy_process_group()
 
 
+def _train_worker(rank, world, port, npz, out_dir):
+    """Data-parallel training step on CPU: per-shard oracle gradients -> ONE all-reduce of the flat vector."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+    import util
+    from empose_b200 import sharding, synthetic
+    from oracle import ief as oracle_ief
+    from oracle import sensors, smplh_lbs
+    from oracle import train as oracle_train
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    smpl = smplh_lbs.SmplhModel(npz, num_betas=10, dtype=torch.float64)
+    topo = sensors.sensor_topology(smpl.faces.numpy())
+    n_windows, n_frames = 4, 5
+    params = synthetic.synth_window_params(n_windows, n_frames, seed=5, ragged=False, offsets=True)
+    inp = util.oracle_inputs_from_params(smpl, topo, params, seed=5)
+    kw = dict(n_markers=12, rnn_init=True, hidden_size=64, rnn_hidden_size=32, batch_norm=False)
+    cfg = oracle_ief.IefConfig(n_markers=12, num_iterations=2, rnn_init=True, hidden_size=64, rnn_hidden_size=32,
+                               no_batch_norm=True)
+    sd = util.torch_state_dict(synthetic.synth_state_dict(seed=0, **kw), torch.float64)
+    full = {k: (v.double() if v is not None and v.is_floating_point() else v) for k, v in inp.items()}
+    full['poses_gt'] = torch.from_numpy(params['poses']).double()
+    full['shapes_gt'] = torch.from_numpy(params['shapes']).double()
+    full['joints_gt'] = torch.zeros(n_windows, n_frames, 66, dtype=torch.float64)
+    weights = dict(pose_weight=10.0, shape_weight=1.0, r_weight=0.01, fk_weight=0.1)
+    local = oracle_train.ief_train_step(cfg, sd, smpl, topo, **sharding.shard_batch(full, rank, world), **weights)
+    names = sorted(local['grads'])
+    flat = torch.cat([local['grads'][k].reshape(-1) for k in names])
+    sharding.allreduce_mean_(flat, dist)                       # the single collective of the training step
+    if rank == 0:
+        whole = oracle_train.ief_train_step(cfg, sd, smpl, topo, **full, **weights)
+        want = torch.cat([whole['grads'][k].reshape(-1) for k in names])
+        np.save(os.path.join(out_dir, 'train_err.npy'), np.array([(flat - want).abs().max().item(), want.abs().max().item()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_equals_whole_batch(smpl_npz, tmp_path):
+    """Without BatchNorm and with equal shards, the all-reduced mean of the shard gradients is the whole-batch gradient."""
+    port = _free_port()
+    mp.spawn(_train_worker, args=(2, port, smpl_npz, str(tmp_path)), nprocs=2, join=True)
+    err, scale = np.load(os.path.join(str(tmp_path), 'train_err.npy'))
+    assert err < 1e-10 * max(scale, 1.0), (err, scale)
+
+
 def test_shard_range_covers_everything():
     sys.path.insert(0, ROOT)
     from empose_b200 import sharding
