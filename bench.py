@@ -91,7 +91,7 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def build_b200_model(device):
+def build_b200_model(device, precision='fp16'):
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from empose_b200 import lib, synthetic
     from empose_b200.bodymodels.smpl import SMPLLayer
@@ -99,7 +99,8 @@ def build_b200_model(device):
     from empose_b200.nn.models import IterativeErrorFeedback
     npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0)
     cfg = lgd_config(n_markers=12, num_iterations=4, rnn_init=True, hidden_size=512, window_size=FRAMES)
-    net = IterativeErrorFeedback(cfg, SMPLLayer(npz).to(dtype=torch.float32), precision=lib.PRECISION_TF32)
+    prec = {'fp16': lib.PRECISION_FP16, 'tf32': lib.PRECISION_TF32, 'fp32': lib.PRECISION_FP32}[precision]
+    net = IterativeErrorFeedback(cfg, SMPLLayer(npz).to(dtype=torch.float32), precision=prec)
     sd = net.state_dict()
     for k, v in synthetic.synth_state_dict(seed=0, n_markers=12, rnn_init=True).items():
         sd[k] = torch.from_numpy(np.asarray(v))
@@ -207,7 +208,7 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=device)
-    net = build_b200_model(device)
+    net = build_b200_model(device, args.precision)
     ctx = net.native_context(device)
     b = args.windows
     inp = synth_device_inputs(ctx, b, device, seed=1000 + rank)
@@ -266,8 +267,9 @@ def run_b200(args, rank, local_rank, world):
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / peaks['bf16_tflops_sustained'], 'traffic': NCU_TRAFFIC_BYTES,
                 'traffic_note': NCU_TRAFFIC_NOTE,
-                'kernel': 'gemm_tc_kernel (tcgen05.mma kind::tf32)', 'peak_source': peaks['source'] + ' bf16 dense, sustained',
-                'frac_of_tf32_rate': achieved / (peaks['bf16_tflops_sustained'] / 2.0),
+                'kernel': 'gemm_tc_kernel (tcgen05.mma kind::f16 for the learned layers, kind::tf32 x3 for the pose blend)'
+                          if args.precision == 'fp16' else 'gemm_tc_kernel (tcgen05.mma kind::tf32)',
+                'peak_source': peaks['source'] + ' bf16 dense, sustained',
                 'launches_per_step': gemm_launches / prof_steps, 'avg_launch_ms': gemm_ms / max(gemm_launches, 1),
                 'kernel_share_of_step': (gemm_ms / prof_steps) / (ms / args.steps),
                 'algorithmic_flop_per_launch': FLOP_PER_FRAME * frames_per_step * prof_steps / max(gemm_launches, 1)}
@@ -286,12 +288,15 @@ def run_b200(args, rank, local_rank, world):
     if rank == 0:
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32',
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision,
             'data': 'synthetic',
             'config': {'workload': 'LGD-RNN (2x512 LSTM init), 12 sensors, N=4, ws=32, %d windows per GPU (BASELINE config 3)' % b,
                        'windows_per_gpu': b, 'frames_per_window': FRAMES, 'parallelism': 'windows sharded, no collective',
                        'l2': 'per-step working set (~3 GB of activations and features) exceeds the 126 MB L2; no flush needed',
-                       'arithmetic': 'tf32 tensor cores (tcgen05), fp32 accumulate; pose blend 3xTF32; per-frame SMPL math fp32'},
+                       'arithmetic': {'fp16': 'learned layers: fp16 operands on tcgen05 (kind::f16), fp32 accumulate in TMEM; pose blend 3xTF32; '
+                                              'per-frame SMPL math, LSTM cell state and all outputs fp32',
+                                      'tf32': 'tf32 tensor cores (tcgen05), fp32 accumulate; pose blend 3xTF32; per-frame SMPL math fp32',
+                                      'fp32': 'FFMA executor, fp32 everywhere (parity mode)'}[args.precision]},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / e2e_steps, 'api': 'empose_ief_forward_host (pinned host buffers)'},
@@ -446,6 +451,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='infer', choices=['infer', 'train'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'tf32', 'fp32'], help='inference arithmetic of the learned layers')
     ap.add_argument('--windows', type=int, default=None, help='windows per GPU (inference: 4096 = BASELINE config 3; training: 512)')
     ap.add_argument('--ref-windows', type=int, default=16, help='windows per step of the CPU reference arm / baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -1,6 +1,7 @@
 // Shared device/host utilities for the empose_b200 CUDA sources.
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -39,6 +40,21 @@ __device__ __forceinline__ float tanh_f(float x) {
     float e = __expf(2.0f * x);
     return 1.0f - 2.0f / (e + 1.0f);
 }
+
+// How a value that feeds a later GEMM is stored: exact fp32 (FFMA executor), tf32-rounded fp32 (kind::tf32 operands)
+// or fp16 (kind::f16 operands; the buffer then holds __half elements and strides count elements).
+enum OperandMode : int { OPERAND_F32 = 0, OPERAND_TF32 = 1, OPERAND_F16 = 2 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void store_operand(float* base, int64_t idx, float v, int mode) {
+    if (mode == OPERAND_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+    else base[idx] = (mode == OPERAND_TF32) ? round_tf32(v) : v;
+}
+__device__ __forceinline__ float load_operand(const float* base, int64_t idx, int mode) {
+    return mode == OPERAND_F16 ? __half2float(reinterpret_cast<const __half*>(base)[idx]) : base[idx];
+}
+#endif
+inline size_t operand_bytes(int mode) { return mode == OPERAND_F16 ? 2 : 4; }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

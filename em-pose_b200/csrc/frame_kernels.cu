@@ -48,9 +48,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(PrepareParams p) {
     }
     p.meas[idx] = v;
     if (dst >= 0) {
-        const float r = maybe_round(v, p.round_out);
-        if (p.xin) p.xin[(int64_t)row * p.in_stride + dst] = r;
-        if (p.xiter) p.xiter[(int64_t)row * p.iter_stride + dst] = r;
+        if (p.xin) store_operand(p.xin, (int64_t)row * p.in_stride + dst, v, p.operand_mode);
+        if (p.xiter) store_operand(p.xiter, (int64_t)row * p.iter_stride + dst, v, p.operand_mode);
     }
     if (c == 0) {
         const int b = row / p.F, f = row % p.F;
@@ -96,7 +95,7 @@ __global__ void __launch_bounds__(128) update_kernel(UpdateParams p) {
             p.beta[row * kBetas + k] = v;
             if (p.hist_shape) p.hist_shape[row * kBetas + k] = v;
         }
-        if (p.xiter) p.xiter[row * p.iter_stride + p.in_size + c] = maybe_round(v, p.round_out);
+        if (p.xiter) store_operand(p.xiter, row * p.iter_stride + p.in_size + c, v, p.operand_mode);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.F * (kJoints - 1); i += blockDim.x) {
@@ -244,7 +243,7 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p) {
     if (i >= (int64_t)p.R * 32) return;
     const int64_t row = i >> 5;
     const int j = (int)(i & 31);
-    float* xg = p.xiter ? p.xiter + row * p.iter_stride + p.in_size + 76 : nullptr;
+    const int64_t xg = row * p.iter_stride + p.in_size + 76;      // first gradient column of this row in xiter
     if (j < kJoints) {
         float g[3] = {p.gtheta_part[row * kPoseDim + j * 3], p.gtheta_part[row * kPoseDim + j * 3 + 1],
                       p.gtheta_part[row * kPoseDim + j * 3 + 2]};
@@ -259,23 +258,38 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p) {
         }
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
-            if (xg) xg[j * 3 + e] = maybe_round(g[e], p.round_out);
+            if (p.xiter) store_operand(p.xiter, xg + j * 3 + e, g[e], p.operand_mode);
             if (p.g_theta_out) p.g_theta_out[row * kPoseDim + j * 3 + e] = g[e];
         }
     } else if (j < kJoints + kBetas) {
         const int k = j - kJoints;
         const float g = p.gbeta[row * kBetas + k];
-        if (xg) xg[kPoseDim + k] = maybe_round(g, p.round_out);
+        if (p.xiter) store_operand(p.xiter, xg + kPoseDim + k, g, p.operand_mode);
         if (p.g_beta_out) p.g_beta_out[row * kBetas + k] = g;
     }
 }
 
-__global__ void gather_last_kernel(const float* __restrict__ seq, float* __restrict__ out, int B, int F, int H) {
+__global__ void gather_last_kernel(const float* __restrict__ seq, float* __restrict__ out, int B, int F, int H, int mode) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * H) return;
     const int64_t b = i / H;
     const int u = (int)(i % H);
-    out[i] = seq[(b * F + (F - 1)) * H + u];
+    out[i] = load_operand(seq, (b * F + (F - 1)) * H + u, mode);
+}
+
+__global__ void to_operand_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int mode) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_operand(dst, i, src[i], mode);
+}
+
+__global__ void convert_2d_kernel(const float* __restrict__ src, int64_t src_ld, int64_t rows, int cols, float* __restrict__ dst,
+                                  int64_t dst_ld, int mode, int to_operand) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols;
+    const int c = (int)(i % cols);
+    if (to_operand) store_operand(dst, r * dst_ld + c, src[r * src_ld + c], mode);
+    else dst[r * dst_ld + c] = load_operand(src, r * src_ld + c, mode);
 }
 
 inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
@@ -328,8 +342,28 @@ int launch_post(const PostParams& p, cudaStream_t s) {
     return EMPOSE_OK;
 }
 
-int launch_gather_last(const float* seq, float* out, int B, int F, int H, cudaStream_t s) {
-    gather_last_kernel<<<blocks_for((int64_t)B * H, 256), 256, 0, s>>>(seq, out, B, F, H);
+int launch_gather_last(const float* seq, float* out, int B, int F, int H, int operand_mode, cudaStream_t s) {
+    gather_last_kernel<<<blocks_for((int64_t)B * H, 256), 256, 0, s>>>(seq, out, B, F, H, operand_mode);
+    EMPOSE_CUDA_TRY(cudaGetLastError());
+    return EMPOSE_OK;
+}
+
+int launch_to_operand_2d(const float* src, int64_t src_ld, int64_t rows, int cols, float* dst, int64_t dst_ld, int operand_mode,
+                         cudaStream_t s) {
+    convert_2d_kernel<<<blocks_for(rows * cols, 256), 256, 0, s>>>(src, src_ld, rows, cols, dst, dst_ld, operand_mode, 1);
+    EMPOSE_CUDA_TRY(cudaGetLastError());
+    return EMPOSE_OK;
+}
+
+int launch_from_operand_2d(const float* src, int64_t src_ld, int64_t rows, int cols, float* dst, int64_t dst_ld, int operand_mode,
+                           cudaStream_t s) {
+    convert_2d_kernel<<<blocks_for(rows * cols, 256), 256, 0, s>>>(src, src_ld, rows, cols, dst, dst_ld, operand_mode, 0);
+    EMPOSE_CUDA_TRY(cudaGetLastError());
+    return EMPOSE_OK;
+}
+
+int launch_to_operand(const float* src, float* dst, int64_t n, int operand_mode, cudaStream_t s) {
+    to_operand_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, dst, n, operand_mode);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

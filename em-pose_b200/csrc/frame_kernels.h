@@ -19,8 +19,8 @@ struct PrepareParams {
     int slot_of_sensor[kSensors];   // position of each sensor in the network input, -1 if not fed
     int use_pos, use_ori, n_pos;    // n_pos = number of position columns in the network input
     int in_size;
-    int in_stride, iter_stride; // row pitches of xin / xiter in floats (multiples of 4: TMA needs 16-byte aligned rows)
-    int round_out;
+    int in_stride, iter_stride; // row pitches of xin / xiter in elements (TMA needs 16-byte aligned rows)
+    int operand_mode;           // OperandMode of xin / xiter (exact fp32, tf32-rounded fp32 or fp16 elements)
     float* meas;                // [R][144] exact copy [pos | ori]
     float* xin;                 // [R][in_stride]   (may be null)
     float* xiter;               // [R][iter_stride] columns [0, in_size) written (may be null)
@@ -38,7 +38,7 @@ struct UpdateParams {
     int first;                  // 1: theta = dtheta, beta = (mean of) dbeta  (initial estimate)
     int average_shape;
     int B, F;
-    int round_out;
+    int operand_mode;           // OperandMode of xiter
     float* xiter;               // [R][iter_stride] or null: columns [in_size, in_size+76) receive theta | beta
     int in_size, iter_stride;
     float* pf;                  // [R][pf_stride] pose features vec(R_1..R_21 - I); split: [hi(192) | lo(192)]
@@ -88,7 +88,7 @@ struct PostParams {
     const float* gbeta;         // [R][10]
     const float* coef;          // [R]
     int R;
-    int round_out;
+    int operand_mode;           // OperandMode of xiter
     float* xiter;               // [R][iter_stride]: columns [in_size+76, in_size+152) receive g_theta | g_beta
     int in_size, iter_stride;
     float* g_theta_out;         // optional exact copies (tests), may be null
@@ -96,7 +96,15 @@ struct PostParams {
 };
 int launch_post(const PostParams& p, cudaStream_t s);
 
-// gather the last time step of a [B][F][H] sequence buffer into [B][H]
-int launch_gather_last(const float* seq, float* out, int B, int F, int H, cudaStream_t s);
+// gather the last time step of a [B][F][H] sequence buffer (elements per `operand_mode`) into fp32 [B][H]
+int launch_gather_last(const float* seq, float* out, int B, int F, int H, int operand_mode, cudaStream_t s);
+
+// dst (an operand buffer of `operand_mode` elements) = src (fp32), n elements
+int launch_to_operand(const float* src, float* dst, int64_t n, int operand_mode, cudaStream_t s);
+// 2-D variants with row pitches (in elements): fp32 -> operand and operand -> fp32
+int launch_to_operand_2d(const float* src, int64_t src_ld, int64_t rows, int cols, float* dst, int64_t dst_ld, int operand_mode,
+                         cudaStream_t s);
+int launch_from_operand_2d(const float* src, int64_t src_ld, int64_t rows, int cols, float* dst, int64_t dst_ld, int operand_mode,
+                           cudaStream_t s);
 
 }  // namespace empose

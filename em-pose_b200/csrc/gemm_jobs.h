@@ -20,7 +20,8 @@ namespace empose {
 
 constexpr int kTileM = 128;       // rows per tile (UMMA M)
 constexpr int kMaxTileN = 256;    // columns per job (UMMA N), multiple of 16
-constexpr int kChunkK = 32;       // floats per K chunk = one 128-byte swizzle row
+constexpr int kChunkK = 32;       // fp32 / tf32 elements per K chunk = one 128-byte swizzle row
+constexpr int kChunkKHalf = 64;   // fp16 elements per K chunk (same 128 bytes)
 
 enum EpilogueKind : int32_t { EPI_LINEAR = 0, EPI_LSTM = 1 };
 
@@ -31,6 +32,8 @@ struct GemmJob {
     int32_t a_k[2];          // real K extent of the segment (0 = unused); padded to kChunkK in W
     int32_t a_map[2];        // tensor-map slot (tcgen05 executor)
     int32_t a_scratch[2];    // 1: the segment is CTA-local scratch: rows are indexed by 128 * blockIdx.x, not by the tile
+    int32_t in_half;         // 1: A and W hold fp16 elements (kind::f16, 64-element K chunks); strides / extents count elements
+    int32_t out_half;        // 1: `out` (and, for LSTM jobs, h_prev) hold fp16 elements
     int32_t out_scratch;     // 1: the output is CTA-local scratch (tcgen05 executor only)
     // ---- W operand: packed [n_total][w_ld], K-major, segment s starts at column w_koff[s] ----
     const float* w_ptr;
@@ -106,7 +109,61 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
 #pragma unroll
         for (int i = 0; i < 32; ++i) bias[i] = 0.0f;
     }
-    if (j.epi == EPI_LINEAR) {
+    if (j.epi == EPI_LINEAR && j.out_half && !j.res && n0 + 32 <= j.n_valid && n0 + 32 <= j.split) {
+        // fp16 activations: the 32 columns of a lane are 64 contiguous bytes of its row -> four 16-byte stores straight
+        // from registers (two full 32-byte sectors per lane), no shared-memory transpose
+        if (j.mask_rows && row < j.m_rows && (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window]) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+        }
+        const float alpha = j.has_act ? j.prelu_alpha : 1.0f;
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float y0 = v[2 * i] + bias[2 * i], y1 = v[2 * i + 1] + bias[2 * i + 1];
+            y0 = y0 > 0.0f ? y0 : alpha * y0;
+            y1 = y1 > 0.0f ? y1 : alpha * y1;
+            const __half2 h = __floats2half2_rn(y0, y1);
+            packed[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        if (row < j.m_rows) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(j.out) + (int64_t)row * j.out_stride + j.out_col0 + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+    } else if (j.epi == EPI_LSTM && j.out_half) {
+        // fp16 hidden state: a lane owns 8 consecutive units of its row -> c is two 16-byte accesses, h one
+        const int unit0 = lstm_unit_of_packed(n0);
+        if (row < j.m_rows) {
+            __half* hout = reinterpret_cast<__half*>(j.out) + (int64_t)row * j.out_stride + unit0;
+            if (j.t < j.seq_len[row]) {
+                float4* cp = reinterpret_cast<float4*>(j.c_state + (int64_t)row * j.hidden + unit0);
+                const float4 c0v = cp[0], c1v = cp[1];
+                const float c_old[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+                float c_new[8];
+                uint32_t hp[4];
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    float h2[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float gi = v[k + q] + bias[k + q], gf = v[8 + k + q] + bias[8 + k + q];
+                        const float gg = v[16 + k + q] + bias[16 + k + q], go = v[24 + k + q] + bias[24 + k + q];
+                        c_new[k + q] = sigmoid_f(gf) * c_old[k + q] + sigmoid_f(gi) * tanh_f(gg);
+                        h2[q] = sigmoid_f(go) * tanh_f(c_new[k + q]);
+                    }
+                    const __half2 h = __floats2half2_rn(h2[0], h2[1]);
+                    hp[k / 2] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                cp[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
+                cp[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
+                *reinterpret_cast<uint4*>(hout) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            } else {      // padded step: the state is carried (packed-sequence semantics); c stays where it is
+                const __half* hprev = reinterpret_cast<const __half*>(j.h_prev) + (int64_t)row * j.h_prev_stride + unit0;
+                *reinterpret_cast<uint4*>(hout) = *reinterpret_cast<const uint4*>(hprev);
+            }
+        }
+    } else if (j.epi == EPI_LINEAR) {
         if (j.mask_rows && row < j.m_rows && (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window]) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.0f;
@@ -137,16 +194,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
         int stride;
         if (n < j.split) { dst = j.out + j.out_col0 + n; stride = (int)j.out_stride; }
         else { dst = j.out2 + (n - j.split); stride = (int)j.out2_stride; }
-        dst += (int64_t)row0 * stride;
         const int rows = col_ok ? min(32, j.m_rows - row0) : 0;
+        if (j.out_half) {                              // fp16 output on an edge chunk (rare): element-wise stores
+            __half* hd = reinterpret_cast<__half*>(j.out) + j.out_col0 + n + (int64_t)row0 * stride;
+            for (int r = 0; r < rows; ++r) hd[(int64_t)r * stride] = __float2half_rn(stage[r * kStageLd + lane]);
+        } else {
+            dst += (int64_t)row0 * stride;
 #pragma unroll
-        for (int r0 = 0; r0 < 32; r0 += 8) {          // batches of 8: loads first, then stores, few live registers
-            float o[8];
+            for (int r0 = 0; r0 < 32; r0 += 8) {          // batches of 8: loads first, then stores, few live registers
+                float o[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) o[r] = stage[(r0 + r) * kStageLd + lane];
+                for (int r = 0; r < 8; ++r) o[r] = stage[(r0 + r) * kStageLd + lane];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r0 + r < rows) dst[(r0 + r) * stride] = o[r];
+                for (int r = 0; r < 8; ++r)
+                    if (r0 + r < rows) dst[(r0 + r) * stride] = o[r];
+            }
         }
         __syncwarp();
     } else {  // EPI_LSTM: 8 hidden units x 4 gates per chunk

@@ -102,6 +102,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
 }
 
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major tile whose rows are 128 bytes (32 fp32) apart, stored
 // with the 128-byte swizzle TMA produces: 8-row groups are 1024 bytes apart (SBO), LBO is unused.
 // Field layout: cute::UMMA::SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
@@ -116,10 +126,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major,
-// N>>3 at bit 17, M>>4 at bit 24.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10) or f16 (0, 0), both
+// K-major, N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc(int n, int half) {
+    const uint32_t fmt = half ? 0u : ((2u << 7) | (2u << 10));
+    return (1u << 4) | fmt | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, float (&v)[32]) {
@@ -138,8 +149,10 @@ __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ int job_chunk_k(const GemmJob& j) { return j.in_half ? kChunkKHalf : kChunkK; }
 __device__ __forceinline__ int job_k_chunks(const GemmJob& j) {
-    return (j.a_k[0] + kChunkK - 1) / kChunkK + (j.a_k[1] + kChunkK - 1) / kChunkK;
+    const int ck = job_chunk_k(j);
+    return (j.a_k[0] + ck - 1) / ck + (j.a_k[1] + ck - 1) / ck;
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -195,9 +208,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         }
                         __threadfence_block();
                     }
-                    const uint32_t w_bytes = (uint32_t)job.n_count * kChunkK * 4u;
+                    const uint32_t w_bytes = (uint32_t)job.n_count * kChunkK * 4u;        // 128 bytes per row in either type
+                    const int ck = job_chunk_k(job);
                     for (int seg = 0; seg < 2; ++seg) {
-                        const int chunks = (job.a_k[seg] + kChunkK - 1) / kChunkK;
+                        const int chunks = (job.a_k[seg] + ck - 1) / ck;
                         for (int kc = 0; kc < chunks; ++kc) {
                             mbar_wait(&ctl->empty[stage], phase ^ 1u);
                             uint8_t* a_dst = smem + stage * kStageBytes;
@@ -206,9 +220,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                 mbar_arrive(&ctl->full[stage]);
                             } else {
                                 mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
-                                tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * kChunkK,
+                                tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * ck,
                                             job.a_scratch[seg] ? (int)blockIdx.x * kTileM : m0);
-                                tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * kChunkK,
+                                tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * ck,
                                             job.n_begin);
                             }
                             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -229,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     mbar_wait(&ctl->tmem_empty[buf], ((seq >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * kMaxTileN;
-                    const uint32_t idesc = make_idesc(job.n_count);
+                    const int half = job.in_half;
+                    const uint32_t idesc = make_idesc(job.n_count, half);
                     const int chunks = job_k_chunks(job);
                     for (int kc = 0; kc < chunks; ++kc) {
                         mbar_wait(&ctl->full[stage], phase);
@@ -242,9 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         } else {
 #pragma unroll
                             for (int k = 0; k < kChunkK / 8; ++k) {
-                                // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
-                                umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                                          (kc | k) != 0 ? 1u : 0u);
+                                // advance 8 tf32 / 16 f16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
+                                if (half) umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                                else umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
                             }
                             umma_commit(&ctl->empty[stage]);
                         }
@@ -320,23 +335,25 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-int tc_encode_map(void* out_map, const float* base, int64_t row_stride_floats, int k_extent, int64_t rows,
-                  int box_rows) {
+int tc_encode_map(void* out_map, const float* base, int64_t row_stride_elems, int k_extent, int64_t rows,
+                  int box_rows, int half) {
+    const int64_t row_stride_floats = row_stride_elems;      // (name kept for the messages below)
+    const int elem = half ? 2 : 4;
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
         return EMPOSE_E_CUDA;
     }
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((row_stride_floats * 4) & 15) || box_rows < 1 || box_rows > 256) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((row_stride_floats * elem) & 15) || box_rows < 1 || box_rows > 256) {
         set_last_error("tensor map: base / stride must be 16-byte aligned and the box at most 256 rows");
         return EMPOSE_E_ARG;
     }
     cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)row_stride_floats * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
-    cuuint32_t elem[2] = {1, 1};
-    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                    const_cast<float*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride_floats * elem};
+    cuuint32_t box[2] = {(cuuint32_t)(half ? kChunkKHalf : kChunkK), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));

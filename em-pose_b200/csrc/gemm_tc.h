@@ -10,10 +10,11 @@ namespace empose {
 
 constexpr int kTensorMapBytes = 128;   // sizeof(CUtensorMap)
 
-// Encode a 2-D fp32 tensor map {k_extent, rows} with row stride `row_stride_floats`, box {32, box_rows},
-// 128-byte swizzle, zero fill out of bounds.  `out_map` is HOST memory of kTensorMapBytes.
-int tc_encode_map(void* out_map, const float* base, int64_t row_stride_floats, int k_extent, int64_t rows,
-                  int box_rows);
+// Encode a 2-D tensor map {k_extent, rows} of fp32 (half = 0) or fp16 (half = 1) elements with row stride
+// `row_stride_elems`, box {128 bytes, box_rows}, 128-byte swizzle, zero fill out of bounds.  `out_map` is HOST
+// memory of kTensorMapBytes.
+int tc_encode_map(void* out_map, const float* base, int64_t row_stride_elems, int k_extent, int64_t rows,
+                  int box_rows, int half);
 
 // Run jobs [job_begin, job_begin + job_count) of the device array `d_jobs` on `m_tiles` row tiles.
 // `jobs_per_item` consecutive jobs form one work item executed by one CTA in order.

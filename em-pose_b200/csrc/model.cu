@@ -75,14 +75,16 @@ int build_mlp_pair(empose_ief* ctx, Plan& pl, const MlpPacked& mp, const MlpPack
             const PackedMatrix& W = nets[c]->layers[l];
             ASrc a0, none;
             const bool scratch = ctx->round;
-            if (l == 0) a0 = ASrc{X, x_stride, x_k, R};
-            else a0 = ASrc{pl.act[c][(l - 1) & 1], hidden, hidden, pl.act_rows};
+            const int hf = ctx->op_half;
+            if (l == 0) a0 = ASrc{X, x_stride, x_k, R, hf};
+            else a0 = ASrc{pl.act[c][(l - 1) & 1], hidden, hidden, pl.act_rows, hf};
             GemmJob proto;
             int m_rows = R;
             if (l == nl - 1) {
                 proto = linear_proto(W, false, finals[c], final_n[c], final_n[c]);
             } else {
-                proto = linear_proto(W, ctx->round, pl.act[c][l & 1], hidden, hidden);
+                proto = linear_proto(W, ctx->op_mode == OPERAND_TF32, pl.act[c][l & 1], hidden, hidden);
+                proto.out_half = hf;
                 if (ctx->cfg.skip_connections && l >= 2 && (l % 2) == 0) {   // end of a LinearLayers block
                     proto.res = pl.act[c][l & 1];                            // block input lives in the buffer being overwritten
                     proto.res_stride = hidden;
@@ -111,8 +113,16 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
     Arena& A = pl.arena;
     const size_t Rz = (size_t)R;
     EMPOSE_TRY(A.alloc_n(Rz * 144, &pl.meas));
-    EMPOSE_TRY(A.alloc_n(Rz * ctx->in_stride, &pl.xin, true));
-    EMPOSE_TRY(A.alloc_n(Rz * ctx->iter_stride, &pl.xiter, true));
+    const int hf = ctx->op_half;
+    const size_t esz = hf ? 2 : 4;                 // bytes per element of the MLP / LSTM operand buffers
+    auto alloc_operand = [&](size_t elems, float** out) -> int {
+        void* p;
+        EMPOSE_TRY(A.alloc(elems * esz, &p, true));
+        *out = static_cast<float*>(p);
+        return EMPOSE_OK;
+    };
+    EMPOSE_TRY(alloc_operand(Rz * ctx->in_stride, &pl.xin));
+    EMPOSE_TRY(alloc_operand(Rz * ctx->iter_stride, &pl.xiter));
     EMPOSE_TRY(A.alloc_n(Rz, &pl.coef));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.theta));
     EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.beta));
@@ -134,29 +144,31 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
     // are CTA-local scratch (num_sms tiles, L2-resident); the FFMA executor runs layer by layer over all rows.
     pl.act_rows = ctx->round ? (int64_t)ctx->num_sms * kTileM : (int64_t)R;
     for (int c = 0; c < 2; ++c)
-        for (int q = 0; q < 2; ++q) EMPOSE_TRY(A.alloc_n((size_t)pl.act_rows * hidden, &pl.act[c][q], true));
+        for (int q = 0; q < 2; ++q) EMPOSE_TRY(alloc_operand((size_t)pl.act_rows * hidden, &pl.act[c][q]));
 
     const int m_rows_R = R;
     if (cfg.rnn_init) {
         pl.hseq.resize(L); pl.cstate.resize(L); pl.hinit.resize(L);
         for (int l = 0; l < L; ++l) {
-            EMPOSE_TRY(A.alloc_n(Rz * H, &pl.hseq[l]));
+            EMPOSE_TRY(alloc_operand(Rz * H, &pl.hseq[l]));
             EMPOSE_TRY(A.alloc_n((size_t)B * H, &pl.cstate[l], true));
-            EMPOSE_TRY(A.alloc_n((size_t)B * H, &pl.hinit[l], true));
+            EMPOSE_TRY(alloc_operand((size_t)B * H, &pl.hinit[l]));
         }
         pl.lstm_diag.resize(F + L - 1);
         for (int d = 0; d < F + L - 1; ++d)
             for (int l = 0; l < L; ++l) {
                 const int t = d - l;
                 if (t < 0 || t >= F) continue;
-                ASrc a0 = (t == 0) ? ASrc{pl.hinit[l], H, H, B} : ASrc{pl.hseq[l] + (size_t)(t - 1) * H, (int64_t)F * H, H, B};
-                ASrc a1 = (l == 0) ? ASrc{pl.xin + (size_t)t * ctx->in_stride, (int64_t)F * ctx->in_stride, ctx->in_size, B}
-                                   : ASrc{pl.hseq[l - 1] + (size_t)t * H, (int64_t)F * H, H, B};
+                ASrc a0 = (t == 0) ? ASrc{pl.hinit[l], H, H, B, hf}
+                                   : ASrc{operand_at(pl.hseq[l], (size_t)(t - 1) * H, hf), (int64_t)F * H, H, B, hf};
+                ASrc a1 = (l == 0) ? ASrc{operand_at(pl.xin, (size_t)t * ctx->in_stride, hf), (int64_t)F * ctx->in_stride, ctx->in_size, B, hf}
+                                   : ASrc{operand_at(pl.hseq[l - 1], (size_t)t * H, hf), (int64_t)F * H, H, B, hf};
                 GemmJob proto;
                 memset(&proto, 0, sizeof(proto));
                 proto.epi = EPI_LSTM;
                 proto.round_out = ctx->round ? 1 : 0;
-                proto.out = pl.hseq[l] + (size_t)t * H;
+                proto.out_half = hf;
+                proto.out = operand_at(pl.hseq[l], (size_t)t * H, hf);
                 proto.out_stride = (int64_t)F * H;
                 proto.c_state = pl.cstate[l];
                 proto.h_prev = a0.ptr;
@@ -176,7 +188,7 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
         proto.mask_rows = 1;
         proto.seq_len = pl.seq_len;
         proto.frames_per_window = F;
-        EMPOSE_TRY(pl.book.add(ctx->heads, ASrc{pl.hseq[L - 1], H, H, R}, ASrc{}, proto, m_rows_R, -1, &pl.heads));
+        EMPOSE_TRY(pl.book.add(ctx->heads, ASrc{pl.hseq[L - 1], H, H, R, hf}, ASrc{}, proto, m_rows_R, -1, &pl.heads));
     } else {
         EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_init, ctx->shape_init, pl.xin, ctx->in_stride, ctx->in_size, &pl.init_chain));
     }
@@ -225,7 +237,8 @@ int check_config(const empose_ief_config& c) {
             return bad("rnn_hidden_size must make 4H a multiple of 32 and, above 256, of 256");
         if (c.rnn_num_layers < 1 || c.rnn_num_layers > 4) return bad("rnn_num_layers must be 1..4");
     }
-    if (c.precision != EMPOSE_PRECISION_TF32 && c.precision != EMPOSE_PRECISION_FP32) return bad("unknown precision");
+    if (c.precision != EMPOSE_PRECISION_TF32 && c.precision != EMPOSE_PRECISION_FP32 && c.precision != EMPOSE_PRECISION_FP16)
+        return bad("unknown precision");
     return EMPOSE_OK;
 }
 
@@ -345,7 +358,7 @@ int pack_lstm(empose_ief* ctx, const TensorTable& tt) {
         EMPOSE_TRY(tt.get_f32("rnn.lstm.bias_ih" + sfx, {4 * H}, &bih));
         EMPOSE_TRY(tt.get_f32("rnn.lstm.bias_hh" + sfx, {4 * H}, &bhh));
         // packed row n <- torch row gate*H + unit (gate order i,f,g,o; layers.py:114 / torch.nn.LSTM layout)
-        EMPOSE_TRY(pack_matrix(ctx->arena, 4 * H, H, n_in, 32, ctx->round, true, [&](int n) {
+        EMPOSE_TRY(pack_matrix(ctx->arena, 4 * H, H, n_in, 32, ctx->op_mode, true, [&](int n) {
             const int src = lstm_gate_of_packed(n) * H + lstm_unit_of_packed(n);
             return RowSource{whh + (size_t)src * H, wih + (size_t)src * n_in, 1.0, (double)bih[src] + (double)bhh[src]};
         }, &ctx->lstm[l]));
@@ -356,7 +369,7 @@ int pack_lstm(empose_ief* ctx, const TensorTable& tt) {
     EMPOSE_TRY(tt.get_f32("pose_net_init.bias", {kPoseDim}, &bp));
     EMPOSE_TRY(tt.get_f32("shape_net_init.weight", {kBetas, H}, &ws));
     EMPOSE_TRY(tt.get_f32("shape_net_init.bias", {kBetas}, &bs));
-    EMPOSE_TRY(pack_matrix(ctx->arena, kPoseDim + kBetas, H, 0, 16, ctx->round, true, [&](int r) {
+    EMPOSE_TRY(pack_matrix(ctx->arena, kPoseDim + kBetas, H, 0, 16, ctx->op_mode, true, [&](int r) {
         if (r < kPoseDim) return RowSource{wp + (size_t)r * H, nullptr, 1.0, (double)bp[r]};
         return RowSource{ws + (size_t)(r - kPoseDim) * H, nullptr, 1.0, (double)bs[r - kPoseDim]};
     }, &ctx->heads));
@@ -384,7 +397,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
     pp.R = R; pp.F = F;
     for (int i = 0; i < kSensors; ++i) pp.slot_of_sensor[i] = ctx->slot_of_sensor[i];
     pp.use_pos = cfg.use_marker_pos; pp.use_ori = cfg.use_marker_ori; pp.n_pos = ctx->n_pos;
-    pp.in_size = ctx->in_size; pp.in_stride = ctx->in_stride; pp.iter_stride = ctx->iter_stride; pp.round_out = rnd;
+    pp.in_size = ctx->in_size; pp.in_stride = ctx->in_stride; pp.iter_stride = ctx->iter_stride; pp.operand_mode = ctx->op_mode;
     pp.meas = pl.meas; pp.xin = pl.xin; pp.xiter = pl.xiter; pp.coef = pl.coef;
     EMPOSE_TRY(count(launch_prepare(pp, s)));
 
@@ -392,10 +405,10 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         const size_t st_bytes = (size_t)B * H * 4;
         for (int l = 0; l < L; ++l) {
             if (lstm_state && !is_new_sequence) {
-                EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.hinit[l], lstm_state + (size_t)l * B * H, st_bytes, cudaMemcpyDeviceToDevice, s));
+                EMPOSE_TRY(count(launch_to_operand(lstm_state + (size_t)l * B * H, pl.hinit[l], (int64_t)B * H, ctx->op_mode, s)));
                 EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.cstate[l], lstm_state + (size_t)(L + l) * B * H, st_bytes, cudaMemcpyDeviceToDevice, s));
             } else {
-                EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.hinit[l], 0, st_bytes, s));
+                EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.hinit[l], 0, (size_t)B * H * operand_bytes(ctx->op_mode), s));
                 EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.cstate[l], 0, st_bytes, s));
             }
         }
@@ -403,7 +416,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         EMPOSE_TRY(run_jobs(ctx, pl, pl.heads, mt_R, s));
         if (lstm_state)
             for (int l = 0; l < L; ++l) {
-                EMPOSE_TRY(count(launch_gather_last(pl.hseq[l], lstm_state + (size_t)l * B * H, B, F, H, s)));
+                EMPOSE_TRY(count(launch_gather_last(pl.hseq[l], lstm_state + (size_t)l * B * H, B, F, H, ctx->op_mode, s)));
                 EMPOSE_CUDA_TRY(cudaMemcpyAsync(lstm_state + (size_t)(L + l) * B * H, pl.cstate[l], st_bytes, cudaMemcpyDeviceToDevice, s));
             }
     } else {
@@ -415,7 +428,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         memset(&up, 0, sizeof(up));
         up.theta = pl.theta; up.beta = pl.beta; up.dtheta = pl.dtheta; up.dbeta = pl.dbeta;
         up.step = cfg.step_size; up.first = (it == 0); up.average_shape = cfg.average_shape;
-        up.B = B; up.F = F; up.round_out = rnd;
+        up.B = B; up.F = F; up.operand_mode = ctx->op_mode;
         up.xiter = pl.xiter; up.in_size = ctx->in_size; up.iter_stride = ctx->iter_stride; up.pf = pl.pf;
         up.pf_stride = ctx->pf_stride; up.pf_split = rnd;
         if (hist && hist->pose) up.hist_pose = hist->pose + (size_t)it * R * kPoseDim;
@@ -460,7 +473,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
             PostParams po;
             memset(&po, 0, sizeof(po));
             po.theta = pl.theta; po.dpf = pl.dpf; po.gtheta_part = pl.gth_part; po.gbeta = pl.gbeta; po.coef = pl.coef;
-            po.R = R; po.round_out = rnd; po.xiter = pl.xiter; po.in_size = ctx->in_size; po.iter_stride = ctx->iter_stride;
+            po.R = R; po.operand_mode = ctx->op_mode; po.xiter = pl.xiter; po.in_size = ctx->in_size; po.iter_stride = ctx->iter_stride;
             EMPOSE_TRY(count(launch_post(po, s)));
         }
         EMPOSE_TRY(run_jobs(ctx, pl, pl.iter_chain, mt_R, s));
@@ -510,13 +523,15 @@ int empose_ief_create(const empose_ief_config* cfg, const empose_tensor* tensors
     std::unique_ptr<empose_ief> ctx(new empose_ief());
     ctx->cfg = *cfg;
     ctx->num_sms = prop.multiProcessorCount;
-    ctx->round = cfg->precision == EMPOSE_PRECISION_TF32;
+    ctx->round = cfg->precision != EMPOSE_PRECISION_FP32;
+    ctx->op_mode = cfg->precision == EMPOSE_PRECISION_FP32 ? OPERAND_F32 : cfg->precision == EMPOSE_PRECISION_TF32 ? OPERAND_TF32 : OPERAND_F16;
+    ctx->op_half = ctx->op_mode == OPERAND_F16 ? 1 : 0;
     ctx->pf_stride = ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad;
     ctx->n_pos = cfg->use_marker_pos ? 3 * cfg->n_markers : 0;
     ctx->in_size = ctx->n_pos + (cfg->use_marker_ori ? 9 * cfg->n_markers : 0);
     ctx->iter_in = ctx->in_size + kPoseDim + kBetas + (cfg->use_gradient ? kPoseDim + kBetas : 0);
-    ctx->in_stride = round_up(ctx->in_size, 4);
-    ctx->iter_stride = round_up(ctx->iter_in, 4);
+    ctx->in_stride = round_up(ctx->in_size, ctx->op_half ? 8 : 4);        // rows must be 16-byte aligned for TMA
+    ctx->iter_stride = round_up(ctx->iter_in, ctx->op_half ? 8 : 4);
     static const int kConfig6[6] = {0, 1, 2, 6, 7, 11};                     // reference configuration.py:89
     for (int i = 0; i < kSensors; ++i) { ctx->slot_of_sensor[i] = cfg->n_markers == 12 ? i : -1; }
     if (cfg->n_markers == 6) for (int i = 0; i < 6; ++i) ctx->slot_of_sensor[kConfig6[i]] = i;
@@ -529,11 +544,11 @@ int empose_ief_create(const empose_ief_config* cfg, const empose_tensor* tensors
     if (cfg->rnn_init) {
         EMPOSE_TRY(pack_lstm(ctx.get(), tt));
     } else {
-        EMPOSE_TRY(pack_mlp(ctx->arena, tt, "pose_net_init", ctx->in_size, kPoseDim, cfg->hidden_size, cfg->num_layers, bn, ctx->round, &ctx->pose_init));
-        EMPOSE_TRY(pack_mlp(ctx->arena, tt, "shape_net_init", ctx->in_size, kBetas, cfg->hidden_size, cfg->num_layers, bn, ctx->round, &ctx->shape_init));
+        EMPOSE_TRY(pack_mlp(ctx->arena, tt, "pose_net_init", ctx->in_size, kPoseDim, cfg->hidden_size, cfg->num_layers, bn, ctx->op_mode, &ctx->pose_init));
+        EMPOSE_TRY(pack_mlp(ctx->arena, tt, "shape_net_init", ctx->in_size, kBetas, cfg->hidden_size, cfg->num_layers, bn, ctx->op_mode, &ctx->shape_init));
     }
-    EMPOSE_TRY(pack_mlp(ctx->arena, tt, "pose_net_iter", ctx->iter_in, kPoseDim, cfg->hidden_size, cfg->num_layers, bn, ctx->round, &ctx->pose_iter));
-    EMPOSE_TRY(pack_mlp(ctx->arena, tt, "shape_net_iter", ctx->iter_in, kBetas, cfg->hidden_size, cfg->num_layers, bn, ctx->round, &ctx->shape_iter));
+    EMPOSE_TRY(pack_mlp(ctx->arena, tt, "pose_net_iter", ctx->iter_in, kPoseDim, cfg->hidden_size, cfg->num_layers, bn, ctx->op_mode, &ctx->pose_iter));
+    EMPOSE_TRY(pack_mlp(ctx->arena, tt, "shape_net_iter", ctx->iter_in, kBetas, cfg->hidden_size, cfg->num_layers, bn, ctx->op_mode, &ctx->shape_iter));
     *out = ctx.release();
     return EMPOSE_OK;
 }
@@ -675,22 +690,38 @@ static int gemm_engine_run(int32_t precision, const float* A, int64_t lda, const
     choose_tiles(N, 16, &pm);
     Arena arena;
     JobBook book;
-    book.use_tc = precision == EMPOSE_PRECISION_TF32;
+    book.use_tc = precision != EMPOSE_PRECISION_FP32;
+    const int hf = precision == EMPOSE_PRECISION_FP16 ? 1 : 0;
     JobRange range;
+    float* c_half = nullptr;                           // fp16 mode: operands converted here; C goes through an fp16 buffer
+    const int64_t ldc_h = round_up(N, 8);              //            when N is a multiple of 32 (exercises the fp16 epilogue)
+    const bool half_out = hf && (N % 32 == 0);
+    if (hf) {
+        const int64_t k8 = round_up(K, 8);
+        float *a_h, *w_h;
+        EMPOSE_TRY(arena.alloc((size_t)M * k8 * 2, reinterpret_cast<void**>(&a_h), true));
+        EMPOSE_TRY(arena.alloc((size_t)N * k8 * 2, reinterpret_cast<void**>(&w_h), true));
+        EMPOSE_TRY(launch_to_operand_2d(A, lda, M, K, a_h, k8, OPERAND_F16, s));
+        EMPOSE_TRY(launch_to_operand_2d(W, ldw, N, K, w_h, k8, OPERAND_F16, s));
+        A = a_h; lda = k8; W = w_h; ldw = k8;
+        if (half_out) EMPOSE_TRY(arena.alloc((size_t)M * ldc_h * 2, reinterpret_cast<void**>(&c_half), true));
+    }
     float* bias_padded = nullptr;                      // the epilogue reads bias in aligned groups of 32
     if (bias) {
         EMPOSE_TRY(arena.alloc_n((size_t)pm.n_pad + 32, &bias_padded, true));
         EMPOSE_CUDA_TRY(cudaMemcpyAsync(bias_padded, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, s));
     }
-    GemmJob proto = linear_proto(pm, false, C, ldc, N);
+    GemmJob proto = half_out ? linear_proto(pm, false, c_half, ldc_h, N) : linear_proto(pm, false, C, ldc, N);
+    proto.out_half = half_out ? 1 : 0;
+    proto.in_half = hf;
     // the W tensor map describes the caller's matrix directly: K extent K (zero fill beyond), N rows
     for (int t = 0; t < pm.n_tiles; ++t) {
         GemmJob j = proto;
         j.a_ptr[0] = A; j.a_stride[0] = lda; j.a_k[0] = K;
-        EMPOSE_TRY(book.get_map(A, lda, K, M, kTileM, &j.a_map[0]));
+        EMPOSE_TRY(book.get_map(A, lda, K, M, kTileM, hf, &j.a_map[0]));
         j.a_map[1] = -1;
         j.w_ptr = W; j.w_ld = ldw;
-        EMPOSE_TRY(book.get_map(W, ldw, K, N, pm.tile_n, &j.w_map));
+        EMPOSE_TRY(book.get_map(W, ldw, K, N, pm.tile_n, hf, &j.w_map));
         j.n_begin = t * pm.tile_n; j.n_count = pm.tile_n; j.m_rows = M; j.dep = -1; j.bias = bias_padded;
         if (range.count == 0) range.begin = (int)book.jobs.size();
         book.jobs.push_back(j);
@@ -709,6 +740,7 @@ static int gemm_engine_run(int32_t precision, const float* A, int64_t lda, const
         else rc = simt_launch(book.d_jobs, book.jobs.data(), range.begin, range.count, ceil_div(M, kTileM), s, nullptr);
     }
     if (ms_out) cudaEventRecord(e1, s);
+    if (half_out && rc == EMPOSE_OK) rc = launch_from_operand_2d(c_half, ldc_h, M, N, C, ldc, OPERAND_F16, s);
     EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));     // the job array is freed when `arena` goes out of scope
     if (ms_out) {
         float ms = 0.0f;

@@ -108,6 +108,7 @@ struct Arena {
 
 // ---- packed weights -----------------------------------------------------------------------------
 struct PackedMatrix {
+    int half = 0;             // 1: `w` holds fp16 elements (ld, koff, kseg count elements either way)
     float* w = nullptr;       // device [n_pad][ld]
     float* bias = nullptr;    // device [n_pad] or null
     int n = 0, n_pad = 0, tile_n = 0, n_tiles = 0;
@@ -131,12 +132,16 @@ struct RowSource {
     const float* w0; const float* w1; double scale; double bias;
 };
 
+// `mode`: OperandMode of the stored weights (exact fp32, tf32-rounded fp32, fp16)
 template <typename F>
-int pack_matrix(Arena& arena, int n, int k0, int k1, int granule, bool round, bool with_bias, F row_of, PackedMatrix* pm) {
+int pack_matrix(Arena& arena, int n, int k0, int k1, int granule, int mode, bool with_bias, F row_of, PackedMatrix* pm) {
+    const bool round = mode == OPERAND_TF32;
+    const int chunk = mode == OPERAND_F16 ? kChunkKHalf : kChunkK;
     choose_tiles(n, granule, pm);
+    pm->half = mode == OPERAND_F16 ? 1 : 0;
     pm->kseg[0] = k0; pm->kseg[1] = k1;
-    pm->koff[0] = 0; pm->koff[1] = round_up(k0, kChunkK);
-    pm->ld = round_up(k0, kChunkK) + (k1 > 0 ? round_up(k1, kChunkK) : 0);
+    pm->koff[0] = 0; pm->koff[1] = round_up(k0, chunk);
+    pm->ld = round_up(k0, chunk) + (k1 > 0 ? round_up(k1, chunk) : 0);
     std::vector<float> hw((size_t)pm->n_pad * pm->ld, 0.0f), hb((size_t)pm->n_pad + 32, 0.0f);   // bias padded for vector loads
     for (int r = 0; r < n; ++r) {
         RowSource src = row_of(r);
@@ -146,7 +151,15 @@ int pack_matrix(Arena& arena, int n, int k0, int k1, int granule, bool round, bo
         if (round) for (int64_t k = 0; k < pm->ld; ++k) dst[k] = host_round_tf32(dst[k]);
         hb[r] = (float)src.bias;
     }
-    EMPOSE_TRY(arena.upload(hw, &pm->w));
+    if (mode == OPERAND_F16) {
+        std::vector<__half> hh(hw.size());
+        for (size_t i = 0; i < hw.size(); ++i) hh[i] = __float2half_rn(hw[i]);
+        __half* d;
+        EMPOSE_TRY(arena.upload(hh, &d));
+        pm->w = reinterpret_cast<float*>(d);
+    } else {
+        EMPOSE_TRY(arena.upload(hw, &pm->w));
+    }
     if (with_bias) EMPOSE_TRY(arena.upload(hb, &pm->bias));
     return EMPOSE_OK;
 }
@@ -155,7 +168,7 @@ struct MlpPacked { std::vector<PackedMatrix> layers; };   // input, 2*blocks hid
 
 // nn.Linear (+ BatchNorm1d in eval mode folded in double) (+ PReLU slope) -> PackedMatrix
 inline int pack_linear(Arena& arena, const TensorTable& tt, const std::string& lin, const std::string& bn,
-                const std::string& prelu, int n_out, int n_in, bool round, PackedMatrix* pm) {
+                const std::string& prelu, int n_out, int n_in, int mode, PackedMatrix* pm) {
     const float *w, *b, *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
     EMPOSE_TRY(tt.get_f32(lin + ".weight", {n_out, n_in}, &w));
     EMPOSE_TRY(tt.get_f32(lin + ".bias", {n_out}, &b));
@@ -165,7 +178,7 @@ inline int pack_linear(Arena& arena, const TensorTable& tt, const std::string& l
         EMPOSE_TRY(tt.get_f32(bn + ".running_mean", {n_out}, &mu));
         EMPOSE_TRY(tt.get_f32(bn + ".running_var", {n_out}, &var));
     }
-    EMPOSE_TRY(pack_matrix(arena, n_out, n_in, 0, 16, round, true, [&](int r) {
+    EMPOSE_TRY(pack_matrix(arena, n_out, n_in, 0, 16, mode, true, [&](int r) {
         RowSource s{w + (size_t)r * n_in, nullptr, 1.0, (double)b[r]};
         if (g) {   // y = gamma (Wx + b - mean) / sqrt(var + eps) + beta   (eps = 1e-5, torch default used by layers.py:26,57)
             const double sc = (double)g[r] / std::sqrt((double)var[r] + 1e-5);
@@ -185,20 +198,20 @@ inline int pack_linear(Arena& arena, const TensorTable& tt, const std::string& l
 
 // MLP of empose/nn/layers.py:46-77 with the reference's state-dict key layout
 inline int pack_mlp(Arena& arena, const TensorTable& tt, const std::string& prefix, int n_in, int n_out, int hidden, int blocks,
-             bool bn, bool round, MlpPacked* out) {
+             bool bn, int mode, MlpPacked* out) {
     out->layers.clear();
     out->layers.resize(2 + 2 * blocks);
     EMPOSE_TRY(pack_linear(arena, tt, prefix + ".input_to_hidden", bn ? prefix + ".batch_norm" : "", prefix + ".activation_fn",
-                           hidden, n_in, round, &out->layers[0]));
+                           hidden, n_in, mode, &out->layers[0]));
     const int stride = bn ? 4 : 3;
     for (int b = 0; b < blocks; ++b)
         for (int l = 0; l < 2; ++l) {
             const std::string base = prefix + ".hidden_layers." + std::to_string(b) + ".layers.";
             EMPOSE_TRY(pack_linear(arena, tt, base + std::to_string(l * stride), bn ? base + std::to_string(l * stride + 1) : "",
-                                   base + std::to_string(l * stride + (bn ? 2 : 1)), hidden, hidden, round,
+                                   base + std::to_string(l * stride + (bn ? 2 : 1)), hidden, hidden, mode,
                                    &out->layers[1 + 2 * b + l]));
         }
-    EMPOSE_TRY(pack_linear(arena, tt, prefix + ".hidden_to_output", "", "", n_out, hidden, round, &out->layers.back()));
+    EMPOSE_TRY(pack_linear(arena, tt, prefix + ".hidden_to_output", "", "", n_out, hidden, mode, &out->layers.back()));
     return EMPOSE_OK;
 }
 
@@ -206,13 +219,22 @@ inline int pack_mlp(Arena& arena, const TensorTable& tt, const std::string& pref
 struct JobRange { int begin = 0, count = 0, per_item = 1; };
 
 struct MapKey {
-    const void* ptr; int64_t stride; int k; int64_t rows; int box;
+    const void* ptr; int64_t stride; int k; int64_t rows; int box; int half;
     bool operator<(const MapKey& o) const {
-        return std::tie(ptr, stride, k, rows, box) < std::tie(o.ptr, o.stride, o.k, o.rows, o.box);
+        return std::tie(ptr, stride, k, rows, box, half) < std::tie(o.ptr, o.stride, o.k, o.rows, o.box, o.half);
     }
 };
 
-struct ASrc { const float* ptr = nullptr; int64_t stride = 0; int k = 0; int64_t rows = 0; };
+// one K segment of an A operand; strides / extents count elements (fp32, or fp16 when half = 1)
+struct ASrc { const float* ptr = nullptr; int64_t stride = 0; int k = 0; int64_t rows = 0; int half = 0; };
+
+// pointer to element `index` of an operand buffer that holds fp32 (half = 0) or fp16 (half = 1) elements
+inline float* operand_at(float* base, size_t index, int half) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + index * (half ? 2 : 4));
+}
+inline const float* operand_at(const float* base, size_t index, int half) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + index * (half ? 2 : 4));
+}
 
 struct JobBook {        // jobs + tensor maps of one plan
     bool use_tc = false;
@@ -222,15 +244,15 @@ struct JobBook {        // jobs + tensor maps of one plan
     GemmJob* d_jobs = nullptr;
     void* d_maps = nullptr;
 
-    int get_map(const float* ptr, int64_t stride, int k, int64_t rows, int box, int* out) {
+    int get_map(const float* ptr, int64_t stride, int k, int64_t rows, int box, int half, int* out) {
         *out = -1;
         if (!use_tc) return EMPOSE_OK;
-        MapKey key{ptr, stride, k, rows, box};
+        MapKey key{ptr, stride, k, rows, box, half};
         auto it = map_index.find(key);
         if (it != map_index.end()) { *out = it->second; return EMPOSE_OK; }
         const int idx = (int)(maps.size() / kTensorMapBytes);
         maps.resize(maps.size() + kTensorMapBytes);
-        EMPOSE_TRY(tc_encode_map(&maps[(size_t)idx * kTensorMapBytes], ptr, stride, k, rows, box));
+        EMPOSE_TRY(tc_encode_map(&maps[(size_t)idx * kTensorMapBytes], ptr, stride, k, rows, box, half));
         map_index[key] = idx;
         *out = idx;
         return EMPOSE_OK;
@@ -247,11 +269,16 @@ struct JobBook {        // jobs + tensor maps of one plan
             GemmJob j = proto;
             j.a_ptr[0] = a0.ptr; j.a_stride[0] = a0.stride; j.a_k[0] = a0.k;
             j.a_ptr[1] = a1.ptr; j.a_stride[1] = a1.stride; j.a_k[1] = a1.k;
-            EMPOSE_TRY(get_map(a0.ptr, a0.stride, a0.k, a0.rows, kTileM, &j.a_map[0]));
+            if (a0.half != W.half || (a1.k > 0 && a1.half != W.half)) {
+                set_last_error("internal error: A and W operands of a job must have the same element type");
+                return EMPOSE_E_ARG;
+            }
+            j.in_half = W.half;
+            EMPOSE_TRY(get_map(a0.ptr, a0.stride, a0.k, a0.rows, kTileM, W.half, &j.a_map[0]));
             j.a_map[1] = -1;
-            if (a1.k > 0) EMPOSE_TRY(get_map(a1.ptr, a1.stride, a1.k, a1.rows, kTileM, &j.a_map[1]));
+            if (a1.k > 0) EMPOSE_TRY(get_map(a1.ptr, a1.stride, a1.k, a1.rows, kTileM, W.half, &j.a_map[1]));
             j.w_ptr = W.w; j.w_ld = W.ld; j.w_koff[0] = W.koff[0]; j.w_koff[1] = W.koff[1];
-            EMPOSE_TRY(get_map(W.w, W.ld, (int)W.ld, W.n_pad, W.tile_n, &j.w_map));
+            EMPOSE_TRY(get_map(W.w, W.ld, (int)W.ld, W.n_pad, W.tile_n, W.half, &j.w_map));
             j.n_begin = t * W.tile_n;
             j.n_count = W.tile_n;
             j.m_rows = m_rows;
@@ -322,7 +349,9 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
     int num_sms = 148;
     int in_size = 0, iter_in = 0, n_pos = 0;
     int in_stride = 0, iter_stride = 0;   // row pitches of the network-input buffers (multiples of 4 floats for TMA)
-    bool round = true;         // TF32 mode
+    bool round = true;         // a tensor-core mode (TF32 or FP16): pose-blend operands are tf32-rounded, tcgen05 executor
+    int op_mode = OPERAND_TF32;   // storage of the MLP / LSTM / heads operands: OPERAND_F32, OPERAND_TF32 or OPERAND_F16
+    int op_half = 0;           // op_mode == OPERAND_F16
     int pf_stride = kPoseFeatPad;   // floats per row of the pose-feature buffer (2x when split hi|lo)
     Arena arena;
     SubModel sub;

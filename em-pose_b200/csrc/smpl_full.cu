@@ -173,7 +173,7 @@ int empose_smpl_create(const empose_tensor* tensors, int32_t n_tensors, int32_t 
     if (prop.major != 10) { set_last_error("empose_b200 is built for sm_100a (B200) only"); return EMPOSE_E_CUDA; }
     std::unique_ptr<empose_smpl> ctx(new empose_smpl());
     ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
-    ctx->round = precision == EMPOSE_PRECISION_TF32;
+    ctx->round = precision != EMPOSE_PRECISION_FP32;      // TF32 and FP16 modes both run the pose blend as error-compensated tf32
     ctx->pf_stride = ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad;
     TensorTable tt{tensors, n_tensors};
     const int32_t* dims;

@@ -607,7 +607,7 @@ int gradient_tail(empose_train* t, TrainPlan& pl, int it, float* xiter, cudaStre
     PostParams po;
     memset(&po, 0, sizeof(po));
     po.theta = pl.theta; po.dpf = pl.dpf; po.gtheta_part = pl.gth_part; po.gbeta = pl.gbeta; po.coef = pl.coef;
-    po.R = pl.R; po.round_out = ctx->round ? 1 : 0; po.xiter = xiter; po.in_size = ctx->in_size; po.iter_stride = ctx->iter_stride;
+    po.R = pl.R; po.operand_mode = ctx->op_mode; po.xiter = xiter; po.in_size = ctx->in_size; po.iter_stride = ctx->iter_stride;
     po.g_theta_out = pl.g_theta + (size_t)it * pl.R * kPoseDim;
     po.g_beta_out = pl.g_beta + (size_t)it * pl.R * kBetas;
     ++t->launches;
@@ -639,7 +639,7 @@ int train_forward(empose_train* t, TrainPlan& pl, const float* marker_pos, const
         pp.R = R; pp.F = F;
         for (int i = 0; i < kSensors; ++i) pp.slot_of_sensor[i] = ctx->slot_of_sensor[i];
         pp.use_pos = cfg.use_marker_pos; pp.use_ori = cfg.use_marker_ori; pp.n_pos = ctx->n_pos;
-        pp.in_size = ctx->in_size; pp.in_stride = ctx->in_stride; pp.iter_stride = ctx->iter_stride; pp.round_out = rnd;
+        pp.in_size = ctx->in_size; pp.in_stride = ctx->in_stride; pp.iter_stride = ctx->iter_stride; pp.operand_mode = ctx->op_mode;
         pp.meas = pl.meas; pp.xin = k == 0 ? pl.xin : nullptr; pp.xiter = pl.xiter + (size_t)k * R * ctx->iter_stride; pp.coef = pl.coef;
         EMPOSE_TRY(launch_prepare(pp, s));
         ++t->launches;
@@ -661,7 +661,7 @@ int train_forward(empose_train* t, TrainPlan& pl, const float* marker_pos, const
         memset(&up, 0, sizeof(up));
         up.theta = pl.theta; up.beta = pl.beta; up.dtheta = pl.dtheta; up.dbeta = pl.dbeta;
         up.step = cfg.step_size; up.first = (it == 0); up.average_shape = cfg.average_shape;
-        up.B = B; up.F = F; up.round_out = rnd;
+        up.B = B; up.F = F; up.operand_mode = ctx->op_mode;
         up.xiter = xiter_k; up.in_size = ctx->in_size; up.iter_stride = ctx->iter_stride; up.pf = pl.pf;
         up.pf_stride = ctx->pf_stride; up.pf_split = rnd;
         up.hist_pose = pl.hist[0] + (size_t)it * R * kPoseDim;
@@ -849,6 +849,10 @@ int empose_train_create(const empose_ief_config* cfg, const empose_tensor* tenso
     if (!cfg || !tensors || !params || !grads || !out) { set_last_error("null argument"); return EMPOSE_E_ARG; }
     *out = nullptr;
     if (cfg->skip_connections) { set_last_error("training with m_skip_connections is not implemented"); return EMPOSE_E_ARG; }
+    if (cfg->precision == EMPOSE_PRECISION_FP16) {
+        set_last_error("training runs in EMPOSE_PRECISION_TF32 or EMPOSE_PRECISION_FP32 (fp16 operands are an inference mode)");
+        return EMPOSE_E_ARG;
+    }
     std::unique_ptr<empose_train> t(new empose_train());
     t->cfg = *cfg;
     EMPOSE_TRY(empose_ief_create(cfg, tensors, n_tensors, &t->base));

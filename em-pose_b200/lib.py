@@ -13,8 +13,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libempose_b200.so')
 
-PRECISION_TF32 = 0
-PRECISION_FP32 = 1
+PRECISION_TF32 = 0      # tcgen05 kind::tf32 everywhere (training default)
+PRECISION_FP32 = 1      # FFMA executor, exact arithmetic
+PRECISION_FP16 = 2      # inference: fp16 operands for the learned layers (kind::f16), pose blend 3xTF32
 _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2}
 
 #: every symbol include/empose_b200.h declares (checked by tests/test_cabi.py)

@@ -41,7 +41,7 @@ def _frame_mask(seq_lengths, n_frames):
 class IterativeErrorFeedback(nn.Module):
     """The LGD(-RNN) model (``models.py:369-688``)."""
 
-    def __init__(self, config, smpl_model, precision=_lib.PRECISION_TF32):
+    def __init__(self, config, smpl_model, precision=_lib.PRECISION_FP16):
         super(IterativeErrorFeedback, self).__init__()
         self.config = config
         self.n_markers = config.n_markers if getattr(config, 'n_markers', -1) > -1 else C.N_TRACKERS_WO_ROOT
@@ -183,6 +183,8 @@ class IterativeErrorFeedback(nn.Module):
             self._trainer.close()
             self._trainer = None
         cfg = self._native_config(index)
+        if cfg['precision'] == _lib.PRECISION_FP16:          # fp16 operands are an inference mode: train on tf32 tensor cores
+            cfg['precision'] = _lib.PRECISION_TF32
         entries, n_params, n_buffers = _lib.train_layout(cfg)
         dev = torch.device('cuda', index)
         params = torch.zeros(max(n_params, 4), dtype=torch.float32, device=dev)

@@ -58,8 +58,11 @@ enum { EMPOSE_F32 = 0, EMPOSE_I32 = 1, EMPOSE_I64 = 2 };
 
 /* Arithmetic of the learned layers and the pose-blend contraction. */
 enum {
-    EMPOSE_PRECISION_TF32 = 0,   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (product default) */
-    EMPOSE_PRECISION_FP32 = 1    /* plain fp32 FFMA kernels: exact-arithmetic mode for parity studies */
+    EMPOSE_PRECISION_TF32 = 0,   /* tcgen05.mma kind::tf32 everywhere, fp32 accumulate in TMEM (training default) */
+    EMPOSE_PRECISION_FP32 = 1,   /* plain fp32 FFMA kernels: exact-arithmetic mode for parity studies */
+    EMPOSE_PRECISION_FP16 = 2    /* inference: MLP / LSTM / heads operands in fp16 (kind::f16, the same 10-bit mantissa
+                                    as tf32 at twice the rate and half the bytes), fp32 accumulate; the pose blend stays
+                                    error-compensated tf32 */
 };
 
 /* One named host tensor.  Names are the reference's state-dict keys ("rnn.lstm.weight_ih_l0",

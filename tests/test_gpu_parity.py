@@ -18,8 +18,8 @@ pytestmark = pytest.mark.gpu
 
 PARITY_RAD = 1e-4      # north_star tolerance, per-joint axis-angle
 PARITY_MM = 0.1        # north_star tolerance, joint position
-PRECISIONS = [native.PRECISION_FP32, native.PRECISION_TF32]
-PNAME = {native.PRECISION_FP32: 'fp32', native.PRECISION_TF32: 'tf32'}
+PRECISIONS = [native.PRECISION_FP32, native.PRECISION_TF32, native.PRECISION_FP16]
+PNAME = {native.PRECISION_FP32: 'fp32', native.PRECISION_TF32: 'tf32', native.PRECISION_FP16: 'fp16'}
 
 
 @pytest.fixture(scope='module')
@@ -44,6 +44,7 @@ def test_gemm_engine(dev, precision, m, n, k):
     want = (a.double() @ w.double().T + bias.double()).float()
     err = (got - want).abs().max().item()
     # tf32 inputs carry 2^-11 relative rounding (truncation in the worst case 2^-10): |a||w| ~ 1 per term, sqrt(k) growth
+    # (fp16 mode: operands AND, for N % 32 == 0, the outputs are rounded to fp16)
     tol = 2e-5 if precision == native.PRECISION_FP32 else 1e-2
     assert err < tol, 'max abs err %g' % err
     if precision == native.PRECISION_TF32:          # same operands pre-rounded: only accumulation order differs
@@ -193,7 +194,7 @@ def test_ief_matches_oracle(dev, smpl_npz, oracle_smpl, topology, precision, n_m
 def test_window_shape_is_shared_and_batch_shards_are_independent(dev, smpl_npz):
     """Size-independent properties at a larger size: one shape per window (models.py:529-535) and
     window independence (what lets inference shard over GPUs without a collective)."""
-    net = util.build_module(smpl_npz, precision=native.PRECISION_TF32, device=dev)
+    net = util.build_module(smpl_npz, precision=native.PRECISION_FP16, device=dev)
     ctx = net.native_context(dev)
     b, f = 512, 32
     p = synthetic.synth_window_params(b, f, seed=77, offsets=True)
@@ -214,7 +215,7 @@ def test_window_shape_is_shared_and_batch_shards_are_independent(dev, smpl_npz):
 
 
 def test_host_buffer_entry_point_matches_device_entry_point(dev, smpl_npz, oracle_smpl, topology):
-    net = util.build_module(smpl_npz, precision=native.PRECISION_TF32, device=dev)
+    net = util.build_module(smpl_npz, precision=native.PRECISION_FP16, device=dev)
     ctx = net.native_context(dev)
     params = synthetic.synth_window_params(4, 16, seed=9, ragged=True, offsets=True)
     inp = util.oracle_inputs_from_params(oracle_smpl, topology, params, seed=2)
@@ -255,7 +256,7 @@ def _compare_with_oracle(dev, smpl_npz, oracle_smpl, topology, b, f, precision, 
 
 def test_baseline_config2_lgd_no_rnn_256_windows(dev, smpl_npz, oracle_smpl, topology):
     """BASELINE.json configs[1]: LGD without RNN, 12 sensors, N=4, 256 windows x 32 frames, every frame checked."""
-    _compare_with_oracle(dev, smpl_npz, oracle_smpl, topology, 256, 32, native.PRECISION_TF32, seed=61,
+    _compare_with_oracle(dev, smpl_npz, oracle_smpl, topology, 256, 32, native.PRECISION_FP16, seed=61,
                          cfg_kwargs=dict(n_markers=12, num_iterations=4, rnn_init=False), module_kwargs={}, tag='config2')
 
 
