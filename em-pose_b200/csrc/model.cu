@@ -12,6 +12,7 @@
 // FFMA executor (FP32 mode).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -99,11 +100,11 @@ int build_mlp_pair(empose_ief* ctx, Plan& pl, const MlpPacked& mp, const MlpPack
     return EMPOSE_OK;
 }
 
-int build_plan(empose_ief* ctx, int B, int F, Plan** out) {
-    auto key = std::make_pair(B, F);
+int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
+    auto key = std::make_tuple(B, F, slot);
     auto it = ctx->plans.find(key);
     if (it != ctx->plans.end()) { *out = it->second.get(); return EMPOSE_OK; }
-    if (ctx->plans.size() >= 4) ctx->plans.clear();      // bound the workspace kept alive
+    if (ctx->plans.size() >= 8) ctx->plans.clear();      // bound the workspace kept alive
     std::unique_ptr<Plan> plp(new Plan());
     Plan& pl = *plp;
     const empose_ief_config& cfg = ctx->cfg;
@@ -384,7 +385,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
     const int B = pl.B, F = pl.F, R = pl.R, H = cfg.rnn_hidden_size, L = cfg.rnn_num_layers, N = cfg.num_iterations;
     const int mt_R = ceil_div(R, kTileM), mt_B = ceil_div(B, kTileM);
     const int rnd = ctx->round ? 1 : 0;
-    ctx->last_launches = 0;
+    ctx->last_launches = 0;       // (the chunked host path adds the sub-batches up itself)
     auto count = [&](int rc) { ++ctx->last_launches; return rc; };
 
     EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.seq_len, seq_lengths, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
@@ -596,19 +597,18 @@ int empose_ief_forward(empose_ief* ctx, const float* marker_pos, const float* ma
                           is_new_sequence, pose_hat, shape_hat, joints_hat, history, static_cast<cudaStream_t>(stream));
 }
 
-int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const float* marker_oris, const float* offset_r,
-                            const float* offset_t, const int32_t* seq_lengths, const float* marker_masks, float* lstm_state,
-                            int32_t is_new_sequence, int32_t B, int32_t F, float* pose_hat, float* shape_hat,
-                            float* joints_hat, const empose_ief_history* history, void* stream) {
-    EMPOSE_TRY(check_call(ctx, B, F));
-    if (!marker_pos || !marker_oris || !offset_r || !offset_t || !seq_lengths) { set_last_error("null input"); return EMPOSE_E_ARG; }
-    Plan* plp;
-    EMPOSE_TRY(build_plan(ctx, B, F, &plp));
-    Plan& pl = *plp;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t R = (size_t)pl.R;
+// One sub-batch of the host-buffer entry point: windows [b0, b0 + bc) of a batch of B.  Uploads on `s_in`, runs the pass
+// on `s`, downloads on `s_out`; the three streams are chained with events so that consecutive sub-batches overlap
+// (upload k+1 | compute k | download k-1).
+static int forward_host_chunk(empose_ief* ctx, Plan& pl, int B, int b0, const float* marker_pos, const float* marker_oris,
+                              const float* offset_r, const float* offset_t, const int32_t* seq_lengths, const float* marker_masks,
+                              float* lstm_state, int is_new_sequence, float* pose_hat, float* shape_hat, float* joints_hat,
+                              const empose_ief_history* history, cudaStream_t s_in, cudaStream_t s, cudaStream_t s_out,
+                              cudaEvent_t ev_in, cudaEvent_t ev_done) {
+    const int bc = pl.B, F = pl.F;
+    const size_t R = (size_t)pl.R, r0 = (size_t)b0 * F, Rall = (size_t)B * F;
     const int L = ctx->cfg.rnn_num_layers, H = ctx->cfg.rnn_hidden_size, N = ctx->cfg.num_iterations;
-    const size_t state_n = ctx->cfg.rnn_init ? (size_t)2 * L * B * H : 0;
+    const size_t state_n = ctx->cfg.rnn_init ? (size_t)2 * L * bc * H : 0;
     if (!pl.in_pos) {
         EMPOSE_TRY(pl.arena.alloc_n(R * 36, &pl.in_pos));
         EMPOSE_TRY(pl.arena.alloc_n(R * 108, &pl.in_ori));
@@ -617,42 +617,111 @@ int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const floa
         EMPOSE_TRY(pl.arena.alloc_n(R * kPoseDim, &pl.o_pose));
         EMPOSE_TRY(pl.arena.alloc_n(R * kBetas, &pl.o_shape));
         EMPOSE_TRY(pl.arena.alloc_n(R * kPoseDim, &pl.o_joints));
-        EMPOSE_TRY(pl.arena.alloc_n((size_t)B * 108, &pl.in_off_r));
-        EMPOSE_TRY(pl.arena.alloc_n((size_t)B * 36, &pl.in_off_t));
-        EMPOSE_TRY(pl.arena.alloc_n((size_t)B, &pl.in_len));
+        EMPOSE_TRY(pl.arena.alloc_n((size_t)bc * 108, &pl.in_off_r));
+        EMPOSE_TRY(pl.arena.alloc_n((size_t)bc * 36, &pl.in_off_t));
+        EMPOSE_TRY(pl.arena.alloc_n((size_t)bc, &pl.in_len));
     }
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_pos, marker_pos, R * 36 * 4, cudaMemcpyHostToDevice, s));
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_ori, marker_oris, R * 108 * 4, cudaMemcpyHostToDevice, s));
-    if (marker_masks) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_masks, marker_masks, R * 12 * 4, cudaMemcpyHostToDevice, s));
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_off_r, offset_r, (size_t)B * 108 * 4, cudaMemcpyHostToDevice, s));
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_off_t, offset_t, (size_t)B * 36 * 4, cudaMemcpyHostToDevice, s));
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_len, seq_lengths, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-    if (lstm_state && state_n && !is_new_sequence)
-        EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.io_state, lstm_state, state_n * 4, cudaMemcpyHostToDevice, s));
+    // ---- upload ----
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_pos, marker_pos + r0 * 36, R * 36 * 4, cudaMemcpyHostToDevice, s_in));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_ori, marker_oris + r0 * 108, R * 108 * 4, cudaMemcpyHostToDevice, s_in));
+    if (marker_masks) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_masks, marker_masks + r0 * 12, R * 12 * 4, cudaMemcpyHostToDevice, s_in));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_off_r, offset_r + (size_t)b0 * 108, (size_t)bc * 108 * 4, cudaMemcpyHostToDevice, s_in));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_off_t, offset_t + (size_t)b0 * 36, (size_t)bc * 36 * 4, cudaMemcpyHostToDevice, s_in));
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.in_len, seq_lengths + b0, (size_t)bc * 4, cudaMemcpyHostToDevice, s_in));
+    const bool with_state = lstm_state && state_n;
+    if (with_state && !is_new_sequence)      // [2][L][B][H] on the host -> [2][L][bc][H] on the device
+        for (int q = 0; q < 2 * L; ++q)
+            EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.io_state + (size_t)q * bc * H, lstm_state + ((size_t)q * B + b0) * H, (size_t)bc * H * 4,
+                                            cudaMemcpyHostToDevice, s_in));
+    if (s_in != s) {
+        EMPOSE_CUDA_TRY(cudaEventRecord(ev_in, s_in));
+        EMPOSE_CUDA_TRY(cudaStreamWaitEvent(s, ev_in, 0));
+    }
+    // ---- compute ----
     empose_ief_history dh = {nullptr, nullptr, nullptr, nullptr, nullptr};
     const size_t hist_dof[5] = {kPoseDim, kBetas, kPoseDim, 36, 108};
+    float* hp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (history) {
-        float* hp[5] = {history->pose, history->shape, history->joints, history->markers, history->markers_ori};
+        float* src[5] = {history->pose, history->shape, history->joints, history->markers, history->markers_ori};
         float** dp[5] = {&dh.pose, &dh.shape, &dh.joints, &dh.markers, &dh.markers_ori};
-        for (int i = 0; i < 5; ++i)
+        for (int i = 0; i < 5; ++i) {
+            hp[i] = src[i];
             if (hp[i]) {
                 if (!pl.o_hist[i]) EMPOSE_TRY(pl.arena.alloc_n((size_t)(N + 1) * R * hist_dof[i], &pl.o_hist[i]));
                 *dp[i] = pl.o_hist[i];
             }
+        }
     }
-    int rc = forward_device(ctx, pl, pl.in_pos, pl.in_ori, pl.in_off_r, pl.in_off_t, pl.in_len, marker_masks ? pl.in_masks : nullptr,
-                            (lstm_state && state_n) ? pl.io_state : nullptr, is_new_sequence, pl.o_pose, pl.o_shape,
-                            pl.o_joints, history ? &dh : nullptr, s);
-    if (rc != EMPOSE_OK) return rc;
-    if (pose_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pose_hat, pl.o_pose, R * kPoseDim * 4, cudaMemcpyDeviceToHost, s));
-    if (shape_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(shape_hat, pl.o_shape, R * kBetas * 4, cudaMemcpyDeviceToHost, s));
-    if (joints_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(joints_hat, pl.o_joints, R * kPoseDim * 4, cudaMemcpyDeviceToHost, s));
-    if (lstm_state && state_n) EMPOSE_CUDA_TRY(cudaMemcpyAsync(lstm_state, pl.io_state, state_n * 4, cudaMemcpyDeviceToHost, s));
-    if (history) {
-        float* hp[5] = {history->pose, history->shape, history->joints, history->markers, history->markers_ori};
-        for (int i = 0; i < 5; ++i)
-            if (hp[i]) EMPOSE_CUDA_TRY(cudaMemcpyAsync(hp[i], pl.o_hist[i], (size_t)(N + 1) * R * hist_dof[i] * 4, cudaMemcpyDeviceToHost, s));
+    const int64_t launches_before = ctx->last_launches;
+    EMPOSE_TRY(forward_device(ctx, pl, pl.in_pos, pl.in_ori, pl.in_off_r, pl.in_off_t, pl.in_len, marker_masks ? pl.in_masks : nullptr,
+                              with_state ? pl.io_state : nullptr, is_new_sequence, pl.o_pose, pl.o_shape, pl.o_joints,
+                              history ? &dh : nullptr, s));
+    ctx->last_launches += launches_before;
+    if (s_out != s) {
+        EMPOSE_CUDA_TRY(cudaEventRecord(ev_done, s));
+        EMPOSE_CUDA_TRY(cudaStreamWaitEvent(s_out, ev_done, 0));
     }
+    // ---- download ----
+    if (pose_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pose_hat + r0 * kPoseDim, pl.o_pose, R * kPoseDim * 4, cudaMemcpyDeviceToHost, s_out));
+    if (shape_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(shape_hat + r0 * kBetas, pl.o_shape, R * kBetas * 4, cudaMemcpyDeviceToHost, s_out));
+    if (joints_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(joints_hat + r0 * kPoseDim, pl.o_joints, R * kPoseDim * 4, cudaMemcpyDeviceToHost, s_out));
+    if (with_state)
+        for (int q = 0; q < 2 * L; ++q)
+            EMPOSE_CUDA_TRY(cudaMemcpyAsync(lstm_state + ((size_t)q * B + b0) * H, pl.io_state + (size_t)q * bc * H, (size_t)bc * H * 4,
+                                            cudaMemcpyDeviceToHost, s_out));
+    for (int i = 0; i < 5; ++i)
+        if (hp[i])
+            for (int it = 0; it <= N; ++it)      // [N+1][B][F][dof] on the host, [N+1][bc][F][dof] on the device
+                EMPOSE_CUDA_TRY(cudaMemcpyAsync(hp[i] + ((size_t)it * Rall + r0) * hist_dof[i], pl.o_hist[i] + (size_t)it * R * hist_dof[i],
+                                                R * hist_dof[i] * 4, cudaMemcpyDeviceToHost, s_out));
+    return EMPOSE_OK;
+}
+
+int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const float* marker_oris, const float* offset_r,
+                            const float* offset_t, const int32_t* seq_lengths, const float* marker_masks, float* lstm_state,
+                            int32_t is_new_sequence, int32_t B, int32_t F, float* pose_hat, float* shape_hat,
+                            float* joints_hat, const empose_ief_history* history, void* stream) {
+    EMPOSE_TRY(check_call(ctx, B, F));
+    if (!marker_pos || !marker_oris || !offset_r || !offset_t || !seq_lengths) { set_last_error("null input"); return EMPOSE_E_ARG; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // Windows are independent, so a large batch is cut into sub-batches whose PCIe copies overlap the compute of their
+    // neighbours.  Sub-batches stay >= 2048 windows: the LSTM wavefront launches work on B rows and lose efficiency below.
+    const int n_chunks = std::max(1, std::min(4, B / 2048));
+    ctx->last_launches = 0;
+    if (n_chunks == 1) {
+        Plan* plp;
+        EMPOSE_TRY(build_plan(ctx, B, F, &plp));
+        EMPOSE_TRY(forward_host_chunk(ctx, *plp, B, 0, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks, lstm_state,
+                                      is_new_sequence, pose_hat, shape_hat, joints_hat, history, s, s, s, nullptr, nullptr));
+        EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));
+        return EMPOSE_OK;
+    }
+    if (!ctx->copy_in) {
+        EMPOSE_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        EMPOSE_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    }
+    while ((int)ctx->pipe_events.size() < 2 * n_chunks + 2) {
+        cudaEvent_t e;
+        EMPOSE_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
+    // the copy streams start after whatever the caller already queued on `stream`
+    cudaEvent_t ev_start = ctx->pipe_events[2 * n_chunks], ev_end = ctx->pipe_events[2 * n_chunks + 1];
+    EMPOSE_CUDA_TRY(cudaEventRecord(ev_start, s));
+    EMPOSE_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_in, ev_start, 0));
+    EMPOSE_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ev_start, 0));
+    int b0 = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int bc = B / n_chunks + (c < B % n_chunks ? 1 : 0);
+        Plan* plp;
+        EMPOSE_TRY(build_plan(ctx, bc, F, &plp, c + 1));        // one workspace per in-flight sub-batch
+        EMPOSE_TRY(forward_host_chunk(ctx, *plp, B, b0, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks,
+                                      lstm_state, is_new_sequence, pose_hat, shape_hat, joints_hat, history, ctx->copy_in, s,
+                                      ctx->copy_out, ctx->pipe_events[2 * c], ctx->pipe_events[2 * c + 1]));
+        b0 += bc;
+    }
+    EMPOSE_CUDA_TRY(cudaEventRecord(ev_end, ctx->copy_out));
+    EMPOSE_CUDA_TRY(cudaStreamWaitEvent(s, ev_end, 0));
     EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));
     return EMPOSE_OK;
 }

@@ -362,15 +362,21 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
     PackedMatrix heads;
     MlpPacked pose_init, shape_init, pose_iter, shape_iter;
     PackedMatrix pb, pbt;
-    std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+    std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;     // (B, F, slot): slots > 0 serve the pipelined host path
     std::map<int, std::unique_ptr<Plan>> project_plans;
     int64_t last_launches = 0;
     // optional per-launch timing of the GEMM executor (empose_ief_set_profiling)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
+    // copy streams and events of the pipelined host-buffer entry point (empose_ief_forward_host)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::vector<cudaEvent_t> pipe_events;
     ~IefData() {
         for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto& e : pipe_events) cudaEventDestroy(e);
+        if (copy_in) cudaStreamDestroy(copy_in);
+        if (copy_out) cudaStreamDestroy(copy_out);
     }
 };
 }  // namespace empose

@@ -226,6 +226,30 @@ def test_host_buffer_entry_point_matches_device_entry_point(dev, smpl_npz, oracl
     assert torch.equal(a['lstm_state'].cpu(), h['lstm_state'])
 
 
+def test_pipelined_host_entry_point_equals_one_pass(dev, smpl_npz):
+    """empose_ief_forward_host cuts batches of >= 4096 windows into sub-batches whose PCIe copies overlap the compute of
+    their neighbours; windows are independent, so the result must be bit-identical to the single device pass (inputs,
+    offsets, ragged lengths, masks and the carried LSTM state all cross the sub-batch boundary)."""
+    net = util.build_module(smpl_npz, num_iterations=2, precision=native.PRECISION_FP16, device=dev)
+    ctx = net.native_context(dev)
+    b, f = 4100, 3                                   # odd size: sub-batches of 2050 windows
+    g = torch.Generator().manual_seed(9)
+    p = synthetic.synth_window_params(b, f, seed=91, ragged=True, offsets=True)
+    pos = 0.3 * torch.randn(b, f, 36, generator=g)
+    eye = torch.eye(3).reshape(1, 1, 1, 9)
+    ori = (eye + 0.05 * torch.randn(b, f, 12, 9, generator=g)).reshape(b, f, 108)
+    masks = (torch.rand(b, f, 12, generator=g) > 0.02).float()
+    state = 0.1 * torch.randn(2, 2, b, 512, generator=g)
+    off_r, off_t, lens = torch.from_numpy(p['offset_r']), torch.from_numpy(p['offset_t']), torch.from_numpy(p['seq_lengths'])
+    a = ctx.forward(pos.to(dev), ori.to(dev), off_r.to(dev), off_t.to(dev), lens.to(dev), marker_masks=masks.to(dev),
+                    lstm_state=state.to(dev), is_new_sequence=False, want_history=False)
+    pin = lambda t: t.contiguous().pin_memory()
+    h = ctx.forward_host(pin(pos), pin(ori), pin(off_r), pin(off_t), lens, marker_masks=pin(masks), lstm_state=state,
+                         is_new_sequence=False)
+    for k in ('pose', 'shape', 'joints', 'lstm_state'):
+        assert torch.equal(a[k].cpu(), h[k]), k
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # other configurations of the reference and edge cases
 # ---------------------------------------------------------------------------------------------------------------------
