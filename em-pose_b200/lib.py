@@ -250,12 +250,13 @@ class IefContext(object):
         seq_lengths = seq_lengths.to(dtype=torch.int32).contiguous()
         if marker_masks is not None:
             marker_masks = f32(marker_masks)
-        pose = torch.empty((b, f, 66), dtype=torch.float32).pin_memory()
-        shape = torch.empty((b, f, 10), dtype=torch.float32).pin_memory()
-        joints = torch.empty((b, f, 66), dtype=torch.float32).pin_memory()
+        # outputs are allocated pinned (torch's caching host allocator): no staging copy, truly asynchronous downloads
+        pose = torch.empty((b, f, 66), dtype=torch.float32, pin_memory=True)
+        shape = torch.empty((b, f, 10), dtype=torch.float32, pin_memory=True)
+        joints = torch.empty((b, f, 66), dtype=torch.float32, pin_memory=True)
         state = None
         if self.rnn_layers:
-            state = torch.zeros((2, self.rnn_layers, b, self.rnn_hidden), dtype=torch.float32)
+            state = torch.empty((2, self.rnn_layers, b, self.rnn_hidden), dtype=torch.float32, pin_memory=True)
             if lstm_state is not None and not is_new_sequence:
                 state.copy_(lstm_state.reshape(state.shape))
         with torch.cuda.device(self.device_index):

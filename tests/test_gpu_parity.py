@@ -227,12 +227,12 @@ def test_host_buffer_entry_point_matches_device_entry_point(dev, smpl_npz, oracl
 
 
 def test_pipelined_host_entry_point_equals_one_pass(dev, smpl_npz):
-    """empose_ief_forward_host cuts batches of >= 4096 windows into sub-batches whose PCIe copies overlap the compute of
+    """empose_ief_forward_host cuts batches of >= 8192 windows into sub-batches whose PCIe copies overlap the compute of
     their neighbours; windows are independent, so the result must be bit-identical to the single device pass (inputs,
     offsets, ragged lengths, masks and the carried LSTM state all cross the sub-batch boundary)."""
     net = util.build_module(smpl_npz, num_iterations=2, precision=native.PRECISION_FP16, device=dev)
     ctx = net.native_context(dev)
-    b, f = 4100, 3                                   # odd size: sub-batches of 2050 windows
+    b, f = 8200, 2                                   # sub-batches of 4100 windows
     g = torch.Generator().manual_seed(9)
     p = synthetic.synth_window_params(b, f, seed=91, ragged=True, offsets=True)
     pos = 0.3 * torch.randn(b, f, 36, generator=g)
