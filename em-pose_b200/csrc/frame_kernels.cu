@@ -66,43 +66,68 @@ __global__ void __launch_bounds__(256) prepare_kernel(PrepareParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// one CTA per window
-__global__ void __launch_bounds__(128) update_kernel(UpdateParams p) {
+// One CTA per window.  Frames are processed in groups of kUpdateGroup: theta of the group is kept in shared memory for
+// the pose features, which are assembled in a shared-memory tile and written out as one contiguous, 16-byte-vectorised
+// block (a group's rows of `pf` are adjacent in memory) instead of 18 scattered words per joint.
+constexpr int kUpdateGroup = 16;
+constexpr int kUpdateThreads = 256;
+
+__global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) {
+    __shared__ float part_db[8][kBetas];
     __shared__ float mean_db[kBetas];
+    __shared__ float th[kUpdateGroup][kPoseDim];
+    __shared__ __align__(16) float tile[kUpdateGroup * 2 * kPoseFeatPad];
     const int b = blockIdx.x;
     const int64_t row0 = (int64_t)b * p.F;
+    const int tid = threadIdx.x;
     if (p.average_shape) {
-        if (threadIdx.x < kBetas) {
+        if (tid < 8 * kBetas) {
+            const int k = tid % kBetas, part = tid / kBetas;
             float acc = 0.0f;
-            for (int f = 0; f < p.F; ++f) acc += p.dbeta[(row0 + f) * kBetas + threadIdx.x];
-            mean_db[threadIdx.x] = acc / (float)p.F;
+            for (int f = part; f < p.F; f += 8) acc += p.dbeta[(row0 + f) * kBetas + k];
+            part_db[part][k] = acc;
+        }
+        __syncthreads();
+        if (tid < kBetas) {
+            float acc = 0.0f;
+            for (int q = 0; q < 8; ++q) acc += part_db[q][tid];
+            mean_db[tid] = acc / (float)p.F;
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < p.F * 76; i += blockDim.x) {
-        const int f = i / 76, c = i % 76;
-        const int64_t row = row0 + f;
-        float v;
-        if (c < kPoseDim) {
-            const float d = p.dtheta[row * kPoseDim + c];
-            v = p.first ? d : p.theta[row * kPoseDim + c] + p.step * d;
-            p.theta[row * kPoseDim + c] = v;
-            if (p.hist_pose) p.hist_pose[row * kPoseDim + c] = v;
-        } else {
-            const int k = c - kPoseDim;
-            const float d = p.average_shape ? mean_db[k] : p.dbeta[row * kBetas + k];
-            v = p.first ? d : p.beta[row * kBetas + k] + p.step * d;
-            p.beta[row * kBetas + k] = v;
-            if (p.hist_shape) p.hist_shape[row * kBetas + k] = v;
+    // pad columns of the pose-feature rows (189..191 of each half) stay zero
+    for (int i = tid; i < kUpdateGroup * 2 * kPoseFeatPad; i += kUpdateThreads) tile[i] = 0.0f;
+    for (int f0 = 0; f0 < p.F; f0 += kUpdateGroup) {
+        const int nf = min(kUpdateGroup, p.F - f0);
+        const int64_t g0 = row0 + f0;
+        for (int i = tid; i < nf * kPoseDim; i += kUpdateThreads) {          // theta rows of the group are contiguous
+            const int f = i / kPoseDim, c = i - f * kPoseDim;
+            const float d = p.dtheta[g0 * kPoseDim + i];
+            const float v = p.first ? d : p.theta[g0 * kPoseDim + i] + p.step * d;
+            p.theta[g0 * kPoseDim + i] = v;
+            th[f][c] = v;
+            if (p.hist_pose) p.hist_pose[g0 * kPoseDim + i] = v;
+            if (p.xiter) store_operand(p.xiter, (g0 + f) * p.iter_stride + p.in_size + c, v, p.operand_mode);
         }
-        if (p.xiter) store_operand(p.xiter, row * p.iter_stride + p.in_size + c, v, p.operand_mode);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < p.F * (kJoints - 1); i += blockDim.x) {
-        const int f = i / (kJoints - 1), j = 1 + i % (kJoints - 1);
-        const int64_t row = row0 + f;
-        float r[3] = {p.theta[row * kPoseDim + j * 3], p.theta[row * kPoseDim + j * 3 + 1], p.theta[row * kPoseDim + j * 3 + 2]};
-        write_pose_features(r, p.pf + row * p.pf_stride + (j - 1) * 9, p.pf_split);
+        for (int i = tid; i < nf * kBetas; i += kUpdateThreads) {
+            const int f = i / kBetas, k = i - f * kBetas;
+            const float d = p.average_shape ? mean_db[k] : p.dbeta[g0 * kBetas + i];
+            const float v = p.first ? d : p.beta[g0 * kBetas + i] + p.step * d;
+            p.beta[g0 * kBetas + i] = v;
+            if (p.hist_shape) p.hist_shape[g0 * kBetas + i] = v;
+            if (p.xiter) store_operand(p.xiter, (g0 + f) * p.iter_stride + p.in_size + kPoseDim + k, v, p.operand_mode);
+        }
+        __syncthreads();
+        const int row_floats = p.pf_stride;                              // 192, or 384 when split into hi | lo
+        for (int i = tid; i < nf * (kJoints - 1); i += kUpdateThreads) {
+            const int f = i / (kJoints - 1), j = 1 + i - f * (kJoints - 1);
+            write_pose_features(&th[f][j * 3], tile + f * row_floats + (j - 1) * 9, p.pf_split);
+        }
+        __syncthreads();
+        float4* dst = reinterpret_cast<float4*>(p.pf + g0 * row_floats);
+        const float4* src = reinterpret_cast<const float4*>(tile);
+        for (int i = tid; i < nf * row_floats / 4; i += kUpdateThreads) dst[i] = src[i];
+        __syncthreads();
     }
 }
 
@@ -303,7 +328,7 @@ int launch_prepare(const PrepareParams& p, cudaStream_t s) {
 }
 
 int launch_update(const UpdateParams& p, cudaStream_t s) {
-    update_kernel<<<p.B, 128, 0, s>>>(p);
+    update_kernel<<<p.B, kUpdateThreads, 0, s>>>(p);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

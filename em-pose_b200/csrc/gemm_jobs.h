@@ -94,7 +94,7 @@ constexpr int kStageFloats = 32 * kStageLd;        // one warp-private [32][33] 
 // Bias arrays are padded by 32 floats, so the vector loads below never leave the allocation.
 // Must be called by all 32 lanes of the warp.
 __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int lane, int c0, float (&v)[32],
-                                               float* __restrict__ stage) {
+                                               float* __restrict__ stage, bool no_store = false) {
     const int n0 = j.n_begin + c0;                 // global column of v[0]
     const int row = row0 + lane;
     float bias[32];
@@ -110,8 +110,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
         for (int i = 0; i < 32; ++i) bias[i] = 0.0f;
     }
     if (j.epi == EPI_LINEAR && j.out_half && !j.res && n0 + 32 <= j.n_valid && n0 + 32 <= j.split) {
-        // fp16 activations: the 32 columns of a lane are 64 contiguous bytes of its row -> four 16-byte stores straight
-        // from registers (two full 32-byte sectors per lane), no shared-memory transpose
+        // fp16 activations.  A lane's 32 columns are 64 contiguous bytes of ITS row, so storing straight from registers
+        // makes every store instruction touch 32 different lines with 16 bytes each (measured: 40 % of a 512x512 layer).
+        // Instead the warp stages its [32 rows][64 B] block in shared memory (80-byte pitch: conflict-free 16-byte
+        // accesses) and writes it out 8 rows per instruction: 4 lanes x 16 B = two full sectors per row.
         if (j.mask_rows && row < j.m_rows && (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window]) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.0f;
@@ -126,13 +128,94 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
             const __half2 h = __floats2half2_rn(y0, y1);
             packed[i] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        if (row < j.m_rows) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(j.out) + (int64_t)row * j.out_stride + j.out_col0 + n0);
+        char* tile = reinterpret_cast<char*>(stage);
+        uint4* srow = reinterpret_cast<uint4*>(tile + lane * 80);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) srow[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        __syncwarp();
+        __half* out_h = reinterpret_cast<__half*>(j.out) + j.out_col0 + n0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2), seg = lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(tile + r * 80 + seg * 16);
+            if (row0 + r < j.m_rows && !no_store)
+                *reinterpret_cast<uint4*>(out_h + (int64_t)(row0 + r) * j.out_stride + seg * 8) = val;
+        }
+        __syncwarp();
+    } else if (j.epi == EPI_LSTM && j.out_half && (j.n_count % 64) == 0) {
+        // fp16 hidden state, two chunks (16 units) at a time: the cell state of the pair is 64 B per row, the hidden state
+        // 32 B.  They are moved between global and shared memory with coalesced 16-byte accesses (8 / 16 rows per
+        // instruction, whole sectors) and every lane works on its own row in shared memory in between.
+        const int pos = (c0 >> 5) & 1;                          // first / second chunk of the pair
+        const int unit0 = lstm_unit_of_packed(n0) - pos * 8;    // first unit of the pair
+        char* ctile = reinterpret_cast<char*>(stage);           // [32][80 B]: 16 fp32 cell states per row
+        char* htile = ctile + 32 * 80;                          // [32][48 B]: 16 fp16 hidden states per row
+        const bool live = row < j.m_rows && j.t < j.seq_len[row];
+        if (pos == 0) {
+            const bool any_frozen = __any_sync(0xffffffffu, row < j.m_rows && !live);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int r = it * 8 + (lane >> 2), seg = lane & 3;
+                if (row0 + r < j.m_rows)
+                    *reinterpret_cast<float4*>(ctile + r * 80 + seg * 16) =
+                        *reinterpret_cast<const float4*>(j.c_state + (int64_t)(row0 + r) * j.hidden + unit0 + seg * 4);
+            }
+            if (any_frozen) {
+                const __half* hprev = reinterpret_cast<const __half*>(j.h_prev) + unit0;
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int r = it * 16 + (lane >> 1), seg = lane & 1;
+                    if (row0 + r < j.m_rows)
+                        *reinterpret_cast<uint4*>(htile + r * 48 + seg * 16) =
+                            *reinterpret_cast<const uint4*>(hprev + (int64_t)(row0 + r) * j.h_prev_stride + seg * 8);
+                }
+            }
+            __syncwarp();
+        }
+        if (live) {
+            float4* cp = reinterpret_cast<float4*>(ctile + lane * 80 + pos * 32);
+            const float4 c0v = cp[0], c1v = cp[1];
+            const float c_old[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+            float c_new[8];
+            uint32_t hp[4];
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                float h2[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float gi = v[k + q] + bias[k + q], gf = v[8 + k + q] + bias[8 + k + q];
+                    const float gg = v[16 + k + q] + bias[16 + k + q], go = v[24 + k + q] + bias[24 + k + q];
+                    c_new[k + q] = sigmoid_f(gf) * c_old[k + q] + sigmoid_f(gi) * tanh_f(gg);
+                    h2[q] = sigmoid_f(go) * tanh_f(c_new[k + q]);
+                }
+                const __half2 h = __floats2half2_rn(h2[0], h2[1]);
+                hp[k / 2] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            cp[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
+            cp[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
+            *reinterpret_cast<uint4*>(htile + lane * 48 + pos * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        }
+        if (pos == 1) {       // padded rows carry c (unchanged in the tile) and h (h_prev, loaded above)
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int r = it * 8 + (lane >> 2), seg = lane & 3;
+                if (row0 + r < j.m_rows)
+                    *reinterpret_cast<float4*>(j.c_state + (int64_t)(row0 + r) * j.hidden + unit0 + seg * 4) =
+                        *reinterpret_cast<const float4*>(ctile + r * 80 + seg * 16);
+            }
+            __half* hout = reinterpret_cast<__half*>(j.out) + unit0;
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int r = it * 16 + (lane >> 1), seg = lane & 1;
+                if (row0 + r < j.m_rows)
+                    *reinterpret_cast<uint4*>(hout + (int64_t)(row0 + r) * j.out_stride + seg * 8) =
+                        *reinterpret_cast<const uint4*>(htile + r * 48 + seg * 16);
+            }
+            __syncwarp();
         }
     } else if (j.epi == EPI_LSTM && j.out_half) {
-        // fp16 hidden state: a lane owns 8 consecutive units of its row -> c is two 16-byte accesses, h one
+        // fp16 hidden state, narrow layers (4H not a multiple of 64): a lane owns 8 consecutive units of its row
         const int unit0 = lstm_unit_of_packed(n0);
         if (row < j.m_rows) {
             __half* hout = reinterpret_cast<__half*>(j.out) + (int64_t)row * j.out_stride + unit0;

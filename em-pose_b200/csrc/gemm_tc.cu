@@ -290,8 +290,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 const int c_end = min(job.n_count, (half + 1) * (kMaxTileN / 2));
                 for (int c0 = half * (kMaxTileN / 2); c0 < c_end; c0 += 32) {
                     float v[32];
-                    tmem_load_32cols(taddr + (uint32_t)c0, v);
-                    if (!(debug_mode & 4)) epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats);
+                    if (debug_mode & 32) {                 // measurement only: no TMEM read
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+                    } else {
+                        tmem_load_32cols(taddr + (uint32_t)c0, v);
+                    }
+                    if (!(debug_mode & 4)) epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats, (debug_mode & 16) != 0);
                 }
                 tcgen05_fence_before();
                 if (!(debug_mode & 8)) {
@@ -371,7 +376,9 @@ int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_
     }
     const int n_items = m_tiles * (job_count / jobs_per_item);
     const int grid = n_items < num_sms ? n_items : num_sms;
-    static int debug_mode = -1;       // EMPOSE_TC_DEBUG=1: TMA only, =2: MMA only (throughput experiments; results are garbage)
+    // EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
+    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads
+    static int debug_mode = -1;
     if (debug_mode < 0) {
         const char* e = getenv("EMPOSE_TC_DEBUG");
         debug_mode = e ? atoi(e) : 0;
