@@ -39,7 +39,8 @@ struct GemmJob {
     const float* w_ptr;
     int64_t w_ld;
     int32_t w_koff[2];
-    int32_t w_map;
+    int32_t w_map;           // tensor map with a box of n_count rows
+    int32_t w_map2;          // tensor map with a box of n_count / 2 rows (2-CTA cluster variant: each CTA loads half)
     int32_t n_begin;         // first W row / output column of this job
     int32_t n_count;         // columns computed (multiple of 16, <= kMaxTileN)
     int32_t m_rows;          // valid rows overall; rows >= m_rows are never written

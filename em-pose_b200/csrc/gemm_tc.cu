@@ -83,6 +83,36 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// multicast variants: the tile / the arrival lands at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int crd0, int crd1,
+                                                      uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// spin with a watchdog: a protocol bug must end in a trap (an error the host sees), never in a hung GPU
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 28)) __trap();
+    }
+}
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -156,6 +186,12 @@ __device__ __forceinline__ int job_k_chunks(const GemmJob& j) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
+// kCluster = 1: every CTA loads its own A and W tiles.
+// kCluster = 2: launched as clusters of two CTAs that walk the SAME job sequence on two adjacent row tiles.  Each CTA
+//   loads its own A tile and ONE HALF of every W tile, multicast into both CTAs' shared memory, which halves the W
+//   traffic out of L2 (the bound of the K = 512 layers: 48 KB per 512 MMA cycles and SM).  A ring slot may only be
+//   refilled when BOTH CTAs have consumed it, so every MMA commit arrives on the `empty` barrier of both CTAs.
+template <int kCluster>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __restrict__ jobs,
                                                               const CUtensorMap* __restrict__ maps, int job_begin,
                                                               int job_count, int jobs_per_item, int m_tiles,
@@ -168,12 +204,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int groups = job_count / jobs_per_item;
-    const int n_items = m_tiles * groups;
+    // work items: (row tile, job group); in cluster mode an item is a PAIR of row tiles, one per CTA of the cluster
+    const int n_items = (kCluster == 2 ? (m_tiles + 1) / 2 : m_tiles) * groups;
+    const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;
+    const int item0 = kCluster == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_step = kCluster == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr uint16_t kMask = kCluster == 2 ? 3 : 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&ctl->full[s], 1);
-            mbar_init(&ctl->empty[s], 1);
+            mbar_init(&ctl->empty[s], kCluster);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&ctl->tmem_full[b], 1);
@@ -190,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (kCluster == 2) cluster_sync_all();        // the peer's barriers must be initialised before anything is multicast to it
     tcgen05_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
 
@@ -197,8 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, items_done = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++items_done) {
-                const int m0 = (item / groups) * kTileM;
+            for (int item = item0; item < n_items; item += item_step, ++items_done) {
+                const int m0 = (kCluster == 2 ? 2 * (item / groups) + (int)crank : item / groups) * kTileM;
                 const int first = job_begin + (item % groups) * jobs_per_item;
                 for (int jj = 0; jj < jobs_per_item; ++jj) {
                     const GemmJob& job = jobs[first + jj];
@@ -213,7 +255,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     for (int seg = 0; seg < 2; ++seg) {
                         const int chunks = (job.a_k[seg] + ck - 1) / ck;
                         for (int kc = 0; kc < chunks; ++kc) {
-                            mbar_wait(&ctl->empty[stage], phase ^ 1u);
+                            if (kCluster == 2) mbar_wait_guarded(&ctl->empty[stage], phase ^ 1u);
+                            else mbar_wait(&ctl->empty[stage], phase ^ 1u);
                             uint8_t* a_dst = smem + stage * kStageBytes;
                             uint8_t* w_dst = a_dst + kABytes;
                             if (debug_mode & 2) {            // measurement only: no loads, MMAs run on stale data
@@ -222,8 +265,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                 mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
                                 tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * ck,
                                             job.a_scratch[seg] ? (int)blockIdx.x * kTileM : m0);
-                                tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * ck,
-                                            job.n_begin);
+                                if (kCluster == 2) {       // my half of the W rows, delivered to both CTAs
+                                    const int half_rows = job.n_count >> 1;
+                                    tma_load_2d_multicast(w_dst + crank * (uint32_t)half_rows * 128u, &maps[job.w_map2], &ctl->full[stage],
+                                                          job.w_koff[seg] + kc * ck, job.n_begin + (int)crank * half_rows, kMask);
+                                } else {
+                                    tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * ck, job.n_begin);
+                                }
                             }
                             if (++stage == kStages) { stage = 0; phase ^= 1u; }
                         }
@@ -235,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, seq = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = item0; item < n_items; item += item_step) {
                 const int first = job_begin + (item % groups) * jobs_per_item;
                 for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
                     const GemmJob& job = jobs[first + jj];
@@ -247,12 +295,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     const uint32_t idesc = make_idesc(job.n_count, half);
                     const int chunks = job_k_chunks(job);
                     for (int kc = 0; kc < chunks; ++kc) {
-                        mbar_wait(&ctl->full[stage], phase);
+                        if (kCluster == 2) mbar_wait_guarded(&ctl->full[stage], phase);
+                        else mbar_wait(&ctl->full[stage], phase);
                         tcgen05_fence_after();
                         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
                         const uint64_t a_desc = make_smem_desc(a_addr);
                         const uint64_t b_desc = make_smem_desc(a_addr + kABytes);
-                        if (debug_mode & 1) {                // measurement only: loads without MMAs
+                        if (debug_mode & 1) {                // measurement only: loads without MMAs (not in cluster mode)
                             mbar_arrive(&ctl->empty[stage]);
                         } else {
 #pragma unroll
@@ -261,7 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                 if (half) umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
                                 else umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
                             }
-                            umma_commit(&ctl->empty[stage]);
+                            if (kCluster == 2) umma_commit_multicast(&ctl->empty[stage], kMask);   // frees the slot in both CTAs
+                            else umma_commit(&ctl->empty[stage]);
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
@@ -275,8 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         const int quad = ew & 3;                  // TMEM lanes 32*quad .. 32*quad+31 (a warp may only touch its own quadrant)
         const int half = ew >> 2;                 // columns [half*128, half*128 + 128) of the accumulator
         uint32_t seq = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int m0 = (item / groups) * kTileM;
+        for (int item = item0; item < n_items; item += item_step) {
+            const int m0 = (kCluster == 2 ? 2 * (item / groups) + (int)crank : item / groups) * kTileM;
             const int first = job_begin + (item % groups) * jobs_per_item;
             for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
                 const GemmJob& job = jobs[first + jj];      // read-only global data: fields are fetched on demand
@@ -314,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
 
     tcgen05_fence_before();
     __syncthreads();
+    if (kCluster == 2) cluster_sync_all();        // nobody leaves while the peer may still multicast into this CTA
     if (warp == 2) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
@@ -370,21 +421,51 @@ int tc_encode_map(void* out_map, const float* base, int64_t row_stride_elems, in
 int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_count, int jobs_per_item, int m_tiles,
               int num_sms, cudaStream_t stream) {
     static bool configured = false;
-    if (!configured) {
-        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
-    }
-    const int n_items = m_tiles * (job_count / jobs_per_item);
-    const int grid = n_items < num_sms ? n_items : num_sms;
+    static int max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster mode unavailable or disabled)
     // EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
     // 8 no fences, 16 no fp16 stores, 32 no TMEM reads
-    static int debug_mode = -1;
-    if (debug_mode < 0) {
+    static int debug_mode = 0;
+    if (!configured) {
+        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         const char* e = getenv("EMPOSE_TC_DEBUG");
         debug_mode = e ? atoi(e) : 0;
+        // EMPOSE_TC_CLUSTER=1 enables the 2-CTA multicast variant.  It is correct (same parity results) but OFF by default:
+        // measured on the B200 it halves the W traffic out of L2 and changes nothing in time (profiles/r01/README.md) --
+        // the mainloop is bound by SHARED-MEMORY bandwidth (per 512 MMA cycles: 48 KB written by TMA + 48 KB of operand
+        // reads against 128 B/clk), which only a cta_group::2 MMA (half of W per SM) relieves.
+        const char* c = getenv("EMPOSE_TC_CLUSTER");
+        if (c && atoi(c) == 1 && !(debug_mode & 3)) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * (num_sms / 2)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<2>, &cfg) == cudaSuccess) max_clusters = n;
+            else cudaGetLastError();
+        }
+        if (getenv("EMPOSE_TC_VERBOSE")) fprintf(stderr, "empose_b200: gemm executor: %d co-resident 2-CTA clusters on %d SMs\n", max_clusters, num_sms);
+        configured = true;
     }
-    gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(d_jobs, reinterpret_cast<const CUtensorMap*>(d_maps),
-                                                           job_begin, job_count, jobs_per_item, m_tiles, debug_mode);
+    const int groups = job_count / jobs_per_item;
+    const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(d_maps);
+    if (max_clusters > 0 && m_tiles >= 2) {
+        const int n_items = ((m_tiles + 1) / 2) * groups;
+        const int clusters = n_items < max_clusters ? n_items : max_clusters;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode));
+        return EMPOSE_OK;
+    }
+    const int n_items = m_tiles * groups;
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    gemm_tc_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

@@ -279,6 +279,7 @@ struct JobBook {        // jobs + tensor maps of one plan
             if (a1.k > 0) EMPOSE_TRY(get_map(a1.ptr, a1.stride, a1.k, a1.rows, kTileM, W.half, &j.a_map[1]));
             j.w_ptr = W.w; j.w_ld = W.ld; j.w_koff[0] = W.koff[0]; j.w_koff[1] = W.koff[1];
             EMPOSE_TRY(get_map(W.w, W.ld, (int)W.ld, W.n_pad, W.tile_n, W.half, &j.w_map));
+            EMPOSE_TRY(get_map(W.w, W.ld, (int)W.ld, W.n_pad, W.tile_n / 2, W.half, &j.w_map2));
             j.n_begin = t * W.tile_n;
             j.n_count = W.tile_n;
             j.m_rows = m_rows;
