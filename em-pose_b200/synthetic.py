@@ -212,16 +212,59 @@ def lgd_state_dict_spec(n_markers=12, rnn_init=True, hidden_size=512, num_layers
     return spec
 
 
+def rnn_state_dict_spec(n_markers=12, hidden_size=1024, num_layers=2, bidirectional=True, estimate_shape=False,
+                        shape_hidden_size=256, use_marker_pos=True, use_marker_ori=True):
+    """
+    Ordered (key, shape, kind) list of the reference's ``SimpleRNN`` (``empose/nn/models.py:265-289``): a uni- or
+    bidirectional LSTM (``layers.py:114``), ``to_pose`` and, with ``m_estimate_shape``, the BatchNorm-free ``to_shape`` MLP.
+    """
+    in_size = n_markers * ((3 if use_marker_pos else 0) + (9 if use_marker_ori else 0))
+    dirs = 2 if bidirectional else 1
+    h = hidden_size
+    spec = []
+    for layer in range(num_layers):
+        n_in = in_size if layer == 0 else h * dirs
+        for sfx in ([''] + (['_reverse'] if bidirectional else [])):
+            spec.append(('rnn.lstm.weight_ih_l%d%s' % (layer, sfx), (4 * h, n_in), 'w_lstm'))
+            spec.append(('rnn.lstm.weight_hh_l%d%s' % (layer, sfx), (4 * h, h), 'w_lstm'))
+            spec.append(('rnn.lstm.bias_ih_l%d%s' % (layer, sfx), (4 * h,), 'b_lstm'))
+            spec.append(('rnn.lstm.bias_hh_l%d%s' % (layer, sfx), (4 * h,), 'b_lstm'))
+    spec.append(('to_pose.weight', (66, h * dirs), 'w'))
+    spec.append(('to_pose.bias', (66,), 'b'))
+    if estimate_shape:
+        sh = shape_hidden_size
+        spec.append(('to_shape.input_to_hidden.weight', (sh, h * dirs), 'w'))
+        spec.append(('to_shape.input_to_hidden.bias', (sh,), 'b'))
+        spec.append(('to_shape.activation_fn.weight', (1,), 'prelu'))
+        spec.append(('to_shape.hidden_to_output.weight', (10, sh), 'w'))
+        spec.append(('to_shape.hidden_to_output.bias', (10,), 'b'))
+        for b in range(2):
+            for l in range(2):
+                base = 'to_shape.hidden_layers.%d.layers' % b
+                spec.append(('%s.%d.weight' % (base, l * 3), (sh, sh), 'w'))
+                spec.append(('%s.%d.bias' % (base, l * 3), (sh,), 'b'))
+                spec.append(('%s.%d.weight' % (base, l * 3 + 1), (1,), 'prelu'))
+    return spec
+
+
+def synth_rnn_state_dict(seed=0, **model_kwargs):
+    """Deterministic random weights for ``rnn_state_dict_spec`` (same streams / scales as ``synth_state_dict``)."""
+    return _synth_from_spec(rnn_state_dict_spec(**model_kwargs), seed, model_kwargs.get('hidden_size', 1024))
+
+
 def synth_state_dict(seed=0, **model_kwargs):
     """
     Deterministic random weights (numpy RandomState, one stream per key) shaped like torch's default
     initialisation, with BatchNorm running statistics perturbed so that folding them is exercised.
     Returns {key: numpy array}; float32 except ``num_batches_tracked`` (int64).
     """
+    return _synth_from_spec(lgd_state_dict_spec(**model_kwargs), seed, model_kwargs.get('rnn_hidden_size', 512))
+
+
+def _synth_from_spec(spec, seed, rnn_h):
     import zlib
     out = {}
-    rnn_h = model_kwargs.get('rnn_hidden_size', 512)
-    for key, shape, kind in lgd_state_dict_spec(**model_kwargs):
+    for key, shape, kind in spec:
         rng = np.random.RandomState((zlib.crc32(key.encode()) + 7919 * seed) % (2 ** 31 - 1))
         if kind == 'w':
             bound = 1.0 / np.sqrt(shape[1])

@@ -47,38 +47,46 @@ def mlp_eval(x, sd, prefix, num_blocks=2, skip=False):
     return _linear(y, sd, prefix + '.hidden_to_output')
 
 
-def lstm_packed(x, seq_lengths, sd, prefix, num_layers, init_state=None):
+def lstm_packed(x, seq_lengths, sd, prefix, num_layers, init_state=None, bidirectional=False):
     """
-    Unidirectional multi-layer LSTM with packed-sequence semantics (layers.py:133-157): for
-    ``t >= seq_lengths[b]`` the output row is zero and (h, c) stop updating.  Gate order i, f, g, o.
-    :param x: (B, F, in).  :param init_state: (h0, c0) each (layers, B, H) or None.
-    :return: outputs (B, F, H), (h_n, c_n) each (layers, B, H).
+    Multi-layer LSTM with packed-sequence semantics (layers.py:133-157): for ``t >= seq_lengths[b]`` the output row is
+    zero and (h, c) stop updating.  Gate order i, f, g, o.  With ``bidirectional`` the reverse direction of every layer
+    walks each sequence from its last valid frame down to frame 0 (``pack_padded_sequence`` semantics -- equivalently:
+    time runs F-1 .. 0 and the state of a sequence only starts moving at ``t = len - 1``) and a layer's output is
+    ``[h_forward | h_reverse]``.
+    :param x: (B, F, in).  :param init_state: (h0, c0) each (layers * directions, B, H) or None.
+    :return: outputs (B, F, H * directions), (h_n, c_n) each (layers * directions, B, H).
     """
     bsz, n_frames, _ = x.shape
     hid = sd['%s.weight_hh_l0' % prefix].shape[1]
     lengths = torch.as_tensor(seq_lengths).to(torch.long).reshape(-1)
+    dirs = 2 if bidirectional else 1
     layer_in = x
     h_n, c_n = [], []
     for layer in range(num_layers):
-        w_ih = sd['%s.weight_ih_l%d' % (prefix, layer)]
-        w_hh = sd['%s.weight_hh_l%d' % (prefix, layer)]
-        bias = sd['%s.bias_ih_l%d' % (prefix, layer)] + sd['%s.bias_hh_l%d' % (prefix, layer)]
-        if init_state is None:
-            h = torch.zeros(bsz, hid, dtype=x.dtype)
-            c = torch.zeros(bsz, hid, dtype=x.dtype)
-        else:
-            h, c = init_state[0][layer].to(x.dtype), init_state[1][layer].to(x.dtype)
-        outs = []
-        for t in range(n_frames):
-            gates = layer_in[:, t] @ w_ih.T + h @ w_hh.T + bias
-            gi, gf, gg, go = gates.split(hid, dim=1)
-            c_new = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
-            h_new = torch.sigmoid(go) * torch.tanh(c_new)
-            live = (t < lengths).to(x.dtype).unsqueeze(1)
-            c = live * c_new + (1 - live) * c
-            h = live * h_new + (1 - live) * h
-            outs.append(live * h_new)
-        layer_in = torch.stack(outs, dim=1)
-        h_n.append(h)
-        c_n.append(c)
+        outs_dir = []
+        for d in range(dirs):
+            sfx = '_reverse' if d == 1 else ''
+            w_ih = sd['%s.weight_ih_l%d%s' % (prefix, layer, sfx)]
+            w_hh = sd['%s.weight_hh_l%d%s' % (prefix, layer, sfx)]
+            bias = sd['%s.bias_ih_l%d%s' % (prefix, layer, sfx)] + sd['%s.bias_hh_l%d%s' % (prefix, layer, sfx)]
+            if init_state is None:
+                h = torch.zeros(bsz, hid, dtype=x.dtype)
+                c = torch.zeros(bsz, hid, dtype=x.dtype)
+            else:
+                h, c = init_state[0][layer * dirs + d].to(x.dtype), init_state[1][layer * dirs + d].to(x.dtype)
+            outs = [None] * n_frames
+            for t in (range(n_frames) if d == 0 else range(n_frames - 1, -1, -1)):
+                gates = layer_in[:, t] @ w_ih.T + h @ w_hh.T + bias
+                gi, gf, gg, go = gates.split(hid, dim=1)
+                c_new = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+                h_new = torch.sigmoid(go) * torch.tanh(c_new)
+                live = (t < lengths).to(x.dtype).unsqueeze(1)
+                c = live * c_new + (1 - live) * c
+                h = live * h_new + (1 - live) * h
+                outs[t] = live * h_new
+            outs_dir.append(torch.stack(outs, dim=1))
+            h_n.append(h)
+            c_n.append(c)
+        layer_in = torch.cat(outs_dir, dim=-1)
     return layer_in, (torch.stack(h_n), torch.stack(c_n))

@@ -22,6 +22,18 @@ TRAIN_CASES = {
 }
 
 
+#: (Bi)RNN golden cases, mirrored from tests/golden/make_golden_rnn.py
+RNN_CASES = {
+    'rnn_bi12_shape_fk': dict(cfg=dict(n_markers=12, hidden_size=1024, num_layers=2, bidirectional=True, estimate_shape=True,
+                                       average_shape=True, do_fk=True),
+                              weights=dict(n_markers=12, hidden_size=1024, num_layers=2, bidirectional=True, estimate_shape=True)),
+    'rnn_bi6': dict(cfg=dict(n_markers=6, hidden_size=256, num_layers=2, bidirectional=True),
+                    weights=dict(n_markers=6, hidden_size=256, num_layers=2, bidirectional=True, estimate_shape=False)),
+    'rnn_uni12': dict(cfg=dict(n_markers=12, hidden_size=128, num_layers=3, bidirectional=False),
+                      weights=dict(n_markers=12, hidden_size=128, num_layers=3, bidirectional=False, estimate_shape=False)),
+}
+
+
 def train_inputs(gold, dtype=torch.float32):
     get = lambda k: torch.from_numpy(gold[k]).to(dtype)
     masks = torch.from_numpy(gold['marker_masks']) if 'marker_masks' in gold else None
