@@ -243,7 +243,9 @@ int check_config(const empose_ief_config& c) {
     return EMPOSE_OK;
 }
 
-int upload_submodel(empose_ief* ctx, const TensorTable& tt) {
+}  // namespace
+
+int upload_submodel(IefData* ctx, const TensorTable& tt) {
     const int32_t* dims;
     EMPOSE_TRY(tt.get_i32("sub.dims", 6, &dims));   // n_verts, vp_dim, n_faces, max_degree, n_skin, n_sensors
     SubModel& m = ctx->sub;
@@ -346,6 +348,8 @@ int upload_submodel(empose_ief* ctx, const TensorTable& tt) {
                            [&](int r) { return RowSource{P + (size_t)r * vp, nullptr, 1.0, 0.0}; }, &ctx->pbt));
     return EMPOSE_OK;
 }
+
+namespace {
 
 int pack_lstm(empose_ief* ctx, const TensorTable& tt) {
     const int H = ctx->cfg.rnn_hidden_size, L = ctx->cfg.rnn_num_layers;

@@ -385,11 +385,15 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
 struct empose_ief : empose::IefData {};
 
 namespace empose {
+// uploads the "sub.*" arrays (SMPL sub-model, sensor topology) and packs the pose-blend operands into ctx->pb / ctx->pbt;
+// needs ctx->round and ctx->arena (model.cu)
+int upload_submodel(IefData* ctx, const TensorTable& tt);
+
 // A operand of the pose-blend GEMM: [pf_hi | pf_lo] then pf_hi again in TF32 mode, plain pf in FP32 mode
-inline ASrc pose_blend_a0(const empose_ief* ctx, const float* pf, int rows) {
+inline ASrc pose_blend_a0(const IefData* ctx, const float* pf, int rows) {
     return ASrc{pf, ctx->pf_stride, ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad, rows};
 }
-inline ASrc pose_blend_a1(const empose_ief* ctx, const float* pf, int rows) {
+inline ASrc pose_blend_a1(const IefData* ctx, const float* pf, int rows) {
     return ctx->round ? ASrc{pf, ctx->pf_stride, kPoseFeatPad, rows} : ASrc{};
 }
 }  // namespace empose

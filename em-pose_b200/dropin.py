@@ -19,9 +19,12 @@ def install():
     def create_model(config, *args):
         if config.m_type in ('ief', 'lgd'):
             return b200_models.IterativeErrorFeedback(config, *args)
-        return ref_create(config, *args)          # the baselines stay on the reference implementation
+        if config.m_type == 'rnn' and not getattr(config, 'm_learn_init_state', False):
+            return b200_models.SimpleRNN(config, *args)
+        return ref_create(config, *args)          # ResNet (and learned initial states) stay on the reference implementation
 
     ref_models.IterativeErrorFeedback = b200_models.IterativeErrorFeedback
+    ref_models.SimpleRNN = b200_models.SimpleRNN
     ref_models.create_model = create_model
     ref_smpl.SMPLLayer = b200_smpl.SMPLLayer
     ref_smpl.create_default_smpl_model = b200_smpl.create_default_smpl_model

@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_creat
                     'empose_gemm_selftest', 'empose_gemm_bench', 'empose_smpl_create', 'empose_smpl_destroy',
                     'empose_smpl_forward', 'empose_train_layout', 'empose_train_sizes', 'empose_train_create',
                     'empose_train_destroy', 'empose_train_forward', 'empose_train_backward',
-                    'empose_train_last_launch_count')
+                    'empose_train_last_launch_count', 'empose_rnn_create', 'empose_rnn_destroy', 'empose_rnn_forward',
+                    'empose_rnn_last_launch_count')
 
 
 class EmposeError(RuntimeError):
@@ -48,6 +49,12 @@ class IefConfig(ctypes.Structure):
 
 class LossWeights(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ('pose_weight', 'shape_weight', 'reprojection_weight', 'fk_weight')]
+
+
+class RnnConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('n_markers', 'hidden_size', 'num_layers', 'bidirectional', 'learn_init_state',
+                                              'estimate_shape', 'shape_hidden_size', 'average_shape', 'do_fk',
+                                              'use_marker_pos', 'use_marker_ori', 'precision', 'device')]
 
 
 class History(ctypes.Structure):
@@ -114,6 +121,14 @@ def load():
     lib.empose_train_backward.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LossWeights), ctypes.POINTER(ctypes.c_float), vp]
     lib.empose_train_last_launch_count.restype = ctypes.c_int64
     lib.empose_train_last_launch_count.argtypes = [vp]
+    lib.empose_rnn_create.restype = ctypes.c_int
+    lib.empose_rnn_create.argtypes = [ctypes.POINTER(RnnConfig), ctypes.POINTER(Tensor), i32, ctypes.POINTER(vp)]
+    lib.empose_rnn_destroy.restype = None
+    lib.empose_rnn_destroy.argtypes = [vp]
+    lib.empose_rnn_forward.restype = ctypes.c_int
+    lib.empose_rnn_forward.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.empose_rnn_last_launch_count.restype = ctypes.c_int64
+    lib.empose_rnn_last_launch_count.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -392,6 +407,61 @@ class TrainContext(object):
         _check(load().empose_train_backward(self._handle, _ptr(poses_gt), _ptr(shapes_gt), _ptr(joints_gt), ctypes.byref(w),
                                             vals, _stream()))
         return dict(zip(('pose', 'shape', 'reconstruction', 'fk', 'total_loss'), [float(v) for v in vals]))
+
+
+class RnnContext(object):
+    """Owns one ``empose_rnn*``: the (Bi)RNN baseline (``SimpleRNN``, models.py:265-317) on one device."""
+
+    def __init__(self, config, arrays):
+        lib = load()
+        cfg = RnnConfig()
+        for name, _ in RnnConfig._fields_:
+            setattr(cfg, name, int(config[name]))
+        self.config = dict(config)
+        table, keep = make_tensor_table(arrays)
+        handle = ctypes.c_void_p()
+        _check(lib.empose_rnn_create(ctypes.byref(cfg), table, len(arrays), ctypes.byref(handle)))
+        del keep
+        self._handle = handle
+        self.n_state = int(config['num_layers']) * (2 if config['bidirectional'] else 1)
+        self.hidden = int(config['hidden_size'])
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            load().empose_rnn_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def last_launch_count(self):
+        return int(load().empose_rnn_last_launch_count(self._handle))
+
+    def forward(self, marker_pos, marker_oris, seq_lengths, lstm_state=None, is_new_sequence=True):
+        """CUDA tensors in / out: pose (B,F,66), shape (B,F,10) | None, joints (B,F,66) | None, lstm_state (2,L*dirs,B,H)."""
+        import torch
+        dev = marker_pos.device
+        if dev.type != 'cuda':
+            raise EmposeError('inputs must be CUDA tensors (no CPU path)')
+        b, f = int(marker_pos.shape[0]), int(marker_pos.shape[1])
+        f32 = lambda t: t.to(dtype=torch.float32).contiguous()
+        marker_pos, marker_oris = f32(marker_pos).reshape(b, f, 36), f32(marker_oris).reshape(b, f, 108)
+        seq_lengths = seq_lengths.to(device=dev, dtype=torch.int32).contiguous()
+        opts = dict(dtype=torch.float32, device=dev)
+        pose = torch.empty((b, f, 66), **opts)
+        shape = torch.empty((b, f, 10), **opts) if self.config['estimate_shape'] else None
+        joints = torch.empty((b, f, 66), **opts) if self.config['do_fk'] else None
+        if lstm_state is not None and not is_new_sequence:
+            state = f32(lstm_state).reshape(2, self.n_state, b, self.hidden).clone()
+        else:
+            state = torch.zeros((2, self.n_state, b, self.hidden), **opts)
+        _check(load().empose_rnn_forward(self._handle, _ptr(marker_pos), _ptr(marker_oris), _ptr(seq_lengths), _ptr(state),
+                                         int(bool(is_new_sequence)), b, f, _ptr(pose), _ptr(shape), _ptr(joints), _stream()))
+        return {'pose': pose, 'shape': shape, 'joints': joints, 'lstm_state': state}
 
 
 class SmplContext(object):

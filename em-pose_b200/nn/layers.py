@@ -60,12 +60,12 @@ class RNNLayer(nn.Module):
     def __init__(self, input_size, hidden_size, num_layers, output_size=None, bidirectional=False, dropout=0.0,
                  learn_init_state=False):
         super(RNNLayer, self).__init__()
-        if bidirectional or learn_init_state or output_size is not None:
-            raise ValueError('the LGD init RNN is unidirectional without learned initial state or output layer')
+        if learn_init_state or output_size is not None:
+            raise NotImplementedError('learned initial states / an output layer inside RNNLayer are not supported')
         if dropout > 0.0:
-            raise ValueError('input dropout is a training feature; the B200 path is inference only for now')
+            raise ValueError('input dropout > 0 is not supported (the released models use 0)')
         self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
-        self.is_bidirectional, self.num_directions, self.learn_init_state = False, 1, False
+        self.is_bidirectional, self.num_directions, self.learn_init_state = bool(bidirectional), 2 if bidirectional else 1, False
         self.init_state = None
         self.final_state = None
-        self.lstm = nn.LSTM(input_size, hidden_size, num_layers)
+        self.lstm = nn.LSTM(input_size, hidden_size, num_layers, bidirectional=bool(bidirectional))

@@ -28,8 +28,10 @@ def create_model(config, *args):
     m_type = config.m_type
     if m_type in ('ief', 'lgd'):
         return IterativeErrorFeedback(config, *args)
-    if m_type in ('rnn', 'resnet'):
-        raise NotImplementedError("model type '%s' is outside the LGD hot path built by empose_b200" % m_type)
+    if m_type == 'rnn':
+        return SimpleRNN(config, *args)
+    if m_type == 'resnet':
+        raise NotImplementedError("model type 'resnet' is not built by empose_b200")
     raise ValueError("Model type '{}' unknown.".format(m_type))
 
 
@@ -396,4 +398,152 @@ class IterativeErrorFeedback(nn.Module):
             prefix = 'train' if self.training else 'valid'
             for k in loss_vals:
                 writer.add_scalar('{}/{}'.format(k, prefix), loss_vals[k], global_step)
+        return total, loss_vals
+
+
+class SimpleRNN(nn.Module):
+    """The uni- / bidirectional RNN baseline (``models.py:265-366``; "BiRNN" in the paper), inference on the B200.
+
+    Same constructor arguments, ``forward`` signature and outputs, ``rnn.final_state`` carry and state-dict keys as the
+    reference; ``backward`` returns the loss values in eval mode (``eval/helpers.py:86``).  Training this baseline is
+    not built."""
+
+    def __init__(self, config, smpl_layer=None, precision=_lib.PRECISION_FP16):
+        super(SimpleRNN, self).__init__()
+        self.config = config
+        self.n_markers = config.n_markers if getattr(config, 'n_markers', -1) > -1 else C.N_TRACKERS_WO_ROOT
+        assert self.n_markers in [6, 12]
+        self.n_frames = config.window_size
+        self.smpl = smpl_layer
+        self.estimate_shape = config.m_estimate_shape
+        self.shape_avg = config.m_average_shape
+        self.fk_loss_weight = config.m_fk_loss
+        self.do_fk = self.fk_loss_weight > 0.0
+        if self.do_fk:
+            assert self.smpl is not None
+            assert self.estimate_shape                                       # models.py:55
+        self.shape_weight = getattr(config, 'm_shape_loss_weight', 1.0)
+        self.pose_weight = getattr(config, 'm_pose_loss_weight', 1.0)
+        self.precision = precision
+        if getattr(config, 'use_marker_nor', False):
+            raise ValueError('Normals currently not supported.')
+        if getattr(config, 'm_learn_init_state', False):
+            raise NotImplementedError('m_learn_init_state is not supported by empose_b200')
+        input_size = 0
+        if config.use_marker_pos:
+            input_size += self.n_markers * 3
+        if config.use_marker_ori:
+            input_size += self.n_markers * 9
+        self.input_size, self.output_size = input_size, (C.N_JOINTS + 1) * 3
+        setattr(config, 'input_size', input_size)
+        setattr(config, 'output_size', self.output_size)
+        hidden = config.m_hidden_size
+        dirs = 2 if config.m_bidirectional else 1
+        self.rnn = RNNLayer(input_size, hidden, config.m_num_layers, bidirectional=config.m_bidirectional,
+                            dropout=config.m_dropout, learn_init_state=False)
+        self.to_pose = nn.Linear(hidden * dirs, self.output_size)
+        if self.estimate_shape:
+            self.to_shape = MLP(input_size=hidden * dirs, output_size=C.N_SHAPE_PARAMS, hidden_size=config.m_shape_hidden_size,
+                                num_layers=2, dropout_p=config.m_dropout_hidden, skip_connection=config.m_skip_connections,
+                                use_batch_norm=False)
+            if config.m_skip_connections:
+                raise NotImplementedError('skip connections in to_shape are not supported')
+        else:
+            self.to_shape = None
+        self.shape_loss = nn.L1Loss(reduction='none')
+        self._ctx = None
+        self._ctx_key = None
+
+    def model_name(self):
+        """``models.py:283-289`` + ``BaseModel.model_name`` (``:84-94``)."""
+        c = self.config
+        name = "RNN-{}".format('-'.join([str(c.m_hidden_size)] * c.m_num_layers))
+        if c.m_bidirectional:
+            name = "Bi" + name
+        if self.estimate_shape is not None:
+            name += '-shape{}{}'.format(c.m_shape_hidden_size, '-avg' if self.shape_avg else '')
+        if self.do_fk:
+            name += '-fk{}'.format(self.fk_loss_weight)
+        name += '-n{}'.format(self.n_markers)
+        name += '-lr{}'.format(c.lr)
+        return name
+
+    def _native_config(self, device_index):
+        c = self.config
+        return dict(n_markers=self.n_markers, hidden_size=int(c.m_hidden_size), num_layers=int(c.m_num_layers),
+                    bidirectional=int(bool(c.m_bidirectional)), learn_init_state=0, estimate_shape=int(bool(self.estimate_shape)),
+                    shape_hidden_size=int(c.m_shape_hidden_size), average_shape=int(bool(self.shape_avg)), do_fk=int(self.do_fk),
+                    use_marker_pos=int(c.use_marker_pos), use_marker_ori=int(c.use_marker_ori), precision=int(self.precision),
+                    device=int(device_index))
+
+    def native_context(self, device):
+        if device.type != 'cuda':
+            raise _lib.EmposeError('empose_b200 runs on CUDA devices only (no CPU fallback); got %s' % device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        tensors = [t for k, t in self.state_dict(keep_vars=True).items()]
+        key = (index, self.precision) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._ctx is None or key != self._ctx_key:
+            if self._ctx is not None:
+                self._ctx.close()
+            arrays = {k: np.ascontiguousarray(v.detach().cpu().numpy(), dtype=np.float32) for k, v in self.state_dict().items()
+                      if not k.startswith('smpl.') and v.is_floating_point()}
+            if self.do_fk:
+                arrays.update(self.smpl.submodel_arrays())
+            self._ctx = _lib.RnnContext(self._native_config(index), arrays)
+            self._ctx_key = key
+        return self._ctx
+
+    def forward(self, batch, window_size=None, is_new_sequence=True):
+        """``models.py:291-317``.  ``window_size`` is ignored, as in the reference."""
+        if self.training:
+            raise NotImplementedError('training the (Bi)RNN baseline is not built in empose_b200; call net.eval()')
+        if is_new_sequence:
+            self.rnn.final_state = None
+        self.rnn.init_state = self.rnn.final_state
+        inputs = batch.get_inputs()
+        marker_pos = inputs['marker_pos']
+        ctx = self.native_context(marker_pos.device)
+        state = None
+        if self.rnn.final_state is not None:
+            state = torch.stack([self.rnn.final_state[0], self.rnn.final_state[1]])
+        res = ctx.forward(marker_pos, inputs['marker_oris'], batch.seq_lengths, lstm_state=state, is_new_sequence=state is None)
+        self.rnn.final_state = (res['lstm_state'][0], res['lstm_state'][1])
+        pose = res['pose']
+        return {'pose_hat': pose[:, :, 3:], 'root_ori_hat': pose[:, :, :3], 'shape_hat': res['shape'], 'joints_hat': res['joints']}
+
+    def backward(self, batch, model_out, writer=None, global_step=None):
+        """``models.py:319-366`` loss values (eval mode)."""
+        if self.training:
+            raise NotImplementedError('training the (Bi)RNN baseline is not built in empose_b200')
+        pose_hat, root_ori_hat, shape_hat = model_out['pose_hat'], model_out['root_ori_hat'], model_out['shape_hat']
+        n, f = batch.batch_size, batch.seq_length
+        lengths = batch.seq_lengths
+
+        def normal_mse(gt, hat):                                             # loss.py:44-62
+            diff = hat - gt
+            per_frame = (diff * diff).sum(dim=-1).sum(dim=-1)
+            if batch.marker_masks is not None:
+                per_frame = per_frame * batch.marker_masks.logical_not().any(dim=-1).logical_not()
+            return IterativeErrorFeedback._masked_mean(per_frame, lengths)
+
+        pose_loss = normal_mse(batch.poses_body.reshape(n, f, -1, 3), pose_hat.reshape(n, f, -1, 3))
+        root_loss = normal_mse(batch.poses_root.reshape(n, f, -1, 3), root_ori_hat.reshape(n, f, -1, 3))
+        dev = pose_hat.device
+        shape_loss = torch.zeros(1, device=dev)
+        if self.estimate_shape:
+            gt = batch.shapes.unsqueeze(1).repeat((1, f, 1))
+            shape_loss = IterativeErrorFeedback._masked_mean((gt - shape_hat).abs().mean(-1), lengths)
+        fk_loss = torch.zeros(1, device=dev)
+        if self.do_fk:
+            diff = model_out['joints_hat'].reshape(n, f, -1, 3) - batch.joints_gt.reshape(n, f, -1, 3)
+            per_frame = torch.sqrt((diff * diff).sum(dim=-1)).sum(dim=-1)
+            if batch.marker_masks is not None:
+                per_frame = per_frame * batch.marker_masks.logical_not().any(dim=-1).logical_not()
+            fk_loss = IterativeErrorFeedback._masked_mean(per_frame, lengths)
+        total = pose_loss + root_loss + shape_loss + self.fk_loss_weight * fk_loss
+        loss_vals = {'pose': float(pose_loss), 'root_pose': float(root_loss), 'shape': float(shape_loss), 'fk': float(fk_loss),
+                     'total_loss': float(total)}
+        if writer is not None:
+            for k in loss_vals:
+                writer.add_scalar('{}/{}'.format(k, 'valid'), loss_vals[k], global_step)
         return total, loss_vals

@@ -21,6 +21,8 @@
  *                                     (BatchNorm1d on batch statistics, layers.py:26,57; the gradient side effect
  *                                     of models.py:576)
  *   empose_train_backward          <- IterativeErrorFeedback.backward                  empose/nn/models.py:634-688
+ *   empose_rnn_create / _forward   <- create_model(m_type='rnn') + SimpleRNN.forward (the BiRNN baseline)
+ *                                                                                 empose/nn/models.py:265-317
  *   empose_gemm_selftest           <- (no reference counterpart) checks the tcgen05 GEMM engine
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
@@ -206,6 +208,41 @@ int empose_train_forward(empose_train* ctx, const float* marker_pos, const float
 int empose_train_backward(empose_train* ctx, const float* poses_gt, const float* shapes_gt, const float* joints_gt,
                           const empose_loss_weights* weights, float* loss_vals, void* stream);
 int64_t empose_train_last_launch_count(const empose_train* ctx);
+
+/* ---- (Bi)RNN baseline (BASELINE config 4) ------------------------------------------------------- */
+typedef struct {
+    int32_t n_markers;          /* 6 or 12 */
+    int32_t hidden_size;        /* m_hidden_size (1024 in the released BiRNNs, configuration.py:165) */
+    int32_t num_layers;         /* m_num_layers */
+    int32_t bidirectional;      /* m_bidirectional */
+    int32_t learn_init_state;   /* m_learn_init_state: must be 0 (not supported) */
+    int32_t estimate_shape;     /* m_estimate_shape: the BatchNorm-free to_shape MLP (models.py:276-280) */
+    int32_t shape_hidden_size;  /* m_shape_hidden_size */
+    int32_t average_shape;      /* m_average_shape */
+    int32_t do_fk;              /* m_fk_loss > 0: also return the 22 joints (models.py:134-144) */
+    int32_t use_marker_pos;
+    int32_t use_marker_ori;
+    int32_t precision;          /* EMPOSE_PRECISION_* */
+    int32_t device;
+} empose_rnn_config;
+
+typedef struct empose_rnn empose_rnn;
+
+/* `tensors`: the reference's state dict ("rnn.lstm.weight_ih_l0[_reverse]", "to_pose.*", "to_shape.*") plus, when
+ * do_fk is set, the "sub.*" arrays of the SMPL sub-model. */
+int empose_rnn_create(const empose_rnn_config* cfg, const empose_tensor* tensors, int32_t n_tensors, empose_rnn** out);
+void empose_rnn_destroy(empose_rnn* ctx);
+
+/* SimpleRNN.forward over B sequences of F frames (device pointers, stream-ordered):
+ *   marker_pos [B][F][36], marker_oris [B][F][108], seq_lengths [B] int32
+ *   lstm_state [2][num_layers * directions][B][H] (h then c; index layer * directions + direction), in/out or NULL:
+ *              read unless is_new_sequence, always written (RNNLayer.final_state, models.py:292-294)
+ *   pose_hat [B][F][66] (root first); shape_hat [B][F][10] and joints_hat [B][F][66] are written when the
+ *   configuration produces them (estimate_shape / do_fk) and the pointer is non-NULL. */
+int empose_rnn_forward(empose_rnn* ctx, const float* marker_pos, const float* marker_oris, const int32_t* seq_lengths,
+                       float* lstm_state, int32_t is_new_sequence, int32_t B, int32_t F, float* pose_hat, float* shape_hat,
+                       float* joints_hat, void* stream);
+int64_t empose_rnn_last_launch_count(const empose_rnn* ctx);
 
 /* Optional timing of the tensor-core GEMM executor: while enabled, every executor launch is bracketed by
  * CUDA events on its stream (TF32 mode only).  empose_ief_profile_read waits for them, returns the summed

@@ -103,6 +103,26 @@ def test_training_layout_covers_every_trainable_tensor(smpl_npz):
             assert sum(got.values()) + 169 == 5721419
 
 
+def test_rnn_state_dict_keys_match_reference_layout(smpl_npz):
+    """SimpleRNN mirror: the reference's keys for the bidirectional LSTM, to_pose and the BatchNorm-free to_shape MLP."""
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from empose_b200.helpers.configuration import Configuration
+    from empose_b200.nn.models import SimpleRNN, create_model
+    cfg = Configuration(dict(m_type='rnn', m_hidden_size=1024, m_num_layers=2, m_bidirectional=True, m_estimate_shape=True,
+                             m_average_shape=True, m_fk_loss=0.1, use_marker_pos=True, use_marker_ori=True, n_markers=12))
+    net = create_model(cfg, SMPLLayer(smpl_npz).to(dtype=torch.float32))
+    assert isinstance(net, SimpleRNN)
+    keys = {k for k in net.state_dict() if not k.startswith('smpl.')}
+    spec = {k for k, _, _ in synthetic.rnn_state_dict_spec(n_markers=12, hidden_size=1024, num_layers=2, bidirectional=True,
+                                                           estimate_shape=True)}
+    assert keys == spec
+    gold = util.load_golden('rnn_bi12_shape_fk')
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == int(gold['n_trainable_params'])
+    assert net.model_name() == 'BiRNN-1024-1024-shape256-avg-fk0.1-n12-lr0.001'       # what the reference printed for this config
+    with pytest.raises(native.EmposeError):
+        net.eval()(util.DuckBatch(torch.zeros(1, 2, 36), torch.zeros(1, 2, 108), None, None, torch.tensor([2])))
+
+
 def test_submodel_arrays_are_complete(smpl_npz):
     net = util.build_module(smpl_npz)
     sub = net.smpl.submodel_arrays()
