@@ -444,13 +444,115 @@ def run_b200_train(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+BIRNN_METRIC = 'frames/sec BiRNN-2x1024 6-sensor, one full stream (batch 1)'
+
+
+def run_b200_birnn(args, rank, local_rank, world):
+    """BASELINE config 4: the bidirectional 2 x 1024 LSTM baseline on ONE long 6-sensor stream (batch 1, ~15k frames).
+    Along time the recurrence does not shard: under torchrun every rank runs its own replica stream."""
+    from empose_b200 import lib, synthetic
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from empose_b200.helpers.configuration import Configuration
+    from empose_b200.nn.models import SimpleRNN
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import util
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0)
+    wk = dict(n_markers=6, hidden_size=1024, num_layers=2, bidirectional=True, estimate_shape=False)
+    cfg = Configuration(dict(m_type='rnn', m_hidden_size=1024, m_num_layers=2, m_bidirectional=True, use_marker_pos=True,
+                             use_marker_ori=True, n_markers=6, window_size=32))
+    prec = {'fp16': lib.PRECISION_FP16, 'tf32': lib.PRECISION_TF32, 'fp32': lib.PRECISION_FP32}[args.precision]
+    net = SimpleRNN(cfg, SMPLLayer(npz).to(dtype=torch.float32), precision=prec)
+    sd = net.state_dict()
+    for k, v in synthetic.synth_rnn_state_dict(seed=0, **wk).items():
+        sd[k] = torch.from_numpy(np.asarray(v))
+    net.load_state_dict(sd, strict=True)
+    net = net.to(device).eval()
+    f = args.frames
+    g = torch.Generator().manual_seed(77 + rank)
+    pos = (0.3 * torch.randn(1, f, 36, generator=g)).pin_memory()
+    ori = (torch.eye(3).reshape(1, 1, 1, 9) + 0.05 * torch.randn(1, f, 12, 9, generator=g)).reshape(1, f, 108).pin_memory()
+    lens = torch.tensor([f])
+    z = torch.zeros(1, 12, 3)
+    host = util.DuckBatch(pos, ori, z.unsqueeze(-1).repeat(1, 1, 1, 3), z, lens)
+    dev_batch = host.to(device)
+
+    def step_device():
+        with torch.no_grad():
+            net(dev_batch)
+
+    def step_host():
+        with torch.no_grad():
+            out = net(host.to(device))
+        return out['pose_hat'].cpu(), out['root_ori_hat'].cpu()
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    t0 = time.perf_counter()
+    step_device()
+    torch.cuda.synchronize(device)
+    plan_s = time.perf_counter() - t0                      # first call: builds the execution plan (jobs + tensor maps)
+    for _ in range(max(args.warmup, 3) - 1):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(step_device, args.steps, barrier)
+    ms_e2e = timed(step_host, max(2, min(args.steps, 5)), barrier) / max(2, min(args.steps, 5))
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    sampler.stop_flag.set()
+    sampler.join()
+    launches = net._ctx.last_launch_count
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import rnn as oracle_rnn
+        n = min(f, 1500)
+        sd32 = util.torch_state_dict(synthetic.synth_rnn_state_dict(seed=0, **wk))
+        ocfg = oracle_rnn.RnnConfig(n_markers=6, hidden_size=1024, num_layers=2, bidirectional=True)
+        fn = lambda: oracle_rnn.rnn_forward(ocfg, sd32, None, pos[:, :n], ori[:, :n], torch.tensor([n]))
+        with torch.no_grad():
+            fn()
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+        cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': 'the first %d frames of the stream, one pass after 1 warm-up' % n}
+    if rank == 0:
+        print(json.dumps({
+            'metric': BIRNN_METRIC, 'value': world * f * args.steps / (ms / 1000.0), 'unit': 'frames/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+            'config': {'workload': 'BiRNN 2 x 1024, 6 sensors, one stream of %d frames, batch 1 (BASELINE config 4); replicas only across GPUs' % f,
+                       'frames': f, 'plan_build_s': plan_s,
+                       'note': 'every time step of a layer is one launch of the job executor on a single 128-row tile (1 row used): latency-bound'},
+            'clocks': sampler.summary(), 'gpu_launches': int(launches * args.steps),
+            'e2e': {'value': world * f / (ms_e2e / 1000.0), 'unit': 'frames/s', 'ms_per_step': ms_e2e,
+                    'h2d_bytes_per_step': f * 144 * 4, 'd2h_bytes_per_step': f * 66 * 4, 'api': 'SimpleRNN.forward on a host batch + .cpu()'},
+            'cpu_baseline': cpu}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='infer', choices=['infer', 'train'])
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'birnn'])
+    ap.add_argument('--frames', type=int, default=15000, help='stream length of the birnn workload')
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'tf32', 'fp32'], help='inference arithmetic of the learned layers')
     ap.add_argument('--windows', type=int, default=None, help='windows per GPU (inference: 4096 = BASELINE config 3; training: 512)')
     ap.add_argument('--ref-windows', type=int, default=16, help='windows per step of the CPU reference arm / baseline')
@@ -466,7 +568,9 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)')
-    if args.workload == 'train':
+    if args.workload == 'birnn':
+        run_b200_birnn(args, rank, local_rank, world)
+    elif args.workload == 'train':
         run_b200_train(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
