@@ -2,6 +2,8 @@
 // sub-model forward / reverse pass (8 frames per CTA, per-frame state in shared memory, every phase of
 // frame_math.h flattened over (frame, item) across the CTA) and the gradient-feature finish.  Reference call sites are cited in
 // frame_kernels.h and frame_math.h.
+#include <stdlib.h>
+
 #include "../../include/empose_b200.h"
 #include "common.cuh"
 #include "frame_kernels.h"
@@ -146,10 +148,9 @@ __global__ void __launch_bounds__(256) pose_feature_kernel(const float* __restri
 // phase of frame_math.h is flattened over (frame, item) across all threads of the CTA.  Narrow phases (the
 // 3-row kinematic chain, the 12 sensors) then occupy one or two warps for ALL frames of the CTA instead of a
 // few lanes in every warp, which is what the one-warp-per-frame mapping wasted most of its issue slots on.
-constexpr int kFramesPerCta = 4;
+// (kFramesPerCta, CTAs per SM) is a template parameter pair: more frames in flight per SM hide the latency of the narrow
+// phases (the kinematic chains, the 12 sensor frames), fewer threads per frame make the wide phases longer.
 constexpr int kMainThreads = 256;
-constexpr int kMainCtasPerSm = 4;
-constexpr int kGroup = kMainThreads / kFramesPerCta;     // threads per frame in the frame-grouped mapping
 
 // flattened (frame, item) loop over threads [t0, t0 + nt) of the CTA
 #define EMPOSE_FOR_ITEMS_ON(t0, nt, n_items, f, i)                                                       \
@@ -160,14 +161,17 @@ constexpr int kGroup = kMainThreads / kFramesPerCta;     // threads per frame in
 // per frame, no integer division per item
 #define EMPOSE_FOR_FRAME_ITEMS(n_items, f, i)                                                   \
     for (int f = threadIdx.x / kGroup, i = threadIdx.x % kGroup, _n = (n_items); f < nf && i < _n; i += kGroup)
+static_assert(kMainThreads % 32 == 0, "whole warps");
 // items of the serial kinematic chains, on the last warp of the CTA
 #define EMPOSE_FOR_ITEMS_CHAIN(n_items, f, i) EMPOSE_FOR_ITEMS_ON(kMainThreads - 32, 32, n_items, f, i)
 
 // optional phase timing (development aid): thread 0 of one mid-grid CTA stores clock64() after every barrier
 #define EMPOSE_TICK(k) do { if (p.ticks && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) p.ticks[k] = clock64(); } while (0)
 
-template <int VP>
+template <int VP, int kFramesPerCta, int kMainCtasPerSm>
 __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(MainParams p) {
+    constexpr int kGroup = kMainThreads / kFramesPerCta;     // threads per frame in the frame-grouped mapping
+    static_assert(3 * kFramesPerCta <= 32, "the serial chains of all frames of a CTA run on one warp");
     extern __shared__ __align__(16) uint8_t smem_main[];
     FrameState<float, VP>* st = reinterpret_cast<FrameState<float, VP>*>(smem_main);
     const SubModel& m = p.sub;
@@ -339,26 +343,41 @@ int launch_pose_features(const float* theta, float* pf, int pf_stride, int pf_sp
     return EMPOSE_OK;
 }
 
-int launch_main(const MainParams& p, cudaStream_t s) {
-    const unsigned grid = blocks_for(p.R, kFramesPerCta);
+template <int VP, int FPC, int CPS>
+int launch_main_variant(const MainParams& p, cudaStream_t s) {
     static bool configured = false;
+    const size_t smem = sizeof(FrameState<float, VP>) * FPC;
     if (!configured) {
-        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(main_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(FrameState<float, 256>) * kFramesPerCta)));
-        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(main_kernel<kMaxVp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(FrameState<float, kMaxVp>) * kFramesPerCta)));
+        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(main_kernel<VP, FPC, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    if (p.sub.vp_dim <= 256) {
-        main_kernel<256><<<grid, kMainThreads, sizeof(FrameState<float, 256>) * kFramesPerCta, s>>>(p);
-    } else if (p.sub.vp_dim <= kMaxVp) {
-        main_kernel<kMaxVp><<<grid, kMainThreads, sizeof(FrameState<float, kMaxVp>) * kFramesPerCta, s>>>(p);
-    } else {
-        set_last_error("sensor sub-mesh too large (more than 128 vertices)");
-        return EMPOSE_E_ARG;
-    }
+    main_kernel<VP, FPC, CPS><<<blocks_for(p.R, FPC), kMainThreads, smem, s>>>(p);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
+}
+
+int launch_main(const MainParams& p, cudaStream_t s) {
+    // (frames per CTA, CTAs per SM) for the common sub-mesh size.  Measured on the B200 at 4096 windows x 32 frames
+    // (whole step, profiles/r01/README.md): (4,4) 17.25 ms, (5,4) 16.68 ms, (6,3) 16.82 ms, (7,3) 17.29 ms, (8,2) 18.56 ms:
+    // 20 frames in flight per SM is the sweet spot between latency hiding and threads per frame.
+    // EMPOSE_MAIN_VARIANT=0/2/3/4 selects the others (experiments).
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("EMPOSE_MAIN_VARIANT");
+        variant = e ? atoi(e) : 1;
+    }
+    if (p.sub.vp_dim <= 256) {
+        switch (variant) {
+            case 0: return launch_main_variant<256, 4, 4>(p, s);
+            case 2: return launch_main_variant<256, 6, 3>(p, s);
+            case 3: return launch_main_variant<256, 7, 3>(p, s);
+            case 4: return launch_main_variant<256, 8, 2>(p, s);
+            default: return launch_main_variant<256, 5, 4>(p, s);
+        }
+    }
+    if (p.sub.vp_dim <= kMaxVp) return launch_main_variant<kMaxVp, 4, 3>(p, s);
+    set_last_error("sensor sub-mesh too large (more than 128 vertices)");
+    return EMPOSE_E_ARG;
 }
 
 int launch_post(const PostParams& p, cudaStream_t s) {
