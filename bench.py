@@ -535,7 +535,9 @@ def run_b200_birnn(args, rank, local_rank, world):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': 'BiRNN 2 x 1024, 6 sensors, one stream of %d frames, batch 1 (BASELINE config 4); replicas only across GPUs' % f,
                        'frames': f, 'plan_build_s': plan_s,
-                       'note': 'every time step of a layer is one launch of the job executor on a single 128-row tile (1 row used): latency-bound'},
+                       'note': 'fp16 mode: input projections of all frames as one tensor-core GEMM per layer, recurrence in the persistent '
+                               'kernel (W_hh resident in shared memory across 128 cooperating CTAs, hidden vector handed over through L2); '
+                               'latency-bound by design: ~4 us per time step'},
             'clocks': sampler.summary(), 'gpu_launches': int(launches * args.steps),
             'e2e': {'value': world * f / (ms_e2e / 1000.0), 'unit': 'frames/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': f * 144 * 4, 'd2h_bytes_per_step': f * 66 * 4, 'api': 'SimpleRNN.forward on a host batch + .cpu()'},

@@ -14,6 +14,7 @@
 // combined with a bidirectional LSTM).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -25,6 +26,7 @@
 #include "gemm_jobs.h"
 #include "gemm_tc.h"
 #include "model_internal.h"
+#include "rnn_persistent.h"
 
 namespace empose {
 namespace {
@@ -43,6 +45,13 @@ struct RnnPlan {
     int64_t act_rows = 0;
     std::vector<JobRange> steps;                    // [layer * F + s]
     JobRange to_pose, to_shape, pb;
+    // persistent single-sequence path (B == 1, fp16 mode): input projections as one GEMM per layer, W_hh resident in smem
+    bool persistent = false;
+    int pC = 0, pU = 0;
+    float* xw[2] = {nullptr, nullptr};              // [F][4H] per direction, reused by every layer
+    float* hx = nullptr;
+    unsigned* counters = nullptr;
+    std::vector<JobRange> xw_jobs;                  // [layer]
 };
 
 __global__ void gather_state_kernel(const float* __restrict__ seq, int64_t pitch, int t, int col0, float* __restrict__ out, int B,
@@ -71,6 +80,8 @@ struct empose_rnn {
     int in_size = 0, in_stride = 0, n_pos = 0, dirs = 1;
     int slot_of_sensor[kSensors];
     std::vector<PackedMatrix> lstm;      // [layer * dirs + dir]
+    std::vector<PackedMatrix> wih_plain; // fp16 mode: W_ih alone, torch row order, bias = b_ih + b_hh (persistent path)
+    std::vector<__half*> whh_half;       // fp16 mode: W_hh [4H][H] fp16, torch row order
     PackedMatrix to_pose;
     MlpPacked to_shape;
     std::unique_ptr<RnnPlan> plan;
@@ -121,9 +132,25 @@ int build_plan(empose_rnn* ctx, int B, int F, RnnPlan** out) {
             EMPOSE_TRY(A.alloc_n((size_t)B * H, &pl.cstate[l * D + d], true));
         }
     }
+    // ---- single stream: persistent recurrence (rnn_persistent.cu) instead of one launch per time step ----
+    pl.persistent = B == 1 && hf && !ctx->whh_half.empty() && F >= 64 && getenv("EMPOSE_RNN_NO_PERSISTENT") == nullptr &&
+                    lstm_persistent_pick(H, D, fk.num_sms, &pl.pC, &pl.pU);
+    if (pl.persistent) {
+        for (int d = 0; d < D; ++d) EMPOSE_TRY(A.alloc_n(Rz * 4 * H, &pl.xw[d]));
+        EMPOSE_TRY(A.alloc_n((size_t)D * 2 * H, &pl.hx, true));
+        EMPOSE_TRY(A.alloc_n((size_t)64, &pl.counters, true));
+        pl.xw_jobs.resize(L);
+        for (int l = 0; l < L; ++l)
+            for (int d = 0; d < D; ++d) {
+                const PackedMatrix& Wm = ctx->wih_plain[(size_t)l * D + d];
+                ASrc a0 = l == 0 ? ASrc{pl.xin, ctx->in_stride, ctx->in_size, R, hf} : ASrc{pl.hseq[l - 1], W, W, R, hf};
+                GemmJob proto = linear_proto(Wm, false, pl.xw[d], 4 * H, 4 * H);
+                EMPOSE_TRY(pl.book.add(Wm, a0, ASrc{}, proto, R, -1, &pl.xw_jobs[l]));
+            }
+    }
     // ---- LSTM steps ----
-    pl.steps.resize((size_t)L * F);
-    for (int l = 0; l < L; ++l)
+    pl.steps.resize(pl.persistent ? 0 : (size_t)L * F);
+    for (int l = 0; l < L && !pl.persistent; ++l)
         for (int s = 0; s < F; ++s)
             for (int d = 0; d < D; ++d) {
                 const int t = d == 0 ? s : F - 1 - s;
@@ -230,8 +257,30 @@ int rnn_forward(empose_rnn* ctx, RnnPlan& pl, const float* marker_pos, const flo
             EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.cstate[q], 0, st_bytes, s));
         }
     }
+    if (pl.persistent) {
+        int len_host = F;          // B == 1: the one sequence length (device -> host: the kernel takes it as a scalar)
+        EMPOSE_CUDA_TRY(cudaMemcpyAsync(&len_host, pl.seq_len, sizeof(int), cudaMemcpyDeviceToHost, s));
+        EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));
+        for (int l = 0; l < L; ++l) {
+            EMPOSE_TRY(run(ctx, pl, pl.xw_jobs[l], mt_R, s));
+            LstmPersistentParams lp;
+            memset(&lp, 0, sizeof(lp));
+            for (int d = 0; d < D; ++d) { lp.w_hh[d] = ctx->whh_half[(size_t)l * D + d]; lp.xw[d] = pl.xw[d]; }
+            const bool carry = lstm_state && !is_new_sequence;
+            lp.h0 = carry ? lstm_state + (size_t)l * D * H : nullptr;
+            lp.c0 = carry ? lstm_state + (size_t)(LD + l * D) * H : nullptr;
+            lp.h_out = lstm_state ? lstm_state + (size_t)l * D * H : nullptr;
+            lp.c_out = lstm_state ? lstm_state + (size_t)(LD + l * D) * H : nullptr;
+            lp.hseq = pl.hseq[l]; lp.hseq_pitch = W; lp.hseq_mode = fk.op_mode;
+            lp.hx = pl.hx; lp.counters = pl.counters;
+            lp.F = F; lp.H = H; lp.dirs = D; lp.C = pl.pC; lp.U = pl.pU;
+            lp.len = len_host < F ? len_host : F;
+            EMPOSE_TRY(launch_lstm_persistent(lp, s));
+            ++ctx->launches;
+        }
+    }
     for (const JobRange& r : pl.steps) EMPOSE_TRY(run(ctx, pl, r, mt_B, s));
-    if (lstm_state)
+    if (lstm_state && !pl.persistent)
         for (int l = 0; l < L; ++l)
             for (int d = 0; d < D; ++d) {
                 const int q = l * D + d;
@@ -336,6 +385,26 @@ int empose_rnn_create(const empose_rnn_config* cfg, const empose_tensor* tensors
                 return RowSource{whh + (size_t)src * H, wih + (size_t)src * n_in, 1.0, (double)bih[src] + (double)bhh[src]};
             }, &ctx->lstm[(size_t)l * D + d]));
         }
+    if (fk.op_half) {
+        ctx->wih_plain.resize((size_t)cfg->num_layers * D);
+        ctx->whh_half.resize((size_t)cfg->num_layers * D);
+        for (int l = 0; l < cfg->num_layers; ++l)
+            for (int d = 0; d < D; ++d) {
+                const int n_in = l == 0 ? ctx->in_size : D * H;
+                const std::string sfx = "_l" + std::to_string(l) + (d == 1 ? "_reverse" : "");
+                const float *wih, *whh, *bih, *bhh;
+                EMPOSE_TRY(tt.get_f32("rnn.lstm.weight_ih" + sfx, {4 * H, n_in}, &wih));
+                EMPOSE_TRY(tt.get_f32("rnn.lstm.weight_hh" + sfx, {4 * H, H}, &whh));
+                EMPOSE_TRY(tt.get_f32("rnn.lstm.bias_ih" + sfx, {4 * H}, &bih));
+                EMPOSE_TRY(tt.get_f32("rnn.lstm.bias_hh" + sfx, {4 * H}, &bhh));
+                EMPOSE_TRY(pack_matrix(fk.arena, 4 * H, n_in, 0, 16, fk.op_mode, true, [&](int n) {
+                    return RowSource{wih + (size_t)n * n_in, nullptr, 1.0, (double)bih[n] + (double)bhh[n]};
+                }, &ctx->wih_plain[(size_t)l * D + d]));
+                std::vector<__half> hh((size_t)4 * H * H);
+                for (size_t i = 0; i < hh.size(); ++i) hh[i] = __float2half_rn(whh[i]);
+                EMPOSE_TRY(fk.arena.upload(hh, &ctx->whh_half[(size_t)l * D + d]));
+            }
+    }
     EMPOSE_TRY(pack_linear(fk.arena, tt, "to_pose", "", "", kPoseDim, D * H, fk.op_mode, &ctx->to_pose));
     if (cfg->estimate_shape)
         EMPOSE_TRY(pack_mlp(fk.arena, tt, "to_shape", D * H, kBetas, cfg->shape_hidden_size, 2, false, fk.op_mode, &ctx->to_shape));

@@ -101,3 +101,35 @@ def test_birnn_stream_matches_oracle(dev, smpl_npz, oracle_smpl, precision):
               util.max_joint_angle_err(out['root_ori_hat'].cpu().numpy(), want['root_ori_hat'].numpy()))
     util.report('rnn_stream', precision=PNAME[precision], frames=f, rad=rad, launches=net._ctx.last_launch_count)
     assert rad <= (2e-5 if precision == native.PRECISION_FP32 else 1e-4), rad
+
+
+def test_persistent_stream_with_state_carry_and_padding(dev, smpl_npz, oracle_smpl):
+    """The persistent single-stream kernel (B = 1, fp16 mode): two chunks with the LSTM state carried across them
+    (evaluate_real.py:61), the second one padded (len < F), uni- and bidirectional; checked against the oracle."""
+    for bidir, hidden, layers in ((True, 256, 2), (False, 128, 3)):
+        flags = dict(cfg=dict(n_markers=12, hidden_size=hidden, num_layers=layers, bidirectional=bidir),
+                     weights=dict(n_markers=12, hidden_size=hidden, num_layers=layers, bidirectional=bidir, estimate_shape=False))
+        sd = util.torch_state_dict(synthetic.synth_rnn_state_dict(seed=0, **flags['weights']), torch.float64)
+        net = build_rnn(smpl_npz, flags, native.PRECISION_FP16, dev)
+        g = torch.Generator().manual_seed(11)
+        state = None
+        z = torch.zeros(1, 12, 3)
+        for c, (f, n_live) in enumerate(((96, 96), (80, 61))):
+            pos = 0.3 * torch.randn(1, f, 36, generator=g)
+            ori = (torch.eye(3).reshape(1, 1, 1, 9) + 0.05 * torch.randn(1, f, 12, 9, generator=g)).reshape(1, f, 108)
+            lens = torch.tensor([n_live])
+            want = oracle_rnn.rnn_forward(oracle_rnn.RnnConfig(**flags['cfg']), sd, oracle_smpl, pos.double(), ori.double(), lens,
+                                          init_state=state)
+            state = want['final_state']
+            with torch.no_grad():
+                out = net(util.DuckBatch(pos, ori, z.unsqueeze(-1).repeat(1, 1, 1, 3), z, lens).to(dev), is_new_sequence=(c == 0))
+            live = util.valid_frame_mask(lens.numpy(), f)
+            rad = max(util.max_joint_angle_err(out['pose_hat'].cpu().numpy()[live], want['pose_hat'].numpy()[live]),
+                      util.max_joint_angle_err(out['root_ori_hat'].cpu().numpy()[live], want['root_ori_hat'].numpy()[live]))
+            h_err = float((net.rnn.final_state[0].cpu().double() - state[0]).abs().max())
+            c_err = float((net.rnn.final_state[1].cpu().double() - state[1]).abs().max())
+            util.report('rnn_persistent', bidirectional=bidir, chunk=c, rad=rad, h_err=h_err, c_err=c_err,
+                        launches=net._ctx.last_launch_count)
+            assert net._ctx.last_launch_count < 40, 'the persistent path must not launch once per time step'
+            assert rad <= 1e-4, rad
+            assert h_err <= 2e-3 and c_err <= 5e-3, (h_err, c_err)
