@@ -547,13 +547,87 @@ def run_b200_birnn(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_b200_synth(args, rank, local_rank, world):
+    """training-data synthesis (SMPLFK + SampleMarkersWithOffsets) on the device, windows sharded over GPUs."""
+    from empose_b200 import synthetic
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from empose_b200.data.transforms import SMPLFK, SampleMarkersWithOffsets
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0)
+    smpl = SMPLLayer(npz).to(device=device, dtype=torch.float32)
+    files = synthetic.write_synthetic_offsets(asset_dir(), n_files=3, seed=0)
+    b = args.windows
+    p = synthetic.synth_window_params(b, FRAMES, seed=3000 + rank)
+
+    class B(object):
+        pass
+    batch = B()
+    poses = torch.from_numpy(p['poses']).to(device)
+    batch.poses_root, batch.poses_body = poses[:, :, :3].contiguous(), poses[:, :, 3:].contiguous()
+    batch.shapes = torch.from_numpy(p['shapes']).to(device)
+    batch.trans = torch.zeros(b, FRAMES, 3, device=device)
+    batch.batch_size, batch.seq_length = b, FRAMES
+    fk, sampler = SMPLFK(smpl), SampleMarkersWithOffsets(smpl, files, noise_level=0)
+
+    def step():
+        sampler(fk(batch))
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ms = timed(step, args.steps, barrier)
+    if dist is not None:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ief as oracle_ief
+        from oracle import sensors, smplh_lbs
+        osmpl = smplh_lbs.SmplhModel(npz, num_betas=10, dtype=torch.float32)
+        topo = sensors.sensor_topology(osmpl.faces.numpy())
+        n = 16 * FRAMES
+        pp = torch.from_numpy(p['poses'][:16]).reshape(n, 66)
+        ss = torch.from_numpy(p['shapes'][:16]).unsqueeze(1).repeat(1, FRAMES, 1).reshape(n, 10)
+        eye, zero = torch.eye(3).repeat(n, 12, 1, 1), torch.zeros(n, 12, 3)
+        with torch.no_grad():
+            oracle_ief.project_sensors(osmpl, topo, pp, ss, eye, zero)
+            t0 = time.perf_counter()
+            oracle_ief.project_sensors(osmpl, topo, pp, ss, eye, zero)       # full mesh + sensor frames, once (the reference
+            dt = time.perf_counter() - t0                                    # derives both marker sets from one mesh)
+        cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': '16 windows x 32 frames: full-mesh SMPL-H + sensor frames + offsets, one pass after 1 warm-up'}
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'frames/sec training-data synthesis (SMPLFK + SampleMarkersWithOffsets), 12 sensors, ws=32',
+            'value': world * b * FRAMES * args.steps / (ms / 1000.0), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'fp32 (pose blend 3xTF32)', 'data': 'synthetic',
+            'config': {'workload': 'SMPLFK + SampleMarkersWithOffsets(noise_level=0) on %d windows x 32 frames per GPU: three passes of '
+                                   'the sub-model kernels (joints; raw sensor frames; frames with offsets), the mesh is never materialised' % b,
+                       'windows_per_gpu': b}, 'cpu_baseline': cpu}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'birnn'])
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'birnn', 'synth'])
     ap.add_argument('--frames', type=int, default=15000, help='stream length of the birnn workload')
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'tf32', 'fp32'], help='inference arithmetic of the learned layers')
     ap.add_argument('--windows', type=int, default=None, help='windows per GPU (inference: 4096 = BASELINE config 3; training: 512)')
@@ -564,13 +638,15 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.windows is None:
-        args.windows = 4096 if args.workload == 'infer' else 512
+        args.windows = 512 if args.workload == 'train' else 4096
     if args.impl == 'reference':
         run_reference(args, rank)
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)')
-    if args.workload == 'birnn':
+    if args.workload == 'synth':
+        run_b200_synth(args, rank, local_rank, world)
+    elif args.workload == 'birnn':
         run_b200_birnn(args, rank, local_rank, world)
     elif args.workload == 'train':
         run_b200_train(args, rank, local_rank, world)

@@ -490,6 +490,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
 
 int check_call(empose_ief* ctx, int B, int F) {
     if (!ctx) { set_last_error("null context"); return EMPOSE_E_ARG; }
+    if (ctx->sensors_only && F != 1) { set_last_error("this context was made by empose_sensors_create: it only projects sensors"); return EMPOSE_E_ARG; }
     if (B < 1 || F < 1 || (int64_t)B * F > (int64_t)1 << 26) { set_last_error("B and F must be positive (and B*F <= 2^26)"); return EMPOSE_E_ARG; }
     EMPOSE_CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     return EMPOSE_OK;
@@ -733,6 +734,38 @@ int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const floa
     EMPOSE_CUDA_TRY(cudaEventRecord(ev_end, ctx->copy_out));
     EMPOSE_CUDA_TRY(cudaStreamWaitEvent(s, ev_end, 0));
     EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));
+    return EMPOSE_OK;
+}
+
+int empose_sensors_create(const empose_tensor* tensors, int32_t n_tensors, int32_t precision, int32_t device, empose_ief** out) {
+    if (!tensors || !out) { set_last_error("null argument"); return EMPOSE_E_ARG; }
+    *out = nullptr;
+    if (precision < 0 || precision > 2) { set_last_error("unknown precision"); return EMPOSE_E_ARG; }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device available: empose_b200 has no CPU fallback");
+        return EMPOSE_E_CUDA;
+    }
+    EMPOSE_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    EMPOSE_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_last_error("empose_b200 is built for sm_100a (B200) only"); return EMPOSE_E_CUDA; }
+    std::unique_ptr<empose_ief> ctx(new empose_ief());
+    memset(&ctx->cfg, 0, sizeof(ctx->cfg));
+    ctx->cfg.device = device;
+    ctx->cfg.precision = precision;
+    ctx->sensors_only = true;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->round = precision != EMPOSE_PRECISION_FP32;
+    ctx->op_mode = precision == EMPOSE_PRECISION_FP32 ? OPERAND_F32 : OPERAND_TF32;
+    ctx->op_half = 0;
+    ctx->pf_stride = ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad;
+    ctx->spec.use_pos = 0; ctx->spec.use_ori = 0; ctx->spec.weight = 1.0f;
+    for (int i = 0; i < kSensors; ++i) { ctx->spec.sensor_active[i] = 0; ctx->slot_of_sensor[i] = i; }
+    TensorTable tt{tensors, n_tensors};
+    EMPOSE_TRY(upload_submodel(ctx.get(), tt));
+    *out = ctx.release();
     return EMPOSE_OK;
 }
 

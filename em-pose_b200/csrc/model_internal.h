@@ -350,6 +350,7 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
     int num_sms = 148;
     int in_size = 0, iter_in = 0, n_pos = 0;
     int in_stride = 0, iter_stride = 0;   // row pitches of the network-input buffers (multiples of 4 floats for TMA)
+    bool sensors_only = false; // made by empose_sensors_create: sub-model only, no learned layers
     bool round = true;         // a tensor-core mode (TF32 or FP16): pose-blend operands are tf32-rounded, tcgen05 executor
     int op_mode = OPERAND_TF32;   // storage of the MLP / LSTM / heads operands: OPERAND_F32, OPERAND_TF32 or OPERAND_F16
     int op_half = 0;           // op_mode == OPERAND_F16

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_creat
                     'empose_smpl_forward', 'empose_train_layout', 'empose_train_sizes', 'empose_train_create',
                     'empose_train_destroy', 'empose_train_forward', 'empose_train_backward',
                     'empose_train_last_launch_count', 'empose_rnn_create', 'empose_rnn_destroy', 'empose_rnn_forward',
-                    'empose_rnn_last_launch_count')
+                    'empose_rnn_last_launch_count', 'empose_sensors_create')
 
 
 class EmposeError(RuntimeError):
@@ -121,6 +121,8 @@ def load():
     lib.empose_train_backward.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LossWeights), ctypes.POINTER(ctypes.c_float), vp]
     lib.empose_train_last_launch_count.restype = ctypes.c_int64
     lib.empose_train_last_launch_count.argtypes = [vp]
+    lib.empose_sensors_create.restype = ctypes.c_int
+    lib.empose_sensors_create.argtypes = [ctypes.POINTER(Tensor), i32, i32, i32, ctypes.POINTER(vp)]
     lib.empose_rnn_create.restype = ctypes.c_int
     lib.empose_rnn_create.argtypes = [ctypes.POINTER(RnnConfig), ctypes.POINTER(Tensor), i32, ctypes.POINTER(vp)]
     lib.empose_rnn_destroy.restype = None
@@ -407,6 +409,31 @@ class TrainContext(object):
         _check(load().empose_train_backward(self._handle, _ptr(poses_gt), _ptr(shapes_gt), _ptr(joints_gt), ctypes.byref(w),
                                             vals, _stream()))
         return dict(zip(('pose', 'shape', 'reconstruction', 'fk', 'total_loss'), [float(v) for v in vals]))
+
+
+class SensorContext(object):
+    """Owns a sub-model-only context (``empose_sensors_create``): poses / shapes / offsets -> 12 sensor frames + 22 joints."""
+
+    def __init__(self, arrays, precision, device_index):
+        table, keep = make_tensor_table(arrays)
+        handle = ctypes.c_void_p()
+        _check(load().empose_sensors_create(table, len(arrays), int(precision), int(device_index), ctypes.byref(handle)))
+        del keep
+        self._handle = handle
+        self.device_index = int(device_index)
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            load().empose_ief_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    sensor_project = IefContext.sensor_project
 
 
 class RnnContext(object):

@@ -339,6 +339,24 @@ def synth_window_params(n_windows, n_frames, seed=0, ragged=False, offsets=False
             'seq_lengths': seq_lengths.astype(np.int64), 'marker_masks': masks}
 
 
+def write_synthetic_offsets(out_dir, n_files=3, seed=0):
+    """Stand-ins for the reference's estimated sensor-to-skin offset files (``transforms.py:145-160``: ``means`` (12,3),
+    ``covs`` (12,3,3), ``r`` (12,3,3), ``vertex_ids``).  Returns the list of paths."""
+    os.makedirs(out_dir, exist_ok=True)
+    paths = []
+    vertex_ids = [3027, 3748, 5430, 5178, 5006, 4447, 4559, 1961, 1391, 1535, 959, 1072]      # configuration.py:32-34
+    for i in range(n_files):
+        rng = np.random.RandomState(7000 + 31 * seed + i)
+        means = 0.02 * rng.standard_normal((12, 3))
+        a = 0.004 * rng.standard_normal((12, 3, 3))
+        covs = a @ np.transpose(a, (0, 2, 1)) + 1e-6 * np.eye(3)[None]
+        r = _random_rotations(rng, 12)
+        path = os.path.join(out_dir, 'offsets_%d_%d.npz' % (seed, i))
+        np.savez(path, means=means, covs=covs, r=r, vertex_ids=np.asarray(vertex_ids))
+        paths.append(path)
+    return paths
+
+
 def synth_measurements(gt_pos, gt_ori, seed=0, pos_noise=0.01):
     """Measured sensors = projected ground truth + 1 cm position noise; (B,F,12,3)/(B,F,12,3,3) -> (B,F,36)/(B,F,108)."""
     rng = np.random.RandomState(1000003 * seed + 71)

@@ -14,6 +14,8 @@
  *                                     chunk.to_gpu(), net(chunk), .cpu())
  *   empose_sensor_project          <- IterativeErrorFeedback.get_estimated_real_markers
  *                                                                                 empose/nn/models.py:471-483
+ *   empose_sensors_create          <- SMPLFK + SampleMarkersWithOffsets (data synthesis before the hot path)
+ *                                                                                 empose/data/transforms.py:163-226, 259-282
  *   empose_smpl_create / _forward  <- SMPLLayer.__init__ / forward / fk / _fk     empose/bodymodels/smpl.py:31-165
  *                                     (the third-party BodyModel call at smpl.py:121)
  *   empose_train_create / _layout  <- create_model + net.parameters() as ONE flat vector (scripts/train.py:125)
@@ -147,6 +149,13 @@ int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const floa
 int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shapes, const float* offset_r,
                           const float* offset_t, int32_t R, float* sensor_pos, float* sensor_ori, float* joints,
                           void* stream);
+
+/* A context that holds ONLY the SMPL sub-model ("sub.*" arrays), for empose_sensor_project without a learned model:
+ * the device side of the reference's training-data synthesis, SMPLFK + SampleMarkersWithOffsets
+ * (empose/data/transforms.py:163-226, 259-282), i.e. ground-truth SMPL evaluation -> 12 sensor frames -> offsets in
+ * one pass that never materialises the 6890-vertex mesh.  Destroy with empose_ief_destroy; the forward entry points
+ * refuse such a context.  `precision`: EMPOSE_PRECISION_FP32, or a tensor-core mode (pose blend 3xTF32). */
+int empose_sensors_create(const empose_tensor* tensors, int32_t n_tensors, int32_t precision, int32_t device, empose_ief** out);
 
 /* Number of kernels the last empose_ief_forward* call on this context launched (for bench accounting). */
 int64_t empose_ief_last_launch_count(const empose_ief* ctx);
