@@ -71,7 +71,8 @@ struct GemmJob {
     int64_t h_prev_stride;
     int32_t t;               // time step of this job
     int32_t hidden;          // H
-    // training only (may be null): activated gates [row][4H] in torch order i|f|g|o and the cell state after the step [row][H]
+    // training only (may be null): activated gates [row][4H] in the packed column order of this job (groups of 32 =
+    // [i f g o] x 8 units) and the cell state after the step [row][H]
     float* gates_out;
     int64_t gates_stride;
     float* c_seq_out;
@@ -326,6 +327,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
         __syncwarp();
         if (live) {
             float c_old[8];
+            float gates[32];
 #pragma unroll
             for (int k = 0; k < 8; ++k) c_old[k] = sc[lane * 9 + k];
 #pragma unroll
@@ -344,12 +346,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
                     c_new = sf * c_old[k] + si * tg;
                     h_new = so * tanhf(c_new);
                 }
-                if (j.gates_out) {                 // training: keep the activated gates for the backward pass
-                    float* gp = j.gates_out + (int64_t)row * j.gates_stride + unit0 + k;
-                    gp[0] = si; gp[j.hidden] = sf; gp[2 * j.hidden] = tg; gp[3 * j.hidden] = so;
-                }
+                if (j.gates_out) { gates[k] = si; gates[8 + k] = sf; gates[16 + k] = tg; gates[24 + k] = so; }
                 v[k] = c_new;
                 v[8 + k] = h_new;
+            }
+            if (j.gates_out) {
+                // training: keep the activated gates for the backward pass, in the accumulator's own column order
+                // (32 contiguous floats per row and chunk: eight 16-byte stores instead of 32 scattered words)
+                float4* gp = reinterpret_cast<float4*>(j.gates_out + (int64_t)row * j.gates_stride + n0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) gp[q] = make_float4(gates[4 * q], gates[4 * q + 1], gates[4 * q + 2], gates[4 * q + 3]);
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {

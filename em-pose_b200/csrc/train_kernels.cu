@@ -119,33 +119,43 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     }
 }
 
+// grid (rows / kApplyRows, S): a block owns kApplyRows rows of one segment; per-column constants are formed once per block
+constexpr int kApplyRows = 64;
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ da, int64_t da_ld, const float* __restrict__ z,
                                                            int64_t z_ld, int R, int n, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ alpha,
                                                            const double* __restrict__ sums, int round_out,
-                                                           float* __restrict__ dz, int64_t dz_ld, int64_t total) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int64_t row = idx / n;
-    const int c = (int)(idx % n);
-    const int seg = (int)(row / R);
+                                                           float* __restrict__ dz, int64_t dz_ld) {
+    extern __shared__ float cst[];              // [6][n]: mean, invstd, gamma, beta, m1, m2
+    const int seg = blockIdx.y;
+    float *c_mu = cst, *c_is = cst + n, *c_g = cst + 2 * n, *c_b = cst + 3 * n, *c_m1 = cst + 4 * n, *c_m2 = cst + 5 * n;
+    if (gamma)
+        for (int c = threadIdx.x; c < n; c += blockDim.x) {
+            c_mu[c] = mean[seg * n + c]; c_is[c] = invstd[seg * n + c]; c_g[c] = gamma[c]; c_b[c] = beta[c];
+            c_m1[c] = (float)(sums[((int64_t)seg * 3 + 0) * n + c] / R);
+            c_m2[c] = (float)(sums[((int64_t)seg * 3 + 1) * n + c] / R);
+        }
+    __syncthreads();
     const float al = alpha[0];
-    const float d = da[row * da_ld + c];
-    float out;
-    if (gamma) {
-        const float is = invstd[seg * n + c];
-        const float xh = (z[row * z_ld + c] - mean[seg * n + c]) * is;
-        const float y = gamma[c] * xh + beta[c];
-        const float dy = y > 0.0f ? d : al * d;
-        const float m1 = (float)(sums[((int64_t)seg * 3 + 0) * n + c] / R);
-        const float m2 = (float)(sums[((int64_t)seg * 3 + 1) * n + c] / R);
-        out = gamma[c] * is * (dy - m1 - xh * m2);
-    } else {
-        const float y = z[row * z_ld + c];
-        out = y > 0.0f ? d : al * d;
+    const int r0 = blockIdx.x * kApplyRows;
+    const int rows = min(kApplyRows, R - r0);
+    for (int i = threadIdx.x; i < rows * n; i += blockDim.x) {
+        const int r = i / n, c = i - r * n;
+        const int64_t row = (int64_t)seg * R + r0 + r;
+        const float d = da[row * da_ld + c];
+        float out;
+        if (gamma) {
+            const float xh = (z[row * z_ld + c] - c_mu[c]) * c_is[c];
+            const float y = c_g[c] * xh + c_b[c];
+            const float dy = y > 0.0f ? d : al * d;
+            out = c_g[c] * c_is[c] * (dy - c_m1[c] - xh * c_m2[c]);
+        } else {
+            const float y = z[row * z_ld + c];
+            out = y > 0.0f ? d : al * d;
+        }
+        dz[row * dz_ld + c] = maybe_round(out, round_out);
     }
-    dz[row * dz_ld + c] = maybe_round(out, round_out);
 }
 
 __global__ void __launch_bounds__(256) bn_param_grads_kernel(const double* __restrict__ sums, int S, int n, float* g_gamma,
@@ -229,8 +239,9 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(LstmCellBwdParams p)
         dg[0] = 0.0f; dg[p.H] = 0.0f; dg[2 * p.H] = 0.0f; dg[3 * p.H] = 0.0f;
         return;
     }
-    const float* g = p.gates + row * 4 * p.H + u;
-    const float gi = g[0], gf = g[p.H], gg = g[2 * p.H], go = g[3 * p.H];
+    // the forward epilogue keeps the activated gates in ITS column order: 32-column groups of [i f g o] x 8 units
+    const float* g = p.gates + row * 4 * p.H + (u >> 3) * 32 + (u & 7);
+    const float gi = g[0], gf = g[8], gg = g[16], go = g[24];
     const float c = p.c_seq[row * p.H + u];
     const float c_prev = p.t > 0 ? p.c_seq[(row - 1) * p.H + u] : 0.0f;
     float dh = p.dh_out[row * p.H + u];
@@ -446,9 +457,8 @@ int launch_bn_bwd_reduce(const float* da, int64_t da_ld, const float* z, int64_t
 int launch_bn_bwd_apply(const float* da, int64_t da_ld, const float* z, int64_t z_ld, int R, int S, int n, const float* mean,
                         const float* invstd, const float* gamma, const float* beta, const float* alpha, const double* sums,
                         int round_out, float* dz, int64_t dz_ld, cudaStream_t s) {
-    const int64_t total = (int64_t)S * R * n;
-    bn_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, s>>>(da, da_ld, z, z_ld, R, n, mean, invstd, gamma, beta, alpha, sums,
-                                                               round_out, dz, dz_ld, total);
+    bn_bwd_apply_kernel<<<dim3(blocks_for(R, kApplyRows), S), 256, (size_t)6 * n * sizeof(float), s>>>(
+        da, da_ld, z, z_ld, R, n, mean, invstd, gamma, beta, alpha, sums, round_out, dz, dz_ld);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

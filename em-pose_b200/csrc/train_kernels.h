@@ -60,7 +60,8 @@ int launch_transpose(const float* src, int64_t src_ld, int64_t rows, int n, int 
                      int64_t dst_ld, cudaStream_t s);
 
 // ---- LSTM cell backward -------------------------------------------------------------------------------------
-// One time step t of one layer for B windows: gates [B][F][4H] (activated, torch order i|f|g|o), c_seq [B][F][H],
+// One time step t of one layer for B windows: gates [B][F][4H] (activated, in the packed column order of gemm_jobs.h:
+// groups of 32 = [i f g o] x 8 units), c_seq [B][F][H],
 // dh_out [B][F][H] (gradient arriving at the layer output at time t), dh_rec [B][H] (from step t+1; zero at t = F-1),
 // dc_rec [B][H] in/out.  Writes dgates [B][F][4H] at time t (zero rows for t >= seq_len[b]).
 struct LstmCellBwdParams {
