@@ -1,6 +1,7 @@
 """Stand-ins that let the UNMODIFIED reference modules import and run here (test infrastructure).
 
-``/root/reference`` imports three packages that are absent from this image: ``trimesh``
+``/root/reference`` imports three packages that are absent from this image (``quaternion`` gets a scipy-backed
+stand-in for the four functions the metrics use): ``trimesh``
 (``virtual_sensors.py:11``, ``smpl.py:12``), ``quaternion`` (``helpers/utils.py:12``) and
 ``human_body_prior`` (``smpl.py:20-21``).  ``install()`` registers minimal substitutes in
 ``sys.modules`` -- the third-party SMPL arithmetic comes from ``oracle.smplh_lbs`` -- sets the four
@@ -57,6 +58,36 @@ class _Trimesh(object):
         self.vertex_faces = sensors.vertex_faces_table(np.asarray(faces), len(vertices))
 
 
+def _quaternion_module():
+    """Stand-in for the absent ``numpy-quaternion`` package: the four functions ``empose/eval/metrics.py:148-161`` and
+    ``empose/data/transforms.py:106-116`` call, on top of ``scipy.spatial.transform.Rotation`` (unit quaternions)."""
+    from scipy.spatial.transform import Rotation
+    mod = types.ModuleType('quaternion')
+
+    def from_rotation_vector(rv):
+        rv = np.asarray(rv, dtype=np.float64)
+        return Rotation.from_rotvec(rv.reshape(-1, 3)), rv.shape[:-1]
+
+    def from_rotation_matrix(rm):
+        rm = np.asarray(rm, dtype=np.float64)
+        return Rotation.from_matrix(rm.reshape(-1, 3, 3)), rm.shape[:-2]
+
+    def as_rotation_matrix(q):
+        rot, shape = q
+        return rot.as_matrix().reshape(shape + (3, 3))
+
+    def rotation_intrinsic_distance(q1, q2):
+        """2 |log(q1^-1 q2)|: the geodesic angle between the two rotations, in [0, pi]."""
+        (r1, shape), (r2, _) = q1, q2
+        return (r1.inv() * r2).magnitude().reshape(shape)
+
+    mod.from_rotation_vector = from_rotation_vector
+    mod.from_rotation_matrix = from_rotation_matrix
+    mod.as_rotation_matrix = as_rotation_matrix
+    mod.rotation_intrinsic_distance = rotation_intrinsic_distance
+    return mod
+
+
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'empose'))
 
@@ -71,7 +102,7 @@ def install(asset_dir, seed=0):
     model_path = smplh_synth.write_synthetic_smplh(os.environ['SMPL_MODELS'], seed=seed)
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    sys.modules.setdefault('quaternion', types.ModuleType('quaternion'))
+    sys.modules.setdefault('quaternion', _quaternion_module())
     tm = types.ModuleType('trimesh')
     tm.Trimesh = _Trimesh
     sys.modules.setdefault('trimesh', tm)
