@@ -622,13 +622,66 @@ def run_b200_synth(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_b200_metrics(args, rank, local_rank, world):
+    """MetricsEngine.compute on the device (FK x2 + Procrustes + angular distances, one kernel)."""
+    from empose_b200 import synthetic
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from empose_b200.eval.metrics import MetricsEngine
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0)
+    me = MetricsEngine(SMPLLayer(npz).to(device=device, dtype=torch.float32))
+    b = args.windows
+    p = synthetic.synth_window_params(b, FRAMES, seed=4000 + rank)
+    g = torch.Generator().manual_seed(4000 + rank)
+    poses = torch.from_numpy(p['poses'])
+    poses_hat = poses + 0.08 * torch.randn(poses.shape, generator=g)
+    shapes = torch.from_numpy(p['shapes'])
+    dv = lambda t: t.to(device)
+    args_dev = (dv(poses[:, :, 3:]), dv(shapes), dv(poses_hat[:, :, 3:]), None, None, dv(poses[:, :, :3]), dv(poses_hat[:, :, :3]))
+
+    def step():
+        me.reset()
+        me.compute(*args_dev)                   # includes the (frames x joints) tables coming back to the host
+        return me.get_metrics()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        metrics = step()
+    ms = 1000.0 * (time.perf_counter() - t0)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import metrics as oracle_metrics
+        from oracle import smplh_lbs
+        osmpl = smplh_lbs.SmplhModel(npz, num_betas=10, dtype=torch.float32)
+        n = 16 * FRAMES
+        a = (poses[:16].reshape(n, 66), shapes[:16].unsqueeze(1).repeat(1, FRAMES, 1).reshape(n, 10), poses_hat[:16].reshape(n, 66),
+             shapes[:16].unsqueeze(1).repeat(1, FRAMES, 1).reshape(n, 10))
+        oracle_metrics.frame_metrics(osmpl, *a)
+        t0 = time.perf_counter()
+        oracle_metrics.frame_metrics(osmpl, *a)
+        cpu = {'value': n / (time.perf_counter() - t0), 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': '16 windows x 32 frames: two full-mesh FK passes + per-frame numpy Procrustes + angular distances'}
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'frames/sec MetricsEngine.compute (MPJPE, PA-MPJPE, MPJAE)', 'value': b * FRAMES * args.steps / (ms / 1000.0),
+            'unit': 'frames/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (Procrustes in f64)', 'data': 'synthetic',
+            'config': {'workload': 'MetricsEngine.compute + get_metrics on %d windows x 32 frames, wall clock incl. the result tables '
+                                   'coming back to the host' % b, 'windows_per_gpu': b},
+            'metrics': {k: float(v) for k, v in metrics.items()}, 'cpu_baseline': cpu}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'birnn', 'synth'])
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'birnn', 'synth', 'metrics'])
     ap.add_argument('--frames', type=int, default=15000, help='stream length of the birnn workload')
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'tf32', 'fp32'], help='inference arithmetic of the learned layers')
     ap.add_argument('--windows', type=int, default=None, help='windows per GPU (inference: 4096 = BASELINE config 3; training: 512)')
@@ -645,7 +698,9 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)')
-    if args.workload == 'synth':
+    if args.workload == 'metrics':
+        run_b200_metrics(args, rank, local_rank, world)
+    elif args.workload == 'synth':
         run_b200_synth(args, rank, local_rank, world)
     elif args.workload == 'birnn':
         run_b200_birnn(args, rank, local_rank, world)

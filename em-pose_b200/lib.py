@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_creat
                     'empose_smpl_forward', 'empose_train_layout', 'empose_train_sizes', 'empose_train_create',
                     'empose_train_destroy', 'empose_train_forward', 'empose_train_backward',
                     'empose_train_last_launch_count', 'empose_rnn_create', 'empose_rnn_destroy', 'empose_rnn_forward',
-                    'empose_rnn_last_launch_count', 'empose_sensors_create')
+                    'empose_rnn_last_launch_count', 'empose_sensors_create', 'empose_metrics_compute', 'empose_metrics_joints')
 
 
 class EmposeError(RuntimeError):
@@ -123,6 +123,10 @@ def load():
     lib.empose_train_last_launch_count.argtypes = [vp]
     lib.empose_sensors_create.restype = ctypes.c_int
     lib.empose_sensors_create.argtypes = [ctypes.POINTER(Tensor), i32, i32, i32, ctypes.POINTER(vp)]
+    lib.empose_metrics_compute.restype = ctypes.c_int
+    lib.empose_metrics_compute.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.empose_metrics_joints.restype = ctypes.c_int
+    lib.empose_metrics_joints.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.empose_rnn_create.restype = ctypes.c_int
     lib.empose_rnn_create.argtypes = [ctypes.POINTER(RnnConfig), ctypes.POINTER(Tensor), i32, ctypes.POINTER(vp)]
     lib.empose_rnn_destroy.restype = None
@@ -434,6 +438,32 @@ class SensorContext(object):
             pass
 
     sensor_project = IefContext.sensor_project
+
+    def metrics(self, pose, shape, pose_hat, shape_hat, want_angle=True):
+        """(R,66), (R,10) x2 CUDA tensors -> eucl (R,22), eucl_pa (R,22), angle_deg (R,21) | None (``empose_metrics_compute``)."""
+        import torch
+        r = int(pose.shape[0])
+        f32 = lambda t: t.to(dtype=torch.float32).contiguous()
+        pose, shape, pose_hat, shape_hat = f32(pose), f32(shape), f32(pose_hat), f32(shape_hat)
+        opts = dict(dtype=torch.float32, device=pose.device)
+        eucl, eucl_pa = torch.empty((r, 22), **opts), torch.empty((r, 22), **opts)
+        angle = torch.empty((r, 21), **opts) if want_angle else None
+        _check(load().empose_metrics_compute(self._handle, _ptr(pose), _ptr(shape), _ptr(pose_hat), _ptr(shape_hat), r, _ptr(eucl),
+                                             _ptr(eucl_pa), _ptr(angle), _stream()))
+        return eucl, eucl_pa, angle
+
+
+def metrics_from_joints(joints, joints_hat):
+    """(R,66) CUDA tensors -> eucl (R,22), eucl_pa (R,22) (``empose_metrics_joints``)."""
+    import torch
+    if joints.device.type != 'cuda':
+        raise EmposeError('inputs must be CUDA tensors (no CPU path)')
+    r = int(joints.shape[0])
+    joints, joints_hat = joints.to(dtype=torch.float32).contiguous(), joints_hat.to(dtype=torch.float32).contiguous()
+    eucl = torch.empty((r, 22), dtype=torch.float32, device=joints.device)
+    eucl_pa = torch.empty_like(eucl)
+    _check(load().empose_metrics_joints(_ptr(joints), _ptr(joints_hat), r, _ptr(eucl), _ptr(eucl_pa), _stream()))
+    return eucl, eucl_pa
 
 
 class RnnContext(object):

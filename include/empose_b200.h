@@ -18,6 +18,8 @@
  *                                                                                 empose/data/transforms.py:163-226, 259-282
  *   empose_smpl_create / _forward  <- SMPLLayer.__init__ / forward / fk / _fk     empose/bodymodels/smpl.py:31-165
  *                                     (the third-party BodyModel call at smpl.py:121)
+ *   empose_metrics_compute         <- MetricsEngine.compute (per-frame FK x2, Procrustes, angular distance)
+ *                                                                                 empose/eval/metrics.py:183-241, 19-66
  *   empose_train_create / _layout  <- create_model + net.parameters() as ONE flat vector (scripts/train.py:125)
  *   empose_train_forward           <- IterativeErrorFeedback.forward with net.train()  empose/nn/models.py:485-632
  *                                     (BatchNorm1d on batch statistics, layers.py:26,57; the gradient side effect
@@ -156,6 +158,16 @@ int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shap
  * one pass that never materialises the 6890-vertex mesh.  Destroy with empose_ief_destroy; the forward entry points
  * refuse such a context.  `precision`: EMPOSE_PRECISION_FP32, or a tensor-core mode (pose blend 3xTF32). */
 int empose_sensors_create(const empose_tensor* tensors, int32_t n_tensors, int32_t precision, int32_t device, empose_ief** out);
+
+/* Evaluation metrics of MetricsEngine.compute (empose/eval/metrics.py:183-241) for R frames in one kernel: FK of ground
+ * truth and prediction (22 body joints; `ctx` provides the sub-model: any empose_ief, e.g. from empose_sensors_create),
+ * per-joint Euclidean distance eucl [R][22] (metres), the same after per-frame Procrustes alignment with optimal scale
+ * eucl_pa [R][22] (metrics.py:19-66) and the geodesic angle between global joint orientations with a zero root
+ * angle_deg [R][21] (degrees; may be NULL).  pose / pose_hat [R][66] (root first), shape / shape_hat [R][10]. */
+int empose_metrics_compute(empose_ief* ctx, const float* pose, const float* shape, const float* pose_hat, const float* shape_hat,
+                           int32_t R, float* eucl, float* eucl_pa, float* angle_deg, void* stream);
+/* Same distances from given joints [R][66] (MetricsEngine.compute_joint_dist, metrics.py:243-265). */
+int empose_metrics_joints(const float* joints, const float* joints_hat, int32_t R, float* eucl, float* eucl_pa, void* stream);
 
 /* Number of kernels the last empose_ief_forward* call on this context launched (for bench accounting). */
 int64_t empose_ief_last_launch_count(const empose_ief* ctx);

@@ -107,3 +107,22 @@ extern "C" int host_frame_eval(const HostSub* h, int n_frames, const float* thet
                    want_grad, sensor_weight, joints_gt, joint_weight, sensor_pos, sensor_ori, joints, g_theta, g_beta, verts);
     return 0;
 }
+
+// ---- evaluation metrics (csrc/metrics_math.h) on the host --------------------------------------------------------
+#include "metrics_math.h"
+
+extern "C" int host_metrics_eval(const float* j0, const float* jdirs, const int* parents, int n_frames, const float* pose,
+                                 const float* shape, const float* pose_hat, const float* shape_hat, float* eucl, float* eucl_pa,
+                                 float* joints_out) {
+    MetricsParams p;
+    memset(&p, 0, sizeof(p));
+    p.j0 = j0; p.jdirs = jdirs; p.parents = parents;
+    for (int f = 0; f < n_frames; ++f) {
+        float jg[kJoints][3], jh[kJoints][3], og[kJoints][9], oh[kJoints][9];
+        fk_frame(p, pose + f * kPoseDim, shape + f * kBetas, jg, og);
+        fk_frame(p, pose_hat + f * kPoseDim, shape_hat + f * kBetas, jh, oh);
+        joint_distances(jg, jh, eucl + f * kJoints, eucl_pa + f * kJoints);
+        if (joints_out) memcpy(joints_out + f * kPoseDim, jg, sizeof(jg));
+    }
+    return 0;
+}

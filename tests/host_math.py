@@ -28,7 +28,8 @@ def _lib():
         so = os.path.join(out_dir, 'host_harness.so')
         src = os.path.join(HERE, 'host_harness.cpp')
         hdr = os.path.join(ROOT, 'em-pose_b200', 'csrc', 'frame_math.h')
-        if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        hdr2 = os.path.join(ROOT, 'em-pose_b200', 'csrc', 'metrics_math.h')
+        if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-I', os.path.dirname(hdr), src,
                                    '-o', so])
         _LIB = ctypes.CDLL(so)
@@ -71,3 +72,18 @@ def frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef,
                                 dp(out['verts']))
     assert rc == 0
     return out
+
+
+def metrics_eval(sub, pose, shape, pose_hat, shape_hat):
+    """The metrics kernel's per-frame math on the host: eucl (n,22), eucl_pa (n,22), ground-truth joints (n,22,3)."""
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    pose, shape, pose_hat, shape_hat = map(f32, (pose, shape, pose_hat, shape_hat))
+    j0, jd = f32(sub['sub.j0']), f32(sub['sub.jdirs'])
+    par = np.ascontiguousarray(sub['sub.parents'], dtype=np.int32)
+    n = pose.shape[0]
+    eucl, pa, joints = np.zeros((n, 22), np.float32), np.zeros((n, 22), np.float32), np.zeros((n, 22, 3), np.float32)
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    rc = _lib().host_metrics_eval(fp(j0), fp(jd), par.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n, fp(pose), fp(shape),
+                                  fp(pose_hat), fp(shape_hat), fp(eucl), fp(pa), fp(joints))
+    assert rc == 0
+    return eucl, pa, joints

@@ -32,3 +32,21 @@ def test_frame_metrics_match_reference(oracle_smpl):
     np.testing.assert_allclose(eucl, gold['eucl'], atol=2e-6, rtol=0)
     np.testing.assert_allclose(eucl_pa, gold['eucl_pa'], atol=2e-6, rtol=0)
     np.testing.assert_allclose(angle, gold['angle'], atol=2e-3, rtol=0)        # degrees; the reference went through float32 axis-angles
+
+
+def test_kernel_math_on_host_matches_oracle(smpl_npz, oracle_smpl):
+    """csrc/metrics_math.h (what metrics_kernel runs per frame) compiled for the host: FK joints, Euclidean and
+    Procrustes-aligned distances vs the restatement -- including near-degenerate point sets for the 3x3 SVD."""
+    import host_math
+    from empose_b200 import submodel
+    sub, _ = submodel.submodel_from_npz(smpl_npz)
+    g = torch.Generator().manual_seed(5)
+    n = 64
+    pose, pose_hat = 0.3 * torch.randn(n, 66, generator=g), 0.3 * torch.randn(n, 66, generator=g)
+    shape, shape_hat = torch.randn(n, 10, generator=g), torch.randn(n, 10, generator=g)
+    pose_hat[:4] = pose[:4]                                   # identical skeletons up to shape
+    shape_hat[:2] = shape[:2]                                 # ... and fully identical ones (zero residual)
+    want = oracle_metrics.frame_metrics(oracle_smpl, pose.double(), shape.double(), pose_hat.double(), shape_hat.double())
+    eucl, pa, joints = host_math.metrics_eval(sub, pose.numpy(), shape.numpy(), pose_hat.numpy(), shape_hat.numpy())
+    np.testing.assert_allclose(eucl, want[0], atol=3e-6, rtol=0)
+    np.testing.assert_allclose(pa, want[1], atol=1e-5, rtol=0)
