@@ -214,6 +214,56 @@ def test_window_shape_is_shared_and_batch_shards_are_independent(dev, smpl_npz):
     assert torch.equal(half['pose'], full['pose'][256:]) and torch.equal(half['joints'], full['joints'][256:])
 
 
+def test_baseline_config3_full_size(dev, smpl_npz, oracle_smpl, topology):
+    """BASELINE.json configs[2] at its full size -- LGD-RNN, 12 sensors, N=4, 4096 windows x 32 frames -- through
+    size-independent properties: (i) eight windows picked across the batch equal, bit for bit, a run of those eight alone
+    (window independence, i.e. what multi-GPU sharding relies on), (ii) those eight match the CPU oracle within the parity bar,
+    (iii) every window has ONE shape (models.py:529-535), (iv) the LGD iterations reduce the sensor reconstruction error on
+    average (the loop does what it is for), (v) the host-buffer entry point returns the same bits."""
+    b, f = 4096, 32
+    net = util.build_module(smpl_npz, precision=native.PRECISION_FP16, device=dev)
+    ctx = net.native_context(dev)
+    params = synthetic.synth_window_params(b, f, seed=303, ragged=True, offsets=True)
+    pick = np.array([0, 1, 777, 2047, 2048, 3001, 4094, 4095])
+    sub_params = {k: (None if v is None else v[pick]) for k, v in params.items()}
+    sub_inp = util.oracle_inputs_from_params(oracle_smpl, topology, sub_params, seed=303)
+    # the full batch: measurements of every window through the CUDA projection, the eight picked ones replaced by the
+    # oracle-made ones so that both runs and the oracle see identical inputs
+    t = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    r = b * f
+    pos, ori, _ = ctx.sensor_project(t(params['poses']).reshape(r, 66), t(params['shapes']).unsqueeze(1).repeat(1, f, 1).reshape(r, 10),
+                                     t(params['offset_r']).unsqueeze(1).repeat(1, f, 1, 1, 1).reshape(r, 12, 3, 3),
+                                     t(params['offset_t']).unsqueeze(1).repeat(1, f, 1, 1).reshape(r, 12, 3))
+    g = torch.Generator(device=dev).manual_seed(5)
+    mpos = (pos + 0.01 * torch.randn(pos.shape, device=dev, generator=g)).reshape(b, f, 36)
+    mori = ori.reshape(b, f, 108).clone()
+    mpos[pick] = sub_inp['marker_pos'].to(dev)
+    mori[pick] = sub_inp['marker_oris'].to(dev)
+    lens, off_r, off_t = t(params['seq_lengths']), t(params['offset_r']), t(params['offset_t'])
+    full = ctx.forward(mpos, mori, off_r, off_t, lens, want_history=True)
+    alone = ctx.forward(mpos[pick], mori[pick], off_r[pick], off_t[pick], lens[pick], want_history=False)
+    for k in ('pose', 'shape', 'joints'):
+        assert torch.equal(full[k][pick], alone[k]), k                                              # (i)
+    cfg = oracle_ief.IefConfig(n_markers=12, num_iterations=4, rnn_init=True)
+    sd = util.torch_state_dict(synthetic.synth_state_dict(seed=0, n_markers=12, rnn_init=True))
+    want = oracle_ief.ief_forward(cfg, sd, oracle_smpl, topology, **sub_inp)
+    live = util.valid_frame_mask(sub_params['seq_lengths'], f)
+    want_pose = torch.cat([want['root_ori_hat'], want['pose_hat']], dim=-1).numpy()
+    rad = util.max_joint_angle_err(alone['pose'].cpu().numpy()[live], want_pose[live])
+    mm = util.max_joint_pos_err_mm(alone['joints'].cpu().numpy()[live], want['joints_hat'].numpy()[live])
+    util.report('config3_full', rad=rad, mm=mm, windows=b)
+    assert rad <= PARITY_RAD and mm <= PARITY_MM, (rad, mm)                                         # (ii)
+    assert (full['shape'] - full['shape'][:, :1]).abs().max().item() == 0.0                        # (iii)
+    assert torch.isfinite(full['pose']).all() and torch.isfinite(full['joints']).all()
+    mask = (torch.arange(f, device=dev).unsqueeze(0) < lens.unsqueeze(1)).float()
+    hist = full['history']['markers']
+    err = [(((hist[i] - mpos).reshape(b, f, 12, 3).norm(dim=-1).sum(-1) * mask).sum() / mask.sum()).item() for i in (0, 4)]
+    assert err[1] < err[0], err                                                                     # (iv)
+    pin = lambda x: x.cpu().contiguous().pin_memory()
+    host = ctx.forward_host(pin(mpos), pin(mori), pin(off_r), pin(off_t), lens.cpu())
+    assert torch.equal(host['pose'], full['pose'].cpu()) and torch.equal(host['joints'], full['joints'].cpu())   # (v)
+
+
 def test_host_buffer_entry_point_matches_device_entry_point(dev, smpl_npz, oracle_smpl, topology):
     net = util.build_module(smpl_npz, precision=native.PRECISION_FP16, device=dev)
     ctx = net.native_context(dev)
