@@ -34,11 +34,14 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(r);
 }
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// MUFU-based activations: ex2.approx + rcp.approx (2 ulp each; __fdividef returns 0 for a denominator beyond 2^126,
+// which is the limit wanted here).  An IEEE division instead costs ~10 instructions and a slow-path call per use --
+// the LSTM epilogue has five of these per hidden unit and row.
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) {
-    // tanh(x) = 1 - 2/(exp(2x)+1); accurate to a few ulp with the fast exp, saturates cleanly
-    float e = __expf(2.0f * x);
-    return 1.0f - 2.0f / (e + 1.0f);
+    // tanh(x) = 1 - 2/(exp(2x)+1): saturates cleanly at both ends
+    const float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
 // How a value that feeds a later GEMM is stored: exact fp32 (FFMA executor), tf32-rounded fp32 (kind::tf32 operands)

@@ -95,8 +95,21 @@ constexpr int kStageFloats = 32 * kStageLd;        // one warp-private [32][33] 
 // Loads are batched into registers before any store so that pointer aliasing cannot serialise them.
 // Bias arrays are padded by 32 floats, so the vector loads below never leave the allocation.
 // Must be called by all 32 lanes of the warp.
+// Cell-state block of one chunk pair [c0, c0 + 64) of an fp16 LSTM job -> registers, in the lane mapping the tile fill of
+// epilogue_chunk uses (8 rows x 64 B per instruction).  The tcgen05 executor issues this a pair ahead, so that the L2
+// round trip overlaps the wait for the accumulator / the arithmetic of the previous pair.
+__device__ __forceinline__ bool lstm_half_paired(const GemmJob& j) { return j.epi == EPI_LSTM && j.out_half && (j.n_count % 64) == 0; }
+__device__ __forceinline__ void lstm_half_load_c(const GemmJob& j, int row0, int lane, int c0, float4 (&cpre)[4]) {
+    const float* cs = j.c_state + lstm_unit_of_packed(j.n_begin + c0) + (lane & 3) * 4;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = row0 + it * 8 + (lane >> 2);
+        cpre[it] = r < j.m_rows ? *reinterpret_cast<const float4*>(cs + (int64_t)r * j.hidden) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
 __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int lane, int c0, float (&v)[32],
-                                               float* __restrict__ stage, bool no_store = false) {
+                                               float* __restrict__ stage, bool no_store = false, const float4* cpre = nullptr) {
     const int n0 = j.n_begin + c0;                 // global column of v[0]
     const int row = row0 + lane;
     float bias[32];
@@ -158,7 +171,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int r = it * 8 + (lane >> 2), seg = lane & 3;
-                if (row0 + r < j.m_rows)
+                if (cpre)
+                    *reinterpret_cast<float4*>(ctile + r * 80 + seg * 16) = cpre[it];
+                else if (row0 + r < j.m_rows)
                     *reinterpret_cast<float4*>(ctile + r * 80 + seg * 16) =
                         *reinterpret_cast<const float4*>(j.c_state + (int64_t)(row0 + r) * j.hidden + unit0 + seg * 4);
             }
@@ -326,41 +341,35 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
         for (int q = 0; q < 8; ++q) sc[(q * 4 + sub) * 9 + u] = cl[q];
         __syncwarp();
         if (live) {
-            float c_old[8];
-            float gates[32];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) c_old[k] = sc[lane * 9 + k];
+            // new cell / hidden state go straight back into the staging tiles; the activated gates replace the
+            // pre-activations in v[] (no second register array: this path must not cost the other paths registers)
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float gi = v[k] + bias[k];
                 const float gf = v[8 + k] + bias[8 + k];
                 const float gg = v[16 + k] + bias[16 + k];
                 const float go = v[24 + k] + bias[24 + k];
+                const float c_old = sc[lane * 9 + k];
                 float c_new, h_new, si, sf, tg, so;
                 if (j.round_out) {
                     si = sigmoid_f(gi); sf = sigmoid_f(gf); tg = tanh_f(gg); so = sigmoid_f(go);
-                    c_new = sf * c_old[k] + si * tg;
+                    c_new = sf * c_old + si * tg;
                     h_new = round_tf32(so * tanh_f(c_new));
                 } else {
                     si = 1.0f / (1.0f + expf(-gi)); sf = 1.0f / (1.0f + expf(-gf)); tg = tanhf(gg); so = 1.0f / (1.0f + expf(-go));
-                    c_new = sf * c_old[k] + si * tg;
+                    c_new = sf * c_old + si * tg;
                     h_new = so * tanhf(c_new);
                 }
-                if (j.gates_out) { gates[k] = si; gates[8 + k] = sf; gates[16 + k] = tg; gates[24 + k] = so; }
-                v[k] = c_new;
-                v[8 + k] = h_new;
+                v[k] = si; v[8 + k] = sf; v[16 + k] = tg; v[24 + k] = so;
+                sc[lane * 9 + k] = c_new;
+                sh[lane * 9 + k] = h_new;
             }
             if (j.gates_out) {
                 // training: keep the activated gates for the backward pass, in the accumulator's own column order
                 // (32 contiguous floats per row and chunk: eight 16-byte stores instead of 32 scattered words)
                 float4* gp = reinterpret_cast<float4*>(j.gates_out + (int64_t)row * j.gates_stride + n0);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) gp[q] = make_float4(gates[4 * q], gates[4 * q + 1], gates[4 * q + 2], gates[4 * q + 3]);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                sc[lane * 9 + k] = v[k];
-                sh[lane * 9 + k] = v[8 + k];
+                for (int q = 0; q < 8; ++q) gp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
         }
         __syncwarp();

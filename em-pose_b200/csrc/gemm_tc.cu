@@ -28,6 +28,7 @@ namespace empose {
 namespace {
 
 constexpr int kStages = 4;
+constexpr int kDefaultClusterMode = 0;      // EMPOSE_TC_CLUSTER when the variable is not set
 constexpr int kABytes = kTileM * kChunkK * 4;        // 16 KB
 constexpr int kWBytes = kMaxTileN * kChunkK * 4;     // 32 KB
 constexpr int kStageBytes = kABytes + kWBytes;
@@ -46,7 +47,35 @@ struct __align__(8) Control {
 };
 
 constexpr int kEpiStageBytes = kEpiWarps * kStageFloats * 4;     // one [32][33] fp32 transpose tile per epilogue warp
-constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*alignment slack*/ + 256 /*Control*/;
+constexpr int kControlBytes = 256;
+constexpr int kJobWords = (int)(sizeof(GemmJob) / 4);              // the epilogue keeps the current and the next job in shared memory
+static_assert(sizeof(GemmJob) % 8 == 0 && kJobWords <= kEpiThreads, "one word of a job per epilogue thread");
+static_assert(sizeof(Control) <= kControlBytes, "Control grew");
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*alignment slack*/ + kControlBytes + 2 * (int)sizeof(GemmJob);
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+// What the single-thread roles need of a job.  They fetch the fields of the NEXT job while working on the current one:
+// every epilogue ends in a device-scope fence, which invalidates L1, so a field read on demand is an L2 round trip on
+// the critical path (ncu, v10: 38 % of all stall samples were waits for such loads).
+struct ProducerView {
+    int32_t dep, n_count, n_begin, in_half, a_k[2], a_map[2], a_scratch[2], w_map, w_map2, w_koff[2];
+};
+struct IssuerView {
+    int32_t in_half, n_count, a_k[2];
+};
+__device__ __forceinline__ ProducerView producer_view(const GemmJob& j) {
+    ProducerView v;
+    v.dep = j.dep; v.n_count = j.n_count; v.n_begin = j.n_begin; v.in_half = j.in_half;
+    v.a_k[0] = j.a_k[0]; v.a_k[1] = j.a_k[1]; v.a_map[0] = j.a_map[0]; v.a_map[1] = j.a_map[1];
+    v.a_scratch[0] = j.a_scratch[0]; v.a_scratch[1] = j.a_scratch[1];
+    v.w_map = j.w_map; v.w_map2 = j.w_map2; v.w_koff[0] = j.w_koff[0]; v.w_koff[1] = j.w_koff[1];
+    return v;
+}
+__device__ __forceinline__ IssuerView issuer_view(const GemmJob& j) {
+    IssuerView v;
+    v.in_half = j.in_half; v.n_count = j.n_count; v.a_k[0] = j.a_k[0]; v.a_k[1] = j.a_k[1];
+    return v;
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,6 +125,28 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
                  ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
+// CTA-pair (cta_group::2) variants.  The tile lands in the executing CTA's shared memory, the bytes are counted on a
+// barrier that may live in the peer CTA (`bar_cluster_addr` is a shared::cluster address, see mapa_rank0).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int crd0, int crd1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(crd0), "r"(crd1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA 0 of the cluster
+__device__ __forceinline__ uint32_t mapa_rank0(const void* p) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -142,6 +193,27 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         : "memory");
 }
 
+// CTA-pair MMA: D is [256 x N]: rows 0-127 accumulate in the TMEM of CTA 0, rows 128-255 in CTA 1's; each CTA's shared
+// memory holds ITS 128 rows of A and ITS N/2 rows of W at the offsets the descriptors name.  Issued by CTA 0 only.
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major tile whose rows are 128 bytes (32 fp32) apart, stored
 // with the 128-byte swizzle TMA produces: 8-row groups are 1024 bytes apart (SBO), LBO is unused.
 // Field layout: cute::UMMA::SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
@@ -158,9 +230,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10) or f16 (0, 0), both
 // K-major, N>>3 at bit 17, M>>4 at bit 24.
-__device__ __forceinline__ uint32_t make_idesc(int n, int half) {
+__device__ __forceinline__ uint32_t make_idesc(int n, int half, int m = kTileM) {
     const uint32_t fmt = half ? 0u : ((2u << 7) | (2u << 10));
-    return (1u << 4) | fmt | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    return (1u << 4) | fmt | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, float (&v)[32]) {
@@ -179,19 +251,25 @@ __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ int job_chunk_k(const GemmJob& j) { return j.in_half ? kChunkKHalf : kChunkK; }
-__device__ __forceinline__ int job_k_chunks(const GemmJob& j) {
+template <class View>
+__device__ __forceinline__ int job_chunk_k(const View& j) { return j.in_half ? kChunkKHalf : kChunkK; }
+template <class View>
+__device__ __forceinline__ int job_k_chunks(const View& j) {
     const int ck = job_chunk_k(j);
     return (j.a_k[0] + ck - 1) / ck + (j.a_k[1] + ck - 1) / ck;
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-// kCluster = 1: every CTA loads its own A and W tiles.
-// kCluster = 2: launched as clusters of two CTAs that walk the SAME job sequence on two adjacent row tiles.  Each CTA
+// kMode = 1: every CTA loads its own A and W tiles.
+// kMode = 2: launched as clusters of two CTAs that walk the SAME job sequence on two adjacent row tiles.  Each CTA
 //   loads its own A tile and ONE HALF of every W tile, multicast into both CTAs' shared memory, which halves the W
-//   traffic out of L2 (the bound of the K = 512 layers: 48 KB per 512 MMA cycles and SM).  A ring slot may only be
-//   refilled when BOTH CTAs have consumed it, so every MMA commit arrives on the `empty` barrier of both CTAs.
-template <int kCluster>
+//   traffic out of L2.  A ring slot may only be refilled when BOTH CTAs have consumed it, so every MMA commit arrives
+//   on the `empty` barrier of both CTAs.  (Measured: no faster -- L2 is not the bound, shared memory is.)
+// kMode = 3: the same pairs of row tiles as ONE tcgen05.mma.cta_group::2 (M = 256): each CTA keeps its A tile and HALF
+//   of the W tile in its own shared memory (32 KB per ring slot instead of 48) and the tensor cores of the two SMs
+//   share the W halves.  CTA 0 issues the MMAs for both; its `full` barriers count the TMA bytes of both CTAs; MMA
+//   commits arrive on both CTAs' `empty` / `tmem_full` barriers; both epilogues arrive on CTA 0's `tmem_empty`.
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __restrict__ jobs,
                                                               const CUtensorMap* __restrict__ maps, int job_begin,
                                                               int job_count, int jobs_per_item, int m_tiles,
@@ -200,11 +278,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes);
     Control* ctl = reinterpret_cast<Control*>(smem + kStages * kStageBytes + kEpiStageBytes);
+    GemmJob* job_s = reinterpret_cast<GemmJob*>(smem + kStages * kStageBytes + kEpiStageBytes + kControlBytes);     // [2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int groups = job_count / jobs_per_item;
+    // the job sequence of this CTA: (item, jj) -> index into `jobs`; the successor of the last job of an item is the first of the next
+    auto job_index = [&](int item, int jj) { return job_begin + (item % groups) * jobs_per_item + jj; };
     // work items: (row tile, job group); in cluster mode an item is a PAIR of row tiles, one per CTA of the cluster
+    constexpr int kCluster = kMode >= 2 ? 2 : 1;
+    constexpr bool kPair = kMode == 3;
     const int n_items = (kCluster == 2 ? (m_tiles + 1) / 2 : m_tiles) * groups;
     const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;
     const int item0 = kCluster == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -214,20 +297,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&ctl->full[s], 1);
-            mbar_init(&ctl->empty[s], kCluster);
+            mbar_init(&ctl->empty[s], kMode == 2 ? 2 : 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&ctl->tmem_full[b], 1);
-            mbar_init(&ctl->tmem_empty[b], 1);
+            mbar_init(&ctl->tmem_empty[b], kPair ? 2 : 1);
         }
         ctl->epi_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
-                     "n"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {      // the same warp of both CTAs allocates the same columns in both tensor memories
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                         "n"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                         "n"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -239,11 +329,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, items_done = 0;
+            ProducerView nxt;
+            if (item0 < n_items) nxt = producer_view(jobs[job_index(item0, 0)]);
             for (int item = item0; item < n_items; item += item_step, ++items_done) {
                 const int m0 = (kCluster == 2 ? 2 * (item / groups) + (int)crank : item / groups) * kTileM;
-                const int first = job_begin + (item % groups) * jobs_per_item;
                 for (int jj = 0; jj < jobs_per_item; ++jj) {
-                    const GemmJob& job = jobs[first + jj];
+                    const ProducerView job = nxt;
+                    {
+                        const int nj = jj + 1 < jobs_per_item ? jj + 1 : 0;
+                        const int ni = nj ? item : item + item_step;
+                        if (ni < n_items) nxt = producer_view(jobs[job_index(ni, nj)]);
+                    }
                     if (job.dep >= 0) {
                         const uint32_t need = items_done * (uint32_t)jobs_per_item + (uint32_t)job.dep + 1u;
                         while (ctl->epi_done < need) {
@@ -259,7 +355,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                             else mbar_wait(&ctl->empty[stage], phase ^ 1u);
                             uint8_t* a_dst = smem + stage * kStageBytes;
                             uint8_t* w_dst = a_dst + kABytes;
-                            if (debug_mode & 2) {            // measurement only: no loads, MMAs run on stale data
+                            if (kPair) {
+                                // both CTAs fill their own slot; the bytes of both are counted on CTA 0's barrier
+                                const uint32_t full0 = mapa_rank0(&ctl->full[stage]);
+                                if (crank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)kABytes + w_bytes);
+                                const int half_rows = job.n_count >> 1;
+                                tma_load_2d_pair(a_dst, &maps[job.a_map[seg]], full0, kc * ck,
+                                                 job.a_scratch[seg] ? (int)blockIdx.x * kTileM : m0);
+                                tma_load_2d_pair(w_dst, &maps[job.w_map2], full0, job.w_koff[seg] + kc * ck,
+                                                 job.n_begin + (int)crank * half_rows);
+                            } else if (debug_mode & 2) {            // measurement only: no loads, MMAs run on stale data
                                 mbar_arrive(&ctl->full[stage]);
                             } else {
                                 mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
@@ -281,18 +386,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && !(kPair && crank != 0)) {
             uint32_t stage = 0, phase = 0, seq = 0;
+            IssuerView nxt;
+            if (item0 < n_items) nxt = issuer_view(jobs[job_index(item0, 0)]);
             for (int item = item0; item < n_items; item += item_step) {
-                const int first = job_begin + (item % groups) * jobs_per_item;
                 for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
-                    const GemmJob& job = jobs[first + jj];
+                    const IssuerView job = nxt;
+                    {
+                        const int nj = jj + 1 < jobs_per_item ? jj + 1 : 0;
+                        const int ni = nj ? item : item + item_step;
+                        if (ni < n_items) nxt = issuer_view(jobs[job_index(ni, nj)]);
+                    }
                     const uint32_t buf = seq & 1u;
-                    mbar_wait(&ctl->tmem_empty[buf], ((seq >> 1) & 1u) ^ 1u);
+                    if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_empty[buf], ((seq >> 1) & 1u) ^ 1u);
+                    else mbar_wait(&ctl->tmem_empty[buf], ((seq >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * kMaxTileN;
                     const int half = job.in_half;
-                    const uint32_t idesc = make_idesc(job.n_count, half);
+                    const uint32_t idesc = make_idesc(job.n_count, half, kPair ? 2 * kTileM : kTileM);
                     const int chunks = job_k_chunks(job);
                     for (int kc = 0; kc < chunks; ++kc) {
                         if (kCluster == 2) mbar_wait_guarded(&ctl->full[stage], phase);
@@ -307,15 +419,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
 #pragma unroll
                             for (int k = 0; k < kChunkK / 8; ++k) {
                                 // advance 8 tf32 / 16 f16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
-                                if (half) umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
-                                else umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                                const uint32_t acc = (kc | k) != 0 ? 1u : 0u;
+                                if (kPair) {
+                                    if (half) umma_f16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
+                                    else umma_tf32_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
+                                } else {
+                                    if (half) umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
+                                    else umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
+                                }
                             }
-                            if (kCluster == 2) umma_commit_multicast(&ctl->empty[stage], kMask);   // frees the slot in both CTAs
+                            if (kPair) umma_commit_pair(&ctl->empty[stage], kMask);                     // frees the slot in both CTAs
+                            else if (kCluster == 2) umma_commit_multicast(&ctl->empty[stage], kMask);   // ditto
                             else umma_commit(&ctl->empty[stage]);
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
-                    umma_commit(&ctl->tmem_full[buf]);
+                    if (kPair) umma_commit_pair(&ctl->tmem_full[buf], kMask);     // both CTAs' epilogues read their half of D
+                    else umma_commit(&ctl->tmem_full[buf]);
                 }
             }
         }
@@ -325,20 +445,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         const int quad = ew & 3;                  // TMEM lanes 32*quad .. 32*quad+31 (a warp may only touch its own quadrant)
         const int half = ew >> 2;                 // columns [half*128, half*128 + 128) of the accumulator
         uint32_t seq = 0;
+        // The epilogue reads job fields all the time (per 32-column chunk): it works on a shared-memory copy.  Thread e
+        // of the 256 epilogue threads carries word e of the NEXT job through the current one and drops it into the other
+        // slot before the barrier that ends the job.
+        const int et = (int)threadIdx.x - 4 * 32;
+        if (item0 < n_items && et < kJobWords)
+            reinterpret_cast<uint32_t*>(&job_s[0])[et] = reinterpret_cast<const uint32_t*>(&jobs[job_index(item0, 0)])[et];
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         for (int item = item0; item < n_items; item += item_step) {
             const int m0 = (kCluster == 2 ? 2 * (item / groups) + (int)crank : item / groups) * kTileM;
-            const int first = job_begin + (item % groups) * jobs_per_item;
             for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
-                const GemmJob& job = jobs[first + jj];      // read-only global data: fields are fetched on demand
                 const uint32_t buf = seq & 1u;
-                mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
-                tcgen05_fence_after();
+                const GemmJob& job = job_s[buf];
+                uint32_t next_word = 0;
+                bool has_next = false;
+                {
+                    const int nj = jj + 1 < jobs_per_item ? jj + 1 : 0;
+                    const int ni = nj ? item : item + item_step;
+                    has_next = ni < n_items && et < kJobWords;
+                    if (has_next) next_word = reinterpret_cast<const uint32_t*>(&jobs[job_index(ni, nj)])[et];
+                }
                 // activations chained inside this CTA live in CTA-local scratch rows: they are re-read from L2 by the next
                 // layer and overwritten by the next tile before they would be written back to HBM
                 const int row0 = (job.out_scratch ? (int)blockIdx.x * kTileM : m0) + quad * 32;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kMaxTileN;
+                const int c_begin = half * (kMaxTileN / 2);
                 const int c_end = min(job.n_count, (half + 1) * (kMaxTileN / 2));
-                for (int c0 = half * (kMaxTileN / 2); c0 < c_end; c0 += 32) {
+                // fp16 LSTM jobs: the cell state of the first chunk pair is fetched while the MMAs are still running
+                const bool lstm_pre = lstm_half_paired(job) && !(debug_mode & 128);
+                float4 cpre[4];
+                if (lstm_pre && c_begin < c_end) lstm_half_load_c(job, row0, lane, c_begin, cpre);
+                if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_full[buf], (seq >> 1) & 1u);
+                else mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
+                tcgen05_fence_after();
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     float v[32];
                     if (debug_mode & 32) {                 // measurement only: no TMEM read
 #pragma unroll
@@ -346,16 +486,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     } else {
                         tmem_load_32cols(taddr + (uint32_t)c0, v);
                     }
-                    if (!(debug_mode & 4)) epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats, (debug_mode & 16) != 0);
+                    if (!(debug_mode & 4))
+                        epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats, (debug_mode & 16) != 0, lstm_pre ? cpre : nullptr);
+                    // ... and the next pair's while this pair is being computed
+                    if (lstm_pre && !(c0 & 32) && c0 + 64 < c_end) lstm_half_load_c(job, row0, lane, c0 + 64, cpre);
                 }
                 tcgen05_fence_before();
+                if (has_next) reinterpret_cast<uint32_t*>(&job_s[buf ^ 1u])[et] = next_word;
                 if (!(debug_mode & 8)) {
-                    __threadfence();                                  // stores visible at L2 ...
-                    asm volatile("fence.proxy.async;" ::: "memory");   // ... and ordered before later TMA reads
+                    // The only in-kernel consumer of these stores is this CTA's own TMA (scratch activations of the next
+                    // layer): order them before the barrier at CTA scope and hand them to the async proxy.  A device-scope
+                    // fence here also invalidates L1 on every job, which turned every bias / sequence-length / job-field
+                    // read of the next job into an L2 round trip (bit 64 brings it back for comparison).
+                    if (debug_mode & 64) __threadfence();
+                    else __threadfence_block();
+                    asm volatile("fence.proxy.async;" ::: "memory");
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 if (threadIdx.x == 4 * 32) {
-                    mbar_arrive(&ctl->tmem_empty[buf]);
+                    if (kPair) mbar_arrive_cluster(mapa_rank0(&ctl->tmem_empty[buf]));      // CTA 0 issues the MMAs of both
+                    else mbar_arrive(&ctl->tmem_empty[buf]);
                     ctl->epi_done = seq + 1u;
                 }
             }
@@ -367,7 +517,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     if (kCluster == 2) cluster_sync_all();        // nobody leaves while the peer may still multicast into this CTA
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
 }
 
@@ -421,21 +572,23 @@ int tc_encode_map(void* out_map, const float* base, int64_t row_stride_elems, in
 int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_count, int jobs_per_item, int m_tiles,
               int num_sms, cudaStream_t stream) {
     static bool configured = false;
-    static int max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster mode unavailable or disabled)
+    static int max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster modes unavailable or disabled)
+    static int cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
     // EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
-    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads
+    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch
     static int debug_mode = 0;
     if (!configured) {
         EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         const char* e = getenv("EMPOSE_TC_DEBUG");
         debug_mode = e ? atoi(e) : 0;
-        // EMPOSE_TC_CLUSTER=1 enables the 2-CTA multicast variant.  It is correct (same parity results) but OFF by default:
-        // measured on the B200 it halves the W traffic out of L2 and changes nothing in time (profiles/r01/README.md) --
-        // the mainloop is bound by SHARED-MEMORY bandwidth (per 512 MMA cycles: 48 KB written by TMA + 48 KB of operand
-        // reads against 128 B/clk), which only a cta_group::2 MMA (half of W per SM) relieves.
+        // EMPOSE_TC_CLUSTER: 0 one CTA per row tile; 1 pairs of CTAs with the W tile multicast (correct, halves the W
+        // traffic out of L2, no faster: profiles/r01/README.md); 2 pairs of CTAs issuing ONE cta_group::2 MMA per pair
+        // (each SM stages half of W: relieves the shared-memory bandwidth that bounds the mainloop).
         const char* c = getenv("EMPOSE_TC_CLUSTER");
-        if (c && atoi(c) == 1 && !(debug_mode & 3)) {
+        const int want = c ? atoi(c) : kDefaultClusterMode;
+        if ((want == 1 || want == 2) && !(debug_mode & 3)) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(2 * (num_sms / 2)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
             cudaLaunchAttribute attr;
@@ -443,10 +596,13 @@ int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_
             attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
             cfg.attrs = &attr; cfg.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<2>, &cfg) == cudaSuccess) max_clusters = n;
+            const cudaError_t q = want == 1 ? cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<2>, &cfg)
+                                            : cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<3>, &cfg);
+            if (q == cudaSuccess && n > 0) { max_clusters = n; cluster_mode = want + 1; }
             else cudaGetLastError();
         }
-        if (getenv("EMPOSE_TC_VERBOSE")) fprintf(stderr, "empose_b200: gemm executor: %d co-resident 2-CTA clusters on %d SMs\n", max_clusters, num_sms);
+        if (getenv("EMPOSE_TC_VERBOSE"))
+            fprintf(stderr, "empose_b200: gemm executor: mode %d, %d co-resident 2-CTA clusters on %d SMs\n", cluster_mode, max_clusters, num_sms);
         configured = true;
     }
     const int groups = job_count / jobs_per_item;
@@ -460,7 +616,10 @@ int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
-        EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode));
+        if (cluster_mode == 3)
+            EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3>, d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode));
+        else
+            EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode));
         return EMPOSE_OK;
     }
     const int n_items = m_tiles * groups;

@@ -14,6 +14,10 @@ tail -n 2 gpurun_out/bench.log | cut -c1-300
 timeout -s KILL 600 python bench.py --workload train --steps 10 --warmup 3 > gpurun_out/bench_train.log 2>&1
 timeout -s KILL 600 python bench.py --workload synth --steps 10 --warmup 3 > gpurun_out/bench_synth.log 2>&1
 tail -n 1 gpurun_out/bench_synth.log | cut -c1-400
+timeout -s KILL 600 python bench.py --workload metrics --steps 10 --warmup 3 > gpurun_out/bench_metrics.log 2>&1
+tail -n 1 gpurun_out/bench_metrics.log | cut -c1-400
+timeout -s KILL 600 python bench.py --workload birnn --steps 5 --warmup 3 > gpurun_out/bench_birnn.log 2>&1
+tail -n 1 gpurun_out/bench_birnn.log | cut -c1-400
 if [ "$1" = "profile" ]; then
   timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
