@@ -27,7 +27,8 @@ namespace empose {
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kStages = 4;                   // ring slots of A [128 x 128 B] + W [256 x 128 B] (48 KB)
+constexpr int kStagesPair = 6;               // CTA-pair mode: a slot holds half of W (32 KB), so the same memory is a deeper ring
 constexpr int kDefaultClusterMode = 0;      // EMPOSE_TC_CLUSTER when the variable is not set
 constexpr int kABytes = kTileM * kChunkK * 4;        // 16 KB
 constexpr int kWBytes = kMaxTileN * kChunkK * 4;     // 32 KB
@@ -38,8 +39,8 @@ constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kEpiThreads = kEpiWarps * 32;
 
 struct __align__(8) Control {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+    uint64_t full[kStagesPair];
+    uint64_t empty[kStagesPair];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
@@ -162,6 +163,20 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 28)) __trap();
     }
+}
+
+// One lane of a fully active, converged warp.  The TMA and MMA roles run their loops on the WHOLE warp with uniform
+// values and let the elected lane issue: inside an `if (lane == 0)` region the compiler treats every operand as divergent
+// and wraps each UTMALDG / UTCHMMA in ELECT + R2UR shuffles -- ~200 instructions per K chunk for four MMAs, which made the
+// issuing thread, not the tensor pipe, the mainloop's bound (ncu: pipe 58 % active with nothing else running).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -288,6 +303,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     // work items: (row tile, job group); in cluster mode an item is a PAIR of row tiles, one per CTA of the cluster
     constexpr int kCluster = kMode >= 2 ? 2 : 1;
     constexpr bool kPair = kMode == 3;
+    constexpr int kRing = kPair ? kStagesPair : kStages;                                    // slots in the operand ring ...
+    constexpr int kSlotBytes = kPair ? kABytes + kWBytes / 2 : kStageBytes;                 // ... of this many bytes
+    static_assert(kRing * kSlotBytes <= kStages * kStageBytes, "the ring must fit the operand region");
+    const uint32_t ring = (kPair && (debug_mode & 256)) ? (uint32_t)kStages : (uint32_t)kRing;     // bit 256: experiment, shallow ring
     const int n_items = (kCluster == 2 ? (m_tiles + 1) / 2 : m_tiles) * groups;
     const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;
     const int item0 = kCluster == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     constexpr uint16_t kMask = kCluster == 2 ? 3 : 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kRing; ++s) {
             mbar_init(&ctl->full[s], 1);
             mbar_init(&ctl->empty[s], kMode == 2 ? 2 : 1);
         }
@@ -326,8 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     const uint32_t tmem_base = ctl->tmem_base;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (whole warp, one elected lane issues) =================
+        {
             uint32_t stage = 0, phase = 0, items_done = 0;
             ProducerView nxt;
             if (item0 < n_items) nxt = producer_view(jobs[job_index(item0, 0)]);
@@ -345,51 +364,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         while (ctl->epi_done < need) {
                         }
                         __threadfence_block();
+                        __syncwarp();
                     }
                     const uint32_t w_bytes = (uint32_t)job.n_count * kChunkK * 4u;        // 128 bytes per row in either type
                     const int ck = job_chunk_k(job);
+                    const int half_rows = job.n_count >> 1;
                     for (int seg = 0; seg < 2; ++seg) {
                         const int chunks = (job.a_k[seg] + ck - 1) / ck;
+                        const CUtensorMap* a_map = &maps[job.a_map[seg]];
+                        const int a_row = job.a_scratch[seg] ? (int)blockIdx.x * kTileM : m0;
+                        const int w_k0 = job.w_koff[seg];
                         for (int kc = 0; kc < chunks; ++kc) {
                             if (kCluster == 2) mbar_wait_guarded(&ctl->empty[stage], phase ^ 1u);
                             else mbar_wait(&ctl->empty[stage], phase ^ 1u);
-                            uint8_t* a_dst = smem + stage * kStageBytes;
+                            uint8_t* a_dst = smem + stage * kSlotBytes;
                             uint8_t* w_dst = a_dst + kABytes;
-                            if (kPair) {
-                                // both CTAs fill their own slot; the bytes of both are counted on CTA 0's barrier
-                                const uint32_t full0 = mapa_rank0(&ctl->full[stage]);
-                                if (crank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)kABytes + w_bytes);
-                                const int half_rows = job.n_count >> 1;
-                                tma_load_2d_pair(a_dst, &maps[job.a_map[seg]], full0, kc * ck,
-                                                 job.a_scratch[seg] ? (int)blockIdx.x * kTileM : m0);
-                                tma_load_2d_pair(w_dst, &maps[job.w_map2], full0, job.w_koff[seg] + kc * ck,
-                                                 job.n_begin + (int)crank * half_rows);
-                            } else if (debug_mode & 2) {            // measurement only: no loads, MMAs run on stale data
-                                mbar_arrive(&ctl->full[stage]);
-                            } else {
-                                mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
-                                tma_load_2d(a_dst, &maps[job.a_map[seg]], &ctl->full[stage], kc * ck,
-                                            job.a_scratch[seg] ? (int)blockIdx.x * kTileM : m0);
-                                if (kCluster == 2) {       // my half of the W rows, delivered to both CTAs
-                                    const int half_rows = job.n_count >> 1;
-                                    tma_load_2d_multicast(w_dst + crank * (uint32_t)half_rows * 128u, &maps[job.w_map2], &ctl->full[stage],
-                                                          job.w_koff[seg] + kc * ck, job.n_begin + (int)crank * half_rows, kMask);
+                            if (elect_one()) {
+                                if (kPair) {
+                                    // both CTAs fill their own slot; the bytes of both are counted on CTA 0's barrier
+                                    const uint32_t full0 = mapa_rank0(&ctl->full[stage]);
+                                    if (crank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)kABytes + w_bytes);
+                                    tma_load_2d_pair(a_dst, a_map, full0, kc * ck, a_row);
+                                    tma_load_2d_pair(w_dst, &maps[job.w_map2], full0, w_k0 + kc * ck, job.n_begin + (int)crank * half_rows);
+                                } else if (debug_mode & 2) {            // measurement only: no loads, MMAs run on stale data
+                                    mbar_arrive(&ctl->full[stage]);
                                 } else {
-                                    tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], job.w_koff[seg] + kc * ck, job.n_begin);
+                                    mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kABytes + w_bytes);
+                                    tma_load_2d(a_dst, a_map, &ctl->full[stage], kc * ck, a_row);
+                                    if (kCluster == 2) {       // my half of the W rows, delivered to both CTAs
+                                        tma_load_2d_multicast(w_dst + crank * (uint32_t)half_rows * 128u, &maps[job.w_map2], &ctl->full[stage],
+                                                              w_k0 + kc * ck, job.n_begin + (int)crank * half_rows, kMask);
+                                    } else {
+                                        tma_load_2d(w_dst, &maps[job.w_map], &ctl->full[stage], w_k0 + kc * ck, job.n_begin);
+                                    }
                                 }
                             }
-                            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                            __syncwarp();
+                            if (++stage == ring) { stage = 0; phase ^= 1u; }
                         }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0 && !(kPair && crank != 0)) {
+        // ================= MMA issuer (whole warp, one elected lane issues) =================
+        if (!(kPair && crank != 0)) {
             uint32_t stage = 0, phase = 0, seq = 0;
             IssuerView nxt;
             if (item0 < n_items) nxt = issuer_view(jobs[job_index(item0, 0)]);
+            const uint32_t ring_base = smem_u32(smem);
             for (int item = item0; item < n_items; item += item_step) {
                 for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
                     const IssuerView job = nxt;
@@ -403,39 +426,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     else mbar_wait(&ctl->tmem_empty[buf], ((seq >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * kMaxTileN;
-                    const int half = job.in_half;
+                    const bool half = job.in_half != 0;
                     const uint32_t idesc = make_idesc(job.n_count, half, kPair ? 2 * kTileM : kTileM);
                     const int chunks = job_k_chunks(job);
                     for (int kc = 0; kc < chunks; ++kc) {
                         if (kCluster == 2) mbar_wait_guarded(&ctl->full[stage], phase);
                         else mbar_wait(&ctl->full[stage], phase);
                         tcgen05_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-                        const uint64_t a_desc = make_smem_desc(a_addr);
-                        const uint64_t b_desc = make_smem_desc(a_addr + kABytes);
-                        if (debug_mode & 1) {                // measurement only: loads without MMAs (not in cluster mode)
-                            mbar_arrive(&ctl->empty[stage]);
-                        } else {
+                        const uint64_t a_desc = make_smem_desc(ring_base + stage * (uint32_t)kSlotBytes);
+                        const uint64_t b_desc = a_desc + (uint64_t)(kABytes >> 4);
+                        if (elect_one()) {
+                            if (debug_mode & 1) {                // measurement only: loads without MMAs (not in cluster mode)
+                                mbar_arrive(&ctl->empty[stage]);
+                            } else {
+                                // 8 tf32 / 16 f16 = 32 bytes along K inside the 128-byte swizzle row per MMA: +2 in the >>4 address field
+                                if (half) {
 #pragma unroll
-                            for (int k = 0; k < kChunkK / 8; ++k) {
-                                // advance 8 tf32 / 16 f16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
-                                const uint32_t acc = (kc | k) != 0 ? 1u : 0u;
-                                if (kPair) {
-                                    if (half) umma_f16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
-                                    else umma_tf32_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
+                                    for (int k = 0; k < kChunkK / 8; ++k) {
+                                        if (kPair) umma_f16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                                        else umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                                    }
                                 } else {
-                                    if (half) umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
-                                    else umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
+#pragma unroll
+                                    for (int k = 0; k < kChunkK / 8; ++k) {
+                                        if (kPair) umma_tf32_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                                        else umma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                                    }
                                 }
+                                if (kPair) umma_commit_pair(&ctl->empty[stage], kMask);                     // frees the slot in both CTAs
+                                else if (kCluster == 2) umma_commit_multicast(&ctl->empty[stage], kMask);   // ditto
+                                else umma_commit(&ctl->empty[stage]);
                             }
-                            if (kPair) umma_commit_pair(&ctl->empty[stage], kMask);                     // frees the slot in both CTAs
-                            else if (kCluster == 2) umma_commit_multicast(&ctl->empty[stage], kMask);   // ditto
-                            else umma_commit(&ctl->empty[stage]);
                         }
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        __syncwarp();
+                        if (++stage == ring) { stage = 0; phase ^= 1u; }
                     }
-                    if (kPair) umma_commit_pair(&ctl->tmem_full[buf], kMask);     // both CTAs' epilogues read their half of D
-                    else umma_commit(&ctl->tmem_full[buf]);
+                    if (elect_one()) {
+                        if (kPair) umma_commit_pair(&ctl->tmem_full[buf], kMask);     // both CTAs' epilogues read their half of D
+                        else umma_commit(&ctl->tmem_full[buf]);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -575,7 +605,7 @@ int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_
     static int max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster modes unavailable or disabled)
     static int cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
     // EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
-    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch
+    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring
     static int debug_mode = 0;
     if (!configured) {
         EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
