@@ -45,6 +45,8 @@ struct GemmJob {
     int32_t n_count;         // columns computed (multiple of 16, <= kMaxTileN)
     int32_t m_rows;          // valid rows overall; rows >= m_rows are never written
     int32_t dep;             // chain-local index of the job that must have finished before A may be loaded (-1: none)
+    int32_t is_dep;          // 1: a later job of the same item names this job as its `dep`: its epilogue must hand the
+                             // stores of this thread (this job's and the earlier ones') over to the async proxy (TMA)
     // ---- epilogue ----
     int32_t epi;
     int32_t round_out;       // 1: round outputs that feed later GEMMs to tf32 and use fast transcendentals
@@ -95,6 +97,124 @@ constexpr int kStageFloats = 32 * kStageLd;        // one warp-private [32][33] 
 // Loads are batched into registers before any store so that pointer aliasing cannot serialise them.
 // Bias arrays are padded by 32 floats, so the vector loads below never leave the allocation.
 // Must be called by all 32 lanes of the warp.
+// 16-byte accesses to the staging tiles in the shared state space proper (through a generic pointer they compile to
+// LD.E / ST.E, whose latency sits on the long scoreboard)
+__device__ __forceinline__ uint32_t smem_addr_of(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
+    sts128(addr, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    const uint4 v = lds128(addr);
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+
+// ---- fp16 linear jobs (the MLP chains) ----
+// Everything the chunk loop needs of such a job, fetched ONCE per job into registers: the job record lives in memory the
+// compiler must assume any store may alias, so fields read on demand are re-read after every store.
+struct LinearHalfView {
+    __half* out;             // first output element of the job's column 0 in row 0 (out_col0 and n_begin folded in)
+    int64_t out_stride;
+    const float* bias;       // bias of the job's column 0, or null
+    float alpha;             // PReLU slope (1: no activation)
+    int32_t m_rows;
+    int32_t fast_cols;       // chunks with c0 + 32 <= fast_cols take this path (0: none)
+    bool zero_row;           // this lane's row is a padded frame: it contributes only the bias (layers.py:153)
+};
+__device__ __forceinline__ LinearHalfView linear_half_view(const GemmJob& j, int row0, int lane) {
+    LinearHalfView lv;
+    const bool ok = j.epi == EPI_LINEAR && j.out_half && !j.res;
+    const int n_begin = j.n_begin;
+    lv.fast_cols = ok ? min(j.n_valid, j.split) - n_begin : 0;
+    lv.out = reinterpret_cast<__half*>(j.out) + j.out_col0 + n_begin;
+    lv.out_stride = j.out_stride;
+    lv.bias = j.bias ? j.bias + n_begin : nullptr;
+    lv.alpha = j.has_act ? j.prelu_alpha : 1.0f;
+    lv.m_rows = j.m_rows;
+    const int row = row0 + lane;
+    lv.zero_row = false;
+    if (ok && j.mask_rows && row < lv.m_rows) {
+        const int fpw = j.frames_per_window;
+        lv.zero_row = (row % fpw) >= j.seq_len[row / fpw];
+    }
+    return lv;
+}
+__device__ __forceinline__ void linear_half_load_bias(const LinearHalfView& lv, int c0, float (&bias)[32]) {
+    if (lv.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(lv.bias + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldg(bp + q);
+            bias[4 * q] = t.x; bias[4 * q + 1] = t.y; bias[4 * q + 2] = t.z; bias[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias[i] = 0.0f;
+    }
+}
+// staged [32 rows][64 B] block (80-byte pitch) -> global memory, 8 rows per instruction
+__device__ __forceinline__ void linear_half_flush(const LinearHalfView& lv, int row0, int lane, int c0, uint32_t tile, bool no_store) {
+    __half* out_h = lv.out + c0;
+    const int64_t out_stride = lv.out_stride;
+    const int rows = no_store ? 0 : lv.m_rows - row0;
+    uint4 val[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) val[it] = lds128(tile + (it * 8 + (lane >> 2)) * 80 + (lane & 3) * 16);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        if (r < rows) *reinterpret_cast<uint4*>(out_h + (int64_t)(row0 + r) * out_stride + (lane & 3) * 8) = val[it];
+    }
+    __syncwarp();
+}
+// 16 accumulator columns of this lane's row -> bias, PReLU, fp16 -> 32 bytes of the staged row (byte offset `off`)
+__device__ __forceinline__ void linear_half_pack16(const LinearHalfView& lv, int lane, const uint32_t (&acc)[16], const float* bias,
+                                                   uint32_t tile, int off) {
+    const float alpha = lv.alpha;
+    const float keep = lv.zero_row ? 0.0f : 1.0f;       // (accumulators are finite: x * 1 + b rounds exactly like x + b)
+    uint32_t packed[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float y0 = fmaf(__uint_as_float(acc[2 * i]), keep, bias[2 * i]), y1 = fmaf(__uint_as_float(acc[2 * i + 1]), keep, bias[2 * i + 1]);
+        y0 = y0 > 0.0f ? y0 : alpha * y0;
+        y1 = y1 > 0.0f ? y1 : alpha * y1;
+        const __half2 h = __floats2half2_rn(y0, y1);
+        packed[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    sts128(tile + lane * 80 + off, packed[0], packed[1], packed[2], packed[3]);
+    sts128(tile + lane * 80 + off + 16, packed[4], packed[5], packed[6], packed[7]);
+}
+// A lane's 32 columns are 64 contiguous bytes of ITS row, so storing straight from registers makes every store
+// instruction touch 32 different lines with 16 bytes each (measured: 40 % of a 512x512 layer).  Instead the warp stages
+// its [32 rows][64 B] block in shared memory (80-byte pitch: conflict-free 16-byte accesses) and writes it out 8 rows
+// per instruction: 4 lanes x 16 B = two full sectors per row.
+__device__ __forceinline__ void linear_half_chunk(const LinearHalfView& lv, int row0, int lane, int c0, const float (&v)[32],
+                                                  const float (&bias)[32], float* __restrict__ stage, bool no_store) {
+    const float alpha = lv.alpha;
+    const bool zero = lv.zero_row;
+    uint32_t packed[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float y0 = (zero ? 0.0f : v[2 * i]) + bias[2 * i], y1 = (zero ? 0.0f : v[2 * i + 1]) + bias[2 * i + 1];
+        y0 = y0 > 0.0f ? y0 : alpha * y0;
+        y1 = y1 > 0.0f ? y1 : alpha * y1;
+        const __half2 h = __floats2half2_rn(y0, y1);
+        packed[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const uint32_t tile = smem_addr_of(stage);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sts128(tile + lane * 80 + q * 16, packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    __syncwarp();
+    linear_half_flush(lv, row0, lane, c0, tile, no_store);
+}
+
 // Cell-state block of one chunk pair [c0, c0 + 64) of an fp16 LSTM job -> registers, in the lane mapping the tile fill of
 // epilogue_chunk uses (8 rows x 64 B per instruction).  The tcgen05 executor issues this a pair ahead, so that the L2
 // round trip overlaps the wait for the accumulator / the arithmetic of the previous pair.
@@ -125,73 +245,52 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
         for (int i = 0; i < 32; ++i) bias[i] = 0.0f;
     }
     if (j.epi == EPI_LINEAR && j.out_half && !j.res && n0 + 32 <= j.n_valid && n0 + 32 <= j.split) {
-        // fp16 activations.  A lane's 32 columns are 64 contiguous bytes of ITS row, so storing straight from registers
-        // makes every store instruction touch 32 different lines with 16 bytes each (measured: 40 % of a 512x512 layer).
-        // Instead the warp stages its [32 rows][64 B] block in shared memory (80-byte pitch: conflict-free 16-byte
-        // accesses) and writes it out 8 rows per instruction: 4 lanes x 16 B = two full sectors per row.
-        if (j.mask_rows && row < j.m_rows && (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window]) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-        }
-        const float alpha = j.has_act ? j.prelu_alpha : 1.0f;
-        uint32_t packed[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float y0 = v[2 * i] + bias[2 * i], y1 = v[2 * i + 1] + bias[2 * i + 1];
-            y0 = y0 > 0.0f ? y0 : alpha * y0;
-            y1 = y1 > 0.0f ? y1 : alpha * y1;
-            const __half2 h = __floats2half2_rn(y0, y1);
-            packed[i] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        char* tile = reinterpret_cast<char*>(stage);
-        uint4* srow = reinterpret_cast<uint4*>(tile + lane * 80);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) srow[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-        __syncwarp();
-        __half* out_h = reinterpret_cast<__half*>(j.out) + j.out_col0 + n0;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int r = it * 8 + (lane >> 2), seg = lane & 3;
-            const uint4 val = *reinterpret_cast<const uint4*>(tile + r * 80 + seg * 16);
-            if (row0 + r < j.m_rows && !no_store)
-                *reinterpret_cast<uint4*>(out_h + (int64_t)(row0 + r) * j.out_stride + seg * 8) = val;
-        }
-        __syncwarp();
+        // fp16 activations (the tcgen05 executor builds the view once per job and calls linear_half_chunk directly)
+        const LinearHalfView lv = linear_half_view(j, row0, lane);
+        linear_half_chunk(lv, row0, lane, c0, v, bias, stage, no_store);
     } else if (j.epi == EPI_LSTM && j.out_half && (j.n_count % 64) == 0) {
+        // (job fields into registers first: after any store the compiler has to assume the job record changed)
+        const int m_rows = j.m_rows, hidden = j.hidden, t_step = j.t;
+        float* const c_state = j.c_state;
+        float* const out = j.out;
+        const float* const h_prev = j.h_prev;
+        const int64_t out_stride = j.out_stride, h_prev_stride = j.h_prev_stride;
+        const int32_t* const seq_len = j.seq_len;
         // fp16 hidden state, two chunks (16 units) at a time: the cell state of the pair is 64 B per row, the hidden state
         // 32 B.  They are moved between global and shared memory with coalesced 16-byte accesses (8 / 16 rows per
         // instruction, whole sectors) and every lane works on its own row in shared memory in between.
         const int pos = (c0 >> 5) & 1;                          // first / second chunk of the pair
         const int unit0 = lstm_unit_of_packed(n0) - pos * 8;    // first unit of the pair
-        char* ctile = reinterpret_cast<char*>(stage);           // [32][80 B]: 16 fp32 cell states per row
-        char* htile = ctile + 32 * 80;                          // [32][48 B]: 16 fp16 hidden states per row
-        const bool live = row < j.m_rows && j.t < j.seq_len[row];
+        const uint32_t ctile = smem_addr_of(stage);             // [32][80 B]: 16 fp32 cell states per row
+        const uint32_t htile = ctile + 32 * 80;                 // [32][48 B]: 16 fp16 hidden states per row
+        const bool live = row < m_rows && t_step < seq_len[row];
         if (pos == 0) {
-            const bool any_frozen = __any_sync(0xffffffffu, row < j.m_rows && !live);
+            const bool any_frozen = __any_sync(0xffffffffu, row < m_rows && !live);
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int r = it * 8 + (lane >> 2), seg = lane & 3;
                 if (cpre)
-                    *reinterpret_cast<float4*>(ctile + r * 80 + seg * 16) = cpre[it];
-                else if (row0 + r < j.m_rows)
-                    *reinterpret_cast<float4*>(ctile + r * 80 + seg * 16) =
-                        *reinterpret_cast<const float4*>(j.c_state + (int64_t)(row0 + r) * j.hidden + unit0 + seg * 4);
+                    sts128f(ctile + r * 80 + seg * 16, cpre[it]);
+                else if (row0 + r < m_rows)
+                    sts128f(ctile + r * 80 + seg * 16,
+                            *reinterpret_cast<const float4*>(c_state + (int64_t)(row0 + r) * hidden + unit0 + seg * 4));
             }
             if (any_frozen) {
-                const __half* hprev = reinterpret_cast<const __half*>(j.h_prev) + unit0;
+                const __half* hprev = reinterpret_cast<const __half*>(h_prev) + unit0;
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
                     const int r = it * 16 + (lane >> 1), seg = lane & 1;
-                    if (row0 + r < j.m_rows)
-                        *reinterpret_cast<uint4*>(htile + r * 48 + seg * 16) =
-                            *reinterpret_cast<const uint4*>(hprev + (int64_t)(row0 + r) * j.h_prev_stride + seg * 8);
+                    if (row0 + r < m_rows) {
+                        const uint4 hv = *reinterpret_cast<const uint4*>(hprev + (int64_t)(row0 + r) * h_prev_stride + seg * 8);
+                        sts128(htile + r * 48 + seg * 16, hv.x, hv.y, hv.z, hv.w);
+                    }
                 }
             }
             __syncwarp();
         }
         if (live) {
-            float4* cp = reinterpret_cast<float4*>(ctile + lane * 80 + pos * 32);
-            const float4 c0v = cp[0], c1v = cp[1];
+            const uint32_t cp = ctile + lane * 80 + pos * 32;
+            const float4 c0v = lds128f(cp), c1v = lds128f(cp + 16);
             const float c_old[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
             float c_new[8];
             uint32_t hp[4];
@@ -208,26 +307,30 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
                 const __half2 h = __floats2half2_rn(h2[0], h2[1]);
                 hp[k / 2] = *reinterpret_cast<const uint32_t*>(&h);
             }
-            cp[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
-            cp[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
-            *reinterpret_cast<uint4*>(htile + lane * 48 + pos * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            sts128f(cp, make_float4(c_new[0], c_new[1], c_new[2], c_new[3]));
+            sts128f(cp + 16, make_float4(c_new[4], c_new[5], c_new[6], c_new[7]));
+            sts128(htile + lane * 48 + pos * 16, hp[0], hp[1], hp[2], hp[3]);
         }
         if (pos == 1) {       // padded rows carry c (unchanged in the tile) and h (h_prev, loaded above)
             __syncwarp();
+            float4 cv[4];
+            uint4 hv[2];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) cv[it] = lds128f(ctile + (it * 8 + (lane >> 2)) * 80 + (lane & 3) * 16);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) hv[it] = lds128(htile + (it * 16 + (lane >> 1)) * 48 + (lane & 1) * 16);
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int r = it * 8 + (lane >> 2), seg = lane & 3;
-                if (row0 + r < j.m_rows)
-                    *reinterpret_cast<float4*>(j.c_state + (int64_t)(row0 + r) * j.hidden + unit0 + seg * 4) =
-                        *reinterpret_cast<const float4*>(ctile + r * 80 + seg * 16);
+                if (row0 + r < m_rows)
+                    *reinterpret_cast<float4*>(c_state + (int64_t)(row0 + r) * hidden + unit0 + seg * 4) = cv[it];
             }
-            __half* hout = reinterpret_cast<__half*>(j.out) + unit0;
+            __half* hout = reinterpret_cast<__half*>(out) + unit0;
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
                 const int r = it * 16 + (lane >> 1), seg = lane & 1;
-                if (row0 + r < j.m_rows)
-                    *reinterpret_cast<uint4*>(hout + (int64_t)(row0 + r) * j.out_stride + seg * 8) =
-                        *reinterpret_cast<const uint4*>(htile + r * 48 + seg * 16);
+                if (row0 + r < m_rows)
+                    *reinterpret_cast<uint4*>(hout + (int64_t)(row0 + r) * out_stride + seg * 8) = hv[it];
             }
             __syncwarp();
         }

@@ -52,8 +52,8 @@ constexpr int kControlBytes = 256;
 constexpr int kJobWords = (int)(sizeof(GemmJob) / 4);              // the epilogue keeps the current and the next job in shared memory
 static_assert(sizeof(GemmJob) % 8 == 0 && kJobWords <= kEpiThreads, "one word of a job per epilogue thread");
 static_assert(sizeof(Control) <= kControlBytes, "Control grew");
-constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*alignment slack*/ + kControlBytes + 2 * (int)sizeof(GemmJob);
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*alignment slack*/ + kControlBytes;      // dynamic
+static_assert(kSmemBytes + 2 * (int)sizeof(GemmJob) <= 227 * 1024, "shared memory budget (dynamic + the static job copies)");
 
 // What the single-thread roles need of a job.  They fetch the fields of the NEXT job while working on the current one:
 // every epilogue ends in a device-scope fence, which invalidates L1, so a field read on demand is an L2 round trip on
@@ -266,6 +266,45 @@ __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 columns at a time, issue and wait apart: the fp16 linear epilogue reads the next half chunk while it works on this one
+__device__ __forceinline__ void tmem_load_16cols_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// all loads issued so far have landed; the registers are passed through so that no use of them is scheduled before this point
+__device__ __forceinline__ void tmem_load_16cols_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+// Epilogue of a whole fp16 linear job for one warp: columns [c_begin, c_end) in chunks of 32, software-pipelined over
+// half chunks so that the TMEM read of the next 16 columns is in flight during the arithmetic of the current ones.
+__device__ __forceinline__ void linear_half_job(const LinearHalfView& lv, int row0, int lane, uint32_t taddr, int c_begin, int c_end,
+                                                float* stage, bool no_store) {
+    const uint32_t tile = smem_addr_of(stage);
+    uint32_t va[16], vb[16];
+    tmem_load_16cols_issue(taddr + (uint32_t)c_begin, va);
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        float bias[32];
+        linear_half_load_bias(lv, c0, bias);
+        tmem_load_16cols_wait(va);
+        tmem_load_16cols_issue(taddr + (uint32_t)(c0 + 16), vb);
+        linear_half_pack16(lv, lane, va, bias, tile, 0);
+        tmem_load_16cols_wait(vb);
+        if (c0 + 32 < c_end) tmem_load_16cols_issue(taddr + (uint32_t)(c0 + 32), va);
+        linear_half_pack16(lv, lane, vb, bias + 16, tile, 32);
+        __syncwarp();
+        linear_half_flush(lv, row0, lane, c0, tile, no_store);
+    }
+}
+
 template <class View>
 __device__ __forceinline__ int job_chunk_k(const View& j) { return j.in_half ? kChunkKHalf : kChunkK; }
 template <class View>
@@ -293,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes);
     Control* ctl = reinterpret_cast<Control*>(smem + kStages * kStageBytes + kEpiStageBytes);
-    GemmJob* job_s = reinterpret_cast<GemmJob*>(smem + kStages * kStageBytes + kEpiStageBytes + kControlBytes);     // [2]
+    __shared__ GemmJob job_s[2];        // static: the compiler then knows the address space (LDS, not generic loads)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -505,11 +544,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 const bool lstm_pre = lstm_half_paired(job) && !(debug_mode & 128);
                 float4 cpre[4];
                 if (lstm_pre && c_begin < c_end) lstm_half_load_c(job, row0, lane, c_begin, cpre);
+                // fp16 linear jobs: all fields the chunk loop needs, once per job
+                const LinearHalfView lv = linear_half_view(job, row0, lane);
+                float* my_stage = epi_stage + ew * kStageFloats;
                 if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 else mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 tcgen05_fence_after();
-                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                // (every chunk of an MLP-chain job qualifies; bits 4 / 32 / 1024 fall back to the chunk-at-a-time loop)
+                const bool whole_job_fast = c_begin < c_end && c_end <= lv.fast_cols && !(debug_mode & (4 | 32 | 1024));
+                if (whole_job_fast) linear_half_job(lv, row0, lane, taddr, c_begin, c_end, my_stage, (debug_mode & 16) != 0);
+                for (int c0 = whole_job_fast ? c_end : c_begin; c0 < c_end; c0 += 32) {
                     float v[32];
+                    if (c0 + 32 <= lv.fast_cols) {
+                        float bias[32];
+                        linear_half_load_bias(lv, c0, bias);              // in flight while the accumulator is read
+                        tmem_load_32cols(taddr + (uint32_t)c0, v);
+                        if (!(debug_mode & 4)) linear_half_chunk(lv, row0, lane, c0, v, bias, my_stage, (debug_mode & 16) != 0);
+                        continue;
+                    }
                     if (debug_mode & 32) {                 // measurement only: no TMEM read
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = 0.0f;
@@ -517,13 +569,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         tmem_load_32cols(taddr + (uint32_t)c0, v);
                     }
                     if (!(debug_mode & 4))
-                        epilogue_chunk(job, row0, lane, c0, v, epi_stage + ew * kStageFloats, (debug_mode & 16) != 0, lstm_pre ? cpre : nullptr);
+                        epilogue_chunk(job, row0, lane, c0, v, my_stage, (debug_mode & 16) != 0, lstm_pre ? cpre : nullptr);
                     // ... and the next pair's while this pair is being computed
                     if (lstm_pre && !(c0 & 32) && c0 + 64 < c_end) lstm_half_load_c(job, row0, lane, c0 + 64, cpre);
                 }
                 tcgen05_fence_before();
                 if (has_next) reinterpret_cast<uint32_t*>(&job_s[buf ^ 1u])[et] = next_word;
-                if (!(debug_mode & 8)) {
+                if (!(debug_mode & 8) && (job.is_dep || (debug_mode & 512))) {
+                    // Only a job that a later job of this item waits for publishes stores (its own and, by program order,
+                    // those of the jobs before it: every thread owns the same rows and column half in all jobs).
                     // The only in-kernel consumer of these stores is this CTA's own TMA (scratch activations of the next
                     // layer): order them before the barrier at CTA scope and hand them to the async proxy.  A device-scope
                     // fence here also invalidates L1 on every job, which turned every bias / sequence-length / job-field
@@ -605,7 +659,7 @@ int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_
     static int max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster modes unavailable or disabled)
     static int cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
     // EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
-    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring
+    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring, 512 fence after every job, 1024 no half-chunk pipelining of the fp16 linear epilogue
     static int debug_mode = 0;
     if (!configured) {
         EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

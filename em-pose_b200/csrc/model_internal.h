@@ -265,6 +265,9 @@ struct JobBook {        // jobs + tensor maps of one plan
             set_last_error("internal error: the jobs of a range must be added contiguously");
             return EMPOSE_E_ARG;
         }
+        // `dep` counts jobs from the start of the range; ranges that use it run as ONE item per row tile (per_item == count),
+        // so this is also the index inside the item.  The job it names must publish its stores to the TMA (gemm_tc.cu).
+        if (dep >= 0) jobs[(size_t)range->begin + dep].is_dep = 1;
         for (int t = 0; t < W.n_tiles; ++t) {
             GemmJob j = proto;
             j.a_ptr[0] = a0.ptr; j.a_stride[0] = a0.stride; j.a_k[0] = a0.k;
@@ -284,6 +287,7 @@ struct JobBook {        // jobs + tensor maps of one plan
             j.n_count = W.tile_n;
             j.m_rows = m_rows;
             j.dep = dep;
+            j.is_dep = 0;
             j.bias = W.bias;
             jobs.push_back(j);
             ++range->count;
