@@ -262,6 +262,7 @@ def run_b200(args, rank, local_rank, world):
         step_device()
     torch.cuda.synchronize(device)
     gemm_ms, gemm_launches = ctx.profile_read()
+    main_ms, main_launches = ctx.profile_read_main()
     ctx.set_profiling(False)
     peaks = measured_peaks()
     achieved = FLOP_PER_FRAME * frames_per_step * prof_steps / (gemm_ms / 1000.0) / 1e12
@@ -273,6 +274,12 @@ def run_b200(args, rank, local_rank, world):
                 'peak_source': peaks['source'] + ' bf16 dense, sustained',
                 'launches_per_step': gemm_launches / prof_steps, 'avg_launch_ms': gemm_ms / max(gemm_launches, 1),
                 'kernel_share_of_step': (gemm_ms / prof_steps) / (ms / args.steps),
+                # the other half of the step: the per-frame SMPL sub-model kernel (forward + hand-derived reverse pass), fp32
+                # SIMT arithmetic on ~3 KB of state per frame -- neither HBM- nor tensor-bound (ncu: issue slots 46 % busy,
+                # DRAM 0.2 TB/s), so it has no roofline line of its own; its share is reported so that the two add up
+                'other_kernels': {'main_kernel': {'share_of_step': (main_ms / prof_steps) / (ms / args.steps),
+                                                  'launches_per_step': main_launches / prof_steps,
+                                                  'avg_launch_ms': main_ms / max(main_launches, 1)}},
                 'algorithmic_flop_per_launch': FLOP_PER_FRAME * frames_per_step * prof_steps / max(gemm_launches, 1)}
 
     cpu = None

@@ -174,32 +174,14 @@ __device__ __forceinline__ void linear_half_flush(const LinearHalfView& lv, int 
     }
     __syncwarp();
 }
-// 16 accumulator columns of this lane's row -> bias, PReLU, fp16 -> 32 bytes of the staged row (byte offset `off`)
-__device__ __forceinline__ void linear_half_pack16(const LinearHalfView& lv, int lane, const uint32_t (&acc)[16], const float* bias,
-                                                   uint32_t tile, int off) {
-    const float alpha = lv.alpha;
-    const float keep = lv.zero_row ? 0.0f : 1.0f;       // (accumulators are finite: x * 1 + b rounds exactly like x + b)
-    uint32_t packed[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float y0 = fmaf(__uint_as_float(acc[2 * i]), keep, bias[2 * i]), y1 = fmaf(__uint_as_float(acc[2 * i + 1]), keep, bias[2 * i + 1]);
-        y0 = y0 > 0.0f ? y0 : alpha * y0;
-        y1 = y1 > 0.0f ? y1 : alpha * y1;
-        const __half2 h = __floats2half2_rn(y0, y1);
-        packed[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    sts128(tile + lane * 80 + off, packed[0], packed[1], packed[2], packed[3]);
-    sts128(tile + lane * 80 + off + 16, packed[4], packed[5], packed[6], packed[7]);
-}
 // A lane's 32 columns are 64 contiguous bytes of ITS row, so storing straight from registers makes every store
 // instruction touch 32 different lines with 16 bytes each (measured: 40 % of a 512x512 layer).  Instead the warp stages
 // its [32 rows][64 B] block in shared memory (80-byte pitch: conflict-free 16-byte accesses) and writes it out 8 rows
 // per instruction: 4 lanes x 16 B = two full sectors per row.
-__device__ __forceinline__ void linear_half_chunk(const LinearHalfView& lv, int row0, int lane, int c0, const float (&v)[32],
-                                                  const float (&bias)[32], float* __restrict__ stage, bool no_store) {
+// Step 1: bias, PReLU, fp16 -- 32 accumulator columns of this lane's row become 16 packed words
+__device__ __forceinline__ void linear_half_pack(const LinearHalfView& lv, const float (&v)[32], const float (&bias)[32], uint32_t (&packed)[16]) {
     const float alpha = lv.alpha;
     const bool zero = lv.zero_row;
-    uint32_t packed[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         float y0 = (zero ? 0.0f : v[2 * i]) + bias[2 * i], y1 = (zero ? 0.0f : v[2 * i + 1]) + bias[2 * i + 1];
@@ -208,11 +190,21 @@ __device__ __forceinline__ void linear_half_chunk(const LinearHalfView& lv, int 
         const __half2 h = __floats2half2_rn(y0, y1);
         packed[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
+}
+// Step 2: through the staging tile to global memory
+__device__ __forceinline__ void linear_half_store(const LinearHalfView& lv, int row0, int lane, int c0, const uint32_t (&packed)[16],
+                                                  float* __restrict__ stage, bool no_store) {
     const uint32_t tile = smem_addr_of(stage);
 #pragma unroll
     for (int q = 0; q < 4; ++q) sts128(tile + lane * 80 + q * 16, packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
     __syncwarp();
     linear_half_flush(lv, row0, lane, c0, tile, no_store);
+}
+__device__ __forceinline__ void linear_half_chunk(const LinearHalfView& lv, int row0, int lane, int c0, const float (&v)[32],
+                                                  const float (&bias)[32], float* __restrict__ stage, bool no_store) {
+    uint32_t packed[16];
+    linear_half_pack(lv, v, bias, packed);
+    linear_half_store(lv, row0, lane, c0, packed, stage, no_store);
 }
 
 // Cell-state block of one chunk pair [c0, c0 + 64) of an fp16 LSTM job -> registers, in the lane mapping the tile fill of

@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kStages = 4;                   // ring slots of A [128 x 128 B] + W [256 x 128 B] (48 KB)
 constexpr int kStagesPair = 6;               // CTA-pair mode: a slot holds half of W (32 KB), so the same memory is a deeper ring
-constexpr int kDefaultClusterMode = 0;      // EMPOSE_TC_CLUSTER when the variable is not set
+constexpr int kDefaultClusterMode = 2;      // EMPOSE_TC_CLUSTER when the variable is not set: CTA pairs (cta_group::2)
 constexpr int kABytes = kTileM * kChunkK * 4;        // 16 KB
 constexpr int kWBytes = kMaxTileN * kChunkK * 4;     // 32 KB
 constexpr int kStageBytes = kABytes + kWBytes;
@@ -264,45 +264,6 @@ __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, float (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 16 columns at a time, issue and wait apart: the fp16 linear epilogue reads the next half chunk while it works on this one
-__device__ __forceinline__ void tmem_load_16cols_issue(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-// all loads issued so far have landed; the registers are passed through so that no use of them is scheduled before this point
-__device__ __forceinline__ void tmem_load_16cols_wait(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
-
-// Epilogue of a whole fp16 linear job for one warp: columns [c_begin, c_end) in chunks of 32, software-pipelined over
-// half chunks so that the TMEM read of the next 16 columns is in flight during the arithmetic of the current ones.
-__device__ __forceinline__ void linear_half_job(const LinearHalfView& lv, int row0, int lane, uint32_t taddr, int c_begin, int c_end,
-                                                float* stage, bool no_store) {
-    const uint32_t tile = smem_addr_of(stage);
-    uint32_t va[16], vb[16];
-    tmem_load_16cols_issue(taddr + (uint32_t)c_begin, va);
-    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        float bias[32];
-        linear_half_load_bias(lv, c0, bias);
-        tmem_load_16cols_wait(va);
-        tmem_load_16cols_issue(taddr + (uint32_t)(c0 + 16), vb);
-        linear_half_pack16(lv, lane, va, bias, tile, 0);
-        tmem_load_16cols_wait(vb);
-        if (c0 + 32 < c_end) tmem_load_16cols_issue(taddr + (uint32_t)(c0 + 32), va);
-        linear_half_pack16(lv, lane, vb, bias + 16, tile, 32);
-        __syncwarp();
-        linear_half_flush(lv, row0, lane, c0, tile, no_store);
-    }
 }
 
 template <class View>
@@ -550,10 +511,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 else mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 tcgen05_fence_after();
-                // (every chunk of an MLP-chain job qualifies; bits 4 / 32 / 1024 fall back to the chunk-at-a-time loop)
-                const bool whole_job_fast = c_begin < c_end && c_end <= lv.fast_cols && !(debug_mode & (4 | 32 | 1024));
-                if (whole_job_fast) linear_half_job(lv, row0, lane, taddr, c_begin, c_end, my_stage, (debug_mode & 16) != 0);
-                for (int c0 = whole_job_fast ? c_end : c_begin; c0 < c_end; c0 += 32) {
+                // (tried and dropped: software-pipelining the accumulator reads -- 16 columns at a time, or the next chunk's read
+                //  issued before the current chunk is staged.  With the read's registers live across the loop ptxas feeds the
+                //  eight bias loads one by one into the additions: 11 % slower on a [131072 x 512] . [512 x 512] layer.)
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     float v[32];
                     if (c0 + 32 <= lv.fast_cols) {
                         float bias[32];
@@ -659,7 +620,7 @@ int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_
     static int max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster modes unavailable or disabled)
     static int cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
     // EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
-    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring, 512 fence after every job, 1024 no half-chunk pipelining of the fp16 linear epilogue
+    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring, 512 fence after every job
     static int debug_mode = 0;
     if (!configured) {
         EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

@@ -460,7 +460,20 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
             if (!tick_buf) cudaMalloc(&tick_buf, 32 * sizeof(long long));
             mp.ticks = tick_buf;
         }
-        EMPOSE_TRY(count(launch_main(mp, s)));
+        if (ctx->profiling) {
+            if (ctx->prof_main_used == ctx->prof_main_events.size()) {
+                cudaEvent_t a, b;
+                EMPOSE_CUDA_TRY(cudaEventCreate(&a));
+                EMPOSE_CUDA_TRY(cudaEventCreate(&b));
+                ctx->prof_main_events.emplace_back(a, b);
+            }
+            auto& ev = ctx->prof_main_events[ctx->prof_main_used++];
+            EMPOSE_CUDA_TRY(cudaEventRecord(ev.first, s));
+            EMPOSE_TRY(count(launch_main(mp, s)));
+            EMPOSE_CUDA_TRY(cudaEventRecord(ev.second, s));
+        } else {
+            EMPOSE_TRY(count(launch_main(mp, s)));
+        }
         if (want_ticks && it == 0) {
             long long h[32];
             cudaMemcpy(h, tick_buf, sizeof(h), cudaMemcpyDeviceToHost);
@@ -571,6 +584,23 @@ int empose_ief_set_profiling(empose_ief* ctx, int32_t enable) {
     if (!ctx) { set_last_error("null context"); return EMPOSE_E_ARG; }
     ctx->profiling = enable != 0;
     ctx->prof_used = 0;
+    ctx->prof_main_used = 0;
+    return EMPOSE_OK;
+}
+
+int empose_ief_profile_read_main(empose_ief* ctx, double* main_ms, int64_t* main_launches) {
+    if (!ctx || !main_ms || !main_launches) { set_last_error("null argument"); return EMPOSE_E_ARG; }
+    EMPOSE_CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    double total = 0.0;
+    for (size_t i = 0; i < ctx->prof_main_used; ++i) {
+        EMPOSE_CUDA_TRY(cudaEventSynchronize(ctx->prof_main_events[i].second));
+        float ms = 0.0f;
+        EMPOSE_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->prof_main_events[i].first, ctx->prof_main_events[i].second));
+        total += ms;
+    }
+    *main_ms = total;
+    *main_launches = (int64_t)ctx->prof_main_used;
+    ctx->prof_main_used = 0;
     return EMPOSE_OK;
 }
 

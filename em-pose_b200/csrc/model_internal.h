@@ -375,11 +375,14 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_main_events;    // same for the per-frame sub-model kernel
+    size_t prof_main_used = 0;
     // copy streams and events of the pipelined host-buffer entry point (empose_ief_forward_host)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> pipe_events;
     ~IefData() {
         for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto& e : prof_main_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto& e : pipe_events) cudaEventDestroy(e);
         if (copy_in) cudaStreamDestroy(copy_in);
         if (copy_out) cudaStreamDestroy(copy_out);

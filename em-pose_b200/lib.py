@@ -21,7 +21,7 @@ _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2
 #: every symbol include/empose_b200.h declares (checked by tests/test_cabi.py)
 EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_create', 'empose_ief_destroy',
                     'empose_ief_forward', 'empose_ief_forward_host', 'empose_sensor_project',
-                    'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read',
+                    'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read', 'empose_ief_profile_read_main',
                     'empose_gemm_selftest', 'empose_gemm_bench', 'empose_smpl_create', 'empose_smpl_destroy',
                     'empose_smpl_forward', 'empose_train_layout', 'empose_train_sizes', 'empose_train_create',
                     'empose_train_destroy', 'empose_train_forward', 'empose_train_backward',
@@ -94,6 +94,8 @@ def load():
     lib.empose_ief_set_profiling.argtypes = [vp, i32]
     lib.empose_ief_profile_read.restype = ctypes.c_int
     lib.empose_ief_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
+    lib.empose_ief_profile_read_main.restype = ctypes.c_int
+    lib.empose_ief_profile_read_main.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     lib.empose_gemm_selftest.restype = ctypes.c_int
     lib.empose_gemm_selftest.argtypes = [i32, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, i32, i32,
                                          i32, vp]
@@ -217,6 +219,12 @@ class IefContext(object):
         """(summed device ms of the GEMM executor launches, number of launches) since the last read."""
         ms, n = ctypes.c_double(), ctypes.c_int64()
         _check(load().empose_ief_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def profile_read_main(self):
+        """The same for the per-frame sub-model kernel (main_kernel)."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        _check(load().empose_ief_profile_read_main(self._handle, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
     def forward(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None, lstm_state=None,

@@ -265,11 +265,13 @@ int empose_rnn_forward(empose_rnn* ctx, const float* marker_pos, const float* ma
                        float* joints_hat, void* stream);
 int64_t empose_rnn_last_launch_count(const empose_rnn* ctx);
 
-/* Optional timing of the tensor-core GEMM executor: while enabled, every executor launch is bracketed by
- * CUDA events on its stream (TF32 mode only).  empose_ief_profile_read waits for them, returns the summed
- * device time and the number of launches since the last read / enable, and resets the counters. */
+/* Optional timing of the two kernels that make up the step: while enabled, every launch of the tensor-core GEMM
+ * executor and of the per-frame sub-model kernel is bracketed by CUDA events on its stream (tensor-core modes only).
+ * empose_ief_profile_read / _read_main wait for them, return the summed device time and the number of launches
+ * since the last read / enable, and reset their counters. */
 int empose_ief_set_profiling(empose_ief* ctx, int32_t enable);
 int empose_ief_profile_read(empose_ief* ctx, double* gemm_ms, int64_t* gemm_launches);
+int empose_ief_profile_read_main(empose_ief* ctx, double* main_ms, int64_t* main_launches);
 
 /* Engine self-test: C[M][N] = A[M][K] . W[N][K]^T + bias through the same job executor the model uses
  * (precision selects tcgen05 or FFMA).  Device pointers; lda / ldw / ldc in floats. */
