@@ -35,9 +35,9 @@ FLOP_PER_FRAME = 26472448          # 2 x MACs of the learn
 BYTES_PER_FRAME = 1162             # algorithmic HBM bytes per frame
 METRIC = 'frames/sec LGD-RNN-12 N=4 ws=32'
 # dram__bytes_read.sum + dram__bytes_write.sum of gemm_tc_kernel from the committed ncu --set full captures
-# (profiles/r01/ncu_summary_v10.txt, fp16 operand mode): launch-weighted mean over the 47 launches of a step.
-NCU_TRAFFIC_BYTES = (4 * 1.066e9 + 33 * 0.0342e9 + 10 * 0.30e9) / 47
-NCU_TRAFFIC_NOTE = ('mean per launch at 4096 windows: MLP-chain launch 1.07 GB (0.11 read + 0.96 written: the CTA-local fp16 activation '
+# (profiles/r01/ncu_summary_v11.txt, fp16 operand mode): launch-weighted mean over the 47 launches of a step.
+NCU_TRAFFIC_BYTES = (4 * 1.083e9 + 33 * 0.0344e9 + 10 * 0.30e9) / 47
+NCU_TRAFFIC_NOTE = ('mean per launch at 4096 windows: MLP-chain launch 1.08 GB (0.11 read + 0.97 written: the CTA-local fp16 activation '
                     'scratch is still written back) and LSTM launch 0.034 GB measured, the ten pose-blend / heads launches estimated at '
                     '0.3 GB; algorithmic bytes per launch ~3 MB')
 

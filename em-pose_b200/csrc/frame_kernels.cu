@@ -168,6 +168,56 @@ static_assert(kMainThreads % 32 == 0, "whole warps");
 // optional phase timing (development aid): thread 0 of one mid-grid CTA stores clock64() after every barrier
 #define EMPOSE_TICK(k) do { if (p.ticks && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) p.ticks[k] = clock64(); } while (0)
 
+// The two shape-blend phases, CTA-wide and with 16-byte accesses (same arithmetic as item_blend_verts /
+// item_shape_bwd_partial of frame_math.h, which the host harness checks; vp_dim is a multiple of 16 and the padding of
+// v_template / shapedirs / vp_off is zero, submodel.py:173-176).
+// Forward: thread t owns coordinates [2t, 2t + 2) of EVERY frame of the CTA, so a blend-shape row is read once per CTA
+// instead of once per frame.
+template <int VP>
+__device__ __forceinline__ void cta_blend_verts(const SubModel& m, FrameState<float, VP>* st, const float* vp_off, int64_t row0, int nf) {
+    const int t = threadIdx.x;
+    if (t * 2 >= m.vp_dim) return;
+    const float2 vt = __ldg(reinterpret_cast<const float2*>(m.v_template) + t);
+    float2 S[kBetas];                    // (two coordinates per thread: ten float4 rows would not fit the 64-register budget)
+#pragma unroll
+    for (int k = 0; k < kBetas; ++k) S[k] = __ldg(reinterpret_cast<const float2*>(m.shapedirs + (size_t)k * m.vp_dim) + t);
+    for (int f = 0; f < nf; ++f) {
+        float2 acc = vt;
+        const float4* b4 = reinterpret_cast<const float4*>(st[f].beta);
+        const float4 b0 = b4[0], b1 = b4[1];
+        const float2 b2 = *reinterpret_cast<const float2*>(st[f].beta + 8);
+        const float beta[kBetas] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+#pragma unroll
+        for (int k = 0; k < kBetas; ++k) { acc.x = fmaf(S[k].x, beta[k], acc.x); acc.y = fmaf(S[k].y, beta[k], acc.y); }
+        if (vp_off) {
+            const float2 o = *(reinterpret_cast<const float2*>(vp_off + (row0 + f) * m.vp_dim) + t);
+            acc.x += o.x; acc.y += o.y;
+        }
+        reinterpret_cast<float2*>(st[f].vp)[t] = acc;
+    }
+}
+// Reverse: item (frame, k, part) sums a contiguous third of the coordinates, four at a time.
+template <int VP>
+__device__ __forceinline__ void cta_shape_bwd_partial(const SubModel& m, FrameState<float, VP>* st, int nf) {
+    const int nv3 = m.n_verts * 3;
+    const int q = nv3 / 4;               // whole float4s; dx beyond 3 n_verts is never written, so it must not be read
+    for (int idx = threadIdx.x; idx < nf * 3 * kBetas; idx += kMainThreads) {
+        const int f = idx / (3 * kBetas), it = idx - f * 3 * kBetas;
+        const int k = it % kBetas, part = it / kBetas;
+        const float4* S = reinterpret_cast<const float4*>(m.shapedirs + (size_t)k * m.vp_dim);
+        const float4* dx = reinterpret_cast<const float4*>(st[f].dx);
+        float a0 = 0.0f, a1 = 0.0f;
+        const int lo = part * q / 3, hi = (part + 1) * q / 3;
+        for (int i = lo; i < hi; ++i) {
+            const float4 s = __ldg(S + i), d = dx[i];
+            a0 = fmaf(s.x, d.x, a0); a1 = fmaf(s.y, d.y, a1); a0 = fmaf(s.z, d.z, a0); a1 = fmaf(s.w, d.w, a1);
+        }
+        if (part == 2)
+            for (int i = q * 4; i < nv3; ++i) a0 = fmaf(__ldg(m.shapedirs + (size_t)k * m.vp_dim + i), st[f].dx[i], a0);
+        st[f].dbeta_part[part][k] = a0 + a1;
+    }
+}
+
 template <int VP, int kFramesPerCta, int kMainCtasPerSm>
 __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(MainParams p) {
     constexpr int kGroup = kMainThreads / kFramesPerCta;     // threads per frame in the frame-grouped mapping
@@ -197,7 +247,8 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
         if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_static(st[f], i); }
         else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain(m, st[f], i); }
     }
-    EMPOSE_FOR_FRAME_ITEMS(nv3, f, i) item_blend_verts(m, st[f], p.vp_off + (row0 + f) * m.vp_dim, i);
+    if (p.legacy_blend) { EMPOSE_FOR_FRAME_ITEMS(nv3, f, i) item_blend_verts(m, st[f], p.vp_off + (row0 + f) * m.vp_dim, i); }
+    else cta_blend_verts(m, st, p.vp_off, row0, nf);
     __syncthreads();
     EMPOSE_TICK(3);
     EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_skin(m, st[f], i);
@@ -254,7 +305,8 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     }
     EMPOSE_FOR_FRAME_ITEMS(m.vp_dim, f, i)
         p.dvp[(row0 + f) * m.vp_dim + i] = i < nv3 ? maybe_round(st[f].dx[i], p.round_out) : 0.0f;
-    EMPOSE_FOR_ITEMS(3 * kBetas, f, i) item_shape_bwd_partial(m, st[f], i);
+    if (p.legacy_blend) { EMPOSE_FOR_ITEMS(3 * kBetas, f, i) item_shape_bwd_partial(m, st[f], i); }
+    else cta_shape_bwd_partial(m, st, nf);
     __syncthreads();
     EMPOSE_TICK(11);
     EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_chain_bwd_local(m, st[f], i, joint_up);
@@ -356,7 +408,11 @@ int launch_main_variant(const MainParams& p, cudaStream_t s) {
     return EMPOSE_OK;
 }
 
-int launch_main(const MainParams& p, cudaStream_t s) {
+int launch_main(const MainParams& p_in, cudaStream_t s) {
+    static int legacy_blend = -1;
+    if (legacy_blend < 0) legacy_blend = getenv("EMPOSE_MAIN_LEGACY_BLEND") ? 1 : 0;
+    MainParams p = p_in;
+    p.legacy_blend = legacy_blend;
     // (frames per CTA, CTAs per SM) for the common sub-mesh size.  Measured on the B200 at 4096 windows x 32 frames
     // (whole step, profiles/r01/README.md): (4,4) 17.25 ms, (5,4) 16.68 ms, (6,3) 16.82 ms, (7,3) 17.29 ms, (8,2) 18.56 ms:
     // 20 frames in flight per SM is the sweet spot between latency hiding and threads per frame.

@@ -68,6 +68,8 @@ struct MainParams {
     int want_grad;
     int round_out;
     int static_tree;            // 1: sub.parents is the standard SMPL body tree -> register-resident chain phases
+    int legacy_blend;           // 1: per-item shape-blend phases of frame_math.h instead of the CTA-wide vector ones (set by launch_main
+                                // from EMPOSE_MAIN_LEGACY_BLEND; A/B measurements)
     long long* ticks;           // development aid: per-phase clock64() samples of one CTA, or null
     float* sensor_pos;          // [R][36] or null
     float* sensor_ori;          // [R][108] or null

@@ -75,14 +75,15 @@ struct ResidualSpec {
 };
 
 template <typename T, int VP = kMaxVp>
-struct FrameState {
+struct alignas(16) FrameState {
+    // (the two vertex-sized vectors and beta come first so that the CUDA kernel can use 16-byte accesses on them)
+    T vp[VP];                 // v_template + S beta + pose blend
+    T dx[VP];                 // dE/dx, then reused for dE/dvp
+    T beta[kBetas + 2];       // (two unused slots keep what follows 8-byte aligned for T = float)
     T theta[kPoseDim];
-    T beta[kBetas];
     T rot[kJoints][9];        // R_j = exp(theta_j)
     T jrest[kJoints][3];      // J(beta)
     T grot[kJoints][9];       // world rotation G_j^R  (== A_j^R)
-    T vp[VP];                 // v_template + S beta + pose blend
-    T dx[VP];                 // dE/dx, then reused for dE/dvp
     union {
         struct {
             T dar[kJoints][9];    // dE/dA^R
