@@ -218,6 +218,60 @@ __device__ __forceinline__ void cta_shape_bwd_partial(const SubModel& m, FrameSt
     }
 }
 
+// More phases in the "one thread owns an item of EVERY frame of the CTA" form: the model constants (index ranges, blend
+// rows) are read once per CTA instead of once per frame.  The kernel is bound by the L1 / shared-memory pipe (ncu: 78 %
+// busy), so what counts is the number of load instructions, not the arithmetic.
+// rest joints J(beta) (item_rest_joints): thread i < 66
+template <int VP>
+__device__ __forceinline__ void cta_rest_joints(const SubModel& m, FrameState<float, VP>* st, int nf) {
+    const int i = threadIdx.x;
+    if (i >= kPoseDim) return;
+    const float j0 = __ldg(m.j0 + i);
+    float jd[kBetas];
+#pragma unroll
+    for (int k = 0; k < kBetas; ++k) jd[k] = __ldg(m.jdirs + k * kPoseDim + i);
+    for (int f = 0; f < nf; ++f) {
+        const float4* b4 = reinterpret_cast<const float4*>(st[f].beta);
+        const float4 b0 = b4[0], b1 = b4[1];
+        const float2 b2 = *reinterpret_cast<const float2*>(st[f].beta + 8);
+        const float beta[kBetas] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+        float acc = j0;
+#pragma unroll
+        for (int k = 0; k < kBetas; ++k) acc = fmaf(jd[k], beta[k], acc);
+        st[f].jrest[i / 3][i % 3] = acc;
+    }
+}
+// dE/dA_j = sum of its chunks (item_skin_bwd_reduce): thread (j, e), 22 x 12 items
+template <int VP>
+__device__ __forceinline__ void cta_skin_bwd_reduce(const SubModel& m, FrameState<float, VP>* st, int nf) {
+    for (int it = threadIdx.x; it < kJoints * 12; it += kMainThreads) {
+        const int j = it / 12, e = it - j * 12;
+        const int c0 = __ldg(m.jvj_ptr + j), c1 = __ldg(m.jvj_ptr + j + 1);
+        for (int f = 0; f < nf; ++f) {
+            float acc = 0.0f;
+            for (int c = c0; c < c1; ++c) acc += st[f].dav[c][e];
+            if (e < 9) st[f].dar[j][e] = acc;
+            else st[f].dat[j][e - 9] = acc;
+        }
+    }
+}
+// dE/dvp rows -> global memory, 16 bytes at a time (columns beyond 3 n_verts are zero: they are K padding of the
+// transposed pose-blend GEMM)
+template <int VP>
+__device__ __forceinline__ void cta_store_dvp(const SubModel& m, FrameState<float, VP>* st, float* dvp, int64_t row0, int nf, int round_out) {
+    const int q = m.vp_dim / 4, nv3 = m.n_verts * 3;
+    for (int idx = threadIdx.x; idx < nf * q; idx += kMainThreads) {
+        const int f = idx / q, t = idx - f * q;
+        float4 v = reinterpret_cast<const float4*>(st[f].dx)[t];
+        const int i = t * 4;
+        v.x = i < nv3 ? maybe_round(v.x, round_out) : 0.0f;
+        v.y = i + 1 < nv3 ? maybe_round(v.y, round_out) : 0.0f;
+        v.z = i + 2 < nv3 ? maybe_round(v.z, round_out) : 0.0f;
+        v.w = i + 3 < nv3 ? maybe_round(v.w, round_out) : 0.0f;
+        reinterpret_cast<float4*>(dvp + (row0 + f) * m.vp_dim)[t] = v;
+    }
+}
+
 template <int VP, int kFramesPerCta, int kMainCtasPerSm>
 __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(MainParams p) {
     constexpr int kGroup = kMainThreads / kFramesPerCta;     // threads per frame in the frame-grouped mapping
@@ -238,7 +292,8 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     __syncthreads();
     EMPOSE_TICK(1);
     EMPOSE_FOR_ITEMS(kJoints, f, i) item_rodrigues(st[f], i);
-    EMPOSE_FOR_FRAME_ITEMS(kPoseDim, f, i) item_rest_joints(m, st[f], i);
+    if (p.legacy_blend) { EMPOSE_FOR_FRAME_ITEMS(kPoseDim, f, i) item_rest_joints(m, st[f], i); }
+    else cta_rest_joints(m, st, nf);
     __syncthreads();
     EMPOSE_TICK(2);
     // The serial kinematic chain runs on the last warp first; all threads (that warp joining late) then do the
@@ -295,7 +350,8 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     EMPOSE_FOR_FRAME_ITEMS(m.n_vj, f, i) item_skin_bwd_chunks(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(9);
-    EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_skin_bwd_reduce(m, st[f], i);
+    if (p.legacy_blend) { EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_skin_bwd_reduce(m, st[f], i); }
+    else cta_skin_bwd_reduce(m, st, nf);
     EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_skin_bwd_verts(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(10);
@@ -303,8 +359,12 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
         if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd_static(st[f], i, joint_up); }
         else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd(m, st[f], i, joint_up); }
     }
-    EMPOSE_FOR_FRAME_ITEMS(m.vp_dim, f, i)
-        p.dvp[(row0 + f) * m.vp_dim + i] = i < nv3 ? maybe_round(st[f].dx[i], p.round_out) : 0.0f;
+    if (p.legacy_blend) {
+        EMPOSE_FOR_FRAME_ITEMS(m.vp_dim, f, i)
+            p.dvp[(row0 + f) * m.vp_dim + i] = i < nv3 ? maybe_round(st[f].dx[i], p.round_out) : 0.0f;
+    } else {
+        cta_store_dvp(m, st, p.dvp, row0, nf, p.round_out);
+    }
     if (p.legacy_blend) { EMPOSE_FOR_ITEMS(3 * kBetas, f, i) item_shape_bwd_partial(m, st[f], i); }
     else cta_shape_bwd_partial(m, st, nf);
     __syncthreads();
