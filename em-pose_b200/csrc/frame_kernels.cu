@@ -208,6 +208,7 @@ __device__ __forceinline__ void cta_shape_bwd_partial(const SubModel& m, FrameSt
         const float4* dx = reinterpret_cast<const float4*>(st[f].dx);
         float a0 = 0.0f, a1 = 0.0f;
         const int lo = part * q / 3, hi = (part + 1) * q / 3;
+#pragma unroll 4
         for (int i = lo; i < hi; ++i) {
             const float4 s = __ldg(S + i), d = dx[i];
             a0 = fmaf(s.x, d.x, a0); a1 = fmaf(s.y, d.y, a1); a0 = fmaf(s.z, d.z, a0); a1 = fmaf(s.w, d.w, a1);
@@ -247,11 +248,13 @@ __device__ __forceinline__ void cta_skin_bwd_reduce(const SubModel& m, FrameStat
     for (int it = threadIdx.x; it < kJoints * 12; it += kMainThreads) {
         const int j = it / 12, e = it - j * 12;
         const int c0 = __ldg(m.jvj_ptr + j), c1 = __ldg(m.jvj_ptr + j + 1);
-        for (int f = 0; f < nf; ++f) {
+        constexpr int kFrameFloats = (int)(sizeof(FrameState<float, VP>) / sizeof(float));
+        const float* src = &st[0].dav[c0][e];
+        float* dst = e < 9 ? &st[0].dar[j][e] : &st[0].dat[j][e - 9];
+        for (int f = 0; f < nf; ++f, src += kFrameFloats, dst += kFrameFloats) {
             float acc = 0.0f;
-            for (int c = c0; c < c1; ++c) acc += st[f].dav[c][e];
-            if (e < 9) st[f].dar[j][e] = acc;
-            else st[f].dat[j][e - 9] = acc;
+            for (int c = 0; c < c1 - c0; ++c) acc += src[c * 12];
+            *dst = acc;
         }
     }
 }
@@ -285,9 +288,17 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     const bool static_tree = p.static_tree != 0;
     EMPOSE_TICK(0);
 
-    EMPOSE_FOR_FRAME_ITEMS(kPoseDim + kBetas, f, i) {
-        if (i < kPoseDim) st[f].theta[i] = p.theta[(row0 + f) * kPoseDim + i];
-        else st[f].beta[i - kPoseDim] = p.beta[(row0 + f) * kBetas + (i - kPoseDim)];
+    if (p.legacy_blend) {
+        EMPOSE_FOR_FRAME_ITEMS(kPoseDim + kBetas, f, i) {
+            if (i < kPoseDim) st[f].theta[i] = p.theta[(row0 + f) * kPoseDim + i];
+            else st[f].beta[i - kPoseDim] = p.beta[(row0 + f) * kBetas + (i - kPoseDim)];
+        }
+    } else {
+        // the rows of the CTA's frames are contiguous in global memory: one flat, coalesced copy each
+        const float* th = p.theta + row0 * kPoseDim;
+        for (int idx = threadIdx.x; idx < nf * kPoseDim; idx += kMainThreads) { const int f = idx / kPoseDim; st[f].theta[idx - f * kPoseDim] = th[idx]; }
+        const float* be = p.beta + row0 * kBetas;
+        for (int idx = threadIdx.x; idx < nf * kBetas; idx += kMainThreads) { const int f = idx / kBetas; st[f].beta[idx - f * kBetas] = be[idx]; }
     }
     __syncthreads();
     EMPOSE_TICK(1);
