@@ -485,13 +485,14 @@ int launch_main(const MainParams& p_in, cudaStream_t s) {
     MainParams p = p_in;
     p.legacy_blend = legacy_blend;
     // (frames per CTA, CTAs per SM) for the common sub-mesh size.  Measured on the B200 at 4096 windows x 32 frames
-    // (whole step, profiles/r01/README.md): (4,4) 17.25 ms, (5,4) 16.68 ms, (6,3) 16.82 ms, (7,3) 17.29 ms, (8,2) 18.56 ms:
-    // 20 frames in flight per SM is the sweet spot between latency hiding and threads per frame.
-    // EMPOSE_MAIN_VARIANT=0/2/3/4 selects the others (experiments).
+    // (whole step, profiles/r01/README.md): (4,4) 13.70 ms, (5,4) 13.18 ms, (6,3) 13.39 ms, (7,3) 13.85 ms, (6,4) 12.86 ms:
+    // the more frames in flight per SM the better the latency of the narrow phases (kinematic chains, 12 sensor frames)
+    // hides; 24 is what fits (4 x (6 x 9536 B + 1 KB) of the 228 KB, which is why `jup` shares storage with `fg`).
+    // EMPOSE_MAIN_VARIANT=0..4 selects the others (experiments).
     static int variant = -1;
     if (variant < 0) {
         const char* e = getenv("EMPOSE_MAIN_VARIANT");
-        variant = e ? atoi(e) : 1;
+        variant = e ? atoi(e) : 5;
     }
     if (p.sub.vp_dim <= 256) {
         switch (variant) {
@@ -499,7 +500,8 @@ int launch_main(const MainParams& p_in, cudaStream_t s) {
             case 2: return launch_main_variant<256, 6, 3>(p, s);
             case 3: return launch_main_variant<256, 7, 3>(p, s);
             case 4: return launch_main_variant<256, 8, 2>(p, s);
-            default: return launch_main_variant<256, 5, 4>(p, s);
+            case 1: return launch_main_variant<256, 5, 4>(p, s);
+            default: return launch_main_variant<256, 6, 4>(p, s);
         }
     }
     if (p.sub.vp_dim <= kMaxVp) return launch_main_variant<kMaxVp, 4, 3>(p, s);

@@ -92,8 +92,11 @@ struct alignas(16) FrameState {
         T fn[kSensors][kSplitDegree][3];   // split sensor phases: un-normalised face normals, then (slot 0) dE/dn
     };
     T dbeta_part[3][kBetas];
-    T jup[kJoints][3];        // upstream dE/d(posed joint) of the FK loss (training, models.py:657-660); else unused
-    T fg[kSensors * kSplitDegree][6];   // split sensor phases: dE/d(edge1), dE/d(edge2) of every (sensor, face) item
+    union {
+        T fg[kSensors * kSplitDegree][6];   // split sensor phases: dE/d(edge1), dE/d(edge2) of every (sensor, face) item
+        T jup[kJoints][3];    // upstream dE/d(posed joint) of the FK loss (training, models.py:657-660); written by
+                              // item_joint_residual, i.e. after item_sensor_gather has consumed `fg`
+    };
     // Forward-only scratch and reverse-only scratch share storage: everything in `fwd` is dead once the sensor
     // outputs and joints have been written out, which is before the first member of `bwd` is written.
     union {
