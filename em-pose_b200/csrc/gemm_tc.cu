@@ -2,18 +2,22 @@
 //
 // One persistent, warp-specialised kernel executes lists of GemmJob (gemm_jobs.h) on 128-row tiles:
 //
-//   warp 0   TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of A [128 x 32] and W [n x 32] fp32 chunks
-//                           into a 4-stage shared-memory ring, completion on mbarriers
-//   warp 1   MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256, K=8),
-//                           accumulating in TMEM; tcgen05.commit releases ring slots and publishes accumulators
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of A [128 x 128 B] and W [n x 128 B] K chunks (32 fp32 /
+//                           tf32 or 64 fp16 elements) into a shared-memory ring (4 slots of 48 KB, or 6 of 32 KB in CTA-pair
+//                           mode), completion on mbarriers
+//   warp 1   MMA issuer     tcgen05.mma kind::f16 / kind::tf32 (M=128 per CTA, N<=256, 32 bytes of K per instruction),
+//                           accumulating in TMEM; tcgen05.commit releases ring slots and publishes accumulators.  In the
+//                           default mode pairs of CTAs form ONE cta_group::2 MMA (M=256), issued by CTA 0 of the pair.
+//                           Both roles run their loops on the whole warp with uniform values; an elect.sync lane issues.
 //   warp 2   TMEM allocator 512 columns = two 128x256 fp32 accumulators (double buffered across jobs)
-//   warps 4-11 epilogue     tcgen05.ld 32 columns at a time -> epilogue_chunk() -> global memory
-//                           (two warps per TMEM lane quadrant, each taking 128 of the 256 columns)
+//   warps 4-11 epilogue     tcgen05.ld 32 columns at a time -> epilogue_chunk() / linear_half_chunk() -> global memory
+//                           (two warps per TMEM lane quadrant, each taking 128 of the 256 columns); works on a
+//                           shared-memory copy of the job record, fetched one job ahead
 //
 // A work item is (row tile, group of consecutive jobs).  Jobs of one item run back to back in the
 // same CTA; a job may depend on an earlier job of its item (an MLP layer reading the previous layer's
-// activations): the producer then waits for that job's epilogue, whose global stores are made visible
-// to the TMA (async proxy) with fence.proxy.async before it is counted as done.  Independent jobs in
+// activations): the producer then waits for that job's epilogue, whose global stores are ordered at CTA
+// scope and handed to the TMA (async proxy) with fence.proxy.async before it is counted as done.  Independent jobs in
 // between (the pose and shape MLPs are interleaved layer by layer) keep the tensor pipe busy meanwhile.
 #include <cuda.h>
 #include <cuda_runtime.h>
