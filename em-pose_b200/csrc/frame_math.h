@@ -34,8 +34,17 @@ constexpr int kPoseDim = 66;
 constexpr int kBetas = 10;            // reference configuration.py:107
 constexpr int kSensors = 12;          // reference configuration.py:32-34
 constexpr int kPoseFeat = 189;        // 21 joints x 9 rotation entries
-constexpr int kPoseFeatPad = 192;     // K of the pose-blend GEMM (multiple of 32 floats = one 128B swizzle row)
-constexpr int kMaxVp = 384;           // padded 3*Vs, supports sub-meshes of up to 128 vertices
+// Feature row of the blend GEMM: [vec(R_1..R_21 - I) (189) | 0 0 0 | beta (10) | 0 ...], so that ONE contraction gives
+// S beta + P pf (the blended rest vertices minus the template, reference smpl.py:121 steps 1 and 4) and, in 66 extra
+// output columns, Jdirs beta; v_template and J0 are the bias of that GEMM, i.e. they are added ONCE, in fp32, after
+// the accumulation (metre-sized constants inside a tensor-core accumulator would cost the millimetre-sized terms
+// their low bits).  Padded to a multiple of 32 floats = one 128B swizzle row.
+constexpr int kFeatBeta = 192;        // first shape column of the feature row
+constexpr int kFeatK = 202;           // real K of the blend GEMM
+constexpr int kPoseFeatPad = 224;     // padded K
+// The transposed contraction returns [dE/dpf (189) | 0 0 0 | dE/dbeta (10)] per frame in rows of kPoseFeatPad floats.
+constexpr int kJrestLd = 68;          // row pitch of the rest-joint / dE/dJ buffers (66 values, 16-byte aligned rows)
+constexpr int kMaxVp = 448;           // padded 3*Vs, supports sub-meshes of up to 144 vertices (12 sensors x 12 slots)
 constexpr int kMaxDegree = 12;
 constexpr int kSplitDegree = 7;        // sensor valence up to which the sensor phase is split over (sensor, face) items
 constexpr int kMaxVj = 44;            // chunks of the joint->vertex lists (their partial sums alias dgr .. dj below)

@@ -9,7 +9,8 @@ the minimal equivalent ("sub-model"):
 * hand joints folded into the wrists (the reference always feeds a zero hand pose, ``smpl.py:99``,
   so every hand joint's skinning transform equals its wrist ancestor's and only the first
   21*9 pose-blend features are ever non-zero);
-* only the vertices in the 1-ring of the 12 sensor vertices (``virtual_sensors.py:61-75``).
+* only the vertices in the 1-ring of the 12 sensor vertices (``virtual_sensors.py:61-75``), stored ring by ring
+  ("fan form", see ``extract_submodel`` and ``csrc/fan_math.h``).
 
 The mesh connectivity is derived exactly the way the reference derives it (``topology_from_faces``),
 and is plain data for the C-ABI so that kernel and oracle can never disagree about it.
@@ -76,12 +77,56 @@ def _first_body_ancestor(parents, j):
     return j
 
 
+MAX_FAN_JOINTS = 8           # csrc/fan_math.h kMaxFanJoints
+
+
+def sensor_ring(faces_of_sensor, v):
+    """
+    Ring of sensor vertex ``v`` from its incident faces (``(deg, 3)`` global ids, in the reference's order).
+
+    Returns ``(ring, is_fan)``: ``ring[0] == v``; if the faces form a closed, consistently wound fan, ``ring[1:]`` are the
+    neighbours in winding order, starting with the first face, so that face ``d`` is -- up to a cyclic rotation of its
+    corners, which leaves the normal ``(v1-v0)x(v2-v0)`` of ``utils.py:135`` unchanged -- ``(v, ring[1+d], ring[1+(d+1)%deg])``.
+    Otherwise (boundary, non-manifold or inconsistently wound neighbourhood) the other vertices follow in order of appearance.
+    """
+    faces_of_sensor = [[int(a) for a in f] for f in faces_of_sensor]
+    deg = len(faces_of_sensor)
+    nxt, first = {}, None
+    ok = deg >= 3
+    for f in faces_of_sensor:
+        k = f.index(v)
+        p, q = f[(k + 1) % 3], f[(k + 2) % 3]
+        if first is None:
+            first = p
+        if p in nxt or p == v or q == v:
+            ok = False
+        nxt[p] = q
+    if ok:
+        order, cur = [first], nxt[first]
+        while cur != first and cur in nxt and len(order) <= deg:
+            order.append(cur)
+            cur = nxt[cur]
+        ok = cur == first and len(order) == deg
+        if ok:
+            return [v] + order, True
+    ring = [v]
+    for f in faces_of_sensor:
+        for a in f:
+            if a not in ring:
+                ring.append(a)
+    return ring, False
+
+
 def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kintree_table, topology):
     """
     :param v_template: (V,3) or (1,V,3).  shapedirs: (V,3,>=10).  posedirs: (459, V*3) (the BodyModel buffer
         layout found in released checkpoints under ``smpl.bm.posedirs``) or (V,3,459) (the npz layout).
     :param j_regressor: (52,V).  weights: (V,52).  kintree_table: (2,52).  topology: ``topology_from_faces``.
     :return: dict of float32 / int32 arrays keyed ``sub.*`` (see include/empose_b200.h) plus python ints.
+
+    The sub-mesh is stored RING-MAJOR: sensor ``s`` owns the ``slots`` (8 or 12) consecutive sub-model vertices
+    ``s*slots ..``, slot 0 being the sensor vertex, then its neighbours (``sensor_ring``), then zero padding.  A vertex
+    shared by two rings is simply stored twice (the blend GEMMs are linear, so its gradient columns add up).
     """
     f64 = lambda a: np.asarray(a, dtype=np.float64)
     v_template = f64(v_template).reshape(-1, 3)
@@ -98,13 +143,39 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
         assert 0 <= parents[j] < j, 'body joints must be topologically ordered'
 
     sub_faces = np.asarray(topology['sub_faces'], dtype=np.int64)
-    verts = np.unique(sub_faces)                                # sorted global ids of the sub-mesh
-    local = -np.ones(n_v, dtype=np.int64)
-    local[verts] = np.arange(verts.shape[0])
-    n_sub = int(verts.shape[0])
-    sensor_ids = np.asarray(topology['vertex_ids'], dtype=np.int64)
-    helper_ids = np.asarray(topology['helper_ids'], dtype=np.int64)
-    assert (local[sensor_ids] >= 0).all() and (local[helper_ids] >= 0).all()
+    sensor_ids = [int(v) for v in topology['vertex_ids']]
+    helper_ids = [int(v) for v in topology['helper_ids']]
+    sensor_faces_g = np.asarray(topology['sensor_faces'], dtype=np.int64)          # rows of sub_faces, -1 padded
+    n_sensors = len(sensor_ids)
+    degree = (sensor_faces_g > -1).sum(axis=1)
+    max_deg = int(sensor_faces_g.shape[1])
+
+    rings, fans = [], []
+    for s_idx, v in enumerate(sensor_ids):
+        ring, is_fan = sensor_ring(sub_faces[sensor_faces_g[s_idx, :degree[s_idx]]], v)
+        assert helper_ids[s_idx] in ring
+        rings.append(ring)
+        fans.append(is_fan)
+    max_ring = max(len(r) for r in rings)
+    if max_ring > 12:
+        raise ValueError('sensor rings of more than 12 vertices are not supported (found %d)' % max_ring)
+    slots = 8 if max_ring <= 8 else 12
+    n_sub = n_sensors * slots
+    gid = -np.ones(n_sub, dtype=np.int64)                                           # global id of every sub-model vertex
+    for s_idx, ring in enumerate(rings):
+        gid[s_idx * slots:s_idx * slots + len(ring)] = ring
+    real = gid >= 0
+    local_of = [{g: s_idx * slots + r for r, g in enumerate(ring)} for s_idx, ring in enumerate(rings)]
+
+    # per-sensor face lists in the reference's order, corners as ring-local sub-model vertices
+    faces_local, sensor_faces = [], -np.ones((n_sensors, max_deg), dtype=np.int64)
+    for s_idx in range(n_sensors):
+        for d in range(int(degree[s_idx])):
+            sensor_faces[s_idx, d] = len(faces_local)
+            faces_local.append([local_of[s_idx][int(g)] for g in sub_faces[sensor_faces_g[s_idx, d]]])
+    faces_local = np.asarray(faces_local, dtype=np.int64)
+    sensor_vert = np.asarray([s_idx * slots for s_idx in range(n_sensors)], dtype=np.int64)
+    helper_vert = np.asarray([local_of[s_idx][helper_ids[s_idx]] for s_idx in range(n_sensors)], dtype=np.int64)
 
     # joints folded through the shape blend shapes
     j0 = j_regressor[:N_BODY_JOINTS] @ v_template                                   # (22,3)
@@ -113,7 +184,7 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
     # hands folded into their first body ancestor
     w22 = np.zeros((n_sub, N_BODY_JOINTS))
     for j in range(weights.shape[1]):
-        w22[:, _first_body_ancestor(parents, j)] += weights[verts, j]
+        w22[real, _first_body_ancestor(parents, j)] += weights[gid[real], j]
     nnz = (w22 != 0.0)
     n_skin = int(nnz.sum(axis=1).max())
     skin_joint = np.zeros((n_sub, n_skin), dtype=np.int32)
@@ -122,7 +193,7 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
         js = np.nonzero(nnz[v])[0]
         skin_joint[v, :js.shape[0]] = js
         skin_weight[v, :js.shape[0]] = w22[v, js]
-    # the same relation grouped by joint (gather lists for the reverse pass)
+    # the same relation grouped by joint (gather lists for the reverse pass of the general kernel)
     jt_ptr = np.zeros(N_BODY_JOINTS + 1, dtype=np.int32)
     jt_vert, jt_weight = [], []
     for j in range(N_BODY_JOINTS):
@@ -146,22 +217,19 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
             break
         chunk_len += 2
 
-    # per-vertex incidence lists for the atomic-free reverse of the sensor phase: entry (item, code) with
+    # per-vertex incidence lists for the atomic-free reverse of the sensor phase (general kernel): entry (item, code) with
     # item = sensor * max_degree + slot and code 0/1/2 = corner of that face, 3 = the sensor vertex itself,
     # 4 = the sensor's helper vertex
-    sensor_faces_arr = np.asarray(topology['sensor_faces'], dtype=np.int64)
-    max_deg = int(sensor_faces_arr.shape[1])
-    local_faces = local[sub_faces]
     inc = [[] for _ in range(n_sub)]
-    for s_idx in range(sensor_ids.shape[0]):
+    for s_idx in range(n_sensors):
         for d in range(max_deg):
-            fid = int(sensor_faces_arr[s_idx, d])
+            fid = int(sensor_faces[s_idx, d])
             if fid < 0:
                 continue
             for corner in range(3):
-                inc[int(local_faces[fid, corner])].append((s_idx * max_deg + d, corner))
-        inc[int(local[sensor_ids[s_idx]])].append((s_idx * max_deg, 3))
-        inc[int(local[helper_ids[s_idx]])].append((s_idx * max_deg, 4))
+                inc[int(faces_local[fid, corner])].append((s_idx * max_deg + d, corner))
+        inc[int(sensor_vert[s_idx])].append((s_idx * max_deg, 3))
+        inc[int(helper_vert[s_idx])].append((s_idx * max_deg, 4))
     vinc_ptr = np.zeros(n_sub + 1, dtype=np.int32)
     vinc_item, vinc_code = [], []
     for v in range(n_sub):
@@ -170,21 +238,48 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
             vinc_code.append(code)
         vinc_ptr[v + 1] = len(vinc_item)
 
+    # fan tables (csrc/fan_math.h FanModel): per sensor the union of its ring's skinning joints with dense weights,
+    # and per joint the list of (sensor, joint) partial sums that make up dE/dA_j
+    fan_ok = all(fans)
+    fan_nj = np.zeros(n_sensors, dtype=np.int32)
+    fan_joint = np.zeros((n_sensors, MAX_FAN_JOINTS), dtype=np.int32)
+    fan_weight = np.zeros((n_sensors, MAX_FAN_JOINTS, slots), dtype=np.float64)
+    fan_helper = np.zeros(n_sensors, dtype=np.int32)
+    for s_idx in range(n_sensors):
+        blk = slice(s_idx * slots, (s_idx + 1) * slots)
+        js = np.nonzero(nnz[blk].any(axis=0))[0]
+        if js.shape[0] > MAX_FAN_JOINTS:
+            fan_ok = False
+            js = js[:MAX_FAN_JOINTS]
+        fan_nj[s_idx] = js.shape[0]
+        fan_joint[s_idx, :js.shape[0]] = js
+        fan_weight[s_idx, :js.shape[0]] = w22[blk][:, js].T
+        fan_helper[s_idx] = rings[s_idx].index(helper_ids[s_idx]) - 1
+    fan_part_ptr = np.concatenate([[0], np.cumsum(fan_nj)]).astype(np.int32)
+    jp = [[] for _ in range(N_BODY_JOINTS)]
+    for s_idx in range(n_sensors):
+        for u in range(int(fan_nj[s_idx])):
+            jp[int(fan_joint[s_idx, u])].append(int(fan_part_ptr[s_idx]) + u)
+    fan_jp_ptr = np.concatenate([[0], np.cumsum([len(x) for x in jp])]).astype(np.int32)
+    fan_jp_idx = np.asarray([i for x in jp for i in x] or [0], dtype=np.int32)
+
     vp_dim = ((n_sub * 3 + 15) // 16) * 16                     # padded width of the per-frame vertex vector
-    pd = posedirs.reshape(posedirs.shape[0], n_v, 3)[:N_POSE_FEATURES, verts].reshape(N_POSE_FEATURES, n_sub * 3)
-    sd = shapedirs[verts].reshape(n_sub * 3, N_BETAS).T                              # (10, Vs*3)
+    safe = np.where(real, gid, 0)
+    mask3 = np.repeat(real, 3)
+    pd = posedirs.reshape(posedirs.shape[0], n_v, 3)[:N_POSE_FEATURES, safe].reshape(N_POSE_FEATURES, n_sub * 3) * mask3
+    sd = shapedirs[safe].reshape(n_sub * 3, N_BETAS).T * mask3                       # (10, Vs*3)
+    vt = v_template[safe].reshape(-1) * mask3
     pad = lambda a: np.concatenate([a, np.zeros(a.shape[:-1] + (vp_dim - n_sub * 3,))], axis=-1)
 
-    sensor_faces = np.asarray(topology['sensor_faces'], dtype=np.int64)
-    degree = (sensor_faces > -1).sum(axis=1)
     out = {
-        'sub.v_template': pad(v_template[verts].reshape(-1)),                         # (VP,)
+        'sub.v_template': pad(vt),                                                    # (VP,)
         'sub.shapedirs': pad(sd),                                                     # (10, VP)
         'sub.posedirs': pad(pd),                                                      # (189, VP)
         'sub.j0': j0.reshape(-1),                                                     # (66,)
         'sub.jdirs': jdirs.reshape(N_BETAS, N_BODY_JOINTS * 3),                       # (10, 66)
         'sub.skin_weight': skin_weight,                                               # (Vs, n_skin)
         'sub.jt_weight': np.asarray(jt_weight, dtype=np.float64),
+        'sub.fan_weight': fan_weight,                                                 # (12, 8, slots)
     }
     out = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
     out.update({
@@ -197,15 +292,22 @@ def extract_submodel(v_template, shapedirs, posedirs, j_regressor, weights, kint
         'sub.vinc_code': np.asarray(vinc_code, dtype=np.int32),
         'sub.vj_ptr': np.asarray(vj_ptr, dtype=np.int32),
         'sub.jvj_ptr': np.asarray(jvj_ptr, dtype=np.int32),
-        'sub.faces': local[sub_faces].astype(np.int32),                               # (Fs,3) local ids
-        'sub.sensor_vert': local[sensor_ids].astype(np.int32),                        # (12,)
-        'sub.helper_vert': local[helper_ids].astype(np.int32),                        # (12,)
+        'sub.faces': faces_local.astype(np.int32),                                    # (sum of degrees, 3) sub-model vertex ids
+        'sub.sensor_vert': sensor_vert.astype(np.int32),                              # (12,)
+        'sub.helper_vert': helper_vert.astype(np.int32),                              # (12,)
         'sub.sensor_faces': sensor_faces.astype(np.int32),                            # (12,deg) rows into faces, -1 pad
         'sub.sensor_degree': degree.astype(np.int32),
-        'sub.global_vertex_ids': verts.astype(np.int32),
+        'sub.global_vertex_ids': gid.astype(np.int32),                                # -1: padding slot
+        'sub.fan_dims': np.asarray([int(fan_ok), slots, int(degree.max()), int(fan_part_ptr[-1])], dtype=np.int32),
+        'sub.fan_helper': fan_helper,                                                 # (12,) fan index of the helper vertex
+        'sub.fan_n_joints': fan_nj,                                                   # (12,)
+        'sub.fan_part_ptr': fan_part_ptr,                                             # (13,)
+        'sub.fan_joint': fan_joint,                                                   # (12, 8)
+        'sub.fan_jp_ptr': fan_jp_ptr,                                                 # (23,)
+        'sub.fan_jp_idx': fan_jp_idx,
     })
-    out['dims'] = {'n_verts': n_sub, 'vp_dim': int(vp_dim), 'n_faces': int(sub_faces.shape[0]),
-                   'max_degree': int(sensor_faces.shape[1]), 'n_skin': n_skin, 'n_sensors': int(sensor_ids.shape[0])}
+    out['dims'] = {'n_verts': n_sub, 'vp_dim': int(vp_dim), 'n_faces': int(faces_local.shape[0]),
+                   'max_degree': max_deg, 'n_skin': n_skin, 'n_sensors': n_sensors, 'slots': slots, 'fan_ok': bool(fan_ok)}
     return out
 
 

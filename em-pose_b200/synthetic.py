@@ -94,10 +94,53 @@ def _rest_joint_targets(rng):
     return np.concatenate([body, np.asarray(hands)], axis=0)
 
 
-def make_synthetic_smplh(seed=0):
-    """Return a dict with the SMPL-H ``model.npz`` keys (float64 / int64)."""
+def _flip_edge(faces, a, b):
+    """Replace the edge (a, b) shared by two triangles by the other diagonal of their quad; winding is preserved."""
+    def find(u, v):          # the face that contains the directed edge u -> v, rotated to (u, v, w)
+        for i, f in enumerate(faces):
+            for k in range(3):
+                if f[k] == u and f[(k + 1) % 3] == v:
+                    return i, int(f[(k + 2) % 3])
+        raise ValueError('edge %d -> %d not found' % (u, v))
+    i1, c = find(a, b)
+    i2, d = find(b, a)
+    faces[i1] = (a, d, c)
+    faces[i2] = (d, b, c)
+
+
+#: valence of the first sensor vertices in the irregular variants (all others keep the lat-long mesh's 6)
+IRREGULAR_VALENCES = {'mild': (5, 7, 6, 7, 5), 'wild': (5, 7, 8, 9, 10, 4, 11)}
+
+
+def _make_irregular(faces, kind):
+    """
+    Edge flips around the sensor vertices (``submodel.VERTEX_IDS``) so that their valences differ from 6 -- a real
+    SMPL-H mesh is not regular.  The surface stays a closed, consistently wound 2-manifold with the same vertex and
+    face counts.  'mild' keeps every ring within 8 vertices, 'wild' needs 12-vertex sensor blocks.
+    """
+    from empose_b200.submodel import VERTEX_IDS, sensor_ring
+    faces = faces.copy()
+    for v, want in zip(VERTEX_IDS, IRREGULAR_VALENCES[kind]):
+        while True:
+            inc = faces[(faces == v).any(axis=1)]
+            ring, is_fan = sensor_ring(inc, v)
+            assert is_fan
+            deg = len(ring) - 1
+            if deg == want:
+                break
+            if deg > want:
+                _flip_edge(faces, v, ring[1])                 # the spoke to a neighbour goes: valence - 1
+            else:
+                _flip_edge(faces, ring[1], ring[2])           # the rim edge of the first face becomes a spoke: valence + 1
+    return faces
+
+
+def make_synthetic_smplh(seed=0, irregular=None):
+    """Return a dict with the SMPL-H ``model.npz`` keys (float64 / int64).  ``irregular``: None, 'mild' or 'wild'."""
     rng = np.random.RandomState(seed)
     verts, faces = _ellipsoid_mesh()
+    if irregular:
+        faces = _make_irregular(faces, irregular)
     targets = _rest_joint_targets(rng)
     n_j = N_JOINTS_SMPLH
 
@@ -140,13 +183,16 @@ def make_synthetic_smplh(seed=0):
             'J_regressor': r32(j_reg), 'kintree_table': kintree, 'weights': r32(weights)}
 
 
-def write_synthetic_smplh(root_dir, seed=0):
-    """Write ``<root_dir>/smplh_amass/neutral/model.npz`` (the path of reference smpl.py:26); returns it."""
+def write_synthetic_smplh(root_dir, seed=0, irregular=None):
+    """Write ``<root_dir>/smplh_amass/neutral/model.npz`` (the path of reference smpl.py:26); returns it.
+    The irregular-valence variants go to ``<root_dir>/<irregular>/smplh_amass/neutral/model.npz``."""
+    if irregular:
+        root_dir = os.path.join(root_dir, irregular)
     path = os.path.join(root_dir, 'smplh_amass', 'neutral', 'model.npz')
     if not os.path.exists(path):
         os.makedirs(os.path.dirname(path), exist_ok=True)
         tmp = path + '.tmp%d.npz' % os.getpid()
-        np.savez(tmp, **make_synthetic_smplh(seed))
+        np.savez(tmp, **make_synthetic_smplh(seed, irregular))
         os.replace(tmp, path)
     return path
 

@@ -108,6 +108,115 @@ extern "C" int host_frame_eval(const HostSub* h, int n_frames, const float* thet
     return 0;
 }
 
+// ---- fan form (csrc/fan_math.h): the per-(frame, sensor) arithmetic of the production kernel -------------------------
+#include "fan_math.h"
+
+struct HostFan {
+    int ok, slots, max_deg, n_part;
+    const int *deg, *helper, *n_joints, *part_ptr, *joint;
+    const float* weight;
+    const int *jp_ptr, *jp_idx;
+};
+
+template <typename T, int SLOTS, int MAXD>
+static void run_fan(const HostSub& h, const HostFan& hf, int n_frames, const float* theta, const float* beta, const float* off_r,
+                    const float* off_t, const float* meas_pos, const float* meas_ori, const int* active, int use_pos,
+                    int use_ori, const float* coef, int want_grad, float sensor_weight, const float* joints_gt, float joint_weight,
+                    double* sensor_pos, double* sensor_ori, double* joints, double* g_theta, double* g_beta) {
+    constexpr int RING = MAXD + 1;
+    FanModel fm;
+    fm.ok = hf.ok; fm.slots = hf.slots; fm.max_deg = hf.max_deg; fm.n_part = hf.n_part;
+    fm.deg = hf.deg; fm.helper = hf.helper; fm.n_joints = hf.n_joints; fm.part_ptr = hf.part_ptr; fm.joint = hf.joint;
+    fm.weight = hf.weight; fm.jp_ptr = hf.jp_ptr; fm.jp_idx = hf.jp_idx;
+    ResidualSpec spec;
+    spec.use_pos = use_pos; spec.use_ori = use_ori; spec.weight = sensor_weight;
+    for (int s = 0; s < kSensors; ++s) spec.sensor_active[s] = active[s];
+    bool use_static = h.use_static_tree != 0;
+    for (int j = 0; j < kJoints; ++j) use_static = use_static && (h.parents[j] == smpl_parent(j));
+    const bool joint_up = joints_gt != nullptr;
+    std::vector<JointState<T>> store(1);
+    JointState<T>& st = store[0];
+    std::vector<T> var(fan_var_floats(hf.n_part)), vp(h.vp_dim), dvp_all(h.vp_dim), feat(kPoseFeatPad);
+    for (int f = 0; f < n_frames; ++f) {
+        for (int i = 0; i < kPoseDim; ++i) st.theta[i] = T(theta[f * kPoseDim + i]);
+        // the blend GEMM: feature row [pf | beta] against [P ; S] and [0 ; Jdirs], bias [v_template | J0]
+        for (int k = 0; k < kPoseFeatPad; ++k) feat[k] = T(0);
+        for (int j = 0; j < kJoints; ++j) jt_rodrigues(st, j);
+        for (int j = 1; j < kJoints; ++j)
+            for (int e = 0; e < 9; ++e) feat[(j - 1) * 9 + e] = st.rot[j][e] - ((e % 4 == 0) ? T(1) : T(0));
+        for (int k = 0; k < kBetas; ++k) feat[kFeatBeta + k] = T(beta[f * kBetas + k]);
+        for (int i = 0; i < h.vp_dim; ++i) {
+            T acc = T(0);
+            for (int k = 0; k < kPoseFeat; ++k) acc += T(h.posedirs[k * h.vp_dim + i]) * feat[k];
+            for (int k = 0; k < kBetas; ++k) acc += T(h.shapedirs[k * h.vp_dim + i]) * feat[kFeatBeta + k];
+            vp[i] = acc + T(h.v_template[i]);                 // the template is the bias of the GEMM
+        }
+        for (int i = 0; i < kPoseDim; ++i) {
+            T acc = T(0);
+            for (int k = 0; k < kBetas; ++k) acc += T(h.jdirs[k * kPoseDim + i]) * feat[kFeatBeta + k];
+            st.jrest[i / 3][i % 3] = acc + T(h.j0[i]);
+        }
+        for (int r = 0; r < 3; ++r) { if (use_static) jt_chain_static(st, r); else jt_chain(h.parents, st, r); }
+        for (int i = 0; i < h.vp_dim; ++i) dvp_all[i] = T(0);
+        for (int s = 0; s < kSensors; ++s) {
+            T vps[RING * 3], off[12], meas[12], opos[3], oori[9], dvp[RING * 3];
+            for (int i = 0; i < RING * 3; ++i) vps[i] = vp[s * SLOTS * 3 + i];
+            for (int i = 0; i < 9; ++i) off[i] = T(off_r[f * 108 + s * 9 + i]);
+            for (int i = 0; i < 3; ++i) off[9 + i] = T(off_t[f * 36 + s * 3 + i]);
+            for (int i = 0; i < 3; ++i) meas[i] = T(meas_pos[f * 36 + s * 3 + i]);
+            for (int i = 0; i < 9; ++i) meas[3 + i] = T(meas_ori[f * 108 + s * 9 + i]);
+            fan_sensor_item<T, SLOTS, MAXD>(fm, s, &st.A[0][0], vps, off, meas, spec, want_grad != 0, opos, oori, dvp, var.data());
+            for (int i = 0; i < 3; ++i) sensor_pos[f * 36 + s * 3 + i] = double(opos[i]);
+            for (int i = 0; i < 9; ++i) sensor_ori[f * 108 + s * 9 + i] = double(oori[i]);
+            if (want_grad) for (int i = 0; i < RING * 3; ++i) dvp_all[s * SLOTS * 3 + i] = dvp[i];
+        }
+        for (int i = 0; i < 66; ++i) joints[f * 66 + i] = double(st.gpos[i / 3][i % 3]);
+        if (!want_grad) continue;
+        for (int it = 0; it < kJoints * 12; ++it) jt_reduce(fm, st, var.data(), it);
+        if (joint_up) for (int j = 0; j < kJoints; ++j) jt_joint_residual(st, joints_gt + f * kPoseDim, T(joint_weight), j);
+        for (int r = 0; r < 3; ++r) { if (use_static) jt_chain_bwd_static(st, r, joint_up); else jt_chain_bwd(h.parents, st, r, joint_up); }
+        for (int i = 0; i < kJoints * 12; ++i) jt_local(h.parents, st, var.data(), i, joint_up);
+        // the transposed GEMM: [dvp | dJ] against [P^T | 0], [S^T | Jdirs^T]
+        T gt[kPoseDim];
+        for (int j = 0; j < kJoints; ++j) jt_finish_theta(st, var.data(), T(coef[f]), gt, j);
+        for (int j = 1; j < kJoints; ++j) {
+            T dR[9], g[3] = {T(0), T(0), T(0)};
+            for (int e = 0; e < 9; ++e) {
+                T acc = T(0);
+                for (int i = 0; i < h.vp_dim; ++i) acc += T(h.posedirs[((j - 1) * 9 + e) * h.vp_dim + i]) * dvp_all[i];
+                dR[e] = acc * T(coef[f]);
+            }
+            rodrigues_bwd(&st.theta[j * 3], dR, g);
+            for (int c = 0; c < 3; ++c) gt[j * 3 + c] += g[c];
+        }
+        for (int i = 0; i < kPoseDim; ++i) g_theta[f * kPoseDim + i] = double(gt[i]);
+        for (int k = 0; k < kBetas; ++k) {
+            T acc = T(0);
+            for (int i = 0; i < h.vp_dim; ++i) acc += T(h.shapedirs[k * h.vp_dim + i]) * dvp_all[i];
+            for (int i = 0; i < kPoseDim; ++i) acc += T(h.jdirs[k * kPoseDim + i]) * var[kJoints * 9 + i];
+            g_beta[f * kBetas + k] = double(T(coef[f]) * acc);
+        }
+    }
+}
+
+extern "C" int host_fan_eval(const HostSub* h, const HostFan* hf, int n_frames, const float* theta, const float* beta,
+                             const float* off_r, const float* off_t, const float* meas_pos, const float* meas_ori,
+                             const int* active, int use_pos, int use_ori, const float* coef, int want_grad,
+                             int use_double, int force_maxd, float sensor_weight, const float* joints_gt, float joint_weight,
+                             double* sensor_pos, double* sensor_ori, double* joints, double* g_theta, double* g_beta) {
+    if (!hf->ok || h->vp_dim > kMaxVp) return -1;
+    int maxd = force_maxd > 0 ? force_maxd : hf->max_deg;
+#define EMPOSE_RUN_FAN(T, S, D)                                                                                                  \
+    run_fan<T, S, D>(*h, *hf, n_frames, theta, beta, off_r, off_t, meas_pos, meas_ori, active, use_pos, use_ori, coef, want_grad, \
+                     sensor_weight, joints_gt, joint_weight, sensor_pos, sensor_ori, joints, g_theta, g_beta)
+    if (hf->slots == 8 && maxd <= 6) { if (use_double) EMPOSE_RUN_FAN(double, 8, 6); else EMPOSE_RUN_FAN(float, 8, 6); }
+    else if (hf->slots == 8 && maxd <= 7) { if (use_double) EMPOSE_RUN_FAN(double, 8, 7); else EMPOSE_RUN_FAN(float, 8, 7); }
+    else if (hf->slots == 12 && maxd <= 11) { if (use_double) EMPOSE_RUN_FAN(double, 12, 11); else EMPOSE_RUN_FAN(float, 12, 11); }
+    else return -2;
+#undef EMPOSE_RUN_FAN
+    return 0;
+}
+
 // ---- evaluation metrics (csrc/metrics_math.h) on the host --------------------------------------------------------
 #include "metrics_math.h"
 

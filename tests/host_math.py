@@ -29,7 +29,8 @@ def _lib():
         src = os.path.join(HERE, 'host_harness.cpp')
         hdr = os.path.join(ROOT, 'em-pose_b200', 'csrc', 'frame_math.h')
         hdr2 = os.path.join(ROOT, 'em-pose_b200', 'csrc', 'metrics_math.h')
-        if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
+        hdr3 = os.path.join(ROOT, 'em-pose_b200', 'csrc', 'fan_math.h')
+        if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2), os.path.getmtime(hdr3)):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-I', os.path.dirname(hdr), src,
                                    '-o', so])
         _LIB = ctypes.CDLL(so)
@@ -71,6 +72,60 @@ def frame_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef,
                                 dp(out['sensor_ori']), dp(out['joints']), dp(out['g_theta']), dp(out['g_beta']),
                                 dp(out['verts']))
     assert rc == 0
+    return out
+
+
+class HostFan(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int) for n in ('ok', 'slots', 'max_deg', 'n_part')] +
+                [(n, ctypes.POINTER(ctypes.c_int)) for n in ('deg', 'helper', 'n_joints', 'part_ptr', 'joint')] +
+                [('weight', ctypes.POINTER(ctypes.c_float))] +
+                [(n, ctypes.POINTER(ctypes.c_int)) for n in ('jp_ptr', 'jp_idx')])
+
+
+def fan_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef, use_pos=True, use_ori=True,
+             want_grad=True, use_double=False, static_tree=True, sensor_weight=1.0, joints_gt=None, joint_weight=0.0,
+             force_maxd=0):
+    """The fan-form pass (csrc/fan_math.h, what the production kernel runs) on the host; same contract as frame_eval."""
+    keep = []
+    hs = HostSub()
+    d = sub['dims']
+    hs.n_verts, hs.vp_dim, hs.n_faces, hs.max_degree, hs.n_skin = (d['n_verts'], d['vp_dim'], d['n_faces'],
+                                                                   d['max_degree'], d['n_skin'])
+    for n in _F32_FIELDS:
+        a = np.ascontiguousarray(sub['sub.' + n], dtype=np.float32)
+        keep.append(a)
+        setattr(hs, n, a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    for n in _I32_FIELDS:
+        a = np.ascontiguousarray(sub['sub.' + n], dtype=np.int32)
+        keep.append(a)
+        setattr(hs, n, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    hs.n_vj = int(sub['sub.vj_ptr'].shape[0]) - 1
+    hs.use_static_tree = int(static_tree)
+    hf = HostFan()
+    hf.ok, hf.slots, hf.max_deg, hf.n_part = [int(v) for v in sub['sub.fan_dims']]
+    for field, key in (('deg', 'sensor_degree'), ('helper', 'fan_helper'), ('n_joints', 'fan_n_joints'),
+                       ('part_ptr', 'fan_part_ptr'), ('joint', 'fan_joint'), ('jp_ptr', 'fan_jp_ptr'), ('jp_idx', 'fan_jp_idx')):
+        a = np.ascontiguousarray(sub['sub.' + key], dtype=np.int32)
+        keep.append(a)
+        setattr(hf, field, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    w = np.ascontiguousarray(sub['sub.fan_weight'], dtype=np.float32)
+    keep.append(w)
+    hf.weight = w.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    n = theta.shape[0]
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    theta, beta, off_r, off_t, meas_pos, meas_ori, coef = map(f32, (theta, beta, off_r, off_t, meas_pos, meas_ori, coef))
+    active = np.ascontiguousarray(active, dtype=np.int32)
+    out = {'sensor_pos': np.zeros((n, 12, 3)), 'sensor_ori': np.zeros((n, 12, 3, 3)), 'joints': np.zeros((n, 22, 3)),
+           'g_theta': np.zeros((n, 66)), 'g_beta': np.zeros((n, 10))}
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    jgt = None if joints_gt is None else f32(joints_gt)
+    rc = _lib().host_fan_eval(ctypes.byref(hs), ctypes.byref(hf), n, fp(theta), fp(beta), fp(off_r), fp(off_t), fp(meas_pos),
+                              fp(meas_ori), active.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(use_pos),
+                              int(use_ori), fp(coef), int(want_grad), int(use_double), int(force_maxd),
+                              ctypes.c_float(sensor_weight), None if jgt is None else fp(jgt), ctypes.c_float(joint_weight),
+                              dp(out['sensor_pos']), dp(out['sensor_ori']), dp(out['joints']), dp(out['g_theta']), dp(out['g_beta']))
+    assert rc == 0, rc
     return out
 
 
