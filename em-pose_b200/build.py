@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libempose_b200.so')
-SOURCES = ['model.cu', 'metrics.cu', 'rnn_model.cu', 'rnn_persistent.cu', 'train.cu', 'train_kernels.cu', 'smpl_full.cu', 'frame_kernels.cu', 'gemm_tc.cu', 'gemm_simt.cu']
-HEADERS = ['common.cuh', 'frame_math.h', 'frame_kernels.h', 'gemm_jobs.h', 'gemm_tc.h', 'model_internal.h', 'train_kernels.h', 'rnn_persistent.h', 'metrics_math.h',
+SOURCES = ['model.cu', 'metrics.cu', 'rnn_model.cu', 'rnn_persistent.cu', 'train.cu', 'train_kernels.cu', 'smpl_full.cu', 'frame_kernels.cu', 'fan_kernel.cu', 'gemm_tc.cu', 'gemm_simt.cu']
+HEADERS = ['common.cuh', 'frame_math.h', 'fan_math.h', 'frame_kernels.h', 'gemm_jobs.h', 'gemm_tc.h', 'model_internal.h', 'train_kernels.h', 'rnn_persistent.h', 'metrics_math.h',
            os.path.join('..', '..', 'include', 'empose_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']

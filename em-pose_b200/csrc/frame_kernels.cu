@@ -1,7 +1,7 @@
-// Per-frame CUDA kernels of the LGD loop: input assembly, estimate update + pose features, the SMPL
-// sub-model forward / reverse pass (8 frames per CTA, per-frame state in shared memory, every phase of
-// frame_math.h flattened over (frame, item) across the CTA) and the gradient-feature finish.  Reference call sites are cited in
-// frame_kernels.h and frame_math.h.
+// Per-frame CUDA kernels of the LGD loop: input assembly, estimate update + feature rows of the blend GEMM, the GENERAL
+// SMPL sub-model forward / reverse kernel (per-frame state in shared memory, every phase of frame_math.h flattened over
+// (frame, item) across the CTA; the production kernel for fan-form sub-models is fan_kernel.cu) and the gradient-feature
+// finish.  Reference call sites are cited in frame_kernels.h and frame_math.h.
 #include <stdlib.h>
 
 #include "../../include/empose_b200.h"
@@ -14,21 +14,22 @@ namespace {
 
 __device__ __forceinline__ float maybe_round(float x, int round_out) { return round_out ? round_tf32(x) : x; }
 
-// pose features of one joint: vec(R - I), optionally split into a tf32 value and its tf32 residual
+// one value of a feature row of the blend GEMM, optionally split into a tf32 value and its tf32 residual (3xTF32)
+__device__ __forceinline__ void write_feature(float v, float* dst, int split) {
+    if (split) {
+        const float hi = round_tf32(v);
+        dst[0] = hi;
+        dst[kPoseFeatPad] = round_tf32(v - hi);
+    } else {
+        dst[0] = v;
+    }
+}
+// pose features of one joint: vec(R - I)
 __device__ __forceinline__ void write_pose_features(const float* r, float* dst, int split) {
     float R[9];
     rodrigues_fwd(r, R);
 #pragma unroll
-    for (int e = 0; e < 9; ++e) {
-        const float v = R[e] - ((e % 4 == 0) ? 1.0f : 0.0f);
-        if (split) {
-            const float hi = round_tf32(v);
-            dst[e] = hi;
-            dst[kPoseFeatPad + e] = round_tf32(v - hi);
-        } else {
-            dst[e] = v;
-        }
-    }
+    for (int e = 0; e < 9; ++e) write_feature(R[e] - ((e % 4 == 0) ? 1.0f : 0.0f), dst + e, split);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -42,13 +43,14 @@ __global__ void __launch_bounds__(256) prepare_kernel(PrepareParams p) {
         v = p.marker_pos[(int64_t)row * 36 + c];
         const int slot = p.slot_of_sensor[c / 3];
         if (p.use_pos && slot >= 0) dst = slot * 3 + c % 3;
+        p.meas[(int64_t)row * 144 + (c / 3) * 12 + c % 3] = v;
     } else {
         const int e = c - 36;
         v = p.marker_oris[(int64_t)row * 108 + e];
         const int slot = p.slot_of_sensor[e / 9];
         if (p.use_ori && slot >= 0) dst = p.n_pos + slot * 9 + e % 9;
+        p.meas[(int64_t)row * 144 + (e / 9) * 12 + 3 + e % 9] = v;
     }
-    p.meas[idx] = v;
     if (dst >= 0) {
         if (p.xin) store_operand(p.xin, (int64_t)row * p.in_stride + dst, v, p.operand_mode);
         if (p.xiter) store_operand(p.xiter, (int64_t)row * p.iter_stride + dst, v, p.operand_mode);
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) 
     __shared__ float part_db[8][kBetas];
     __shared__ float mean_db[kBetas];
     __shared__ float th[kUpdateGroup][kPoseDim];
+    __shared__ float be[kUpdateGroup][kBetas];
     __shared__ __align__(16) float tile[kUpdateGroup * 2 * kPoseFeatPad];
     const int b = blockIdx.x;
     const int64_t row0 = (int64_t)b * p.F;
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) 
             const float d = p.average_shape ? mean_db[k] : p.dbeta[g0 * kBetas + i];
             const float v = p.first ? d : p.beta[g0 * kBetas + i] + p.step * d;
             p.beta[g0 * kBetas + i] = v;
+            be[f][k] = v;
             if (p.hist_shape) p.hist_shape[g0 * kBetas + i] = v;
             if (p.xiter) store_operand(p.xiter, (g0 + f) * p.iter_stride + p.in_size + kPoseDim + k, v, p.operand_mode);
         }
@@ -125,6 +129,10 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) 
             const int f = i / (kJoints - 1), j = 1 + i - f * (kJoints - 1);
             write_pose_features(&th[f][j * 3], tile + f * row_floats + (j - 1) * 9, p.pf_split);
         }
+        for (int i = tid; i < nf * kBetas; i += kUpdateThreads) {            // shape columns of the feature row
+            const int f = i / kBetas, k = i - f * kBetas;
+            write_feature(be[f][k], tile + f * row_floats + kFeatBeta + k, p.pf_split);
+        }
         __syncthreads();
         float4* dst = reinterpret_cast<float4*>(p.pf + g0 * row_floats);
         const float4* src = reinterpret_cast<const float4*>(tile);
@@ -133,14 +141,22 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) 
     }
 }
 
-__global__ void __launch_bounds__(256) pose_feature_kernel(const float* __restrict__ theta, float* __restrict__ pf,
-                                                           int pf_stride, int pf_split, int R) {
+__global__ void __launch_bounds__(256) pose_feature_kernel(const float* __restrict__ theta, const float* __restrict__ beta,
+                                                           float* __restrict__ pf, int pf_stride, int pf_split, int R) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)R * (kJoints - 1)) return;
     const int64_t row = i / (kJoints - 1);
     const int j = 1 + (int)(i % (kJoints - 1));
     float r[3] = {theta[row * kPoseDim + j * 3], theta[row * kPoseDim + j * 3 + 1], theta[row * kPoseDim + j * 3 + 2]};
     write_pose_features(r, pf + row * pf_stride + (j - 1) * 9, pf_split);
+    if (j <= kBetas) write_feature(beta[row * kBetas + j - 1], pf + row * pf_stride + kFeatBeta + j - 1, pf_split);
+}
+
+__global__ void pack_offsets_kernel(const float* __restrict__ offset_r, const float* __restrict__ offset_t, float* __restrict__ packed, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one (window, sensor) pair
+    if (i >= n * kSensors) return;
+    for (int e = 0; e < 9; ++e) packed[(int64_t)i * 12 + e] = offset_r[(int64_t)i * 9 + e];
+    for (int e = 0; e < 3; ++e) packed[(int64_t)i * 12 + 9 + e] = offset_t[(int64_t)i * 3 + e];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -168,80 +184,8 @@ static_assert(kMainThreads % 32 == 0, "whole warps");
 // optional phase timing (development aid): thread 0 of one mid-grid CTA stores clock64() after every barrier
 #define EMPOSE_TICK(k) do { if (p.ticks && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) p.ticks[k] = clock64(); } while (0)
 
-// The two shape-blend phases, CTA-wide and with 16-byte accesses (same arithmetic as item_blend_verts /
-// item_shape_bwd_partial of frame_math.h, which the host harness checks; vp_dim is a multiple of 16 and the padding of
-// v_template / shapedirs / vp_off is zero, submodel.py:173-176).
-// Forward: thread t owns coordinates [2t, 2t + 2) of EVERY frame of the CTA, so a blend-shape row is read once per CTA
-// instead of once per frame.
-template <int VP>
-__device__ __forceinline__ void cta_blend_verts(const SubModel& m, FrameState<float, VP>* st, const float* vp_off, int64_t row0, int nf) {
-    const int t = threadIdx.x;
-    if (t * 2 >= m.vp_dim) return;
-    const float2 vt = __ldg(reinterpret_cast<const float2*>(m.v_template) + t);
-    float2 S[kBetas];                    // (two coordinates per thread: ten float4 rows would not fit the 64-register budget)
-#pragma unroll
-    for (int k = 0; k < kBetas; ++k) S[k] = __ldg(reinterpret_cast<const float2*>(m.shapedirs + (size_t)k * m.vp_dim) + t);
-    for (int f = 0; f < nf; ++f) {
-        float2 acc = vt;
-        const float4* b4 = reinterpret_cast<const float4*>(st[f].beta);
-        const float4 b0 = b4[0], b1 = b4[1];
-        const float2 b2 = *reinterpret_cast<const float2*>(st[f].beta + 8);
-        const float beta[kBetas] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
-#pragma unroll
-        for (int k = 0; k < kBetas; ++k) { acc.x = fmaf(S[k].x, beta[k], acc.x); acc.y = fmaf(S[k].y, beta[k], acc.y); }
-        if (vp_off) {
-            const float2 o = *(reinterpret_cast<const float2*>(vp_off + (row0 + f) * m.vp_dim) + t);
-            acc.x += o.x; acc.y += o.y;
-        }
-        reinterpret_cast<float2*>(st[f].vp)[t] = acc;
-    }
-}
-// Reverse: item (frame, k, part) sums a contiguous third of the coordinates, four at a time.
-template <int VP>
-__device__ __forceinline__ void cta_shape_bwd_partial(const SubModel& m, FrameState<float, VP>* st, int nf) {
-    const int nv3 = m.n_verts * 3;
-    const int q = nv3 / 4;               // whole float4s; dx beyond 3 n_verts is never written, so it must not be read
-    for (int idx = threadIdx.x; idx < nf * 3 * kBetas; idx += kMainThreads) {
-        const int f = idx / (3 * kBetas), it = idx - f * 3 * kBetas;
-        const int k = it % kBetas, part = it / kBetas;
-        const float4* S = reinterpret_cast<const float4*>(m.shapedirs + (size_t)k * m.vp_dim);
-        const float4* dx = reinterpret_cast<const float4*>(st[f].dx);
-        float a0 = 0.0f, a1 = 0.0f;
-        const int lo = part * q / 3, hi = (part + 1) * q / 3;
-#pragma unroll 4
-        for (int i = lo; i < hi; ++i) {
-            const float4 s = __ldg(S + i), d = dx[i];
-            a0 = fmaf(s.x, d.x, a0); a1 = fmaf(s.y, d.y, a1); a0 = fmaf(s.z, d.z, a0); a1 = fmaf(s.w, d.w, a1);
-        }
-        if (part == 2)
-            for (int i = q * 4; i < nv3; ++i) a0 = fmaf(__ldg(m.shapedirs + (size_t)k * m.vp_dim + i), st[f].dx[i], a0);
-        st[f].dbeta_part[part][k] = a0 + a1;
-    }
-}
-
-// More phases in the "one thread owns an item of EVERY frame of the CTA" form: the model constants (index ranges, blend
-// rows) are read once per CTA instead of once per frame.  The kernel is bound by the L1 / shared-memory pipe (ncu: 78 %
-// busy), so what counts is the number of load instructions, not the arithmetic.
-// rest joints J(beta) (item_rest_joints): thread i < 66
-template <int VP>
-__device__ __forceinline__ void cta_rest_joints(const SubModel& m, FrameState<float, VP>* st, int nf) {
-    const int i = threadIdx.x;
-    if (i >= kPoseDim) return;
-    const float j0 = __ldg(m.j0 + i);
-    float jd[kBetas];
-#pragma unroll
-    for (int k = 0; k < kBetas; ++k) jd[k] = __ldg(m.jdirs + k * kPoseDim + i);
-    for (int f = 0; f < nf; ++f) {
-        const float4* b4 = reinterpret_cast<const float4*>(st[f].beta);
-        const float4 b0 = b4[0], b1 = b4[1];
-        const float2 b2 = *reinterpret_cast<const float2*>(st[f].beta + 8);
-        const float beta[kBetas] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
-        float acc = j0;
-#pragma unroll
-        for (int k = 0; k < kBetas; ++k) acc = fmaf(jd[k], beta[k], acc);
-        st[f].jrest[i / 3][i % 3] = acc;
-    }
-}
+// Phases in the "one thread owns an item of EVERY frame of the CTA" form: the model constants (index ranges) are read
+// once per CTA instead of once per frame.
 // dE/dA_j = sum of its chunks (item_skin_bwd_reduce): thread (j, e), 22 x 12 items
 template <int VP>
 __device__ __forceinline__ void cta_skin_bwd_reduce(const SubModel& m, FrameState<float, VP>* st, int nf) {
@@ -275,6 +219,10 @@ __device__ __forceinline__ void cta_store_dvp(const SubModel& m, FrameState<floa
     }
 }
 
+// The GENERAL sub-model kernel: any sensor neighbourhood (boundary or non-manifold rings, more than 8 skinning joints per
+// ring), index-table driven, per-frame state in shared memory.  Sub-models in fan form -- every closed manifold mesh,
+// i.e. SMPL-H -- run fan_kernel.cu instead; this one is the fallback and the A/B reference (EMPOSE_MAIN_GENERAL=1).
+// Inputs and outputs are those of the fan kernel: blended rest vertices and rest joints in, dE/dvp and dE/dJ out.
 template <int VP, int kFramesPerCta, int kMainCtasPerSm>
 __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(MainParams p) {
     constexpr int kGroup = kMainThreads / kFramesPerCta;     // threads per frame in the frame-grouped mapping
@@ -284,53 +232,54 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     const SubModel& m = p.sub;
     const int64_t row0 = (int64_t)blockIdx.x * kFramesPerCta;
     const int nf = (int)min((int64_t)kFramesPerCta, (int64_t)p.R - row0);
-    const int nv3 = m.n_verts * 3;
     const bool static_tree = p.static_tree != 0;
     EMPOSE_TICK(0);
 
-    if (p.legacy_blend) {
-        EMPOSE_FOR_FRAME_ITEMS(kPoseDim + kBetas, f, i) {
-            if (i < kPoseDim) st[f].theta[i] = p.theta[(row0 + f) * kPoseDim + i];
-            else st[f].beta[i - kPoseDim] = p.beta[(row0 + f) * kBetas + (i - kPoseDim)];
-        }
-    } else {
-        // the rows of the CTA's frames are contiguous in global memory: one flat, coalesced copy each
+    {   // the rows of the CTA's frames are contiguous in global memory: flat, coalesced copies
         const float* th = p.theta + row0 * kPoseDim;
         for (int idx = threadIdx.x; idx < nf * kPoseDim; idx += kMainThreads) { const int f = idx / kPoseDim; st[f].theta[idx - f * kPoseDim] = th[idx]; }
-        const float* be = p.beta + row0 * kBetas;
-        for (int idx = threadIdx.x; idx < nf * kBetas; idx += kMainThreads) { const int f = idx / kBetas; st[f].beta[idx - f * kBetas] = be[idx]; }
+        const float* jr = p.jrest + row0 * kJrestLd;
+        for (int idx = threadIdx.x; idx < nf * kJrestLd; idx += kMainThreads) {
+            const int f = idx / kJrestLd, c = idx - f * kJrestLd;
+            if (c < kPoseDim) (&st[f].jrest[0][0])[c] = jr[idx];
+        }
+        const int q = m.vp_dim / 4;
+        for (int idx = threadIdx.x; idx < nf * q; idx += kMainThreads) {
+            const int f = idx / q, t = idx - f * q;
+            reinterpret_cast<float4*>(st[f].vp)[t] = __ldg(reinterpret_cast<const float4*>(p.vp + (row0 + f) * m.vp_dim) + t);
+        }
     }
     __syncthreads();
     EMPOSE_TICK(1);
     EMPOSE_FOR_ITEMS(kJoints, f, i) item_rodrigues(st[f], i);
-    if (p.legacy_blend) { EMPOSE_FOR_FRAME_ITEMS(kPoseDim, f, i) item_rest_joints(m, st[f], i); }
-    else cta_rest_joints(m, st, nf);
     __syncthreads();
     EMPOSE_TICK(2);
-    // The serial kinematic chain runs on the last warp first; all threads (that warp joining late) then do the
-    // wide, independent vertex blend, so the chain's latency hides behind it.
     if (threadIdx.x >= kMainThreads - 32) {
         if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_static(st[f], i); }
         else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain(m, st[f], i); }
     }
-    if (p.legacy_blend) { EMPOSE_FOR_FRAME_ITEMS(nv3, f, i) item_blend_verts(m, st[f], p.vp_off + (row0 + f) * m.vp_dim, i); }
-    else cta_blend_verts(m, st, p.vp_off, row0, nf);
     __syncthreads();
     EMPOSE_TICK(3);
     EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_skin(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(4);
+    // sensor-major inputs -> the [12][3] / [12][9] views frame_math.h expects
+    __shared__ float io[kFramesPerCta][2][144];            // [frame][offsets | measurement]: R (108) then t / position (36)
+    EMPOSE_FOR_FRAME_ITEMS(144, f, i) {
+        const int64_t row = row0 + f;
+        const int64_t orow = row / p.rows_per_offset;
+        const int sn = i / 12, e = i - sn * 12;
+        if (p.offsets) io[f][0][e < 9 ? sn * 9 + e : 108 + sn * 3 + e - 9] = p.offsets[orow * 144 + i];
+        else io[f][0][i] = i < 108 ? p.offset_r[orow * 108 + i] : p.offset_t[orow * 36 + i - 108];
+        if (p.meas) io[f][1][e < 3 ? 108 + sn * 3 + e : sn * 9 + e - 3] = p.meas[row * 144 + i];
+    }
+    __syncthreads();
     if (m.max_degree <= kSplitDegree) {
         EMPOSE_FOR_FRAME_ITEMS(kSensors * m.max_degree, f, i) item_sensor_faces(m, st[f], i);
         __syncthreads();
     EMPOSE_TICK(5);
-        EMPOSE_FOR_ITEMS(kSensors, f, i) {
-            const int64_t row = row0 + f;
-            const int64_t orow = row / p.rows_per_offset;
-            const float* meas = p.meas ? p.meas + row * 144 : nullptr;
-            item_sensor_frames(m, st[f], p.offset_r + orow * 108, p.offset_t + orow * 36, meas, meas ? meas + 36 : nullptr,
-                                p.spec, p.want_grad != 0, i);
-        }
+        EMPOSE_FOR_ITEMS(kSensors, f, i)
+            item_sensor_frames(m, st[f], &io[f][0][0], &io[f][0][108], &io[f][1][108], &io[f][1][0], p.spec, p.want_grad != 0, i);
         __syncthreads();
     EMPOSE_TICK(6);
         if (p.want_grad) {
@@ -339,13 +288,8 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
             EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_sensor_gather(m, st[f], i);
         }
     } else {
-        EMPOSE_FOR_ITEMS(kSensors, f, i) {
-            const int64_t row = row0 + f;
-            const int64_t orow = row / p.rows_per_offset;
-            const float* meas = p.meas ? p.meas + row * 144 : nullptr;
-            item_sensors(m, st[f], p.offset_r + orow * 108, p.offset_t + orow * 36, meas, meas ? meas + 36 : nullptr, p.spec,
-                          p.want_grad != 0, i);
-        }
+        EMPOSE_FOR_ITEMS(kSensors, f, i)
+            item_sensors(m, st[f], &io[f][0][0], &io[f][0][108], &io[f][1][108], &io[f][1][0], p.spec, p.want_grad != 0, i);
     }
     __syncthreads();
     EMPOSE_TICK(7);
@@ -361,8 +305,7 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     EMPOSE_FOR_FRAME_ITEMS(m.n_vj, f, i) item_skin_bwd_chunks(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(9);
-    if (p.legacy_blend) { EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_skin_bwd_reduce(m, st[f], i); }
-    else cta_skin_bwd_reduce(m, st, nf);
+    cta_skin_bwd_reduce(m, st, nf);
     EMPOSE_FOR_FRAME_ITEMS(m.n_verts, f, i) item_skin_bwd_verts(m, st[f], i);
     __syncthreads();
     EMPOSE_TICK(10);
@@ -370,14 +313,7 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
         if (static_tree) { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd_static(st[f], i, joint_up); }
         else { EMPOSE_FOR_ITEMS_CHAIN(3, f, i) item_chain_bwd(m, st[f], i, joint_up); }
     }
-    if (p.legacy_blend) {
-        EMPOSE_FOR_FRAME_ITEMS(m.vp_dim, f, i)
-            p.dvp[(row0 + f) * m.vp_dim + i] = i < nv3 ? maybe_round(st[f].dx[i], p.round_out) : 0.0f;
-    } else {
-        cta_store_dvp(m, st, p.dvp, row0, nf, p.round_out);
-    }
-    if (p.legacy_blend) { EMPOSE_FOR_ITEMS(3 * kBetas, f, i) item_shape_bwd_partial(m, st[f], i); }
-    else cta_shape_bwd_partial(m, st, nf);
+    cta_store_dvp(m, st, p.dvp, row0, nf, p.round_out);
     __syncthreads();
     EMPOSE_TICK(11);
     EMPOSE_FOR_FRAME_ITEMS(kJoints * 12, f, i) item_chain_bwd_local(m, st[f], i, joint_up);
@@ -385,7 +321,8 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     EMPOSE_TICK(12);
     EMPOSE_FOR_ITEMS(kJoints, f, i)
         item_finish_theta(st[f], p.coef[row0 + f], (const float*)nullptr, p.gtheta_part + (row0 + f) * kPoseDim, i);
-    EMPOSE_FOR_ITEMS(kBetas, f, i) item_finish_beta(m, st[f], p.coef[row0 + f], p.gbeta + (row0 + f) * kBetas, i);
+    EMPOSE_FOR_FRAME_ITEMS(kJrestLd, f, i)
+        p.dj[(row0 + f) * kJrestLd + i] = i < kPoseDim ? maybe_round(st[f].dj[i / 3][i % 3], p.round_out) : 0.0f;
     EMPOSE_TICK(13);
 }
 
@@ -415,7 +352,7 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p) {
         }
     } else if (j < kJoints + kBetas) {
         const int k = j - kJoints;
-        const float g = p.gbeta[row * kBetas + k];
+        const float g = p.coef[row] * p.dpf[row * kPoseFeatPad + kFeatBeta + k];
         if (p.xiter) store_operand(p.xiter, xg + kPoseDim + k, g, p.operand_mode);
         if (p.g_beta_out) p.g_beta_out[row * kBetas + k] = g;
     }
@@ -460,8 +397,14 @@ int launch_update(const UpdateParams& p, cudaStream_t s) {
     return EMPOSE_OK;
 }
 
-int launch_pose_features(const float* theta, float* pf, int pf_stride, int pf_split, int R, cudaStream_t s) {
-    pose_feature_kernel<<<blocks_for((int64_t)R * (kJoints - 1), 256), 256, 0, s>>>(theta, pf, pf_stride, pf_split, R);
+int launch_pose_features(const float* theta, const float* beta, float* pf, int pf_stride, int pf_split, int R, cudaStream_t s) {
+    pose_feature_kernel<<<blocks_for((int64_t)R * (kJoints - 1), 256), 256, 0, s>>>(theta, beta, pf, pf_stride, pf_split, R);
+    EMPOSE_CUDA_TRY(cudaGetLastError());
+    return EMPOSE_OK;
+}
+
+int launch_pack_offsets(const float* offset_r, const float* offset_t, float* packed, int n, cudaStream_t s) {
+    pack_offsets_kernel<<<blocks_for((int64_t)n * kSensors, 128), 128, 0, s>>>(offset_r, offset_t, packed, n);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }
@@ -469,7 +412,7 @@ int launch_pose_features(const float* theta, float* pf, int pf_stride, int pf_sp
 template <int VP, int FPC, int CPS>
 int launch_main_variant(const MainParams& p, cudaStream_t s) {
     static bool configured = false;
-    const size_t smem = sizeof(FrameState<float, VP>) * FPC;
+    const size_t smem = sizeof(FrameState<float, VP>) * FPC;      // (+ FPC * 1152 B static)
     if (!configured) {
         EMPOSE_CUDA_TRY(cudaFuncSetAttribute(main_kernel<VP, FPC, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -479,33 +422,25 @@ int launch_main_variant(const MainParams& p, cudaStream_t s) {
     return EMPOSE_OK;
 }
 
-int launch_main(const MainParams& p_in, cudaStream_t s) {
-    static int legacy_blend = -1;
-    if (legacy_blend < 0) legacy_blend = getenv("EMPOSE_MAIN_LEGACY_BLEND") ? 1 : 0;
-    MainParams p = p_in;
-    p.legacy_blend = legacy_blend;
-    // (frames per CTA, CTAs per SM) for the common sub-mesh size.  Measured on the B200 at 4096 windows x 32 frames
-    // (whole step, profiles/r01/README.md): (4,4) 13.70 ms, (5,4) 13.18 ms, (6,3) 13.39 ms, (7,3) 13.85 ms, (6,4) 12.86 ms:
-    // the more frames in flight per SM the better the latency of the narrow phases (kinematic chains, 12 sensor frames)
-    // hides; 24 is what fits (4 x (6 x 9536 B + 1 KB) of the 228 KB, which is why `jup` shares storage with `fg`).
-    // EMPOSE_MAIN_VARIANT=0..4 selects the others (experiments).
-    static int variant = -1;
-    if (variant < 0) {
-        const char* e = getenv("EMPOSE_MAIN_VARIANT");
-        variant = e ? atoi(e) : 5;
-    }
-    if (p.sub.vp_dim <= 256) {
-        switch (variant) {
-            case 0: return launch_main_variant<256, 4, 4>(p, s);
-            case 2: return launch_main_variant<256, 6, 3>(p, s);
-            case 3: return launch_main_variant<256, 7, 3>(p, s);
-            case 4: return launch_main_variant<256, 8, 2>(p, s);
-            case 1: return launch_main_variant<256, 5, 4>(p, s);
-            default: return launch_main_variant<256, 6, 4>(p, s);
-        }
-    }
-    if (p.sub.vp_dim <= kMaxVp) return launch_main_variant<kMaxVp, 4, 3>(p, s);
-    set_last_error("sensor sub-mesh too large (more than 128 vertices)");
+DebugOptions& debug_options() {
+    static DebugOptions opt = [] {
+        DebugOptions o;
+        const char* e = getenv("EMPOSE_MAIN_GENERAL");
+        o.main_general = e ? atoi(e) : 0;
+        e = getenv("EMPOSE_FAN_VARIANT");
+        o.fan_variant = e ? atoi(e) : 0;
+        e = getenv("EMPOSE_LSTM_PERSISTENT");
+        o.lstm_persistent = e ? atoi(e) : 1;
+        return o;
+    }();
+    return opt;
+}
+
+int launch_main(const MainParams& p, cudaStream_t s) {
+    if (p.fan.ok && !debug_options().main_general) return launch_main_fan(p, s);
+    if (p.sub.vp_dim <= 288) return launch_main_variant<288, 5, 3>(p, s);
+    if (p.sub.vp_dim <= kMaxVp) return launch_main_variant<kMaxVp, 3, 3>(p, s);
+    set_last_error("sensor sub-mesh too large (more than 144 vertices)");
     return EMPOSE_E_ARG;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fan_math.h"
 #include "frame_math.h"
 
 namespace empose {
@@ -21,14 +22,14 @@ struct PrepareParams {
     int in_size;
     int in_stride, iter_stride; // row pitches of xin / xiter in elements (TMA needs 16-byte aligned rows)
     int operand_mode;           // OperandMode of xin / xiter (exact fp32, tf32-rounded fp32 or fp16 elements)
-    float* meas;                // [R][144] exact copy [pos | ori]
+    float* meas;                // [R][12][12] exact copy, sensor-major: position (3) | orientation row-major (9)
     float* xin;                 // [R][in_stride]   (may be null)
     float* xiter;               // [R][iter_stride] columns [0, in_size) written (may be null)
     float* coef;                // [R]
 };
 int launch_prepare(const PrepareParams& p, cudaStream_t s);
 
-// theta/beta update (models.py:529-535, 588-592) + pose features for the pose-blend GEMM.
+// theta/beta update (models.py:529-535, 588-592) + feature rows [vec(R_j - I) | beta] of the blend GEMM (kFeat* in frame_math.h).
 struct UpdateParams {
     float* theta;               // [R][66] in/out
     float* beta;                // [R][10] in/out
@@ -41,53 +42,60 @@ struct UpdateParams {
     int operand_mode;           // OperandMode of xiter
     float* xiter;               // [R][iter_stride] or null: columns [in_size, in_size+76) receive theta | beta
     int in_size, iter_stride;
-    float* pf;                  // [R][pf_stride] pose features vec(R_1..R_21 - I); split: [hi(192) | lo(192)]
-    int pf_stride;              // 192, or 384 when split
+    float* pf;                  // [R][pf_stride] feature rows; split: [hi(kPoseFeatPad) | lo(kPoseFeatPad)]
+    int pf_stride;              // kPoseFeatPad, or twice that when split
     int pf_split;               // 1: write tf32 hi part and tf32 residual (error-compensated pose-blend GEMM)
     float* hist_pose;           // [R][66] or null
     float* hist_shape;          // [R][10] or null
 };
 int launch_update(const UpdateParams& p, cudaStream_t s);
 
-// pose features only (for empose_sensor_project)
-int launch_pose_features(const float* theta, float* pf, int pf_stride, int pf_split, int R, cudaStream_t s);
+// feature rows only (for empose_sensor_project): theta [R][66], beta [R][10]
+int launch_pose_features(const float* theta, const float* beta, float* pf, int pf_stride, int pf_split, int R, cudaStream_t s);
+
+// per-window offsets [B][12][9], [B][12][3] -> sensor-major [B][12][12] = R_off (9) | t_off (3)
+int launch_pack_offsets(const float* offset_r, const float* offset_t, float* packed, int n, cudaStream_t s);
 
 // SMPL sub-model forward (+ reverse) per frame.
 struct MainParams {
     SubModel sub;
+    FanModel fan;               // fan.ok: the fan-form kernel (fan_kernel.cu) runs, else the general one (frame_kernels.cu)
     ResidualSpec spec;
     const float* theta;         // [R][66]
-    const float* beta;          // [R][10]
-    const float* vp_off;        // [R][vp_dim]  pose-blend result
+    const float* vp;            // [R][vp_dim]  blended rest vertices v_template + S beta + P pf (the blend GEMM's output)
+    const float* jrest;         // [R][kJrestLd] rest joints J0 + Jdirs beta (same GEMM)
+    const float* offsets;       // [R / rows_per_offset][12][12] sensor-major R_off (9) | t_off (3), or null: use the two below
     const float* offset_r;      // [R / rows_per_offset][108]
     const float* offset_t;      // [R / rows_per_offset][36]
     int rows_per_offset;        // F for windows, 1 for per-frame offsets
-    const float* meas;          // [R][144] (grad only)
+    const float* meas;          // [R][12][12] sensor-major position (3) | orientation (9) (grad only)
     const float* coef;          // [R]      (grad only)
     int R;
     int want_grad;
     int round_out;
     int static_tree;            // 1: sub.parents is the standard SMPL body tree -> register-resident chain phases
-    int legacy_blend;           // 1: per-item shape-blend phases of frame_math.h instead of the CTA-wide vector ones (set by launch_main
-                                // from EMPOSE_MAIN_LEGACY_BLEND; A/B measurements)
     long long* ticks;           // development aid: per-phase clock64() samples of one CTA, or null
     float* sensor_pos;          // [R][36] or null
     float* sensor_ori;          // [R][108] or null
     float* joints;              // [R][66] or null
-    float* dvp;                 // [R][vp_dim]  (grad only)
+    float* dvp;                 // [R][vp_dim]  (grad only) dE/dvp, NOT yet times coef
+    float* dj;                  // [R][kJrestLd] (grad only) dE/dJ, NOT yet times coef (columns 66, 67 are written as zero)
     float* gtheta_part;         // [R][66]      (grad only) coef * chain part of dE/dtheta
-    float* gbeta;               // [R][10]      (grad only) coef * dE/dbeta
     const float* joints_gt;     // [R][66] or null (training): adds joint_weight * d/d(theta,beta) sum_j ||J_j - Jgt_j||
     float joint_weight;
 };
-int launch_main(const MainParams& p, cudaStream_t s);
+// development switches (empose_set_option; the environment variables EMPOSE_MAIN_GENERAL / EMPOSE_FAN_VARIANT seed them)
+struct DebugOptions { int main_general; int fan_variant; int lstm_persistent; };
+DebugOptions& debug_options();
 
-// adds the pose-blend part of dE/dtheta and writes the gradient features into the iter-MLP input
+int launch_main(const MainParams& p, cudaStream_t s);          // dispatches on p.fan.ok (option main_general forces the general kernel)
+int launch_main_fan(const MainParams& p, cudaStream_t s);      // fan_kernel.cu
+
+// adds the pose-blend part of dE/dtheta, scales dE/dbeta and writes the gradient features into the iter-MLP input
 struct PostParams {
     const float* theta;         // [R][66]
-    const float* dpf;           // [R][192]
+    const float* dpf;           // [R][kPoseFeatPad] transposed blend GEMM: dE/dpf (189) | . | dE/dbeta (10 at kFeatBeta), not yet times coef
     const float* gtheta_part;   // [R][66]
-    const float* gbeta;         // [R][10]
     const float* coef;          // [R]
     int R;
     int operand_mode;           // OperandMode of xiter

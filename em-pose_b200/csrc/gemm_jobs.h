@@ -79,6 +79,13 @@ struct GemmJob {
     int64_t gates_stride;
     float* c_seq_out;
     int64_t c_seq_stride;
+    // ---- cross-CTA ordering inside ONE launch (the persistent LSTM wavefront, tc_launch_items) ----
+    // Counters are indexed by the 128-row tile; a job is complete for a tile when its epilogue has stored it.  A job may
+    // start on a tile once the counters it names have reached wait_need * epoch (epoch = launches so far on this plan:
+    // counters are never reset).  Null pointers: no ordering (the per-diagonal launches).
+    const uint32_t* wait_ctr[2];
+    uint32_t wait_need[2];
+    uint32_t* done_ctr;
 };
 
 // Columns of an LSTM job are packed in groups of 32 = 8 hidden units x 4 gates:
@@ -216,7 +223,7 @@ __device__ __forceinline__ void lstm_half_load_c(const GemmJob& j, int row0, int
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int r = row0 + it * 8 + (lane >> 2);
-        cpre[it] = r < j.m_rows ? *reinterpret_cast<const float4*>(cs + (int64_t)r * j.hidden) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        cpre[it] = r < j.m_rows ? __ldcg(reinterpret_cast<const float4*>(cs + (int64_t)r * j.hidden)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
@@ -265,7 +272,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
                     sts128f(ctile + r * 80 + seg * 16, cpre[it]);
                 else if (row0 + r < m_rows)
                     sts128f(ctile + r * 80 + seg * 16,
-                            *reinterpret_cast<const float4*>(c_state + (int64_t)(row0 + r) * hidden + unit0 + seg * 4));
+                            __ldcg(reinterpret_cast<const float4*>(c_state + (int64_t)(row0 + r) * hidden + unit0 + seg * 4)));
             }
             if (any_frozen) {
                 const __half* hprev = reinterpret_cast<const __half*>(h_prev) + unit0;
@@ -273,7 +280,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
                 for (int it = 0; it < 2; ++it) {
                     const int r = it * 16 + (lane >> 1), seg = lane & 1;
                     if (row0 + r < m_rows) {
-                        const uint4 hv = *reinterpret_cast<const uint4*>(hprev + (int64_t)(row0 + r) * h_prev_stride + seg * 8);
+                        const uint4 hv = __ldcg(reinterpret_cast<const uint4*>(hprev + (int64_t)(row0 + r) * h_prev_stride + seg * 8));
                         sts128(htile + r * 48 + seg * 16, hv.x, hv.y, hv.z, hv.w);
                     }
                 }
@@ -333,7 +340,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
             __half* hout = reinterpret_cast<__half*>(j.out) + (int64_t)row * j.out_stride + unit0;
             if (j.t < j.seq_len[row]) {
                 float4* cp = reinterpret_cast<float4*>(j.c_state + (int64_t)row * j.hidden + unit0);
-                const float4 c0v = cp[0], c1v = cp[1];
+                const float4 c0v = __ldcg(cp), c1v = __ldcg(cp + 1);
                 const float c_old[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
                 float c_new[8];
                 uint32_t hp[4];
@@ -355,7 +362,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
                 *reinterpret_cast<uint4*>(hout) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
             } else {      // padded step: the state is carried (packed-sequence semantics); c stays where it is
                 const __half* hprev = reinterpret_cast<const __half*>(j.h_prev) + (int64_t)row * j.h_prev_stride + unit0;
-                *reinterpret_cast<uint4*>(hout) = *reinterpret_cast<const uint4*>(hprev);
+                *reinterpret_cast<uint4*>(hout) = __ldcg(reinterpret_cast<const uint4*>(hprev));
             }
         }
     } else if (j.epi == EPI_LINEAR) {
@@ -421,13 +428,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
 #pragma unroll
         for (int q = 0; q < 8; ++q) {      // coalesced: 4 rows x 8 units per instruction
             const int r = q * 4 + sub;
-            cl[q] = r < rows ? cg[(int64_t)r * j.hidden] : 0.0f;
+            cl[q] = r < rows ? __ldcg(cg + (int64_t)r * j.hidden) : 0.0f;
         }
         if (any_frozen) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int r = q * 4 + sub;
-                hl[q] = r < rows ? hg[(int64_t)r * j.h_prev_stride] : 0.0f;
+                hl[q] = r < rows ? __ldcg(hg + (int64_t)r * j.h_prev_stride) : 0.0f;
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) sh[(q * 4 + sub) * 9 + u] = hl[q];

@@ -134,12 +134,12 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
     EMPOSE_TRY(A.alloc_n(Rz * vp, &pl.dvp));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseFeatPad, &pl.dpf));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.gth_part));
-    EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.gbeta));
+    EMPOSE_TRY(A.alloc_n(Rz * kJrestLd, &pl.jrest));
+    EMPOSE_TRY(A.alloc_n(Rz * kJrestLd, &pl.dj, true));
+    EMPOSE_TRY(A.alloc_n((size_t)B * 144, &pl.offsets));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.joints));
     EMPOSE_TRY(A.alloc_n(Rz * 36, &pl.spos));
     EMPOSE_TRY(A.alloc_n(Rz * 108, &pl.sori));
-    EMPOSE_TRY(A.alloc_n((size_t)B * 108, &pl.off_r));
-    EMPOSE_TRY(A.alloc_n((size_t)B * 36, &pl.off_t));
     EMPOSE_TRY(A.alloc_n((size_t)B, &pl.seq_len));
     // Hidden activations of the MLP chains: in TF32 mode a CTA chains all layers of a 128-row tile, so the buffers
     // are CTA-local scratch (num_sms tiles, L2-resident); the FFMA executor runs layer by layer over all rows.
@@ -194,12 +194,8 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
         EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_init, ctx->shape_init, pl.xin, ctx->in_stride, ctx->in_size, &pl.init_chain));
     }
     EMPOSE_TRY(build_mlp_pair(ctx, pl, ctx->pose_iter, ctx->shape_iter, pl.xiter, ctx->iter_stride, ctx->iter_in, &pl.iter_chain));
-    {
-        GemmJob proto = linear_proto(ctx->pb, false, pl.vpoff, vp, vp);
-        EMPOSE_TRY(pl.book.add(ctx->pb, pose_blend_a0(ctx, pl.pf, R), pose_blend_a1(ctx, pl.pf, R), proto, m_rows_R, -1, &pl.pb));
-        GemmJob proto_t = linear_proto(ctx->pbt, false, pl.dpf, kPoseFeatPad, kPoseFeatPad);
-        EMPOSE_TRY(pl.book.add(ctx->pbt, ASrc{pl.dvp, vp, vp, R}, ASrc{}, proto_t, m_rows_R, -1, &pl.pbt));
-    }
+    EMPOSE_TRY(add_blend_jobs(pl.book, ctx, pl.pf, pl.vpoff, pl.jrest, R, &pl.pb));
+    EMPOSE_TRY(add_blend_transposed_jobs(pl.book, ctx, pl.dvp, pl.dj, pl.dpf, R, &pl.pbt));
     EMPOSE_TRY(pl.book.finalize(A));
     *out = plp.get();
     ctx->plans[key] = std::move(plp);
@@ -217,8 +213,8 @@ int project_plan(empose_ief* ctx, int R, Plan** out) {
     const int vp = ctx->sub.vp_dim;
     EMPOSE_TRY(pl.arena.alloc_n((size_t)R * ctx->pf_stride, &pl.pf, true));
     EMPOSE_TRY(pl.arena.alloc_n((size_t)R * vp, &pl.vpoff));
-    GemmJob proto = linear_proto(ctx->pb, false, pl.vpoff, vp, vp);
-    EMPOSE_TRY(pl.book.add(ctx->pb, pose_blend_a0(ctx, pl.pf, R), pose_blend_a1(ctx, pl.pf, R), proto, R, -1, &pl.pb));
+    EMPOSE_TRY(pl.arena.alloc_n((size_t)R * kJrestLd, &pl.jrest));
+    EMPOSE_TRY(add_blend_jobs(pl.book, ctx, pl.pf, pl.vpoff, pl.jrest, R, &pl.pb));
     EMPOSE_TRY(pl.book.finalize(pl.arena));
     *out = plp.get();
     ctx->project_plans[R] = std::move(plp);
@@ -315,37 +311,90 @@ int upload_submodel(IefData* ctx, const TensorTable& tt) {
     EMPOSE_TRY(up_i("sub.sensor_faces", (int64_t)kSensors * m.max_degree, &m.sensor_faces, -1, m.n_faces));
     EMPOSE_TRY(up_i("sub.sensor_degree", kSensors, &m.sensor_degree, 1, m.max_degree + 1));
 
-    // pose-blend matrices: forward W[i][k] = P[k][i] (N = vp_dim, K = 189 -> 192), transposed W[k][i] = P[k][i]
-    const float* P;
+    // ---- fan tables (csrc/fan_math.h; submodel.py) ----
+    {
+        FanModel& fm = ctx->fan;
+        memset(&fm, 0, sizeof(fm));
+        const int32_t* fd;
+        EMPOSE_TRY(tt.get_i32("sub.fan_dims", 4, &fd));      // fan_ok, slots, max valence, partial sums per frame
+        fm.ok = fd[0]; fm.slots = fd[1]; fm.max_deg = fd[2]; fm.n_part = fd[3];
+        if (fm.ok && ((fm.slots != 8 && fm.slots != 12) || fm.max_deg >= fm.slots || fm.max_deg < 3 || fm.n_part < 1 ||
+                      fm.n_part > kMaxPartials || kSensors * fm.slots != m.n_verts)) {
+            set_last_error("sub.fan_dims out of range");
+            return EMPOSE_E_ARG;
+        }
+        if (fm.ok) {
+            fm.deg = m.sensor_degree;
+            EMPOSE_TRY(up_i("sub.fan_helper", kSensors, &fm.helper, 0, fm.max_deg));
+            EMPOSE_TRY(up_i("sub.fan_n_joints", kSensors, &fm.n_joints, 1, kMaxFanJoints + 1));
+            EMPOSE_TRY(up_i("sub.fan_part_ptr", kSensors + 1, &fm.part_ptr, 0, fm.n_part + 1));
+            EMPOSE_TRY(up_i("sub.fan_joint", (int64_t)kSensors * kMaxFanJoints, &fm.joint, 0, kJoints));
+            EMPOSE_TRY(up_f("sub.fan_weight", {kSensors, kMaxFanJoints, fm.slots}, &fm.weight));
+            const int32_t* jp;
+            EMPOSE_TRY(tt.get_i32("sub.fan_jp_ptr", kJoints + 1, &jp));
+            if (jp[kJoints] != fm.n_part) { set_last_error("sub.fan_jp_ptr does not cover the partial sums"); return EMPOSE_E_ARG; }
+            EMPOSE_TRY(up_i("sub.fan_jp_ptr", kJoints + 1, &fm.jp_ptr, 0, fm.n_part + 1));
+            EMPOSE_TRY(up_i("sub.fan_jp_idx", fm.n_part, &fm.jp_idx, 0, fm.n_part));
+            const int32_t *hn, *hp;
+            EMPOSE_TRY(tt.get_i32("sub.fan_n_joints", kSensors, &hn));
+            EMPOSE_TRY(tt.get_i32("sub.fan_part_ptr", kSensors + 1, &hp));
+            for (int i = 0; i < kSensors; ++i)
+                if (hp[i + 1] - hp[i] != hn[i] || hp[0] != 0) { set_last_error("sub.fan_part_ptr is not the prefix sum of sub.fan_n_joints"); return EMPOSE_E_ARG; }
+        }
+    }
+
+    // ---- the blend contraction and its transpose (kFeat* in frame_math.h) ----
+    // forward: output column i < vp_dim is a blended-vertex coordinate, column vp_dim + c a rest-joint coordinate;
+    //          K index k < 189 a pose feature, kFeatBeta + b a shape parameter.  W[i][k] = P[k][i] | S[b][i] | Jdirs[b][c];
+    //          bias = v_template | J0 (added in fp32 after the accumulation).
+    const float *P, *S, *VT, *J0, *JD;
     EMPOSE_TRY(tt.get_f32("sub.posedirs", {kPoseFeat, m.vp_dim}, &P));
-    std::vector<float> col(kPoseFeat);
-    const int vp = m.vp_dim;
-    std::vector<float> pt((size_t)vp * kPoseFeat);
-    for (int i = 0; i < vp; ++i)
-        for (int k = 0; k < kPoseFeat; ++k) pt[(size_t)i * kPoseFeat + k] = P[(size_t)k * vp + i];
+    EMPOSE_TRY(tt.get_f32("sub.shapedirs", {kBetas, m.vp_dim}, &S));
+    EMPOSE_TRY(tt.get_f32("sub.v_template", {m.vp_dim}, &VT));
+    EMPOSE_TRY(tt.get_f32("sub.j0", {kPoseDim}, &J0));
+    EMPOSE_TRY(tt.get_f32("sub.jdirs", {kBetas, kPoseDim}, &JD));
+    const int vp = m.vp_dim, n_fwd = vp + kPoseDim;
+    std::vector<float> wf((size_t)n_fwd * kFeatK, 0.0f), bf(n_fwd);
+    for (int i = 0; i < n_fwd; ++i) {
+        float* row = &wf[(size_t)i * kFeatK];
+        if (i < vp) {
+            for (int k = 0; k < kPoseFeat; ++k) row[k] = P[(size_t)k * vp + i];
+            for (int b2 = 0; b2 < kBetas; ++b2) row[kFeatBeta + b2] = S[(size_t)b2 * vp + i];
+            bf[i] = VT[i];
+        } else {
+            for (int b2 = 0; b2 < kBetas; ++b2) row[kFeatBeta + b2] = JD[(size_t)b2 * kPoseDim + (i - vp)];
+            bf[i] = J0[i - vp];
+        }
+    }
     if (ctx->round) {
-        // Error-compensated (3xTF32) pose blend by K-concatenation: with x = x_hi + x_lo (both tf32),
-        //   [pf_hi | pf_lo | pf_hi] . [P_hi | P_hi | P_lo]^T = pf_hi P_hi + pf_lo P_hi + pf_hi P_lo.
+        // Error-compensated (3xTF32) blend by K-concatenation: with x = x_hi + x_lo (both tf32),
+        //   [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]^T = x_hi W_hi + x_lo W_hi + x_hi W_lo.
         // The vertex offsets feed cross products of ~1 cm mesh edges, which amplify plain TF32 rounding
         // into ~1e-3 rad of sensor-orientation noise; the split brings it back to fp32 level.
-        std::vector<float> w0((size_t)vp * 2 * kPoseFeatPad, 0.0f), w1((size_t)vp * kPoseFeat, 0.0f);
-        for (int i = 0; i < vp; ++i)
-            for (int k = 0; k < kPoseFeat; ++k) {
-                const float v = pt[(size_t)i * kPoseFeat + k];
+        std::vector<float> w0((size_t)n_fwd * 2 * kPoseFeatPad, 0.0f), w1((size_t)n_fwd * kFeatK, 0.0f);
+        for (int i = 0; i < n_fwd; ++i)
+            for (int k = 0; k < kFeatK; ++k) {
+                const float v = wf[(size_t)i * kFeatK + k];
                 const float hi = host_round_tf32(v);
                 w0[(size_t)i * 2 * kPoseFeatPad + k] = hi;
                 w0[(size_t)i * 2 * kPoseFeatPad + kPoseFeatPad + k] = hi;
-                w1[(size_t)i * kPoseFeat + k] = host_round_tf32(v - hi);
+                w1[(size_t)i * kFeatK + k] = host_round_tf32(v - hi);
             }
-        EMPOSE_TRY(pack_matrix(ctx->arena, vp, 2 * kPoseFeatPad, kPoseFeat, 16, true, false, [&](int r) {
-            return RowSource{&w0[(size_t)r * 2 * kPoseFeatPad], &w1[(size_t)r * kPoseFeat], 1.0, 0.0};
+        EMPOSE_TRY(pack_matrix(ctx->arena, n_fwd, 2 * kPoseFeatPad, kFeatK, 16, OPERAND_TF32, true, [&](int r) {
+            return RowSource{&w0[(size_t)r * 2 * kPoseFeatPad], &w1[(size_t)r * kFeatK], 1.0, (double)bf[r]};
         }, &ctx->pb));
     } else {
-        EMPOSE_TRY(pack_matrix(ctx->arena, vp, kPoseFeat, 0, 16, false, false,
-                               [&](int r) { return RowSource{&pt[(size_t)r * kPoseFeat], nullptr, 1.0, 0.0}; }, &ctx->pb));
+        EMPOSE_TRY(pack_matrix(ctx->arena, n_fwd, kFeatK, 0, 16, OPERAND_F32, true,
+                               [&](int r) { return RowSource{&wf[(size_t)r * kFeatK], nullptr, 1.0, (double)bf[r]}; }, &ctx->pb));
     }
-    EMPOSE_TRY(pack_matrix(ctx->arena, kPoseFeat, vp, 0, 16, ctx->round, false,
-                           [&](int r) { return RowSource{P + (size_t)r * vp, nullptr, 1.0, 0.0}; }, &ctx->pbt));
+    // transposed: output column n < 189 is dE/dpf_n = sum_i P[n][i] dvp_i, column kFeatBeta + b is
+    //             dE/dbeta_b = sum_i S[b][i] dvp_i + sum_c Jdirs[b][c] dJ_c; K = [dvp (vp_dim) | dJ (66)].
+    std::vector<float> zero_v(vp, 0.0f), zero_j(kPoseDim, 0.0f);
+    EMPOSE_TRY(pack_matrix(ctx->arena, kFeatK, vp, kPoseDim, 16, ctx->round ? OPERAND_TF32 : OPERAND_F32, false, [&](int r) {
+        if (r < kPoseFeat) return RowSource{P + (size_t)r * vp, zero_j.data(), 1.0, 0.0};
+        if (r < kFeatBeta) return RowSource{zero_v.data(), zero_j.data(), 1.0, 0.0};
+        return RowSource{S + (size_t)(r - kFeatBeta) * vp, JD + (size_t)(r - kFeatBeta) * kPoseDim, 1.0, 0.0};
+    }, &ctx->pbt));
     return EMPOSE_OK;
 }
 
@@ -393,8 +442,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
     auto count = [&](int rc) { ++ctx->last_launches; return rc; };
 
     EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.seq_len, seq_lengths, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.off_r, offset_r, (size_t)B * 108 * 4, cudaMemcpyDeviceToDevice, s));
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.off_t, offset_t, (size_t)B * 36 * 4, cudaMemcpyDeviceToDevice, s));
+    EMPOSE_TRY(count(launch_pack_offsets(offset_r, offset_t, pl.offsets, B, s)));
 
     PrepareParams pp;
     memset(&pp, 0, sizeof(pp));
@@ -444,16 +492,16 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         const bool grad = (it < N) && cfg.use_gradient;
         MainParams mp;
         memset(&mp, 0, sizeof(mp));
-        mp.sub = ctx->sub; mp.spec = ctx->spec;
-        mp.theta = pl.theta; mp.beta = pl.beta; mp.vp_off = pl.vpoff;
-        mp.offset_r = pl.off_r; mp.offset_t = pl.off_t; mp.rows_per_offset = F;
+        mp.sub = ctx->sub; mp.fan = ctx->fan; mp.spec = ctx->spec;
+        mp.theta = pl.theta; mp.vp = pl.vpoff; mp.jrest = pl.jrest;
+        mp.offsets = pl.offsets; mp.rows_per_offset = F;
         mp.meas = pl.meas; mp.coef = pl.coef; mp.R = R; mp.want_grad = grad; mp.round_out = rnd;
         mp.static_tree = ctx->static_tree;
         mp.sensor_pos = (hist && hist->markers) ? hist->markers + (size_t)it * R * 36 : nullptr;
         mp.sensor_ori = (hist && hist->markers_ori) ? hist->markers_ori + (size_t)it * R * 108 : nullptr;
         mp.joints = (hist && hist->joints) ? hist->joints + (size_t)it * R * kPoseDim : nullptr;
         if (it == N && !mp.joints) mp.joints = pl.joints;
-        mp.dvp = pl.dvp; mp.gtheta_part = pl.gth_part; mp.gbeta = pl.gbeta;
+        mp.dvp = pl.dvp; mp.dj = pl.dj; mp.gtheta_part = pl.gth_part;
         static long long* tick_buf = nullptr;          // EMPOSE_MAIN_TICKS=1: dump phase timing of the first gradient launch
         static const bool want_ticks = getenv("EMPOSE_MAIN_TICKS") != nullptr;
         if (want_ticks && it == 0) {
@@ -490,7 +538,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
             EMPOSE_TRY(run_jobs(ctx, pl, pl.pbt, mt_R, s));
             PostParams po;
             memset(&po, 0, sizeof(po));
-            po.theta = pl.theta; po.dpf = pl.dpf; po.gtheta_part = pl.gth_part; po.gbeta = pl.gbeta; po.coef = pl.coef;
+            po.theta = pl.theta; po.dpf = pl.dpf; po.gtheta_part = pl.gth_part; po.coef = pl.coef;
             po.R = R; po.operand_mode = ctx->op_mode; po.xiter = pl.xiter; po.in_size = ctx->in_size; po.iter_stride = ctx->iter_stride;
             EMPOSE_TRY(count(launch_post(po, s)));
         }
@@ -520,6 +568,17 @@ extern "C" {
 
 int empose_abi_version(void) { return EMPOSE_ABI_VERSION; }
 const char* empose_last_error(void) { return g_last_error.c_str(); }
+
+int empose_set_option(const char* key, int32_t value) {
+    if (!key) { set_last_error("null key"); return EMPOSE_E_ARG; }
+    const std::string k(key);
+    DebugOptions& o = debug_options();
+    if (k == "main_general") o.main_general = value;
+    else if (k == "fan_variant") o.fan_variant = value;
+    else if (k == "lstm_persistent") o.lstm_persistent = value;
+    else { set_last_error("unknown option '" + k + "'"); return EMPOSE_E_ARG; }
+    return EMPOSE_OK;
+}
 
 int empose_ief_create(const empose_ief_config* cfg, const empose_tensor* tensors, int32_t n_tensors, empose_ief** out) {
     if (!cfg || !tensors || !out) { set_last_error("null argument"); return EMPOSE_E_ARG; }
@@ -808,11 +867,11 @@ int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shap
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int rnd = ctx->round ? 1 : 0;
     ctx->last_launches = 1;
-    EMPOSE_TRY(launch_pose_features(poses, pl->pf, ctx->pf_stride, rnd, R, s));
+    EMPOSE_TRY(launch_pose_features(poses, shapes, pl->pf, ctx->pf_stride, rnd, R, s));
     EMPOSE_TRY(run_jobs(ctx, *pl, pl->pb, ceil_div(R, kTileM), s));
     MainParams mp;
     memset(&mp, 0, sizeof(mp));
-    mp.sub = ctx->sub; mp.spec = ctx->spec; mp.theta = poses; mp.beta = shapes; mp.vp_off = pl->vpoff;
+    mp.sub = ctx->sub; mp.fan = ctx->fan; mp.spec = ctx->spec; mp.theta = poses; mp.vp = pl->vpoff; mp.jrest = pl->jrest;
     mp.offset_r = offset_r; mp.offset_t = offset_t; mp.rows_per_offset = 1; mp.R = R; mp.want_grad = 0; mp.round_out = rnd;
     mp.static_tree = ctx->static_tree;
     mp.sensor_pos = sensor_pos; mp.sensor_ori = sensor_ori; mp.joints = joints;

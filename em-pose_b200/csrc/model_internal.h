@@ -330,9 +330,9 @@ struct Plan {
     // workspace
     float *meas = nullptr, *xin = nullptr, *xiter = nullptr, *coef = nullptr;
     float *theta = nullptr, *beta = nullptr, *dtheta = nullptr, *dbeta = nullptr;
-    float *pf = nullptr, *vpoff = nullptr, *dvp = nullptr, *dpf = nullptr, *gth_part = nullptr, *gbeta = nullptr;
+    float *pf = nullptr, *vpoff = nullptr, *dvp = nullptr, *dpf = nullptr, *gth_part = nullptr;
+    float *jrest = nullptr, *dj = nullptr, *offsets = nullptr;     // rest joints / dE/dJ [R][kJrestLd]; packed offsets [B][12][12]
     float *joints = nullptr, *spos = nullptr, *sori = nullptr;
-    float *off_r = nullptr, *off_t = nullptr;
     int32_t* seq_len = nullptr;
     float* act[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pose|shape][ping-pong]
     int64_t act_rows = 0;
@@ -361,6 +361,7 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
     int pf_stride = kPoseFeatPad;   // floats per row of the pose-feature buffer (2x when split hi|lo)
     Arena arena;
     SubModel sub;
+    FanModel fan;              // fan tables of the sub-model (fan.ok = 0: the general kernel runs)
     ResidualSpec spec;
     int slot_of_sensor[kSensors];
     int static_tree = 0;       // sub.parents equals the standard SMPL body tree
@@ -397,11 +398,27 @@ namespace empose {
 // needs ctx->round and ctx->arena (model.cu)
 int upload_submodel(IefData* ctx, const TensorTable& tt);
 
-// A operand of the pose-blend GEMM: [pf_hi | pf_lo] then pf_hi again in TF32 mode, plain pf in FP32 mode
+// A operand of the blend GEMM: [pf_hi | pf_lo] then pf_hi again in TF32 mode, plain pf in FP32 mode
 inline ASrc pose_blend_a0(const IefData* ctx, const float* pf, int rows) {
     return ASrc{pf, ctx->pf_stride, ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad, rows};
 }
 inline ASrc pose_blend_a1(const IefData* ctx, const float* pf, int rows) {
     return ctx->round ? ASrc{pf, ctx->pf_stride, kPoseFeatPad, rows} : ASrc{};
+}
+
+// The two contractions around the per-frame sub-model kernel, as jobs of `book`:
+//   forward     [pf | beta] . [P ; S | 0 ; Jdirs] + [v_template | J0]  ->  vp [R][vp_dim], jrest [R][kJrestLd]
+//   transposed  [dvp | dJ] . [P^T ; 0 | S^T ; Jdirs^T]                  ->  dpf [R][kPoseFeatPad] (dE/dpf | . | dE/dbeta)
+// (reference: the shape blend, pose blend and joint regression of the BodyModel call at smpl.py:121 and their backward).
+inline int add_blend_jobs(JobBook& book, const IefData* ctx, const float* pf, float* vp, float* jrest, int R, JobRange* fwd) {
+    GemmJob proto = linear_proto(ctx->pb, false, vp, ctx->sub.vp_dim, ctx->sub.vp_dim + kPoseDim);
+    proto.split = ctx->sub.vp_dim;
+    proto.out2 = jrest;
+    proto.out2_stride = kJrestLd;
+    return book.add(ctx->pb, pose_blend_a0(ctx, pf, R), pose_blend_a1(ctx, pf, R), proto, R, -1, fwd);
+}
+inline int add_blend_transposed_jobs(JobBook& book, const IefData* ctx, const float* dvp, const float* dj, float* dpf, int R, JobRange* bwd) {
+    GemmJob proto = linear_proto(ctx->pbt, false, dpf, kPoseFeatPad, kFeatK);
+    return book.add(ctx->pbt, ASrc{dvp, ctx->sub.vp_dim, ctx->sub.vp_dim, R}, ASrc{dj, kJrestLd, kPoseDim, R}, proto, R, -1, bwd);
 }
 }  // namespace empose

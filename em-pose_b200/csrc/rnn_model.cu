@@ -40,7 +40,7 @@ struct RnnPlan {
     std::vector<float*> hseq;                       // [layer]: [B][F][dirs*H] operand elements
     std::vector<float*> hinit, cstate;              // [layer*dirs + dir]: [B][H]
     float *pose = nullptr, *dshape = nullptr, *theta = nullptr, *beta = nullptr, *pf = nullptr, *vpoff = nullptr, *joints = nullptr;
-    float *off_r = nullptr, *off_t = nullptr;
+    float *jrest = nullptr, *offsets = nullptr;
     float* act[2] = {nullptr, nullptr};
     int64_t act_rows = 0;
     std::vector<JobRange> steps;                    // [layer * F + s]
@@ -63,10 +63,10 @@ __global__ void gather_state_kernel(const float* __restrict__ seq, int64_t pitch
     out[i] = load_operand(seq, (b * F + t) * pitch + col0 + u, mode);
 }
 
-__global__ void identity_offsets_kernel(float* __restrict__ off_r, float* __restrict__ off_t) {
+// one row of sensor-major offsets [12][12] = R_off (9) | t_off (3): identity, zero
+__global__ void identity_offsets_kernel(float* __restrict__ offsets) {
     const int i = threadIdx.x;
-    if (i < 108) off_r[i] = (i % 9) % 4 == 0 ? 1.0f : 0.0f;
-    if (i < 36) off_t[i] = 0.0f;
+    if (i < 144) offsets[i] = ((i % 12) < 9 && ((i % 12) % 4) == 0) ? 1.0f : 0.0f;
 }
 
 }  // namespace
@@ -215,10 +215,9 @@ int build_plan(empose_rnn* ctx, int B, int F, RnnPlan** out) {
             const int vp = fk.sub.vp_dim;
             EMPOSE_TRY(A.alloc_n(Rz * vp, &pl.vpoff));
             EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.joints));
-            EMPOSE_TRY(A.alloc_n((size_t)108, &pl.off_r));
-            EMPOSE_TRY(A.alloc_n((size_t)36, &pl.off_t));
-            GemmJob proto = linear_proto(fk.pb, false, pl.vpoff, vp, vp);
-            EMPOSE_TRY(pl.book.add(fk.pb, pose_blend_a0(&fk, pl.pf, R), pose_blend_a1(&fk, pl.pf, R), proto, R, -1, &pl.pb));
+            EMPOSE_TRY(A.alloc_n((size_t)R * kJrestLd, &pl.jrest));
+            EMPOSE_TRY(A.alloc_n((size_t)144, &pl.offsets));
+            EMPOSE_TRY(add_blend_jobs(pl.book, &fk, pl.pf, pl.vpoff, pl.jrest, R, &pl.pb));
         }
     }
     EMPOSE_TRY(pl.book.finalize(A));
@@ -305,12 +304,12 @@ int rnn_forward(empose_rnn* ctx, RnnPlan& pl, const float* marker_pos, const flo
     if (shape_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(shape_hat, pl.beta, (size_t)R * kBetas * 4, cudaMemcpyDeviceToDevice, s));
     if (!cfg.do_fk) return EMPOSE_OK;
     EMPOSE_TRY(run(ctx, pl, pl.pb, mt_R, s));
-    identity_offsets_kernel<<<1, 128, 0, s>>>(pl.off_r, pl.off_t);
+    identity_offsets_kernel<<<1, 160, 0, s>>>(pl.offsets);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     MainParams mp;
     memset(&mp, 0, sizeof(mp));
-    mp.sub = fk.sub; mp.spec = fk.spec; mp.theta = pl.theta; mp.beta = pl.beta; mp.vp_off = pl.vpoff;
-    mp.offset_r = pl.off_r; mp.offset_t = pl.off_t; mp.rows_per_offset = R;       // one identity offset row for every frame
+    mp.sub = fk.sub; mp.fan = fk.fan; mp.spec = fk.spec; mp.theta = pl.theta; mp.vp = pl.vpoff; mp.jrest = pl.jrest;
+    mp.offsets = pl.offsets; mp.rows_per_offset = R;       // one identity offset row for every frame
     mp.R = R; mp.want_grad = 0; mp.round_out = fk.round ? 1 : 0; mp.static_tree = fk.static_tree;
     mp.joints = pl.joints;
     EMPOSE_TRY(launch_main(mp, s));

@@ -22,6 +22,10 @@
 #include "model_internal.h"
 
 namespace empose {
+
+// K of the full-mesh pose-blend GEMM (189 pose features padded to a multiple of 32 floats); the sub-model path has its own,
+// wider feature row (frame_math.h kPoseFeatPad) because its GEMM also carries the shape blend.
+constexpr int kFullFeatPad = 192;
 namespace {
 
 constexpr int kAllJoints = 52;
@@ -52,7 +56,7 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(FullModel fm, const floa
             float* dst = pf + f * pf_stride + (j - 1) * 9;
             for (int e = 0; e < 9; ++e) {
                 const float v = s_rot[warp][j][e] - ((e % 4 == 0) ? 1.0f : 0.0f);
-                if (pf_split) { const float hi = round_tf32(v); dst[e] = hi; dst[kPoseFeatPad + e] = round_tf32(v - hi); }
+                if (pf_split) { const float hi = round_tf32(v); dst[e] = hi; dst[kFullFeatPad + e] = round_tf32(v - hi); }
                 else dst[e] = v;
             }
         }
@@ -145,7 +149,7 @@ using namespace empose;
 struct empose_smpl {
     int device = 0, num_sms = 148;
     bool round = true;
-    int pf_stride = kPoseFeatPad;
+    int pf_stride = kFullFeatPad;
     Arena arena;
     FullModel fm;
     PackedMatrix pb;
@@ -174,7 +178,7 @@ int empose_smpl_create(const empose_tensor* tensors, int32_t n_tensors, int32_t 
     std::unique_ptr<empose_smpl> ctx(new empose_smpl());
     ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
     ctx->round = precision != EMPOSE_PRECISION_FP32;      // TF32 and FP16 modes both run the pose blend as error-compensated tf32
-    ctx->pf_stride = ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad;
+    ctx->pf_stride = ctx->round ? 2 * kFullFeatPad : kFullFeatPad;
     TensorTable tt{tensors, n_tensors};
     const int32_t* dims;
     EMPOSE_TRY(tt.get_i32("smpl.dims", 3, &dims));
@@ -207,17 +211,17 @@ int empose_smpl_create(const empose_tensor* tensors, int32_t n_tensors, int32_t 
     EMPOSE_TRY(tt.get_f32("smpl.posedirs", {kPoseFeat, fm.v3}, &P));
     const int v3 = fm.v3;
     if (ctx->round) {
-        std::vector<float> w0((size_t)v3 * 2 * kPoseFeatPad, 0.0f), w1((size_t)v3 * kPoseFeat, 0.0f);
+        std::vector<float> w0((size_t)v3 * 2 * kFullFeatPad, 0.0f), w1((size_t)v3 * kPoseFeat, 0.0f);
         for (int i = 0; i < v3; ++i)
             for (int k = 0; k < kPoseFeat; ++k) {
                 const float v = P[(size_t)k * v3 + i];
                 const float hi = host_round_tf32(v);
-                w0[(size_t)i * 2 * kPoseFeatPad + k] = hi;
-                w0[(size_t)i * 2 * kPoseFeatPad + kPoseFeatPad + k] = hi;
+                w0[(size_t)i * 2 * kFullFeatPad + k] = hi;
+                w0[(size_t)i * 2 * kFullFeatPad + kFullFeatPad + k] = hi;
                 w1[(size_t)i * kPoseFeat + k] = host_round_tf32(v - hi);
             }
-        EMPOSE_TRY(pack_matrix(A, v3, 2 * kPoseFeatPad, kPoseFeat, 16, true, false, [&](int r) {
-            return RowSource{&w0[(size_t)r * 2 * kPoseFeatPad], &w1[(size_t)r * kPoseFeat], 1.0, 0.0};
+        EMPOSE_TRY(pack_matrix(A, v3, 2 * kFullFeatPad, kPoseFeat, 16, true, false, [&](int r) {
+            return RowSource{&w0[(size_t)r * 2 * kFullFeatPad], &w1[(size_t)r * kPoseFeat], 1.0, 0.0};
         }, &ctx->pb));
     } else {
         std::vector<float> pt((size_t)v3 * kPoseFeat);
@@ -233,8 +237,8 @@ int empose_smpl_create(const empose_tensor* tensors, int32_t n_tensors, int32_t 
     EMPOSE_TRY(A.alloc_n((size_t)kSlabFrames * kJoints * 12, &ctx->amat));
     ctx->book.use_tc = ctx->round;
     GemmJob proto = linear_proto(ctx->pb, false, ctx->vp_off, vp_stride, v3);
-    ASrc a0{ctx->pf, ctx->pf_stride, ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad, kSlabFrames};
-    ASrc a1 = ctx->round ? ASrc{ctx->pf, ctx->pf_stride, kPoseFeatPad, kSlabFrames} : ASrc{};
+    ASrc a0{ctx->pf, ctx->pf_stride, ctx->round ? 2 * kFullFeatPad : kFullFeatPad, kSlabFrames};
+    ASrc a1 = ctx->round ? ASrc{ctx->pf, ctx->pf_stride, kFullFeatPad, kSlabFrames} : ASrc{};
     EMPOSE_TRY(ctx->book.add(ctx->pb, a0, a1, proto, kSlabFrames, -1, &ctx->range));
     EMPOSE_TRY(ctx->book.finalize(A));
     *out = ctx.release();

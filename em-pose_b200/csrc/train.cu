@@ -164,8 +164,8 @@ struct TrainPlan {
     // forward workspace (same roles as Plan in model_internal.h)
     float *meas = nullptr, *xin = nullptr, *xiter = nullptr, *coef = nullptr;
     float *theta = nullptr, *beta = nullptr, *dtheta = nullptr, *dbeta = nullptr;
-    float *pf = nullptr, *vpoff = nullptr, *dvp = nullptr, *dpf = nullptr, *gth_part = nullptr, *gbeta = nullptr;
-    float *off_r = nullptr, *off_t = nullptr;
+    float *pf = nullptr, *vpoff = nullptr, *dvp = nullptr, *dpf = nullptr, *gth_part = nullptr;
+    float *jrest = nullptr, *dj = nullptr, *offsets = nullptr;
     int32_t* seq_len = nullptr;
     float* hist[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // pose, shape, joints, markers, markers_ori: [N+1][R][dof]
     float *g_theta = nullptr, *g_beta = nullptr;                         // [N+1][R][66|10]
@@ -403,9 +403,9 @@ int build_plan(empose_train* t, int B, int F, TrainPlan** out) {
     EMPOSE_TRY(A.alloc_n(Rz * vp, &pl.dvp));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseFeatPad, &pl.dpf));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.gth_part));
-    EMPOSE_TRY(A.alloc_n(Rz * kBetas, &pl.gbeta));
-    EMPOSE_TRY(A.alloc_n((size_t)B * 108, &pl.off_r));
-    EMPOSE_TRY(A.alloc_n((size_t)B * 36, &pl.off_t));
+    EMPOSE_TRY(A.alloc_n(Rz * kJrestLd, &pl.jrest));
+    EMPOSE_TRY(A.alloc_n(Rz * kJrestLd, &pl.dj, true));
+    EMPOSE_TRY(A.alloc_n((size_t)B * 144, &pl.offsets));
     EMPOSE_TRY(A.alloc_n((size_t)B, &pl.seq_len));
     EMPOSE_TRY(A.alloc_n(Rz * 12, &pl.masks));
     const size_t dof[5] = {kPoseDim, kBetas, kPoseDim, 36, 108};
@@ -512,12 +512,8 @@ int build_plan(empose_train* t, int B, int F, TrainPlan** out) {
         EMPOSE_TRY(build_mlp_run(t, pl, t->shape_iter, N, pl.xiter, ctx->iter_stride, ctx->iter_in, pl.xiterT, pl.dbeta, kBetas,
                                  pl.d_dbeta, 12, &pl.shape_iter));
     }
-    {
-        GemmJob proto = plain_proto(pl.vpoff, vp, vp, false);
-        EMPOSE_TRY(pl.book.add(ctx->pb, pose_blend_a0(ctx, pl.pf, R), pose_blend_a1(ctx, pl.pf, R), proto, R, -1, &pl.pb));
-        GemmJob proto_t = plain_proto(pl.dpf, kPoseFeatPad, kPoseFeatPad, false);
-        EMPOSE_TRY(pl.book.add(ctx->pbt, ASrc{pl.dvp, vp, vp, R}, ASrc{}, proto_t, R, -1, &pl.pbt));
-    }
+    EMPOSE_TRY(add_blend_jobs(pl.book, ctx, pl.pf, pl.vpoff, pl.jrest, R, &pl.pb));
+    EMPOSE_TRY(add_blend_transposed_jobs(pl.book, ctx, pl.dvp, pl.dj, pl.dpf, R, &pl.pbt));
     EMPOSE_TRY(emit_dw_jobs(pl));
     EMPOSE_TRY(pl.book.finalize(A));
     *out = plp.get();
@@ -593,12 +589,12 @@ int mlp_backward(empose_train* t, TrainPlan& pl, MlpRun& r, bool transpose_x, cu
 void fill_main_params(const empose_train* t, const TrainPlan& pl, MainParams* mp) {
     const empose_ief* ctx = t->base;
     memset(mp, 0, sizeof(*mp));
-    mp->sub = ctx->sub; mp->spec = ctx->spec;
-    mp->theta = pl.theta; mp->beta = pl.beta; mp->vp_off = pl.vpoff;
-    mp->offset_r = pl.off_r; mp->offset_t = pl.off_t; mp->rows_per_offset = pl.F;
+    mp->sub = ctx->sub; mp->fan = ctx->fan; mp->spec = ctx->spec;
+    mp->theta = pl.theta; mp->vp = pl.vpoff; mp->jrest = pl.jrest;
+    mp->offsets = pl.offsets; mp->rows_per_offset = pl.F;
     mp->meas = pl.meas; mp->coef = pl.coef; mp->R = pl.R; mp->round_out = ctx->round ? 1 : 0;
     mp->static_tree = ctx->static_tree;
-    mp->dvp = pl.dvp; mp->gtheta_part = pl.gth_part; mp->gbeta = pl.gbeta;
+    mp->dvp = pl.dvp; mp->dj = pl.dj; mp->gtheta_part = pl.gth_part;
 }
 
 int gradient_tail(empose_train* t, TrainPlan& pl, int it, float* xiter, cudaStream_t s) {
@@ -606,7 +602,7 @@ int gradient_tail(empose_train* t, TrainPlan& pl, int it, float* xiter, cudaStre
     EMPOSE_TRY(run(t, pl, pl.pbt, ceil_div(pl.R, kTileM), s));
     PostParams po;
     memset(&po, 0, sizeof(po));
-    po.theta = pl.theta; po.dpf = pl.dpf; po.gtheta_part = pl.gth_part; po.gbeta = pl.gbeta; po.coef = pl.coef;
+    po.theta = pl.theta; po.dpf = pl.dpf; po.gtheta_part = pl.gth_part; po.coef = pl.coef;
     po.R = pl.R; po.operand_mode = ctx->op_mode; po.xiter = xiter; po.in_size = ctx->in_size; po.iter_stride = ctx->iter_stride;
     po.g_theta_out = pl.g_theta + (size_t)it * pl.R * kPoseDim;
     po.g_beta_out = pl.g_beta + (size_t)it * pl.R * kBetas;
@@ -627,8 +623,8 @@ int train_forward(empose_train* t, TrainPlan& pl, const float* marker_pos, const
     EMPOSE_TRY(launch_pack(t->d_pack_ops, (int)t->pack_ops.size(), t->pack_max_elems, s));
     ++t->launches;
     EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.seq_len, seq_lengths, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.off_r, offset_r, (size_t)B * 108 * 4, cudaMemcpyDeviceToDevice, s));
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.off_t, offset_t, (size_t)B * 36 * 4, cudaMemcpyDeviceToDevice, s));
+    EMPOSE_TRY(launch_pack_offsets(offset_r, offset_t, pl.offsets, B, s));
+    ++t->launches;
     pl.have_masks = marker_masks != nullptr;
     if (marker_masks) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pl.masks, marker_masks, (size_t)R * 12 * 4, cudaMemcpyDeviceToDevice, s));
 

@@ -364,12 +364,12 @@ __global__ void __launch_bounds__(256) loss_kernel(LossParams p) {
                 if (!p.sensor_active[s]) continue;
                 if (p.use_pos) {
                     float q = 0.0f;
-                    for (int d = 0; d < 3; ++d) { const float t = mp[s * 3 + d] - me[s * 3 + d]; q += t * t; }
+                    for (int d = 0; d < 3; ++d) { const float t = mp[s * 3 + d] - me[s * 12 + d]; q += t * t; }
                     e += sqrtf(q);
                 }
                 if (p.use_ori) {
                     float q = 0.0f;
-                    for (int d = 0; d < 9; ++d) { const float t = mo[s * 9 + d] - me[36 + s * 9 + d]; q += t * t; }
+                    for (int d = 0; d < 9; ++d) { const float t = mo[s * 9 + d] - me[s * 12 + 3 + d]; q += t * t; }
                     e += sqrtf(q);
                 }
             }

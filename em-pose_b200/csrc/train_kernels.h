@@ -101,7 +101,7 @@ struct LossParams {
     const float* pose_hist; const float* shape_hist;        // [N+1][R][66|10]
     const float* markers_hist; const float* markers_ori_hist;   // [N+1][R][36|108]
     const float* joints_final;          // [R][66]
-    const float* meas;                  // [R][144] = [pos | ori]
+    const float* meas;                  // [R][12][12] sensor-major: position (3) | orientation (9)
     const float* pose_gt; const float* shape_gt; const float* joints_gt;   // joints_gt may be null
     int sensor_active[12];
     int use_pos, use_ori;

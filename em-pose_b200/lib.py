@@ -19,7 +19,7 @@ PRECISION_FP16 = 2      # inference: fp16 operands for the learned layers (kind:
 _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2}
 
 #: every symbol include/empose_b200.h declares (checked by tests/test_cabi.py)
-EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_ief_create', 'empose_ief_destroy',
+EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_set_option', 'empose_ief_create', 'empose_ief_destroy',
                     'empose_ief_forward', 'empose_ief_forward_host', 'empose_sensor_project',
                     'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read', 'empose_ief_profile_read_main',
                     'empose_gemm_selftest', 'empose_gemm_bench', 'empose_smpl_create', 'empose_smpl_destroy',
@@ -77,6 +77,8 @@ def load():
     i32 = ctypes.c_int32
     lib.empose_abi_version.restype = ctypes.c_int
     lib.empose_last_error.restype = ctypes.c_char_p
+    lib.empose_set_option.restype = ctypes.c_int
+    lib.empose_set_option.argtypes = [ctypes.c_char_p, i32]
     lib.empose_ief_create.restype = ctypes.c_int
     lib.empose_ief_create.argtypes = [ctypes.POINTER(IefConfig), ctypes.POINTER(Tensor), i32, ctypes.POINTER(vp)]
     lib.empose_ief_destroy.restype = None
@@ -566,6 +568,13 @@ class SmplContext(object):
         _check(load().empose_smpl_forward(self._handle, _ptr(poses_root), _ptr(poses_body), _ptr(betas), _ptr(trans), n,
                                           _ptr(verts), _ptr(joints), _stream()))
         return verts, joints
+
+
+def set_option(key, value):
+    """Development switch of the library (``empose_set_option``): e.g. ``set_option('main_general', 1)``."""
+    rc = load().empose_set_option(key.encode(), int(value))
+    if rc != 0:
+        raise EmposeError(load().empose_last_error().decode())
 
 
 def gemm_selftest(a, w, bias, precision=PRECISION_TF32):

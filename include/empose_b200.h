@@ -73,7 +73,14 @@ enum {
 
 /* One named host tensor.  Names are the reference's state-dict keys ("rnn.lstm.weight_ih_l0",
  * "pose_net_iter.hidden_layers.0.layers.1.running_var", ...) plus the "sub.*" arrays produced by
- * submodel.py (the SMPL-H sub-model and sensor topology). */
+ * submodel.py (the SMPL-H sub-model and sensor topology).
+ *
+ * The sub-model is stored ring-major: sensor s owns sub-model vertices [s*slots, (s+1)*slots) (slots = 8 or 12): its
+ * sensor vertex, then the neighbours in the winding order of its incident faces, then zero padding.  "sub.fan_dims" =
+ * {fan_ok, slots, max valence, number of (sensor, joint) pairs}; fan_ok = 1 (every closed manifold mesh, e.g. SMPL-H)
+ * selects the register-resident fan kernel (csrc/fan_kernel.cu), which reads "sub.fan_helper", "sub.fan_n_joints",
+ * "sub.fan_part_ptr", "sub.fan_joint", "sub.fan_weight", "sub.fan_jp_ptr", "sub.fan_jp_idx"; otherwise the general,
+ * index-table driven kernel (csrc/frame_kernels.cu) runs on "sub.faces", "sub.sensor_faces", "sub.skin_*", ... */
 typedef struct {
     const char* name;
     const void* data;        /* HOST pointer, contiguous row-major */
@@ -116,6 +123,13 @@ typedef struct {
 
 int empose_abi_version(void);
 const char* empose_last_error(void);
+
+/* Development switches (process-wide, never needed in production; the tests use them for A/B comparisons of two
+ * implementations of the same arithmetic).  Keys: "main_general" (1: run the general sub-model kernel even when the
+ * sub-model is in fan form), "fan_variant" (frames per CTA / CTAs per SM variant of the fan kernel), "lstm_persistent"
+ * (0: one launch per wavefront diagonal instead of the persistent wavefront kernel).  Returns EMPOSE_E_ARG for an
+ * unknown key. */
+int empose_set_option(const char* key, int32_t value);
 
 /* Build a model context: folds BatchNorm (eval statistics) into the Linear layers in double
  * precision, packs and (TF32 mode) rounds the weights, uploads the sub-model.  Inference semantics

@@ -419,3 +419,70 @@ def test_validation_loss_matches_reference_formula(dev, smpl_npz, oracle_smpl, t
     want_total = (10.0 * pose_l + 0.1 * fk_l + 1.0 * shape_l + 0.01 * rec_l) / 5
     assert abs(total.item() - want_total.item()) <= 1e-4 * abs(want_total.item())
     assert abs(vals['pose'] - pose_l.item() / 5) <= 1e-5 and abs(vals['reconstruction'] - rec_l.item() / 5) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the two sub-model kernels (fan form / general) and sensor vertices of irregular valence
+# ---------------------------------------------------------------------------------------------------------------------
+def _lgd_run(net, dev, inp):
+    with torch.no_grad():
+        out = net(util.DuckBatch(**inp).to(dev))
+    hist = {k: np.stack([h.cpu().numpy() for h in getattr(net, k)]) for k in
+            ('pose_hat_history', 'shape_hat_history', 'joints_hat_history', 'markers_hat_history', 'markers_ori_hat_history')}
+    return {k: v.cpu().numpy() for k, v in out.items()}, hist
+
+
+@pytest.mark.parametrize('n_markers', [12, 6])
+def test_fan_kernel_equals_general_kernel(dev, smpl_npz, oracle_smpl, topology, n_markers):
+    """The production fan-form kernel (csrc/fan_kernel.cu) and the general index-table kernel (csrc/frame_kernels.cu) are two
+    implementations of the same arithmetic: all N+1 iterates -- i.e. sensors, joints AND the gradient features that drive
+    the updates -- must agree to float32 rounding (exact-arithmetic mode, so nothing else differs)."""
+    params = synthetic.synth_window_params(5, 9, seed=21, ragged=True, offsets=True, drop_rate=0.05)
+    inp = util.oracle_inputs_from_params(oracle_smpl, topology, params, seed=8)
+    net = util.build_module(smpl_npz, n_markers=n_markers, precision=native.PRECISION_FP32, device=dev)
+    try:
+        native.set_option('main_general', 1)
+        out_g, hist_g = _lgd_run(net, dev, inp)
+    finally:
+        native.set_option('main_general', 0)
+    out_f, hist_f = _lgd_run(net, dev, inp)
+    live = util.valid_frame_mask(params['seq_lengths'], 9)
+    for k in out_f:
+        np.testing.assert_allclose(out_f[k][live], out_g[k][live], atol=5e-6, rtol=0, err_msg=k)
+    for k in hist_f:
+        np.testing.assert_allclose(hist_f[k][:, live], hist_g[k][:, live], atol=5e-5 if 'ori' in k else 5e-6, rtol=0, err_msg=k)
+    util.report('fan_vs_general', n_markers=n_markers, pose=float(np.abs(out_f['pose_hat'][live] - out_g['pose_hat'][live]).max()),
+                ori=float(np.abs(hist_f['markers_ori_hat_history'][:, live] - hist_g['markers_ori_hat_history'][:, live]).max()))
+
+
+@pytest.mark.parametrize('precision', [native.PRECISION_FP32, native.PRECISION_FP16], ids=PNAME.get)
+@pytest.mark.parametrize('kind', ['mild', 'wild'])
+def test_irregular_valence_mesh(dev, asset_dir, kind, precision):
+    """Sensor vertices of valence 4..11 (a real SMPL-H mesh is not regular): 'mild' runs the 8-slot / valence <= 7 fan kernel,
+    'wild' the 12-slot one; both against the full-mesh oracle, and the general kernel on the same sub-model."""
+    from oracle import sensors, smplh_lbs
+    npz = synthetic.write_synthetic_smplh(asset_dir, seed=0, irregular=kind)
+    osm = smplh_lbs.SmplhModel(npz, num_betas=10, dtype=torch.float64)
+    topo = sensors.sensor_topology(osm.faces.numpy())
+    b, f = 4, 12
+    params = synthetic.synth_window_params(b, f, seed=51, ragged=True, offsets=True)
+    inp = util.oracle_inputs_from_params(osm, topo, params, seed=6)
+    cfg = oracle_ief.IefConfig(n_markers=12, num_iterations=4, rnn_init=True)
+    sd = util.torch_state_dict(synthetic.synth_state_dict(seed=0, n_markers=12, rnn_init=True))
+    want = oracle_ief.ief_forward(cfg, sd, osm, topo, **inp)
+    net = util.build_module(npz, precision=precision, device=dev)
+    assert int(net.smpl.submodel_arrays()['sub.fan_dims'][0]) == 1
+    live = util.valid_frame_mask(params['seq_lengths'], f)
+    want_pose = torch.cat([want['root_ori_hat'], want['pose_hat']], dim=-1).numpy()
+    rad_tol, mm_tol = (2e-5, 0.02) if precision == native.PRECISION_FP32 else (PARITY_RAD, PARITY_MM)
+    for general in (0, 1):
+        try:
+            native.set_option('main_general', general)
+            out, _ = _lgd_run(net, dev, inp)
+        finally:
+            native.set_option('main_general', 0)
+        pose = np.concatenate([out['root_ori_hat'], out['pose_hat']], axis=-1)
+        rad = util.max_joint_angle_err(pose[live], want_pose[live])
+        mm = util.max_joint_pos_err_mm(out['joints_hat'][live], want['joints_hat'].numpy()[live])
+        util.report('irregular', mesh=kind, general=general, precision=PNAME[precision], rad=rad, mm=mm)
+        assert rad <= rad_tol and mm <= mm_tol, (kind, general, rad, mm)
