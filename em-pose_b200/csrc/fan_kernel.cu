@@ -146,16 +146,7 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
     // ---- P4: dE/dA_j = sum of the partials naming joint j, fixed order; a thread owns (j, e) of EVERY frame, so the
     // ---- lists are read once per CTA.  Training: the FK-loss upstream replaces the posed joints in place.
     const bool joint_up = p.joints_gt != nullptr;
-    for (int it = tid; it < kJoints * 12; it += NT) {
-        const int j = it / 12, e = it - j * 12;
-        const int q0 = __ldg(p.fan.jp_ptr + j), q1 = __ldg(p.fan.jp_ptr + j + 1);
-        for (int f = 0; f < nf; ++f) {
-            const float* part = var_of(f);
-            float acc = 0.0f;
-            for (int q = q0; q < q1; ++q) acc += part[__ldg(p.fan.jp_idx + q) * 12 + e];
-            state(f).dA[j][e] = acc;
-        }
-    }
+    jt_reduce_frames<float>(p.fan, state, var_of, nf, tid, NT);
     if (joint_up)
         for (int idx = tid; idx < nf * kJoints; idx += NT) {
             const int f = idx / kJoints;
@@ -172,10 +163,7 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
     }
     __syncthreads();
     // ---- P6: local gradients dE/dR_j, dE/dJ_j (over the dead partial sums) ----
-    for (int idx = tid; idx < nf * kJoints * 12; idx += NT) {
-        const int f = idx / (kJoints * 12);
-        jt_local(p.sub.parents, state(f), var_of(f), idx - f * (kJoints * 12), joint_up);
-    }
+    jt_local_frames<float>(p.sub.parents, state, var_of, nf, tid, NT, joint_up);
     __syncthreads();
     // ---- P7: outputs ----
     for (int idx = tid; idx < nf * kJoints; idx += NT) {

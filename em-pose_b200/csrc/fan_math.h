@@ -147,6 +147,28 @@ EMPOSE_HD void fan_store12(T* dst, const T (&a)[12]) {
 #endif
     for (int i = 0; i < 12; ++i) dst[i] = a[i];
 }
+// four consecutive values (16-byte aligned): one 128-bit access on the GPU
+template <typename T>
+EMPOSE_HD void fan_load4(const T* src, T (&a)[4]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(src);
+        a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w;
+        return;
+    }
+#endif
+    for (int i = 0; i < 4; ++i) a[i] = src[i];
+}
+template <typename T>
+EMPOSE_HD void fan_store4(T* dst, const T (&a)[4]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+        return;
+    }
+#endif
+    for (int i = 0; i < 4; ++i) dst[i] = a[i];
+}
 // one weight row [slots] of the dense (joint, slot) table -> registers
 template <typename T, int SLOTS>
 EMPOSE_HD void fan_load_weights(const float* w, T (&wr)[SLOTS]) {
@@ -351,6 +373,32 @@ EMPOSE_HD void jt_reduce(const FanModel& fm, JointState<T>& st, const T* part, i
     for (int q = fm.jp_ptr[j]; q < fm.jp_ptr[j + 1]; ++q) acc += part[fm.jp_idx[q] * 12 + e];
     st.dA[j][e] = acc;
 }
+// The same reduction for ALL frames of a CTA in the form the kernel runs: thread `tid` of `nt` owns a (joint, quarter)
+// item of EVERY frame, so the index lists are read once and every access is 16 bytes wide (22 * 3 items).
+// state(f) -> JointState<T>&, var_of(f) -> T* (the frame's partial sums).
+template <typename T, typename StateFn, typename VarFn>
+EMPOSE_HD void jt_reduce_frames(const FanModel& fm, StateFn state, VarFn var_of, int nf, int tid, int nt) {
+    for (int it = tid; it < kJoints * 3; it += nt) {
+        const int j = it / 3, q4 = (it - j * 3) * 4;
+        const int q0 = fm.jp_ptr[j], n = fm.jp_ptr[j + 1] - q0;
+        int idx[4] = {0, 0, 0, 0};                     // the first four partials of the joint stay in registers
+        for (int k = 0; k < 4; ++k) if (k < n) idx[k] = fm.jp_idx[q0 + k] * 12 + q4;
+        for (int f = 0; f < nf; ++f) {
+            const T* part = var_of(f);
+            T acc[4] = {T(0), T(0), T(0), T(0)}, v[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < 4; ++k)
+                if (k < n) { fan_load4(part + idx[k], v); acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3]; }
+            for (int k = 4; k < n; ++k) {
+                fan_load4(part + fm.jp_idx[q0 + k] * 12 + q4, v);
+                acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
+            }
+            fan_store4(&state(f).dA[j][q4], acc);
+        }
+    }
+}
 // upstream gradient of the FK loss sum_j ||J_j - Jgt_j|| (models.py:657-660) times `weight`, in place over gpos (22 items)
 template <typename T, typename TIn>
 EMPOSE_HD void jt_joint_residual(JointState<T>& st, const TIn* joints_gt, T weight, int j) {
@@ -427,6 +475,30 @@ EMPOSE_HD void jt_local(const int* parents, const JointState<T>& st, T* var, int
             if (joint_up) acc += st.A[j][r * 3 + c] * st.gpos[j][r];
         }
         var[kJoints * 9 + j * 3 + c] = acc;
+    }
+}
+// jt_local for ALL frames of a CTA: thread `tid` of `nt` owns (joint j, column a) of EVERY frame (22 * 3 items): row a of
+// dE/dR_j = G_p^T dE/dG_j^R and entry a of dE/dJ_j.  One column of G_p and of G_j, all of dE/dG_j per item and frame.
+template <typename T, typename StateFn, typename VarFn>
+EMPOSE_HD void jt_local_frames(const int* parents, StateFn state, VarFn var_of, int nf, int tid, int nt, bool joint_up) {
+    for (int it = tid; it < kJoints * 3; it += nt) {
+        const int j = it / 3, a = it - j * 3;
+        const int p = j > 0 ? parents[j] : 0;
+        for (int f = 0; f < nf; ++f) {
+            const JointState<T>& st = state(f);
+            T* var = var_of(f);
+            T d[12];
+            fan_load12(&st.dA[j][0], d);
+            const T gj0 = st.A[j][a], gj1 = st.A[j][3 + a], gj2 = st.A[j][6 + a];
+            T gp0 = a == 0 ? T(1) : T(0), gp1 = a == 1 ? T(1) : T(0), gp2 = a == 2 ? T(1) : T(0);   // root: G_p = I
+            if (j > 0) { gp0 = st.A[p][a]; gp1 = st.A[p][3 + a]; gp2 = st.A[p][6 + a]; }
+            var[j * 9 + a * 3 + 0] = gp0 * d[0] + gp1 * d[3] + gp2 * d[6];
+            var[j * 9 + a * 3 + 1] = gp0 * d[1] + gp1 * d[4] + gp2 * d[7];
+            var[j * 9 + a * 3 + 2] = gp0 * d[2] + gp1 * d[5] + gp2 * d[8];
+            T dj = (gp0 - gj0) * d[9] + (gp1 - gj1) * d[10] + (gp2 - gj2) * d[11];
+            if (joint_up) dj += gj0 * st.gpos[j][0] + gj1 * st.gpos[j][1] + gj2 * st.gpos[j][2];
+            var[kJoints * 9 + j * 3 + a] = dj;
+        }
     }
 }
 // chain part of dE/dtheta_j, times coef (22 items); the pose-blend part is added by the caller (the map is linear in dR)

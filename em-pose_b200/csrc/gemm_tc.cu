@@ -64,6 +64,8 @@ static_assert(kSmemBytes + 2 * (int)sizeof(GemmJob) <= 227 * 1024, "shared memor
 // the critical path (ncu, v10: 38 % of all stall samples were waits for such loads).
 struct ProducerView {
     int32_t dep, n_count, n_begin, in_half, a_k[2], a_map[2], a_scratch[2], w_map, w_map2, w_koff[2];
+    const uint32_t* wait_ctr[2];
+    uint32_t wait_need[2];
 };
 struct IssuerView {
     int32_t in_half, n_count, a_k[2];
@@ -74,6 +76,7 @@ __device__ __forceinline__ ProducerView producer_view(const GemmJob& j) {
     v.a_k[0] = j.a_k[0]; v.a_k[1] = j.a_k[1]; v.a_map[0] = j.a_map[0]; v.a_map[1] = j.a_map[1];
     v.a_scratch[0] = j.a_scratch[0]; v.a_scratch[1] = j.a_scratch[1];
     v.w_map = j.w_map; v.w_map2 = j.w_map2; v.w_koff[0] = j.w_koff[0]; v.w_koff[1] = j.w_koff[1];
+    v.wait_ctr[0] = j.wait_ctr[0]; v.wait_ctr[1] = j.wait_ctr[1]; v.wait_need[0] = j.wait_need[0]; v.wait_need[1] = j.wait_need[1];
     return v;
 }
 __device__ __forceinline__ IssuerView issuer_view(const GemmJob& j) {
@@ -166,6 +169,24 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 28)) __trap();
+    }
+}
+
+// ---- cross-CTA ordering inside one launch (GemmJob::wait_ctr / done_ctr) ----
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin (with back-off and a watchdog that traps) until a completion counter has reached `need`
+__device__ __forceinline__ void wait_counter(const uint32_t* p, uint32_t need) {
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_gpu(p) - need) < 0) {
+        __nanosleep(40);
+        if (++spins > (1u << 25)) __trap();
     }
 }
 
@@ -292,7 +313,8 @@ template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __restrict__ jobs,
                                                               const CUtensorMap* __restrict__ maps, int job_begin,
                                                               int job_count, int jobs_per_item, int m_tiles,
-                                                              int debug_mode) {
+                                                              int debug_mode, const int2* __restrict__ items, int n_items_table,
+                                                              uint32_t epoch) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes);
@@ -303,7 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     const int lane = threadIdx.x & 31;
     const int groups = job_count / jobs_per_item;
     // the job sequence of this CTA: (item, jj) -> index into `jobs`; the successor of the last job of an item is the first of the next
-    auto job_index = [&](int item, int jj) { return job_begin + (item % groups) * jobs_per_item + jj; };
+    // With an item table (the persistent LSTM wavefront) item i is the single job items[i].x on row-tile unit items[i].y, and
+    // jobs order themselves across CTAs through completion counters (GemmJob::wait_ctr / done_ctr).
+    auto job_index = [&](int item, int jj) { return items ? items[item].x : job_begin + (item % groups) * jobs_per_item + jj; };
+    auto item_unit = [&](int item) { return items ? items[item].y : item / groups; };
     // work items: (row tile, job group); in cluster mode an item is a PAIR of row tiles, one per CTA of the cluster
     constexpr int kCluster = kMode >= 2 ? 2 : 1;
     constexpr bool kPair = kMode == 3;
@@ -311,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     constexpr int kSlotBytes = kPair ? kABytes + kWBytes / 2 : kStageBytes;                 // ... of this many bytes
     static_assert(kRing * kSlotBytes <= kStages * kStageBytes, "the ring must fit the operand region");
     const uint32_t ring = (kPair && (debug_mode & 256)) ? (uint32_t)kStages : (uint32_t)kRing;     // bit 256: experiment, shallow ring
-    const int n_items = (kCluster == 2 ? (m_tiles + 1) / 2 : m_tiles) * groups;
+    const int n_items = items ? n_items_table : (kCluster == 2 ? (m_tiles + 1) / 2 : m_tiles) * groups;
     const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;
     const int item0 = kCluster == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int item_step = kCluster == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -355,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
             ProducerView nxt;
             if (item0 < n_items) nxt = producer_view(jobs[job_index(item0, 0)]);
             for (int item = item0; item < n_items; item += item_step, ++items_done) {
-                const int m0 = (kCluster == 2 ? 2 * (item / groups) + (int)crank : item / groups) * kTileM;
+                const int m0 = (kCluster == 2 ? 2 * item_unit(item) + (int)crank : item_unit(item)) * kTileM;
                 for (int jj = 0; jj < jobs_per_item; ++jj) {
                     const ProducerView job = nxt;
                     {
@@ -368,6 +393,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         while (ctl->epi_done < need) {
                         }
                         __threadfence_block();
+                        __syncwarp();
+                    }
+                    if (job.wait_ctr[0] || job.wait_ctr[1]) {
+                        // this tile's A rows are produced by other CTAs of THIS launch: wait for their epilogues, then
+                        // order the TMA reads (async proxy) after what the acquire made visible
+                        if (m0 < m_tiles * kTileM) {
+#pragma unroll
+                            for (int q = 0; q < 2; ++q)
+                                if (job.wait_ctr[q]) wait_counter(job.wait_ctr[q] + m0 / kTileM, job.wait_need[q] * epoch);
+                        }
+                        asm volatile("fence.proxy.async;" ::: "memory");
                         __syncwarp();
                     }
                     const uint32_t w_bytes = (uint32_t)job.n_count * kChunkK * 4u;        // 128 bytes per row in either type
@@ -487,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
             reinterpret_cast<uint32_t*>(&job_s[0])[et] = reinterpret_cast<const uint32_t*>(&jobs[job_index(item0, 0)])[et];
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         for (int item = item0; item < n_items; item += item_step) {
-            const int m0 = (kCluster == 2 ? 2 * (item / groups) + (int)crank : item / groups) * kTileM;
+            const int m0 = (kCluster == 2 ? 2 * item_unit(item) + (int)crank : item_unit(item)) * kTileM;
             for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
                 const uint32_t buf = seq & 1u;
                 const GemmJob& job = job_s[buf];
@@ -507,6 +543,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 const int c_end = min(job.n_count, (half + 1) * (kMaxTileN / 2));
                 // fp16 LSTM jobs: the cell state of the first chunk pair is fetched while the MMAs are still running
                 const bool lstm_pre = lstm_half_paired(job) && !(debug_mode & 128);
+                // Wavefront jobs: the recurrent state this epilogue reads (cell state, carried hidden state) is written by
+                // other CTAs of this launch -- wait for them here too (the MMAs cannot start earlier either).
+                if ((job.wait_ctr[0] || job.wait_ctr[1]) && m0 < m_tiles * kTileM) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (job.wait_ctr[q]) wait_counter(job.wait_ctr[q] + m0 / kTileM, job.wait_need[q] * epoch);
+                }
                 float4 cpre[4];
                 if (lstm_pre && c_begin < c_end) lstm_half_load_c(job, row0, lane, c_begin, cpre);
                 // fp16 linear jobs: all fields the chunk loop needs, once per job
@@ -540,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 }
                 tcgen05_fence_before();
                 if (has_next) reinterpret_cast<uint32_t*>(&job_s[buf ^ 1u])[et] = next_word;
-                if (!(debug_mode & 8) && (job.is_dep || (debug_mode & 512))) {
+                if (!(debug_mode & 8) && (job.is_dep || job.done_ctr || (debug_mode & 512))) {
                     // Only a job that a later job of this item waits for publishes stores (its own and, by program order,
                     // those of the jobs before it: every thread owns the same rows and column half in all jobs).
                     // The only in-kernel consumer of these stores is this CTA's own TMA (scratch activations of the next
@@ -556,6 +599,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     if (kPair) mbar_arrive_cluster(mapa_rank0(&ctl->tmem_empty[buf]));      // CTA 0 issues the MMAs of both
                     else mbar_arrive(&ctl->tmem_empty[buf]);
                     ctl->epi_done = seq + 1u;
+                    // publish this tile to the other CTAs: the barrier above ordered every epilogue thread's stores before
+                    // this thread, the release makes them visible device-wide before the count
+                    if (job.done_ctr && m0 < m_tiles * kTileM) red_release_gpu(job.done_ctr + m0 / kTileM, 1u);
                 }
             }
         }
@@ -618,42 +664,55 @@ int tc_encode_map(void* out_map, const float* base, int64_t row_stride_elems, in
     return EMPOSE_OK;
 }
 
+// Executor configuration, once per process (one process per GPU).
+static int g_max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster modes unavailable or disabled)
+static int g_cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
+// EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
+// 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring, 512 fence after every job
+static int g_debug_mode = 0;
+
+static int tc_configure(int num_sms) {
+    static bool configured = false;
+    if (configured) return EMPOSE_OK;
+    EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    const char* e = getenv("EMPOSE_TC_DEBUG");
+    g_debug_mode = e ? atoi(e) : 0;
+    // EMPOSE_TC_CLUSTER: 0 one CTA per row tile; 1 pairs of CTAs with the W tile multicast (correct, halves the W
+    // traffic out of L2, no faster: profiles/r01/README.md); 2 pairs of CTAs issuing ONE cta_group::2 MMA per pair
+    // (each SM stages half of W: relieves the shared-memory bandwidth that bounds the mainloop).
+    const char* c = getenv("EMPOSE_TC_CLUSTER");
+    const int want = c ? atoi(c) : kDefaultClusterMode;
+    if ((want == 1 || want == 2) && !(g_debug_mode & 3)) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (num_sms / 2)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int n = 0;
+        const cudaError_t q = want == 1 ? cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<2>, &cfg)
+                                        : cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<3>, &cfg);
+        if (q == cudaSuccess && n > 0) { g_max_clusters = n; g_cluster_mode = want + 1; }
+        else cudaGetLastError();
+    }
+    if (getenv("EMPOSE_TC_VERBOSE"))
+        fprintf(stderr, "empose_b200: gemm executor: mode %d, %d co-resident 2-CTA clusters on %d SMs\n", g_cluster_mode, g_max_clusters, num_sms);
+    configured = true;
+    return EMPOSE_OK;
+}
+#define EMPOSE_TRY_CONFIG(num_sms)                 \
+    do {                                           \
+        int _rc = tc_configure(num_sms);           \
+        if (_rc != EMPOSE_OK) return _rc;          \
+    } while (0)
+
 int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_count, int jobs_per_item, int m_tiles,
               int num_sms, cudaStream_t stream) {
-    static bool configured = false;
-    static int max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster modes unavailable or disabled)
-    static int cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
-    // EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
-    // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring, 512 fence after every job
-    static int debug_mode = 0;
-    if (!configured) {
-        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        const char* e = getenv("EMPOSE_TC_DEBUG");
-        debug_mode = e ? atoi(e) : 0;
-        // EMPOSE_TC_CLUSTER: 0 one CTA per row tile; 1 pairs of CTAs with the W tile multicast (correct, halves the W
-        // traffic out of L2, no faster: profiles/r01/README.md); 2 pairs of CTAs issuing ONE cta_group::2 MMA per pair
-        // (each SM stages half of W: relieves the shared-memory bandwidth that bounds the mainloop).
-        const char* c = getenv("EMPOSE_TC_CLUSTER");
-        const int want = c ? atoi(c) : kDefaultClusterMode;
-        if ((want == 1 || want == 2) && !(debug_mode & 3)) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(2 * (num_sms / 2)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
-            cudaLaunchAttribute attr;
-            attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-            cfg.attrs = &attr; cfg.numAttrs = 1;
-            int n = 0;
-            const cudaError_t q = want == 1 ? cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<2>, &cfg)
-                                            : cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<3>, &cfg);
-            if (q == cudaSuccess && n > 0) { max_clusters = n; cluster_mode = want + 1; }
-            else cudaGetLastError();
-        }
-        if (getenv("EMPOSE_TC_VERBOSE"))
-            fprintf(stderr, "empose_b200: gemm executor: mode %d, %d co-resident 2-CTA clusters on %d SMs\n", cluster_mode, max_clusters, num_sms);
-        configured = true;
-    }
+    EMPOSE_TRY_CONFIG(num_sms);
+    const int max_clusters = g_max_clusters, cluster_mode = g_cluster_mode, debug_mode = g_debug_mode;
+    const int2* no_items = nullptr;
     const int groups = job_count / jobs_per_item;
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(d_maps);
     if (max_clusters > 0 && m_tiles >= 2) {
@@ -666,14 +725,51 @@ int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
         if (cluster_mode == 3)
-            EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3>, d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode));
+            EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3>, d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode, no_items, 0, 0u));
         else
-            EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode));
+            EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode, no_items, 0, 0u));
         return EMPOSE_OK;
     }
     const int n_items = m_tiles * groups;
     const int grid = n_items < num_sms ? n_items : num_sms;
-    gemm_tc_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode);
+    gemm_tc_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(d_jobs, maps, job_begin, job_count, jobs_per_item, m_tiles, debug_mode, no_items, 0, 0u);
+    EMPOSE_CUDA_TRY(cudaGetLastError());
+    return EMPOSE_OK;
+}
+
+int tc_item_rows(int m_tiles, int num_sms) {
+    EMPOSE_TRY_CONFIG(num_sms);
+    return (g_max_clusters > 0 && m_tiles >= 2) ? 2 * kTileM : kTileM;
+}
+
+int tc_launch_items(const GemmJob* d_jobs, const void* d_maps, const void* d_items, int n_items, int rows_per_unit, uint32_t epoch,
+                    int m_tiles, int num_sms, cudaStream_t stream) {
+    EMPOSE_TRY_CONFIG(num_sms);
+    const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(d_maps);
+    const int2* items = reinterpret_cast<const int2*>(d_items);
+    if (rows_per_unit != tc_item_rows(m_tiles, num_sms)) {
+        set_last_error("internal error: item table built for a different executor mode");
+        return EMPOSE_E_ARG;
+    }
+    // The grid must be co-resident: CTAs spin on counters that other CTAs of the same launch advance.  Items are taken
+    // round-robin in table order and every item only waits for items earlier in the table, so the earliest unfinished item
+    // can always run.
+    if (rows_per_unit == 2 * kTileM) {
+        const int clusters = n_items < g_max_clusters ? n_items : g_max_clusters;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        if (g_cluster_mode == 3)
+            EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3>, d_jobs, maps, 0, n_items, 1, m_tiles, g_debug_mode, items, n_items, epoch));
+        else
+            EMPOSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, d_jobs, maps, 0, n_items, 1, m_tiles, g_debug_mode, items, n_items, epoch));
+        return EMPOSE_OK;
+    }
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    gemm_tc_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(d_jobs, maps, 0, n_items, 1, m_tiles, g_debug_mode, items, n_items, epoch);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

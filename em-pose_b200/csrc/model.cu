@@ -156,6 +156,9 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
             EMPOSE_TRY(alloc_operand((size_t)B * H, &pl.hinit[l]));
         }
         pl.lstm_diag.resize(F + L - 1);
+        const int mt_B = ceil_div(B, kTileM);
+        if (ctx->round) EMPOSE_TRY(A.alloc_n((size_t)L * F * mt_B, &pl.wave_ctr, true));
+        auto ctr_of = [&](int l, int t) { return pl.wave_ctr + ((size_t)l * F + t) * mt_B; };
         for (int d = 0; d < F + L - 1; ++d)
             for (int l = 0; l < L; ++l) {
                 const int t = d - l;
@@ -179,8 +182,29 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
                 proto.seq_len = pl.seq_len;
                 proto.frames_per_window = 1;
                 proto.split = 1 << 30;
+                if (ctx->round) {
+                    // ordering inside the persistent wavefront launch: step t of layer l reads h_{t-1} of its own layer (all
+                    // N tiles of that step; its cell state and carried rows come with it) and h_t of the layer below
+                    proto.done_ctr = ctr_of(l, t);
+                    if (t > 0) { proto.wait_ctr[0] = ctr_of(l, t - 1); proto.wait_need[0] = (uint32_t)ctx->lstm[l].n_tiles; }
+                    if (l > 0) { proto.wait_ctr[1] = ctr_of(l - 1, t); proto.wait_need[1] = (uint32_t)ctx->lstm[l - 1].n_tiles; }
+                }
                 EMPOSE_TRY(pl.book.add(ctx->lstm[l], a0, a1, proto, B, -1, &pl.lstm_diag[d]));
             }
+        if (ctx->round) {
+            // item table in wavefront order: diagonal by diagonal, row-tile units inside a diagonal, jobs inside a unit
+            pl.wave_unit_rows = tc_item_rows(mt_B, ctx->num_sms);
+            if (pl.wave_unit_rows < 0) return pl.wave_unit_rows;
+            const int units = ceil_div(B, pl.wave_unit_rows);
+            std::vector<int2> items;
+            for (const JobRange& dg : pl.lstm_diag)
+                for (int u = 0; u < units; ++u)
+                    for (int j = dg.begin; j < dg.begin + dg.count; ++j) items.push_back(make_int2(j, u));
+            int2* d_items;
+            EMPOSE_TRY(A.upload(items, &d_items));
+            pl.wave_items = d_items;
+            pl.wave_n_items = (int)items.size();
+        }
         // heads: theta0 | beta0 from the (masked) last-layer sequence
         GemmJob proto = linear_proto(ctx->heads, false, pl.dtheta, kPoseDim, kPoseDim + kBetas);
         proto.split = kPoseDim;
@@ -465,7 +489,27 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
                 EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.cstate[l], 0, st_bytes, s));
             }
         }
-        for (const JobRange& d : pl.lstm_diag) EMPOSE_TRY(run_jobs(ctx, pl, d, mt_B, s));
+        if (ctx->round && pl.wave_items && debug_options().lstm_persistent) {
+            // the whole wavefront (F + L - 1 diagonals) as ONE persistent launch; jobs order themselves through counters
+            ++ctx->last_launches;
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (ctx->profiling) {
+                if (ctx->prof_used == ctx->prof_events.size()) {
+                    cudaEvent_t a, b;
+                    EMPOSE_CUDA_TRY(cudaEventCreate(&a));
+                    EMPOSE_CUDA_TRY(cudaEventCreate(&b));
+                    ctx->prof_events.emplace_back(a, b);
+                }
+                ev0 = ctx->prof_events[ctx->prof_used].first; ev1 = ctx->prof_events[ctx->prof_used].second;
+                ++ctx->prof_used;
+                EMPOSE_CUDA_TRY(cudaEventRecord(ev0, s));
+            }
+            EMPOSE_TRY(tc_launch_items(pl.book.d_jobs, pl.book.d_maps, pl.wave_items, pl.wave_n_items, pl.wave_unit_rows, ++pl.wave_epoch,
+                                       mt_B, ctx->num_sms, s));
+            if (ev1) EMPOSE_CUDA_TRY(cudaEventRecord(ev1, s));
+        } else {
+            for (const JobRange& d : pl.lstm_diag) EMPOSE_TRY(run_jobs(ctx, pl, d, mt_B, s));
+        }
         EMPOSE_TRY(run_jobs(ctx, pl, pl.heads, mt_R, s));
         if (lstm_state)
             for (int l = 0; l < L; ++l) {

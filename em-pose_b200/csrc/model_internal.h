@@ -343,6 +343,12 @@ struct Plan {
     int32_t* in_len = nullptr;
     float *o_pose = nullptr, *o_shape = nullptr, *o_joints = nullptr;
     float* o_hist[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // the LSTM wavefront as ONE persistent launch (tc_launch_items): item table, per-(layer, step, row tile) completion
+    // counters and the number of launches that have used them
+    void* wave_items = nullptr;
+    int wave_n_items = 0, wave_unit_rows = 0;
+    uint32_t* wave_ctr = nullptr;
+    uint32_t wave_epoch = 0;
     // job ranges
     std::vector<JobRange> lstm_diag;
     JobRange heads, init_chain, iter_chain, pb, pbt;

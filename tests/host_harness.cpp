@@ -125,7 +125,7 @@ static void run_fan(const HostSub& h, const HostFan& hf, int n_frames, const flo
                     double* sensor_pos, double* sensor_ori, double* joints, double* g_theta, double* g_beta) {
     constexpr int RING = MAXD + 1;
     FanModel fm;
-    fm.ok = hf.ok; fm.slots = hf.slots; fm.max_deg = hf.max_deg; fm.n_part = hf.n_part;
+    fm.ok = hf.ok & 1; fm.slots = hf.slots; fm.max_deg = hf.max_deg; fm.n_part = hf.n_part;
     fm.deg = hf.deg; fm.helper = hf.helper; fm.n_joints = hf.n_joints; fm.part_ptr = hf.part_ptr; fm.joint = hf.joint;
     fm.weight = hf.weight; fm.jp_ptr = hf.jp_ptr; fm.jp_idx = hf.jp_idx;
     ResidualSpec spec;
@@ -172,10 +172,14 @@ static void run_fan(const HostSub& h, const HostFan& hf, int n_frames, const flo
         }
         for (int i = 0; i < 66; ++i) joints[f * 66 + i] = double(st.gpos[i / 3][i % 3]);
         if (!want_grad) continue;
-        for (int it = 0; it < kJoints * 12; ++it) jt_reduce(fm, st, var.data(), it);
+        auto state_of = [&](int) -> JointState<T>& { return st; };
+        auto var_of = [&](int) -> T* { return var.data(); };
+        if (hf.ok & 2) jt_reduce_frames<T>(fm, state_of, var_of, 1, 0, 1);          // the form the kernel runs
+        else for (int it = 0; it < kJoints * 12; ++it) jt_reduce(fm, st, var.data(), it);
         if (joint_up) for (int j = 0; j < kJoints; ++j) jt_joint_residual(st, joints_gt + f * kPoseDim, T(joint_weight), j);
         for (int r = 0; r < 3; ++r) { if (use_static) jt_chain_bwd_static(st, r, joint_up); else jt_chain_bwd(h.parents, st, r, joint_up); }
-        for (int i = 0; i < kJoints * 12; ++i) jt_local(h.parents, st, var.data(), i, joint_up);
+        if (hf.ok & 2) jt_local_frames<T>(h.parents, state_of, var_of, 1, 0, 1, joint_up);
+        else for (int i = 0; i < kJoints * 12; ++i) jt_local(h.parents, st, var.data(), i, joint_up);
         // the transposed GEMM: [dvp | dJ] against [P^T | 0], [S^T | Jdirs^T]
         T gt[kPoseDim];
         for (int j = 0; j < kJoints; ++j) jt_finish_theta(st, var.data(), T(coef[f]), gt, j);
@@ -204,7 +208,7 @@ extern "C" int host_fan_eval(const HostSub* h, const HostFan* hf, int n_frames, 
                              const int* active, int use_pos, int use_ori, const float* coef, int want_grad,
                              int use_double, int force_maxd, float sensor_weight, const float* joints_gt, float joint_weight,
                              double* sensor_pos, double* sensor_ori, double* joints, double* g_theta, double* g_beta) {
-    if (!hf->ok || h->vp_dim > kMaxVp) return -1;
+    if (!(hf->ok & 1) || h->vp_dim > kMaxVp) return -1;
     int maxd = force_maxd > 0 ? force_maxd : hf->max_deg;
 #define EMPOSE_RUN_FAN(T, S, D)                                                                                                  \
     run_fan<T, S, D>(*h, *hf, n_frames, theta, beta, off_r, off_t, meas_pos, meas_ori, active, use_pos, use_ori, coef, want_grad, \

@@ -84,7 +84,7 @@ class HostFan(ctypes.Structure):
 
 def fan_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef, use_pos=True, use_ori=True,
              want_grad=True, use_double=False, static_tree=True, sensor_weight=1.0, joints_gt=None, joint_weight=0.0,
-             force_maxd=0):
+             force_maxd=0, cta_forms=True):
     """The fan-form pass (csrc/fan_math.h, what the production kernel runs) on the host; same contract as frame_eval."""
     keep = []
     hs = HostSub()
@@ -103,6 +103,8 @@ def fan_eval(sub, theta, beta, off_r, off_t, meas_pos, meas_ori, active, coef, u
     hs.use_static_tree = int(static_tree)
     hf = HostFan()
     hf.ok, hf.slots, hf.max_deg, hf.n_part = [int(v) for v in sub['sub.fan_dims']]
+    if cta_forms:
+        hf.ok |= 2          # reduce / local gradients in the "thread owns an item of every frame" form the kernel runs
     for field, key in (('deg', 'sensor_degree'), ('helper', 'fan_helper'), ('n_joints', 'fan_n_joints'),
                        ('part_ptr', 'fan_part_ptr'), ('joint', 'fan_joint'), ('jp_ptr', 'fan_jp_ptr'), ('jp_idx', 'fan_jp_idx')):
         a = np.ascontiguousarray(sub['sub.' + key], dtype=np.int32)
