@@ -291,6 +291,34 @@ __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 64 accumulator columns in ONE instruction: half as many waits per column as two x32 reads
+__device__ __forceinline__ void tmem_load_64cols(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Register budgets of the warp roles (setmaxnreg): the four single-thread / idle warps hand registers to the eight epilogue
+// warps, whose 64-column chunks keep the accumulator read, the bias and two packed halves live.  168 * 384 = 40 * 128 + 232 * 256.
+constexpr int kRegsControl = 72;
+constexpr int kRegsEpilogue = 216;
+
 template <class View>
 __device__ __forceinline__ int job_chunk_k(const View& j) { return j.in_half ? kChunkKHalf : kChunkK; }
 template <class View>
@@ -374,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     const uint32_t tmem_base = ctl->tmem_base;
 
     if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
         // ================= TMA producer (whole warp, one elected lane issues) =================
         {
             uint32_t stage = 0, phase = 0, items_done = 0;
@@ -447,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
             }
         }
     } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
         // ================= MMA issuer (whole warp, one elected lane issues) =================
         if (!(kPair && crank != 0)) {
             uint32_t stage = 0, phase = 0, seq = 0;
@@ -509,7 +539,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));       // warps 2, 3: the rest of warpgroup 0
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
         // ================= epilogue =================
         const int ew = warp - 4;
         const int quad = ew & 3;                  // TMEM lanes 32*quad .. 32*quad+31 (a warp may only touch its own quadrant)
@@ -562,6 +595,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 //  issued before the current chunk is staged.  With the read's registers live across the loop ptxas feeds the
                 //  eight bias loads one by one into the additions: 11 % slower on a [131072 x 512] . [512 x 512] layer.)
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                    if (c0 + 64 <= lv.fast_cols && c0 + 64 <= c_end && !(debug_mode & 1024)) {
+                        // fp16 linear jobs, 64 columns at a time: ONE accumulator read (one wait) per 64 columns, the bias
+                        // loads of both halves in flight meanwhile, two independent pack / stage / store sequences
+                        float v2[64], b0[32], b1[32];
+                        linear_half_load_bias(lv, c0, b0);
+                        linear_half_load_bias(lv, c0 + 32, b1);
+                        tmem_load_64cols(taddr + (uint32_t)c0, v2);
+                        if (!(debug_mode & 4)) {
+                            uint32_t pk[16];
+                            linear_half_pack(lv, *reinterpret_cast<const float(*)[32]>(&v2[0]), b0, pk);
+                            linear_half_store(lv, row0, lane, c0, pk, my_stage, (debug_mode & 16) != 0);
+                            linear_half_pack(lv, *reinterpret_cast<const float(*)[32]>(&v2[32]), b1, pk);
+                            linear_half_store(lv, row0, lane, c0 + 32, pk, my_stage, (debug_mode & 16) != 0);
+                        }
+                        c0 += 32;
+                        continue;
+                    }
                     float v[32];
                     if (c0 + 32 <= lv.fast_cols) {
                         float bias[32];

@@ -41,6 +41,19 @@ using namespace empose;
 namespace empose {
 namespace {
 
+// Evict least-recently-used plans, one at a time, until fewer than `limit` remain -- but never a plan the current C-ABI
+// call has already used (last_use > call_clock): its kernels / copies may still be in flight.
+template <typename Map>
+void evict_lru(Map& plans, size_t limit, uint64_t call_clock) {
+    while (plans.size() >= limit) {
+        auto victim = plans.end();
+        for (auto it = plans.begin(); it != plans.end(); ++it)
+            if (it->second->last_use <= call_clock && (victim == plans.end() || it->second->last_use < victim->second->last_use)) victim = it;
+        if (victim == plans.end()) return;          // everything belongs to this call: let the cache grow
+        plans.erase(victim);
+    }
+}
+
 int run_jobs(empose_ief* ctx, Plan& pl, const JobRange& r, int m_tiles, cudaStream_t s) {
     if (r.count == 0) return EMPOSE_OK;
     if (ctx->round) {
@@ -103,8 +116,8 @@ int build_mlp_pair(empose_ief* ctx, Plan& pl, const MlpPacked& mp, const MlpPack
 int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
     auto key = std::make_tuple(B, F, slot);
     auto it = ctx->plans.find(key);
-    if (it != ctx->plans.end()) { *out = it->second.get(); return EMPOSE_OK; }
-    if (ctx->plans.size() >= 8) ctx->plans.clear();      // bound the workspace kept alive
+    if (it != ctx->plans.end()) { it->second->last_use = ++ctx->plan_clock; *out = it->second.get(); return EMPOSE_OK; }
+    evict_lru(ctx->plans, 8, ctx->call_clock);            // bound the workspace kept alive
     std::unique_ptr<Plan> plp(new Plan());
     Plan& pl = *plp;
     const empose_ief_config& cfg = ctx->cfg;
@@ -222,14 +235,15 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
     EMPOSE_TRY(add_blend_transposed_jobs(pl.book, ctx, pl.dvp, pl.dj, pl.dpf, R, &pl.pbt));
     EMPOSE_TRY(pl.book.finalize(A));
     *out = plp.get();
+    plp->last_use = ++ctx->plan_clock;
     ctx->plans[key] = std::move(plp);
     return EMPOSE_OK;
 }
 
 int project_plan(empose_ief* ctx, int R, Plan** out) {
     auto it = ctx->project_plans.find(R);
-    if (it != ctx->project_plans.end()) { *out = it->second.get(); return EMPOSE_OK; }
-    if (ctx->project_plans.size() >= 4) ctx->project_plans.clear();
+    if (it != ctx->project_plans.end()) { it->second->last_use = ++ctx->plan_clock; *out = it->second.get(); return EMPOSE_OK; }
+    evict_lru(ctx->project_plans, 4, ctx->call_clock);
     std::unique_ptr<Plan> plp(new Plan());
     Plan& pl = *plp;
     pl.R = R; pl.B = R; pl.F = 1;
@@ -241,6 +255,7 @@ int project_plan(empose_ief* ctx, int R, Plan** out) {
     EMPOSE_TRY(add_blend_jobs(pl.book, ctx, pl.pf, pl.vpoff, pl.jrest, R, &pl.pb));
     EMPOSE_TRY(pl.book.finalize(pl.arena));
     *out = plp.get();
+    plp->last_use = ++ctx->plan_clock;
     ctx->project_plans[R] = std::move(plp);
     return EMPOSE_OK;
 }
@@ -598,6 +613,7 @@ int check_call(empose_ief* ctx, int B, int F) {
     if (ctx->sensors_only && F != 1) { set_last_error("this context was made by empose_sensors_create: it only projects sensors"); return EMPOSE_E_ARG; }
     if (B < 1 || F < 1 || (int64_t)B * F > (int64_t)1 << 26) { set_last_error("B and F must be positive (and B*F <= 2^26)"); return EMPOSE_E_ARG; }
     EMPOSE_CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    ctx->call_clock = ctx->plan_clock;          // plans touched from here on belong to this call (evict_lru)
     return EMPOSE_OK;
 }
 

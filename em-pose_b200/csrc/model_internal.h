@@ -325,6 +325,7 @@ inline GemmJob linear_proto(const PackedMatrix& W, bool round, float* out, int64
 // ---- the inference plan and the model context (model.cu) ------------------------------------------
 struct Plan {
     int B = 0, F = 0, R = 0;
+    uint64_t last_use = 0;      // plan-cache clock value of the call that used this plan last (LRU eviction)
     Arena arena;
     JobBook book;
     // workspace
@@ -377,6 +378,11 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
     PackedMatrix pb, pbt;
     std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;     // (B, F, slot): slots > 0 serve the pipelined host path
     std::map<int, std::unique_ptr<Plan>> project_plans;
+    // Plan cache policy: at most kMaxPlans / kMaxProjectPlans workspaces stay alive; the least recently used one is
+    // evicted, one at a time, and never one that the current C-ABI call has already touched (its work may be in flight:
+    // cudaFree would serialise the copy / compute overlap of the chunked host entry point).
+    uint64_t plan_clock = 0;    // incremented per plan lookup
+    uint64_t call_clock = 0;    // plan_clock at the start of the current C-ABI call
     int64_t last_launches = 0;
     // optional per-launch timing of the GEMM executor (empose_ief_set_profiling)
     bool profiling = false;
