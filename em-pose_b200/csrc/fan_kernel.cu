@@ -35,7 +35,7 @@ struct FanCfg {
     static_assert(kChainThreads <= kThreads, "chain lanes must fit the CTA");
 };
 
-__device__ __forceinline__ float maybe_round(float x, int round_out) { return round_out ? round_tf32(x) : x; }
+__device__ __forceinline__ float grad_operand_f32(float x, int mode) { return mode == OPERAND_TF32 ? round_tf32(x) : x; }
 
 template <int SLOTS, int MAXD, int G, int CTAS>
 __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_kernel(MainParams p, int frame_bytes) {
@@ -125,15 +125,22 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
             for (int i = 0; i < 9; ++i) p.sensor_ori[row * 108 + s * 9 + i] = out_ori[i];
         }
         if (grad) {         // the whole sensor block, padding columns as zeros (K of the transposed blend GEMM)
-            float4* dst = reinterpret_cast<float4*>(p.dvp + row * p.sub.vp_dim + s * (SLOTS * 3));
+            const int mode = p.round_out;
+            auto val = [&](int i) { return i < RING * 3 ? grad_operand_f32(dvp[i < RING * 3 ? i : 0], mode) : 0.0f; };
+            if (mode == OPERAND_F16) {      // fp16 elements of value * kDvpScale, four per store
+                uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.dvp) + row * p.sub.vp_dim + s * (SLOTS * 3));
 #pragma unroll
-            for (int i = 0; i < Cfg::kBlockVec; ++i) {
-                float4 v;
-                v.x = 4 * i < RING * 3 ? maybe_round(dvp[4 * i < RING * 3 ? 4 * i : 0], p.round_out) : 0.0f;
-                v.y = 4 * i + 1 < RING * 3 ? maybe_round(dvp[4 * i + 1 < RING * 3 ? 4 * i + 1 : 0], p.round_out) : 0.0f;
-                v.z = 4 * i + 2 < RING * 3 ? maybe_round(dvp[4 * i + 2 < RING * 3 ? 4 * i + 2 : 0], p.round_out) : 0.0f;
-                v.w = 4 * i + 3 < RING * 3 ? maybe_round(dvp[4 * i + 3 < RING * 3 ? 4 * i + 3 : 0], p.round_out) : 0.0f;
-                dst[i] = v;
+                for (int i = 0; i < Cfg::kBlockVec; ++i) {
+                    const __half2 a = __floats2half2_rn(val(4 * i) * kDvpScale, val(4 * i + 1) * kDvpScale);
+                    const __half2 b = __floats2half2_rn(val(4 * i + 2) * kDvpScale, val(4 * i + 3) * kDvpScale);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&b);
+                    dst[i] = pk;
+                }
+            } else {
+                float4* dst = reinterpret_cast<float4*>(p.dvp + row * p.sub.vp_dim + s * (SLOTS * 3));
+#pragma unroll
+                for (int i = 0; i < Cfg::kBlockVec; ++i) dst[i] = make_float4(val(4 * i), val(4 * i + 1), val(4 * i + 2), val(4 * i + 3));
             }
         }
     }
@@ -171,10 +178,12 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
         jt_finish_theta(state(f), var_of(f), p.coef[row0 + f], p.gtheta_part + (row0 + f) * kPoseDim, idx - f * kJoints);
     }
     {
-        float* dst = p.dj + row0 * kJrestLd;
-        for (int idx = tid; idx < nf * kJrestLd; idx += NT) {
-            const int f = idx / kJrestLd, c = idx - f * kJrestLd;
-            dst[idx] = c < kPoseDim ? maybe_round(var_of(f)[kJoints * 9 + c], p.round_out) : 0.0f;
+        const int ld = p.dj_ld;
+        for (int idx = tid; idx < nf * ld; idx += NT) {
+            const int f = idx / ld, c = idx - f * ld;
+            const float v = c < kPoseDim ? var_of(f)[kJoints * 9 + c] : 0.0f;
+            if (p.round_out == OPERAND_F16) reinterpret_cast<__half*>(p.dj)[row0 * ld + idx] = __float2half_rn(v * kDvpScale);
+            else p.dj[row0 * ld + idx] = grad_operand_f32(v, p.round_out);
         }
     }
 }

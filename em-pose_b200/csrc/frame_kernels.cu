@@ -14,23 +14,32 @@ namespace {
 
 __device__ __forceinline__ float maybe_round(float x, int round_out) { return round_out ? round_tf32(x) : x; }
 
-// one value of a feature row of the blend GEMM, optionally split into a tf32 value and its tf32 residual (3xTF32)
-__device__ __forceinline__ void write_feature(float v, float* dst, int split) {
-    if (split) {
+// Column `col` of a feature row of the blend GEMM (`row` points at the row's first element), in the operand mode of
+// the GEMM: plain fp32; tf32 value | tf32 residual (3xTF32); fp16 value | fp16 (residual * 2^11) (3xFP16).  Both
+// splits carry 22 mantissa bits; the second half of the row starts kPoseFeatPad elements in.
+__device__ __forceinline__ void write_feature(float v, float* row, int col, int mode) {
+    if (mode == OPERAND_F16) {
+        __half* h = reinterpret_cast<__half*>(row);
+        const __half hi = __float2half_rn(v);
+        h[col] = hi;
+        h[kPoseFeatPad + col] = __float2half_rn((v - __half2float(hi)) * kSplitLoScale);
+    } else if (mode == OPERAND_TF32) {
         const float hi = round_tf32(v);
-        dst[0] = hi;
-        dst[kPoseFeatPad] = round_tf32(v - hi);
+        row[col] = hi;
+        row[kPoseFeatPad + col] = round_tf32(v - hi);
     } else {
-        dst[0] = v;
+        row[col] = v;
     }
 }
-// pose features of one joint: vec(R - I)
-__device__ __forceinline__ void write_pose_features(const float* r, float* dst, int split) {
+// pose features of one joint: vec(R - I) into columns [col0, col0 + 9)
+__device__ __forceinline__ void write_pose_features(const float* r, float* row, int col0, int mode) {
     float R[9];
     rodrigues_fwd(r, R);
 #pragma unroll
-    for (int e = 0; e < 9; ++e) write_feature(R[e] - ((e % 4 == 0) ? 1.0f : 0.0f), dst + e, split);
+    for (int e = 0; e < 9; ++e) write_feature(R[e] - ((e % 4 == 0) ? 1.0f : 0.0f), row, col0 + e, mode);
 }
+// value headed for the transposed blend GEMM: dE/dvp or dE/dJ in the GEMM's operand mode
+__device__ __forceinline__ float grad_operand_f32(float x, int mode) { return mode == OPERAND_TF32 ? round_tf32(x) : x; }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prepare_kernel(PrepareParams p) {
@@ -124,19 +133,20 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) 
             if (p.xiter) store_operand(p.xiter, (g0 + f) * p.iter_stride + p.in_size + kPoseDim + k, v, p.operand_mode);
         }
         __syncthreads();
-        const int row_floats = p.pf_stride;                              // 192, or 384 when split into hi | lo
+        // a row is pf_stride elements of 4 bytes (fp32 / tf32) or 2 bytes (fp16); rows of the group are adjacent in the tile
+        const int row_words = p.pf_split == OPERAND_F16 ? p.pf_stride / 2 : p.pf_stride;
         for (int i = tid; i < nf * (kJoints - 1); i += kUpdateThreads) {
             const int f = i / (kJoints - 1), j = 1 + i - f * (kJoints - 1);
-            write_pose_features(&th[f][j * 3], tile + f * row_floats + (j - 1) * 9, p.pf_split);
+            write_pose_features(&th[f][j * 3], tile + f * row_words, (j - 1) * 9, p.pf_split);
         }
         for (int i = tid; i < nf * kBetas; i += kUpdateThreads) {            // shape columns of the feature row
             const int f = i / kBetas, k = i - f * kBetas;
-            write_feature(be[f][k], tile + f * row_floats + kFeatBeta + k, p.pf_split);
+            write_feature(be[f][k], tile + f * row_words, kFeatBeta + k, p.pf_split);
         }
         __syncthreads();
-        float4* dst = reinterpret_cast<float4*>(p.pf + g0 * row_floats);
+        float4* dst = reinterpret_cast<float4*>(p.pf + g0 * row_words);
         const float4* src = reinterpret_cast<const float4*>(tile);
-        for (int i = tid; i < nf * row_floats / 4; i += kUpdateThreads) dst[i] = src[i];
+        for (int i = tid; i < nf * row_words / 4; i += kUpdateThreads) dst[i] = src[i];
         __syncthreads();
     }
 }
@@ -148,8 +158,9 @@ __global__ void __launch_bounds__(256) pose_feature_kernel(const float* __restri
     const int64_t row = i / (kJoints - 1);
     const int j = 1 + (int)(i % (kJoints - 1));
     float r[3] = {theta[row * kPoseDim + j * 3], theta[row * kPoseDim + j * 3 + 1], theta[row * kPoseDim + j * 3 + 2]};
-    write_pose_features(r, pf + row * pf_stride + (j - 1) * 9, pf_split);
-    if (j <= kBetas) write_feature(beta[row * kBetas + j - 1], pf + row * pf_stride + kFeatBeta + j - 1, pf_split);
+    float* frow = pf + row * (pf_split == OPERAND_F16 ? pf_stride / 2 : pf_stride);
+    write_pose_features(r, frow, (j - 1) * 9, pf_split);
+    if (j <= kBetas) write_feature(beta[row * kBetas + j - 1], frow, kFeatBeta + j - 1, pf_split);
 }
 
 __global__ void pack_offsets_kernel(const float* __restrict__ offset_r, const float* __restrict__ offset_t, float* __restrict__ packed, int n) {
@@ -205,17 +216,24 @@ __device__ __forceinline__ void cta_skin_bwd_reduce(const SubModel& m, FrameStat
 // dE/dvp rows -> global memory, 16 bytes at a time (columns beyond 3 n_verts are zero: they are K padding of the
 // transposed pose-blend GEMM)
 template <int VP>
-__device__ __forceinline__ void cta_store_dvp(const SubModel& m, FrameState<float, VP>* st, float* dvp, int64_t row0, int nf, int round_out) {
+__device__ __forceinline__ void cta_store_dvp(const SubModel& m, FrameState<float, VP>* st, float* dvp, int64_t row0, int nf, int mode) {
     const int q = m.vp_dim / 4, nv3 = m.n_verts * 3;
     for (int idx = threadIdx.x; idx < nf * q; idx += kMainThreads) {
         const int f = idx / q, t = idx - f * q;
         float4 v = reinterpret_cast<const float4*>(st[f].dx)[t];
         const int i = t * 4;
-        v.x = i < nv3 ? maybe_round(v.x, round_out) : 0.0f;
-        v.y = i + 1 < nv3 ? maybe_round(v.y, round_out) : 0.0f;
-        v.z = i + 2 < nv3 ? maybe_round(v.z, round_out) : 0.0f;
-        v.w = i + 3 < nv3 ? maybe_round(v.w, round_out) : 0.0f;
-        reinterpret_cast<float4*>(dvp + (row0 + f) * m.vp_dim)[t] = v;
+        v.x = i < nv3 ? grad_operand_f32(v.x, mode) : 0.0f;
+        v.y = i + 1 < nv3 ? grad_operand_f32(v.y, mode) : 0.0f;
+        v.z = i + 2 < nv3 ? grad_operand_f32(v.z, mode) : 0.0f;
+        v.w = i + 3 < nv3 ? grad_operand_f32(v.w, mode) : 0.0f;
+        if (mode == OPERAND_F16) {
+            const __half2 a = __floats2half2_rn(v.x * kDvpScale, v.y * kDvpScale), b = __floats2half2_rn(v.z * kDvpScale, v.w * kDvpScale);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&b);
+            reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dvp) + (row0 + f) * m.vp_dim)[t] = pk;
+        } else {
+            reinterpret_cast<float4*>(dvp + (row0 + f) * m.vp_dim)[t] = v;
+        }
     }
 }
 
@@ -321,8 +339,11 @@ __global__ void __launch_bounds__(kMainThreads, kMainCtasPerSm) main_kernel(Main
     EMPOSE_TICK(12);
     EMPOSE_FOR_ITEMS(kJoints, f, i)
         item_finish_theta(st[f], p.coef[row0 + f], (const float*)nullptr, p.gtheta_part + (row0 + f) * kPoseDim, i);
-    EMPOSE_FOR_FRAME_ITEMS(kJrestLd, f, i)
-        p.dj[(row0 + f) * kJrestLd + i] = i < kPoseDim ? maybe_round(st[f].dj[i / 3][i % 3], p.round_out) : 0.0f;
+    EMPOSE_FOR_FRAME_ITEMS(p.dj_ld, f, i) {
+        const float v = i < kPoseDim ? st[f].dj[i / 3][i % 3] : 0.0f;
+        if (p.round_out == OPERAND_F16) reinterpret_cast<__half*>(p.dj)[(row0 + f) * p.dj_ld + i] = __float2half_rn(v * kDvpScale);
+        else p.dj[(row0 + f) * p.dj_ld + i] = grad_operand_f32(v, p.round_out);
+    }
     EMPOSE_TICK(13);
 }
 
@@ -431,6 +452,8 @@ DebugOptions& debug_options() {
         o.fan_variant = e ? atoi(e) : 0;
         e = getenv("EMPOSE_LSTM_PERSISTENT");
         o.lstm_persistent = e ? atoi(e) : 1;
+        e = getenv("EMPOSE_BLEND_FP16");
+        o.blend_fp16 = e ? atoi(e) : 1;
         return o;
     }();
     return opt;

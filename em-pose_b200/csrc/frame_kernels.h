@@ -44,7 +44,8 @@ struct UpdateParams {
     int in_size, iter_stride;
     float* pf;                  // [R][pf_stride] feature rows; split: [hi(kPoseFeatPad) | lo(kPoseFeatPad)]
     int pf_stride;              // kPoseFeatPad, or twice that when split
-    int pf_split;               // 1: write tf32 hi part and tf32 residual (error-compensated pose-blend GEMM)
+    int pf_split;               // OperandMode of the feature rows: OPERAND_F32 plain fp32; OPERAND_TF32 tf32 hi | tf32 residual;
+                                // OPERAND_F16 fp16 hi | fp16 (residual * 2^11) (error-compensated blend GEMM)
     float* hist_pose;           // [R][66] or null
     float* hist_shape;          // [R][10] or null
 };
@@ -72,7 +73,8 @@ struct MainParams {
     const float* coef;          // [R]      (grad only)
     int R;
     int want_grad;
-    int round_out;
+    int round_out;              // OperandMode of dvp / dj: fp32, tf32-rounded fp32, or fp16 elements holding value * kDvpScale
+    int dj_ld;                  // row pitch of dj in elements (kJrestLd, or kDjLdHalf for fp16)
     int static_tree;            // 1: sub.parents is the standard SMPL body tree -> register-resident chain phases
     long long* ticks;           // development aid: per-phase clock64() samples of one CTA, or null
     float* sensor_pos;          // [R][36] or null
@@ -85,7 +87,7 @@ struct MainParams {
     float joint_weight;
 };
 // development switches (empose_set_option; the environment variables EMPOSE_MAIN_GENERAL / EMPOSE_FAN_VARIANT seed them)
-struct DebugOptions { int main_general; int fan_variant; int lstm_persistent; };
+struct DebugOptions { int main_general; int fan_variant; int lstm_persistent; int blend_fp16; };
 DebugOptions& debug_options();
 
 int launch_main(const MainParams& p, cudaStream_t s);          // dispatches on p.fan.ok (option main_general forces the general kernel)

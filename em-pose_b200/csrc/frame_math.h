@@ -44,6 +44,12 @@ constexpr int kFeatK = 202;           // real K of the blend GEMM
 constexpr int kPoseFeatPad = 224;     // padded K
 // The transposed contraction returns [dE/dpf (189) | 0 0 0 | dE/dbeta (10)] per frame in rows of kPoseFeatPad floats.
 constexpr int kJrestLd = 68;          // row pitch of the rest-joint / dE/dJ buffers (66 values, 16-byte aligned rows)
+constexpr int kDjLdHalf = 72;         // row pitch of the dE/dJ buffer when it holds fp16 elements
+// fp16 form of the blend GEMMs: a value x is split as hi = fp16(x), lo = fp16((x - hi) * 2^11) -- 22 mantissa bits, like the
+// tf32 split, at twice the tensor rate and half the bytes; the weights carry the matching 2^-11 (model.cu).  dE/dvp and
+// dE/dJ (hundreds at most: 1 / edge length) are stored times kDvpScale so that even a very fine mesh stays inside fp16.
+constexpr float kSplitLoScale = 2048.0f;
+constexpr float kDvpScale = 0.125f;
 constexpr int kMaxVp = 448;           // padded 3*Vs, supports sub-meshes of up to 144 vertices (12 sensors x 12 slots)
 constexpr int kMaxDegree = 12;
 constexpr int kSplitDegree = 7;        // sensor valence up to which the sensor phase is split over (sensor, face) items

@@ -53,6 +53,8 @@ struct GemmJob {
     const float* bias;       // indexed by global column (n_begin + c); may be null
     int32_t has_act;
     float prelu_alpha;
+    float out_scale;         // accumulator scale applied before the bias (0 or 1: none); the fp16 blend GEMMs keep their
+                             // operands in range with power-of-two factors and undo them here
     int32_t n_valid;         // columns >= n_valid (global index) are discarded
     float* out;              // columns [0, split)
     int64_t out_stride;
@@ -137,7 +139,7 @@ struct LinearHalfView {
 };
 __device__ __forceinline__ LinearHalfView linear_half_view(const GemmJob& j, int row0, int lane) {
     LinearHalfView lv;
-    const bool ok = j.epi == EPI_LINEAR && j.out_half && !j.res;
+    const bool ok = j.epi == EPI_LINEAR && j.out_half && !j.res && (j.out_scale == 0.0f || j.out_scale == 1.0f);
     const int n_begin = j.n_begin;
     lv.fast_cols = ok ? min(j.n_valid, j.split) - n_begin : 0;
     lv.out = reinterpret_cast<__half*>(j.out) + j.out_col0 + n_begin;
@@ -243,7 +245,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
 #pragma unroll
         for (int i = 0; i < 32; ++i) bias[i] = 0.0f;
     }
-    if (j.epi == EPI_LINEAR && j.out_half && !j.res && n0 + 32 <= j.n_valid && n0 + 32 <= j.split) {
+    if (j.epi == EPI_LINEAR && j.out_half && !j.res && n0 + 32 <= j.n_valid && n0 + 32 <= j.split &&
+        (j.out_scale == 0.0f || j.out_scale == 1.0f)) {
         // fp16 activations (the tcgen05 executor builds the view once per job and calls linear_half_chunk directly)
         const LinearHalfView lv = linear_half_view(j, row0, lane);
         linear_half_chunk(lv, row0, lane, c0, v, bias, stage, no_store);
@@ -365,15 +368,51 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
                 *reinterpret_cast<uint4*>(hout) = __ldcg(reinterpret_cast<const uint4*>(hprev));
             }
         }
+    } else if (j.epi == EPI_LINEAR && !j.out_half && !j.res && !j.has_act && !j.mask_rows && n0 + 32 <= j.n_valid &&
+               (n0 >= j.split || n0 + 32 <= j.split) &&
+               ((n0 >= j.split ? ((n0 - j.split) | (int)j.out2_stride) : ((j.out_col0 + n0) | (int)j.out_stride)) & 3) == 0) {
+        // fp32 outputs of a plain contraction (the blend GEMMs), a whole chunk on one side of `split`, 16-byte aligned rows:
+        // two passes of 16 columns through the staging tile ([32 rows][64 B], 80-byte pitch: conflict-free 128-bit
+        // accesses), written out 8 rows x 64 B per instruction -- 24 memory instructions per chunk instead of 96.
+        const float scale = j.out_scale != 0.0f ? j.out_scale : 1.0f;
+        const int round_out = j.round_out;
+        float* dst;
+        int64_t stride;
+        if (n0 >= j.split) { dst = j.out2 + (n0 - j.split); stride = j.out2_stride; }
+        else { dst = j.out + j.out_col0 + n0; stride = j.out_stride; }
+        const int rows = no_store ? 0 : j.m_rows - row0;
+        const uint32_t tile = smem_addr_of(stage);
+#pragma unroll
+        for (int hcol = 0; hcol < 32; hcol += 16) {
+            float y[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                y[i] = fmaf(v[hcol + i], scale, bias[hcol + i]);
+                if (round_out) y[i] = round_tf32(y[i]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sts128f(tile + lane * 80 + q * 16, make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]));
+            __syncwarp();
+            float4 val[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) val[it] = lds128f(tile + (it * 8 + (lane >> 2)) * 80 + (lane & 3) * 16);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int r = it * 8 + (lane >> 2);
+                if (r < rows) *reinterpret_cast<float4*>(dst + (int64_t)(row0 + r) * stride + hcol + (lane & 3) * 4) = val[it];
+            }
+            __syncwarp();
+        }
     } else if (j.epi == EPI_LINEAR) {
         if (j.mask_rows && row < j.m_rows && (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window]) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.0f;
         }
         const float alpha = j.has_act ? j.prelu_alpha : 1.0f;
+        const float scale = j.out_scale != 0.0f ? j.out_scale : 1.0f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            float y = v[i] + bias[i];
+            float y = fmaf(v[i], scale, bias[i]);
             y = y > 0.0f ? y : alpha * y;
             v[i] = y;
         }

@@ -148,7 +148,7 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
     EMPOSE_TRY(A.alloc_n(Rz * kPoseFeatPad, &pl.dpf));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.gth_part));
     EMPOSE_TRY(A.alloc_n(Rz * kJrestLd, &pl.jrest));
-    EMPOSE_TRY(A.alloc_n(Rz * kJrestLd, &pl.dj, true));
+    EMPOSE_TRY(A.alloc_n(Rz * ctx->dj_ld, &pl.dj, true));
     EMPOSE_TRY(A.alloc_n((size_t)B * 144, &pl.offsets));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.joints));
     EMPOSE_TRY(A.alloc_n(Rz * 36, &pl.spos));
@@ -405,7 +405,35 @@ int upload_submodel(IefData* ctx, const TensorTable& tt) {
             bf[i] = J0[i - vp];
         }
     }
-    if (ctx->round) {
+    // power-of-two factor that brings the largest entry of a matrix to ~2^9 (fp16 operands: exact, no overflow, and the
+    // 2^-11 of the split stays far above the subnormal range)
+    auto pow2_scale = [](const float* w, size_t n) {
+        float mx = 0.0f;
+        for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(w[i]));
+        if (!(mx > 0.0f)) return 1.0f;
+        return std::ldexp(1.0f, 9 - (int)std::ceil(std::log2(mx)));
+    };
+    auto f16r = [](float x) { return __half2float(__float2half_rn(x)); };
+    if (ctx->blend_half) {
+        // Error-compensated blend on fp16 operands (3xFP16), by K-concatenation like the tf32 form below: the feature row
+        // holds x_hi = fp16(x) and x_lo = fp16((x - x_hi) 2^11); with W' = s W split the same way,
+        //   [x_hi | x_lo | x_hi] . [W'_hi | W'_hi 2^-11 | W'_lo 2^-11]^T = s (x_hi W_hi + (x - x_hi) W_hi + x_hi (W - W_hi)),
+        // accumulated in fp32 and multiplied by 1/s in the epilogue, where the fp32 bias (template / J0) is added.
+        const float sc = pow2_scale(wf.data(), wf.size());
+        std::vector<float> w0((size_t)n_fwd * 2 * kPoseFeatPad, 0.0f), w1((size_t)n_fwd * kFeatK, 0.0f);
+        for (int i = 0; i < n_fwd; ++i)
+            for (int k = 0; k < kFeatK; ++k) {
+                const float v = wf[(size_t)i * kFeatK + k] * sc;
+                const float hi = f16r(v);
+                w0[(size_t)i * 2 * kPoseFeatPad + k] = hi;
+                w0[(size_t)i * 2 * kPoseFeatPad + kPoseFeatPad + k] = f16r(hi / kSplitLoScale);
+                w1[(size_t)i * kFeatK + k] = f16r(f16r((v - hi) * kSplitLoScale) / kSplitLoScale);
+            }
+        EMPOSE_TRY(pack_matrix(ctx->arena, n_fwd, 2 * kPoseFeatPad, kFeatK, 16, OPERAND_F16, true, [&](int r) {
+            return RowSource{&w0[(size_t)r * 2 * kPoseFeatPad], &w1[(size_t)r * kFeatK], 1.0, (double)bf[r]};
+        }, &ctx->pb));
+        ctx->pb.out_scale = 1.0f / sc;
+    } else if (ctx->round) {
         // Error-compensated (3xTF32) blend by K-concatenation: with x = x_hi + x_lo (both tf32),
         //   [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]^T = x_hi W_hi + x_lo W_hi + x_hi W_lo.
         // The vertex offsets feed cross products of ~1 cm mesh edges, which amplify plain TF32 rounding
@@ -428,12 +456,17 @@ int upload_submodel(IefData* ctx, const TensorTable& tt) {
     }
     // transposed: output column n < 189 is dE/dpf_n = sum_i P[n][i] dvp_i, column kFeatBeta + b is
     //             dE/dbeta_b = sum_i S[b][i] dvp_i + sum_c Jdirs[b][c] dJ_c; K = [dvp (vp_dim) | dJ (66)].
+    // Single pass: tf32 operands, or (blend_half) fp16 operands -- the same 11 significant bits -- with the weights times a
+    // power of two and dvp / dJ times kDvpScale, both undone by the epilogue.
     std::vector<float> zero_v(vp, 0.0f), zero_j(kPoseDim, 0.0f);
-    EMPOSE_TRY(pack_matrix(ctx->arena, kFeatK, vp, kPoseDim, 16, ctx->round ? OPERAND_TF32 : OPERAND_F32, false, [&](int r) {
-        if (r < kPoseFeat) return RowSource{P + (size_t)r * vp, zero_j.data(), 1.0, 0.0};
+    float st = 1.0f;
+    if (ctx->blend_half) st = std::min(std::min(pow2_scale(P, (size_t)kPoseFeat * vp), pow2_scale(S, (size_t)kBetas * vp)), pow2_scale(JD, (size_t)kBetas * kPoseDim));
+    EMPOSE_TRY(pack_matrix(ctx->arena, kFeatK, vp, kPoseDim, 16, blend_operand_mode(ctx), false, [&](int r) {
+        if (r < kPoseFeat) return RowSource{P + (size_t)r * vp, zero_j.data(), (double)st, 0.0};
         if (r < kFeatBeta) return RowSource{zero_v.data(), zero_j.data(), 1.0, 0.0};
-        return RowSource{S + (size_t)(r - kFeatBeta) * vp, JD + (size_t)(r - kFeatBeta) * kPoseDim, 1.0, 0.0};
+        return RowSource{S + (size_t)(r - kFeatBeta) * vp, JD + (size_t)(r - kFeatBeta) * kPoseDim, (double)st, 0.0};
     }, &ctx->pbt));
+    if (ctx->blend_half) ctx->pbt.out_scale = 1.0f / (st * kDvpScale);
     return EMPOSE_OK;
 }
 
@@ -542,7 +575,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         up.step = cfg.step_size; up.first = (it == 0); up.average_shape = cfg.average_shape;
         up.B = B; up.F = F; up.operand_mode = ctx->op_mode;
         up.xiter = pl.xiter; up.in_size = ctx->in_size; up.iter_stride = ctx->iter_stride; up.pf = pl.pf;
-        up.pf_stride = ctx->pf_stride; up.pf_split = rnd;
+        up.pf_stride = ctx->pf_stride; up.pf_split = blend_operand_mode(ctx);
         if (hist && hist->pose) up.hist_pose = hist->pose + (size_t)it * R * kPoseDim;
         if (hist && hist->shape) up.hist_shape = hist->shape + (size_t)it * R * kBetas;
         EMPOSE_TRY(count(launch_update(up, s)));
@@ -554,7 +587,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         mp.sub = ctx->sub; mp.fan = ctx->fan; mp.spec = ctx->spec;
         mp.theta = pl.theta; mp.vp = pl.vpoff; mp.jrest = pl.jrest;
         mp.offsets = pl.offsets; mp.rows_per_offset = F;
-        mp.meas = pl.meas; mp.coef = pl.coef; mp.R = R; mp.want_grad = grad; mp.round_out = rnd;
+        mp.meas = pl.meas; mp.coef = pl.coef; mp.R = R; mp.want_grad = grad; mp.round_out = blend_operand_mode(ctx); mp.dj_ld = ctx->dj_ld;
         mp.static_tree = ctx->static_tree;
         mp.sensor_pos = (hist && hist->markers) ? hist->markers + (size_t)it * R * 36 : nullptr;
         mp.sensor_ori = (hist && hist->markers_ori) ? hist->markers_ori + (size_t)it * R * 108 : nullptr;
@@ -636,6 +669,7 @@ int empose_set_option(const char* key, int32_t value) {
     if (k == "main_general") o.main_general = value;
     else if (k == "fan_variant") o.fan_variant = value;
     else if (k == "lstm_persistent") o.lstm_persistent = value;
+    else if (k == "blend_fp16") o.blend_fp16 = value;          // read when a context is created
     else { set_last_error("unknown option '" + k + "'"); return EMPOSE_E_ARG; }
     return EMPOSE_OK;
 }
@@ -664,7 +698,7 @@ int empose_ief_create(const empose_ief_config* cfg, const empose_tensor* tensors
     ctx->round = cfg->precision != EMPOSE_PRECISION_FP32;
     ctx->op_mode = cfg->precision == EMPOSE_PRECISION_FP32 ? OPERAND_F32 : cfg->precision == EMPOSE_PRECISION_TF32 ? OPERAND_TF32 : OPERAND_F16;
     ctx->op_half = ctx->op_mode == OPERAND_F16 ? 1 : 0;
-    ctx->pf_stride = ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad;
+    configure_blend(ctx.get());
     ctx->n_pos = cfg->use_marker_pos ? 3 * cfg->n_markers : 0;
     ctx->in_size = ctx->n_pos + (cfg->use_marker_ori ? 9 * cfg->n_markers : 0);
     ctx->iter_in = ctx->in_size + kPoseDim + kBetas + (cfg->use_gradient ? kPoseDim + kBetas : 0);
@@ -909,7 +943,7 @@ int empose_sensors_create(const empose_tensor* tensors, int32_t n_tensors, int32
     ctx->round = precision != EMPOSE_PRECISION_FP32;
     ctx->op_mode = precision == EMPOSE_PRECISION_FP32 ? OPERAND_F32 : OPERAND_TF32;
     ctx->op_half = 0;
-    ctx->pf_stride = ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad;
+    configure_blend(ctx.get());
     ctx->spec.use_pos = 0; ctx->spec.use_ori = 0; ctx->spec.weight = 1.0f;
     for (int i = 0; i < kSensors; ++i) { ctx->spec.sensor_active[i] = 0; ctx->slot_of_sensor[i] = i; }
     TensorTable tt{tensors, n_tensors};
@@ -927,12 +961,13 @@ int empose_sensor_project(empose_ief* ctx, const float* poses, const float* shap
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int rnd = ctx->round ? 1 : 0;
     ctx->last_launches = 1;
-    EMPOSE_TRY(launch_pose_features(poses, shapes, pl->pf, ctx->pf_stride, rnd, R, s));
+    EMPOSE_TRY(launch_pose_features(poses, shapes, pl->pf, ctx->pf_stride, blend_operand_mode(ctx), R, s));
     EMPOSE_TRY(run_jobs(ctx, *pl, pl->pb, ceil_div(R, kTileM), s));
     MainParams mp;
     memset(&mp, 0, sizeof(mp));
     mp.sub = ctx->sub; mp.fan = ctx->fan; mp.spec = ctx->spec; mp.theta = poses; mp.vp = pl->vpoff; mp.jrest = pl->jrest;
-    mp.offset_r = offset_r; mp.offset_t = offset_t; mp.rows_per_offset = 1; mp.R = R; mp.want_grad = 0; mp.round_out = rnd;
+    mp.offset_r = offset_r; mp.offset_t = offset_t; mp.rows_per_offset = 1; mp.R = R; mp.want_grad = 0; mp.round_out = blend_operand_mode(ctx);
+    mp.dj_ld = ctx->dj_ld;
     mp.static_tree = ctx->static_tree;
     mp.sensor_pos = sensor_pos; mp.sensor_ori = sensor_ori; mp.joints = joints;
     ++ctx->last_launches;

@@ -117,6 +117,7 @@ struct PackedMatrix {
     int64_t ld = 0;
     int has_act = 0;
     float alpha = 0.0f;
+    float out_scale = 1.0f;   // GemmJob::out_scale of the jobs made from this matrix
 };
 
 inline void choose_tiles(int n, int granule, PackedMatrix* pm) {
@@ -314,6 +315,7 @@ inline GemmJob linear_proto(const PackedMatrix& W, bool round, float* out, int64
     j.round_out = round ? 1 : 0;
     j.has_act = W.has_act;
     j.prelu_alpha = W.alpha;
+    j.out_scale = W.out_scale;
     j.n_valid = n_valid;
     j.out = out;
     j.out_stride = out_stride;
@@ -365,7 +367,11 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
     bool round = true;         // a tensor-core mode (TF32 or FP16): pose-blend operands are tf32-rounded, tcgen05 executor
     int op_mode = OPERAND_TF32;   // storage of the MLP / LSTM / heads operands: OPERAND_F32, OPERAND_TF32 or OPERAND_F16
     int op_half = 0;           // op_mode == OPERAND_F16
-    int pf_stride = kPoseFeatPad;   // floats per row of the pose-feature buffer (2x when split hi|lo)
+    int pf_stride = kPoseFeatPad;   // elements per row of the feature buffer (2x when split hi|lo)
+    bool blend_half = false;   // tensor-core modes: the blend GEMM and its transpose run on fp16 operands (feature rows
+                               // split into fp16 hi | lo * 2^11, dE/dvp and dE/dJ stored as fp16 * kDvpScale); option blend_fp16 = 0
+                               // keeps the tf32 form of round 1 (3xTF32 forward, single TF32 transposed)
+    int dj_ld = kJrestLd;      // row pitch of the dE/dJ buffer in elements (kDjLdHalf when blend_half)
     Arena arena;
     SubModel sub;
     FanModel fan;              // fan tables of the sub-model (fan.ok = 0: the general kernel runs)
@@ -412,10 +418,18 @@ int upload_submodel(IefData* ctx, const TensorTable& tt);
 
 // A operand of the blend GEMM: [pf_hi | pf_lo] then pf_hi again in TF32 mode, plain pf in FP32 mode
 inline ASrc pose_blend_a0(const IefData* ctx, const float* pf, int rows) {
-    return ASrc{pf, ctx->pf_stride, ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad, rows};
+    return ASrc{pf, ctx->pf_stride, ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad, rows, ctx->blend_half ? 1 : 0};
 }
 inline ASrc pose_blend_a1(const IefData* ctx, const float* pf, int rows) {
-    return ctx->round ? ASrc{pf, ctx->pf_stride, kPoseFeatPad, rows} : ASrc{};
+    return ctx->round ? ASrc{pf, ctx->pf_stride, kPoseFeatPad, rows, ctx->blend_half ? 1 : 0} : ASrc{};
+}
+// How the per-frame kernels store what feeds the blend GEMMs (UpdateParams::pf_mode, MainParams::round_out)
+inline int blend_operand_mode(const IefData* ctx) { return !ctx->round ? OPERAND_F32 : ctx->blend_half ? OPERAND_F16 : OPERAND_TF32; }
+// call once ctx->round is known (before upload_submodel)
+inline void configure_blend(IefData* ctx) {
+    ctx->blend_half = ctx->round && debug_options().blend_fp16 != 0;
+    ctx->pf_stride = ctx->round ? 2 * kPoseFeatPad : kPoseFeatPad;
+    ctx->dj_ld = ctx->blend_half ? kDjLdHalf : kJrestLd;
 }
 
 // The two contractions around the per-frame sub-model kernel, as jobs of `book`:
@@ -431,6 +445,7 @@ inline int add_blend_jobs(JobBook& book, const IefData* ctx, const float* pf, fl
 }
 inline int add_blend_transposed_jobs(JobBook& book, const IefData* ctx, const float* dvp, const float* dj, float* dpf, int R, JobRange* bwd) {
     GemmJob proto = linear_proto(ctx->pbt, false, dpf, kPoseFeatPad, kFeatK);
-    return book.add(ctx->pbt, ASrc{dvp, ctx->sub.vp_dim, ctx->sub.vp_dim, R}, ASrc{dj, kJrestLd, kPoseDim, R}, proto, R, -1, bwd);
+    const int hf = ctx->blend_half ? 1 : 0;
+    return book.add(ctx->pbt, ASrc{dvp, ctx->sub.vp_dim, ctx->sub.vp_dim, R, hf}, ASrc{dj, ctx->dj_ld, kPoseDim, R, hf}, proto, R, -1, bwd);
 }
 }  // namespace empose

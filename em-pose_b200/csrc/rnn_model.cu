@@ -298,7 +298,7 @@ int rnn_forward(empose_rnn* ctx, RnnPlan& pl, const float* marker_pos, const flo
     memset(&up, 0, sizeof(up));
     up.theta = pl.theta; up.beta = pl.beta; up.dtheta = pl.pose; up.dbeta = pl.dshape;
     up.step = 0.0f; up.first = 1; up.average_shape = cfg.average_shape; up.B = B; up.F = F; up.operand_mode = fk.op_mode;
-    up.xiter = nullptr; up.pf = pl.pf; up.pf_stride = fk.pf_stride; up.pf_split = fk.round ? 1 : 0;
+    up.xiter = nullptr; up.pf = pl.pf; up.pf_stride = fk.pf_stride; up.pf_split = blend_operand_mode(&fk);
     EMPOSE_TRY(launch_update(up, s));
     ++ctx->launches;
     if (shape_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(shape_hat, pl.beta, (size_t)R * kBetas * 4, cudaMemcpyDeviceToDevice, s));
@@ -310,7 +310,7 @@ int rnn_forward(empose_rnn* ctx, RnnPlan& pl, const float* marker_pos, const flo
     memset(&mp, 0, sizeof(mp));
     mp.sub = fk.sub; mp.fan = fk.fan; mp.spec = fk.spec; mp.theta = pl.theta; mp.vp = pl.vpoff; mp.jrest = pl.jrest;
     mp.offsets = pl.offsets; mp.rows_per_offset = R;       // one identity offset row for every frame
-    mp.R = R; mp.want_grad = 0; mp.round_out = fk.round ? 1 : 0; mp.static_tree = fk.static_tree;
+    mp.R = R; mp.want_grad = 0; mp.round_out = blend_operand_mode(&fk); mp.dj_ld = fk.dj_ld; mp.static_tree = fk.static_tree;
     mp.joints = pl.joints;
     EMPOSE_TRY(launch_main(mp, s));
     ctx->launches += 2;
@@ -355,7 +355,7 @@ int empose_rnn_create(const empose_rnn_config* cfg, const empose_tensor* tensors
     fk.round = cfg->precision != EMPOSE_PRECISION_FP32;
     fk.op_mode = cfg->precision == EMPOSE_PRECISION_FP32 ? OPERAND_F32 : cfg->precision == EMPOSE_PRECISION_TF32 ? OPERAND_TF32 : OPERAND_F16;
     fk.op_half = fk.op_mode == OPERAND_F16 ? 1 : 0;
-    fk.pf_stride = fk.round ? 2 * kPoseFeatPad : kPoseFeatPad;
+    configure_blend(&fk);
     fk.spec.use_pos = 0; fk.spec.use_ori = 0; fk.spec.weight = 1.0f;
     for (int i = 0; i < kSensors; ++i) fk.spec.sensor_active[i] = 0;
     ctx->dirs = cfg->bidirectional ? 2 : 1;

@@ -404,7 +404,7 @@ int build_plan(empose_train* t, int B, int F, TrainPlan** out) {
     EMPOSE_TRY(A.alloc_n(Rz * kPoseFeatPad, &pl.dpf));
     EMPOSE_TRY(A.alloc_n(Rz * kPoseDim, &pl.gth_part));
     EMPOSE_TRY(A.alloc_n(Rz * kJrestLd, &pl.jrest));
-    EMPOSE_TRY(A.alloc_n(Rz * kJrestLd, &pl.dj, true));
+    EMPOSE_TRY(A.alloc_n(Rz * ctx->dj_ld, &pl.dj, true));
     EMPOSE_TRY(A.alloc_n((size_t)B * 144, &pl.offsets));
     EMPOSE_TRY(A.alloc_n((size_t)B, &pl.seq_len));
     EMPOSE_TRY(A.alloc_n(Rz * 12, &pl.masks));
@@ -592,7 +592,7 @@ void fill_main_params(const empose_train* t, const TrainPlan& pl, MainParams* mp
     mp->sub = ctx->sub; mp->fan = ctx->fan; mp->spec = ctx->spec;
     mp->theta = pl.theta; mp->vp = pl.vpoff; mp->jrest = pl.jrest;
     mp->offsets = pl.offsets; mp->rows_per_offset = pl.F;
-    mp->meas = pl.meas; mp->coef = pl.coef; mp->R = pl.R; mp->round_out = ctx->round ? 1 : 0;
+    mp->meas = pl.meas; mp->coef = pl.coef; mp->R = pl.R; mp->round_out = blend_operand_mode(ctx); mp->dj_ld = ctx->dj_ld;
     mp->static_tree = ctx->static_tree;
     mp->dvp = pl.dvp; mp->dj = pl.dj; mp->gtheta_part = pl.gth_part;
 }
@@ -659,7 +659,7 @@ int train_forward(empose_train* t, TrainPlan& pl, const float* marker_pos, const
         up.step = cfg.step_size; up.first = (it == 0); up.average_shape = cfg.average_shape;
         up.B = B; up.F = F; up.operand_mode = ctx->op_mode;
         up.xiter = xiter_k; up.in_size = ctx->in_size; up.iter_stride = ctx->iter_stride; up.pf = pl.pf;
-        up.pf_stride = ctx->pf_stride; up.pf_split = rnd;
+        up.pf_stride = ctx->pf_stride; up.pf_split = blend_operand_mode(ctx);
         up.hist_pose = pl.hist[0] + (size_t)it * R * kPoseDim;
         up.hist_shape = pl.hist[1] + (size_t)it * R * kBetas;
         EMPOSE_TRY(launch_update(up, s));
