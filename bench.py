@@ -34,12 +34,33 @@ FRAMES = 32
 FLOP_PER_FRAME = 26472448          # 2 x MACs of the learned layers, LGD-RNN-12-N4
 BYTES_PER_FRAME = 1162             # algorithmic HBM bytes per frame
 METRIC = 'frames/sec LGD-RNN-12 N=4 ws=32'
-# dram__bytes_read.sum + dram__bytes_write.sum of gemm_tc_kernel from the committed ncu --set full captures
-# (profiles/r01/ncu_summary_v11.txt, fp16 operand mode): launch-weighted mean over the 47 launches of a step.
-NCU_TRAFFIC_BYTES = (4 * 1.083e9 + 33 * 0.0344e9 + 10 * 0.30e9) / 47
-NCU_TRAFFIC_NOTE = ('mean per launch at 4096 windows: MLP-chain launch 1.08 GB (0.11 read + 0.97 written: the CTA-local fp16 activation '
-                    'scratch is still written back) and LSTM launch 0.034 GB measured, the ten pose-blend / heads launches estimated at '
-                    '0.3 GB; algorithmic bytes per launch ~3 MB')
+CEILING_FRAMES_PER_S = None        # tensor ceiling per GPU = measured sustained dense peak / FLOP_PER_FRAME (set in run_b200)
+# launches of the tcgen05 executor in one step of the headline workload, by kind (N = 4 iterations, LSTM wavefront as
+# ONE persistent launch): name in profiles/ncu_kernels.json -> launches per step
+EXECUTOR_LAUNCHES = {'lstm': 1, 'heads': 1, 'blend_fwd': 5, 'blend_t': 4, 'chain': 4}
+
+
+def ncu_kernels():
+    """profiles/ncu_kernels.json: numbers extracted by scripts/ncu_to_json.py from the committed ncu --set full captures
+    (one launch per kernel kind, 4096 windows x 32 frames, fp16 operand mode)."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_kernels.json')
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+def executor_traffic():
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch of the executor, launch-weighted over
+    the kinds of launch in a step; None when a kind has no committed capture."""
+    k = ncu_kernels()
+    if not all(name in k for name in EXECUTOR_LAUNCHES):
+        return None, 'profiles/ncu_kernels.json lacks a capture for: ' + ', '.join(n for n in EXECUTOR_LAUNCHES if n not in k)
+    total = sum(n * (k[name]['dram_read_bytes'] + k[name]['dram_write_bytes']) for name, n in EXECUTOR_LAUNCHES.items())
+    note = '; '.join('%s %d x %.0f MB' % (name, n, (k[name]['dram_read_bytes'] + k[name]['dram_write_bytes']) / 1e6)
+                     for name, n in EXECUTOR_LAUNCHES.items())
+    return total / sum(EXECUTOR_LAUNCHES.values()), 'launch-weighted mean of the committed captures (profiles/ncu_kernels.json): ' + note
 
 
 def asset_dir():
@@ -201,6 +222,95 @@ def run_reference(args, rank):
         'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
+class _HostBatch(object):
+    """What the reference's evaluation loop hands to ``net(batch)``: an ``ABatch``-like object whose tensors live in pinned
+    host memory and are moved by ``to_gpu()`` (``data.py:270-282``, ``eval/helpers.py:78-83``)."""
+
+    def __init__(self, tensors, device=None):
+        self.t = tensors
+        self.device = device
+        self.seq_lengths = tensors['seq_lengths']
+        self.batch_size, self.seq_length = tensors['marker_pos'].shape[0], tensors['marker_pos'].shape[1]
+        self.marker_masks = None
+
+    def to_gpu(self, device):
+        return _HostBatch({k: v.to(device, non_blocking=True) for k, v in self.t.items()}, device)
+
+    def get_inputs(self, sf=None, ef=None, **kwargs):
+        t = self.t
+        return {'marker_pos': t['marker_pos'][:, sf:ef], 'marker_oris': t['marker_oris'][:, sf:ef], 'offset_r': t['offset_r'],
+                'offset_t': t['offset_t'], 'marker_masks': None}
+
+
+def train_subrecord(args, device, dist, rank, world, windows=512, steps=5):
+    """BASELINE config 5 beside the headline: a short run of the data-parallel training step (train-mode forward, backward,
+    ONE all-reduce of the flat gradient when N > 1, Adam).  Returns the dict that goes under ``train`` in the JSON line."""
+    from empose_b200 import lib, synthetic
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from empose_b200.helpers.configuration import lgd_config
+    from empose_b200.nn.models import IterativeErrorFeedback
+    npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0)
+    cfg = lgd_config(n_markers=12, num_iterations=4, rnn_init=True, hidden_size=512, window_size=FRAMES, **TRAIN_FLAGS)
+    net = IterativeErrorFeedback(cfg, SMPLLayer(npz).to(dtype=torch.float32), precision=lib.PRECISION_TF32)
+    sd = net.state_dict()
+    for k, v in synthetic.synth_state_dict(seed=0, n_markers=12, rnn_init=True).items():
+        sd[k] = torch.from_numpy(np.asarray(v))
+    net.load_state_dict(sd, strict=True)
+    net = net.to(device).eval()
+    ctx = net.native_context(device)
+    b = windows
+    inp = synth_device_inputs(ctx, b, device, seed=2000 + rank)
+    p = synthetic.synth_window_params(b, FRAMES, seed=2000 + rank)
+    poses, shapes = torch.from_numpy(p['poses']).to(device), torch.from_numpy(p['shapes']).to(device)
+    r = b * FRAMES
+    _, _, joints = ctx.sensor_project(poses.reshape(r, 66), shapes.unsqueeze(1).repeat(1, FRAMES, 1).reshape(r, 10),
+                                      torch.eye(3, device=device).repeat(r, 12, 1, 1), torch.zeros(r, 12, 3, device=device))
+    batch = _TrainBatch(inp, poses, shapes, joints.reshape(b, FRAMES, 66))
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=cfg.lr)
+    ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar_ms, losses = [], []
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        out = net(batch)
+        _, vals = net.backward(batch, out)
+        if dist is not None:
+            ar0.record()
+            net.allreduce_gradients(average=True)
+            ar1.record()
+        opt.step()
+        losses.append(vals['total_loss'])
+        if dist is not None:
+            ar1.synchronize()
+            ar_ms.append(ar0.elapsed_time(ar1))
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(3):
+        step()
+    del ar_ms[:]
+    ms = timed(step, steps, barrier)
+    if dist is not None:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    rec = {'metric': TRAIN_METRIC, 'value': world * b * FRAMES * steps / (ms / 1000.0), 'unit': 'frames/s', 'ms_per_step': ms / steps,
+           'steps': steps, 'warmup': 3, 'windows_per_gpu': b, 'global_batch_windows': world * b, 'dtype': 'tf32',
+           'allreduce_ms': (sum(ar_ms) / len(ar_ms)) if ar_ms else 0.0,
+           'allreduce_bytes': int(net.flat_gradients().numel()) * 4 if world > 1 else 0,
+           'launches_per_step': int(net._trainer.last_launch_count), 'loss_first_last': [losses[0], losses[-1]],
+           'parallelism': 'data parallel: windows sharded, one NCCL all-reduce of the flat gradient (DDP semantics, per-shard BatchNorm statistics)'}
+    net.invalidate()
+    del net, opt, batch
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_b200(args, rank, local_rank, world):
     from empose_b200 import lib
     device = torch.device('cuda', local_rank)
@@ -210,18 +320,24 @@ def run_b200(args, rank, local_rank, world):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=device)
     net = build_b200_model(device, args.precision)
+    net.precision_guard = False          # the timed loops stay asynchronous; the guard's one read per forward is in the 'api' figure
     ctx = net.native_context(device)
     b = args.windows
     inp = synth_device_inputs(ctx, b, device, seed=1000 + rank)
     host = {k: v.cpu().pin_memory() for k, v in inp.items()}
     frames_per_step = b * FRAMES
+    peaks = measured_peaks()
+    ceiling = peaks['bf16_tflops_sustained'] * 1e12 / FLOP_PER_FRAME         # frames/s per GPU if the learned layers ran at the peak
 
     def step_device():
         ctx.forward(inp['marker_pos'], inp['marker_oris'], inp['offset_r'], inp['offset_t'], inp['seq_lengths'],
-                    want_history=False)
+                    want_history=False, want_state=False)
 
     def step_host():
-        ctx.forward_host(host['marker_pos'], host['marker_oris'], host['offset_r'], host['offset_t'], host['seq_lengths'])
+        # fresh windows: nobody consumes the final LSTM state, so it is not downloaded (models.py:489-492 reads it only
+        # when the NEXT chunk of the same sequences follows)
+        ctx.forward_host(host['marker_pos'], host['marker_oris'], host['offset_r'], host['offset_t'], host['seq_lengths'],
+                         want_state=False)
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -246,16 +362,36 @@ def run_b200(args, rank, local_rank, world):
     sampler.join()
     value = world * frames_per_step * args.steps / (ms / 1000.0)
 
-    # end to end through the host-buffer C-ABI entry point
+    # ---- end to end through the host-buffer C-ABI entry point ----
     for _ in range(2):
         step_host()
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = max_over_ranks(timed(step_host, e2e_steps, barrier))
     e2e_value = world * frames_per_step * e2e_steps / (ms_e2e / 1000.0)
     h2d = sum(host[k].numel() * host[k].element_size() for k in host)
-    d2h = frames_per_step * (66 + 10 + 66) * 4 + 2 * 2 * b * 512 * 4
+    d2h = frames_per_step * (66 + 10 + 66) * 4
 
-    # roofline of the dominant kernel (the tcgen05 GEMM executor): live CUDA-event timing of every launch
+    # ---- end to end through the drop-in class: net(batch) on a host batch, all five histories, outputs back on the host ----
+    api_net = build_b200_model(device, args.precision)          # guard on: what a user of the reference surface gets
+    host_batch = _HostBatch(host)
+
+    def step_api():
+        with torch.no_grad():
+            out = api_net(host_batch.to_gpu(device))
+        return {k: v.cpu() for k, v in out.items()}
+
+    for _ in range(2):
+        step_api()
+    api_steps = max(3, min(args.steps, 5))
+    ms_api = max_over_ranks(timed(step_api, api_steps, barrier))
+    api = {'value': world * frames_per_step * api_steps / (ms_api / 1000.0), 'unit': 'frames/s', 'ms_per_step': ms_api / api_steps,
+           'api': 'IterativeErrorFeedback.forward(batch) with the five N+1 histories kept on the module, host batch -> to_gpu() -> '
+                  'outputs .cpu(); precision guard on (one scalar read per forward)',
+           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': frames_per_step * (63 + 3 + 10 + 66) * 4,
+           'history_bytes_per_step': frames_per_step * 5 * 286 * 4}
+    del api_net
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM executor): live CUDA-event timing of every launch ----
     ctx.set_profiling(True)
     prof_steps = max(2, min(args.steps, 5))
     for _ in range(prof_steps):
@@ -264,23 +400,68 @@ def run_b200(args, rank, local_rank, world):
     gemm_ms, gemm_launches = ctx.profile_read()
     main_ms, main_launches = ctx.profile_read_main()
     ctx.set_profiling(False)
-    peaks = measured_peaks()
     achieved = FLOP_PER_FRAME * frames_per_step * prof_steps / (gemm_ms / 1000.0) / 1e12
+    traffic, traffic_note = executor_traffic()
+    clocks = sampler.summary()
+    kern = ncu_kernels()
+    fan = None
+    if 'fan_grad' in kern and main_launches:
+        # instruction roofline of the per-frame sub-model kernel: it moves its algorithmic bytes only (~3.7 KB per frame at
+        # 0.8 TB/s) and issues no tensor instruction; what bounds it is instruction issue.  Warp instructions per launch from
+        # the committed ncu capture (a fixed property of the build), duration live; peak = 4 schedulers x SMs x SM clock.
+        n_grad = 4.0 * kern['fan_grad']['warp_instructions'] + (kern['fan_fwd']['warp_instructions'] if 'fan_fwd' in kern else 0.0)
+        sm_hz = (clocks.get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)) * 1e6
+        peak_ips = 4.0 * torch.cuda.get_device_properties(device).multi_processor_count * sm_hz
+        fan = {'kernel': 'fan_kernel (SMPL-H sub-model forward + hand-derived reverse pass, fp32 SIMT)', 'bound': 'instruction issue',
+               'share_of_step': (main_ms / prof_steps) / (ms / args.steps), 'launches_per_step': main_launches / prof_steps,
+               'avg_launch_ms': main_ms / max(main_launches, 1),
+               'warp_instructions_per_step': n_grad * (frames_per_step / 131072.0),
+               'achieved': n_grad * (frames_per_step / 131072.0) / (main_ms / prof_steps / 1000.0) / 1e12,
+               'peak': peak_ips / 1e12, 'unit': 'T warp-instructions/s',
+               'frac': n_grad * (frames_per_step / 131072.0) / (main_ms / prof_steps / 1000.0) / peak_ips,
+               'issue_active_pct_ncu': kern['fan_grad'].get('issue_active_pct'),
+               'dram_bytes_per_launch_ncu': kern['fan_grad']['dram_read_bytes'] + kern['fan_grad']['dram_write_bytes']}
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / peaks['bf16_tflops_sustained'], 'traffic': NCU_TRAFFIC_BYTES,
-                'traffic_note': NCU_TRAFFIC_NOTE,
-                'kernel': 'gemm_tc_kernel (tcgen05.mma kind::f16 for the learned layers, kind::tf32 x3 for the pose blend)'
-                          if args.precision == 'fp16' else 'gemm_tc_kernel (tcgen05.mma kind::tf32)',
+                'frac': achieved / peaks['bf16_tflops_sustained'], 'traffic': traffic, 'traffic_note': traffic_note,
+                'kernel': 'gemm_tc_kernel (tcgen05.mma kind::f16: learned layers, and the blend GEMMs as a 3-term fp16 split)'
+                          if args.precision == 'fp16' else 'gemm_tc_kernel (tcgen05.mma kind::tf32; blend GEMMs kind::f16 split)',
                 'peak_source': peaks['source'] + ' bf16 dense, sustained',
                 'launches_per_step': gemm_launches / prof_steps, 'avg_launch_ms': gemm_ms / max(gemm_launches, 1),
                 'kernel_share_of_step': (gemm_ms / prof_steps) / (ms / args.steps),
-                # the other half of the step: the per-frame SMPL sub-model kernel (forward + hand-derived reverse pass), fp32
-                # SIMT arithmetic on ~3 KB of state per frame -- neither HBM- nor tensor-bound (ncu: issue slots 46 % busy,
-                # DRAM 0.2 TB/s), so it has no roofline line of its own; its share is reported so that the two add up
-                'other_kernels': {'main_kernel': {'share_of_step': (main_ms / prof_steps) / (ms / args.steps),
-                                                  'launches_per_step': main_launches / prof_steps,
-                                                  'avg_launch_ms': main_ms / max(main_launches, 1)}},
+                # the whole step against the same ceiling: frames/s per GPU over (sustained peak / FLOP per frame)
+                'step_frac': (value / world) / ceiling, 'step_ceiling_frames_per_s_per_gpu': ceiling,
+                'e2e_step_frac': (e2e_value / world) / ceiling,
+                'other_kernels': {'fan_kernel': fan},
                 'algorithmic_flop_per_launch': FLOP_PER_FRAME * frames_per_step * prof_steps / max(gemm_launches, 1)}
+
+    # ---- the same step with tf32 operands for the learned layers (what the reference's fp32 is closest to on tensor cores) ----
+    tf32 = None
+    if args.precision == 'fp16' and not args.no_companions:
+        net32 = build_b200_model(device, 'tf32')
+        c32 = net32.native_context(device)
+        run32 = lambda: c32.forward(inp['marker_pos'], inp['marker_oris'], inp['offset_r'], inp['offset_t'], inp['seq_lengths'],
+                                    want_history=False, want_state=False)
+        for _ in range(3):
+            run32()
+        n32 = max(3, min(args.steps, 10))
+        ms32 = max_over_ranks(timed(run32, n32, barrier))
+        c32.set_profiling(True)
+        for _ in range(2):
+            run32()
+        torch.cuda.synchronize(device)
+        g32, _ = c32.profile_read()
+        c32.set_profiling(False)
+        a32 = FLOP_PER_FRAME * frames_per_step * 2 / (g32 / 1000.0) / 1e12
+        v32 = world * frames_per_step * n32 / (ms32 / 1000.0)
+        tf32 = {'value': v32, 'unit': 'frames/s', 'ms_per_step': ms32 / n32, 'executor_tflops': a32,
+                'frac_of_tf32_rate': a32 / (peaks['bf16_tflops_sustained'] / 2.0), 'tf32_rate_tflops': peaks['bf16_tflops_sustained'] / 2.0,
+                'step_frac_of_tf32_ceiling': (v32 / world) / (ceiling / 2.0),
+                'note': 'tcgen05 kind::tf32 issues at half the f16 rate; same kernels, same launches'}
+        del net32, c32
+
+    train = None
+    if not args.no_companions:
+        train = train_subrecord(args, device, dist, rank, world)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -301,15 +482,17 @@ def run_b200(args, rank, local_rank, world):
             'config': {'workload': 'LGD-RNN (2x512 LSTM init), 12 sensors, N=4, ws=32, %d windows per GPU (BASELINE config 3)' % b,
                        'windows_per_gpu': b, 'frames_per_window': FRAMES, 'parallelism': 'windows sharded, no collective',
                        'l2': 'per-step working set (~3 GB of activations and features) exceeds the 126 MB L2; no flush needed',
-                       'arithmetic': {'fp16': 'learned layers: fp16 operands on tcgen05 (kind::f16), fp32 accumulate in TMEM; pose blend 3xTF32; '
-                                              'per-frame SMPL math, LSTM cell state and all outputs fp32',
-                                      'tf32': 'tf32 tensor cores (tcgen05), fp32 accumulate; pose blend 3xTF32; per-frame SMPL math fp32',
+                       'arithmetic': {'fp16': 'learned layers: fp16 operands on tcgen05 (kind::f16), fp32 accumulate in TMEM; blend GEMMs as a '
+                                              '3-term fp16 split (22 mantissa bits); per-frame SMPL math, LSTM cell state and all outputs fp32',
+                                      'tf32': 'tf32 tensor cores (tcgen05), fp32 accumulate; blend GEMMs as a 3-term fp16 split; per-frame SMPL math fp32',
                                       'fp32': 'FFMA executor, fp32 everywhere (parity mode)'}[args.precision]},
-            'clocks': sampler.summary(),
+            'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': ms_e2e / e2e_steps, 'api': 'empose_ief_forward_host (pinned host buffers)'},
-            'gpu_launches': int(launches_per_step * args.steps),
-            'roofline': roofline, 'cpu_baseline': cpu}))
+                    'ms_per_step': ms_e2e / e2e_steps, 'api': 'empose_ief_forward_host (pinned host buffers; pose, shape, joints back)',
+                    'frac_of_device_rate': e2e_value / value},
+            'e2e_api': api,
+            'gpu_launches': int(launches_per_step * args.steps), 'launches_per_step': int(launches_per_step),
+            'roofline': roofline, 'tf32': tf32, 'train': train, 'cpu_baseline': cpu}))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -694,6 +877,7 @@ def main():
     ap.add_argument('--windows', type=int, default=None, help='windows per GPU (inference: 4096 = BASELINE config 3; training: 512)')
     ap.add_argument('--ref-windows', type=int, default=16, help='windows per step of the CPU reference arm / baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-companions', action='store_true', help='skip the tf32 and training sub-records (quick A/B runs)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

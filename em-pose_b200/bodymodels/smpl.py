@@ -97,6 +97,12 @@ class SMPLLayer(nn.Module):
         return _submodel.extract_fullmodel(f64(bm.v_template), f64(bm.shapedirs), f64(bm.posedirs), f64(bm.J_regressor),
                                            f64(bm.weights), bm.kintree_table.cpu().numpy())
 
+    def invalidate(self):
+        """Drop the packed full-mesh model: the next call re-reads ``self.bm`` (needed after writes through ``.data``)."""
+        if self._ctx is not None:
+            self._ctx.close()
+        self._ctx, self._ctx_key = None, None
+
     def _native(self, device):
         from empose_b200 import lib as _lib
         if device.type != 'cuda':

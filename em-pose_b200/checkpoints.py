@@ -32,16 +32,32 @@ def get_model_config(model_id, experiment_dir=None):
     return Configuration.from_json(os.path.join(model_dir, 'config.json')), model_dir
 
 
-def load_model_weights(checkpoint_file, net, state_key='model_state_dict', strict=True):
+def _load_checkpoint(checkpoint_file, allow_pickle):
+    """
+    ``torch.load`` restricted to tensors and plain containers (``weights_only=True``): a ``model.pth`` is a downloaded
+    file, and the unrestricted loader executes whatever pickle code it contains.  The reference's checkpoint dict holds
+    tensors, numbers and the optimiser's state dict, all of which the restricted loader accepts; a checkpoint that needs
+    more is refused unless the caller opts in with ``allow_pickle=True``.
+    """
+    try:
+        return torch.load(checkpoint_file, map_location='cpu', weights_only=True)
+    except Exception as err:                         # pickle.UnpicklingError and friends
+        if not allow_pickle:
+            raise ValueError('{} needs the unrestricted pickle loader ({}); pass allow_pickle=True only for files you trust'
+                             .format(checkpoint_file, err))
+        return torch.load(checkpoint_file, map_location='cpu', weights_only=False)
+
+
+def load_model_weights(checkpoint_file, net, state_key='model_state_dict', strict=True, allow_pickle=False):
     """``eval/helpers.py:131-137``.  Returns the rest of the checkpoint dict (epoch, losses, optimiser state ...)."""
     if not os.path.exists(checkpoint_file):
         raise ValueError("Could not find model checkpoint {}.".format(checkpoint_file))
-    checkpoint = torch.load(checkpoint_file, map_location='cpu', weights_only=False)
+    checkpoint = _load_checkpoint(checkpoint_file, allow_pickle)
     net.load_state_dict(checkpoint[state_key], strict=strict)
     return {k: v for k, v in checkpoint.items() if k != state_key}
 
 
-def load_model(model_id, smpl_model, experiment_dir=None, device=None, precision=None):
+def load_model(model_id, smpl_model, experiment_dir=None, device=None, precision=None, allow_pickle=False):
     """
     ``eval/helpers.py:148-164`` without the data pipeline: config.json -> ``create_model`` -> ``model.pth``.
     :return: (net in eval mode, config, model_dir, the rest of the checkpoint dict)
@@ -51,7 +67,7 @@ def load_model(model_id, smpl_model, experiment_dir=None, device=None, precision
     net = create_model(config, smpl_model)
     if precision is not None:
         net.precision = precision
-    extra = load_model_weights(os.path.join(model_dir, 'model.pth'), net)
+    extra = load_model_weights(os.path.join(model_dir, 'model.pth'), net, allow_pickle=allow_pickle)
     if device is not None:
         net = net.to(device)
     return net.eval(), config, model_dir, extra
@@ -66,9 +82,9 @@ def save_checkpoint(checkpoint_file, net, optimizer=None, **fields):
     torch.save(payload, checkpoint_file)
 
 
-def describe_checkpoint(checkpoint_file, state_key='model_state_dict'):
+def describe_checkpoint(checkpoint_file, state_key='model_state_dict', allow_pickle=False):
     """Summary of a ``model.pth``: tensors per top-level module, trainable-parameter count as the reference prints it."""
-    checkpoint = torch.load(checkpoint_file, map_location='cpu', weights_only=False)
+    checkpoint = _load_checkpoint(checkpoint_file, allow_pickle)
     sd = checkpoint[state_key]
     groups = {}
     for k, v in sd.items():

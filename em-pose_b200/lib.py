@@ -230,9 +230,12 @@ class IefContext(object):
         return ms.value, n.value
 
     def forward(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None, lstm_state=None,
-                is_new_sequence=True, want_history=True):
+                is_new_sequence=True, want_history=True, want_state=True, history_out=None):
         """
         Device tensors in, device tensors out (all float32 / int32, contiguous, on this context's device).
+        :param want_state: False skips the LSTM state output (a batch of fresh windows never needs it).
+        :param history_out: a ``history`` dict returned by an earlier call with the same (B, F): its tensors are overwritten
+            instead of allocating 5 x (N+1) new ones.
         :return: dict pose (B,F,66), shape (B,F,10), joints (B,F,66), history (dict of (N+1,B,F,dof)) or None,
                  lstm_state (2,L,B,H) or None.
         """
@@ -254,12 +257,15 @@ class IefContext(object):
         hist, hist_struct = None, None
         if want_history:
             n1 = self.n_iter + 1
-            hist = {'pose': torch.empty((n1, b, f, 66), **opts), 'shape': torch.empty((n1, b, f, 10), **opts),
-                    'joints': torch.empty((n1, b, f, 66), **opts), 'markers': torch.empty((n1, b, f, 36), **opts),
-                    'markers_ori': torch.empty((n1, b, f, 108), **opts)}
-            hist_struct = History(*[hist[k].data_ptr() for k in ('pose', 'shape', 'joints', 'markers', 'markers_ori')])
+            dof = (('pose', 66), ('shape', 10), ('joints', 66), ('markers', 36), ('markers_ori', 108))
+            if history_out is not None and all(history_out[k].shape == (n1, b, f, d) and history_out[k].device == dev
+                                               for k, d in dof):
+                hist = history_out
+            else:
+                hist = {k: torch.empty((n1, b, f, d), **opts) for k, d in dof}
+            hist_struct = History(*[hist[k].data_ptr() for k, _ in dof])
         state = None
-        if self.rnn_layers:
+        if self.rnn_layers and (want_state or (lstm_state is not None and not is_new_sequence)):
             if lstm_state is not None and not is_new_sequence:
                 state = f32(lstm_state).reshape(2, self.rnn_layers, b, self.rnn_hidden).clone()
             else:
@@ -271,8 +277,10 @@ class IefContext(object):
         return {'pose': pose, 'shape': shape, 'joints': joints, 'history': hist, 'lstm_state': state}
 
     def forward_host(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None,
-                     lstm_state=None, is_new_sequence=True):
-        """Host (CPU, ideally pinned) tensors in and out through ``empose_ief_forward_host``; synchronises."""
+                     lstm_state=None, is_new_sequence=True, want_state=True):
+        """Host (CPU, ideally pinned) tensors in and out through ``empose_ief_forward_host``; synchronises.
+        ``want_state=False`` skips the download of the final LSTM state (2 x L x B x H floats), which only a caller that
+        streams the next chunk of the same sequences needs (``models.py:489-492``)."""
         import torch
         b, f = int(marker_pos.shape[0]), int(marker_pos.shape[1])
         f32 = lambda t: t.to(dtype=torch.float32).contiguous()
@@ -286,7 +294,7 @@ class IefContext(object):
         shape = torch.empty((b, f, 10), dtype=torch.float32, pin_memory=True)
         joints = torch.empty((b, f, 66), dtype=torch.float32, pin_memory=True)
         state = None
-        if self.rnn_layers:
+        if self.rnn_layers and (want_state or (lstm_state is not None and not is_new_sequence)):
             state = torch.empty((2, self.rnn_layers, b, self.rnn_hidden), dtype=torch.float32, pin_memory=True)
             if lstm_state is not None and not is_new_sequence:
                 state.copy_(lstm_state.reshape(state.shape))

@@ -13,6 +13,8 @@ the gradients its forward pass accumulates as a side effect (``models.py:576``).
 built on ``net.parameters()`` then steps in place, and data-parallel training all-reduces the single flat
 gradient vector (``allreduce_gradients``).
 """
+import re
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -118,6 +120,13 @@ class IterativeErrorFeedback(nn.Module):
         self._trainer_device = None
         self._flat = None                    # dict(params=, grads=, bn=, entries=) once training has started
         self._train_batch_shape = None
+        self._hist_buf = None                # history tensors of the last single-span forward, reused when the shape repeats
+        #: fp16 operands (the inference default) cannot represent everything fp32 can.  With the guard on, (i) a model
+        #: whose BatchNorm-folded weights leave the range where fp16 keeps its 11 significant bits is run on tf32 tensor
+        #: cores from the start, and (ii) a forward pass whose result is not finite (an activation beyond 65504) is
+        #: repeated on tf32.  Costs one scalar device->host read per forward; set False for asynchronous pipelines.
+        self.precision_guard = True
+        self.precision_fallbacks = 0         # forward passes the guard repeated on tf32
 
     # ------------------------------------------------------------------------------------------------
     def model_name(self):
@@ -143,25 +152,90 @@ class IterativeErrorFeedback(nn.Module):
                     skip_connections=int(self.skip_connections), batch_norm=int(not c.m_no_batch_norm),
                     precision=int(self.precision), device=int(device_index))
 
-    def _weights_key(self, device_index):
+    def _weights_key(self, device_index, precision):
         tensors = [t for k, t in self.state_dict(keep_vars=True).items()]
-        return (device_index, self.precision) + tuple((t.data_ptr(), t._version) for t in tensors)
+        return (device_index, precision, self._weights_epoch) + tuple((t.data_ptr(), t._version) for t in tensors)
 
-    def native_context(self, device):
+    _weights_epoch = 0
+
+    def invalidate(self):
+        """
+        Drop the packed copies of the weights (inference context and trainer) so that the next ``forward`` re-reads the
+        module's tensors.  The cache notices ordinary in-place updates (``tensor._version``) and re-assignments
+        (``data_ptr``), but NOT writes through ``.data`` (``p.data.mul_()``, EMA / weight-surgery code): call this after such
+        writes.  ``train()`` / ``eval()`` transitions call it themselves.
+        """
+        self._weights_epoch += 1
+        self._hist_buf = None
+        if self._trainer is not None:
+            self._trainer.close()
+            self._trainer = None
+            self._trainer_device = None
+
+    def train(self, mode=True):
+        if mode != self.training:
+            self._weights_epoch += 1              # the other mode's packed weights are stale once this one has stepped
+        return super(IterativeErrorFeedback, self).train(mode)
+
+    def folded_weight_range(self):
+        """(largest, smallest non-zero) magnitude of the BatchNorm-folded Linear / LSTM weights and biases -- what the
+        fp16 operand mode has to represent (the context folds BN exactly like this, csrc/model_internal.h pack_linear)."""
+        sd = self.state_dict()
+        hi, lo = 0.0, float('inf')
+        for name, w in sd.items():
+            if name.startswith('smpl.') or not w.is_floating_point() or w.dim() != 2:
+                continue
+            w = w.detach().double().cpu()
+            bn = None
+            if name.endswith('input_to_hidden.weight'):
+                bn = name[:-len('input_to_hidden.weight')] + 'batch_norm'
+            else:
+                m = re.match(r'(.*\.layers\.)(\d+)\.weight$', name)
+                if m:
+                    bn = m.group(1) + str(int(m.group(2)) + 1)
+            if bn is not None and (bn + '.running_var') in sd:
+                scale = sd[bn + '.weight'].double().cpu() / torch.sqrt(sd[bn + '.running_var'].double().cpu() + 1e-5)
+                w = w * scale.reshape(-1, 1)
+            mag = w.abs()
+            hi = max(hi, float(mag.max()))
+            nz = mag[mag > 0]
+            if nz.numel():
+                lo = min(lo, float(nz.min()))
+        return hi, lo
+
+    def _effective_precision(self):
+        """fp16 unless the guard finds folded weights that fp16 would overflow or flush (see ``precision_guard``)."""
+        if self.precision != _lib.PRECISION_FP16 or not self.precision_guard:
+            return self.precision
+        key = (self._weights_epoch,) + tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        if getattr(self, '_range_key', None) != key:
+            hi, _ = self.folded_weight_range()
+            # 65504 is fp16's largest value; activations are sums of ~hundreds of weight x O(1)-input products, so keep
+            # two orders of magnitude of head room.  (Small weights are harmless: below 6e-5 fp16 degrades gracefully.)
+            self._range_ok = hi < 256.0
+            self._range_key = key
+        return _lib.PRECISION_FP16 if self._range_ok else _lib.PRECISION_TF32
+
+    def native_context(self, device, precision=None):
         """Build (or reuse) the native context for the current weights on ``device``."""
         if device.type != 'cuda':
             raise _lib.EmposeError('empose_b200 runs on CUDA devices only (no CPU fallback); got %s' % device)
         index = device.index if device.index is not None else torch.cuda.current_device()
-        key = self._weights_key(index)
-        if self._ctx is None or key != self._ctx_key:
-            if self._ctx is not None:
-                self._ctx.close()
+        precision = self._effective_precision() if precision is None else precision
+        key = self._weights_key(index, precision)
+        cache = self.__dict__.setdefault('_ctx_cache', {})
+        for prec in list(cache):                         # contexts of other precisions built from older weights
+            if cache[prec][0][2:] != key[2:] or cache[prec][0][0] != index:
+                cache.pop(prec)[1].close()
+        if precision not in cache:
             arrays = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()
                       if not k.startswith('smpl.') and v.is_floating_point()}
             arrays = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in arrays.items()}
             arrays.update(self.smpl.submodel_arrays())
-            self._ctx = _lib.IefContext(self._native_config(index), arrays)
-            self._ctx_key = key
+            cfg = self._native_config(index)
+            cfg['precision'] = int(precision)
+            cache[precision] = (key, _lib.IefContext(cfg, arrays))
+        self._ctx, self._ctx_key = cache[precision][1], key
         return self._ctx
 
     # ------------------------------------------------------------------------------------------------
@@ -304,22 +378,34 @@ class IterativeErrorFeedback(nn.Module):
                 lengths = batch.seq_lengths
             else:
                 lengths = torch.full((marker_pos.shape[0],), ef - sf, dtype=torch.int32, device=marker_pos.device)
-            ctx = self.native_context(marker_pos.device)
             state = None
             if self.rnn_init and self.rnn.final_state is not None:
                 state = torch.stack([self.rnn.final_state[0], self.rnn.final_state[1]])
-            res = ctx.forward(marker_pos, inputs['marker_oris'], inputs['offset_r'], inputs['offset_t'], lengths,
-                              marker_masks=inputs.get('marker_masks'), lstm_state=state,
-                              is_new_sequence=state is None, want_history=True)
+            run = lambda ctx: ctx.forward(marker_pos, inputs['marker_oris'], inputs['offset_r'], inputs['offset_t'], lengths,
+                                          marker_masks=inputs.get('marker_masks'), lstm_state=state,
+                                          is_new_sequence=state is None, want_history=True,
+                                          history_out=self._hist_buf if len(spans) == 1 else None)
+            ctx = self.native_context(marker_pos.device)
+            res = run(ctx)
+            if (self.precision_guard and ctx.config['precision'] == _lib.PRECISION_FP16 and
+                    not bool(torch.isfinite(res['pose']).all() & torch.isfinite(res['joints']).all())):
+                # an activation left fp16's range: the documented fallback is the same pass on tf32 tensor cores
+                self.precision_fallbacks += 1
+                res = run(self.native_context(marker_pos.device, precision=_lib.PRECISION_TF32))
             if self.rnn_init:
                 self.rnn.init_state = self.rnn.final_state
                 self.rnn.final_state = (res['lstm_state'][0], res['lstm_state'][1])
             outs.append(res)
             hists.append(res['history'])
 
-        cat = lambda key: torch.cat([o[key] for o in outs], dim=1)
         n1 = self.N + 1
-        hist_cat = {k: [torch.cat([h[k][i] for h in hists], dim=1) for i in range(n1)] for k in hists[0]}
+        if len(outs) == 1:          # the reference's callers: one span, nothing to concatenate (and nothing to copy)
+            cat = lambda key: outs[0][key]
+            hist_cat = {k: [hists[0][k][i] for i in range(n1)] for k in hists[0]}
+            self._hist_buf = hists[0]
+        else:
+            cat = lambda key: torch.cat([o[key] for o in outs], dim=1)
+            hist_cat = {k: [torch.cat([h[k][i] for h in hists], dim=1) for i in range(n1)] for k in hists[0]}
         self.pose_hat_history = hist_cat['pose']
         self.shape_hat_history = hist_cat['shape']
         self.joints_hat_history = hist_cat['joints']
@@ -475,6 +561,13 @@ class SimpleRNN(nn.Module):
                     shape_hidden_size=int(c.m_shape_hidden_size), average_shape=int(bool(self.shape_avg)), do_fk=int(self.do_fk),
                     use_marker_pos=int(c.use_marker_pos), use_marker_ori=int(c.use_marker_ori), precision=int(self.precision),
                     device=int(device_index))
+
+    def invalidate(self):
+        """Drop the packed weights: the next ``forward`` re-reads the module's tensors (needed after writes through
+        ``.data``, which neither change ``data_ptr`` nor bump ``_version``; see ``IterativeErrorFeedback.invalidate``)."""
+        if self._ctx is not None:
+            self._ctx.close()
+        self._ctx, self._ctx_key = None, None
 
     def native_context(self, device):
         if device.type != 'cuda':

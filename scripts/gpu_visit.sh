@@ -9,7 +9,7 @@
 #   bench[:ENV=V,ENV=V]        python bench.py --steps 10 --warmup 3 --no-cpu-baseline with the environment given (A/B switches)
 #   fullbench                  the default bench line incl. the CPU baseline leg, and the reference arm
 #   train | synth | metrics | birnn   the other bench workloads
-#   launches                   ncu launch list (gpu__time_duration) of two bench steps -> <tag>_launches.csv
+#   launches[:workload]        ncu launch list (gpu__time_duration) of two bench steps -> <tag>_launches[_workload].csv
 #   prof:<name>:<kernel regex>:<skip>[:workload]   ncu --set full of ONE launch -> <tag>_prof_<name>.ncu-rep
 #   micro:<MxNxK>[,...]        scripts/gemm_microbench.py
 #   sass                       opcode histogram of the tcgen05 executor and the fan kernel from the shipped .so
@@ -29,7 +29,7 @@ for step in "$@"; do
       timeout -s KILL 300 python __graft_entry__.py --smoke > $log 2>&1; echo "rc=$?" >> $log; tail -n 3 $log ;;
     bench)
       suffix=$(echo "$arg" | tr -c 'A-Za-z0-9=\n' '_'); log=gpurun_out/${tag}_bench_${suffix}.log
-      env $(echo "$arg" | tr ',' ' ') timeout -s KILL 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $log 2>&1; echo "rc=$?" >> $log
+      env $(echo "$arg" | tr ',' ' ') timeout -s KILL 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-companions > $log 2>&1; echo "rc=$?" >> $log
       echo "bench [$arg]"; tail -n 2 $log | cut -c1-700 ;;
     fullbench)
       timeout -s KILL 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.log 2>&1
@@ -37,12 +37,13 @@ for step in "$@"; do
     train|synth|metrics|birnn)
       timeout -s KILL 600 python bench.py --workload $name --steps 10 --warmup 3 $arg > $log 2>&1; echo "rc=$?" >> $log; tail -n 2 $log | cut -c1-600 ;;
     launches)
-      timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${tag}_launches.csv \
-          python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $log 2>&1; echo "rc=$?" >> $log; tail -n 1 $log | cut -c1-200 ;;
+      wl=""; suffix=""; [ -n "$arg" ] && wl="--workload $arg" && suffix="_$arg"
+      timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_launches${suffix}.csv \
+          python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-companions $wl > $log 2>&1; echo "rc=$?" >> $log; tail -n 1 $log | cut -c1-200 ;;
     prof)
       pname=${arg%%:*}; rest=${arg#*:}; regex=${rest%%:*}; rest=${rest#*:}; skip=${rest%%:*}; wl=""; [ "$rest" != "$skip" ] && wl="--workload ${rest#*:}"
       timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -o gpurun_out/${tag}_prof_$pname -f \
-          python bench.py --steps 1 --warmup 3 --no-cpu-baseline $wl > gpurun_out/${tag}_prof_$pname.log 2>&1; echo "prof $pname rc=$?" ;;
+          python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-companions $wl > gpurun_out/${tag}_prof_$pname.log 2>&1; echo "prof $pname rc=$?" ;;
     micro)
       timeout -s KILL 300 python scripts/gemm_microbench.py $(echo "$arg" | tr ',' ' ') > $log 2>&1; grep -h tflops $log | tr -d '\n'; echo ;;
     sass)

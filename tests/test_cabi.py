@@ -149,3 +149,69 @@ def test_dropin_rebinds_the_reference_factories(smpl_npz, asset_dir):
     assert isinstance(net, IterativeErrorFeedback) and isinstance(net, ref_models.IterativeErrorFeedback)
     assert sum(p.numel() for p in net.parameters() if p.requires_grad) == 5721419     # README.md:228
     assert net.model_name().startswith('IEF-2x512-N2-RNN-2x512')
+
+
+def test_dropin_rebinds_names_imported_before_install(smpl_npz, asset_dir):
+    """The reference binds its factories with ``from empose.nn.models import create_model`` (eval/helpers.py:20-25): a module
+    imported BEFORE install() keeps the old objects unless install() also rebinds them there."""
+    import sys
+    import types
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip('reference tree not present on this machine')
+    ref_shims.install(asset_dir, seed=0)
+    import empose.bodymodels.smpl as ref_smpl
+    import empose.nn.models as ref_models
+    import empose_b200.dropin
+    from empose_b200.nn.models import IterativeErrorFeedback
+    early = types.ModuleType('empose._imported_before_install')          # stands for empose.eval.helpers
+    early.create_model, early.IterativeErrorFeedback = ref_models.create_model, ref_models.IterativeErrorFeedback
+    early.create_default_smpl_model, early.SMPLLayer = ref_smpl.create_default_smpl_model, ref_smpl.SMPLLayer
+    sys.modules[early.__name__] = early
+    try:
+        empose_b200.dropin.install()
+        assert early.IterativeErrorFeedback is IterativeErrorFeedback
+        assert early.create_model is ref_models.create_model and early.SMPLLayer is ref_smpl.SMPLLayer
+        flags = ['--m_type', 'lgd', '--m_num_iterations', '2', '--m_hidden_size', '512', '--m_rnn_init', '--m_average_shape',
+                 '--m_use_gradient', '--use_marker_pos', '--use_marker_ori', '--n_markers', '6', '--window_size', '32']
+        net = early.create_model(ref_shims.make_config(flags), early.SMPLLayer(smpl_npz))
+        assert isinstance(net, IterativeErrorFeedback)
+    finally:
+        sys.modules.pop(early.__name__, None)
+
+
+def test_fp16_guard_static_range_check_and_invalidate(smpl_npz):
+    """The precision guard of the mirror class: BatchNorm-folded weights outside fp16's comfortable range
+    select tf32 before anything runs; wide running statistics alone do not (the fold happens in double); invalidate()
+    changes the cache key that .data writes leave untouched."""
+    net = util.build_module(smpl_npz, precision=native.PRECISION_FP16)
+    hi, lo = net.folded_weight_range()
+    assert 0.0 < lo < hi < 16.0
+    assert net._effective_precision() == native.PRECISION_FP16
+    sd = net.state_dict()
+    # (i) BN statistics over six orders of magnitude, the Linear in front scaled to match: same folded weights
+    g = torch.Generator().manual_seed(3)
+    for name in [k for k in sd if k.endswith('running_var')]:
+        var = torch.exp(torch.empty_like(sd[name]).uniform_(np.log(1e-4), np.log(1e2), generator=g))
+        ratio = torch.sqrt((var + 1e-5) / (sd[name] + 1e-5))
+        lin = name.replace('batch_norm.running_var', 'input_to_hidden') if 'batch_norm' in name else \
+            '.'.join(name.split('.')[:-2] + [str(int(name.split('.')[-2]) - 1)])
+        sd[lin + '.weight'] = sd[lin + '.weight'] * ratio.reshape(-1, 1)
+        sd[lin + '.bias'] = sd[lin + '.bias'] * ratio
+        sd[name.replace('running_var', 'running_mean')] = sd[name.replace('running_var', 'running_mean')] * ratio
+        sd[name] = var
+    net.load_state_dict(sd)
+    hi2, _ = net.folded_weight_range()
+    assert abs(hi2 - hi) < 1e-3 * hi and net._effective_precision() == native.PRECISION_FP16
+    # (ii) a genuinely huge layer: tf32 from the start
+    with torch.no_grad():
+        net.pose_net_iter.hidden_to_output.weight.mul_(1e4)
+    assert net._effective_precision() == native.PRECISION_TF32
+    net.precision_guard = False
+    assert net._effective_precision() == native.PRECISION_FP16
+    # (iii) .data writes change neither data_ptr nor _version: only invalidate() moves the key
+    k0 = net._weights_key(0, net.precision)
+    net.pose_net_iter.hidden_to_output.weight.data.mul_(0.5)
+    assert net._weights_key(0, net.precision) == k0
+    net.invalidate()
+    assert net._weights_key(0, net.precision) != k0

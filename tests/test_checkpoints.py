@@ -63,3 +63,24 @@ def test_reference_experiment_folder_loads_strict(smpl_npz, asset_dir, tmp_path)
     assert rest['epoch'] == 4
     with pytest.raises(ValueError):
         checkpoints.get_model_config(42, experiment_dir=str(tmp_path))
+
+
+def test_checkpoint_loader_refuses_pickled_code(tmp_path, smpl_npz):
+    """A model.pth is a downloaded file: the loader takes tensors and plain containers only, unless the caller opts in."""
+    import os
+    import pickle
+    import util
+    from empose_b200 import checkpoints
+    net = util.build_module(smpl_npz)
+    good = os.path.join(str(tmp_path), 'model.pth')
+    checkpoints.save_checkpoint(good, net, epoch=3, train_loss=torch.tensor(0.5), valid_loss=0.25)
+    extra = checkpoints.load_model_weights(good, net)
+    assert extra['epoch'] == 3 and float(extra['train_loss']) == 0.5
+
+    class Evil(object):
+        def __reduce__(self):
+            return (os.system, ('true',))
+    bad = os.path.join(str(tmp_path), 'evil.pth')
+    torch.save({'model_state_dict': net.state_dict(), 'payload': Evil()}, bad, pickle_module=pickle)
+    with pytest.raises(ValueError, match='unrestricted pickle'):
+        checkpoints.load_model_weights(bad, net)

@@ -486,3 +486,96 @@ def test_irregular_valence_mesh(dev, asset_dir, kind, precision):
         mm = util.max_joint_pos_err_mm(out['joints_hat'][live], want['joints_hat'].numpy()[live])
         util.report('irregular', mesh=kind, general=general, precision=PNAME[precision], rad=rad, mm=mm)
         assert rad <= rad_tol and mm <= mm_tol, (kind, general, rad, mm)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# evidence for the fp16 operand default: adversarial-but-plausible weights and inputs
+# ---------------------------------------------------------------------------------------------------------------------
+def _wide_bn_state_dict(sd, seed):
+    """BatchNorm running variances log-uniform in [1e-4, 1e2] with the Linear in front scaled to match (what training
+    produces: a unit with tiny variance has tiny pre-activations), so the network function is the same but the RAW
+    weights span six orders of magnitude; the folded ones (what the kernels see) must not care."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {k: v.clone() for k, v in sd.items()}
+    for name in [k for k in sd if k.endswith('running_var')]:
+        var = torch.exp(torch.empty_like(sd[name]).uniform_(float(np.log(1e-4)), float(np.log(1e2)), generator=g))
+        ratio = torch.sqrt(var / sd[name])
+        lin = name.replace('batch_norm.running_var', 'input_to_hidden') if 'batch_norm' in name else \
+            '.'.join(name.split('.')[:-2] + [str(int(name.split('.')[-2]) - 1)])
+        sd[lin + '.weight'] = sd[lin + '.weight'] * ratio.reshape(-1, 1)
+        sd[lin + '.bias'] = sd[lin + '.bias'] * ratio
+        mean = name.replace('running_var', 'running_mean')
+        sd[mean] = sd[mean] * ratio
+        sd[name] = var
+    return sd
+
+
+@pytest.mark.parametrize('precision', [native.PRECISION_FP16, native.PRECISION_TF32], ids=PNAME.get)
+def test_wide_batchnorm_statistics(dev, smpl_npz, oracle_smpl, topology, precision):
+    """BN running var in [1e-4, 1e2] (folded scale up to 100x / down to 0.1x of the raw weights): parity bar unchanged."""
+    params = synthetic.synth_window_params(6, 32, seed=61, ragged=True, offsets=True)
+    inp = util.oracle_inputs_from_params(oracle_smpl, topology, params, seed=9)
+    net = util.build_module(smpl_npz, precision=precision, device='cpu')
+    sd = _wide_bn_state_dict(net.state_dict(), seed=4)
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+    assert net._effective_precision() == precision            # the folded weights are as tame as before
+    cfg = oracle_ief.IefConfig(n_markers=12, num_iterations=4, rnn_init=True)
+    osd = {k: v.cpu() for k, v in sd.items() if not k.startswith('smpl.')}
+    want = oracle_ief.ief_forward(cfg, osd, oracle_smpl, topology, **inp)
+    with torch.no_grad():
+        out = net(util.DuckBatch(**inp).to(dev))
+    live = util.valid_frame_mask(params['seq_lengths'], 32)
+    pose = torch.cat([out['root_ori_hat'], out['pose_hat']], dim=-1).cpu().numpy()
+    want_pose = torch.cat([want['root_ori_hat'], want['pose_hat']], dim=-1).numpy()
+    rad = util.max_joint_angle_err(pose[live], want_pose[live])
+    mm = util.max_joint_pos_err_mm(out['joints_hat'].cpu().numpy()[live], want['joints_hat'].numpy()[live])
+    util.report('wide_bn', precision=PNAME[precision], rad=rad, mm=mm)
+    assert rad <= PARITY_RAD and mm <= PARITY_MM, (rad, mm)
+
+
+@pytest.mark.parametrize('precision', PRECISIONS, ids=PNAME.get)
+def test_short_sequences_in_long_windows(dev, smpl_npz, oracle_smpl, topology, precision):
+    """seq_len << F: the gradient features carry the factor F / len (up to 32 here, loss.py:36-41 folded per frame), the
+    largest inputs the iter-MLPs ever see.  Reported per precision; the bar is asserted for the fp32 executor and for the
+    guard's choice (``IterativeErrorFeedback.precision_guard``)."""
+    b, f = 6, 32
+    params = synthetic.synth_window_params(b, f, seed=71, ragged=False, offsets=True)
+    params['seq_lengths'] = np.asarray([1, 2, 3, 5, 8, 32], dtype=params['seq_lengths'].dtype)
+    inp = util.oracle_inputs_from_params(oracle_smpl, topology, params, seed=10)
+    cfg = oracle_ief.IefConfig(n_markers=12, num_iterations=4, rnn_init=True)
+    sd = util.torch_state_dict(synthetic.synth_state_dict(seed=0, n_markers=12, rnn_init=True))
+    want = oracle_ief.ief_forward(cfg, sd, oracle_smpl, topology, **inp)
+    net = util.build_module(smpl_npz, precision=precision, device=dev)
+    with torch.no_grad():
+        out = net(util.DuckBatch(**inp).to(dev))
+    live = util.valid_frame_mask(params['seq_lengths'], f)
+    pose = torch.cat([out['root_ori_hat'], out['pose_hat']], dim=-1).cpu().numpy()
+    want_pose = torch.cat([want['root_ori_hat'], want['pose_hat']], dim=-1).numpy()
+    rad = util.max_joint_angle_err(pose[live], want_pose[live])
+    mm = util.max_joint_pos_err_mm(out['joints_hat'].cpu().numpy()[live], want['joints_hat'].numpy()[live])
+    gmax = float(np.abs(np.stack([h.cpu().numpy() for h in net.pose_hat_history])[:, live]).max())
+    util.report('short_sequences', precision=PNAME[precision], rad=rad, mm=mm, pose_max=gmax)
+    rad_tol, mm_tol = (2e-5, 0.02) if precision == native.PRECISION_FP32 else (PARITY_RAD, PARITY_MM)
+    assert rad <= rad_tol and mm <= mm_tol, (rad, mm)
+
+
+def test_fp16_overflow_falls_back_to_tf32(dev, smpl_npz, oracle_smpl, topology):
+    """Inputs beyond fp16's range (65504): the fp16 pass returns non-finite values, the guard repeats the pass on tf32 tensor
+    cores and returns exactly what an explicit tf32 model returns; with the guard off the caller sees the non-finite result."""
+    params = synthetic.synth_window_params(3, 8, seed=81, offsets=True)
+    inp = util.oracle_inputs_from_params(oracle_smpl, topology, params, seed=11)
+    inp['marker_pos'] = inp['marker_pos'] + 1.0e5
+    batch = util.DuckBatch(**inp).to(dev)
+    net = util.build_module(smpl_npz, precision=native.PRECISION_FP16, device=dev)
+    ref = util.build_module(smpl_npz, precision=native.PRECISION_TF32, device=dev)
+    with torch.no_grad():
+        out, want = net(batch), ref(batch)
+    assert net.precision_fallbacks == 1
+    for k in out:
+        assert torch.isfinite(out[k]).all() and torch.equal(out[k], want[k]), k
+    net.precision_guard = False
+    with torch.no_grad():
+        raw = net(batch)
+    assert not torch.isfinite(raw['pose_hat']).all()
+    assert net.precision_fallbacks == 1
