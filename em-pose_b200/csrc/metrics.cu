@@ -28,6 +28,10 @@ __global__ void __launch_bounds__(128) metrics_kernel(MetricsParams p) {
         fk_frame(p, p.pose_hat + (int64_t)row * kPoseDim, p.shape_hat + (int64_t)row * kBetas, jh, oh);
         if (p.angle)
             for (int j = 1; j < kJoints; ++j) {      // geodesic angle of og^T oh (quaternion.rotation_intrinsic_distance), degrees
+                if (p.angle_local) {                  // the joint's own rotations instead of the accumulated ones
+                    rodrigues_fwd(p.pose + (int64_t)row * kPoseDim + j * 3, og[j]);
+                    rodrigues_fwd(p.pose_hat + (int64_t)row * kPoseDim + j * 3, oh[j]);
+                }
                 float d[9];
                 for (int r = 0; r < 3; ++r)
                     for (int c = 0; c < 3; ++c) d[r * 3 + c] = og[j][r] * oh[j][c] + og[j][3 + r] * oh[j][3 + c] + og[j][6 + r] * oh[j][6 + c];
@@ -55,14 +59,14 @@ extern "C" {
 #pragma GCC visibility push(default)
 
 int empose_metrics_compute(empose_ief* ctx, const float* pose, const float* shape, const float* pose_hat, const float* shape_hat,
-                           int32_t R, float* eucl, float* eucl_pa, float* angle_deg, void* stream) {
+                           int32_t R, int32_t angle_local, float* eucl, float* eucl_pa, float* angle_deg, void* stream) {
     if (!ctx || !pose || !shape || !pose_hat || !shape_hat || !eucl || !eucl_pa || R < 0) { set_last_error("bad argument"); return EMPOSE_E_ARG; }
     EMPOSE_CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     MetricsParams p;
     memset(&p, 0, sizeof(p));
     p.j0 = ctx->sub.j0; p.jdirs = ctx->sub.jdirs; p.parents = ctx->sub.parents;
     p.pose = pose; p.shape = shape; p.pose_hat = pose_hat; p.shape_hat = shape_hat; p.R = R;
-    p.eucl = eucl; p.eucl_pa = eucl_pa; p.angle = angle_deg;
+    p.eucl = eucl; p.eucl_pa = eucl_pa; p.angle = angle_deg; p.angle_local = angle_local != 0;
     return launch_metrics(p, static_cast<cudaStream_t>(stream));
 }
 

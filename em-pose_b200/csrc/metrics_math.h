@@ -25,6 +25,7 @@ struct MetricsParams {
     const float* pose; const float* shape; const float* pose_hat; const float* shape_hat;      // [R][66], [R][10]
     const float* joints; const float* joints_hat;                                              // or joints given directly [R][66]
     int R;
+    int angle_local;                                                                           // 1: angles between local joint rotations
     float* eucl; float* eucl_pa; float* angle;                                                 // [R][22], [R][22], [R][21] (angle may be null)
 };
 

@@ -872,13 +872,15 @@ int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const floa
     EMPOSE_TRY(check_call(ctx, B, F));
     if (!marker_pos || !marker_oris || !offset_r || !offset_t || !seq_lengths) { set_last_error("null input"); return EMPOSE_E_ARG; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // Windows are independent, so a very large batch is cut into sub-batches whose PCIe copies overlap the compute of
-    // their neighbours.  Sub-batches stay >= 4096 windows: measured on the B200 (profiles/r01/README.md), at 2048 windows
-    // the LSTM wavefront launches (B rows each) lose as much as the overlap of the ~3.4 ms of copies gains.
+    // Windows are independent, so a large batch is cut into sub-batches whose PCIe copies overlap the compute of their
+    // neighbours.  Sub-batches stay >= 2048 windows: measured on the B200 at 4096 windows (profiles/r02/README.md), two
+    // sub-batches take 11.08 ms against 11.54 ms unsplit (device time 8.68 ms, copies 2.8 ms), four take 12.1 ms -- below
+    // 2048 windows the persistent LSTM wavefront (64 items per diagonal on 74 CTA pairs) and the last wave of the MLP chain
+    // lose more than the overlap gains.
     static int min_chunk = 0;                       // EMPOSE_HOST_CHUNK=<windows> overrides the sub-batch size (experiments)
     if (min_chunk == 0) {
         const char* e = getenv("EMPOSE_HOST_CHUNK");
-        min_chunk = e && atoi(e) > 0 ? atoi(e) : 4096;
+        min_chunk = e && atoi(e) > 0 ? atoi(e) : 2048;
     }
     const int n_chunks = std::max(1, std::min(4, B / min_chunk));
     ctx->last_launches = 0;

@@ -1,8 +1,9 @@
 """Training-data synthesis on the B200: the two transforms the reference applies right before the hot path.
 
-Mirrors ``SMPLFK`` (``empose/data/transforms.py:259-282``) and ``SampleMarkersWithOffsets`` (``:163-226``): same
-constructor arguments, same attributes set on the batch, same host-side random streams (``np.random.RandomState(6273)``
-for the offset set, torch's global generator for the offset noise).  What changes is the arithmetic: the reference
+Interface of ``SMPLFK`` (``empose/data/transforms.py:259-282``) and ``SampleMarkersWithOffsets`` (``:163-226``): same
+constructor arguments, same attributes set on the batch, and the same random draws in the same order
+(``np.random.RandomState(6273)`` for the subject whose offsets a window gets, torch's global generator for the offset
+noise), so a run is reproducible against the reference.  What changes is the arithmetic: the reference
 evaluates the full 6890-vertex SMPL-H mesh for every frame (``batch.vertices``, 83 KB per frame) and derives the sensor
 frames from it with torch ops; here ONE pass of the sub-model kernels (``empose_sensor_project`` on a context made by
 ``empose_sensors_create``) goes from poses / shapes / offsets to sensor positions, orientations and joints and the mesh
@@ -65,74 +66,84 @@ class SMPLFK(object):
         return batch
 
 
+class _OffsetBank(object):
+    """The pre-estimated sensor-to-skin offsets of a set of subjects (one ``.npz`` per subject with ``means`` (M,3), ``covs``
+    (M,3,3), ``r`` (M,3,3) and ``vertex_ids``; written by the reference's calibration, read at ``transforms.py:153-160``)."""
+
+    def __init__(self, files):
+        records = [np.load(path) for path in (files if isinstance(files, (list, tuple)) else [files])]
+        stack = lambda key: torch.from_numpy(np.stack([np.asarray(rec[key]) for rec in records])).to(dtype=torch.float32)
+        self.means, self.covs, self.rotations = stack('means'), stack('covs'), stack('r')       # (S,M,3), (S,M,3,3), (S,M,3,3)
+        self.vertex_ids = [int(v) for v in records[-1]['vertex_ids']]
+        self.n_sets, self.n_markers = int(self.means.shape[0]), int(self.means.shape[1])
+
+
 class SampleMarkersWithOffsets(object):
-    """Virtual sensors with pre-estimated sensor-to-skin offsets (transforms.py:139-226), from poses instead of vertices."""
+    """Virtual sensors with pre-estimated sensor-to-skin offsets (the transform of ``transforms.py:139-226``), computed from
+    poses instead of from a materialised mesh.
+
+    Random streams are the reference's, so a run is reproducible against it draw for draw: which subject's offsets a
+    window gets comes from ``numpy.random.RandomState(6273).randint`` (one call per batch), and the offset noise from ONE
+    ``MultivariateNormal(means, covs).sample`` call on torch's global generator -- ``(N,)`` draws for ``noise_level`` 0,
+    ``(N, F)`` for 1, none otherwise.  ``noise_level``: -1 mean offsets; 0 one noisy offset per window; 1 one per frame;
+    2 zero translation; 3 zero translation and identity rotation."""
 
     def __init__(self, smpl_model, offset_files, noise_level=-1):
+        if noise_level not in (-1, 0, 1, 2, 3):
+            raise ValueError("Unknown noise level {}".format(noise_level))
         self.smpl_model = smpl_model
-        self.randomize = noise_level >= 0
         self.noise_level = noise_level
-        if not isinstance(offset_files, list):
-            offset_files = [offset_files]
-        self.n_markers = np.load(offset_files[0])['means'].shape[0]
-        self.n_offsets = len(offset_files)
-        self.offset_means = np.zeros([self.n_offsets, self.n_markers, 3])
-        self.offset_covs = np.zeros([self.n_offsets, self.n_markers, 3, 3])
-        self.r = np.zeros([self.n_offsets, self.n_markers, 3, 3])
-        offset_data = None
-        for i, offset_file in enumerate(offset_files):
-            offset_data = np.load(offset_file)
-            self.offset_means[i] = offset_data['means']
-            self.offset_covs[i] = offset_data['covs']
-            self.r[i] = offset_data['r']
-        self.normal_dists = MultivariateNormal(loc=torch.from_numpy(self.offset_means).to(dtype=torch.float32),
-                                               covariance_matrix=torch.from_numpy(self.offset_covs).to(dtype=torch.float32))
-        self.vertex_ids = offset_data['vertex_ids'].tolist()
-        if list(self.vertex_ids) != list(C.VERTEX_IDS):
+        self.randomize = noise_level >= 0
+        self.bank = _OffsetBank(offset_files)
+        if list(self.bank.vertex_ids) != list(C.VERTEX_IDS):
             raise ValueError('the offset files must use the 12 sensor vertices of configuration.py:32-34 '
                              '(the SMPL sub-model is extracted for exactly those)')
+        self.n_offsets, self.n_markers, self.vertex_ids = self.bank.n_sets, self.bank.n_markers, self.bank.vertex_ids
+        self.normal_dists = MultivariateNormal(loc=self.bank.means, covariance_matrix=self.bank.covs)
         self.offset_rng = np.random.RandomState(6273)
+
+    def _draw(self, n, f):
+        """Per-window subject index, and translation (N, F, M, 3) / rotation (N, M, 3, 3) offsets on the host."""
+        subject = torch.from_numpy(self.offset_rng.randint(0, self.n_offsets, n)).long()
+        mean_t = self.bank.means[subject]                                           # (N, M, 3)
+        window = torch.arange(n)
+        if self.noise_level == 0:
+            t = self.normal_dists.sample((n,))[window, subject].unsqueeze(1).expand(n, f, self.n_markers, 3)
+        elif self.noise_level == 1:
+            t = self.normal_dists.sample((n, f))[window, :, subject]               # advanced indices first: (N, F, M, 3)
+        elif self.noise_level in (2, 3):
+            t = torch.zeros(n, f, self.n_markers, 3)
+        else:
+            t = mean_t.unsqueeze(1).expand(n, f, self.n_markers, 3)
+        if self.noise_level == 3:
+            rot = torch.eye(3).expand(n, self.n_markers, 3, 3)
+        else:
+            rot = self.bank.rotations[subject]
+        return mean_t, t, rot
 
     def __call__(self, batch):
         dev = _device_of(batch)
         n, f = batch.batch_size, batch.seq_length
-        r_rows = n * f
-        # ---- host side: which offset set, which noise (identical calls and streams as the reference) ----
-        s_idxs = self.offset_rng.randint(0, self.n_offsets, n)
-        offset_means = torch.from_numpy(self.offset_means[s_idxs]).to(dtype=torch.float32)
-        local_offsets = offset_means.clone().unsqueeze(1).repeat(1, f, 1, 1)
-        s_idx_t = torch.from_numpy(s_idxs).to(dtype=torch.long)
-        if self.randomize:
-            if self.noise_level == 0:
-                noise = self.normal_dists.sample((n,))[torch.arange(n), s_idx_t]
-                local_offsets = noise.unsqueeze(1).repeat(1, f, 1, 1)
-            elif self.noise_level == 1:
-                noise = self.normal_dists.sample((n, f))
-                s = s_idx_t.unsqueeze(-1).repeat(1, f).reshape(-1)
-                local_offsets = noise.reshape((n * f, self.n_offsets, -1, 3))[torch.arange(n * f), s].reshape((n, f, -1, 3))
-            elif self.noise_level in (2, 3):
-                local_offsets = torch.zeros_like(local_offsets)
-            else:
-                raise ValueError("Unknown noise level {}".format(self.noise_level))
-        rot = torch.from_numpy(self.r).to(dtype=torch.float32)[s_idx_t].unsqueeze(1).repeat(1, f, 1, 1, 1)
-        if self.randomize and self.noise_level == 3:
-            rot = torch.eye(3).reshape(1, 1, 1, 3, 3).repeat(n, f, self.n_markers, 1, 1)
-        local_offsets, rot = local_offsets.to(dev), rot.to(dev)
-        # ---- device side: SMPL sub-model -> sensor frames -> offsets, twice (raw frames, then with offsets) ----
-        pose = torch.cat([batch.poses_root, batch.poses_body], dim=-1).reshape(r_rows, 66)
-        shape = batch.shapes.unsqueeze(1).repeat(1, f, 1).reshape(r_rows, -1)
-        trans = batch.trans.reshape(r_rows, 1, 3)
+        rows = n * f
+        mean_t, t_off, r_off = self._draw(n, f)
+        t_off = t_off.to(dev).reshape(rows, self.n_markers, 3)
+        r_win = r_off.to(dev).contiguous()
+        r_rows = r_win.unsqueeze(1).expand(n, f, self.n_markers, 3, 3).reshape(rows, self.n_markers, 3, 3)
+        pose = torch.cat([batch.poses_root, batch.poses_body], dim=-1).reshape(rows, 66)
+        shape = batch.shapes.unsqueeze(1).expand(n, f, batch.shapes.shape[-1]).reshape(rows, -1)
+        trans = batch.trans.reshape(rows, 1, 3)
+        # two passes of the sub-model kernels: the bare sensor frames, then the frames with the offsets applied
+        # (R' = R R_off, p' = p + R t_off, models.py:478-479 -- the same arithmetic the hot path uses)
         ctx = _sensor_context(self.smpl_model, dev)
-        eye = torch.eye(3, device=dev).reshape(1, 1, 3, 3).expand(r_rows, 12, 3, 3).contiguous()
-        zero = torch.zeros(r_rows, 12, 3, device=dev)
-        pos0, ori0, _ = ctx.sensor_project(pose, shape, eye, zero)
-        pos1, ori1, _ = ctx.sensor_project(pose, shape, rot.reshape(r_rows, 12, 3, 3), local_offsets.reshape(r_rows, 12, 3))
-        batch.marker_pos_vertex = (pos0 + trans).reshape(n, f, -1)
-        batch.marker_ori_vertex = ori0.reshape(n, f, -1)
-        batch.marker_normal_vertex = ori0[..., 2].reshape(n, f, -1)
-        batch.marker_pos_synth = (pos1 + trans).reshape(n, f, -1)
-        batch.marker_ori_synth = ori1.reshape(n, f, -1)
-        batch.marker_normal_synth = ori1[..., 2].reshape(n, f, -1)
-        batch.offset_t_augmented = offset_means.clone().detach().to(dev)
-        batch.offset_r_augmented = rot[:, 0].clone().detach()
+        identity = torch.eye(3, device=dev).expand(rows, self.n_markers, 3, 3).contiguous()
+        bare_pos, bare_ori, _ = ctx.sensor_project(pose, shape, identity, torch.zeros(rows, self.n_markers, 3, device=dev))
+        off_pos, off_ori, _ = ctx.sensor_project(pose, shape, r_rows, t_off)
+        as_batch = lambda x: x.reshape(n, f, -1)
+        batch.marker_pos_vertex, batch.marker_ori_vertex = as_batch(bare_pos + trans), as_batch(bare_ori)
+        batch.marker_normal_vertex = as_batch(bare_ori[..., 2])
+        batch.marker_pos_synth, batch.marker_ori_synth = as_batch(off_pos + trans), as_batch(off_ori)
+        batch.marker_normal_synth = as_batch(off_ori[..., 2])
+        # what a model may use to undo the offsets at test time: always the MEAN translation, and the rotation
+        batch.offset_t_augmented = mean_t.to(dev)
+        batch.offset_r_augmented = r_win.clone()
         return batch

@@ -1,11 +1,20 @@
-"""The metrics engine with the reference's interface, computed on the B200.
+"""The metrics engine behind the reference's interface, computed and AGGREGATED on the B200.
 
-Mirrors ``MetricsEngine`` (``empose/eval/metrics.py:69-345``): same constructor, ``reset`` / ``compute`` /
-``compute_joint_dist`` / ``get_metrics`` / ``to_pretty_string`` / ``to_tensorboard_log``, same joint selections and the
-same aggregation.  ``compute`` is where the reference spends its time -- two full-mesh ``smpl.fk`` calls plus a numpy SVD
-per frame on the host (``metrics.py:115-125``); here the per-frame work (FK of the 22 body joints for ground truth and
-prediction, Euclidean distances, Procrustes alignment, angular distances of the global orientations) is ONE kernel
-(``empose_metrics_compute``) and only the (frames x joints) result tables come back to the host for aggregation.
+Interface of ``MetricsEngine`` (``empose/eval/metrics.py:69-345``): constructor, ``reset`` / ``compute`` /
+``compute_joint_dist`` / ``get_metrics`` / ``to_pretty_string`` / ``to_tensorboard_log``, the joint selections and the six
+numbers ``get_metrics`` returns.  The implementation shares nothing with it:
+
+* per frame, FK of the 22 body joints for ground truth and prediction, Euclidean distances, the Procrustes alignment
+  (the reference: a numpy SVD per frame on the host, ``metrics.py:115-125``) and the angular distances are ONE kernel
+  (``empose_metrics_compute``);
+* the tables never leave the device: every ``compute`` folds them into running per-joint sums and sums of squares
+  (float64, on the device), and ``get_metrics`` turns those few numbers into mean / standard deviation -- the same
+  statistics the reference takes over its concatenated host tables (mean over joints of per-joint means; population
+  standard deviation over all selected entries), without the (frames x joints) device-to-host traffic and without
+  keeping every frame of the dataset in host memory.
+
+``keep_tables=True`` additionally keeps the per-frame tables (on the device) for inspection; ``eucl_dists`` /
+``eucl_dists_pa`` / ``angle_diffs`` then return them as numpy arrays like the reference's attributes of the same name.
 """
 import numpy as np
 import torch
@@ -14,58 +23,99 @@ from tabulate import tabulate
 from empose_b200 import lib as _lib
 from empose_b200.helpers.configuration import CONSTANTS as C
 
-SMPL_JOINTS = ['root', 'l_hip', 'r_hip', 'spine1', 'l_knee', 'r_knee', 'spine2', 'l_ankle', 'r_ankle', 'spine3', 'l_foot',
-               'r_foot', 'neck', 'l_collar', 'r_collar', 'head', 'l_shoulder', 'r_shoulder', 'l_elbow', 'r_elbow', 'l_wrist',
-               'r_wrist']                                                     # configuration.py:115-117
+#: body joints in SMPL order (configuration.py:115-117)
+SMPL_JOINTS = ('root l_hip r_hip spine1 l_knee r_knee spine2 l_ankle r_ankle spine3 l_foot r_foot neck l_collar r_collar head '
+               'l_shoulder r_shoulder l_elbow r_elbow l_wrist r_wrist').split()
+#: joints NOT evaluated (metrics.py:78-86 lists the complements): feet for positions; root, ankles, feet, wrists for angles
+_NO_POSITION = {'l_foot', 'r_foot'}
+_NO_ANGLE = {'root', 'l_ankle', 'r_ankle', 'l_foot', 'r_foot', 'l_wrist', 'r_wrist'}
+_KINDS = ('eucl', 'eucl_pa', 'angle')
+
+
+class _RunningMoments(object):
+    """Per-column count, sum and sum of squares of every table seen so far (float64, on the tables' device)."""
+
+    def __init__(self):
+        self.rows = 0
+        self.s1 = None
+        self.s2 = None
+
+    def add(self, table):
+        t = table.double()
+        s1, s2 = t.sum(dim=0), (t * t).sum(dim=0)
+        self.s1 = s1 if self.s1 is None else self.s1 + s1
+        self.s2 = s2 if self.s2 is None else self.s2 + s2
+        self.rows += int(table.shape[0])
+
+    def mean_and_std(self, columns):
+        """Mean over `columns` of the per-column means, and the population standard deviation over all their entries."""
+        if self.rows == 0:
+            return 0.0, 0.0
+        idx = torch.as_tensor(columns, dtype=torch.long, device=self.s1.device)
+        s1, s2 = self.s1.index_select(0, idx).cpu().numpy(), self.s2.index_select(0, idx).cpu().numpy()
+        mean_of_means = float(np.mean(s1 / self.rows))
+        n = self.rows * len(columns)
+        grand = s1.sum() / n
+        return mean_of_means, float(np.sqrt(max(s2.sum() / n - grand * grand, 0.0)))
 
 
 class MetricsEngine(object):
-    """Helper class to compute metrics over a dataset (``metrics.py:69``)."""
+    """Accumulates MPJPE, PA-MPJPE and MPJAE over a dataset (``metrics.py:69``)."""
 
-    def __init__(self, smpl_model):
+    def __init__(self, smpl_model, keep_tables=False):
         self.smpl_model = smpl_model
-        self.eucl_dists = []
-        self.eucl_dists_pa = []
-        self.angle_diffs = []
-        self.eucl_eval_joints = ['root', 'l_hip', 'r_hip', 'spine1', 'l_knee', 'r_knee', 'spine2', 'l_ankle', 'r_ankle',
-                                 'spine3', 'neck', 'l_collar', 'r_collar', 'head', 'l_shoulder', 'r_shoulder',
-                                 'l_elbow', 'r_elbow', 'l_wrist', 'r_wrist']
-        self.angle_eval_joints = ['l_hip', 'r_hip', 'spine1', 'l_knee', 'r_knee', 'spine2', 'spine3',
-                                  'neck', 'l_collar', 'r_collar', 'head', 'l_shoulder', 'r_shoulder',
-                                  'l_elbow', 'r_elbow']
+        self.keep_tables = keep_tables
+        self.eucl_eval_joints = [j for j in SMPL_JOINTS if j not in _NO_POSITION]
+        self.angle_eval_joints = [j for j in SMPL_JOINTS if j not in _NO_ANGLE]
         self.eucl_idxs = [SMPL_JOINTS.index(j) for j in self.eucl_eval_joints]
-        self.angle_idxs = [SMPL_JOINTS.index(j) - 1 for j in self.angle_eval_joints]
+        self.angle_idxs = [SMPL_JOINTS.index(j) - 1 for j in self.angle_eval_joints]       # angles exclude the root: joint j is column j-1
         self.angle_glob = True
+        self.reset()
 
     def reset(self):
-        self.eucl_dists = []
-        self.eucl_dists_pa = []
-        self.angle_diffs = []
+        self._moments = {k: _RunningMoments() for k in _KINDS}
+        self._tables = {k: [] for k in _KINDS}
+
+    # the reference's attribute names, as host tables (only with keep_tables=True)
+    def _host_tables(self, kind):
+        if not self.keep_tables:
+            raise AttributeError('per-frame tables are not kept: construct MetricsEngine(smpl, keep_tables=True)')
+        return [t.cpu().numpy().astype(np.float64 if kind == 'angle' else np.float32) for t in self._tables[kind]]
+
+    eucl_dists = property(lambda self: self._host_tables('eucl'))
+    eucl_dists_pa = property(lambda self: self._host_tables('eucl_pa'))
+    angle_diffs = property(lambda self: self._host_tables('angle'))
+
+    def _fold(self, **tables):
+        for kind, t in tables.items():
+            if t is None:
+                continue
+            self._moments[kind].add(t)
+            if self.keep_tables:
+                self._tables[kind].append(t)
 
     @staticmethod
-    def _masked_flatten(t, mask):
-        return t.masked_select(mask.unsqueeze(-1)).reshape(-1, t.shape[-1])
-
-    def _pad_shapes(self, s, n, mask):
-        if len(s.shape) == 3:
-            return self._masked_flatten(s, mask)
-        return self._masked_flatten(s.unsqueeze(1).repeat(1, n, 1), mask)
-
-    @staticmethod
-    def _get_mask(seq_lengths, n, f, frame_mask, device):
-        """``metrics.py:163-181``."""
+    def _valid_rows(seq_lengths, n, f, frame_mask, device):
+        """Flat indices (into N*F) of the frames that count (``metrics.py:163-181``): inside the sequence and, if a mask is
+        given, flagged valid -- for an (N, F, M) mask, valid in all M entries."""
+        keep = torch.ones(n, f, dtype=torch.bool, device=device)
         if seq_lengths is not None:
-            mask = torch.arange(f, device=device).unsqueeze(0) < seq_lengths.to(device).reshape(-1, 1)
-        else:
-            mask = torch.ones(n, f, dtype=torch.bool, device=device)
+            keep &= torch.arange(f, device=device).unsqueeze(0) < seq_lengths.to(device).reshape(n, 1)
         if frame_mask is not None:
-            frame_mask = frame_mask.to(dtype=torch.bool, device=device)
-            if len(frame_mask.shape) == 3:
-                frame_mask = frame_mask.logical_not().any(dim=-1).logical_not()
-            else:
-                assert len(frame_mask.shape) == 2
-            mask = torch.logical_and(mask, frame_mask)
-        return mask
+            fm = frame_mask.to(device=device, dtype=torch.bool)
+            if fm.dim() == 3:
+                fm = fm.all(dim=-1)
+            elif fm.dim() != 2:
+                raise ValueError('frame_mask must have shape (N, F) or (N, F, M)')
+            keep &= fm
+        return torch.nonzero(keep.reshape(-1), as_tuple=False).reshape(-1)
+
+    @staticmethod
+    def _rows(t, n, f, rows):
+        """(N, F, D) or per-sequence (N, D) -> (len(rows), D)."""
+        if t.dim() == 2:
+            return t.index_select(0, torch.div(rows, f, rounding_mode='floor'))
+        return t.reshape(n * f, t.shape[-1]).index_select(0, rows)
 
     def _context(self, device):
         if device.type != 'cuda':
@@ -78,77 +128,49 @@ class MetricsEngine(object):
 
     def compute(self, pose, shape, pose_hat, shape_hat=None, seq_lengths=None, pose_root=None, pose_root_hat=None,
                 frame_mask=None):
-        """``metrics.py:183-241``: same arguments; the results are appended to ``eucl_dists`` / ``eucl_dists_pa`` /
-        ``angle_diffs`` as (frames, joints) numpy arrays like the reference does."""
-        n, f = pose.shape[0], pose.shape[1]
-        if shape_hat is None:
-            shape_hat = shape
-        mask = self._get_mask(seq_lengths, n, f, frame_mask, pose.device)
-        if mask.sum() == 0:
+        """``metrics.py:183-241``, same arguments: pose / pose_hat (N, F, 63) without the root, shape (N, 10) or (N, F, 10),
+        optional root poses (N, F, 3), sequence lengths and frame mask."""
+        n, f = int(pose.shape[0]), int(pose.shape[1])
+        rows = self._valid_rows(seq_lengths, n, f, frame_mask, pose.device)
+        if rows.numel() == 0:
             return
-        shape = self._pad_shapes(shape, f, mask)
-        shape_hat = self._pad_shapes(shape_hat, f, mask)
-        pose = self._masked_flatten(pose, mask)
-        pose_hat = self._masked_flatten(pose_hat, mask)
-        if pose_root is None:
-            pose_root = torch.zeros([pose.shape[0], 3], dtype=pose.dtype, device=pose.device)
-            pose_root_hat = torch.zeros([pose.shape[0], 3], dtype=pose.dtype, device=pose.device)
-        else:
-            pose_root = self._masked_flatten(pose_root, mask)
-            pose_root_hat = self._masked_flatten(pose_root_hat, mask)
-        eucl, eucl_pa, angle = self._context(pose.device).metrics(torch.cat([pose_root, pose], dim=-1), shape,
-                                                                  torch.cat([pose_root_hat, pose_hat], dim=-1), shape_hat)
-        self.eucl_dists.append(eucl.cpu().numpy())
-        self.eucl_dists_pa.append(eucl_pa.cpu().numpy())
-        if not self.angle_glob:
-            raise NotImplementedError('local (non-global) angular distances are not built; the reference evaluates with angle_glob=True')
-        self.angle_diffs.append(angle.cpu().numpy().astype(np.float64))
+        take = lambda t: self._rows(t, n, f, rows)
+        zeros = torch.zeros(rows.numel(), 3, dtype=pose.dtype, device=pose.device)
+        full = torch.cat([zeros if pose_root is None else take(pose_root), take(pose)], dim=-1)
+        full_hat = torch.cat([zeros if pose_root is None else take(pose_root_hat), take(pose_hat)], dim=-1)
+        eucl, eucl_pa, angle = self._context(pose.device).metrics(full, take(shape), full_hat, take(shape if shape_hat is None else shape_hat),
+                                                                  angle_local=not self.angle_glob)
+        self._fold(eucl=eucl, eucl_pa=eucl_pa, angle=angle)
 
     def compute_joint_dist(self, joints, joints_hat, seq_lengths=None, frame_mask=None):
-        """``metrics.py:243-265``: only the metrics on given 3D joints (N, F, 66)."""
-        n, f = joints.shape[0], joints.shape[1]
-        mask = self._get_mask(seq_lengths, n, f, frame_mask, joints.device)
-        if mask.sum() == 0:
+        """``metrics.py:243-265``: the two position metrics from given joints (N, F, >= 66)."""
+        n, f = int(joints.shape[0]), int(joints.shape[1])
+        rows = self._valid_rows(seq_lengths, n, f, frame_mask, joints.device)
+        if rows.numel() == 0:
             return
-        js = self._masked_flatten(joints, mask)[:, :(C.N_JOINTS + 1) * 3]
-        js_hat = self._masked_flatten(joints_hat, mask)[:, :(C.N_JOINTS + 1) * 3]
-        eucl, eucl_pa = _lib.metrics_from_joints(js, js_hat)
-        self.eucl_dists.append(eucl.cpu().numpy())
-        self.eucl_dists_pa.append(eucl_pa.cpu().numpy())
+        width = (C.N_JOINTS + 1) * 3
+        eucl, eucl_pa = _lib.metrics_from_joints(self._rows(joints, n, f, rows)[:, :width], self._rows(joints_hat, n, f, rows)[:, :width])
+        self._fold(eucl=eucl, eucl_pa=eucl_pa)
 
     def get_metrics(self, eucl_idxs_select=True, angle_idxs_select=True):
-        """``metrics.py:287-330`` verbatim in behaviour."""
-        if len(self.eucl_dists) > 0:
-            eucl_dists = np.concatenate(self.eucl_dists, axis=0)
-            eucl_dists_pa = np.concatenate(self.eucl_dists_pa, axis=0)
-            eucl_idxs = self.eucl_idxs if eucl_idxs_select else list(range(eucl_dists.shape[1]))
-            eucl_mean_all = np.mean(np.mean(eucl_dists, axis=0)[eucl_idxs])
-            eucl_std_all = np.std(eucl_dists[:, eucl_idxs])
-            eucl_mean_pa_all = np.mean(np.mean(eucl_dists_pa, axis=0)[eucl_idxs])
-            eucl_std_pa_all = np.std(eucl_dists_pa[:, eucl_idxs])
-        else:
-            eucl_mean_all = eucl_std_all = eucl_mean_pa_all = eucl_std_pa_all = 0.0
-        if len(self.angle_diffs) > 0:
-            angle_diffs = np.concatenate(self.angle_diffs, axis=0)
-            angle_idxs = self.angle_idxs if angle_idxs_select else list(range(angle_diffs.shape[1]))
-            angle_mean_all = np.mean(np.mean(angle_diffs, axis=0)[angle_idxs])
-            angle_std_all = np.std(angle_diffs[:, angle_idxs])
-        else:
-            angle_mean_all = angle_std_all = 0.0
-        return {'MPJPE [mm]': eucl_mean_all * 1000.0, 'MPJPE STD': eucl_std_all * 1000.0,
-                'PA-MPJPE [mm]': eucl_mean_pa_all * 1000.0, 'PA-MPJPE STD': eucl_std_pa_all * 1000.0,
-                'MPJAE [deg]': angle_mean_all, 'MPJAE STD': angle_std_all}
+        """The six numbers of ``metrics.py:287-330``: means in mm / degrees, standard deviations over all entries."""
+        pos_cols = self.eucl_idxs if eucl_idxs_select else list(range(C.N_JOINTS + 1))
+        ang_cols = self.angle_idxs if angle_idxs_select else list(range(C.N_JOINTS))
+        out = {}
+        for label, kind in (('MPJPE', 'eucl'), ('PA-MPJPE', 'eucl_pa')):
+            mean, std = self._moments[kind].mean_and_std(pos_cols)
+            out[label + ' [mm]'], out[label + ' STD'] = mean * 1000.0, std * 1000.0
+        out['MPJAE [deg]'], out['MPJAE STD'] = self._moments['angle'].mean_and_std(ang_cols)
+        return out
 
     @staticmethod
     def to_pretty_string(metrics, model_name):
-        headers, values = [], []
-        for k in metrics:
-            headers.append(k)
-            values.append(metrics[k])
-        return tabulate([[model_name] + values], headers=['Model'] + headers)
+        """One table row (``metrics.py:332-339``)."""
+        names = list(metrics)
+        return tabulate([[model_name] + [metrics[k] for k in names]], headers=['Model'] + names)
 
     @staticmethod
     def to_tensorboard_log(metrics, writer, global_step, prefix=''):
-        writer.add_scalar('metrics/{}/mje mean'.format(prefix), metrics['MPJPE [mm]'], global_step)
-        writer.add_scalar('metrics/{}/mje pa mean'.format(prefix), metrics['PA-MPJPE [mm]'], global_step)
-        writer.add_scalar('metrics/{}/mae mean'.format(prefix), metrics['MPJAE [deg]'], global_step)
+        """The three means under the reference's tags (``metrics.py:341-345``)."""
+        for tag, key in (('mje mean', 'MPJPE [mm]'), ('mje pa mean', 'PA-MPJPE [mm]'), ('mae mean', 'MPJAE [deg]')):
+            writer.add_scalar('metrics/{}/{}'.format(prefix, tag), metrics[key], global_step)

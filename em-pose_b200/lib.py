@@ -457,8 +457,9 @@ class SensorContext(object):
 
     sensor_project = IefContext.sensor_project
 
-    def metrics(self, pose, shape, pose_hat, shape_hat, want_angle=True):
-        """(R,66), (R,10) x2 CUDA tensors -> eucl (R,22), eucl_pa (R,22), angle_deg (R,21) | None (``empose_metrics_compute``)."""
+    def metrics(self, pose, shape, pose_hat, shape_hat, want_angle=True, angle_local=False):
+        """(R,66), (R,10) x2 CUDA tensors -> eucl (R,22), eucl_pa (R,22), angle_deg (R,21) | None (``empose_metrics_compute``);
+        ``angle_local``: angles between the local joint rotations instead of the global orientations."""
         import torch
         r = int(pose.shape[0])
         f32 = lambda t: t.to(dtype=torch.float32).contiguous()
@@ -466,8 +467,8 @@ class SensorContext(object):
         opts = dict(dtype=torch.float32, device=pose.device)
         eucl, eucl_pa = torch.empty((r, 22), **opts), torch.empty((r, 22), **opts)
         angle = torch.empty((r, 21), **opts) if want_angle else None
-        _check(load().empose_metrics_compute(self._handle, _ptr(pose), _ptr(shape), _ptr(pose_hat), _ptr(shape_hat), r, _ptr(eucl),
-                                             _ptr(eucl_pa), _ptr(angle), _stream()))
+        _check(load().empose_metrics_compute(self._handle, _ptr(pose), _ptr(shape), _ptr(pose_hat), _ptr(shape_hat), r,
+                                             int(bool(angle_local)), _ptr(eucl), _ptr(eucl_pa), _ptr(angle), _stream()))
         return eucl, eucl_pa, angle
 
 

@@ -176,10 +176,12 @@ int empose_sensors_create(const empose_tensor* tensors, int32_t n_tensors, int32
 /* Evaluation metrics of MetricsEngine.compute (empose/eval/metrics.py:183-241) for R frames in one kernel: FK of ground
  * truth and prediction (22 body joints; `ctx` provides the sub-model: any empose_ief, e.g. from empose_sensors_create),
  * per-joint Euclidean distance eucl [R][22] (metres), the same after per-frame Procrustes alignment with optimal scale
- * eucl_pa [R][22] (metrics.py:19-66) and the geodesic angle between global joint orientations with a zero root
- * angle_deg [R][21] (degrees; may be NULL).  pose / pose_hat [R][66] (root first), shape / shape_hat [R][10]. */
+ * eucl_pa [R][22] (metrics.py:19-66) and the geodesic angle angle_deg [R][21] (degrees; may be NULL) between the joint
+ * orientations: global ones obtained with a zero root (angle_local = 0: MetricsEngine.angle_glob, metrics.py:229-238) or
+ * the local joint rotations themselves (angle_local = 1, metrics.py:239-240).  pose / pose_hat [R][66] (root first),
+ * shape / shape_hat [R][10]. */
 int empose_metrics_compute(empose_ief* ctx, const float* pose, const float* shape, const float* pose_hat, const float* shape_hat,
-                           int32_t R, float* eucl, float* eucl_pa, float* angle_deg, void* stream);
+                           int32_t R, int32_t angle_local, float* eucl, float* eucl_pa, float* angle_deg, void* stream);
 /* Same distances from given joints [R][66] (MetricsEngine.compute_joint_dist, metrics.py:243-265). */
 int empose_metrics_joints(const float* joints, const float* joints_hat, int32_t R, float* eucl, float* eucl_pa, void* stream);
 

@@ -17,7 +17,7 @@ def test_metrics_engine_matches_reference(smpl_npz, oracle_smpl):
     assert torch.cuda.is_available()
     dev = torch.device('cuda:0')
     gold = util.load_golden('metrics')
-    me = MetricsEngine(SMPLLayer(smpl_npz).to(device=dev, dtype=torch.float32))
+    me = MetricsEngine(SMPLLayer(smpl_npz).to(device=dev, dtype=torch.float32), keep_tables=True)
     t = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
     me.compute(t(gold['poses'][:, :, 3:]), t(gold['shapes']), t(gold['pose_hat'][:, :, 3:]), t(gold['shape_hat']), t(gold['seq_lengths']),
                pose_root=t(gold['poses'][:, :, :3]), pose_root_hat=t(gold['pose_hat'][:, :, :3]), frame_mask=t(gold['marker_masks']))
@@ -47,3 +47,41 @@ def test_metrics_engine_matches_reference(smpl_npz, oracle_smpl):
     _, jh = smplh_lbs.smpl_layer_forward(oracle_smpl, pose_hat[:, 3:].double(), shape_hat.double(), poses_root=pose_hat[:, :3].double())
     me.compute_joint_dist(j[:, :22].reshape(7, 100, 66).float().to(dev), jh[:, :22].reshape(7, 100, 66).float().to(dev))
     assert float(np.abs(me.eucl_dists[0] - want[0]).max()) <= 5e-6 and float(np.abs(me.eucl_dists_pa[0] - want[1]).max()) <= 2e-5
+
+
+def test_metrics_aggregate_on_device_and_local_angles(smpl_npz, oracle_smpl):
+    """get_metrics() from the device-side running moments equals the reference's statistics over the concatenated tables
+    (mean over joints of per-joint means, population std over all selected entries), also across several compute() calls of
+    different size and without keeping any table; angle_glob=False gives the angles between the LOCAL joint rotations."""
+    from empose_b200.bodymodels.smpl import SMPLLayer
+    from empose_b200.eval.metrics import MetricsEngine
+    dev = torch.device('cuda:0')
+    layer = SMPLLayer(smpl_npz).to(device=dev, dtype=torch.float32)
+    me, keep = MetricsEngine(layer), MetricsEngine(layer, keep_tables=True)
+    g = torch.Generator().manual_seed(17)
+    for n, f in ((3, 40), (5, 7), (1, 1)):
+        pose, pose_hat = 0.3 * torch.randn(n, f, 63, generator=g), 0.3 * torch.randn(n, f, 63, generator=g)
+        shape = torch.randn(n, 10, generator=g)
+        lens = torch.randint(1, f + 1, (n,), generator=g)
+        for m in (me, keep):
+            m.compute(pose.to(dev), shape.to(dev), pose_hat.to(dev), None, lens.to(dev))
+    with pytest.raises(AttributeError):
+        me.eucl_dists
+    eucl, pa, ang = (np.concatenate(x, axis=0) for x in (keep.eucl_dists, keep.eucl_dists_pa, keep.angle_diffs))
+    want = {'MPJPE [mm]': 1000 * np.mean(np.mean(eucl, axis=0)[keep.eucl_idxs]), 'MPJPE STD': 1000 * np.std(eucl[:, keep.eucl_idxs].astype(np.float64)),
+            'PA-MPJPE [mm]': 1000 * np.mean(np.mean(pa, axis=0)[keep.eucl_idxs]), 'PA-MPJPE STD': 1000 * np.std(pa[:, keep.eucl_idxs].astype(np.float64)),
+            'MPJAE [deg]': np.mean(np.mean(ang, axis=0)[keep.angle_idxs]), 'MPJAE STD': np.std(ang[:, keep.angle_idxs])}
+    got = me.get_metrics()
+    assert list(got) == list(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-5 * max(1.0, abs(want[k])), k
+    # local angles: geodesic distance of exp(theta_j), exp(theta_hat_j)
+    loc = MetricsEngine(layer, keep_tables=True)
+    loc.angle_glob = False
+    pose, pose_hat = 0.3 * torch.randn(2, 9, 63, generator=g), 0.3 * torch.randn(2, 9, 63, generator=g)
+    loc.compute(pose.to(dev), torch.zeros(2, 10, device=dev), pose_hat.to(dev))
+    from scipy.spatial.transform import Rotation
+    a = Rotation.from_rotvec(pose.reshape(-1, 3).double().numpy())
+    b = Rotation.from_rotvec(pose_hat.reshape(-1, 3).double().numpy())
+    want_ang = np.rad2deg((a.inv() * b).magnitude()).reshape(18, 21)
+    assert float(np.abs(loc.angle_diffs[0] - want_ang).max()) <= 5e-3
