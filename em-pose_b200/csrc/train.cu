@@ -166,6 +166,9 @@ struct TrainPlan {
     float *theta = nullptr, *beta = nullptr, *dtheta = nullptr, *dbeta = nullptr;
     float *pf = nullptr, *vpoff = nullptr, *dvp = nullptr, *dpf = nullptr, *gth_part = nullptr;
     float *jrest = nullptr, *dj = nullptr, *offsets = nullptr;
+    cudaStream_t last_stream = nullptr;          // of the last backward pass (empose_train_loss_values)
+    empose_loss_weights last_weights = {0.0f, 0.0f, 0.0f, 0.0f};
+    bool last_fk = false, backward_done = false;
     int32_t* seq_len = nullptr;
     float* hist[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // pose, shape, joints, markers, markers_ori: [N+1][R][dof]
     float *g_theta = nullptr, *g_beta = nullptr;                         // [N+1][R][66|10]
@@ -692,8 +695,23 @@ int train_forward(empose_train* t, TrainPlan& pl, const float* marker_pos, const
     return EMPOSE_OK;
 }
 
+int read_losses(empose_train* t, TrainPlan& pl, float* loss_vals) {
+    double sums[4];
+    EMPOSE_CUDA_TRY(cudaMemcpyAsync(sums, pl.loss_sums, sizeof(sums), cudaMemcpyDeviceToHost, pl.last_stream));
+    EMPOSE_CUDA_TRY(cudaStreamSynchronize(pl.last_stream));      // the reference synchronises here too (5 x .cpu().item(), models.py:676-680)
+    const double n1 = (double)(t->cfg.num_iterations + 1);
+    const empose_loss_weights& w = pl.last_weights;
+    const double fk_sum = pl.last_fk ? sums[3] : 0.0;
+    loss_vals[0] = (float)(sums[0] / n1);
+    loss_vals[1] = (float)(sums[1] / n1);
+    loss_vals[2] = (float)(sums[2] / n1);
+    loss_vals[3] = (float)(fk_sum / n1);
+    loss_vals[4] = (float)((w.pose_weight * sums[0] + w.fk_weight * fk_sum + w.shape_weight * sums[1] + w.reprojection_weight * sums[2]) / n1);
+    return EMPOSE_OK;
+}
+
 int train_backward(empose_train* t, TrainPlan& pl, const float* poses_gt, const float* shapes_gt, const float* joints_gt,
-                   const empose_loss_weights& w, float* loss_vals, cudaStream_t s) {
+                   const empose_loss_weights& w, float* loss_vals, cudaEvent_t dense_ready, cudaStream_t s) {
     const empose_ief* ctx = t->base;
     const empose_ief_config& cfg = t->cfg;
     const int B = pl.B, F = pl.F, R = pl.R, H = cfg.rnn_hidden_size, L = cfg.rnn_num_layers, N = cfg.num_iterations;
@@ -701,6 +719,7 @@ int train_backward(empose_train* t, TrainPlan& pl, const float* poses_gt, const 
     const int rnd = ctx->round ? 1 : 0;
     const bool fk = w.fk_weight > 0.0f && joints_gt != nullptr;
     float* G = t->grads;
+    bool dense_done = false;
 
     // ---- loss values (models.py:646-680) ----
     LossParams lp;
@@ -753,6 +772,20 @@ int train_backward(empose_train* t, TrainPlan& pl, const float* poses_gt, const 
         t->launches += 5;
         if (rnd) { EMPOSE_TRY(launch_round_inplace(pl.d_init_masked, R, kInitBetaCol + kBetas, kInitLd, s)); ++t->launches; }
         EMPOSE_TRY(run(t, pl, pl.heads_dx, mt_R, s));
+        // Everything the dense weight gradients (iter-MLPs, heads) contract is known now, and the transposes of the LSTM's
+        // FORWARD data do not depend on the backward-through-time sweep: do both first, so that the dense bucket of the
+        // flat gradient is final -- and can be all-reduced -- while the sweep runs.
+        for (int l = 0; l < L; ++l) {
+            EMPOSE_TRY(launch_transpose(pl.hseq[l], H, R, H, 1, F, 0, pl.hprevT[l], pl.ldT, s));
+            EMPOSE_TRY(launch_transpose(pl.hseq[l], H, R, H, 0, 1, 0, pl.hT[l], pl.ldT, s));
+            t->launches += 2;
+        }
+        EMPOSE_TRY(launch_transpose(pl.xin, ctx->in_stride, R, ctx->in_size, 0, 1, 0, pl.xinT, pl.ldT, s));
+        ++t->launches;
+        EMPOSE_TRY(run(t, pl, pl.dw512, ceil_div(cfg.hidden_size, kTileM), s));
+        EMPOSE_TRY(run(t, pl, pl.dw_small, 1, s));
+        dense_done = true;
+        if (dense_ready) EMPOSE_CUDA_TRY(cudaEventRecord(dense_ready, s));
         for (int l = 0; l < L; ++l) {
             EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.dh_rec[l], 0, (size_t)B * H * 4, s));
             EMPOSE_CUDA_TRY(cudaMemsetAsync(pl.dc_rec[l], 0, (size_t)B * H * 4, s));
@@ -774,34 +807,22 @@ int train_backward(empose_train* t, TrainPlan& pl, const float* poses_gt, const 
         for (int l = 0; l < L; ++l) {
             EMPOSE_TRY(launch_col_sum(pl.dgall[l], 4 * H, R, 4 * H, pl.col_scratch, G + LY.lstm.bih[l], G + LY.lstm.bhh[l], s));
             EMPOSE_TRY(launch_transpose(pl.dgall[l], 4 * H, R, 4 * H, 0, 1, 0, pl.dgT[l], pl.ldT, s));
-            EMPOSE_TRY(launch_transpose(pl.hseq[l], H, R, H, 1, F, 0, pl.hprevT[l], pl.ldT, s));
-            EMPOSE_TRY(launch_transpose(pl.hseq[l], H, R, H, 0, 1, 0, pl.hT[l], pl.ldT, s));
-            t->launches += 5;
+            t->launches += 3;
         }
-        EMPOSE_TRY(launch_transpose(pl.xin, ctx->in_stride, R, ctx->in_size, 0, 1, 0, pl.xinT, pl.ldT, s));
-        ++t->launches;
     } else {
         EMPOSE_TRY(mlp_backward(t, pl, pl.pose_init, true, s));
         EMPOSE_TRY(mlp_backward(t, pl, pl.shape_init, false, s));
     }
-    // ---- all weight gradients: dW += dz^T x, contraction over the rows ----
-    EMPOSE_TRY(run(t, pl, pl.dw512, ceil_div(cfg.hidden_size, kTileM), s));
-    EMPOSE_TRY(run(t, pl, pl.dw_small, 1, s));
+    // ---- weight gradients: dW += dz^T x, contraction over the rows ----
+    if (!dense_done) {
+        EMPOSE_TRY(run(t, pl, pl.dw512, ceil_div(cfg.hidden_size, kTileM), s));
+        EMPOSE_TRY(run(t, pl, pl.dw_small, 1, s));
+        if (dense_ready) EMPOSE_CUDA_TRY(cudaEventRecord(dense_ready, s));
+    }
     if (cfg.rnn_init) EMPOSE_TRY(run(t, pl, pl.dw_lstm, ceil_div(4 * H, kTileM), s));
 
-    double sums[4];
-    EMPOSE_CUDA_TRY(cudaMemcpyAsync(sums, pl.loss_sums, sizeof(sums), cudaMemcpyDeviceToHost, s));
-    EMPOSE_CUDA_TRY(cudaStreamSynchronize(s));      // the reference synchronises here too (5 x .cpu().item(), models.py:676-680)
-    if (loss_vals) {
-        const double n1 = (double)(N + 1);
-        const double fk_sum = fk ? sums[3] : 0.0;
-        loss_vals[0] = (float)(sums[0] / n1);
-        loss_vals[1] = (float)(sums[1] / n1);
-        loss_vals[2] = (float)(sums[2] / n1);
-        loss_vals[3] = (float)(fk_sum / n1);
-        loss_vals[4] = (float)((w.pose_weight * sums[0] + w.fk_weight * fk_sum + w.shape_weight * sums[1] +
-                                w.reprojection_weight * sums[2]) / n1);
-    }
+    pl.last_stream = s; pl.last_weights = w; pl.last_fk = fk;
+    if (loss_vals) EMPOSE_TRY(read_losses(t, pl, loss_vals));
     return EMPOSE_OK;
 }
 
@@ -883,13 +904,22 @@ int empose_train_forward(empose_train* t, const float* marker_pos, const float* 
 }
 
 int empose_train_backward(empose_train* t, const float* poses_gt, const float* shapes_gt, const float* joints_gt,
-                          const empose_loss_weights* weights, float* loss_vals, void* stream) {
+                          const empose_loss_weights* weights, float* loss_vals, void* dense_ready_event, void* stream) {
     if (!t || !poses_gt || !shapes_gt || !weights) { set_last_error("null argument"); return EMPOSE_E_ARG; }
     if (!t->plan || !t->plan->forward_done) { set_last_error("empose_train_backward needs a preceding empose_train_forward"); return EMPOSE_E_ARG; }
     EMPOSE_CUDA_TRY(cudaSetDevice(t->cfg.device));
-    const int rc = train_backward(t, *t->plan, poses_gt, shapes_gt, joints_gt, *weights, loss_vals, static_cast<cudaStream_t>(stream));
+    const int rc = train_backward(t, *t->plan, poses_gt, shapes_gt, joints_gt, *weights, loss_vals,
+                                  static_cast<cudaEvent_t>(dense_ready_event), static_cast<cudaStream_t>(stream));
     t->plan->forward_done = false;
+    t->plan->backward_done = rc == EMPOSE_OK;
     return rc;
+}
+
+int empose_train_loss_values(empose_train* t, float* loss_vals) {
+    if (!t || !loss_vals) { set_last_error("null argument"); return EMPOSE_E_ARG; }
+    if (!t->plan || !t->plan->backward_done) { set_last_error("empose_train_loss_values needs a preceding empose_train_backward"); return EMPOSE_E_ARG; }
+    EMPOSE_CUDA_TRY(cudaSetDevice(t->cfg.device));
+    return read_losses(t, *t->plan, loss_vals);
 }
 
 int64_t empose_train_last_launch_count(const empose_train* t) { return t ? t->launches : 0; }

@@ -86,6 +86,46 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
     a[row * a_ld + c] = maybe_round(y, round_out);
 }
 
+// Same as bn_apply_kernel for n and both pitches multiples of 4 (the hidden layers): a thread owns FOUR consecutive columns of
+// kApplyVecRows rows, so the per-column constants are formed once and every access is 16 bytes -- the pass is pure HBM
+// traffic (read z, write a), which the scalar form reaches only a third of.
+constexpr int kApplyVecRows = 8;
+__global__ void __launch_bounds__(256) bn_apply_vec_kernel(const float* __restrict__ z, int64_t ld, int R, int n,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ alpha, int round_out, float* __restrict__ a,
+                                                           int64_t a_ld, int S) {
+    const int n4 = n >> 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = (int)(t % n4);
+    const int64_t rb = t / n4;                         // row block
+    const int64_t row0 = rb * kApplyVecRows;
+    if (row0 >= (int64_t)S * R) return;
+    const int c = c4 * 4;
+    const float al = alpha[0];
+    int seg = -1;
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f), mu = be, is = g;
+    if (gamma) { g = *reinterpret_cast<const float4*>(gamma + c); be = *reinterpret_cast<const float4*>(beta + c); }
+    const int64_t row_end = min(row0 + kApplyVecRows, (int64_t)S * R);
+    for (int64_t row = row0; row < row_end; ++row) {
+        const int sg = (int)(row / R);
+        if (gamma && sg != seg) {
+            seg = sg;
+            mu = *reinterpret_cast<const float4*>(mean + seg * n + c);
+            is = *reinterpret_cast<const float4*>(invstd + seg * n + c);
+        }
+        const float4 v = *reinterpret_cast<const float4*>(z + row * ld + c);
+        float y[4] = {v.x, v.y, v.z, v.w};
+        if (gamma) {          // the scalar kernel's association: gamma * ((z - mean) * invstd) + beta
+            y[0] = g.x * ((y[0] - mu.x) * is.x) + be.x; y[1] = g.y * ((y[1] - mu.y) * is.y) + be.y;
+            y[2] = g.z * ((y[2] - mu.z) * is.z) + be.z; y[3] = g.w * ((y[3] - mu.w) * is.w) + be.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { y[q] = y[q] > 0.0f ? y[q] : al * y[q]; y[q] = maybe_round(y[q], round_out); }
+        *reinterpret_cast<float4*>(a + row * a_ld + c) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ da, int64_t da_ld, const float* __restrict__ z,
                                                             int64_t z_ld, int R, int n, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -140,6 +180,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     const float al = alpha[0];
     const int r0 = blockIdx.x * kApplyRows;
     const int rows = min(kApplyRows, R - r0);
+    if ((n & 3) == 0 && (da_ld & 3) == 0 && (z_ld & 3) == 0 && (dz_ld & 3) == 0 && (((uintptr_t)da | (uintptr_t)z | (uintptr_t)dz) & 15) == 0) {
+        // 16-byte accesses: four columns per thread and step (same arithmetic, same association as the scalar loop below)
+        const int n4 = n >> 2;
+        for (int i = threadIdx.x; i < rows * n4; i += blockDim.x) {
+            const int r = i / n4, c = (i - r * n4) * 4;
+            const int64_t row = (int64_t)seg * R + r0 + r;
+            const float4 d4 = *reinterpret_cast<const float4*>(da + row * da_ld + c), z4 = *reinterpret_cast<const float4*>(z + row * z_ld + c);
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (gamma) {
+                    const float xh = (zz[q] - c_mu[c + q]) * c_is[c + q];
+                    const float y = c_g[c + q] * xh + c_b[c + q];
+                    const float dy = y > 0.0f ? dd[q] : al * dd[q];
+                    o[q] = c_g[c + q] * c_is[c + q] * (dy - c_m1[c + q] - xh * c_m2[c + q]);
+                } else {
+                    o[q] = zz[q] > 0.0f ? dd[q] : al * dd[q];
+                }
+                o[q] = maybe_round(o[q], round_out);
+            }
+            *reinterpret_cast<float4*>(dz + row * dz_ld + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < rows * n; i += blockDim.x) {
         const int r = i / n, c = i - r * n;
         const int64_t row = (int64_t)seg * R + r0 + r;
@@ -439,6 +504,12 @@ int launch_bn_finalize(const double* sums, int R, int S, int n, float eps, float
 int launch_bn_apply(const float* z, int64_t ld, int R, int S, int n, const float* mean, const float* invstd, const float* gamma,
                     const float* beta, const float* alpha, int round_out, float* a, int64_t a_ld, cudaStream_t s) {
     const int64_t total = (int64_t)S * R * n;
+    if ((n & 3) == 0 && (ld & 3) == 0 && (a_ld & 3) == 0 && ((uintptr_t)z & 15) == 0 && ((uintptr_t)a & 15) == 0) {
+        const int64_t threads = (((int64_t)S * R + kApplyVecRows - 1) / kApplyVecRows) * (n >> 2);
+        bn_apply_vec_kernel<<<blocks_for(threads, 256), 256, 0, s>>>(z, ld, R, n, mean, invstd, gamma, beta, alpha, round_out, a, a_ld, S);
+        EMPOSE_CUDA_TRY(cudaGetLastError());
+        return EMPOSE_OK;
+    }
     bn_apply_kernel<<<blocks_for(total, 256), 256, 0, s>>>(z, ld, R, n, mean, invstd, gamma, beta, alpha, round_out, a, a_ld, total);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_set_optio
                     'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read', 'empose_ief_profile_read_main',
                     'empose_gemm_selftest', 'empose_gemm_bench', 'empose_smpl_create', 'empose_smpl_destroy',
                     'empose_smpl_forward', 'empose_train_layout', 'empose_train_sizes', 'empose_train_create',
-                    'empose_train_destroy', 'empose_train_forward', 'empose_train_backward',
+                    'empose_train_destroy', 'empose_train_forward', 'empose_train_backward', 'empose_train_loss_values',
                     'empose_train_last_launch_count', 'empose_rnn_create', 'empose_rnn_destroy', 'empose_rnn_forward',
                     'empose_rnn_last_launch_count', 'empose_sensors_create', 'empose_metrics_compute', 'empose_metrics_joints')
 
@@ -122,7 +122,9 @@ def load():
     lib.empose_train_forward.restype = ctypes.c_int
     lib.empose_train_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, ctypes.POINTER(History), vp]
     lib.empose_train_backward.restype = ctypes.c_int
-    lib.empose_train_backward.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LossWeights), ctypes.POINTER(ctypes.c_float), vp]
+    lib.empose_train_backward.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LossWeights), ctypes.POINTER(ctypes.c_float), vp, vp]
+    lib.empose_train_loss_values.restype = ctypes.c_int
+    lib.empose_train_loss_values.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.empose_train_last_launch_count.restype = ctypes.c_int64
     lib.empose_train_last_launch_count.argtypes = [vp]
     lib.empose_sensors_create.restype = ctypes.c_int
@@ -417,9 +419,20 @@ class TrainContext(object):
         self._shape = (b, f)
         return {'pose': pose, 'shape': shape, 'joints': joints, 'history': hist}
 
-    def backward(self, poses_gt, shapes_gt, joints_gt, pose_weight, shape_weight, reprojection_weight, fk_weight):
+    _LOSS_KEYS = ('pose', 'shape', 'reconstruction', 'fk', 'total_loss')
+
+    def loss_values(self):
+        """The five loss values of the last ``backward(..., defer=True)`` (``empose_train_loss_values``).  Synchronises."""
+        vals = (ctypes.c_float * 5)()
+        _check(load().empose_train_loss_values(self._handle, vals))
+        return dict(zip(self._LOSS_KEYS, [float(v) for v in vals]))
+
+    def backward(self, poses_gt, shapes_gt, joints_gt, pose_weight, shape_weight, reprojection_weight, fk_weight,
+                 defer=False, dense_ready_event=None):
         """Adds the step's gradients to the flat ``grads`` vector; returns the five loss values of
-        ``models.py:676-680`` as a dict.  Synchronises."""
+        ``models.py:676-680`` as a dict and synchronises -- unless ``defer``: then the pass is only enqueued (read the values
+        with ``loss_values()``), and ``dense_ready_event`` (a ``torch.cuda.Event`` that has been recorded once, so that its
+        handle exists) is recorded on the current stream when every gradient except the LSTM's is final."""
         import torch
         b, f = self._shape
         f32 = lambda t: None if t is None else t.to(dtype=torch.float32).contiguous()
@@ -427,10 +440,11 @@ class TrainContext(object):
         shapes_gt = f32(shapes_gt).reshape(b, 10)
         joints_gt = None if joints_gt is None else f32(joints_gt).reshape(b, f, 66)
         w = LossWeights(float(pose_weight), float(shape_weight), float(reprojection_weight), float(fk_weight))
-        vals = (ctypes.c_float * 5)()
+        vals = None if defer else (ctypes.c_float * 5)()
+        event = ctypes.c_void_p(int(dense_ready_event.cuda_event)) if dense_ready_event is not None else None
         _check(load().empose_train_backward(self._handle, _ptr(poses_gt), _ptr(shapes_gt), _ptr(joints_gt), ctypes.byref(w),
-                                            vals, _stream()))
-        return dict(zip(('pose', 'shape', 'reconstruction', 'fk', 'total_loss'), [float(v) for v in vals]))
+                                            vals, event, _stream()))
+        return None if defer else dict(zip(self._LOSS_KEYS, [float(v) for v in vals]))
 
 
 class SensorContext(object):

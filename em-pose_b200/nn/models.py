@@ -292,13 +292,40 @@ class IterativeErrorFeedback(nn.Module):
         return None if self._flat is None else self._flat['params']
 
     def allreduce_gradients(self, average=True):
-        """Data-parallel training: ONE all-reduce over the flat gradient vector."""
+        """Data-parallel training: ONE all-reduce over the flat gradient vector.  A no-op when
+        ``overlap_gradient_allreduce`` already reduced this step's gradients inside ``backward``."""
         import torch.distributed as dist
         from empose_b200 import sharding
+        if self._grads_reduced:
+            self._grads_reduced = False
+            return
         if average:
             sharding.allreduce_mean_(self._flat['grads'], dist)
         else:
             dist.all_reduce(self._flat['grads'], op=dist.ReduceOp.SUM)
+
+    _grads_reduced = False
+    _overlap = None
+
+    def overlap_gradient_allreduce(self, enable=True, average=True, group=None):
+        """
+        Reduce the gradients INSIDE ``backward`` in two buckets: the iter-MLPs and heads (everything but the
+        LSTM) as soon as they are final -- the native pass records an event before the LSTM's backward-through-time sweep
+        -- on a side stream, so that the NCCL transfer runs under the sweep; the LSTM bucket when the sweep has finished.
+        ``allreduce_gradients`` then becomes a no-op for that step.  Needs an initialised ``torch.distributed``.
+        """
+        self._overlap = dict(average=average, group=group, stream=None, event=None) if enable else None
+
+    def lstm_bucket_end(self):
+        """Number of floats at the start of the flat vectors that belong to the LSTM (``empose_train_layout`` puts the
+        ``rnn.lstm.*`` tensors first); 0 for models without the RNN initialisation."""
+        end = 0
+        for name, kind, off, numel in self._flat['entries']:
+            if kind == 0 and name.startswith('rnn.lstm.'):
+                end = max(end, off + numel)
+        for name, kind, off, numel in self._flat['entries']:
+            assert kind != 0 or name.startswith('rnn.lstm.') or off >= end, 'the LSTM must be the first bucket of the flat vector'
+        return end
 
     def _attach_gradients(self):
         """``optimizer.zero_grad()`` sets ``.grad`` to None by default: re-attach (zeroed) views of the flat vector."""
@@ -344,8 +371,29 @@ class IterativeErrorFeedback(nn.Module):
     def _backward_train(self, batch, writer, global_step):
         pose_gt = torch.cat([batch.poses_root, batch.poses_body], dim=-1)
         joints_gt = batch.joints_gt if self.do_fk else None
-        vals = self._trainer.backward(pose_gt, batch.shapes, joints_gt, self.pose_weight, self.shape_weight, self.r_weight,
-                                      self.fk_loss_weight if self.do_fk else 0.0)
+        fk_w = self.fk_loss_weight if self.do_fk else 0.0
+        if self._overlap is None:
+            vals = self._trainer.backward(pose_gt, batch.shapes, joints_gt, self.pose_weight, self.shape_weight, self.r_weight, fk_w)
+        else:
+            import torch.distributed as dist
+            ov = self._overlap
+            main = torch.cuda.current_stream(pose_gt.device)
+            if ov['stream'] is None:
+                ov['stream'] = torch.cuda.Stream(device=pose_gt.device)
+                ov['event'] = torch.cuda.Event()
+                ov['event'].record(main)                       # creates the handle the native pass re-records
+            self._trainer.backward(pose_gt, batch.shapes, joints_gt, self.pose_weight, self.shape_weight, self.r_weight, fk_w,
+                                   defer=True, dense_ready_event=ov['event'])
+            grads, cut = self._flat['grads'], self.lstm_bucket_end()
+            op = dist.ReduceOp.AVG if ov['average'] else dist.ReduceOp.SUM
+            ov['stream'].wait_event(ov['event'])
+            with torch.cuda.stream(ov['stream']):              # dense bucket: under the LSTM sweep still running on `main`
+                dist.all_reduce(grads[cut:], op=op, group=ov['group'])
+            if cut > 0:
+                dist.all_reduce(grads[:cut], op=op, group=ov['group'])
+            main.wait_stream(ov['stream'])
+            self._grads_reduced = True
+            vals = self._trainer.loss_values()
         if writer is not None:
             for k in vals:
                 writer.add_scalar('{}/{}'.format(k, 'train'), vals[k], global_step)

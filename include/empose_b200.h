@@ -241,9 +241,15 @@ int empose_train_forward(empose_train* ctx, const float* marker_pos, const float
  * joints_gt [B][F][66] or NULL (required when fk_weight > 0).  ADDS to `grads` what the reference leaves in .grad
  * after forward + backward: d(total_loss) plus, when use_gradient is set, the N reconstruction-energy gradients of
  * the forward pass (models.py:576).  loss_vals: HOST float[5] = pose, shape, reconstruction, fk, total_loss
- * (models.py:676-680).  Synchronises the stream (the reference does, too). */
+ * (models.py:676-680); filling it synchronises the stream (the reference does, too: five .cpu().item() calls).
+ * Data-parallel training overlaps the gradient all-reduce with the tail of this pass: with loss_vals = NULL the call only
+ * ENQUEUES work, and `dense_ready_event` (a cudaEvent_t, may be NULL) is recorded on `stream` as soon as every gradient
+ * except the LSTM's is final -- before the LSTM's backward-through-time runs -- so the caller can reduce that bucket
+ * (empose_train_layout: the LSTM tensors come first in the flat vector) on another stream meanwhile ("issued
+ * per bucket ... LSTM last").  empose_train_loss_values then synchronises and returns the five numbers. */
 int empose_train_backward(empose_train* ctx, const float* poses_gt, const float* shapes_gt, const float* joints_gt,
-                          const empose_loss_weights* weights, float* loss_vals, void* stream);
+                          const empose_loss_weights* weights, float* loss_vals, void* dense_ready_event, void* stream);
+int empose_train_loss_values(empose_train* ctx, float* loss_vals);
 int64_t empose_train_last_launch_count(const empose_train* ctx);
 
 /* ---- (Bi)RNN baseline (BASELINE config 4) ------------------------------------------------------- */
