@@ -31,14 +31,26 @@ namespace empose {
 
 namespace {
 
-constexpr int kStages = 4;                   // ring slots of A [128 x 128 B] + W [256 x 128 B] (48 KB)
-constexpr int kStagesPair = 6;               // CTA-pair mode: a slot holds half of W (32 KB), so the same memory is a deeper ring
+#ifndef EMPOSE_EPI_WARPS
+#define EMPOSE_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = EMPOSE_EPI_WARPS;  // 8 or 12: kEpiParts warps per TMEM lane quadrant share the columns of an accumulator.
+                                             // Measured (profiles/r02/README.md): twelve warps with 32-column chunks (56 / 152
+                                             // registers, a 5-slot ring) run the MLP chain no faster than eight warps with
+                                             // 64-column chunks (810 vs 806 us) and the LSTM wavefront slower (1.33 vs 1.19 ms): the
+                                             // chain is not bound by epilogue parallelism.  Eight is the default.
+constexpr int kEpiParts = kEpiWarps / 4;
+static_assert(kEpiWarps == 8 || kEpiWarps == 12, "two or three epilogue warps per TMEM lane quadrant");
 constexpr int kDefaultClusterMode = 2;      // EMPOSE_TC_CLUSTER when the variable is not set: CTA pairs (cta_group::2)
 constexpr int kABytes = kTileM * kChunkK * 4;        // 16 KB
 constexpr int kWBytes = kMaxTileN * kChunkK * 4;     // 32 KB
 constexpr int kStageBytes = kABytes + kWBytes;
+// operand ring: 192 KB with 8 epilogue warps, 160 KB with 12 (their staging tiles need the difference)
+constexpr int kStages = kEpiWarps == 8 ? 4 : 3;      // ring slots of A [128 x 128 B] + W [256 x 128 B] (48 KB)
+constexpr int kStagesPair = kEpiWarps == 8 ? 6 : 5;  // CTA-pair mode: a slot holds half of W (32 KB), so the same memory is a deeper ring
+constexpr int kOperandBytes = kStagesPair * (kABytes + kWBytes / 2);
+static_assert(kStages * kStageBytes <= kOperandBytes, "both ring layouts share the operand region");
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each taking half of the columns
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kEpiThreads = kEpiWarps * 32;
 
@@ -56,7 +68,7 @@ constexpr int kControlBytes = 256;
 constexpr int kJobWords = (int)(sizeof(GemmJob) / 4);              // the epilogue keeps the current and the next job in shared memory
 static_assert(sizeof(GemmJob) % 8 == 0 && kJobWords <= kEpiThreads, "one word of a job per epilogue thread");
 static_assert(sizeof(Control) <= kControlBytes, "Control grew");
-constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*alignment slack*/ + kControlBytes;      // dynamic
+constexpr int kSmemBytes = kOperandBytes + kEpiStageBytes + 1024 /*alignment slack*/ + kControlBytes;      // dynamic
 static_assert(kSmemBytes + 2 * (int)sizeof(GemmJob) <= 227 * 1024, "shared memory budget (dynamic + the static job copies)");
 
 // What the single-thread roles need of a job.  They fetch the fields of the NEXT job while working on the current one:
@@ -315,9 +327,10 @@ __device__ __forceinline__ void tmem_load_64cols(uint32_t taddr, float (&v)[64])
 }
 
 // Register budgets of the warp roles (setmaxnreg): the four single-thread / idle warps hand registers to the eight epilogue
-// warps, whose 64-column chunks keep the accumulator read, the bias and two packed halves live.  168 * 384 = 40 * 128 + 232 * 256.
-constexpr int kRegsControl = 72;
-constexpr int kRegsEpilogue = 216;
+// warps, whose 64-column chunks keep the accumulator read, the bias and two packed halves live.  168 * 384 = 72 * 128 + 216 * 256; 128 * 512 = 56 * 128 + 152 * 384.
+constexpr int kRegsControl = kEpiWarps == 8 ? 72 : 56;
+constexpr int kRegsEpilogue = kEpiWarps == 8 ? 216 : 152;
+constexpr bool kWideChunks = kEpiWarps == 8;       // the 64-column fp16 linear path needs ~190 registers
 
 template <class View>
 __device__ __forceinline__ int job_chunk_k(const View& j) { return j.in_half ? kChunkKHalf : kChunkK; }
@@ -345,8 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                                               uint32_t epoch) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* epi_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes);
-    Control* ctl = reinterpret_cast<Control*>(smem + kStages * kStageBytes + kEpiStageBytes);
+    float* epi_stage = reinterpret_cast<float*>(smem + kOperandBytes);
+    Control* ctl = reinterpret_cast<Control*>(smem + kOperandBytes + kEpiStageBytes);
     __shared__ GemmJob job_s[2];        // static: the compiler then knows the address space (LDS, not generic loads)
 
     const int warp = threadIdx.x >> 5;
@@ -362,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     constexpr bool kPair = kMode == 3;
     constexpr int kRing = kPair ? kStagesPair : kStages;                                    // slots in the operand ring ...
     constexpr int kSlotBytes = kPair ? kABytes + kWBytes / 2 : kStageBytes;                 // ... of this many bytes
-    static_assert(kRing * kSlotBytes <= kStages * kStageBytes, "the ring must fit the operand region");
+    static_assert(kRing * kSlotBytes <= kOperandBytes, "the ring must fit the operand region");
     const uint32_t ring = (kPair && (debug_mode & 256)) ? (uint32_t)kStages : (uint32_t)kRing;     // bit 256: experiment, shallow ring
     const int n_items = items ? n_items_table : (kCluster == 2 ? (m_tiles + 1) / 2 : m_tiles) * groups;
     const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;
@@ -546,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         // ================= epilogue =================
         const int ew = warp - 4;
         const int quad = ew & 3;                  // TMEM lanes 32*quad .. 32*quad+31 (a warp may only touch its own quadrant)
-        const int half = ew >> 2;                 // columns [half*128, half*128 + 128) of the accumulator
+        const int part = ew >> 2;                 // which share of the accumulator's columns (kEpiParts warps per quadrant)
         uint32_t seq = 0;
         // The epilogue reads job fields all the time (per 32-column chunk): it works on a shared-memory copy.  Thread e
         // of the 256 epilogue threads carries word e of the NEXT job through the current one and drops it into the other
@@ -572,8 +585,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 // layer and overwritten by the next tile before they would be written back to HBM
                 const int row0 = (job.out_scratch ? (int)blockIdx.x * kTileM : m0) + quad * 32;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kMaxTileN;
-                const int c_begin = half * (kMaxTileN / 2);
-                const int c_end = min(job.n_count, (half + 1) * (kMaxTileN / 2));
+                // column shares in units of 32-column chunks -- of chunk PAIRS for fp16 LSTM jobs, whose cell-state blocks span 64
+                int c_begin, c_end;
+                {
+                    const int unit = lstm_half_paired(job) ? 64 : 32;
+                    const int units = (job.n_count + unit - 1) / unit;
+                    c_begin = (part * units / kEpiParts) * unit;
+                    c_end = min(job.n_count, ((part + 1) * units / kEpiParts) * unit);
+                }
                 // fp16 LSTM jobs: the cell state of the first chunk pair is fetched while the MMAs are still running
                 const bool lstm_pre = lstm_half_paired(job) && !(debug_mode & 128);
                 // Wavefront jobs: the recurrent state this epilogue reads (cell state, carried hidden state) is written by
@@ -595,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 //  issued before the current chunk is staged.  With the read's registers live across the loop ptxas feeds the
                 //  eight bias loads one by one into the additions: 11 % slower on a [131072 x 512] . [512 x 512] layer.)
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                    if (c0 + 64 <= lv.fast_cols && c0 + 64 <= c_end && !(debug_mode & 1024)) {
+                    if (kWideChunks && c0 + 64 <= lv.fast_cols && c0 + 64 <= c_end && !(debug_mode & 1024)) {
                         // fp16 linear jobs, 64 columns at a time: ONE accumulator read (one wait) per 64 columns, the bias
                         // loads of both halves in flight meanwhile, two independent pack / stage / store sequences
                         float v2[64], b0[32], b1[32];
