@@ -113,13 +113,16 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+MESH = {'kind': None}          # --mesh: None = the regular lat-long mesh, 'mild' / 'wild' = sensor vertices of valence 5..7 / 4..11
+
+
 def build_b200_model(device, precision='fp16'):
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from empose_b200 import lib, synthetic
     from empose_b200.bodymodels.smpl import SMPLLayer
     from empose_b200.helpers.configuration import lgd_config
     from empose_b200.nn.models import IterativeErrorFeedback
-    npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0)
+    npz = synthetic.write_synthetic_smplh(asset_dir(), seed=0, irregular=MESH['kind'])
     cfg = lgd_config(n_markers=12, num_iterations=4, rnn_init=True, hidden_size=512, window_size=FRAMES)
     prec = {'fp16': lib.PRECISION_FP16, 'tf32': lib.PRECISION_TF32, 'fp32': lib.PRECISION_FP32}[precision]
     net = IterativeErrorFeedback(cfg, SMPLLayer(npz).to(dtype=torch.float32), precision=prec)
@@ -485,6 +488,7 @@ def run_b200(args, rank, local_rank, world):
             'data': 'synthetic',
             'config': {'workload': 'LGD-RNN (2x512 LSTM init), 12 sensors, N=4, ws=32, %d windows per GPU (BASELINE config 3)' % b,
                        'windows_per_gpu': b, 'frames_per_window': FRAMES, 'parallelism': 'windows sharded, no collective',
+                       'mesh': args.mesh + ' (synthetic; sensor sub-mesh in fan form)',
                        'l2': 'per-step working set (~3 GB of activations and features) exceeds the 126 MB L2; no flush needed',
                        'arithmetic': {'fp16': 'learned layers: fp16 operands on tcgen05 (kind::f16), fp32 accumulate in TMEM; blend GEMMs as a '
                                               '3-term fp16 split (22 mantissa bits); per-frame SMPL math, LSTM cell state and all outputs fp32',
@@ -880,12 +884,15 @@ def main():
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'tf32', 'fp32'], help='inference arithmetic of the learned layers')
     ap.add_argument('--windows', type=int, default=None, help='windows per GPU (inference: 4096 = BASELINE config 3; training: 512)')
     ap.add_argument('--ref-windows', type=int, default=16, help='windows per step of the CPU reference arm / baseline')
+    ap.add_argument('--mesh', default='regular', choices=['regular', 'mild', 'wild'],
+                    help='synthetic SMPL-H mesh of the inference workload: regular valence 6, or irregular sensor valences 5..7 / 4..11')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-companions', action='store_true', help='skip the tf32 and training sub-records (quick A/B runs)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    MESH['kind'] = None if args.mesh == 'regular' else args.mesh
     if args.windows is None:
         args.windows = 512 if args.workload == 'train' else 4096
     if args.impl == 'reference':

@@ -220,6 +220,9 @@ int launch_main_fan(const MainParams& p, cudaStream_t s) {
             case 1: return launch_variant<8, 6, 16, 2>(p, s);
             case 2: return launch_variant<8, 6, 8, 3>(p, s);
             case 3: return launch_variant<8, 6, 5, 6>(p, s);
+            case 4: return launch_variant<8, 6, 7, 5>(p, s);
+            case 5: return launch_variant<8, 6, 10, 3>(p, s);
+            case 6: return launch_variant<8, 6, 5, 5>(p, s);
             default: return launch_variant<8, 6, 8, 4>(p, s);
         }
     }

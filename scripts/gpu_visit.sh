@@ -7,6 +7,7 @@
 #   tests[:<pytest -k expr>]   python -m pytest tests -m gpu
 #   smoke                      __graft_entry__.smoke()
 #   bench[:ENV=V,ENV=V]        python bench.py --steps 10 --warmup 3 --no-cpu-baseline with the environment given (A/B switches)
+#   benchargs:--a,v,--b,w      the same with extra bench.py arguments (commas for spaces), e.g. benchargs:--mesh,wild
 #   fullbench                  the default bench line incl. the CPU baseline leg, and the reference arm
 #   train | synth | metrics | birnn   the other bench workloads
 #   launches[:workload]        ncu launch list (gpu__time_duration) of two bench steps -> <tag>_launches[_workload].csv
@@ -31,6 +32,10 @@ for step in "$@"; do
       suffix=$(echo "$arg" | tr -c 'A-Za-z0-9=\n' '_'); log=gpurun_out/${tag}_bench_${suffix}.log
       env $(echo "$arg" | tr ',' ' ') timeout -s KILL 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-companions > $log 2>&1; echo "rc=$?" >> $log
       echo "bench [$arg]"; tail -n 2 $log | cut -c1-700 ;;
+    benchargs)
+      suffix=$(echo "$arg" | tr -c 'A-Za-z0-9=\n' '_'); log=gpurun_out/${tag}_bench_${suffix}.log
+      timeout -s KILL 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-companions $(echo "$arg" | tr ',' ' ') > $log 2>&1; echo "rc=$?" >> $log
+      echo "bench args [$arg]"; tail -n 2 $log | cut -c1-400 ;;
     fullbench)
       timeout -s KILL 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.log 2>&1
       timeout -s KILL 900 python bench.py --steps 20 --warmup 3 > $log 2>&1; echo "rc=$?" >> $log; tail -n 2 $log | cut -c1-1500 ;;
