@@ -906,9 +906,18 @@ int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const floa
     EMPOSE_CUDA_TRY(cudaEventRecord(ev_start, s));
     EMPOSE_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_in, ev_start, 0));
     EMPOSE_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ev_start, 0));
+    // Sub-batch sizes: the MLP chain works in waves of (CTA pairs) x 256 rows, so an even split of 4096 windows x 32 frames
+    // (6.92 waves) into 2 x 3.46 costs a whole extra wave; cut at a multiple of one wave of windows instead (4 + 2.92).
+    static const bool even_split = getenv("EMPOSE_HOST_EVEN") != nullptr;
+    const int wave = std::max(1, (ctx->num_sms / 2) * 2 * kTileM / F);
     int b0 = 0;
     for (int c = 0; c < n_chunks; ++c) {
-        const int bc = B / n_chunks + (c < B % n_chunks ? 1 : 0);
+        int bc = B / n_chunks + (c < B % n_chunks ? 1 : 0);
+        if (!even_split && wave < B / n_chunks) {
+            if (c + 1 < n_chunks) bc = std::max(wave, (int)std::lround((double)(B / n_chunks) / wave) * wave);
+            if (c + 1 == n_chunks || b0 + bc >= B) bc = B - b0;
+        }
+        if (bc <= 0) break;
         Plan* plp;
         EMPOSE_TRY(build_plan(ctx, bc, F, &plp, c + 1));        // one workspace per in-flight sub-batch
         EMPOSE_TRY(forward_host_chunk(ctx, *plp, B, b0, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks,
