@@ -63,7 +63,8 @@ struct __align__(8) Control {
     volatile uint32_t epi_done;
 };
 
-constexpr int kEpiStageBytes = kEpiWarps * kStageFloats * 4;     // one [32][33] fp32 transpose tile per epilogue warp
+constexpr int kEpiStageBytes = kEpiWarps * kStageFloats * 4;     // one 4 KB staging tile per epilogue warp (1024-byte aligned: TMA swizzle)
+static_assert(kOperandBytes % 1024 == 0 && (kStageFloats * 4) % 1024 == 0, "staging tiles must keep the 1024-byte alignment of the swizzle pattern");
 constexpr int kControlBytes = 256;
 constexpr int kJobWords = (int)(sizeof(GemmJob) / 4);              // the epilogue keeps the current and the next job in shared memory
 static_assert(sizeof(GemmJob) % 8 == 0 && kJobWords <= kEpiThreads, "one word of a job per epilogue thread");
@@ -215,6 +216,17 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+
+// ---- TMA stores (epilogue): a staged [32 rows x 128 B] block in the 128-byte swizzle -> global memory, rows beyond the tensor clipped ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int crd0, int crd1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(crd0), "r"(crd1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }     // sources may be overwritten
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }           // the writes are complete
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -561,6 +573,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         const int quad = ew & 3;                  // TMEM lanes 32*quad .. 32*quad+31 (a warp may only touch its own quadrant)
         const int part = ew >> 2;                 // which share of the accumulator's columns (kEpiParts warps per quadrant)
         uint32_t seq = 0;
+        bool generic_stores = false;              // this thread has stored from registers since its last proxy fence
+        bool tma_pending = false;                 // (warp-uniform) a TMA store of this warp may still be reading its staging tile
+        auto release_tile = [&]() {               // before the staging tile is written by any other path
+            if (tma_pending) {
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+                tma_pending = false;
+            }
+        };
         // The epilogue reads job fields all the time (per 32-column chunk): it works on a shared-memory copy.  Thread e
         // of the 256 epilogue threads carries word e of the NEXT job through the current one and drops it into the other
         // slot before the barrier that ends the job.
@@ -615,8 +636,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 //  eight bias loads one by one into the additions: 11 % slower on a [131072 x 512] . [512 x 512] layer.)
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     if (kWideChunks && c0 + 64 <= lv.fast_cols && c0 + 64 <= c_end && !(debug_mode & 1024)) {
-                        // fp16 linear jobs, 64 columns at a time: ONE accumulator read (one wait) per 64 columns, the bias
-                        // loads of both halves in flight meanwhile, two independent pack / stage / store sequences
+                        // fp16 linear jobs, 64 columns at a time: ONE accumulator read (one wait) per 64 columns with the bias loads in
+                        // flight meanwhile, packed fp32 arithmetic, and the [32 rows x 128 B] block leaves through ONE TMA store
+                        // from the warp's staging tile (no shared-memory read-back, no per-lane global stores).
+                        if (lv.out_map >= 0 && !(debug_mode & 2048)) {
+                            float v2[64], bb[64];
+                            linear_half_load_bias(lv, c0, *reinterpret_cast<float(*)[32]>(&bb[0]));
+                            linear_half_load_bias(lv, c0 + 32, *reinterpret_cast<float(*)[32]>(&bb[32]));
+                            tmem_load_64cols(taddr + (uint32_t)c0, v2);
+                            if (!(debug_mode & 4)) {
+                                uint32_t pk[32];
+                                linear_half_pack64(lv, v2, bb, pk);
+                                const uint32_t tile = smem_addr_of(my_stage);
+                                if (lane == 0) bulk_wait_read0();          // the previous block of this warp has left the tile
+                                __syncwarp();
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    sts128(tile + lane * 128 + ((q ^ (lane & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                                fence_async_shared();
+                                __syncwarp();
+                                if (lane == 0 && !(debug_mode & 16)) {
+                                    tma_store_2d(&maps[lv.out_map], tile, lv.out_col + c0, row0);
+                                    bulk_commit();
+                                }
+                                tma_pending = true;
+                            }
+                            c0 += 32;
+                            continue;
+                        }
+                        release_tile();
                         float v2[64], b0[32], b1[32];
                         linear_half_load_bias(lv, c0, b0);
                         linear_half_load_bias(lv, c0 + 32, b1);
@@ -628,15 +676,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                             linear_half_pack(lv, *reinterpret_cast<const float(*)[32]>(&v2[32]), b1, pk);
                             linear_half_store(lv, row0, lane, c0 + 32, pk, my_stage, (debug_mode & 16) != 0);
                         }
+                        generic_stores = true;
                         c0 += 32;
                         continue;
                     }
+                    release_tile();
                     float v[32];
                     if (c0 + 32 <= lv.fast_cols) {
                         float bias[32];
                         linear_half_load_bias(lv, c0, bias);              // in flight while the accumulator is read
                         tmem_load_32cols(taddr + (uint32_t)c0, v);
                         if (!(debug_mode & 4)) linear_half_chunk(lv, row0, lane, c0, v, bias, my_stage, (debug_mode & 16) != 0);
+                        generic_stores = true;
                         continue;
                     }
                     if (debug_mode & 32) {                 // measurement only: no TMEM read
@@ -647,6 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     }
                     if (!(debug_mode & 4))
                         epilogue_chunk(job, row0, lane, c0, v, my_stage, (debug_mode & 16) != 0, lstm_pre ? cpre : nullptr);
+                    generic_stores = true;
                     // ... and the next pair's while this pair is being computed
                     if (lstm_pre && !(c0 & 32) && c0 + 64 < c_end) lstm_half_load_c(job, row0, lane, c0 + 64, cpre);
                 }
@@ -659,9 +711,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     // layer): order them before the barrier at CTA scope and hand them to the async proxy.  A device-scope
                     // fence here also invalidates L1 on every job, which turned every bias / sequence-length / job-field
                     // read of the next job into an L2 round trip (bit 64 brings it back for comparison).
-                    if (debug_mode & 64) __threadfence();
-                    else __threadfence_block();
-                    asm volatile("fence.proxy.async;" ::: "memory");
+                    // Blocks that left through TMA stores are already in the async proxy: their issuing lane waits for the writes
+                    // to complete.  Stores from registers (any other path, this job or an earlier one of the item) need the fence.
+                    if (lane == 0) bulk_wait_all0();
+                    if (generic_stores) {
+                        if (debug_mode & 64) __threadfence();
+                        else __threadfence_block();
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        generic_stores = false;
+                    }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 if (threadIdx.x == 4 * 32) {
@@ -674,6 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 }
             }
         }
+        if (lane == 0) bulk_wait_all0();          // no TMA store may still read this CTA's shared memory when it exits
     }
 
     tcgen05_fence_before();

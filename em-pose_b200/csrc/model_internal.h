@@ -259,6 +259,18 @@ struct JobBook {        // jobs + tensor maps of one plan
         return EMPOSE_OK;
     }
 
+    // fp16 linear outputs the tcgen05 executor may write with TMA stores ([32 rows x 64 columns] boxes, gemm_tc.cu): needs
+    // 16-byte aligned rows and column origin; rows >= m_rows are clipped by the map
+    int attach_out_map(GemmJob& j) {
+        j.out_map1 = 0;
+        if (!use_tc || j.epi != EPI_LINEAR || !j.out_half || j.res || !j.out) return EMPOSE_OK;
+        if ((reinterpret_cast<uintptr_t>(j.out) & 15) || ((j.out_stride * 2) & 15) || (j.out_col0 & 7) || (j.n_begin & 7)) return EMPOSE_OK;
+        int idx = -1;
+        EMPOSE_TRY(get_map(j.out, j.out_stride, (int)j.out_stride, j.m_rows, 32, 1, &idx));
+        j.out_map1 = idx + 1;
+        return EMPOSE_OK;
+    }
+
     // appends one job per N tile of `W`; `proto` carries the epilogue fields (n_begin/n_count/maps are filled here)
     int add(const PackedMatrix& W, const ASrc& a0, const ASrc& a1, GemmJob proto, int m_rows, int dep, JobRange* range) {
         if (range->count == 0) range->begin = (int)jobs.size();
@@ -290,6 +302,7 @@ struct JobBook {        // jobs + tensor maps of one plan
             j.dep = dep;
             j.is_dep = 0;
             j.bias = W.bias;
+            EMPOSE_TRY(attach_out_map(j));
             jobs.push_back(j);
             ++range->count;
         }
