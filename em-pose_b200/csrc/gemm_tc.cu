@@ -21,7 +21,10 @@
 // between (the pose and shape MLPs are interleaved layer by layer) keep the tensor pipe busy meanwhile.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "../../include/empose_b200.h"
 #include "gemm_jobs.h"
@@ -98,6 +101,14 @@ __device__ __forceinline__ IssuerView issuer_view(const GemmJob& j) {
     return v;
 }
 
+// ---- timeline trace (EMPOSE_TC_TRACE=<file>): clock64 stamps of the three roles per job, first CTAs / jobs of a launch ----
+constexpr int kTraceCtas = 4, kTraceJobs = 96, kTraceStamps = 4;
+__device__ unsigned long long* g_trace_buf = nullptr;       // [cta][role 0 producer, 1 issuer, 2 epilogue warp 4][job][stamp]
+// `t` = g_trace_buf read ONCE per role (a stamp must not wait for a load: after a fence that is an L2 round trip)
+__device__ __forceinline__ void trace_stamp(unsigned long long* t, int role, uint32_t seq, int k) {
+    if (t && seq < kTraceJobs) t[((blockIdx.x * 3 + role) * kTraceJobs + seq) * kTraceStamps + k] = clock64();
+}
+
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -165,8 +176,13 @@ __device__ __forceinline__ uint32_t mapa_rank0(const void* p) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
     return r;
 }
+// Arrival on a barrier that may live in the peer CTA.  Default semantics (release at CTA scope) on purpose: with
+// .release.cluster ptxas emits MEMBAR.ALL.GPU + ERRBAR in front of the arrive, which stalled the arriving thread -- and with it
+// the whole epilogue, which meets at a barrier every job -- for ~3500-5400 cycles per job (timeline trace, profiles/r02): the
+// thread had to wait for its outstanding global / TMA stores.  What the arrival orders here are tensor-memory reads, which
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync have already completed.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -425,12 +441,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
     if (kCluster == 2) cluster_sync_all();        // the peer's barriers must be initialised before anything is multicast to it
     tcgen05_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
+    unsigned long long* const trace = blockIdx.x < kTraceCtas ? g_trace_buf : nullptr;
 
     if (warp == 0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
         // ================= TMA producer (whole warp, one elected lane issues) =================
         {
-            uint32_t stage = 0, phase = 0, items_done = 0;
+            uint32_t stage = 0, phase = 0, items_done = 0, pseq = 0;
             ProducerView nxt;
             if (item0 < n_items) nxt = producer_view(jobs[job_index(item0, 0)]);
             for (int item = item0; item < n_items; item += item_step, ++items_done) {
@@ -442,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         const int ni = nj ? item : item + item_step;
                         if (ni < n_items) nxt = producer_view(jobs[job_index(ni, nj)]);
                     }
+                    if (lane == 0) trace_stamp(trace, 0, pseq, 0);
                     if (job.dep >= 0) {
                         const uint32_t need = items_done * (uint32_t)jobs_per_item + (uint32_t)job.dep + 1u;
                         while (ctl->epi_done < need) {
@@ -460,6 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         asm volatile("fence.proxy.async;" ::: "memory");
                         __syncwarp();
                     }
+                    if (lane == 0) trace_stamp(trace, 0, pseq, 1);
                     const uint32_t w_bytes = (uint32_t)job.n_count * kChunkK * 4u;        // 128 bytes per row in either type
                     const int ck = job_chunk_k(job);
                     const int half_rows = job.n_count >> 1;
@@ -497,6 +516,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                             if (++stage == ring) { stage = 0; phase ^= 1u; }
                         }
                     }
+                    if (lane == 0) trace_stamp(trace, 0, pseq, 2);
+                    ++pseq;
                 }
             }
         }
@@ -517,9 +538,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         if (ni < n_items) nxt = issuer_view(jobs[job_index(ni, nj)]);
                     }
                     const uint32_t buf = seq & 1u;
+                    if (lane == 0) trace_stamp(trace, 1, seq, 0);
                     if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_empty[buf], ((seq >> 1) & 1u) ^ 1u);
                     else mbar_wait(&ctl->tmem_empty[buf], ((seq >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
+                    if (lane == 0) trace_stamp(trace, 1, seq, 1);
                     const uint32_t d_tmem = tmem_base + buf * kMaxTileN;
                     const bool half = job.in_half != 0;
                     const uint32_t idesc = make_idesc(job.n_count, half, kPair ? 2 * kTileM : kTileM);
@@ -528,6 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         if (kCluster == 2) mbar_wait_guarded(&ctl->full[stage], phase);
                         else mbar_wait(&ctl->full[stage], phase);
                         tcgen05_fence_after();
+                        if (kc == 0 && lane == 0) trace_stamp(trace, 1, seq, 2);
                         const uint64_t a_desc = make_smem_desc(ring_base + stage * (uint32_t)kSlotBytes);
                         const uint64_t b_desc = a_desc + (uint64_t)(kABytes >> 4);
                         if (elect_one()) {
@@ -560,6 +584,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         if (kPair) umma_commit_pair(&ctl->tmem_full[buf], kMask);     // both CTAs' epilogues read their half of D
                         else umma_commit(&ctl->tmem_full[buf]);
                     }
+                    if (lane == 0) trace_stamp(trace, 1, seq, 3);
                     __syncwarp();
                 }
             }
@@ -628,9 +653,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 // fp16 linear jobs: all fields the chunk loop needs, once per job
                 const LinearHalfView lv = linear_half_view(job, row0, lane);
                 float* my_stage = epi_stage + ew * kStageFloats;
+                if (et == 0) trace_stamp(trace, 2, seq, 0);
                 if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 else mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 tcgen05_fence_after();
+                if (et == 0) trace_stamp(trace, 2, seq, 1);
                 // (tried and dropped: software-pipelining the accumulator reads -- 16 columns at a time, or the next chunk's read
                 //  issued before the current chunk is staged.  With the read's registers live across the loop ptxas feeds the
                 //  eight bias loads one by one into the additions: 11 % slower on a [131072 x 512] . [512 x 512] layer.)
@@ -703,6 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     if (lstm_pre && !(c0 & 32) && c0 + 64 < c_end) lstm_half_load_c(job, row0, lane, c0 + 64, cpre);
                 }
                 tcgen05_fence_before();
+                if (et == 0) trace_stamp(trace, 2, seq, 2);
                 if (has_next) reinterpret_cast<uint32_t*>(&job_s[buf ^ 1u])[et] = next_word;
                 if (!(debug_mode & 8) && (job.is_dep || job.done_ctr || (debug_mode & 512))) {
                     // Only a job that a later job of this item waits for publishes stores (its own and, by program order,
@@ -722,6 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                if (et == 0) trace_stamp(trace, 2, seq, 3);
                 if (threadIdx.x == 4 * 32) {
                     if (kPair) mbar_arrive_cluster(mapa_rank0(&ctl->tmem_empty[buf]));      // CTA 0 issues the MMAs of both
                     else mbar_arrive(&ctl->tmem_empty[buf]);
@@ -798,6 +827,30 @@ static int g_cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
 // EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
 // 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring, 512 fence after every job
 static int g_debug_mode = 0;
+static unsigned long long* g_trace_dev = nullptr;      // EMPOSE_TC_TRACE: the stamps of the LAST launch are written to that file
+static const char* g_trace_path = nullptr;
+constexpr size_t kTraceWords = (size_t)kTraceCtas * 3 * kTraceJobs * kTraceStamps;
+
+static int g_trace_kind = 0;            // EMPOSE_TC_TRACE_KIND: 0 any launch, 1 item-table launches (LSTM wavefront), 2 chained items (MLP chains)
+static bool tc_trace_wanted(int kind) { return g_trace_dev && (g_trace_kind == 0 || g_trace_kind == kind); }
+static void tc_trace_begin(cudaStream_t s, int kind) {
+    if (tc_trace_wanted(kind)) cudaMemsetAsync(g_trace_dev, 0, kTraceWords * 8, s);
+}
+static void tc_trace_end(cudaStream_t s, int kind) {
+    if (!tc_trace_wanted(kind)) return;
+    std::vector<unsigned long long> h(kTraceWords);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h.data(), g_trace_dev, kTraceWords * 8, cudaMemcpyDeviceToHost);
+    FILE* f = fopen(g_trace_path, "w");
+    if (!f) return;
+    for (int c = 0; c < kTraceCtas; ++c)
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < kTraceJobs; ++j) {
+                const unsigned long long* t = &h[(((size_t)c * 3 + r) * kTraceJobs + j) * kTraceStamps];
+                if (t[0] | t[1] | t[2] | t[3]) fprintf(f, "%d %d %d %llu %llu %llu %llu\n", c, r, j, t[0], t[1], t[2], t[3]);
+            }
+    fclose(f);
+}
 
 static int tc_configure(int num_sms) {
     static bool configured = false;
@@ -825,6 +878,13 @@ static int tc_configure(int num_sms) {
         if (q == cudaSuccess && n > 0) { g_max_clusters = n; g_cluster_mode = want + 1; }
         else cudaGetLastError();
     }
+    g_trace_path = getenv("EMPOSE_TC_TRACE");
+    if (g_trace_path && *g_trace_path) {
+        EMPOSE_CUDA_TRY(cudaMalloc(&g_trace_dev, kTraceWords * 8));
+        EMPOSE_CUDA_TRY(cudaMemcpyToSymbol(g_trace_buf, &g_trace_dev, sizeof(g_trace_dev)));
+        const char* k = getenv("EMPOSE_TC_TRACE_KIND");
+        g_trace_kind = k ? atoi(k) : 0;
+    }
     if (getenv("EMPOSE_TC_VERBOSE"))
         fprintf(stderr, "empose_b200: gemm executor: mode %d, %d co-resident 2-CTA clusters on %d SMs\n", g_cluster_mode, g_max_clusters, num_sms);
     configured = true;
@@ -836,9 +896,8 @@ static int tc_configure(int num_sms) {
         if (_rc != EMPOSE_OK) return _rc;          \
     } while (0)
 
-int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_count, int jobs_per_item, int m_tiles,
-              int num_sms, cudaStream_t stream) {
-    EMPOSE_TRY_CONFIG(num_sms);
+static int tc_launch_inner(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_count, int jobs_per_item, int m_tiles,
+                           int num_sms, cudaStream_t stream) {
     const int max_clusters = g_max_clusters, cluster_mode = g_cluster_mode, debug_mode = g_debug_mode;
     const int2* no_items = nullptr;
     const int groups = job_count / jobs_per_item;
@@ -870,9 +929,8 @@ int tc_item_rows(int m_tiles, int num_sms) {
     return (g_max_clusters > 0 && m_tiles >= 2) ? 2 * kTileM : kTileM;
 }
 
-int tc_launch_items(const GemmJob* d_jobs, const void* d_maps, const void* d_items, int n_items, int rows_per_unit, uint32_t epoch,
-                    int m_tiles, int num_sms, cudaStream_t stream) {
-    EMPOSE_TRY_CONFIG(num_sms);
+static int tc_launch_items_inner(const GemmJob* d_jobs, const void* d_maps, const void* d_items, int n_items, int rows_per_unit, uint32_t epoch,
+                                 int m_tiles, int num_sms, cudaStream_t stream) {
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(d_maps);
     const int2* items = reinterpret_cast<const int2*>(d_items);
     if (rows_per_unit != tc_item_rows(m_tiles, num_sms)) {
@@ -900,6 +958,25 @@ int tc_launch_items(const GemmJob* d_jobs, const void* d_maps, const void* d_ite
     gemm_tc_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(d_jobs, maps, 0, n_items, 1, m_tiles, g_debug_mode, items, n_items, epoch);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
+}
+
+int tc_launch(const GemmJob* d_jobs, const void* d_maps, int job_begin, int job_count, int jobs_per_item, int m_tiles,
+              int num_sms, cudaStream_t stream) {
+    EMPOSE_TRY_CONFIG(num_sms);
+    const int kind = jobs_per_item > 1 ? 2 : 3;
+    tc_trace_begin(stream, kind);
+    const int rc = tc_launch_inner(d_jobs, d_maps, job_begin, job_count, jobs_per_item, m_tiles, num_sms, stream);
+    tc_trace_end(stream, kind);
+    return rc;
+}
+
+int tc_launch_items(const GemmJob* d_jobs, const void* d_maps, const void* d_items, int n_items, int rows_per_unit, uint32_t epoch,
+                    int m_tiles, int num_sms, cudaStream_t stream) {
+    EMPOSE_TRY_CONFIG(num_sms);
+    tc_trace_begin(stream, 1);
+    const int rc = tc_launch_items_inner(d_jobs, d_maps, d_items, n_items, rows_per_unit, epoch, m_tiles, num_sms, stream);
+    tc_trace_end(stream, 1);
+    return rc;
 }
 
 }  // namespace empose
