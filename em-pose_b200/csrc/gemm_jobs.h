@@ -47,8 +47,9 @@ struct GemmJob {
     int32_t n_count;         // columns computed (multiple of 16, <= kMaxTileN)
     int32_t m_rows;          // valid rows overall; rows >= m_rows are never written
     int32_t dep;             // chain-local index of the job that must have finished before A may be loaded (-1: none)
-    int32_t is_dep;          // 1: a later job of the same item names this job as its `dep`: its epilogue must hand the
-                             // stores of this thread (this job's and the earlier ones') over to the async proxy (TMA)
+    int32_t is_dep;          // != 0: a later job of the same item names this job as its `dep`: its epilogue must hand the
+                             // stores of this thread (this job's and the earlier ones') over to the async proxy (TMA).
+                             // 2: every such job comes at least two jobs later (the hand-over may be noticed lazily), 1: the next job may
     // ---- epilogue ----
     int32_t epi;
     int32_t round_out;       // 1: round outputs that feed later GEMMs to tf32 and use fast transcendentals
@@ -280,12 +281,20 @@ __device__ __forceinline__ void lstm_half_load_c(const GemmJob& j, int row0, int
     }
 }
 
+// `bias_sa` != 0: shared-memory address of a copy of the job's bias (columns relative to the job; tcgen05 executor)
 __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int lane, int c0, float (&v)[32],
-                                               float* __restrict__ stage, bool no_store = false, const float4* cpre = nullptr) {
+                                               float* __restrict__ stage, bool no_store = false, const float4* cpre = nullptr,
+                                               uint32_t bias_sa = 0) {
     const int n0 = j.n_begin + c0;                 // global column of v[0]
     const int row = row0 + lane;
     float bias[32];
-    if (j.bias) {
+    if (bias_sa) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 t = lds128f(bias_sa + (uint32_t)(c0 + 4 * q) * 4u);
+            bias[4 * q] = t.x; bias[4 * q + 1] = t.y; bias[4 * q + 2] = t.z; bias[4 * q + 3] = t.w;
+        }
+    } else if (j.bias) {
         const float4* bp = reinterpret_cast<const float4*>(j.bias + n0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {

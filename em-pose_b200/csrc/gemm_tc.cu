@@ -62,18 +62,26 @@ struct __align__(8) Control {
     uint64_t empty[kStagesPair];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
+    uint64_t job_full[2];             // the stager warp has put a job record and its bias into slot b
+    uint64_t job_empty[2];            // every epilogue warp is done with slot b
     uint32_t tmem_base;
-    volatile uint32_t epi_done;
+    volatile uint32_t done_seq[kEpiWarps];   // per epilogue warp: 1 + sequence number of the last job whose stores it has handed to the TMA
+    uint32_t job_done_cnt[4];         // per job (sequence number & 3): epilogue warps that have published their part (cross-CTA jobs)
 };
 
 constexpr int kEpiStageBytes = kEpiWarps * kStageFloats * 4;     // one 4 KB staging tile per epilogue warp (1024-byte aligned: TMA swizzle)
 static_assert(kOperandBytes % 1024 == 0 && (kStageFloats * 4) % 1024 == 0, "staging tiles must keep the 1024-byte alignment of the swizzle pattern");
+constexpr int kBiasBytes = 2 * kMaxTileN * 4;                    // the bias of the current and the next job
+constexpr int kJobSlotBytes = ((int)sizeof(GemmJob) + 15) / 16 * 16;
 constexpr int kControlBytes = 256;
-constexpr int kJobWords = (int)(sizeof(GemmJob) / 4);              // the epilogue keeps the current and the next job in shared memory
-static_assert(sizeof(GemmJob) % 8 == 0 && kJobWords <= kEpiThreads, "one word of a job per epilogue thread");
+constexpr int kJobWords = (int)(sizeof(GemmJob) / 4);
+static_assert(sizeof(GemmJob) % 8 == 0 && kJobWords <= 3 * 32, "the stager warp copies a job record with three words per lane");
 static_assert(sizeof(Control) <= kControlBytes, "Control grew");
-constexpr int kSmemBytes = kOperandBytes + kEpiStageBytes + 1024 /*alignment slack*/ + kControlBytes;      // dynamic
-static_assert(kSmemBytes + 2 * (int)sizeof(GemmJob) <= 227 * 1024, "shared memory budget (dynamic + the static job copies)");
+// dynamic shared memory, in this order; the base is 1024-byte aligned (checked at kernel start)
+constexpr int kOffStage = kOperandBytes, kOffBias = kOffStage + kEpiStageBytes, kOffJobs = kOffBias + kBiasBytes,
+              kOffControl = kOffJobs + 2 * kJobSlotBytes;
+constexpr int kSmemBytes = kOffControl + kControlBytes;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 // What the single-thread roles need of a job.  They fetch the fields of the NEXT job while working on the current one:
 // every epilogue ends in a device-scope fence, which invalidates L1, so a field read on demand is an L2 round trip on
@@ -354,6 +362,36 @@ __device__ __forceinline__ void tmem_load_64cols(uint32_t taddr, float (&v)[64])
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same read without the wait: the bias is fetched from shared memory while the accumulator is on its way
+__device__ __forceinline__ void tmem_load_64cols_nowait(uint32_t taddr, float (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31]), "=f"(v[32]),
+          "=f"(v[33]), "=f"(v[34]), "=f"(v[35]), "=f"(v[36]), "=f"(v[37]), "=f"(v[38]), "=f"(v[39]), "=f"(v[40]),
+          "=f"(v[41]), "=f"(v[42]), "=f"(v[43]), "=f"(v[44]), "=f"(v[45]), "=f"(v[46]), "=f"(v[47]), "=f"(v[48]),
+          "=f"(v[49]), "=f"(v[50]), "=f"(v[51]), "=f"(v[52]), "=f"(v[53]), "=f"(v[54]), "=f"(v[55]), "=f"(v[56]),
+          "=f"(v[57]), "=f"(v[58]), "=f"(v[59]), "=f"(v[60]), "=f"(v[61]), "=f"(v[62]), "=f"(v[63])
+        : "r"(taddr));
+}
+// (the values of an unwaited read must not be touched before this; "memory" keeps the compiler from moving their uses up)
+__device__ __forceinline__ void tmem_load_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// N bias values of the job's columns [c0, c0 + N) from the stager warp's shared-memory copy (the same address in every lane: broadcast)
+template <int N>
+__device__ __forceinline__ void bias_from_smem(uint32_t bias_sa, int c0, float (&b)[N]) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        const float4 t = lds128f(bias_sa + (uint32_t)(c0 + 4 * q) * 4u);
+        b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+    }
+}
+
 // Register budgets of the warp roles (setmaxnreg): the four single-thread / idle warps hand registers to the eight epilogue
 // warps, whose 64-column chunks keep the accumulator read, the bias and two packed halves live.  168 * 384 = 72 * 128 + 216 * 256; 128 * 512 = 56 * 128 + 152 * 384.
 constexpr int kRegsControl = kEpiWarps == 8 ? 72 : 56;
@@ -384,11 +422,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                                               int job_count, int jobs_per_item, int m_tiles,
                                                               int debug_mode, const int2* __restrict__ items, int n_items_table,
                                                               uint32_t epoch) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* epi_stage = reinterpret_cast<float*>(smem + kOperandBytes);
-    Control* ctl = reinterpret_cast<Control*>(smem + kOperandBytes + kEpiStageBytes);
-    __shared__ GemmJob job_s[2];        // static: the compiler then knows the address space (LDS, not generic loads)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* epi_stage = reinterpret_cast<float*>(smem + kOffStage);
+    float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
+    Control* ctl = reinterpret_cast<Control*>(smem + kOffControl);
+    auto job_slot = [&](uint32_t b) -> GemmJob& { return *reinterpret_cast<GemmJob*>(smem + kOffJobs + b * kJobSlotBytes); };
+    if (smem_u32(smem) & 1023u) __trap();      // the TMA swizzle patterns assume it
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -418,9 +457,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&ctl->tmem_full[b], 1);
-            mbar_init(&ctl->tmem_empty[b], kPair ? 2 : 1);
+            mbar_init(&ctl->tmem_empty[b], (kPair ? 2 : 1) * kEpiWarps);      // every epilogue warp hands its lanes of the accumulator back
+            mbar_init(&ctl->job_full[b], 1);
+            mbar_init(&ctl->job_empty[b], kEpiWarps);
         }
-        ctl->epi_done = 0;
+        for (int w = 0; w < kEpiWarps; ++w) ctl->done_seq[w] = 0;
+        for (int q = 0; q < 4; ++q) ctl->job_done_cnt[q] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -461,8 +503,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     }
                     if (lane == 0) trace_stamp(trace, 0, pseq, 0);
                     if (job.dep >= 0) {
+                        // every epilogue warp has handed its part of that job's output to the async proxy
                         const uint32_t need = items_done * (uint32_t)jobs_per_item + (uint32_t)job.dep + 1u;
-                        while (ctl->epi_done < need) {
+                        uint32_t spins = 0;
+                        while (!__all_sync(0xffffffffu, lane >= kEpiWarps || ctl->done_seq[lane] >= need)) {
+                            if (++spins > (1u << 28)) __trap();
                         }
                         __threadfence_block();
                         __syncwarp();
@@ -589,8 +634,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 }
             }
         }
-    } else if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));       // warps 2, 3: the rest of warpgroup 0
+    } else if (warp == 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));       // the TMEM allocator has nothing else to do
+    } else if (warp == 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
+        // ================= job stager =================
+        // Keeps the epilogue warps supplied with the record and the bias of the NEXT job in shared memory (two slots), so that
+        // their chunk loops never wait for global memory and need no CTA-wide barrier between jobs: every epilogue warp runs
+        // on its own, paced only by the accumulator barriers.
+        uint32_t seq = 0;
+        for (int item = item0; item < n_items; item += item_step) {
+            for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
+                const uint32_t b = seq & 1u;
+                const GemmJob* src = &jobs[job_index(item, jj)];
+                uint32_t w[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) w[q] = lane + 32 * q < kJobWords ? reinterpret_cast<const uint32_t*>(src)[lane + 32 * q] : 0u;
+                const float* bias = src->bias;
+                const int n_begin = src->n_begin, n4 = src->n_count >> 2;
+                float4 bv[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    bv[q] = (bias && lane + 32 * q < n4) ? __ldg(reinterpret_cast<const float4*>(bias + n_begin) + lane + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                mbar_wait(&ctl->job_empty[b], ((seq >> 1) & 1u) ^ 1u);
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (lane + 32 * q < kJobWords) reinterpret_cast<uint32_t*>(&job_slot(b))[lane + 32 * q] = w[q];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) reinterpret_cast<float4*>(bias_s + b * kMaxTileN)[lane + 32 * q] = bv[q];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->job_full[b]);
+            }
+        }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
         // ================= epilogue =================
@@ -600,33 +675,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         uint32_t seq = 0;
         bool generic_stores = false;              // this thread has stored from registers since its last proxy fence
         bool tma_pending = false;                 // (warp-uniform) a TMA store of this warp may still be reading its staging tile
-        auto release_tile = [&]() {               // before the staging tile is written by any other path
-            if (tma_pending) {
-                if (lane == 0) bulk_wait_read0();
+        uint32_t pub_pending = 0;                 // (warp-uniform) 1 + sequence number of a job whose TMA stores are not yet known to be complete
+        // Wait until the staging tile may be rewritten.  A deferred publication rides on the same wait: by now the stores of the
+        // job it belongs to are a chunk's worth of work old, so waiting for their completion instead of just their reads
+        // costs next to nothing, whereas at the end of the job it was ~1000 cycles on every epilogue warp's critical path.
+        auto release_tile = [&]() {
+            if (tma_pending || pub_pending) {
+                if (lane == 0) {
+                    if (pub_pending) { bulk_wait_all0(); ctl->done_seq[ew] = pub_pending; }
+                    else bulk_wait_read0();
+                }
                 __syncwarp();
                 tma_pending = false;
+                pub_pending = 0;
             }
         };
-        // The epilogue reads job fields all the time (per 32-column chunk): it works on a shared-memory copy.  Thread e
-        // of the 256 epilogue threads carries word e of the NEXT job through the current one and drops it into the other
-        // slot before the barrier that ends the job.
         const int et = (int)threadIdx.x - 4 * 32;
-        if (item0 < n_items && et < kJobWords)
-            reinterpret_cast<uint32_t*>(&job_s[0])[et] = reinterpret_cast<const uint32_t*>(&jobs[job_index(item0, 0)])[et];
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         for (int item = item0; item < n_items; item += item_step) {
             const int m0 = (kCluster == 2 ? 2 * item_unit(item) + (int)crank : item_unit(item)) * kTileM;
             for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
                 const uint32_t buf = seq & 1u;
-                const GemmJob& job = job_s[buf];
-                uint32_t next_word = 0;
-                bool has_next = false;
-                {
-                    const int nj = jj + 1 < jobs_per_item ? jj + 1 : 0;
-                    const int ni = nj ? item : item + item_step;
-                    has_next = ni < n_items && et < kJobWords;
-                    if (has_next) next_word = reinterpret_cast<const uint32_t*>(&jobs[job_index(ni, nj)])[et];
-                }
+                mbar_wait(&ctl->job_full[buf], (seq >> 1) & 1u);
+                const GemmJob& job = job_slot(buf);
+                const uint32_t bias_sa = smem_u32(bias_s + buf * kMaxTileN);
                 // activations chained inside this CTA live in CTA-local scratch rows: they are re-read from L2 by the next
                 // layer and overwritten by the next tile before they would be written back to HBM
                 const int row0 = (job.out_scratch ? (int)blockIdx.x * kTileM : m0) + quad * 32;
@@ -663,20 +734,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 //  eight bias loads one by one into the additions: 11 % slower on a [131072 x 512] . [512 x 512] layer.)
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     if (kWideChunks && c0 + 64 <= lv.fast_cols && c0 + 64 <= c_end && !(debug_mode & 1024)) {
-                        // fp16 linear jobs, 64 columns at a time: ONE accumulator read (one wait) per 64 columns with the bias loads in
-                        // flight meanwhile, packed fp32 arithmetic, and the [32 rows x 128 B] block leaves through ONE TMA store
+                        // fp16 linear jobs, 64 columns at a time: ONE accumulator read (one wait) per 64 columns, the bias from
+                        // shared memory, packed fp32 arithmetic, and the [32 rows x 128 B] block leaves through ONE TMA store
                         // from the warp's staging tile (no shared-memory read-back, no per-lane global stores).
                         if (lv.out_map >= 0 && !(debug_mode & 2048)) {
                             float v2[64], bb[64];
-                            linear_half_load_bias(lv, c0, *reinterpret_cast<float(*)[32]>(&bb[0]));
-                            linear_half_load_bias(lv, c0 + 32, *reinterpret_cast<float(*)[32]>(&bb[32]));
-                            tmem_load_64cols(taddr + (uint32_t)c0, v2);
+                            tmem_load_64cols_nowait(taddr + (uint32_t)c0, v2);
+                            bias_from_smem<64>(bias_sa, c0, bb);
+                            tmem_load_wait();
                             if (!(debug_mode & 4)) {
                                 uint32_t pk[32];
                                 linear_half_pack64(lv, v2, bb, pk);
                                 const uint32_t tile = smem_addr_of(my_stage);
-                                if (lane == 0) bulk_wait_read0();          // the previous block of this warp has left the tile
-                                __syncwarp();
+                                release_tile();          // the previous block of this warp has left the tile
 #pragma unroll
                                 for (int q = 0; q < 8; ++q)
                                     sts128(tile + lane * 128 + ((q ^ (lane & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
@@ -693,9 +763,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         }
                         release_tile();
                         float v2[64], b0[32], b1[32];
-                        linear_half_load_bias(lv, c0, b0);
-                        linear_half_load_bias(lv, c0 + 32, b1);
-                        tmem_load_64cols(taddr + (uint32_t)c0, v2);
+                        tmem_load_64cols_nowait(taddr + (uint32_t)c0, v2);
+                        bias_from_smem<32>(bias_sa, c0, b0);
+                        bias_from_smem<32>(bias_sa, c0 + 32, b1);
+                        tmem_load_wait();
                         if (!(debug_mode & 4)) {
                             uint32_t pk[16];
                             linear_half_pack(lv, *reinterpret_cast<const float(*)[32]>(&v2[0]), b0, pk);
@@ -711,7 +782,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     float v[32];
                     if (c0 + 32 <= lv.fast_cols) {
                         float bias[32];
-                        linear_half_load_bias(lv, c0, bias);              // in flight while the accumulator is read
+                        bias_from_smem<32>(bias_sa, c0, bias);
                         tmem_load_32cols(taddr + (uint32_t)c0, v);
                         if (!(debug_mode & 4)) linear_half_chunk(lv, row0, lane, c0, v, bias, my_stage, (debug_mode & 16) != 0);
                         generic_stores = true;
@@ -724,43 +795,65 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         tmem_load_32cols(taddr + (uint32_t)c0, v);
                     }
                     if (!(debug_mode & 4))
-                        epilogue_chunk(job, row0, lane, c0, v, my_stage, (debug_mode & 16) != 0, lstm_pre ? cpre : nullptr);
+                        epilogue_chunk(job, row0, lane, c0, v, my_stage, (debug_mode & 16) != 0, lstm_pre ? cpre : nullptr, bias_sa);
                     generic_stores = true;
                     // ... and the next pair's while this pair is being computed
                     if (lstm_pre && !(c0 & 32) && c0 + 64 < c_end) lstm_half_load_c(job, row0, lane, c0 + 64, cpre);
                 }
+                // ---- the accumulator goes back to the MMA issuer as soon as this warp has read its lanes ----
                 tcgen05_fence_before();
+                __syncwarp();
                 if (et == 0) trace_stamp(trace, 2, seq, 2);
-                if (has_next) reinterpret_cast<uint32_t*>(&job_s[buf ^ 1u])[et] = next_word;
-                if (!(debug_mode & 8) && (job.is_dep || job.done_ctr || (debug_mode & 512))) {
-                    // Only a job that a later job of this item waits for publishes stores (its own and, by program order,
-                    // those of the jobs before it: every thread owns the same rows and column half in all jobs).
-                    // The only in-kernel consumer of these stores is this CTA's own TMA (scratch activations of the next
-                    // layer): order them before the barrier at CTA scope and hand them to the async proxy.  A device-scope
-                    // fence here also invalidates L1 on every job, which turned every bias / sequence-length / job-field
-                    // read of the next job into an L2 round trip (bit 64 brings it back for comparison).
-                    // Blocks that left through TMA stores are already in the async proxy: their issuing lane waits for the writes
-                    // to complete.  Stores from registers (any other path, this job or an earlier one of the item) need the fence.
-                    if (lane == 0) bulk_wait_all0();
+                if (lane == 0) {
+                    if (kPair) mbar_arrive_cluster(mapa_rank0(&ctl->tmem_empty[buf]));      // CTA 0 issues the MMAs of both
+                    else mbar_arrive(&ctl->tmem_empty[buf]);
+                }
+                // ---- publication: only a job some later job waits for hands its stores over ----
+                const int is_dep = job.is_dep;
+                uint32_t* const done_ctr = job.done_ctr;
+                if (!(debug_mode & 8) && (is_dep || done_ctr)) {
+                    // Blocks that left through TMA stores are in the async proxy already: their issuing lane has to see the
+                    // writes complete.  Stores from registers (any other path, this job's or an earlier one's: a thread owns
+                    // the same rows and columns in all jobs of an item) are ordered at CTA scope and handed to the async
+                    // proxy by the thread that made them.
+                    const bool had_generic = generic_stores;      // warp-uniform: the paths above are
                     if (generic_stores) {
-                        if (debug_mode & 64) __threadfence();
-                        else __threadfence_block();
+                        __threadfence_block();
                         asm volatile("fence.proxy.async;" ::: "memory");
                         generic_stores = false;
                     }
+                    __syncwarp();
+                    if (is_dep == 2 && !had_generic && !done_ctr) {
+                        // the dependent job is at least two jobs away: its producer can wait for the completion to be noticed at
+                        // this warp's next staging-tile wait (release_tile)
+                        if (pub_pending && lane == 0) { bulk_wait_all0(); ctl->done_seq[ew] = pub_pending; }      // (an earlier one still open: close it now)
+                        pub_pending = seq + 1u;
+                    } else {
+                        if (lane == 0) {
+                            bulk_wait_all0();
+                            if (is_dep) ctl->done_seq[ew] = seq + 1u;
+                        }
+                        pub_pending = 0;
+                        tma_pending = false;
+                        if (done_ctr) {
+                            // cross-CTA consumers (the LSTM wavefront): the LAST epilogue warp to get here publishes the tile;
+                            // the acq_rel count makes the other warps' stores part of what its release covers
+                            if (lane == 0) {
+                                uint32_t old;
+                                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&ctl->job_done_cnt[seq & 3u])) : "memory");
+                                if ((old + 1u) % (uint32_t)kEpiWarps == 0u && m0 < m_tiles * kTileM) red_release_gpu(done_ctr + m0 / kTileM, 1u);
+                            }
+                        }
+                    }
+                } else if (pub_pending && c_begin >= c_end) {
+                    release_tile();          // (a warp without columns in this job never reaches the staging-tile wait)
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->job_empty[buf]);
                 if (et == 0) trace_stamp(trace, 2, seq, 3);
-                if (threadIdx.x == 4 * 32) {
-                    if (kPair) mbar_arrive_cluster(mapa_rank0(&ctl->tmem_empty[buf]));      // CTA 0 issues the MMAs of both
-                    else mbar_arrive(&ctl->tmem_empty[buf]);
-                    ctl->epi_done = seq + 1u;
-                    // publish this tile to the other CTAs: the barrier above ordered every epilogue thread's stores before
-                    // this thread, the release makes them visible device-wide before the count
-                    if (job.done_ctr && m0 < m_tiles * kTileM) red_release_gpu(job.done_ctr + m0 / kTileM, 1u);
-                }
             }
         }
+        release_tile();
         if (lane == 0) bulk_wait_all0();          // no TMA store may still read this CTA's shared memory when it exits
     }
 

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -280,7 +281,11 @@ struct JobBook {        // jobs + tensor maps of one plan
         }
         // `dep` counts jobs from the start of the range; ranges that use it run as ONE item per row tile (per_item == count),
         // so this is also the index inside the item.  The job it names must publish its stores to the TMA (gemm_tc.cu).
-        if (dep >= 0) jobs[(size_t)range->begin + dep].is_dep = 1;
+        if (dep >= 0) {
+            int32_t& flag = jobs[(size_t)range->begin + dep].is_dep;
+            const int kind = range->count - dep >= 2 ? 2 : 1;          // distance of the first job added here from the one it waits for
+            flag = flag ? std::min(flag, kind) : kind;
+        }
         for (int t = 0; t < W.n_tiles; ++t) {
             GemmJob j = proto;
             j.a_ptr[0] = a0.ptr; j.a_stride[0] = a0.stride; j.a_k[0] = a0.k;
