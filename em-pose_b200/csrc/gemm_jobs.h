@@ -35,6 +35,8 @@ struct GemmJob {
     int32_t in_half;         // 1: A and W hold fp16 elements (kind::f16, 64-element K chunks); strides / extents count elements
     int32_t out_half;        // 1: `out` (and, for LSTM jobs, h_prev) hold fp16 elements
     int32_t out_scratch;     // 1: the output is CTA-local scratch (tcgen05 executor only)
+    int32_t c_map1;          // 1 + tensor-map slot of `c_state` with a [32 rows x 32 fp32] box (tcgen05 executor, fp16 LSTM jobs: the cell-state
+                             // block of an epilogue warp travels by TMA), 0: none
     int32_t out_map1;        // 1 + tensor-map slot of `out` with a [32 rows x 64 fp16] box (tcgen05 executor: the fp16 linear epilogue
                              // leaves through TMA stores), 0: none -- the epilogue stores from registers
     // ---- W operand: packed [n_total][w_ld], K-major, segment s starts at column w_koff[s] ----

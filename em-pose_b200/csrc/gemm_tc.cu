@@ -65,6 +65,7 @@ struct __align__(8) Control {
     uint64_t job_full[2];             // the stager warp has put a job record and its bias into slot b
     uint64_t job_empty[2];            // every epilogue warp is done with slot b
     uint32_t tmem_base;
+    uint64_t c_bar[kEpiWarps];        // per epilogue warp: its cell-state block has arrived in its staging tile (LSTM jobs)
     volatile uint32_t done_seq[kEpiWarps];   // per epilogue warp: 1 + sequence number of the last job whose stores it has handed to the TMA
     uint32_t job_done_cnt[4];         // per job (sequence number & 3): epilogue warps that have published their part (cross-CTA jobs)
 };
@@ -73,7 +74,7 @@ constexpr int kEpiStageBytes = kEpiWarps * kStageFloats * 4;     // one 4 KB sta
 static_assert(kOperandBytes % 1024 == 0 && (kStageFloats * 4) % 1024 == 0, "staging tiles must keep the 1024-byte alignment of the swizzle pattern");
 constexpr int kBiasBytes = 2 * kMaxTileN * 4;                    // the bias of the current and the next job
 constexpr int kJobSlotBytes = ((int)sizeof(GemmJob) + 15) / 16 * 16;
-constexpr int kControlBytes = 256;
+constexpr int kControlBytes = 288;
 constexpr int kJobWords = (int)(sizeof(GemmJob) / 4);
 static_assert(sizeof(GemmJob) % 8 == 0 && kJobWords <= 3 * 32, "the stager warp copies a job record with three words per lane");
 static_assert(sizeof(Control) <= kControlBytes, "Control grew");
@@ -392,6 +393,44 @@ __device__ __forceinline__ void bias_from_smem(uint32_t bias_sa, int c0, float (
     }
 }
 
+// ---- fp16 LSTM jobs, the fast epilogue: one warp, 32 rows x 128 gate columns = 32 hidden units per row ----
+// NaN-propagating minimum (a clamp must not swallow the non-finite values the precision guard of the host class looks for)
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// One LSTM cell (layers.py:146-153 -> torch.nn.LSTM) from the four gate pre-activations and the old cell state with SEVEN
+// special-function operations instead of ten: with e_i = exp(-x_i), e_f = exp(-x_f), e_g = exp(2 x_g), e_o = exp(-x_o)
+//   c' = sigmoid(x_f) c + sigmoid(x_i) tanh(x_g) = [c (1 + e_i)(1 + e_g) + (e_g - 1)(1 + e_f)] / [(1 + e_i)(1 + e_g)(1 + e_f)]
+//   h  = sigmoid(x_o) tanh(c')                   = (e_c - 1) / [(1 + e_c)(1 + e_o)],   e_c = exp(2 c')
+// The exponents are clamped where the functions have long reached their limits in fp32 (sigmoid(-20) = 2e-9, tanh(15) = 1 - 2e-13),
+// which keeps every product below 3e30.  The special-function pipe (4 lanes per cycle and scheduler) was the floor of the old
+// epilogue: 10 operations x 8192 cells per tile = 5120 cycles of the ~5900 the MMAs of a tile take.
+__device__ __forceinline__ void lstm_cell_fast(float xi, float xf, float xg, float xo, float c_old, float& c_new, float& h) {
+    constexpr float kL2e = 1.4426950408889634f;
+    const float ei = ex2_approx(min_nan(xi * -kL2e, 20.0f * kL2e));
+    const float ef = ex2_approx(min_nan(xf * -kL2e, 20.0f * kL2e));
+    const float eg = ex2_approx(min_nan(xg * (2.0f * kL2e), 30.0f * kL2e));
+    const float eo = ex2_approx(min_nan(xo * -kL2e, 20.0f * kL2e));
+    const float f1 = 1.0f + ef;
+    const float p = (1.0f + ei) * (1.0f + eg);
+    const float num = fmaf(c_old, p, (eg - 1.0f) * f1);
+    c_new = num * rcp_approx(p * f1);
+    const float ec = ex2_approx(min_nan(c_new * (2.0f * kL2e), 30.0f * kL2e));
+    h = (ec - 1.0f) * rcp_approx((1.0f + ec) * (1.0f + eo));
+}
+
 // Register budgets of the warp roles (setmaxnreg): the four single-thread / idle warps hand registers to the eight epilogue
 // warps, whose 64-column chunks keep the accumulator read, the bias and two packed halves live.  168 * 384 = 72 * 128 + 216 * 256; 128 * 512 = 56 * 128 + 152 * 384.
 constexpr int kRegsControl = kEpiWarps == 8 ? 72 : 56;
@@ -461,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
             mbar_init(&ctl->job_full[b], 1);
             mbar_init(&ctl->job_empty[b], kEpiWarps);
         }
+        for (int w = 0; w < kEpiWarps; ++w) mbar_init(&ctl->c_bar[w], 1);
         for (int w = 0; w < kEpiWarps; ++w) ctl->done_seq[w] = 0;
         for (int q = 0; q < 4; ++q) ctl->job_done_cnt[q] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -675,6 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         uint32_t seq = 0;
         bool generic_stores = false;              // this thread has stored from registers since its last proxy fence
         bool tma_pending = false;                 // (warp-uniform) a TMA store of this warp may still be reading its staging tile
+        uint32_t c_phase = 0;                     // (warp-uniform) parity of the next completion of this warp's cell-state barrier
         uint32_t pub_pending = 0;                 // (warp-uniform) 1 + sequence number of a job whose TMA stores are not yet known to be complete
         // Wait until the staging tile may be rewritten.  A deferred publication rides on the same wait: by now the stores of the
         // job it belongs to are a chunk's worth of work old, so waiting for their completion instead of just their reads
@@ -719,11 +760,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     for (int q = 0; q < 2; ++q)
                         if (job.wait_ctr[q]) wait_counter(job.wait_ctr[q] + m0 / kTileM, job.wait_need[q] * epoch);
                 }
+                // The fast LSTM epilogue (a full 256-column tile: this warp owns 128 gate columns = 32 hidden units of its 32 rows):
+                // the warp's [32 rows x 32 units] fp32 cell-state block comes by TMA straight into its staging tile (128-byte
+                // swizzle, conflict-free per-row reads) while the MMAs are still running, is updated in place and leaves by TMA.
+                const bool lstm_fast = lstm_pre && job.c_map1 > 0 && c_end - c_begin == 128 && !job.gates_out && !(debug_mode & 4096);
+                float* my_stage = epi_stage + ew * kStageFloats;
                 float4 cpre[4];
-                if (lstm_pre && c_begin < c_end) lstm_half_load_c(job, row0, lane, c_begin, cpre);
+                int lf_seq_len = 0;
+                if (lstm_fast) {
+                    release_tile();
+                    if (lane == 0) {
+                        // (the block was written by another CTA of this launch through ITS TMA; the counter wait above was the
+                        //  acquire, this orders the async-proxy read behind it)
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        mbar_arrive_expect_tx(&ctl->c_bar[ew], 32u * 128u);
+                        tma_load_2d(my_stage, &maps[job.c_map1 - 1], &ctl->c_bar[ew], lstm_unit_of_packed(job.n_begin + c_begin), row0);
+                    }
+                    if (row0 + lane < job.m_rows) lf_seq_len = __ldcg(job.seq_len + row0 + lane);
+                } else if (lstm_pre && c_begin < c_end) {
+                    lstm_half_load_c(job, row0, lane, c_begin, cpre);
+                }
                 // fp16 linear jobs: all fields the chunk loop needs, once per job
                 const LinearHalfView lv = linear_half_view(job, row0, lane);
-                float* my_stage = epi_stage + ew * kStageFloats;
                 if (et == 0) trace_stamp(trace, 2, seq, 0);
                 if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 else mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
@@ -732,6 +790,69 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 // (tried and dropped: software-pipelining the accumulator reads -- 16 columns at a time, or the next chunk's read
                 //  issued before the current chunk is staged.  With the read's registers live across the loop ptxas feeds the
                 //  eight bias loads one by one into the additions: 11 % slower on a [131072 x 512] . [512 x 512] layer.)
+                if (lstm_fast) {
+                    const int row = row0 + lane, unit0 = lstm_unit_of_packed(job.n_begin + c_begin);
+                    const bool in_rows = row < job.m_rows;
+                    const bool live = in_rows && job.t < lf_seq_len;
+                    const uint32_t tile = smem_addr_of(my_stage);
+                    mbar_wait(&ctl->c_bar[ew], c_phase);
+                    c_phase ^= 1u;
+                    uint32_t hp[16];                       // this row's 32 new hidden states, fp16
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {       // 64 gate columns = 16 units at a time
+                        float v[64], bb[64];
+                        tmem_load_64cols_nowait(taddr + (uint32_t)(c_begin + 64 * hf), v);
+                        bias_from_smem<64>(bias_sa, c_begin + 64 * hf, bb);
+                        float c_old[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 t = lds128f(tile + lane * 128 + (((4 * hf + q) ^ (lane & 7)) << 4));
+                            c_old[4 * q] = t.x; c_old[4 * q + 1] = t.y; c_old[4 * q + 2] = t.z; c_old[4 * q + 3] = t.w;
+                        }
+                        tmem_load_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) add_f32x2(v[2 * i], v[2 * i + 1], bb[2 * i], bb[2 * i + 1]);
+                        float c_new[16], h[16];
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                lstm_cell_fast(v[32 * g + k], v[32 * g + 8 + k], v[32 * g + 16 + k], v[32 * g + 24 + k], c_old[8 * g + k],
+                                               c_new[8 * g + k], h[8 * g + k]);
+                        if (live) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                sts128f(tile + lane * 128 + (((4 * hf + q) ^ (lane & 7)) << 4),
+                                        make_float4(c_new[4 * q], c_new[4 * q + 1], c_new[4 * q + 2], c_new[4 * q + 3]));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __half2 hh = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+                            hp[8 * hf + i] = *reinterpret_cast<const uint32_t*>(&hh);
+                        }
+                    }
+                    if (in_rows && !(debug_mode & 16)) {
+                        if (!live) {       // the sequence has ended: the state is carried (packed-sequence semantics); c stays as it is in the tile
+                            const uint4* hprev = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(job.h_prev) + (int64_t)row * job.h_prev_stride + unit0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 t = __ldcg(hprev + q);
+                                hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
+                            }
+                        }
+                        uint4* hout = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(job.out) + (int64_t)row * job.out_stride + unit0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) hout[q] = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+                    }
+                    generic_stores = true;
+                    fence_async_shared();
+                    __syncwarp();
+                    if (lane == 0 && !(debug_mode & 16)) {
+                        tma_store_2d(&maps[job.c_map1 - 1], tile, unit0, row0);
+                        bulk_commit();
+                    }
+                    tma_pending = true;
+                } else
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     if (kWideChunks && c0 + 64 <= lv.fast_cols && c0 + 64 <= c_end && !(debug_mode & 1024)) {
                         // fp16 linear jobs, 64 columns at a time: ONE accumulator read (one wait) per 64 columns, the bias from

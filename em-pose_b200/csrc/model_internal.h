@@ -272,6 +272,17 @@ struct JobBook {        // jobs + tensor maps of one plan
         return EMPOSE_OK;
     }
 
+    // fp16 LSTM jobs: a tensor map of the cell state [m_rows][hidden] fp32 (boxes of 32 rows x 32 units)
+    int attach_c_map(GemmJob& j) {
+        j.c_map1 = 0;
+        if (!use_tc || j.epi != EPI_LSTM || !j.out_half || !j.c_state || j.gates_out || (j.hidden & 3)) return EMPOSE_OK;
+        if (reinterpret_cast<uintptr_t>(j.c_state) & 15) return EMPOSE_OK;
+        int idx = -1;
+        EMPOSE_TRY(get_map(j.c_state, j.hidden, j.hidden, j.m_rows, 32, 0, &idx));
+        j.c_map1 = idx + 1;
+        return EMPOSE_OK;
+    }
+
     // appends one job per N tile of `W`; `proto` carries the epilogue fields (n_begin/n_count/maps are filled here)
     int add(const PackedMatrix& W, const ASrc& a0, const ASrc& a1, GemmJob proto, int m_rows, int dep, JobRange* range) {
         if (range->count == 0) range->begin = (int)jobs.size();
@@ -308,6 +319,7 @@ struct JobBook {        // jobs + tensor maps of one plan
             j.is_dep = 0;
             j.bias = W.bias;
             EMPOSE_TRY(attach_out_map(j));
+            EMPOSE_TRY(attach_c_map(j));
             jobs.push_back(j);
             ++range->count;
         }
