@@ -166,6 +166,12 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
                  ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int crd0, int crd1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(crd0), "r"(crd1), "l"(policy)
+        : "memory");
+}
 // CTA-pair (cta_group::2) variants.  The tile lands in the executing CTA's shared memory, the bytes are counted on a
 // barrier that may live in the peer CTA (`bar_cluster_addr` is a shared::cluster address, see mapa_rank0).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int crd0, int crd1) {
@@ -246,6 +252,19 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int crd0, int crd1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(crd0), "r"(crd1)
+                 : "memory");
+}
+// L2 eviction priorities: CTA-local scratch activations (written by a layer's epilogue, read back by the next layer's loads,
+// overwritten by the next tile) should stay in L2 -- evict_last -- instead of being written back to HBM under the pressure of
+// the streaming operands; they are 75 MB per launch of the 126 MB.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t smem_src, int crd0, int crd1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(crd0), "r"(crd1), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -530,6 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         // ================= TMA producer (whole warp, one elected lane issues) =================
         {
             uint32_t stage = 0, phase = 0, items_done = 0, pseq = 0;
+            const uint64_t keep_policy = l2_policy_evict_last();
             ProducerView nxt;
             if (item0 < n_items) nxt = producer_view(jobs[job_index(item0, 0)]);
             for (int item = item0; item < n_items; item += item_step, ++items_done) {
@@ -582,7 +602,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                     // both CTAs fill their own slot; the bytes of both are counted on CTA 0's barrier
                                     const uint32_t full0 = mapa_rank0(&ctl->full[stage]);
                                     if (crank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)kABytes + w_bytes);
-                                    tma_load_2d_pair(a_dst, a_map, full0, kc * ck, a_row);
+                                    if (job.a_scratch[seg] && !(debug_mode & 8192)) tma_load_2d_pair_hint(a_dst, a_map, full0, kc * ck, a_row, keep_policy);
+                                    else tma_load_2d_pair(a_dst, a_map, full0, kc * ck, a_row);
                                     tma_load_2d_pair(w_dst, &maps[job.w_map2], full0, w_k0 + kc * ck, job.n_begin + (int)crank * half_rows);
                                 } else if (debug_mode & 2) {            // measurement only: no loads, MMAs run on stale data
                                     mbar_arrive(&ctl->full[stage]);
@@ -715,6 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         uint32_t seq = 0;
         bool generic_stores = false;              // this thread has stored from registers since its last proxy fence
         bool tma_pending = false;                 // (warp-uniform) a TMA store of this warp may still be reading its staging tile
+        const uint64_t keep_policy = l2_policy_evict_last();
         uint32_t c_phase = 0;                     // (warp-uniform) parity of the next completion of this warp's cell-state barrier
         uint32_t pub_pending = 0;                 // (warp-uniform) 1 + sequence number of a job whose TMA stores are not yet known to be complete
         // Wait until the staging tile may be rewritten.  A deferred publication rides on the same wait: by now the stores of the
@@ -874,7 +896,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                 fence_async_shared();
                                 __syncwarp();
                                 if (lane == 0 && !(debug_mode & 16)) {
-                                    tma_store_2d(&maps[lv.out_map], tile, lv.out_col + c0, row0);
+                                    if (job.out_scratch && !(debug_mode & 8192)) tma_store_2d_hint(&maps[lv.out_map], tile, lv.out_col + c0, row0, keep_policy);
+                                    else tma_store_2d(&maps[lv.out_map], tile, lv.out_col + c0, row0);
                                     bulk_commit();
                                 }
                                 tma_pending = true;

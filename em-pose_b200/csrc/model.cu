@@ -931,6 +931,40 @@ int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const floa
     return EMPOSE_OK;
 }
 
+int empose_ief_submit_host(empose_ief* ctx, const float* marker_pos, const float* marker_oris, const float* offset_r,
+                           const float* offset_t, const int32_t* seq_lengths, const float* marker_masks, float* lstm_state,
+                           int32_t is_new_sequence, int32_t B, int32_t F, float* pose_hat, float* shape_hat,
+                           float* joints_hat, const empose_ief_history* history, int32_t slot, void* stream) {
+    EMPOSE_TRY(check_call(ctx, B, F));
+    if (!marker_pos || !marker_oris || !offset_r || !offset_t || !seq_lengths) { set_last_error("null input"); return EMPOSE_E_ARG; }
+    if (slot < 0 || slot >= 4) { set_last_error("slot must be 0..3"); return EMPOSE_E_ARG; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!ctx->copy_in) {
+        EMPOSE_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        EMPOSE_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    }
+    for (auto& e : ctx->slot_events[slot])
+        if (!e) EMPOSE_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // The upload goes on its own stream and is NOT ordered behind `stream`: it overlaps the compute of the requests before
+    // it; the pass runs on `stream` once the upload is there; the download follows on a third stream.  Every slot has its
+    // own workspace (plan), so up to four requests can be at different stages.
+    Plan* plp;
+    EMPOSE_TRY(build_plan(ctx, B, F, &plp, 8 + slot));
+    ctx->last_launches = 0;
+    EMPOSE_TRY(forward_host_chunk(ctx, *plp, B, 0, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks, lstm_state,
+                                  is_new_sequence, pose_hat, shape_hat, joints_hat, history, ctx->copy_in, s, ctx->copy_out,
+                                  ctx->slot_events[slot][0], ctx->slot_events[slot][1]));
+    EMPOSE_CUDA_TRY(cudaEventRecord(ctx->slot_events[slot][2], ctx->copy_out));
+    return EMPOSE_OK;
+}
+
+int empose_ief_wait_host(empose_ief* ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot >= 4) { set_last_error("bad context or slot"); return EMPOSE_E_ARG; }
+    if (!ctx->slot_events[slot][2]) { set_last_error("nothing was submitted into this slot"); return EMPOSE_E_ARG; }
+    EMPOSE_CUDA_TRY(cudaEventSynchronize(ctx->slot_events[slot][2]));
+    return EMPOSE_OK;
+}
+
 int empose_sensors_create(const empose_tensor* tensors, int32_t n_tensors, int32_t precision, int32_t device, empose_ief** out) {
     if (!tensors || !out) { set_last_error("null argument"); return EMPOSE_E_ARG; }
     *out = nullptr;

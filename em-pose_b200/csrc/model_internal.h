@@ -429,10 +429,12 @@ struct IefData {            // everything behind the opaque `empose_ief` handle
     // copy streams and events of the pipelined host-buffer entry point (empose_ief_forward_host)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> pipe_events;
+    cudaEvent_t slot_events[4][3] = {};      // streaming host entry point: per in-flight slot {uploaded, computed, downloaded}
     ~IefData() {
         for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto& e : prof_main_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto& e : pipe_events) cudaEventDestroy(e);
+        for (auto& se : slot_events) for (auto& e : se) if (e) cudaEventDestroy(e);
         if (copy_in) cudaStreamDestroy(copy_in);
         if (copy_out) cudaStreamDestroy(copy_out);
     }

@@ -20,7 +20,7 @@ _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2
 
 #: every symbol include/empose_b200.h declares (checked by tests/test_cabi.py)
 EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_set_option', 'empose_ief_create', 'empose_ief_destroy',
-                    'empose_ief_forward', 'empose_ief_forward_host', 'empose_sensor_project',
+                    'empose_ief_forward', 'empose_ief_forward_host', 'empose_ief_submit_host', 'empose_ief_wait_host', 'empose_sensor_project',
                     'empose_ief_last_launch_count', 'empose_ief_set_profiling', 'empose_ief_profile_read', 'empose_ief_profile_read_main',
                     'empose_gemm_selftest', 'empose_gemm_bench', 'empose_smpl_create', 'empose_smpl_destroy',
                     'empose_smpl_forward', 'empose_train_layout', 'empose_train_sizes', 'empose_train_create',
@@ -88,6 +88,10 @@ def load():
     lib.empose_ief_forward.argtypes = fwd_args
     lib.empose_ief_forward_host.restype = ctypes.c_int
     lib.empose_ief_forward_host.argtypes = fwd_args
+    lib.empose_ief_submit_host.restype = ctypes.c_int
+    lib.empose_ief_submit_host.argtypes = fwd_args[:-1] + [i32, vp]
+    lib.empose_ief_wait_host.restype = ctypes.c_int
+    lib.empose_ief_wait_host.argtypes = [vp, i32]
     lib.empose_sensor_project.restype = ctypes.c_int
     lib.empose_sensor_project.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.empose_ief_last_launch_count.restype = ctypes.c_int64
@@ -306,6 +310,38 @@ class IefContext(object):
                 _ptr(marker_masks), _ptr(state), int(bool(is_new_sequence)), b, f, _ptr(pose), _ptr(shape),
                 _ptr(joints), None, _stream()))
         return {'pose': pose, 'shape': shape, 'joints': joints, 'lstm_state': state}
+
+    def submit_host(self, slot, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None, out=None):
+        """Streaming form of :meth:`forward_host` for fresh windows (``empose_ief_submit_host``): enqueue one request into the
+        in-flight ``slot`` (0..3) and return at once; :meth:`wait_host` makes the results valid.  Inputs must be pinned
+        float32 / int32 host tensors that stay untouched until then.  ``out`` (the dict a previous call on this slot
+        returned) is reused for the results, otherwise pinned tensors are allocated."""
+        import torch
+        b, f = int(marker_pos.shape[0]), int(marker_pos.shape[1])
+        for t in (marker_pos, marker_oris, offset_r, offset_t):
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_pinned():
+                raise EmposeError('submit_host takes pinned, contiguous float32 host tensors')
+        if seq_lengths.dtype != torch.int32 or not seq_lengths.is_pinned():
+            raise EmposeError('submit_host takes seq_lengths as a pinned int32 host tensor')
+        if marker_masks is not None and (marker_masks.dtype != torch.float32 or not marker_masks.is_pinned()):
+            raise EmposeError('submit_host takes marker_masks as a pinned float32 host tensor')
+        if out is None or tuple(out['pose'].shape) != (b, f, 66):
+            out = {'pose': torch.empty((b, f, 66), dtype=torch.float32, pin_memory=True),
+                   'shape': torch.empty((b, f, 10), dtype=torch.float32, pin_memory=True),
+                   'joints': torch.empty((b, f, 66), dtype=torch.float32, pin_memory=True)}
+        out['slot'] = int(slot)
+        out['inputs'] = (marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks)      # kept alive until the wait
+        with torch.cuda.device(self.device_index):
+            _check(load().empose_ief_submit_host(
+                self._handle, _ptr(marker_pos), _ptr(marker_oris), _ptr(offset_r), _ptr(offset_t), _ptr(seq_lengths),
+                _ptr(marker_masks), None, 1, b, f, _ptr(out['pose']), _ptr(out['shape']), _ptr(out['joints']), None, int(slot), _stream()))
+        return out
+
+    def wait_host(self, request):
+        """Blocks until the request :meth:`submit_host` returned has its results in ``request['pose' | 'shape' | 'joints']``."""
+        _check(load().empose_ief_wait_host(self._handle, int(request['slot'])))
+        request.pop('inputs', None)
+        return request
 
     def sensor_project(self, poses, shapes, offset_r, offset_t):
         """(R,66), (R,10), (R,12,3,3), (R,12,3) device tensors -> sensor_pos (R,12,3), sensor_ori (R,12,3,3), joints (R,22,3)."""

@@ -12,6 +12,7 @@
  *   empose_ief_forward             <- IterativeErrorFeedback.forward              empose/nn/models.py:485-632
  *   empose_ief_forward_host        <- same, host buffers (what scripts/evaluate_real.py:61 does around it:
  *                                     chunk.to_gpu(), net(chunk), .cpu())
+ *   empose_ief_submit_host / _wait_host <- the same loop with two or more chunks in flight (copies hidden behind compute)
  *   empose_sensor_project          <- IterativeErrorFeedback.get_estimated_real_markers
  *                                                                                 empose/nn/models.py:471-483
  *   empose_sensors_create          <- SMPLFK + SampleMarkersWithOffsets (data synthesis before the hot path)
@@ -158,6 +159,20 @@ int empose_ief_forward_host(empose_ief* ctx, const float* marker_pos, const floa
                             const float* marker_masks, float* lstm_state, int32_t is_new_sequence, int32_t B,
                             int32_t F, float* pose_hat, float* shape_hat, float* joints_hat,
                             const empose_ief_history* history, void* stream);
+
+/* Streaming form of empose_ief_forward_host (the loop of scripts/evaluate_real.py:39-61 -- chunk.to_gpu(), net(chunk), .cpu() --
+ * with the copies of one chunk hidden behind the pass of another): enqueue one request into the in-flight slot `slot`
+ * (0..3) and return without waiting.  The upload runs on an internal stream (not ordered behind `stream`), the pass on
+ * `stream`, the download on a third stream; each slot has its own device workspace.  The host buffers (pinned, or the
+ * copies are not asynchronous) must stay untouched until empose_ief_wait_host(ctx, slot) has returned, and a slot must be
+ * waited for before it is submitted into again.  Arguments as for empose_ief_forward_host. */
+int empose_ief_submit_host(empose_ief* ctx, const float* marker_pos, const float* marker_oris,
+                           const float* offset_r, const float* offset_t, const int32_t* seq_lengths,
+                           const float* marker_masks, float* lstm_state, int32_t is_new_sequence, int32_t B,
+                           int32_t F, float* pose_hat, float* shape_hat, float* joints_hat,
+                           const empose_ief_history* history, int32_t slot, void* stream);
+/* Blocks the calling host thread until the request submitted into `slot` has written its results to the host buffers. */
+int empose_ief_wait_host(empose_ief* ctx, int32_t slot);
 
 /* SMPL-H sub-model -> 12 sensor frames with offsets applied -> first 22 joints, for R frames.
  *   poses [R][66], shapes [R][10], offset_r [R][12][9], offset_t [R][12][3]

@@ -295,6 +295,43 @@ def test_pipelined_host_entry_point_equals_one_pass(dev, smpl_npz):
         assert torch.equal(a[k].cpu(), h[k]), k
 
 
+def test_streamed_requests_equal_blocking_calls(dev, smpl_npz):
+    """empose_ief_submit_host / empose_ief_wait_host: five different requests streamed through two in-flight slots (the
+    upload of one and the download of another run under the pass of a third) return exactly what one blocking
+    empose_ief_forward_host call per request returns."""
+    net = util.build_module(smpl_npz, num_iterations=2, precision=native.PRECISION_FP16, device=dev)
+    ctx = net.native_context(dev)
+    b, f = 300, 4
+    pin = lambda t: t.contiguous().pin_memory()
+    reqs_in = []
+    for k in range(5):
+        g = torch.Generator().manual_seed(100 + k)
+        p = synthetic.synth_window_params(b, f, seed=200 + k, ragged=True, offsets=True)
+        pos = 0.3 * torch.randn(b, f, 36, generator=g)
+        ori = (torch.eye(3).reshape(1, 1, 1, 9) + 0.05 * torch.randn(b, f, 12, 9, generator=g)).reshape(b, f, 108)
+        reqs_in.append((pin(pos), pin(ori), pin(torch.from_numpy(p['offset_r'])), pin(torch.from_numpy(p['offset_t'])),
+                        pin(torch.from_numpy(p['seq_lengths']).to(torch.int32))))
+    want = [ctx.forward_host(*r, want_state=False) for r in reqs_in]
+    got, inflight, outs = [None] * 5, [None, None], [None, None]
+    for k, r in enumerate(reqs_in):
+        slot = k % 2
+        if inflight[slot] is not None:
+            j, req = inflight[slot]
+            done = ctx.wait_host(req)
+            got[j] = {n: done[n].clone() for n in ('pose', 'shape', 'joints')}
+            outs[slot] = done
+        inflight[slot] = (k, ctx.submit_host(slot, *r, out=outs[slot]))
+    for slot in range(2):
+        j, req = inflight[slot]
+        done = ctx.wait_host(req)
+        got[j] = {n: done[n].clone() for n in ('pose', 'shape', 'joints')}
+    for k in range(5):
+        for n in ('pose', 'shape', 'joints'):
+            assert torch.equal(got[k][n], want[k][n]), (k, n)
+    with pytest.raises(native.EmposeError):
+        ctx.submit_host(0, reqs_in[0][0].clone(), *reqs_in[0][1:])          # not pinned
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # other configurations of the reference and edge cases
 # ---------------------------------------------------------------------------------------------------------------------
