@@ -35,6 +35,13 @@ struct FanCfg {
     static_assert(kChainThreads <= kThreads, "chain lanes must fit the CTA");
 };
 
+// optional phase timing (EMPOSE_MAIN_TICKS): thread 0 of one mid-grid CTA stores clock64() at the phase boundaries
+#define FAN_TICK(k) do { if (p.ticks && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) p.ticks[k] = clock64(); } while (0)
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 __device__ __forceinline__ float grad_operand_f32(float x, int mode) { return mode == OPERAND_TF32 ? round_tf32(x) : x; }
 
 template <int SLOTS, int MAXD, int G, int CTAS>
@@ -55,6 +62,7 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
 
     // ---- P0: inputs.  The lane's ring, offsets and measurement go straight to registers; their latency hides behind
     // ---- the joint phases.
+    FAN_TICK(0);
     float vp[RING * 3], off[12], meas[12];
     if (item) {
         const int64_t row = row0 + fs;
@@ -89,19 +97,25 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
             for (int i = 0; i < 12; ++i) meas[i] = 0.0f;
         }
     }
-    {   // rows of the CTA's frames are contiguous in global memory: flat, coalesced copies
+    {   // rows of the CTA's frames are contiguous in global memory: flat, coalesced copies, straight into shared memory
+        // (cp.async: all of a thread's ~11 words are in flight at once.  Through registers the compiler kept each load next to
+        //  its store, a full memory round trip per loop iteration: the phase took ~8000 of the CTA's ~46000 cycles.)
         const float* th = p.theta + row0 * kPoseDim;
-        for (int idx = tid; idx < nf * kPoseDim; idx += NT) { const int f = idx / kPoseDim; state(f).theta[idx - f * kPoseDim] = th[idx]; }
+        for (int idx = tid; idx < nf * kPoseDim; idx += NT) { const int f = idx / kPoseDim; cp_async_4(&state(f).theta[idx - f * kPoseDim], th + idx); }
         const float* jr = p.jrest + row0 * kJrestLd;
         for (int idx = tid; idx < nf * kJrestLd; idx += NT) {
             const int f = idx / kJrestLd, c = idx - f * kJrestLd;
-            if (c < kPoseDim) (&state(f).jrest[0][0])[c] = jr[idx];
+            if (c < kPoseDim) cp_async_4(&state(f).jrest[0][0] + c, jr + idx);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    FAN_TICK(1);
     // ---- P1: joint rotations ----
     for (int idx = tid; idx < nf * kJoints; idx += NT) { const int f = idx / kJoints; jt_rodrigues(state(f), idx - f * kJoints); }
     __syncthreads();
+    FAN_TICK(2);
     // ---- P2: kinematic chain, three lanes per frame on the last warp ----
     if (tid >= NT - Cfg::kChainThreads) {
         const int l = tid - (NT - Cfg::kChainThreads);
@@ -111,6 +125,7 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
         }
     }
     __syncthreads();
+    FAN_TICK(3);
     // ---- P3: the (frame, sensor) items ----
     if (item) {
         const int64_t row = row0 + fs;
@@ -149,7 +164,9 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
         for (int idx = tid; idx < nf * kPoseDim; idx += NT) { const int f = idx / kPoseDim; dst[idx] = (&state(f).gpos[0][0])[idx - f * kPoseDim]; }
     }
     if (!grad) return;
+    FAN_TICK(4);
     __syncthreads();
+    FAN_TICK(5);
     // ---- P4: dE/dA_j = sum of the partials naming joint j, fixed order; a thread owns (j, e) of EVERY frame, so the
     // ---- lists are read once per CTA.  Training: the FK-loss upstream replaces the posed joints in place.
     const bool joint_up = p.joints_gt != nullptr;
@@ -160,6 +177,7 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
             jt_joint_residual(state(f), p.joints_gt + (row0 + f) * kPoseDim, p.joint_weight, idx - f * kJoints);
         }
     __syncthreads();
+    FAN_TICK(6);
     // ---- P5: reverse sweep of the chain ----
     if (tid >= NT - Cfg::kChainThreads) {
         const int l = tid - (NT - Cfg::kChainThreads);
@@ -169,9 +187,11 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
         }
     }
     __syncthreads();
+    FAN_TICK(7);
     // ---- P6: local gradients dE/dR_j, dE/dJ_j (over the dead partial sums) ----
     jt_local_frames<float>(p.sub.parents, state, var_of, nf, tid, NT, joint_up);
     __syncthreads();
+    FAN_TICK(8);
     // ---- P7: outputs ----
     for (int idx = tid; idx < nf * kJoints; idx += NT) {
         const int f = idx / kJoints;
@@ -179,6 +199,20 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
     }
     {
         const int ld = p.dj_ld;
+        if (p.round_out == OPERAND_F16 && (ld & 3) == 0) {      // four fp16 values per store (rows of the CTA's frames are contiguous)
+            uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.dj) + row0 * ld);
+            for (int q = tid; q < nf * ld / 4; q += NT) {
+                const int f = (4 * q) / ld, c = 4 * q - f * ld;
+                const float* v = var_of(f) + kJoints * 9;
+                float x[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = c + k < kPoseDim ? v[c + k] * kDvpScale : 0.0f;
+                const __half2 a = __floats2half2_rn(x[0], x[1]), b = __floats2half2_rn(x[2], x[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&b);
+                dst[q] = pk;
+            }
+        } else
         for (int idx = tid; idx < nf * ld; idx += NT) {
             const int f = idx / ld, c = idx - f * ld;
             const float v = c < kPoseDim ? var_of(f)[kJoints * 9 + c] : 0.0f;
@@ -186,6 +220,7 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
             else p.dj[row0 * ld + idx] = grad_operand_f32(v, p.round_out);
         }
     }
+    FAN_TICK(9);
 }
 
 template <int SLOTS, int MAXD, int G, int CTAS>

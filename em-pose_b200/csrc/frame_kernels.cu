@@ -114,14 +114,29 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) 
     for (int f0 = 0; f0 < p.F; f0 += kUpdateGroup) {
         const int nf = min(kUpdateGroup, p.F - f0);
         const int64_t g0 = row0 + f0;
-        for (int i = tid; i < nf * kPoseDim; i += kUpdateThreads) {          // theta rows of the group are contiguous
-            const int f = i / kPoseDim, c = i - f * kPoseDim;
-            const float d = p.dtheta[g0 * kPoseDim + i];
-            const float v = p.first ? d : p.theta[g0 * kPoseDim + i] + p.step * d;
-            p.theta[g0 * kPoseDim + i] = v;
-            th[f][c] = v;
-            if (p.hist_pose) p.hist_pose[g0 * kPoseDim + i] = v;
-            if (p.xiter) store_operand(p.xiter, (g0 + f) * p.iter_stride + p.in_size + c, v, p.operand_mode);
+        // theta rows of the group are contiguous.  Loads of a whole batch of items first, then the stores: with one item per
+        // loop iteration every iteration was a full memory round trip (the compiler keeps a load behind the stores before it).
+        constexpr int kBatch = (kUpdateGroup * kPoseDim + kUpdateThreads - 1) / kUpdateThreads;
+        {
+            float d[kBatch], t0[kBatch];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                const int i = tid + q * kUpdateThreads;
+                d[q] = i < nf * kPoseDim ? __ldg(p.dtheta + g0 * kPoseDim + i) : 0.0f;
+                t0[q] = (i < nf * kPoseDim && !p.first) ? p.theta[g0 * kPoseDim + i] : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                const int i = tid + q * kUpdateThreads;
+                if (i < nf * kPoseDim) {
+                    const int f = i / kPoseDim, c = i - f * kPoseDim;
+                    const float v = p.first ? d[q] : t0[q] + p.step * d[q];
+                    p.theta[g0 * kPoseDim + i] = v;
+                    th[f][c] = v;
+                    if (p.hist_pose) p.hist_pose[g0 * kPoseDim + i] = v;
+                    if (p.xiter) store_operand(p.xiter, (g0 + f) * p.iter_stride + p.in_size + c, v, p.operand_mode);
+                }
+            }
         }
         for (int i = tid; i < nf * kBetas; i += kUpdateThreads) {
             const int f = i / kBetas, k = i - f * kBetas;

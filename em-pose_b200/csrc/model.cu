@@ -618,7 +618,7 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
             long long h[32];
             cudaMemcpy(h, tick_buf, sizeof(h), cudaMemcpyDeviceToHost);
             fprintf(stderr, "main_kernel ticks:");
-            for (int q = 1; q < 16; ++q) fprintf(stderr, " %lld", h[q] - h[q - 1]);
+            for (int q = 1; q < 10; ++q) fprintf(stderr, " %lld", h[q] - h[q - 1]);
             fprintf(stderr, "\n");
         }
         if (it == N) {
