@@ -269,28 +269,62 @@ __global__ void col_sum_finish_kernel(const double* __restrict__ scratch, int n,
     if (dst2) dst2[c] += v;
 }
 
-// 32 x 32 tile transpose through shared memory; block (32, 8)
+__global__ void __launch_bounds__(256) dw_reduce_kernel(const DwReduce* __restrict__ table) {
+    const DwReduce d = table[blockIdx.y];
+    const int n4 = d.count >> 2;                          // counts are multiples of 4 (row lengths are), buffers 16-byte aligned
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 acc = reinterpret_cast<float4*>(d.grad)[i];
+        for (int q = 0; q < d.splits; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(d.partial + (size_t)q * d.count) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(d.grad)[i] = acc;
+    }
+    if (blockIdx.x == 0)
+        for (int i = (n4 << 2) + threadIdx.x; i < d.count; i += blockDim.x) {
+            float acc = d.grad[i];
+            for (int q = 0; q < d.splits; ++q) acc += d.partial[(size_t)q * d.count + i];
+            d.grad[i] = acc;
+        }
+}
+
+// 64 x 64 tile transpose through shared memory; block (32, 8): sixteen loads per thread in flight before the first store
+// (with 32 x 32 tiles and four it ran at half the HBM rate: 88 us for a [65536 x 512] operand)
+constexpr int kTrTile = 64;
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int64_t src_ld, int64_t rows, int n, int shift,
                                                         int F, int round_out, float* __restrict__ dst, int64_t dst_ld) {
-    __shared__ float tile[32][33];
-    const int64_t r0 = (int64_t)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
-    for (int q = threadIdx.y; q < 32; q += 8) {
-        const int64_t r = r0 + q;
-        const int c = c0 + threadIdx.x;
-        float v = 0.0f;
-        if (r < rows && c < n) {
-            if (!shift) v = src[r * src_ld + c];
-            else if (r % F != 0) v = src[(r - 1) * src_ld + c];
+    __shared__ float tile[kTrTile][kTrTile + 1];
+    const int64_t r0 = (int64_t)blockIdx.x * kTrTile;
+    const int c0 = blockIdx.y * kTrTile;
+    float v[2][8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int q = threadIdx.y + 8 * k;
+            const int64_t r = r0 + q;
+            const int c = c0 + threadIdx.x + 32 * h;
+            float x = 0.0f;
+            if (r < rows && c < n) {
+                if (!shift) x = src[r * src_ld + c];
+                else if (r % F != 0) x = src[(r - 1) * src_ld + c];
+            }
+            v[h][k] = x;
         }
-        tile[q][threadIdx.x] = v;
-    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tile[threadIdx.y + 8 * k][threadIdx.x + 32 * h] = v[h][k];
     __syncthreads();
-    for (int q = threadIdx.y; q < 32; q += 8) {
-        const int c = c0 + q;
-        const int64_t r = r0 + threadIdx.x;
-        if (c < n && r < rows) dst[(int64_t)c * dst_ld + r] = maybe_round(tile[threadIdx.x][q], round_out);
-    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int q = threadIdx.y + 8 * k;
+            const int c = c0 + q;
+            const int64_t r = r0 + threadIdx.x + 32 * h;
+            if (c < n && r < rows) dst[(int64_t)c * dst_ld + r] = maybe_round(tile[threadIdx.x + 32 * h][q], round_out);
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -548,9 +582,17 @@ int launch_col_sum(const float* src, int64_t ld, int64_t rows, int n, double* sc
     return EMPOSE_OK;
 }
 
+int launch_dw_reduce(const DwReduce* d_table, int n_entries, int max_count, cudaStream_t s) {
+    if (n_entries == 0) return EMPOSE_OK;
+    const unsigned bx = (unsigned)std::max(1, std::min(64, (max_count / 4 + 255) / 256));
+    dw_reduce_kernel<<<dim3(bx, (unsigned)n_entries), 256, 0, s>>>(d_table);
+    EMPOSE_CUDA_TRY(cudaGetLastError());
+    return EMPOSE_OK;
+}
+
 int launch_transpose(const float* src, int64_t src_ld, int64_t rows, int n, int shift, int F, int round_out, float* dst,
                      int64_t dst_ld, cudaStream_t s) {
-    transpose_kernel<<<dim3(blocks_for(rows, 32), blocks_for(n, 32)), dim3(32, 8), 0, s>>>(src, src_ld, rows, n, shift, F, round_out,
+    transpose_kernel<<<dim3(blocks_for(rows, kTrTile), blocks_for(n, kTrTile)), dim3(32, 8), 0, s>>>(src, src_ld, rows, n, shift, F, round_out,
                                                                                            dst, dst_ld);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;

@@ -56,6 +56,10 @@ int launch_bn_param_grads(const double* sums, int S, int n, float* g_gamma, floa
 int launch_col_sum(const float* src, int64_t ld, int64_t rows, int n, double* scratch, float* dst, float* dst2, cudaStream_t s);
 // dst[c][r] = src[r'][c] for c < n, r < rows, with r' = r (shift = 0) or the previous frame of the same window
 // (shift = 1: r' = r - 1, zero at the first frame of every window of F frames).
+// Split-K weight gradients: grad[e] += sum_i partial[i * count + e] for every table entry (fixed order: bit-reproducible)
+struct DwReduce { float* grad; const float* partial; int32_t count; int32_t splits; };
+int launch_dw_reduce(const DwReduce* d_table, int n_entries, int max_count, cudaStream_t s);
+
 int launch_transpose(const float* src, int64_t src_ld, int64_t rows, int n, int shift, int F, int round_out, float* dst,
                      int64_t dst_ld, cudaStream_t s);
 
