@@ -275,7 +275,7 @@ def train_subrecord(args, device, dist, rank, world, windows=512, steps=5):
     ar_ms, losses = [], []
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()                      # scripts/train.py:136 (drops every .grad; the class re-attaches views of its flat vector)
         out = net(batch)
         _, vals = net.backward(batch, out)
         if dist is not None:
@@ -619,7 +619,7 @@ def run_b200_train(args, rank, local_rank, world):
     losses = []
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()
         out = net(batch)
         _, vals = net.backward(batch, out)
         if dist is not None:

@@ -200,6 +200,9 @@ struct empose_train {
     empose_ief_config cfg;
     Layout layout;
     float *params = nullptr, *grads = nullptr, *bn_buffers = nullptr;
+    empose_allreduce_fn sync_fn = nullptr;      // SyncBatchNorm: all-reduce of the batch statistics (null: per-rank statistics)
+    void* sync_user = nullptr;
+    int32_t sync_world = 1;
     Arena arena;
     std::vector<PackedMatrix> lstm_fw, lstm_bw;
     PackedMatrix heads_fw, heads_bw;
@@ -228,6 +231,14 @@ int run(empose_train* t, TrainPlan& pl, const JobRange& r, int m_tiles, cudaStre
 }
 
 int reduce_dw(empose_train* t, TrainPlan& pl, int group, cudaStream_t s);
+// SyncBatchNorm (empose_train_set_sync_batchnorm): all-reduce `count` doubles of statistics over the ranks, on the stream
+int sync_sums(empose_train* t, double* sums, int64_t count, cudaStream_t s) {
+    if (!t->sync_fn) return EMPOSE_OK;
+    const int rc = t->sync_fn(t->sync_user, sums, count, s);
+    if (rc != 0) { set_last_error("the SyncBatchNorm all-reduce callback failed"); return EMPOSE_E_ARG; }
+    return EMPOSE_OK;
+}
+int64_t stat_rows(const empose_train* t, int R) { return t->sync_fn ? (int64_t)R * t->sync_world : (int64_t)R; }
 
 // ---- packed operands and the PackOps that refresh them ---------------------------------------------------------
 void add_op(empose_train* t, const float* src, const float* src2, float* dst, int rows, int cols, int64_t dst_ld, int64_t rs,
@@ -580,7 +591,8 @@ int mlp_forward_segment(empose_train* t, TrainPlan& pl, MlpRun* runs[2], int k, 
             const bool bn = site.gamma >= 0;
             if (bn) {
                 EMPOSE_TRY(launch_col_stats(z, H, R, 1, H, pl.stat_sums, s));
-                EMPOSE_TRY(launch_bn_finalize(pl.stat_sums, R, 1, H, kBnEps, mean, istd, t->bn_buffers + site.rmean,
+                EMPOSE_TRY(sync_sums(t, pl.stat_sums, 2 * (int64_t)H, s));
+                EMPOSE_TRY(launch_bn_finalize(pl.stat_sums, stat_rows(t, R), 1, H, kBnEps, mean, istd, t->bn_buffers + site.rmean,
                                               t->bn_buffers + site.rvar, kBnMomentum, s));
                 t->launches += 2;
             }
@@ -616,7 +628,11 @@ int mlp_backward(empose_train* t, TrainPlan& pl, MlpRun& r, bool transpose_x, cu
         const float* alpha = t->params + site.alpha;
         EMPOSE_TRY(launch_bn_bwd_reduce(r.da, H, r.z[l], H, R, S, H, r.mean[l], r.invstd[l], gamma, beta, alpha, pl.stat_sums, s));
         EMPOSE_TRY(launch_bn_param_grads(pl.stat_sums, S, H, bn ? G + site.gamma : nullptr, bn ? G + site.beta : nullptr, G + site.alpha, s));
-        EMPOSE_TRY(launch_bn_bwd_apply(r.da, H, r.z[l], H, R, S, H, r.mean[l], r.invstd[l], gamma, beta, alpha, pl.stat_sums, rnd, r.dz, H, s));
+        // SyncBatchNorm: the parameter gradients above come from the LOCAL sums (the flat gradient is averaged over the ranks
+        // afterwards, as DDP does for torch.nn.SyncBatchNorm); dz needs the means of dy and dy * xhat over the GLOBAL batch
+        if (bn) EMPOSE_TRY(sync_sums(t, pl.stat_sums, 3 * (int64_t)S * H, s));
+        EMPOSE_TRY(launch_bn_bwd_apply(r.da, H, r.z[l], H, R, S, H, r.mean[l], r.invstd[l], gamma, beta, alpha, pl.stat_sums,
+                                       bn ? stat_rows(t, R) : R, rnd, r.dz, H, s));
         // A bias in front of a BatchNorm has an analytically zero gradient (the batch mean removes it; the reference holds
         // ~1e-8 of rounding noise there): nothing is added.  Without BatchNorm it is the column sum of dz.
         if (!bn) EMPOSE_TRY(launch_col_sum(r.dz, H, M, H, pl.col_scratch, G + site.b, nullptr, s));
@@ -966,6 +982,15 @@ int empose_train_loss_values(empose_train* t, float* loss_vals) {
 }
 
 int64_t empose_train_last_launch_count(const empose_train* t) { return t ? t->launches : 0; }
+
+int empose_train_set_sync_batchnorm(empose_train* t, empose_allreduce_fn fn, void* user, int32_t world_size) {
+    if (!t) { set_last_error("null context"); return EMPOSE_E_ARG; }
+    if (fn && world_size < 1) { set_last_error("world_size must be >= 1"); return EMPOSE_E_ARG; }
+    t->sync_fn = fn;
+    t->sync_user = user;
+    t->sync_world = fn ? world_size : 1;
+    return EMPOSE_OK;
+}
 
 #pragma GCC visibility pop
 }  // extern "C"

@@ -52,18 +52,19 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
     }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int R, int S, int n, float eps, float* __restrict__ mean,
+// `count` = rows behind every sum: R, or the rows of ALL ranks when the sums were all-reduced (SyncBatchNorm)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int S, int n, float eps, float* __restrict__ mean,
                                    float* __restrict__ invstd, float* running_mean, float* running_var, float momentum) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S * n) return;
     const int seg = i / n, c = i % n;
-    const double m = sums[((int64_t)seg * 2) * n + c] / R;
-    double var = sums[((int64_t)seg * 2 + 1) * n + c] / R - m * m;
+    const double m = sums[((int64_t)seg * 2) * n + c] / count;
+    double var = sums[((int64_t)seg * 2 + 1) * n + c] / count - m * m;
     if (var < 0.0) var = 0.0;
     mean[i] = (float)m;
     invstd[i] = (float)(1.0 / sqrt(var + (double)eps));
     if (running_mean) {      // torch.nn.BatchNorm1d: running_var takes the unbiased estimate
-        const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
         running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
         running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
     }
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            int64_t z_ld, int R, int n, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ alpha,
-                                                           const double* __restrict__ sums, int round_out,
+                                                           const double* __restrict__ sums, double count, int round_out,
                                                            float* __restrict__ dz, int64_t dz_ld) {
     extern __shared__ float cst[];              // [6][n]: mean, invstd, gamma, beta, m1, m2
     const int seg = blockIdx.y;
@@ -173,8 +174,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     if (gamma)
         for (int c = threadIdx.x; c < n; c += blockDim.x) {
             c_mu[c] = mean[seg * n + c]; c_is[c] = invstd[seg * n + c]; c_g[c] = gamma[c]; c_b[c] = beta[c];
-            c_m1[c] = (float)(sums[((int64_t)seg * 3 + 0) * n + c] / R);
-            c_m2[c] = (float)(sums[((int64_t)seg * 3 + 1) * n + c] / R);
+            c_m1[c] = (float)(sums[((int64_t)seg * 3 + 0) * n + c] / count);
+            c_m2[c] = (float)(sums[((int64_t)seg * 3 + 1) * n + c] / count);
         }
     __syncthreads();
     const float al = alpha[0];
@@ -527,9 +528,9 @@ int launch_col_stats(const float* z, int64_t ld, int R, int S, int n, double* su
     return EMPOSE_OK;
 }
 
-int launch_bn_finalize(const double* sums, int R, int S, int n, float eps, float* mean, float* invstd, float* running_mean,
+int launch_bn_finalize(const double* sums, int64_t count, int S, int n, float eps, float* mean, float* invstd, float* running_mean,
                        float* running_var, float momentum, cudaStream_t s) {
-    bn_finalize_kernel<<<blocks_for((int64_t)S * n, 256), 256, 0, s>>>(sums, R, S, n, eps, mean, invstd, running_mean, running_var,
+    bn_finalize_kernel<<<blocks_for((int64_t)S * n, 256), 256, 0, s>>>(sums, (double)count, S, n, eps, mean, invstd, running_mean, running_var,
                                                                       momentum);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
@@ -561,9 +562,9 @@ int launch_bn_bwd_reduce(const float* da, int64_t da_ld, const float* z, int64_t
 
 int launch_bn_bwd_apply(const float* da, int64_t da_ld, const float* z, int64_t z_ld, int R, int S, int n, const float* mean,
                         const float* invstd, const float* gamma, const float* beta, const float* alpha, const double* sums,
-                        int round_out, float* dz, int64_t dz_ld, cudaStream_t s) {
+                        int64_t count, int round_out, float* dz, int64_t dz_ld, cudaStream_t s) {
     bn_bwd_apply_kernel<<<dim3(blocks_for(R, kApplyRows), S), 256, (size_t)6 * n * sizeof(float), s>>>(
-        da, da_ld, z, z_ld, R, n, mean, invstd, gamma, beta, alpha, sums, round_out, dz, dz_ld);
+        da, da_ld, z, z_ld, R, n, mean, invstd, gamma, beta, alpha, sums, (double)count, round_out, dz, dz_ld);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

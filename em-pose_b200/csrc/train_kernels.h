@@ -31,7 +31,8 @@ int launch_pack(const PackOp* d_ops, int n_ops, int max_elems, cudaStream_t s);
 int launch_col_stats(const float* z, int64_t ld, int R, int S, int n, double* sums, cudaStream_t s);
 // mean / invstd [S][n] from the sums; if running_mean != null (S must be 1) update the running statistics with
 // momentum (torch semantics: unbiased variance into running_var).
-int launch_bn_finalize(const double* sums, int R, int S, int n, float eps, float* mean, float* invstd, float* running_mean,
+// `count`: rows behind every sum (R; the rows of all ranks when the sums were all-reduced for SyncBatchNorm).
+int launch_bn_finalize(const double* sums, int64_t count, int S, int n, float eps, float* mean, float* invstd, float* running_mean,
                        float* running_var, float momentum, cudaStream_t s);
 // a = prelu(gamma * (z - mean) * invstd + beta); gamma == null -> no BatchNorm (a = prelu(z)).
 int launch_bn_apply(const float* z, int64_t ld, int R, int S, int n, const float* mean, const float* invstd,
@@ -42,10 +43,10 @@ int launch_bn_apply(const float* z, int64_t ld, int R, int S, int n, const float
 int launch_bn_bwd_reduce(const float* da, int64_t da_ld, const float* z, int64_t z_ld, int R, int S, int n, const float* mean,
                          const float* invstd, const float* gamma, const float* beta, const float* alpha, double* sums,
                          cudaStream_t s);
-// backward, pass 2: dz = gamma * invstd * (dy - s1/R - xhat * s2/R)   (no BatchNorm: dz = dy)
+// backward, pass 2: dz = gamma * invstd * (dy - s1/count - xhat * s2/count)   (no BatchNorm: dz = dy)
 int launch_bn_bwd_apply(const float* da, int64_t da_ld, const float* z, int64_t z_ld, int R, int S, int n, const float* mean,
                         const float* invstd, const float* gamma, const float* beta, const float* alpha, const double* sums,
-                        int round_out, float* dz, int64_t dz_ld, cudaStream_t s);
+                        int64_t count, int round_out, float* dz, int64_t dz_ld, cudaStream_t s);
 // parameter gradients of one BN + PReLU site from the pass-1 sums: g_gamma[c] += sum_s s2, g_beta[c] += sum_s s1,
 // g_alpha += sum_{s,c} s3.  g_gamma / g_beta may be null (no BatchNorm).
 int launch_bn_param_grads(const double* sums, int S, int n, float* g_gamma, float* g_beta, float* g_alpha, cudaStream_t s);

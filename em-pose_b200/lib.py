@@ -25,8 +25,19 @@ EXPORTED_SYMBOLS = ('empose_abi_version', 'empose_last_error', 'empose_set_optio
                     'empose_gemm_selftest', 'empose_gemm_bench', 'empose_smpl_create', 'empose_smpl_destroy',
                     'empose_smpl_forward', 'empose_train_layout', 'empose_train_sizes', 'empose_train_create',
                     'empose_train_destroy', 'empose_train_forward', 'empose_train_backward', 'empose_train_loss_values',
-                    'empose_train_last_launch_count', 'empose_rnn_create', 'empose_rnn_destroy', 'empose_rnn_forward',
+                    'empose_train_last_launch_count', 'empose_train_set_sync_batchnorm', 'empose_rnn_create', 'empose_rnn_destroy', 'empose_rnn_forward',
                     'empose_rnn_last_launch_count', 'empose_sensors_create', 'empose_metrics_compute', 'empose_metrics_joints')
+
+
+#: empose_allreduce_fn of include/empose_b200.h: int fn(void* user, double* device_buf, int64_t count, void* stream)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
+
+
+class _DeviceDoubles(object):
+    """A device buffer of the library seen through ``__cuda_array_interface__`` (zero-copy ``torch.as_tensor``)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {'shape': (int(count),), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
 
 
 class EmposeError(RuntimeError):
@@ -119,6 +130,8 @@ def load():
     lib.empose_train_layout.argtypes = [ctypes.POINTER(IefConfig), i32, ctypes.c_char_p, i32, ctypes.POINTER(i32), i64p, i64p]
     lib.empose_train_sizes.restype = ctypes.c_int
     lib.empose_train_sizes.argtypes = [ctypes.POINTER(IefConfig), i64p, i64p]
+    lib.empose_train_set_sync_batchnorm.restype = ctypes.c_int
+    lib.empose_train_set_sync_batchnorm.argtypes = [vp, ALLREDUCE_FN, vp, i32]
     lib.empose_train_create.restype = ctypes.c_int
     lib.empose_train_create.argtypes = [ctypes.POINTER(IefConfig), ctypes.POINTER(Tensor), i32, vp, vp, vp, ctypes.POINTER(vp)]
     lib.empose_train_destroy.restype = None
@@ -423,6 +436,33 @@ class TrainContext(object):
     @property
     def last_launch_count(self):
         return int(load().empose_train_last_launch_count(self._handle))
+
+    def set_sync_batchnorm(self, enabled=True, group=None):
+        """SyncBatchNorm over ``torch.distributed`` (``empose_train_set_sync_batchnorm``): the library hands every
+        BatchNorm's batch statistics to ``dist.all_reduce`` between its own kernels, on the current stream, so means,
+        variances and running statistics are those of the global batch (every rank must run the same number of rows)."""
+        import torch
+        import torch.distributed as dist
+        if not enabled:
+            _check(load().empose_train_set_sync_batchnorm(self._handle, ALLREDUCE_FN(0), None, 1))
+            self._sync_cb = None
+            return
+        if not (dist.is_available() and dist.is_initialized()):
+            raise EmposeError('SyncBatchNorm needs an initialised torch.distributed process group')
+        device = torch.device('cuda', self.device_index)
+        self.sync_calls = 0
+
+        def allreduce(user, buf, count, stream):
+            try:
+                t = torch.as_tensor(_DeviceDoubles(buf, count), device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)      # ordered on the current stream, like the kernels around it
+                self.sync_calls += 1
+                return 0
+            except Exception:                                              # never let an exception cross the C boundary
+                return 1
+
+        self._sync_cb = ALLREDUCE_FN(allreduce)                             # keep the trampoline alive
+        _check(load().empose_train_set_sync_batchnorm(self._handle, self._sync_cb, None, dist.get_world_size(group)))
 
     def forward(self, marker_pos, marker_oris, offset_r, offset_t, seq_lengths, marker_masks=None, want_history=True):
         """Train-mode forward pass; same tensors in / out as ``IefContext.forward`` (no LSTM state carry)."""

@@ -291,6 +291,13 @@ class IterativeErrorFeedback(nn.Module):
     def flat_parameters(self):
         return None if self._flat is None else self._flat['params']
 
+    def sync_batchnorm(self, enabled=True, group=None, device=None):
+        """Data-parallel training with the statistics of the GLOBAL batch in every BatchNorm1d (``layers.py:26,57``), i.e.
+        what ``torch.nn.SyncBatchNorm.convert_sync_batchnorm`` + DDP would give the reference: N ranks on B / N windows
+        each then take the step one device takes on B windows.  Every rank must run the same number of rows per step."""
+        dev = device if device is not None else next(self.parameters()).device
+        self.trainer(dev).set_sync_batchnorm(enabled, group)
+
     def allreduce_gradients(self, average=True):
         """Data-parallel training: ONE all-reduce over the flat gradient vector.  A no-op when
         ``overlap_gradient_allreduce`` already reduced this step's gradients inside ``backward``."""
@@ -331,12 +338,22 @@ class IterativeErrorFeedback(nn.Module):
         """``optimizer.zero_grad()`` sets ``.grad`` to None by default: re-attach (zeroed) views of the flat vector."""
         items = dict(self.named_parameters())
         grads = self._flat['grads']
+        todo = []
+        n_params = 0
         for name, kind, off, numel in self._flat['entries']:
             if kind != 0:
                 continue
+            n_params += 1
             p = items[name]
             view = grads[off:off + numel].view(p.shape)
             if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                todo.append((p, view))
+        if todo and len(todo) == n_params:
+            grads.zero_()                    # the usual case (zero_grad() dropped every .grad): ONE fill instead of one per tensor
+            for p, view in todo:
+                p.grad = view
+        else:
+            for p, view in todo:
                 view.zero_()
                 p.grad = view
 

@@ -265,6 +265,18 @@ int empose_train_forward(empose_train* ctx, const float* marker_pos, const float
 int empose_train_backward(empose_train* ctx, const float* poses_gt, const float* shapes_gt, const float* joints_gt,
                           const empose_loss_weights* weights, float* loss_vals, void* dense_ready_event, void* stream);
 int empose_train_loss_values(empose_train* ctx, float* loss_vals);
+
+/* SyncBatchNorm for data-parallel training (with per-rank statistics -- the DDP default, and what this library does
+ * unless told otherwise -- a run on N ranks is not the run of one device on the global batch; the BatchNorm sites are
+ * empose/nn/layers.py:26,57).  `fn` must all-reduce (sum) `count` doubles at the DEVICE pointer `buf` over all ranks,
+ * ordered on `stream` (e.g. an NCCL call enqueued on it), and return 0.  The library calls it once per BatchNorm evaluation
+ * in the forward pass (sum and sum of squares per unit) and once per BatchNorm site in the backward pass (sums of dy and
+ * dy * xhat), between its own kernels; means, variances and the running statistics are then those of the global batch,
+ * exactly as torch.nn.SyncBatchNorm under DDP: parameter gradients come from the local sums and are averaged with the
+ * flat gradient afterwards.  Every rank must run the same number of rows per step; `world_size` = number of ranks.
+ * fn = NULL restores per-rank statistics. */
+typedef int (*empose_allreduce_fn)(void* user, double* buf, int64_t count, void* stream);
+int empose_train_set_sync_batchnorm(empose_train* ctx, empose_allreduce_fn fn, void* user, int32_t world_size);
 int64_t empose_train_last_launch_count(const empose_train* ctx);
 
 /* ---- (Bi)RNN baseline (BASELINE config 4) ------------------------------------------------------- */
