@@ -37,6 +37,7 @@ struct GemmJob {
     int32_t out_scratch;     // 1: the output is CTA-local scratch (tcgen05 executor only)
     int32_t c_map1;          // 1 + tensor-map slot of `c_state` with a [32 rows x 32 fp32] box (tcgen05 executor, fp16 LSTM jobs: the cell-state
                              // block of an epilogue warp travels by TMA), 0: none
+    int32_t out2_map1;       // the same for fp32 `out2` (boxes of [32 rows x 32 fp32]; fp32 plain contractions), 0: none
     int32_t out_map1;        // 1 + tensor-map slot of `out` with a [32 rows x 64 fp16] box (tcgen05 executor: the fp16 linear epilogue
                              // leaves through TMA stores), 0: none -- the epilogue stores from registers
     // ---- W operand: packed [n_total][w_ld], K-major, segment s starts at column w_koff[s] ----

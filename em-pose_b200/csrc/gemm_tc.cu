@@ -382,6 +382,17 @@ __device__ __forceinline__ void tmem_load_64cols(uint32_t taddr, float (&v)[64])
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_load_32cols_nowait(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr));
+}
 // the same read without the wait: the bias is fetched from shared memory while the accumulator is on its way
 __device__ __forceinline__ void tmem_load_64cols_nowait(uint32_t taddr, float (&v)[64]) {
     asm volatile(
@@ -804,6 +815,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 }
                 // fp16 linear jobs: all fields the chunk loop needs, once per job
                 const LinearHalfView lv = linear_half_view(job, row0, lane);
+                const bool f32_tma = job.epi == EPI_LINEAR && !job.out_half && (job.out_map1 > 0 || job.out2_map1 > 0);
+                const float f32_scale = job.out_scale != 0.0f ? job.out_scale : 1.0f;
                 if (et == 0) trace_stamp(trace, 2, seq, 0);
                 if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 else mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
@@ -921,6 +934,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         generic_stores = true;
                         c0 += 32;
                         continue;
+                    }
+                    if (f32_tma && !(debug_mode & 2048)) {
+                        // fp32 outputs of a plain contraction (the blend GEMMs): the [32 rows x 32 columns] block goes through the
+                        // swizzled staging tile and ONE TMA store, which also clips rows and columns beyond the valid ones
+                        const int n0 = job.n_begin + c0;
+                        const bool second = n0 >= job.split;
+                        const int map1 = second ? job.out2_map1 : job.out_map1;
+                        if (map1 > 0 && (second || n0 + 32 <= job.split || job.split >= job.n_valid)) {
+                            float v[32], bb[32];
+                            tmem_load_32cols_nowait(taddr + (uint32_t)c0, v);
+                            bias_from_smem<32>(bias_sa, c0, bb);
+                            tmem_load_wait();
+                            if (!(debug_mode & 4)) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    v[i] = fmaf(v[i], f32_scale, bb[i]);
+                                    if (job.round_out) v[i] = round_tf32(v[i]);
+                                }
+                                const uint32_t tile = smem_addr_of(my_stage);
+                                release_tile();
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    sts128f(tile + lane * 128 + ((q ^ (lane & 7)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                                fence_async_shared();
+                                __syncwarp();
+                                if (lane == 0 && !(debug_mode & 16)) {
+                                    tma_store_2d(&maps[map1 - 1], tile, second ? n0 - job.split : job.out_col0 + n0, row0);
+                                    bulk_commit();
+                                }
+                                tma_pending = true;
+                            }
+                            continue;
+                        }
                     }
                     release_tile();
                     float v[32];

@@ -264,6 +264,23 @@ struct JobBook {        // jobs + tensor maps of one plan
     // 16-byte aligned rows and column origin; rows >= m_rows are clipped by the map
     int attach_out_map(GemmJob& j) {
         j.out_map1 = 0;
+        j.out2_map1 = 0;
+        if (use_tc && j.epi == EPI_LINEAR && !j.out_half && !j.res && !j.has_act && !j.mask_rows && j.out) {
+            // fp32 outputs of a plain contraction (the blend GEMMs): [32 rows x 32 columns] boxes; columns beyond the valid
+            // ones are clipped by the map, so its extent is exactly what the job may write
+            const int n_out = std::min(j.n_valid, j.split);
+            if (!(reinterpret_cast<uintptr_t>(j.out) & 15) && !((j.out_stride * 4) & 15) && !(j.out_col0 & 3) && !(j.n_begin & 31) && n_out > 0) {
+                int idx = -1;
+                EMPOSE_TRY(get_map(j.out, j.out_stride, j.out_col0 + n_out, j.m_rows, 32, 0, &idx));
+                j.out_map1 = idx + 1;
+            }
+            if (j.out2 && j.n_valid > j.split && !(reinterpret_cast<uintptr_t>(j.out2) & 15) && !((j.out2_stride * 4) & 15) && !(j.split & 31)) {
+                int idx = -1;
+                EMPOSE_TRY(get_map(j.out2, j.out2_stride, j.n_valid - j.split, j.m_rows, 32, 0, &idx));
+                j.out2_map1 = idx + 1;
+            }
+            return EMPOSE_OK;
+        }
         if (!use_tc || j.epi != EPI_LINEAR || !j.out_half || j.res || !j.out) return EMPOSE_OK;
         if ((reinterpret_cast<uintptr_t>(j.out) & 15) || ((j.out_stride * 2) & 15) || (j.out_col0 & 7) || (j.n_begin & 7)) return EMPOSE_OK;
         int idx = -1;
