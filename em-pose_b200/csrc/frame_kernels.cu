@@ -78,6 +78,59 @@ __global__ void __launch_bounds__(256) prepare_kernel(PrepareParams p) {
     }
 }
 
+// The same for fp16 operand buffers, kPrepRows rows per CTA: inputs are read as flat contiguous blocks, permuted in shared
+// memory and written out as whole 16-byte vectors (`meas` rows and the input columns of `xin` / `xiter` rows), instead of
+// one scattered 2-byte store per element (105 us for 131072 rows, three times what its bytes need).
+constexpr int kPrepRows = 16;
+__global__ void __launch_bounds__(256) prepare_rows_kernel(PrepareParams p) {
+    __shared__ __align__(16) float sm_meas[kPrepRows * 144];
+    __shared__ __align__(16) __half sm_x[kPrepRows * 144];
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * kPrepRows;
+    const int nr = (int)min((int64_t)kPrepRows, (int64_t)p.R - row0);
+    const int n_in = p.in_size;
+    for (int i = tid; i < nr * 36; i += 256) {
+        const int r = i / 36, c = i - r * 36;
+        const float v = __ldg(p.marker_pos + row0 * 36 + i);
+        sm_meas[r * 144 + (c / 3) * 12 + c % 3] = v;
+        const int slot = p.slot_of_sensor[c / 3];
+        if (p.use_pos && slot >= 0) sm_x[r * n_in + slot * 3 + c % 3] = __float2half_rn(v);
+    }
+    for (int i = tid; i < nr * 108; i += 256) {
+        const int r = i / 108, e = i - r * 108;
+        const float v = __ldg(p.marker_oris + row0 * 108 + i);
+        sm_meas[r * 144 + (e / 9) * 12 + 3 + e % 9] = v;
+        const int slot = p.slot_of_sensor[e / 9];
+        if (p.use_ori && slot >= 0) sm_x[r * n_in + p.n_pos + slot * 9 + e % 9] = __float2half_rn(v);
+    }
+    if (tid < nr) {
+        const int64_t row = row0 + tid;
+        const int b = (int)(row / p.F), f = (int)(row % p.F);
+        const int len = p.seq_len[b];
+        float w = (f < len) ? (float)p.F / (float)len : 0.0f;
+        if (p.masks) {
+            const float* mk = p.masks + row * kSensors;
+            bool all_present = true;
+            for (int s = 0; s < kSensors; ++s) all_present = all_present && (mk[s] != 0.0f);
+            if (!all_present) w = 0.0f;
+        }
+        p.coef[row] = w;
+    }
+    __syncthreads();
+    {
+        float4* dst = reinterpret_cast<float4*>(p.meas + row0 * 144);
+        const float4* src = reinterpret_cast<const float4*>(sm_meas);
+        for (int i = tid; i < nr * 36; i += 256) dst[i] = src[i];
+    }
+    const int vec = n_in >> 3;                       // 16-byte vectors per row (launch_prepare checks n_in % 8 == 0 and the pitches)
+    for (int i = tid; i < nr * vec; i += 256) {
+        const int r = i / vec, q = i - r * vec;
+        const uint4 v = reinterpret_cast<const uint4*>(sm_x + r * n_in)[q];
+        if (p.xin) reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.xin) + (row0 + r) * p.in_stride)[q] = v;
+        if (p.xiter) reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.xiter) + (row0 + r) * p.iter_stride)[q] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // One CTA per window.  Frames are processed in groups of kUpdateGroup: theta of the group is kept in shared memory for
 // the pose features, which are assembled in a shared-memory tile and written out as one contiguous, 16-byte-vectorised
@@ -90,7 +143,7 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) 
     __shared__ float mean_db[kBetas];
     __shared__ float th[kUpdateGroup][kPoseDim];
     __shared__ float be[kUpdateGroup][kBetas];
-    __shared__ __align__(16) float tile[kUpdateGroup * 2 * kPoseFeatPad];
+    extern __shared__ __align__(16) float tile[];          // kUpdateGroup feature rows in the operand mode's width (launch_update)
     const int b = blockIdx.x;
     const int64_t row0 = (int64_t)b * p.F;
     const int tid = threadIdx.x;
@@ -110,7 +163,8 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(UpdateParams p) 
         __syncthreads();
     }
     // pad columns of the pose-feature rows (189..191 of each half) stay zero
-    for (int i = tid; i < kUpdateGroup * 2 * kPoseFeatPad; i += kUpdateThreads) tile[i] = 0.0f;
+    const int tile_words = kUpdateGroup * (p.pf_split == OPERAND_F16 ? p.pf_stride / 2 : p.pf_stride);
+    for (int i = tid; i < tile_words; i += kUpdateThreads) tile[i] = 0.0f;
     for (int f0 = 0; f0 < p.F; f0 += kUpdateGroup) {
         const int nf = min(kUpdateGroup, p.F - f0);
         const int64_t g0 = row0 + f0;
@@ -422,13 +476,25 @@ inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1)
 }  // namespace
 
 int launch_prepare(const PrepareParams& p, cudaStream_t s) {
+    if (p.operand_mode == OPERAND_F16 && p.in_size % 8 == 0 && p.in_size <= 144 && p.in_stride % 8 == 0 && p.iter_stride % 8 == 0) {
+        prepare_rows_kernel<<<blocks_for(p.R, kPrepRows), 256, 0, s>>>(p);
+        EMPOSE_CUDA_TRY(cudaGetLastError());
+        return EMPOSE_OK;
+    }
     prepare_kernel<<<blocks_for((int64_t)p.R * 144, 256), 256, 0, s>>>(p);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }
 
 int launch_update(const UpdateParams& p, cudaStream_t s) {
-    update_kernel<<<p.B, kUpdateThreads, 0, s>>>(p);
+    // the staging tile holds kUpdateGroup feature rows: half the bytes with fp16 operands, so eight CTAs fit an SM instead of six
+    const size_t smem = (size_t)kUpdateGroup * (p.pf_split == OPERAND_F16 ? p.pf_stride / 2 : p.pf_stride) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 40 * 1024 && smem > configured) {
+        EMPOSE_CUDA_TRY(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    update_kernel<<<p.B, kUpdateThreads, smem, s>>>(p);
     EMPOSE_CUDA_TRY(cudaGetLastError());
     return EMPOSE_OK;
 }

@@ -12,6 +12,7 @@
 #   train | synth | metrics | birnn   the other bench workloads
 #   launches[:workload]        ncu launch list (gpu__time_duration) of two bench steps -> <tag>_launches[_workload].csv
 #   prof:<name>:<kernel regex>:<skip>[:workload]   ncu --set full of ONE launch -> <tag>_prof_<name>.ncu-rep
+#   profall                    after `launches`: one ncu --set full capture of every kernel kind of the step (scripts/find_skips.py)
 #   micro:<MxNxK>[,...]        scripts/gemm_microbench.py
 #   sass                       opcode histogram of the tcgen05 executor and the fan kernel from the shipped .so
 tag=${1:-visit}; shift
@@ -49,6 +50,13 @@ for step in "$@"; do
       pname=${arg%%:*}; rest=${arg#*:}; regex=${rest%%:*}; rest=${rest#*:}; skip=${rest%%:*}; wl=""; [ "$rest" != "$skip" ] && wl="--workload ${rest#*:}"
       timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -o gpurun_out/${tag}_prof_$pname -f \
           python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-companions $wl > gpurun_out/${tag}_prof_$pname.log 2>&1; echo "prof $pname rc=$?" ;;
+    profall)
+      # one `ncu --set full` capture per kernel kind of the step, located with the launch list of THIS visit (run `launches` first)
+      python scripts/find_skips.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_skips.txt
+      while read pname regex skip; do
+        timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -o gpurun_out/${tag}_prof_$pname -f \
+            python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-companions > gpurun_out/${tag}_prof_$pname.log 2>&1; echo "prof $pname (skip $skip) rc=$?"
+      done < gpurun_out/${tag}_skips.txt ;;
     micro)
       timeout -s KILL 300 python scripts/gemm_microbench.py $(echo "$arg" | tr ',' ' ') > $log 2>&1; grep -h tflops $log | tr -d '\n'; echo ;;
     sass)
