@@ -89,6 +89,8 @@ class ClockSampler(threading.Thread):
         self.stop_flag = threading.Event()
 
     def run(self):
+        if self._run_nvml():
+            return
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         while not self.stop_flag.is_set():
@@ -101,6 +103,33 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
+
+    def _run_nvml(self):
+        """The same numbers through NVML (what nvidia-smi reads), every 5 ms: the timed region is ~150 ms, one nvidia-smi
+        process per sample would see it once."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.index
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                idx = int(vis.split(',')[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [0x8, 0x40, 0x20, 0x4]          # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        while not self.stop_flag.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = int(reasons_fn(h))
+                self.samples.append([str(sm), str(max_sm)] + ['Active' if r & b else 'Not Active' for b in bits])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
+        return True
 
     def summary(self):
         if not self.samples:
