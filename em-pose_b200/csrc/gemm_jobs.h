@@ -26,6 +26,12 @@ constexpr int kChunkKHalf = 64;   // fp16 elements per K chunk (same 128 bytes)
 enum EpilogueKind : int32_t { EPI_LINEAR = 0, EPI_LSTM = 1 };
 
 struct GemmJob {
+    // ---- what the tcgen05 executor's epilogue needs of the commonest job -- an fp16 linear layer on a full 256-column tile
+    // ---- that leaves through TMA stores -- in ONE 16-byte load (JobBook::add fills it; 0 in `hot_path` = look at the fields) ----
+    int32_t hot_path;        // bits 0-7: 1 = such a job; bit 8: out_scratch; bits 9-10: is_dep
+    int32_t hot_out_col;     // out_col0 + n_begin
+    int32_t hot_out_map;     // out_map1 - 1
+    float hot_alpha;         // PReLU slope (1: no activation)
     // ---- A operand: up to two K segments ----
     const float* a_ptr[2];
     int64_t a_stride[2];     // floats between consecutive rows
@@ -252,6 +258,25 @@ __device__ __forceinline__ void linear_half_pack64(const LinearHalfView& lv, flo
             mul_f32x2(t0, t1, v[2 * i], v[2 * i + 1], alpha);
             const __half2 h = __floats2half2_rn(fminf(v[2 * i], t0), fminf(v[2 * i + 1], t1));
             packed[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+    }
+}
+// The same with the bias read from a shared-memory copy eight values at a time (the tcgen05 executor keeps a second
+// accumulator read in flight meanwhile: 64 live bias registers would spill).  No row masking (fast linear jobs have none).
+__device__ __forceinline__ void linear_half_pack64_smem(float alpha, float (&v)[64], uint32_t bias_sa, int c0, uint32_t (&packed)[32]) {
+    const bool use_max = alpha <= 1.0f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float4 b0 = lds128f(bias_sa + (uint32_t)(c0 + 8 * g) * 4u), b1 = lds128f(bias_sa + (uint32_t)(c0 + 8 * g + 4) * 4u);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float &x0 = v[8 * g + 2 * i], &x1 = v[8 * g + 2 * i + 1];
+            float t0, t1;
+            add_f32x2(x0, x1, bb[2 * i], bb[2 * i + 1]);
+            mul_f32x2(t0, t1, x0, x1, alpha);
+            const __half2 h = use_max ? __floats2half2_rn(fmaxf(x0, t0), fmaxf(x1, t1)) : __floats2half2_rn(fminf(x0, t0), fminf(x1, t1));
+            packed[4 * g + i] = *reinterpret_cast<const uint32_t*>(&h);
         }
     }
 }

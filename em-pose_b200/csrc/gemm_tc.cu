@@ -49,8 +49,10 @@ constexpr int kABytes = kTileM * kChunkK * 4;        // 16 KB
 constexpr int kWBytes = kMaxTileN * kChunkK * 4;     // 32 KB
 constexpr int kStageBytes = kABytes + kWBytes;
 // operand ring: 192 KB with 8 epilogue warps, 160 KB with 12 (their staging tiles need the difference)
-constexpr int kStages = kEpiWarps == 8 ? 4 : 3;      // ring slots of A [128 x 128 B] + W [256 x 128 B] (48 KB)
-constexpr int kStagesPair = kEpiWarps == 8 ? 6 : 5;  // CTA-pair mode: a slot holds half of W (32 KB), so the same memory is a deeper ring
+constexpr int kStages = 3;                           // ring slots of A [128 x 128 B] + W [256 x 128 B] (48 KB)
+constexpr int kStagesPair = 5;                       // CTA-pair mode: a slot holds half of W (32 KB), so the same memory is a deeper ring
+                                                     // (6 -> 4 slots cost the MLP chain nothing and a lone GEMM 4 %: the sixth slot's 32 KB
+                                                     //  are better spent on a second staging tile per epilogue warp)
 constexpr int kOperandBytes = kStagesPair * (kABytes + kWBytes / 2);
 static_assert(kStages * kStageBytes <= kOperandBytes, "both ring layouts share the operand region");
 constexpr int kTmemCols = 512;
@@ -70,7 +72,8 @@ struct __align__(8) Control {
     uint32_t job_done_cnt[4];         // per job (sequence number & 3): epilogue warps that have published their part (cross-CTA jobs)
 };
 
-constexpr int kEpiStageBytes = kEpiWarps * kStageFloats * 4;     // one 4 KB staging tile per epilogue warp (1024-byte aligned: TMA swizzle)
+constexpr int kEpiTiles = 2;                                     // staging tiles per epilogue warp: TMA stores alternate between them
+constexpr int kEpiStageBytes = kEpiWarps * kEpiTiles * kStageFloats * 4;     // 4 KB tiles, 1024-byte aligned (TMA swizzle)
 static_assert(kOperandBytes % 1024 == 0 && (kStageFloats * 4) % 1024 == 0, "staging tiles must keep the 1024-byte alignment of the swizzle pattern");
 constexpr int kBiasBytes = 2 * kMaxTileN * 4;                    // the bias of the current and the next job
 constexpr int kJobSlotBytes = ((int)sizeof(GemmJob) + 15) / 16 * 16;
@@ -234,6 +237,18 @@ __device__ __forceinline__ void wait_counter(const uint32_t* p, uint32_t need) {
     }
 }
 
+// two counters at once: both acquire loads are in flight together (each is an L2 round trip); null pointers are skipped
+__device__ __forceinline__ void wait_counters2(const uint32_t* p0, uint32_t need0, const uint32_t* p1, uint32_t need1, int tile) {
+    uint32_t spins = 0;
+    for (;;) {
+        const uint32_t v0 = p0 ? ld_acquire_gpu(p0 + tile) : need0;
+        const uint32_t v1 = p1 ? ld_acquire_gpu(p1 + tile) : need1;
+        if ((int32_t)(v0 - need0) >= 0 && (int32_t)(v1 - need1) >= 0) return;
+        __nanosleep(40);
+        if (++spins > (1u << 25)) __trap();
+    }
+}
+
 // One lane of a fully active, converged warp.  The TMA and MMA roles run their loops on the WHOLE warp with uniform
 // values and let the elected lane issue: inside an `if (lane == 0)` region the compiler treats every operand as divergent
 // and wraps each UTMALDG / UTCHMMA in ELECT + R2UR shuffles -- ~200 instructions per K chunk for four MMAs, which made the
@@ -269,6 +284,7 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }     // sources may be overwritten
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }     // ... all but the latest store's
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }           // the writes are complete
 __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -586,11 +602,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     if (job.wait_ctr[0] || job.wait_ctr[1]) {
                         // this tile's A rows are produced by other CTAs of THIS launch: wait for their epilogues, then
                         // order the TMA reads (async proxy) after what the acquire made visible
-                        if (m0 < m_tiles * kTileM) {
-#pragma unroll
-                            for (int q = 0; q < 2; ++q)
-                                if (job.wait_ctr[q]) wait_counter(job.wait_ctr[q] + m0 / kTileM, job.wait_need[q] * epoch);
-                        }
+                        if (m0 < m_tiles * kTileM)
+                            wait_counters2(job.wait_ctr[0], job.wait_need[0] * epoch, job.wait_ctr[1], job.wait_need[1] * epoch, m0 / kTileM);
                         asm volatile("fence.proxy.async;" ::: "memory");
                         __syncwarp();
                     }
@@ -764,6 +777,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 pub_pending = 0;
             }
         };
+        // TMA stores of the linear paths alternate between the warp's two staging tiles: a block only has to wait for the store
+        // before the previous one (in practice never), not for the one just issued.  Returns the tile's shared-memory address.
+        uint32_t tile_sel = 0;
+        auto next_store_tile = [&](float* stage0) -> uint32_t {
+            if (lane == 0) {
+                if (pub_pending) { bulk_wait_all0(); ctl->done_seq[ew] = pub_pending; }
+                else if (tma_pending) bulk_wait_read1();
+            }
+            __syncwarp();
+            pub_pending = 0;
+            const uint32_t t = smem_addr_of(stage0) + tile_sel * (uint32_t)(kStageFloats * 4);
+            tile_sel ^= 1u;
+            return t;
+        };
         const int et = (int)threadIdx.x - 4 * 32;
         for (int item = item0; item < n_items; item += item_step) {
             const int m0 = (kCluster == 2 ? 2 * item_unit(item) + (int)crank : item_unit(item)) * kTileM;
@@ -772,32 +799,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 mbar_wait(&ctl->job_full[buf], (seq >> 1) & 1u);
                 const GemmJob& job = job_slot(buf);
                 const uint32_t bias_sa = smem_u32(bias_s + buf * kMaxTileN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kMaxTileN;
+                // The commonest job -- an fp16 linear layer on a full tile, out through TMA stores -- is summarised in the first
+                // 16 bytes of its record: one load instead of ~20 dependent ones and their branches before the accumulator wait
+                // (the timeline showed ~1000 cycles between two jobs of an epilogue warp, which is what bounds the MLP chain).
+                const uint4 hot = lds128(smem_u32(&job));
+                const bool fast_linear = (hot.x & 0xffu) == 1u && kWideChunks && !(debug_mode & (1024 | 2048 | 16384));
                 // activations chained inside this CTA live in CTA-local scratch rows: they are re-read from L2 by the next
                 // layer and overwritten by the next tile before they would be written back to HBM
-                const int row0 = (job.out_scratch ? (int)blockIdx.x * kTileM : m0) + quad * 32;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kMaxTileN;
+                const bool out_scratch = fast_linear ? ((hot.x >> 8) & 1u) != 0u : job.out_scratch != 0;
+                const int row0 = (out_scratch ? (int)blockIdx.x * kTileM : m0) + quad * 32;
                 // column shares in units of 32-column chunks -- of chunk PAIRS for fp16 LSTM jobs, whose cell-state blocks span 64
                 int c_begin, c_end;
-                {
+                bool lstm_pre = false;
+                if (fast_linear) {
+                    c_begin = part * (kMaxTileN / kEpiParts);
+                    c_end = c_begin + kMaxTileN / kEpiParts;
+                } else {
                     const int unit = lstm_half_paired(job) ? 64 : 32;
                     const int units = (job.n_count + unit - 1) / unit;
                     c_begin = (part * units / kEpiParts) * unit;
                     c_end = min(job.n_count, ((part + 1) * units / kEpiParts) * unit);
-                }
-                // fp16 LSTM jobs: the cell state of the first chunk pair is fetched while the MMAs are still running
-                const bool lstm_pre = lstm_half_paired(job) && !(debug_mode & 128);
-                // Wavefront jobs: the recurrent state this epilogue reads (cell state, carried hidden state) is written by
-                // other CTAs of this launch -- wait for them here too (the MMAs cannot start earlier either).
-                if ((job.wait_ctr[0] || job.wait_ctr[1]) && m0 < m_tiles * kTileM) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        if (job.wait_ctr[q]) wait_counter(job.wait_ctr[q] + m0 / kTileM, job.wait_need[q] * epoch);
+                    // fp16 LSTM jobs: the cell state of the first chunk pair is fetched while the MMAs are still running
+                    lstm_pre = lstm_half_paired(job) && !(debug_mode & 128);
+                    // Wavefront jobs: the recurrent state this epilogue reads (cell state, carried hidden state) is written by
+                    // other CTAs of this launch -- wait for them here too (the MMAs cannot start earlier either).  Both
+                    // counters are polled at once (an acquire load is an L2 round trip).
+                    if ((job.wait_ctr[0] || job.wait_ctr[1]) && m0 < m_tiles * kTileM)
+                        wait_counters2(job.wait_ctr[0], job.wait_need[0] * epoch, job.wait_ctr[1], job.wait_need[1] * epoch, m0 / kTileM);
                 }
                 // The fast LSTM epilogue (a full 256-column tile: this warp owns 128 gate columns = 32 hidden units of its 32 rows):
                 // the warp's [32 rows x 32 units] fp32 cell-state block comes by TMA straight into its staging tile (128-byte
                 // swizzle, conflict-free per-row reads) while the MMAs are still running, is updated in place and leaves by TMA.
-                const bool lstm_fast = lstm_pre && job.c_map1 > 0 && c_end - c_begin == 128 && !job.gates_out && !(debug_mode & 4096);
-                float* my_stage = epi_stage + ew * kStageFloats;
+                const bool lstm_fast = lstm_pre && job.c_map1 > 0 && c_end - c_begin == 128 && !job.gates_out && !(debug_mode & 4096);      // (false for fast_linear)
+                float* my_stage = epi_stage + ew * (kEpiTiles * kStageFloats);
                 float4 cpre[4];
                 int lf_seq_len = 0;
                 if (lstm_fast) {
@@ -814,9 +849,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     lstm_half_load_c(job, row0, lane, c_begin, cpre);
                 }
                 // fp16 linear jobs: all fields the chunk loop needs, once per job
-                const LinearHalfView lv = linear_half_view(job, row0, lane);
-                const bool f32_tma = job.epi == EPI_LINEAR && !job.out_half && (job.out_map1 > 0 || job.out2_map1 > 0);
-                const float f32_scale = job.out_scale != 0.0f ? job.out_scale : 1.0f;
+                LinearHalfView lv;
+                bool f32_tma = false;
+                float f32_scale = 1.0f;
+                if (fast_linear) {
+                    lv.out = nullptr; lv.out_stride = 0; lv.bias = nullptr; lv.m_rows = 0;        // (TMA stores clip; the bias is in shared memory)
+                    lv.alpha = __uint_as_float(hot.w); lv.fast_cols = kMaxTileN; lv.zero_row = false;
+                    lv.out_map = (int32_t)hot.z; lv.out_col = (int32_t)hot.y;
+                } else {
+                    lv = linear_half_view(job, row0, lane);
+                    f32_tma = job.epi == EPI_LINEAR && !job.out_half && (job.out_map1 > 0 || job.out2_map1 > 0);
+                    f32_scale = job.out_scale != 0.0f ? job.out_scale : 1.0f;
+                }
                 if (et == 0) trace_stamp(trace, 2, seq, 0);
                 if (kCluster == 2) mbar_wait_guarded(&ctl->tmem_full[buf], (seq >> 1) & 1u);
                 else mbar_wait(&ctl->tmem_full[buf], (seq >> 1) & 1u);
@@ -825,7 +869,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 // (tried and dropped: software-pipelining the accumulator reads -- 16 columns at a time, or the next chunk's read
                 //  issued before the current chunk is staged.  With the read's registers live across the loop ptxas feeds the
                 //  eight bias loads one by one into the additions: 11 % slower on a [131072 x 512] . [512 x 512] layer.)
-                if (lstm_fast) {
+                if (fast_linear && !(debug_mode & (4 | 32768))) {
+                    // Both 64-column reads of this warp's share, software-pipelined: the second one is in flight while the first
+                    // block is turned into fp16 and stored.  Tensor memory delivers 64 B per cycle and SM; with all eight warps
+                    // reading at the same moment (they are released together by tmem_full) and then all computing, the 2048
+                    // cycles of reads and the ~1600 of arithmetic of a tile simply added up (timeline: 3685 cycles of work per job).
+                    float va[64], vb[64];
+                    auto store_block = [&](float (&v)[64], int c0) {
+                        uint32_t pk[32];
+                        linear_half_pack64_smem(lv.alpha, v, bias_sa, c0, pk);
+                        const uint32_t tile = next_store_tile(my_stage);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            sts128(tile + lane * 128 + ((q ^ (lane & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        fence_async_shared();
+                        __syncwarp();
+                        if (lane == 0 && !(debug_mode & 16)) {
+                            if (out_scratch && !(debug_mode & 8192)) tma_store_2d_hint(&maps[lv.out_map], tile, lv.out_col + c0, row0, keep_policy);
+                            else tma_store_2d(&maps[lv.out_map], tile, lv.out_col + c0, row0);
+                            bulk_commit();
+                        }
+                        tma_pending = true;
+                    };
+                    tmem_load_64cols_nowait(taddr + (uint32_t)c_begin, va);
+                    tmem_load_wait();
+                    tmem_load_64cols_nowait(taddr + (uint32_t)(c_begin + 64), vb);
+                    store_block(va, c_begin);
+                    tmem_load_wait();
+                    store_block(vb, c_begin + 64);
+                } else if (lstm_fast) {
                     const int row = row0 + lane, unit0 = lstm_unit_of_packed(job.n_begin + c_begin);
                     const bool in_rows = row < job.m_rows;
                     const bool live = in_rows && job.t < lf_seq_len;
@@ -901,15 +973,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                             if (!(debug_mode & 4)) {
                                 uint32_t pk[32];
                                 linear_half_pack64(lv, v2, bb, pk);
-                                const uint32_t tile = smem_addr_of(my_stage);
-                                release_tile();          // the previous block of this warp has left the tile
+                                const uint32_t tile = next_store_tile(my_stage);
 #pragma unroll
                                 for (int q = 0; q < 8; ++q)
                                     sts128(tile + lane * 128 + ((q ^ (lane & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                                 fence_async_shared();
                                 __syncwarp();
                                 if (lane == 0 && !(debug_mode & 16)) {
-                                    if (job.out_scratch && !(debug_mode & 8192)) tma_store_2d_hint(&maps[lv.out_map], tile, lv.out_col + c0, row0, keep_policy);
+                                    if (out_scratch && !(debug_mode & 8192)) tma_store_2d_hint(&maps[lv.out_map], tile, lv.out_col + c0, row0, keep_policy);
                                     else tma_store_2d(&maps[lv.out_map], tile, lv.out_col + c0, row0);
                                     bulk_commit();
                                 }
@@ -952,8 +1023,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                                     v[i] = fmaf(v[i], f32_scale, bb[i]);
                                     if (job.round_out) v[i] = round_tf32(v[i]);
                                 }
-                                const uint32_t tile = smem_addr_of(my_stage);
-                                release_tile();
+                                const uint32_t tile = next_store_tile(my_stage);
 #pragma unroll
                                 for (int q = 0; q < 8; ++q)
                                     sts128f(tile + lane * 128 + ((q ^ (lane & 7)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
@@ -999,8 +1069,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     else mbar_arrive(&ctl->tmem_empty[buf]);
                 }
                 // ---- publication: only a job some later job waits for hands its stores over ----
-                const int is_dep = job.is_dep;
-                uint32_t* const done_ctr = job.done_ctr;
+                const int is_dep = fast_linear ? (int)((hot.x >> 9) & 3u) : job.is_dep;
+                uint32_t* const done_ctr = fast_linear ? nullptr : job.done_ctr;
                 if (!(debug_mode & 8) && (is_dep || done_ctr)) {
                     // Blocks that left through TMA stores are in the async proxy already: their issuing lane has to see the
                     // writes complete.  Stores from registers (any other path, this job's or an earlier one's: a thread owns

@@ -1066,6 +1066,7 @@ static int gemm_engine_run(int32_t precision, const float* A, int64_t lda, const
         EMPOSE_TRY(book.get_map(W, ldw, K, N, pm.tile_n / 2, hf, &j.w_map2));
         j.n_begin = t * pm.tile_n; j.n_count = pm.tile_n; j.m_rows = M; j.dep = -1; j.bias = bias_padded;
         EMPOSE_TRY(book.attach_out_map(j));
+        j.c_map1 = 0;
         if (range.count == 0) range.begin = (int)book.jobs.size();
         book.jobs.push_back(j);
         ++range.count;

@@ -338,12 +338,29 @@ struct JobBook {        // jobs + tensor maps of one plan
             EMPOSE_TRY(attach_out_map(j));
             EMPOSE_TRY(attach_c_map(j));
             jobs.push_back(j);
+            hot_dirty = true;
             ++range->count;
         }
         return EMPOSE_OK;
     }
 
+    // the epilogue's one-load summary of a job (GemmJob::hot_*); is_dep is only final once every job has been added
+    bool hot_dirty = false;
+    void fill_hot() {
+        for (GemmJob& j : jobs) {
+            const bool plain = j.epi == EPI_LINEAR && j.out_half && !j.res && j.out_map1 > 0 &&
+                               (j.out_scale == 0.0f || j.out_scale == 1.0f) && !j.mask_rows && !j.wait_ctr[0] && !j.wait_ctr[1] &&
+                               !j.done_ctr && j.n_count == kMaxTileN && std::min(j.n_valid, j.split) - j.n_begin >= kMaxTileN;
+            j.hot_path = plain ? (1 | (j.out_scratch ? 1 << 8 : 0) | ((j.is_dep & 3) << 9)) : 0;
+            j.hot_out_col = j.out_col0 + j.n_begin;
+            j.hot_out_map = j.out_map1 - 1;
+            j.hot_alpha = j.has_act ? j.prelu_alpha : 1.0f;
+        }
+        hot_dirty = false;
+    }
+
     int finalize(Arena& arena) {
+        fill_hot();
         EMPOSE_TRY(arena.upload(jobs, &d_jobs));
         if (use_tc) {
             void* p;
