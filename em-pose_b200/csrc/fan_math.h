@@ -383,6 +383,9 @@ EMPOSE_HD void jt_reduce_frames(const FanModel& fm, StateFn state, VarFn var_of,
         const int q0 = fm.jp_ptr[j], n = fm.jp_ptr[j + 1] - q0;
         int idx[4] = {0, 0, 0, 0};                     // the first four partials of the joint stay in registers
         for (int k = 0; k < 4; ++k) if (k < n) idx[k] = fm.jp_idx[q0 + k] * 12 + q4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4          // independent frames: four frames' loads in flight instead of one (the phase is latency bound)
+#endif
         for (int f = 0; f < nf; ++f) {
             const T* part = var_of(f);
             T acc[4] = {T(0), T(0), T(0), T(0)}, v[4];
@@ -484,6 +487,9 @@ EMPOSE_HD void jt_local_frames(const int* parents, StateFn state, VarFn var_of, 
     for (int it = tid; it < kJoints * 3; it += nt) {
         const int j = it / 3, a = it - j * 3;
         const int p = j > 0 ? parents[j] : 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
         for (int f = 0; f < nf; ++f) {
             const JointState<T>& st = state(f);
             T* var = var_of(f);

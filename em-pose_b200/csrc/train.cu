@@ -146,6 +146,7 @@ struct MlpRun {
     std::vector<float*> z, a, dzT, aT;                             // hidden layers 0 .. n_hidden-1
     std::vector<float*> mean, invstd;                              // [S][H] per hidden layer
     float *da = nullptr, *dz = nullptr, *DT = nullptr;
+    float* dskip = nullptr;                                        // m_skip_connections: the gradient that bypasses a LinearLayers block
     const float* XT = nullptr;                                     // [x_k rows padded][ldT], shared by the two nets of a pair
     std::vector<std::vector<JobRange>> fwd;                        // [segment][layer]
     std::vector<JobRange> bwd_dx;                                  // [layer] (layer >= 1): da = dz_l W_l
@@ -399,6 +400,8 @@ int build_mlp_run(empose_train* t, TrainPlan& pl, const TrainMlp& net, int S, co
     }
     EMPOSE_TRY(A.alloc_n((size_t)M * H, &r.da));
     EMPOSE_TRY(A.alloc_n((size_t)M * H, &r.dz));
+    const bool skip = t->cfg.skip_connections != 0;
+    if (skip) EMPOSE_TRY(A.alloc_n((size_t)M * H, &r.dskip));
     const int n_out = net.lay->layers[nl - 1].n_out;
     EMPOSE_TRY(A.alloc_n((size_t)kTileM * ldT, &r.DT, true));
     // forward jobs: one range per (segment, layer)
@@ -414,6 +417,9 @@ int build_mlp_run(empose_train* t, TrainPlan& pl, const TrainMlp& net, int S, co
     for (int l = 1; l < nl; ++l) {
         ASrc a0 = l == nl - 1 ? ASrc{D, d_ld, n_out, M} : ASrc{r.dz, H, H, M};
         GemmJob proto = plain_proto(r.da, H, H, false);
+        // LinearLayers skip (layers.py:35-43): blocks are the hidden layers (1, 2), (3, 4), ...; the gradient w.r.t. a block's
+        // input is what comes back through its first layer PLUS what bypassed the block (saved in dskip at the block's end)
+        if (skip && l >= 1 && l <= nl - 3 && (l % 2) == 1) { proto.res = r.dskip; proto.res_stride = H; }
         EMPOSE_TRY(pl.book.add(net.bw[l], a0, ASrc{}, proto, (int)M, -1, &r.bwd_dx[l]));
     }
     // dW jobs
@@ -600,6 +606,10 @@ int mlp_forward_segment(empose_train* t, TrainPlan& pl, MlpRun* runs[2], int k, 
                                        bn ? t->params + site.beta : nullptr, t->params + site.alpha, rnd,
                                        r.a[l] + (size_t)k * R * H, H, s));
             ++t->launches;
+            if (t->cfg.skip_connections && l >= 2 && (l % 2) == 0) {        // end of a LinearLayers block: + the block's input
+                EMPOSE_TRY(launch_add_inplace(r.a[l] + (size_t)k * R * H, r.a[l - 2] + (size_t)k * R * H, (int64_t)R * H, rnd, s));
+                ++t->launches;
+            }
         }
     }
     return EMPOSE_OK;
@@ -626,6 +636,8 @@ int mlp_backward(empose_train* t, TrainPlan& pl, MlpRun& r, bool transpose_x, cu
         const float* gamma = bn ? t->params + site.gamma : nullptr;
         const float* beta = bn ? t->params + site.beta : nullptr;
         const float* alpha = t->params + site.alpha;
+        if (t->cfg.skip_connections && l >= 2 && (l % 2) == 0)             // da = dL/d(block output): it also reaches the block's input directly
+            EMPOSE_CUDA_TRY(cudaMemcpyAsync(r.dskip, r.da, (size_t)M * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
         EMPOSE_TRY(launch_bn_bwd_reduce(r.da, H, r.z[l], H, R, S, H, r.mean[l], r.invstd[l], gamma, beta, alpha, pl.stat_sums, s));
         EMPOSE_TRY(launch_bn_param_grads(pl.stat_sums, S, H, bn ? G + site.gamma : nullptr, bn ? G + site.beta : nullptr, G + site.alpha, s));
         // SyncBatchNorm: the parameter gradients above come from the LOCAL sums (the flat gradient is averaged over the ranks
@@ -924,7 +936,6 @@ int empose_train_create(const empose_ief_config* cfg, const empose_tensor* tenso
                         float* grads, float* bn_buffers, empose_train** out) {
     if (!cfg || !tensors || !params || !grads || !out) { set_last_error("null argument"); return EMPOSE_E_ARG; }
     *out = nullptr;
-    if (cfg->skip_connections) { set_last_error("training with m_skip_connections is not implemented"); return EMPOSE_E_ARG; }
     if (cfg->precision == EMPOSE_PRECISION_FP16) {
         set_last_error("training runs in EMPOSE_PRECISION_TF32 or EMPOSE_PRECISION_FP32 (fp16 operands are an inference mode)");
         return EMPOSE_E_ARG;

@@ -620,6 +620,21 @@ int launch_losses(const LossParams& p, cudaStream_t s) {
     return EMPOSE_OK;
 }
 
+__global__ void __launch_bounds__(256) add_inplace_kernel(float4* __restrict__ dst, const float4* __restrict__ src, int64_t n4, int round_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = dst[i];
+    const float4 b = __ldg(src + i);
+    a.x = maybe_round(a.x + b.x, round_out); a.y = maybe_round(a.y + b.y, round_out);
+    a.z = maybe_round(a.z + b.z, round_out); a.w = maybe_round(a.w + b.w, round_out);
+    dst[i] = a;
+}
+int launch_add_inplace(float* dst, const float* src, int64_t n, int round_out, cudaStream_t s) {
+    add_inplace_kernel<<<blocks_for(n / 4, 256), 256, 0, s>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n / 4, round_out);
+    EMPOSE_CUDA_TRY(cudaGetLastError());
+    return EMPOSE_OK;
+}
+
 int launch_round_inplace(float* x, int64_t rows, int n, int64_t ld, cudaStream_t s) {
     round_kernel<<<blocks_for(rows * n, 256), 256, 0, s>>>(x, rows, n, ld);
     EMPOSE_CUDA_TRY(cudaGetLastError());

@@ -116,5 +116,7 @@ int launch_losses(const LossParams& p, cudaStream_t s);
 
 // x[r][c] = round_tf32(x[r][c]) for c < n (row pitch ld)
 int launch_round_inplace(float* x, int64_t rows, int n, int64_t ld, cudaStream_t s);
+// dst[i] += src[i] for n floats (n % 4 == 0, 16-byte aligned), optionally rounded to tf32 (a LinearLayers skip, layers.py:35-43)
+int launch_add_inplace(float* dst, const float* src, int64_t n, int round_out, cudaStream_t s);
 
 }  // namespace empose

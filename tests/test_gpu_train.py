@@ -146,6 +146,48 @@ def test_training_step_matches_oracle_and_reference(dev, smpl_npz, oracle_smpl, 
     assert abs(float(total) - loss_vals['total_loss']) < 1e-6
 
 
+@pytest.mark.parametrize('name', ['train_lgd_mlp12_n2', 'train_lgd_rnn12_n4'])
+def test_training_step_with_skip_connections_matches_oracle(dev, smpl_npz, oracle_smpl, topology, name):
+    """``m_skip_connections`` (LinearLayers.forward adds a block's input to its output, layers.py:35-43) in the training
+    step: the exact-arithmetic executor against the float64 oracle on the inputs of two golden cases (the reference
+    fixtures themselves were recorded without skip connections)."""
+    gold = util.load_golden(name)
+    flags = util.TRAIN_CASES[name]
+    cfg = oracle_ief.IefConfig(n_markers=flags['n_markers'], num_iterations=flags['num_iterations'], rnn_init=flags['rnn_init'],
+                               skip_connections=True)
+    sd = util.torch_state_dict(synthetic.synth_state_dict(seed=0, n_markers=flags['n_markers'], rnn_init=flags['rnn_init']),
+                               torch.float64)
+    want = oracle_train.ief_train_step(cfg, sd, oracle_smpl, topology, pose_weight=flags['pose_weight'], shape_weight=1.0,
+                                       r_weight=0.01, fk_weight=flags['fk_weight'], **util.train_inputs(gold, torch.float64))
+    precision = native.PRECISION_FP32
+    net = util.build_module(smpl_npz, n_markers=flags['n_markers'], num_iterations=flags['num_iterations'], rnn_init=flags['rnn_init'],
+                            precision=precision, device=dev, m_fk_loss=flags['fk_weight'], m_pose_loss_weight=flags['pose_weight'],
+                            m_skip_connections=True).train()
+    batch = TrainBatch(util.train_inputs(gold, torch.float32), dev)
+    for p in net.parameters():
+        p.grad = None
+    out = net(batch)
+    _, loss_vals = net.backward(batch, out)
+    torch.cuda.synchronize()
+    live = util.valid_frame_mask(gold['seq_lengths'], batch.seq_length)
+    pose = torch.cat([out['root_ori_hat'], out['pose_hat']], dim=-1).cpu().numpy()
+    want_pose = torch.cat([want['root_ori_hat'], want['pose_hat']], dim=-1).numpy()
+    rad = util.max_joint_angle_err(pose[live], want_pose[live])
+    loss_err = max(abs(loss_vals[k] - want['loss_vals'][k]) / max(1.0, abs(want['loss_vals'][k])) for k in loss_vals)
+    items = dict(net.named_parameters())
+    rels, dot, n_got, n_want = [], 0.0, 0.0, 0.0
+    for key, g_want in want['grads'].items():
+        g = items[key].grad.detach().cpu().double().reshape(-1).numpy()
+        w = g_want.reshape(-1).numpy()
+        rels.append(float(np.sqrt(((g - w) ** 2).sum())) / (float(np.sqrt((w * w).sum())) + 1e-5 * np.sqrt(w.size)))
+        dot += float((g * w).sum()); n_got += float((g * g).sum()); n_want += float((w * w).sum())
+    cosine, median = dot / np.sqrt(n_got * n_want), float(np.median(rels))
+    util.report('train_step_skip', case=name, rad=rad, loss_err=loss_err, median_grad_rel=median, cosine=cosine)
+    assert np.isfinite(rad) and rad <= FWD_RAD[precision] * 5, rad
+    assert loss_err <= LOSS_TOL[precision], loss_err
+    assert median <= GRAD_MEDIAN[precision] and cosine >= GRAD_COS[precision], (median, cosine)
+
+
 def test_optimizer_step_and_eval_after_training(dev, smpl_npz):
     """scripts/train.py:125-152 shape: Adam on net.parameters(), zero_grad / forward / backward / step; then the eval
     path must see the updated weights and running statistics."""
