@@ -3,16 +3,21 @@
 // One persistent, warp-specialised kernel executes lists of GemmJob (gemm_jobs.h) on 128-row tiles:
 //
 //   warp 0   TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of A [128 x 128 B] and W [n x 128 B] K chunks (32 fp32 /
-//                           tf32 or 64 fp16 elements) into a shared-memory ring (4 slots of 48 KB, or 6 of 32 KB in CTA-pair
+//                           tf32 or 64 fp16 elements) into a shared-memory ring (3 slots of 48 KB, or 5 of 32 KB in CTA-pair
 //                           mode), completion on mbarriers
 //   warp 1   MMA issuer     tcgen05.mma kind::f16 / kind::tf32 (M=128 per CTA, N<=256, 32 bytes of K per instruction),
 //                           accumulating in TMEM; tcgen05.commit releases ring slots and publishes accumulators.  In the
 //                           default mode pairs of CTAs form ONE cta_group::2 MMA (M=256), issued by CTA 0 of the pair.
 //                           Both roles run their loops on the whole warp with uniform values; an elect.sync lane issues.
 //   warp 2   TMEM allocator 512 columns = two 128x256 fp32 accumulators (double buffered across jobs)
-//   warps 4-11 epilogue     tcgen05.ld 32 columns at a time -> epilogue_chunk() / linear_half_chunk() -> global memory
-//                           (two warps per TMEM lane quadrant, each taking 128 of the 256 columns); works on a
-//                           shared-memory copy of the job record, fetched one job ahead
+//   warp 3   job stager     copies the record and the bias of the NEXT job into one of two shared-memory slots (mbarriers
+//                           job_full / job_empty), so the epilogue never reads job fields or biases from global memory
+//   warps 4-11 epilogue     two warps per TMEM lane quadrant, each taking 128 of the 256 columns, every warp on its own: it
+//                           waits for the job slot and the accumulator, reads 64 columns per tcgen05.ld (two reads software
+//                           pipelined), and its output leaves through TMA stores from two private 4 KB staging tiles (fp16
+//                           and fp32 linear jobs; LSTM jobs: the cell-state block comes and goes by TMA, the hidden state
+//                           goes by TMA); it hands the accumulator back itself (tmem_empty counts the warps) and publishes
+//                           what later jobs wait for.  EMPOSE_TC_TRACE writes a per-job timeline of the three roles.
 //
 // A work item is (row tile, group of consecutive jobs).  Jobs of one item run back to back in the
 // same CTA; a job may depend on an earlier job of its item (an MLP layer reading the previous layer's
@@ -938,24 +943,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                             hp[8 * hf + i] = *reinterpret_cast<const uint32_t*>(&hh);
                         }
                     }
-                    if (in_rows && !(debug_mode & 16)) {
-                        if (!live) {       // the sequence has ended: the state is carried (packed-sequence semantics); c stays as it is in the tile
-                            const uint4* hprev = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(job.h_prev) + (int64_t)row * job.h_prev_stride + unit0);
+                    const bool h_tma = job.out_map1 > 0 && !(debug_mode & 65536);
+                    if (in_rows && !live && !(debug_mode & 16)) {       // the sequence has ended: the state is carried (packed-sequence semantics); c stays as it is in the tile
+                        const uint4* hprev = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(job.h_prev) + (int64_t)row * job.h_prev_stride + unit0);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint4 t = __ldcg(hprev + q);
-                                hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
-                            }
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 t = __ldcg(hprev + q);
+                            hp[4 * q] = t.x; hp[4 * q + 1] = t.y; hp[4 * q + 2] = t.z; hp[4 * q + 3] = t.w;
                         }
+                    }
+                    if (h_tma) {
+                        // the new hidden states leave by TMA as well ([32 rows x 64 B] in the warp's second staging tile, 64-byte
+                        // swizzle): nothing of this job is stored from registers, so its publication needs no proxy fence
+                        const uint32_t htile = tile + (uint32_t)(kStageFloats * 4);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            sts128(htile + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+                    } else if (in_rows && !(debug_mode & 16)) {
                         uint4* hout = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(job.out) + (int64_t)row * job.out_stride + unit0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) hout[q] = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
                     }
-                    generic_stores = true;
+                    if (!h_tma) generic_stores = true;
                     fence_async_shared();
                     __syncwarp();
                     if (lane == 0 && !(debug_mode & 16)) {
                         tma_store_2d(&maps[job.c_map1 - 1], tile, unit0, row0);
+                        if (h_tma) tma_store_2d(&maps[job.out_map1 - 1], tile + (uint32_t)(kStageFloats * 4), unit0, row0);
                         bulk_commit();
                     }
                     tma_pending = true;
@@ -1162,11 +1176,13 @@ int tc_encode_map(void* out_map, const float* base, int64_t row_stride_elems, in
     }
     cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)row_stride_floats * elem};
-    cuuint32_t box[2] = {(cuuint32_t)(half ? kChunkKHalf : kChunkK), (cuuint32_t)box_rows};
+    // half == 2: fp16 elements in boxes of 32 (64 bytes, 64-byte swizzle): the hidden-state block of an LSTM epilogue warp
+    cuuint32_t box[2] = {(cuuint32_t)(half == 2 ? 32 : half ? kChunkKHalf : kChunkK), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                     const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    half == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
         return EMPOSE_E_CUDA;

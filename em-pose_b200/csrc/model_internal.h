@@ -297,6 +297,11 @@ struct JobBook {        // jobs + tensor maps of one plan
         int idx = -1;
         EMPOSE_TRY(get_map(j.c_state, j.hidden, j.hidden, j.m_rows, 32, 0, &idx));
         j.c_map1 = idx + 1;
+        // ... and of this step's hidden states [m_rows][hidden] fp16 (boxes of 32 rows x 32 units, 64-byte swizzle) in out_map1
+        if (j.out && !(reinterpret_cast<uintptr_t>(j.out) & 15) && !((j.out_stride * 2) & 15) && !(j.hidden & 31)) {
+            EMPOSE_TRY(get_map(j.out, j.out_stride, j.hidden, j.m_rows, 32, 2, &idx));
+            j.out_map1 = idx + 1;
+        }
         return EMPOSE_OK;
     }
 
