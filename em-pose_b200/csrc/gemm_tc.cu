@@ -75,6 +75,7 @@ struct __align__(8) Control {
     uint64_t c_bar[kEpiWarps];        // per epilogue warp: its cell-state block has arrived in its staging tile (LSTM jobs)
     volatile uint32_t done_seq[kEpiWarps];   // per epilogue warp: 1 + sequence number of the last job whose stores it has handed to the TMA
     uint32_t job_done_cnt[4];         // per job (sequence number & 3): epilogue warps that have published their part (cross-CTA jobs)
+    volatile uint32_t dep_seq;        // 1 + sequence number of the last job whose cross-CTA counters the producer warp has seen satisfied
 };
 
 constexpr int kEpiTiles = 2;                                     // staging tiles per epilogue warp: TMA stores alternate between them
@@ -554,6 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         for (int w = 0; w < kEpiWarps; ++w) mbar_init(&ctl->c_bar[w], 1);
         for (int w = 0; w < kEpiWarps; ++w) ctl->done_seq[w] = 0;
         for (int q = 0; q < 4; ++q) ctl->job_done_cnt[q] = 0;
+        ctl->dep_seq = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -609,6 +611,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         // order the TMA reads (async proxy) after what the acquire made visible
                         if (m0 < m_tiles * kTileM)
                             wait_counters2(job.wait_ctr[0], job.wait_need[0] * epoch, job.wait_ctr[1], job.wait_need[1] * epoch, m0 / kTileM);
+                        // the epilogue warps need the same counters (they read the recurrent state): they wait for this word in
+                        // shared memory instead of polling the counters themselves -- an L2 round trip per job and warp
+                        __threadfence_block();
+                        if (lane == 0) ctl->dep_seq = pseq + 1u;
                         asm volatile("fence.proxy.async;" ::: "memory");
                         __syncwarp();
                     }
@@ -830,8 +836,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     // Wavefront jobs: the recurrent state this epilogue reads (cell state, carried hidden state) is written by
                     // other CTAs of this launch -- wait for them here too (the MMAs cannot start earlier either).  Both
                     // counters are polled at once (an acquire load is an L2 round trip).
-                    if ((job.wait_ctr[0] || job.wait_ctr[1]) && m0 < m_tiles * kTileM)
-                        wait_counters2(job.wait_ctr[0], job.wait_need[0] * epoch, job.wait_ctr[1], job.wait_need[1] * epoch, m0 / kTileM);
+                    if (job.wait_ctr[0] || job.wait_ctr[1]) {
+                        uint32_t spins = 0;
+                        while ((int32_t)(ctl->dep_seq - (seq + 1u)) < 0) {
+                            if (++spins > (1u << 28)) __trap();
+                        }
+                        __threadfence_block();
+                    }
                 }
                 // The fast LSTM epilogue (a full 256-column tile: this warp owns 128 gate columns = 32 hidden units of its 32 rows):
                 // the warp's [32 rows x 32 units] fp32 cell-state block comes by TMA straight into its staging tile (128-byte
