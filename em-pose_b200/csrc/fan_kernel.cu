@@ -57,8 +57,10 @@ __global__ void __launch_bounds__((FanCfg<SLOTS, MAXD, G>::kThreads), CTAS) fan_
     const int64_t row0 = (int64_t)blockIdx.x * G;
     const int nf = (int)min((int64_t)G, (int64_t)p.R - row0);
     const int fs = tid / kSensors, s = tid - fs * kSensors;          // this lane's (frame, sensor) item
-    const bool item = tid < kSensors * nf;
     const bool grad = p.want_grad != 0;
+    // nobody asked for the sensors (the final evaluation of a pass without marker histories): joints only -- the (frame, sensor)
+    // items, and with them the ring / offset / measurement loads, are skipped
+    const bool item = tid < kSensors * nf && (grad || p.sensor_pos != nullptr || p.sensor_ori != nullptr);
 
     // ---- P0: inputs.  The lane's ring, offsets and measurement go straight to registers; their latency hides behind
     // ---- the joint phases.

@@ -579,9 +579,21 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
         if (hist && hist->pose) up.hist_pose = hist->pose + (size_t)it * R * kPoseDim;
         if (hist && hist->shape) up.hist_shape = hist->shape + (size_t)it * R * kBetas;
         EMPOSE_TRY(count(launch_update(up, s)));
-        EMPOSE_TRY(run_jobs(ctx, pl, pl.pb, mt_R, s));
-
         const bool grad = (it < N) && cfg.use_gradient;
+        // The final evaluation (models.py:593-609) only has to deliver the joints unless the caller keeps the marker
+        // histories: the rest joints are the last columns of the blend GEMM (its last column tile), and the sub-model kernel
+        // stops after the kinematic chain -- no ring skinning, no sensor frames.
+        const bool joints_only = !grad && !(hist && (hist->markers || hist->markers_ori)) && ctx->fan.ok && !debug_options().main_general &&
+                                 pl.pb.per_item == 1 && pl.pb.count > 1 && ctx->sub.vp_dim >= (pl.pb.count - 1) * kMaxTileN;
+        if (joints_only) {
+            JobRange last = pl.pb;
+            last.begin += last.count - 1;
+            last.count = 1;
+            EMPOSE_TRY(run_jobs(ctx, pl, last, mt_R, s));
+        } else {
+            EMPOSE_TRY(run_jobs(ctx, pl, pl.pb, mt_R, s));
+        }
+
         MainParams mp;
         memset(&mp, 0, sizeof(mp));
         mp.sub = ctx->sub; mp.fan = ctx->fan; mp.spec = ctx->spec;
