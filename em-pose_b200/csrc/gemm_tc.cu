@@ -288,6 +288,9 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(crd0), "r"(crd1), "l"(policy)
                  : "memory");
 }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }     // sources may be overwritten
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }     // ... all but the latest store's
@@ -590,10 +593,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 const int m0 = (kCluster == 2 ? 2 * item_unit(item) + (int)crank : item_unit(item)) * kTileM;
                 for (int jj = 0; jj < jobs_per_item; ++jj) {
                     const ProducerView job = nxt;
+                    bool has_nxt = false;
                     {
                         const int nj = jj + 1 < jobs_per_item ? jj + 1 : 0;
                         const int ni = nj ? item : item + item_step;
-                        if (ni < n_items) nxt = producer_view(jobs[job_index(ni, nj)]);
+                        has_nxt = ni < n_items;
+                        if (has_nxt) nxt = producer_view(jobs[job_index(ni, nj)]);
                     }
                     if (lane == 0) trace_stamp(trace, 0, pseq, 0);
                     if (job.dep >= 0) {
@@ -628,6 +633,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         const int a_row = job.a_scratch[seg] ? (int)blockIdx.x * kTileM : m0;
                         const int w_k0 = job.w_koff[seg];
                         for (int kc = 0; kc < chunks; ++kc) {
+                            // The NEXT job's tensor maps into the TMA unit's descriptor cache while this job's chunks stream: a
+                            // job's first load otherwise starts with a descriptor fetch from L2 (every job of a chain names
+                            // other maps; the timeline showed ~1200 cycles until a job's first operands arrived).
+                            if (seg == 0 && kc == 1 && has_nxt && !(debug_mode & 131072)) {
+                                if (elect_one()) {
+                                    prefetch_tensormap(&maps[nxt.a_map[0]]);
+                                    if (nxt.a_k[1] > 0) prefetch_tensormap(&maps[nxt.a_map[1]]);
+                                    prefetch_tensormap(&maps[kPair || kCluster == 2 ? nxt.w_map2 : nxt.w_map]);
+                                }
+                                __syncwarp();
+                            }
                             if (kCluster == 2) mbar_wait_guarded(&ctl->empty[stage], phase ^ 1u);
                             else mbar_wait(&ctl->empty[stage], phase ^ 1u);
                             uint8_t* a_dst = smem + stage * kSlotBytes;
@@ -748,6 +764,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 for (int q = 0; q < 3; ++q) w[q] = lane + 32 * q < kJobWords ? reinterpret_cast<const uint32_t*>(src)[lane + 32 * q] : 0u;
                 const float* bias = src->bias;
                 const int n_begin = src->n_begin, n4 = src->n_count >> 2;
+                if (lane == 0 && !(debug_mode & 131072)) {      // the tensor maps the epilogue of that job will store (and load) through
+                    const int m0i = src->out_map1, m1i = src->out2_map1, m2i = src->c_map1;
+                    if (m0i > 0) prefetch_tensormap(&maps[m0i - 1]);
+                    if (m1i > 0) prefetch_tensormap(&maps[m1i - 1]);
+                    if (m2i > 0) prefetch_tensormap(&maps[m2i - 1]);
+                }
                 float4 bv[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
