@@ -75,6 +75,7 @@ struct __align__(8) Control {
     uint64_t c_bar[kEpiWarps];        // per epilogue warp: its cell-state block has arrived in its staging tile (LSTM jobs)
     volatile uint32_t done_seq[kEpiWarps];   // per epilogue warp: 1 + sequence number of the last job whose stores it has handed to the TMA
     uint32_t job_done_cnt[4];         // per job (sequence number & 3): epilogue warps that have published their part (cross-CTA jobs)
+    int32_t job_unit[2];              // item-table launches: the row-tile unit of the job in slot b (written by the stager warp)
     volatile uint32_t dep_seq;        // 1 + sequence number of the last job whose cross-CTA counters the producer warp has seen satisfied
 };
 
@@ -120,11 +121,11 @@ __device__ __forceinline__ IssuerView issuer_view(const GemmJob& j) {
 }
 
 // ---- timeline trace (EMPOSE_TC_TRACE=<file>): clock64 stamps of the three roles per job, first CTAs / jobs of a launch ----
-constexpr int kTraceCtas = 4, kTraceJobs = 96, kTraceStamps = 4;
+constexpr int kTraceCtas = 4, kTraceJobs = 96, kTraceStamps = 4, kTraceRoles = 4;       // role 3: the epilogue warp's job start in detail
 __device__ unsigned long long* g_trace_buf = nullptr;       // [cta][role 0 producer, 1 issuer, 2 epilogue warp 4][job][stamp]
 // `t` = g_trace_buf read ONCE per role (a stamp must not wait for a load: after a fence that is an L2 round trip)
 __device__ __forceinline__ void trace_stamp(unsigned long long* t, int role, uint32_t seq, int k) {
-    if (t && seq < kTraceJobs) t[((blockIdx.x * 3 + role) * kTraceJobs + seq) * kTraceStamps + k] = clock64();
+    if (t && seq < kTraceJobs) t[((blockIdx.x * kTraceRoles + role) * kTraceJobs + seq) * kTraceStamps + k] = clock64();
 }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -295,6 +296,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }     // sources may be overwritten
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }     // ... all but the latest store's
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }           // the writes are complete
+// orders this thread's async-proxy accesses to GLOBAL memory behind what it has acquired (the recurrent state another CTA wrote
+// through its TMA); bit 262144 of the debug mask brings the all-spaces fence back for comparison
+__device__ __forceinline__ void fence_async_global(int debug_mode) {
+    if (debug_mode & 262144) asm volatile("fence.proxy.async;" ::: "memory");
+    else asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -620,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         // shared memory instead of polling the counters themselves -- an L2 round trip per job and warp
                         __threadfence_block();
                         if (lane == 0) ctl->dep_seq = pseq + 1u;
-                        asm volatile("fence.proxy.async;" ::: "memory");
+                        fence_async_global(debug_mode);
                         __syncwarp();
                     }
                     if (lane == 0) trace_stamp(trace, 0, pseq, 1);
@@ -775,11 +782,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 for (int q = 0; q < 2; ++q)
                     bv[q] = (bias && lane + 32 * q < n4) ? __ldg(reinterpret_cast<const float4*>(bias + n_begin) + lane + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 mbar_wait(&ctl->job_empty[b], ((seq >> 1) & 1u) ^ 1u);
+                const int item_unit_next = items ? items[item].y : 0;       // item-table launches: the row-tile unit goes along
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     if (lane + 32 * q < kJobWords) reinterpret_cast<uint32_t*>(&job_slot(b))[lane + 32 * q] = w[q];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) reinterpret_cast<float4*>(bias_s + b * kMaxTileN)[lane + 32 * q] = bv[q];
+                if (lane == 0) ctl->job_unit[b] = item_unit_next;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->job_full[b]);
             }
@@ -826,11 +835,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
         };
         const int et = (int)threadIdx.x - 4 * 32;
         for (int item = item0; item < n_items; item += item_step) {
-            const int m0 = (kCluster == 2 ? 2 * item_unit(item) + (int)crank : item_unit(item)) * kTileM;
+            const int unit_direct = items ? 0 : item / groups;
             for (int jj = 0; jj < jobs_per_item; ++jj, ++seq) {
                 const uint32_t buf = seq & 1u;
+                if (et == 0) trace_stamp(trace, 3, seq, 0);
                 mbar_wait(&ctl->job_full[buf], (seq >> 1) & 1u);
+                if (et == 0) trace_stamp(trace, 3, seq, 1);
                 const GemmJob& job = job_slot(buf);
+                // item-table launches: the stager warp left the item's row-tile unit in the slot (a lookup in the table here was
+                // an L2 round trip per job on the epilogue's serial path)
+                const int unit = items ? ctl->job_unit[buf] : unit_direct;
+                const int m0 = (kCluster == 2 ? 2 * unit + (int)crank : unit) * kTileM;
                 const uint32_t bias_sa = smem_u32(bias_s + buf * kMaxTileN);
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kMaxTileN;
                 // The commonest job -- an fp16 linear layer on a full tile, out through TMA stores -- is summarised in the first
@@ -869,6 +884,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 // The fast LSTM epilogue (a full 256-column tile: this warp owns 128 gate columns = 32 hidden units of its 32 rows):
                 // the warp's [32 rows x 32 units] fp32 cell-state block comes by TMA straight into its staging tile (128-byte
                 // swizzle, conflict-free per-row reads) while the MMAs are still running, is updated in place and leaves by TMA.
+                if (et == 0) trace_stamp(trace, 3, seq, 2);      // job fields read, cross-CTA dependencies met
                 const bool lstm_fast = lstm_pre && job.c_map1 > 0 && c_end - c_begin == 128 && !job.gates_out && !(debug_mode & 4096);      // (false for fast_linear)
                 float* my_stage = epi_stage + ew * (kEpiTiles * kStageFloats);
                 float4 cpre[4];
@@ -878,7 +894,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     if (lane == 0) {
                         // (the block was written by another CTA of this launch through ITS TMA; the counter wait above was the
                         //  acquire, this orders the async-proxy read behind it)
-                        asm volatile("fence.proxy.async;" ::: "memory");
+                        fence_async_global(debug_mode);
                         mbar_arrive_expect_tx(&ctl->c_bar[ew], 32u * 128u);
                         tma_load_2d(my_stage, &maps[job.c_map1 - 1], &ctl->c_bar[ew], lstm_unit_of_packed(job.n_begin + c_begin), row0);
                     }
@@ -886,6 +902,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                 } else if (lstm_pre && c_begin < c_end) {
                     lstm_half_load_c(job, row0, lane, c_begin, cpre);
                 }
+                if (et == 0) trace_stamp(trace, 3, seq, 3);      // recurrent state requested (LSTM jobs)
                 // fp16 linear jobs: all fields the chunk loop needs, once per job
                 LinearHalfView lv;
                 bool f32_tma = false;
@@ -1231,7 +1248,7 @@ static int g_cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
 static int g_debug_mode = 0;
 static unsigned long long* g_trace_dev = nullptr;      // EMPOSE_TC_TRACE: the stamps of the LAST launch are written to that file
 static const char* g_trace_path = nullptr;
-constexpr size_t kTraceWords = (size_t)kTraceCtas * 3 * kTraceJobs * kTraceStamps;
+constexpr size_t kTraceWords = (size_t)kTraceCtas * kTraceRoles * kTraceJobs * kTraceStamps;
 
 static int g_trace_kind = 0;            // EMPOSE_TC_TRACE_KIND: 0 any launch, 1 item-table launches (LSTM wavefront), 2 chained items (MLP chains)
 static bool tc_trace_wanted(int kind) { return g_trace_dev && (g_trace_kind == 0 || g_trace_kind == kind); }
@@ -1246,9 +1263,9 @@ static void tc_trace_end(cudaStream_t s, int kind) {
     FILE* f = fopen(g_trace_path, "w");
     if (!f) return;
     for (int c = 0; c < kTraceCtas; ++c)
-        for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < kTraceRoles; ++r)
             for (int j = 0; j < kTraceJobs; ++j) {
-                const unsigned long long* t = &h[(((size_t)c * 3 + r) * kTraceJobs + j) * kTraceStamps];
+                const unsigned long long* t = &h[(((size_t)c * kTraceRoles + r) * kTraceJobs + j) * kTraceStamps];
                 if (t[0] | t[1] | t[2] | t[3]) fprintf(f, "%d %d %d %llu %llu %llu %llu\n", c, r, j, t[0], t[1], t[2], t[3]);
             }
     fclose(f);

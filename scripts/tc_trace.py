@@ -24,6 +24,9 @@ for j in jobs:
     p = d.get((0, j), [0] * 4); m = d.get((1, j), [0] * 4); e = d.get((2, j), [0] * 4)
     f = lambda v: '/'.join('%7d' % (x - t0) if x else '      -' for x in v)
     print('%4d | %s | %s | %s' % (j, f(p[:3]), f(m), f(e)))
+    s4 = d.get((3, j))
+    if s4:
+        print('     |   epilogue job start: before job_full %d, +%d job slot ready, +%d fields / dependencies, +%d state requested' % (s4[0] - t0, s4[1] - s4[0], s4[2] - s4[1], s4[3] - s4[2]))
     if m[3] and e[3]:
         per.append((j, m[1] - m[0], m[3] - m[1], e[1] - e[0], e[2] - e[1], e[3] - e[2]))
 if per:
