@@ -1243,8 +1243,11 @@ int tc_encode_map(void* out_map, const float* base, int64_t row_stride_elems, in
 // Executor configuration, once per process (one process per GPU).
 static int g_max_clusters = 0;          // co-resident 2-CTA clusters (0: cluster modes unavailable or disabled)
 static int g_cluster_mode = 0;          // 2: W multicast, 3: CTA-pair MMA
-// EMPOSE_TC_DEBUG bits (throughput experiments; results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math,
-// 8 no fences, 16 no fp16 stores, 32 no TMEM reads, 64 device-scope fence per job, 128 no cell-state prefetch, 256 CTA-pair mode with a 4-slot ring, 512 fence after every job
+// EMPOSE_TC_DEBUG bits.  Throughput experiments (results are garbage): 1 TMA only, 2 MMA only, 4 no epilogue math, 8 no
+// publication, 16 no stores, 32 no TMEM reads.  A/B switches (results stay correct): 128 no cell-state prefetch (and with it the
+// chunk-wise LSTM epilogue), 256 CTA-pair mode with a 3-slot ring, 1024 32-column chunks only, 2048 stores from registers instead
+// of TMA stores, 4096 chunk-wise LSTM epilogue, 8192 no L2 hints, 16384 no one-load job summary, 32768 accumulator reads not
+// pipelined, 65536 LSTM hidden state stored from registers, 131072 no tensor-map prefetch, 262144 all-spaces proxy fences
 static int g_debug_mode = 0;
 static unsigned long long* g_trace_dev = nullptr;      // EMPOSE_TC_TRACE: the stamps of the LAST launch are written to that file
 static const char* g_trace_path = nullptr;
