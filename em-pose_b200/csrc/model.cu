@@ -157,8 +157,13 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
     // Hidden activations of the MLP chains: in TF32 mode a CTA chains all layers of a 128-row tile, so the buffers
     // are CTA-local scratch (num_sms tiles, L2-resident); the FFMA executor runs layer by layer over all rows.
     pl.act_rows = ctx->round ? (int64_t)ctx->num_sms * kTileM : (int64_t)R;
-    for (int c = 0; c < 2; ++c)
-        for (int q = 0; q < 2; ++q) EMPOSE_TRY(alloc_operand((size_t)pl.act_rows * hidden, &pl.act[c][q]));
+    {
+        const size_t one = ((size_t)pl.act_rows * hidden * esz + 1023) / 1024 * 1024;
+        pl.act_block_bytes = 4 * one;
+        EMPOSE_TRY(A.alloc(pl.act_block_bytes, &pl.act_block, true));
+        for (int c = 0; c < 2; ++c)
+            for (int q = 0; q < 2; ++q) pl.act[c][q] = reinterpret_cast<float*>(static_cast<char*>(pl.act_block) + (size_t)(2 * c + q) * one);
+    }
 
     const int m_rows_R = R;
     if (cfg.rnn_init) {
@@ -646,7 +651,36 @@ int forward_device(empose_ief* ctx, Plan& pl, const float* marker_pos, const flo
             po.R = R; po.operand_mode = ctx->op_mode; po.xiter = pl.xiter; po.in_size = ctx->in_size; po.iter_stride = ctx->iter_stride;
             EMPOSE_TRY(count(launch_post(po, s)));
         }
+        // EMPOSE_L2_PERSIST=1 (experiment): the chained scratch activations as a persisting L2 access-policy window
+        static const bool l2_persist = getenv("EMPOSE_L2_PERSIST") != nullptr;
+        if (l2_persist && ctx->round) {
+            static bool limit_set = false;
+            if (!limit_set) {
+                cudaDeviceProp prop;
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaGetDeviceProperties(&prop, dev);
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
+                fprintf(stderr, "empose_b200: persisting L2 max %d MB, window max %d MB, scratch %zu MB\n", prop.persistingL2CacheMaxSize >> 20,
+                        prop.accessPolicyMaxWindowSize >> 20, pl.act_block_bytes >> 20);
+                limit_set = true;
+            }
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = pl.act_block;
+            attr.accessPolicyWindow.num_bytes = pl.act_block_bytes;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            EMPOSE_CUDA_TRY(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+        }
         EMPOSE_TRY(run_jobs(ctx, pl, pl.iter_chain, mt_R, s));
+        if (l2_persist && ctx->round) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.num_bytes = 0;
+            EMPOSE_CUDA_TRY(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+        }
     }
     if (pose_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(pose_hat, pl.theta, (size_t)R * kPoseDim * 4, cudaMemcpyDeviceToDevice, s));
     if (shape_hat) EMPOSE_CUDA_TRY(cudaMemcpyAsync(shape_hat, pl.beta, (size_t)R * kBetas * 4, cudaMemcpyDeviceToDevice, s));

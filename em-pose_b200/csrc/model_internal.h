@@ -408,6 +408,8 @@ struct Plan {
     int32_t* seq_len = nullptr;
     float* act[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pose|shape][ping-pong]
     int64_t act_rows = 0;
+    void* act_block = nullptr;     // the four activation buffers are one allocation (an L2 access-policy window can cover them)
+    size_t act_block_bytes = 0;
     std::vector<float*> hseq, cstate, hinit;
     // staging for the host-buffer entry point
     float *in_pos = nullptr, *in_ori = nullptr, *in_masks = nullptr, *io_state = nullptr;
