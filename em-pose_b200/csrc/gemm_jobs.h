@@ -80,7 +80,7 @@ struct GemmJob {
     // contribute only the bias (the LSTM output of a padded frame is zero, layers.py:153)
     const int32_t* seq_len;
     int32_t frames_per_window;
-    int32_t mask_rows;
+    int32_t mask_rows;       // number of logical rows when rows are masked by sequence length (0: no masking)
     // ---- LSTM ----
     float* c_state;          // [M][H] cell state, updated in place
     const float* h_prev;     // carry source for frozen rows (row stride h_prev_stride)
@@ -151,7 +151,8 @@ struct LinearHalfView {
     int32_t out_map;         // tensor-map slot for TMA stores of [32 rows x 64 columns] blocks, -1: none
     int32_t out_col;         // column of the job's column 0 in that map
 };
-__device__ __forceinline__ LinearHalfView linear_half_view(const GemmJob& j, int row0, int lane) {
+// `row0`: first OUTPUT row of the warp (a CTA-local scratch row for out_scratch jobs), `mask_row0`: its first LOGICAL row
+__device__ __forceinline__ LinearHalfView linear_half_view(const GemmJob& j, int row0, int lane, int mask_row0) {
     LinearHalfView lv;
     const bool ok = j.epi == EPI_LINEAR && j.out_half && !j.res && (j.out_scale == 0.0f || j.out_scale == 1.0f);
     const int n_begin = j.n_begin;
@@ -163,9 +164,9 @@ __device__ __forceinline__ LinearHalfView linear_half_view(const GemmJob& j, int
     lv.m_rows = j.m_rows;
     lv.out_map = ok ? j.out_map1 - 1 : -1;
     lv.out_col = j.out_col0 + n_begin;
-    const int row = row0 + lane;
+    const int row = mask_row0 + lane;
     lv.zero_row = false;
-    if (ok && j.mask_rows && row < lv.m_rows) {
+    if (ok && j.mask_rows && row < j.mask_rows) {
         const int fpw = j.frames_per_window;
         lv.zero_row = (row % fpw) >= j.seq_len[row / fpw];
     }
@@ -312,9 +313,10 @@ __device__ __forceinline__ void lstm_half_load_c(const GemmJob& j, int row0, int
 // `bias_sa` != 0: shared-memory address of a copy of the job's bias (columns relative to the job; tcgen05 executor)
 __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int lane, int c0, float (&v)[32],
                                                float* __restrict__ stage, bool no_store = false, const float4* cpre = nullptr,
-                                               uint32_t bias_sa = 0) {
+                                               uint32_t bias_sa = 0, int mask_row0 = -1) {
     const int n0 = j.n_begin + c0;                 // global column of v[0]
     const int row = row0 + lane;
+    const int mrow = (mask_row0 >= 0 ? mask_row0 : row0) + lane;      // logical row (differs from `row` for CTA-local scratch outputs)
     float bias[32];
     if (bias_sa) {
 #pragma unroll
@@ -336,7 +338,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
     if (j.epi == EPI_LINEAR && j.out_half && !j.res && n0 + 32 <= j.n_valid && n0 + 32 <= j.split &&
         (j.out_scale == 0.0f || j.out_scale == 1.0f)) {
         // fp16 activations (the tcgen05 executor builds the view once per job and calls linear_half_chunk directly)
-        const LinearHalfView lv = linear_half_view(j, row0, lane);
+        const LinearHalfView lv = linear_half_view(j, row0, lane, mask_row0 >= 0 ? mask_row0 : row0);
         linear_half_chunk(lv, row0, lane, c0, v, bias, stage, no_store);
     } else if (j.epi == EPI_LSTM && j.out_half && (j.n_count % 64) == 0) {
         // (job fields into registers first: after any store the compiler has to assume the job record changed)
@@ -492,7 +494,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmJob& j, int row0, int l
             __syncwarp();
         }
     } else if (j.epi == EPI_LINEAR) {
-        if (j.mask_rows && row < j.m_rows && (row % j.frames_per_window) >= j.seq_len[row / j.frames_per_window]) {
+        if (j.mask_rows && mrow < j.mask_rows && (mrow % j.frames_per_window) >= j.seq_len[mrow / j.frames_per_window]) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.0f;
         }

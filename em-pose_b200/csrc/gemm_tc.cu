@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                     lv.alpha = __uint_as_float(hot.w); lv.fast_cols = kMaxTileN; lv.zero_row = false;
                     lv.out_map = (int32_t)hot.z; lv.out_col = (int32_t)hot.y;
                 } else {
-                    lv = linear_half_view(job, row0, lane);
+                    lv = linear_half_view(job, row0, lane, m0 + quad * 32);
                     f32_tma = job.epi == EPI_LINEAR && !job.out_half && (job.out_map1 > 0 || job.out2_map1 > 0);
                     f32_scale = job.out_scale != 0.0f ? job.out_scale : 1.0f;
                 }
@@ -1119,7 +1119,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmJob* __r
                         tmem_load_32cols(taddr + (uint32_t)c0, v);
                     }
                     if (!(debug_mode & 4))
-                        epilogue_chunk(job, row0, lane, c0, v, my_stage, (debug_mode & 16) != 0, lstm_pre ? cpre : nullptr, bias_sa);
+                        epilogue_chunk(job, row0, lane, c0, v, my_stage, (debug_mode & 16) != 0, lstm_pre ? cpre : nullptr, bias_sa, m0 + quad * 32);
                     generic_stores = true;
                     // ... and the next pair's while this pair is being computed
                     if (lstm_pre && !(c0 & 32) && c0 + 64 < c_end) lstm_half_load_c(job, row0, lane, c0 + 64, cpre);

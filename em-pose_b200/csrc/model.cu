@@ -228,7 +228,7 @@ int build_plan(empose_ief* ctx, int B, int F, Plan** out, int slot = 0) {
         proto.split = kPoseDim;
         proto.out2 = pl.dbeta;
         proto.out2_stride = kBetas;
-        proto.mask_rows = 1;
+        proto.mask_rows = R;                 // logical rows (the sequence lengths index windows of F of them)
         proto.seq_len = pl.seq_len;
         proto.frames_per_window = F;
         EMPOSE_TRY(pl.book.add(ctx->heads, ASrc{pl.hseq[L - 1], H, H, R, hf}, ASrc{}, proto, m_rows_R, -1, &pl.heads));

@@ -179,7 +179,7 @@ int build_plan(empose_rnn* ctx, int B, int F, RnnPlan** out) {
     // ---- to_pose: rows of padded frames see a zero LSTM output (pad_packed_sequence) -> bias only ----
     {
         GemmJob proto = linear_proto(ctx->to_pose, false, pl.pose, kPoseDim, kPoseDim);
-        proto.mask_rows = 1; proto.seq_len = pl.seq_len; proto.frames_per_window = F;
+        proto.mask_rows = R; proto.seq_len = pl.seq_len; proto.frames_per_window = F;
         EMPOSE_TRY(pl.book.add(ctx->to_pose, ASrc{pl.hseq[L - 1], W, W, R, hf}, ASrc{}, proto, R, -1, &pl.to_pose));
     }
     if (cfg.estimate_shape) {
@@ -205,7 +205,7 @@ int build_plan(empose_rnn* ctx, int B, int F, RnnPlan** out) {
                 proto.out_half = hf;
                 if (scratch) { proto.out_scratch = 1; m_rows = (int)pl.act_rows; }
             }
-            if (l == 0) { proto.mask_rows = 1; proto.seq_len = pl.seq_len; proto.frames_per_window = F; }
+            if (l == 0) { proto.mask_rows = R; proto.seq_len = pl.seq_len; proto.frames_per_window = F; }
             if (scratch && l > 0) proto.a_scratch[0] = 1;
             EMPOSE_TRY(pl.book.add(Wm, a0, ASrc{}, proto, m_rows, last, &pl.to_shape));
             last = pl.to_shape.count - 1;

@@ -544,7 +544,7 @@ int build_plan(empose_train* t, int B, int F, TrainPlan** out) {
             }
         GemmJob hp = plain_proto(pl.dtheta, kPoseDim, kPoseDim + kBetas, false);
         hp.split = kPoseDim; hp.out2 = pl.dbeta; hp.out2_stride = kBetas;
-        hp.mask_rows = 1; hp.seq_len = pl.seq_len; hp.frames_per_window = F;
+        hp.mask_rows = R; hp.seq_len = pl.seq_len; hp.frames_per_window = F;
         EMPOSE_TRY(pl.book.add(t->heads_fw, ASrc{pl.hseq[L - 1], H, H, R}, ASrc{}, hp, R, -1, &pl.heads));
         GemmJob hd = plain_proto(pl.dhead, H, H, false);
         EMPOSE_TRY(pl.book.add(t->heads_bw, ASrc{pl.d_init_masked, kInitLd, kInitBetaCol + kBetas, R}, ASrc{}, hd, R, -1, &pl.heads_dx));

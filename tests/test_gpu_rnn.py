@@ -133,3 +133,32 @@ def test_persistent_stream_with_state_carry_and_padding(dev, smpl_npz, oracle_sm
             assert net._ctx.last_launch_count < 40, 'the persistent path must not launch once per time step'
             assert rad <= 1e-4, rad
             assert h_err <= 2e-3 and c_err <= 5e-3, (h_err, c_err)
+
+
+def test_birnn_large_ragged_batch_equals_subsets(dev, smpl_npz):
+    """More 128-row tiles than SMs, ragged lengths, shape head with CTA-local scratch activations: the first layer of
+    ``to_shape`` masks padded frames (``pad_packed_sequence`` zeros, models.py:300-309) by LOGICAL row -- a CTA's later tiles
+    write their activations to the scratch rows of its first tile, which once also selected the sequence length.  Windows
+    are independent, so every window of the big batch must equal the same window run in a small batch (bit for bit)."""
+    flags = util.RNN_CASES['rnn_bi12_shape_fk']
+    flags = dict(cfg=dict(flags['cfg'], hidden_size=128), weights=dict(flags['weights'], hidden_size=128))
+    net = build_rnn(smpl_npz, flags, native.PRECISION_FP16, dev)
+    b, f = 1300, 16                                   # 20800 rows = 163 row tiles > 148 SMs
+    g = torch.Generator().manual_seed(5)
+    pos = 0.3 * torch.randn(b, f, 36, generator=g)
+    ori = (torch.eye(3).reshape(1, 1, 1, 9) + 0.05 * torch.randn(b, f, 12, 9, generator=g)).reshape(b, f, 108)
+    lens = torch.randint(1, f + 1, (b,), generator=g).to(torch.int32)
+    z = torch.zeros(b, 12, 3)
+    mk = lambda sl: util.DuckBatch(pos[sl], ori[sl], z[sl].unsqueeze(-1).repeat(1, 1, 1, 3), z[sl], lens[sl]).to(dev)
+    with torch.no_grad():
+        full = net(mk(slice(0, b)), is_new_sequence=True)
+        full = {k: full[k].clone() for k in ('pose_hat', 'shape_hat', 'joints_hat')}
+        worst = 0.0
+        for lo in (0, 640, 1240):                     # first tiles of a CTA, a later round, the tail
+            part = net(mk(slice(lo, lo + 60)), is_new_sequence=True)
+            live = torch.from_numpy(util.valid_frame_mask(lens[lo:lo + 60].numpy(), f)).to(dev)
+            for k in ('pose_hat', 'shape_hat', 'joints_hat'):
+                d = (full[k][lo:lo + 60] - part[k])[live].abs().max().item()
+                worst = max(worst, d)
+    util.report('birnn_large_ragged', worst_abs_diff=worst, rows=b * f)
+    assert worst == 0.0, worst
